@@ -1,0 +1,716 @@
+"""CPU oracle for the offline-RL update step.
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / ``--impl reference`` legs; the product path
+(d3rlpy_b200) never imports it and has no CPU fallback.
+
+A plain-PyTorch (fp32, autograd, ``torch.optim.Adam``) restatement of what one
+``algo.update(batch)`` of the reference computes, written functionally over
+dicts of tensors whose keys equal the reference modules' ``state_dict`` keys so
+weights can be exchanged with the reference and with the CUDA path.  Each
+function cites the reference lines it follows (relative to /root/reference/).
+
+Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
+the reference.  Pinned against the live reference by
+tests/golden/update_*.npz (tests/golden/make_golden.py) — see DESIGN.md §oracle.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------- noise
+class Noise:
+    """Noise source.  ``injected`` is a list of tensors replayed in draw order
+    (the order SURVEY.md §8c lists); otherwise fresh draws from ``generator``."""
+
+    def __init__(self, injected: Optional[List[torch.Tensor]] = None, seed: int = 0):
+        self.injected = list(injected) if injected is not None else None
+        self.gen = torch.Generator().manual_seed(seed)
+        self.log: List[torch.Tensor] = []
+
+    def _next(self, shape, kind):
+        if self.injected is not None:
+            t = self.injected.pop(0)
+            assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape), kind)
+            return t.clone()
+        if kind == "normal":
+            t = torch.randn(shape, generator=self.gen)
+        else:
+            t = torch.rand(shape, generator=self.gen) * 2.0 - 1.0
+        self.log.append(t.clone())
+        return t
+
+    def normal(self, *shape):
+        return self._next(shape, "normal")
+
+    def uniform(self, *shape):
+        return self._next(shape, "uniform")
+
+
+# --------------------------------------------------------------------------- parameter construction
+def _linear_init(out_f: int, in_f: int, gen: torch.Generator):
+    # nn.Linear default: kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(in), 1/sqrt(in)) for W and b
+    bound = 1.0 / math.sqrt(in_f)
+    w = (torch.rand(out_f, in_f, generator=gen) * 2 - 1) * bound
+    b = (torch.rand(out_f, generator=gen) * 2 - 1) * bound
+    return w, b
+
+
+def make_mlp(prefix: str, in_f: int, hidden: Sequence[int], gen) -> Params:
+    """``_VectorEncoder`` Linear stack (d3rlpy/models/torch/encoders.py:236-263)."""
+    p: Params = OrderedDict()
+    for i, h in enumerate(hidden):
+        w, b = _linear_init(h, in_f, gen)
+        p[f"{prefix}_fcs.{i}.weight"], p[f"{prefix}_fcs.{i}.bias"] = w, b
+        in_f = h
+    return p
+
+
+def make_head(prefix: str, out_f: int, in_f: int, gen) -> Params:
+    w, b = _linear_init(out_f, in_f, gen)
+    return OrderedDict([(f"{prefix}.weight", w), (f"{prefix}.bias", b)])
+
+
+def make_critics(obs: int, act: int, hidden, n: int, gen) -> Params:
+    """EnsembleContinuousQFunction of ContinuousMeanQFunction (builders.py:55-77)."""
+    p: Params = OrderedDict()
+    for i in range(n):
+        p.update(make_mlp(f"_q_funcs.{i}._encoder.", obs + act, hidden, gen))
+        p.update(make_head(f"_q_funcs.{i}._fc", 1, hidden[-1], gen))
+    return p
+
+
+def make_squashed_normal_policy(obs: int, act: int, hidden, gen) -> Params:
+    p = make_mlp("_encoder.", obs, hidden, gen)
+    p.update(make_head("_mu", act, hidden[-1], gen))
+    p.update(make_head("_logstd", act, hidden[-1], gen))
+    return p
+
+
+def make_deterministic_policy(obs: int, act: int, hidden, gen) -> Params:
+    p = make_mlp("_encoder.", obs, hidden, gen)
+    p.update(make_head("_fc", act, hidden[-1], gen))
+    return p
+
+
+def make_residual_policy(obs: int, act: int, hidden, gen) -> Params:
+    p = make_mlp("_encoder.", obs + act, hidden, gen)
+    p.update(make_head("_fc", act, hidden[-1], gen))
+    return p
+
+
+def make_cvae(obs: int, act: int, latent: int, hidden, gen) -> Params:
+    """ConditionalVAE (d3rlpy/models/torch/imitators.py:13-61); registration order
+    encoder_encoder, decoder_encoder, _mu, _logstd, _fc."""
+    p = make_mlp("_encoder_encoder.", obs + act, hidden, gen)
+    p.update(make_mlp("_decoder_encoder.", obs + latent, hidden, gen))
+    p.update(make_head("_mu", latent, hidden[-1], gen))
+    p.update(make_head("_logstd", latent, hidden[-1], gen))
+    p.update(make_head("_fc", act, hidden[-1], gen))
+    return p
+
+
+NATURE_FILTERS = [(32, 8, 4), (64, 4, 2), (64, 3, 1)]
+
+
+def conv_out_hw(h: int, w: int, filters=NATURE_FILTERS):
+    for _, k, s in filters:
+        h, w = (h - k) // s + 1, (w - k) // s + 1
+    return h, w
+
+
+def make_discrete_critics(obs_shape, act: int, n: int, gen, hidden=None, feature_size=512) -> Params:
+    """EnsembleDiscreteQFunction of DiscreteMeanQFunction over PixelEncoder
+    (encoders.py:43-162) or VectorEncoder."""
+    p: Params = OrderedDict()
+    for i in range(n):
+        pre = f"_q_funcs.{i}._encoder."
+        if len(obs_shape) == 3:
+            c = obs_shape[0]
+            for l, (oc, k, s) in enumerate(NATURE_FILTERS):
+                bound = 1.0 / math.sqrt(c * k * k)
+                p[f"{pre}_convs.{l}.weight"] = (torch.rand(oc, c, k, k, generator=gen) * 2 - 1) * bound
+                p[f"{pre}_convs.{l}.bias"] = (torch.rand(oc, generator=gen) * 2 - 1) * bound
+                c = oc
+            hh, ww = conv_out_hw(obs_shape[1], obs_shape[2])
+            w, b = _linear_init(feature_size, c * hh * ww, gen)
+            p[f"{pre}_fc.weight"], p[f"{pre}_fc.bias"] = w, b
+            feat = feature_size
+        else:
+            hidden = hidden or [256, 256]
+            p.update(make_mlp(pre, obs_shape[0], hidden, gen))
+            feat = hidden[-1]
+        p.update(make_head(f"_q_funcs.{i}._fc", act, feat, gen))
+    return p
+
+
+def clone_params(p: Params, requires_grad: bool = True) -> Params:
+    return OrderedDict((k, v.detach().clone().requires_grad_(requires_grad)) for k, v in p.items())
+
+
+# --------------------------------------------------------------------------- forward pieces
+def _n_layers(p: Params, prefix: str) -> int:
+    n = 0
+    while f"{prefix}_fcs.{n}.weight" in p:
+        n += 1
+    return n
+
+
+def mlp_forward(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """``_fc_encode`` with ReLU, no BN/dropout/dense (encoders.py:265-275)."""
+    h = x
+    for i in range(_n_layers(p, prefix)):
+        h = torch.relu(F.linear(h, p[f"{prefix}_fcs.{i}.weight"], p[f"{prefix}_fcs.{i}.bias"]))
+    return h
+
+
+def pixel_forward(p: Params, prefix: str, x: torch.Tensor) -> torch.Tensor:
+    """PixelEncoder.forward (encoders.py:106-140)."""
+    h = x
+    for l, (_, _, s) in enumerate(NATURE_FILTERS):
+        h = torch.relu(F.conv2d(h, p[f"{prefix}_convs.{l}.weight"], p[f"{prefix}_convs.{l}.bias"], stride=s))
+    return torch.relu(F.linear(h.reshape(h.shape[0], -1), p[f"{prefix}_fc.weight"], p[f"{prefix}_fc.bias"]))
+
+
+def n_members(p: Params) -> int:
+    n = 0
+    while f"_q_funcs.{n}._fc.weight" in p:
+        n += 1
+    return n
+
+
+def reduce_ensemble(y: torch.Tensor, reduction: str = "min", lam: float = 0.75) -> torch.Tensor:
+    """``_reduce_ensemble`` (q_functions/ensemble_q_function.py:9-24)."""
+    if reduction == "min":
+        return y.min(dim=0).values
+    if reduction == "max":
+        return y.max(dim=0).values
+    if reduction == "mean":
+        return y.mean(dim=0)
+    if reduction == "none":
+        return y
+    if reduction == "mix":
+        return lam * y.min(dim=0).values + (1.0 - lam) * y.max(dim=0).values
+    raise ValueError(reduction)
+
+
+def q_continuous(p: Params, x, action, reduction="mean", lam=0.75) -> torch.Tensor:
+    """EnsembleContinuousQFunction.forward (ensemble_q_function.py:163-170) over
+    ContinuousMeanQFunction.forward (mean_q_function.py:71-72) and
+    VectorEncoderWithAction.forward (encoders.py:328-339)."""
+    xa = torch.cat([x, action], dim=1)
+    vals = []
+    for i in range(n_members(p)):
+        h = mlp_forward(p, f"_q_funcs.{i}._encoder.", xa)
+        q = F.linear(h, p[f"_q_funcs.{i}._fc.weight"], p[f"_q_funcs.{i}._fc.bias"])
+        vals.append(q.view(1, x.shape[0], 1))
+    return reduce_ensemble(torch.cat(vals, dim=0), reduction, lam)
+
+
+def q_discrete(p: Params, x, reduction="mean") -> torch.Tensor:
+    """EnsembleDiscreteQFunction.forward (ensemble_q_function.py:139-146)."""
+    vals = []
+    for i in range(n_members(p)):
+        pre = f"_q_funcs.{i}._encoder."
+        h = pixel_forward(p, pre, x) if f"{pre}_convs.0.weight" in p else mlp_forward(p, pre, x)
+        q = F.linear(h, p[f"_q_funcs.{i}._fc.weight"], p[f"_q_funcs.{i}._fc.bias"])
+        vals.append(q.view(1, x.shape[0], -1))
+    return reduce_ensemble(torch.cat(vals, dim=0), reduction)
+
+
+def td_error_continuous(p: Params, obs, act, rew, target, term, gamma) -> torch.Tensor:
+    """EnsembleQFunction.compute_error (ensemble_q_function.py:81-106): sum over members of
+    per-member batch-mean MSE (mean_q_function.py:74-87)."""
+    assert target.ndim == 2
+    total = torch.tensor(0.0)
+    q = q_continuous(p, obs, act, "none")
+    y = rew + gamma * target * (1 - term)
+    for i in range(q.shape[0]):
+        total = total + F.mse_loss(q[i], y, reduction="none").mean()
+    return total
+
+
+def huber(y, target, beta=1.0):
+    """compute_huber_loss (q_functions/utility.py:27-32)."""
+    diff = target - y
+    cond = diff.detach().abs() < beta
+    return torch.where(cond, 0.5 * diff ** 2, beta * (diff.abs() - 0.5 * beta))
+
+
+def td_error_discrete(p: Params, obs, act_long, rew, target, term, gamma) -> torch.Tensor:
+    """DiscreteMeanQFunction.compute_error (mean_q_function.py:26-42), summed over members."""
+    q = q_discrete(p, obs, "none")
+    one_hot = F.one_hot(act_long.view(-1), num_classes=q.shape[2]).float()
+    y = rew + gamma * target * (1 - term)
+    total = torch.tensor(0.0)
+    for i in range(q.shape[0]):
+        value = (q[i] * one_hot).sum(dim=1, keepdim=True)
+        total = total + huber(value, y).mean()
+    return total
+
+
+LOG2 = math.log(2)
+
+
+def squashed_log_prob(mu, std, raw):
+    """SquashedGaussianDistribution._log_prob_from_raw_y (distributions.py:133-135)."""
+    normal_lp = -((raw - mu) ** 2) / (2 * std ** 2) - std.log() - math.log(math.sqrt(2 * math.pi))
+    jacob = 2 * (LOG2 - raw - F.softplus(-2 * raw))
+    return (normal_lp - jacob).sum(dim=-1, keepdim=True)
+
+
+def policy_dist(p: Params, x, min_logstd=-20.0, max_logstd=2.0):
+    """NormalPolicy.dist (policies.py:167-181): mu, std=exp(clamp(logstd))."""
+    h = mlp_forward(p, "_encoder.", x)
+    mu = F.linear(h, p["_mu.weight"], p["_mu.bias"])
+    logstd = F.linear(h, p["_logstd.weight"], p["_logstd.bias"]).clamp(min_logstd, max_logstd)
+    return mu, logstd.exp()
+
+
+def policy_sample_with_log_prob(p: Params, x, eps):
+    """sample_with_log_prob (policies.py:196-200; distributions.py:103-106); eps (B,A)."""
+    mu, std = policy_dist(p, x)
+    raw = mu + eps * std
+    return torch.tanh(raw), squashed_log_prob(mu, std, raw)
+
+
+def policy_sample_n_with_log_prob(p: Params, x, eps):
+    """sample_n_with_log_prob (policies.py:202-213; distributions.py:116-121); eps (N,B,A)
+    -> actions (B,N,A), log_probs (B,N,1)."""
+    mu, std = policy_dist(p, x)
+    raw = mu.unsqueeze(0) + eps * std.unsqueeze(0)
+    lp = squashed_log_prob(mu.unsqueeze(0), std.unsqueeze(0), raw)
+    return torch.tanh(raw).transpose(0, 1), lp.transpose(0, 1)
+
+
+def policy_best_action(p: Params, x):
+    """best_action -> mean_with_log_prob -> tanh(mu) (policies.py:247-249, distributions.py:126-127)."""
+    mu, _ = policy_dist(p, x)
+    return torch.tanh(mu)
+
+
+def deterministic_policy(p: Params, x):
+    """DeterministicPolicy.forward (policies.py:57-59)."""
+    return torch.tanh(F.linear(mlp_forward(p, "_encoder.", x), p["_fc.weight"], p["_fc.bias"]))
+
+
+def residual_policy(p: Params, x, action, scale):
+    """DeterministicResidualPolicy.forward (policies.py:94-97)."""
+    h = mlp_forward(p, "_encoder.", torch.cat([x, action], dim=1))
+    res = scale * torch.tanh(F.linear(h, p["_fc.weight"], p["_fc.bias"]))
+    return (action + res).clamp(-1.0, 1.0)
+
+
+def vae_decode(p: Params, x, latent):
+    """ConditionalVAE.decode (imitators.py:70-72)."""
+    h = mlp_forward(p, "_decoder_encoder.", torch.cat([x, latent], dim=1))
+    return torch.tanh(F.linear(h, p["_fc.weight"], p["_fc.bias"]))
+
+
+def vae_error(p: Params, x, action, eps, beta, min_logstd=-4.0, max_logstd=15.0):
+    """ConditionalVAE.compute_error (imitators.py:80-86); eps (B,latent)."""
+    h = mlp_forward(p, "_encoder_encoder.", torch.cat([x, action], dim=1))
+    mu = F.linear(h, p["_mu.weight"], p["_mu.bias"])
+    logstd = F.linear(h, p["_logstd.weight"], p["_logstd.bias"]).clamp(min_logstd, max_logstd)
+    std = logstd.exp()
+    # kl_divergence(Normal(mu,std), Normal(0,1)) (torch/distributions/kl.py _kl_normal_normal)
+    var_ratio = std.pow(2)
+    t1 = mu.pow(2)
+    kl = 0.5 * (var_ratio + t1 - 1 - var_ratio.log())
+    y = vae_decode(p, x, mu + eps * std)
+    return F.mse_loss(y, action) + beta * kl.mean()
+
+
+# --------------------------------------------------------------------------- optimiser / sync
+def make_adam(params: Params, lr: float, betas=(0.9, 0.999), eps=1e-8):
+    """AdamFactory defaults (d3rlpy/models/optimizers.py:106-138)."""
+    return torch.optim.Adam(list(params.values()), lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)
+
+
+def soft_sync(targ: Params, src: Params, tau: float):
+    """torch_utility.soft_sync (torch_utility.py:27-33): mul_(1-tau) then add_(tau*p)."""
+    with torch.no_grad():
+        for k in src:
+            targ[k].mul_(1 - tau)
+            targ[k].add_(tau * src[k])
+
+
+def hard_sync(targ: Params, src: Params):
+    """torch_utility.hard_sync (torch_utility.py:36-41)."""
+    with torch.no_grad():
+        for k in src:
+            targ[k].copy_(src[k])
+
+
+# --------------------------------------------------------------------------- batches / scalers
+class Batch:
+    """TorchMiniBatch (torch_utility.py:152-221): every field float32; scaler applied to
+    observations/next_observations, reward scaler to rewards."""
+
+    def __init__(self, arrays: dict, scaler=None, reward_scaler=None):
+        f = lambda a: torch.tensor(np.asarray(a)).float()
+        self.observations = f(arrays["observations"])
+        self.actions = f(arrays["actions"])
+        self.rewards = f(arrays["rewards"])
+        self.next_observations = f(arrays["next_observations"])
+        self.terminals = f(arrays["terminals"])
+        self.n_steps = f(arrays["n_steps"])
+        if scaler is not None:
+            self.observations = scaler(self.observations)
+            self.next_observations = scaler(self.next_observations)
+        if reward_scaler is not None:
+            self.rewards = reward_scaler(self.rewards)
+
+
+def standard_scaler(mean, std, eps=1e-3):
+    """StandardScaler.transform (preprocessing/scalers.py:350-354)."""
+    mean = torch.tensor(np.asarray(mean), dtype=torch.float32).reshape(1, -1)
+    std = torch.tensor(np.asarray(std), dtype=torch.float32).reshape(1, -1)
+    return lambda x: (x - mean) / (std + eps)
+
+
+def pixel_scaler():
+    """PixelScaler.transform (preprocessing/scalers.py:109-110)."""
+    return lambda x: x.float() / 255.0
+
+
+def clip_reward_scaler(low, high, multiplier=1.0):
+    """ClipRewardScaler.transform (preprocessing/reward_scalers.py:176-177)."""
+    return lambda r: multiplier * r.clamp(low, high)
+
+
+# --------------------------------------------------------------------------- algorithms
+class _Algo:
+    grad_step = 0
+
+    def update(self, batch: Batch, noise: Noise) -> Dict[str, float]:
+        """LearnableBase.update (d3rlpy/base.py:746-758)."""
+        m = self._update(batch, noise)
+        self.grad_step += 1
+        return m
+
+
+class TD3PlusBC(_Algo):
+    """TD3PlusBC._update (algos/td3_plus_bc.py:177-192) over TD3PlusBCImpl."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4,
+                 gamma=0.99, tau=0.005, sigma=0.2, clip=0.5, alpha=2.5, update_actor_interval=2,
+                 seed=0, policy=None, critics=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_deterministic_policy(obs, act, hidden, gen))
+        self.targ_q = clone_params(self.q, False)
+        self.targ_pi = clone_params(self.pi, False)
+        self.critic_optim = make_adam(self.q, critic_lr)
+        self.actor_optim = make_adam(self.pi, actor_lr)
+        self.gamma, self.tau, self.sigma, self.clip, self.alpha = gamma, tau, sigma, clip, alpha
+        self.update_actor_interval = update_actor_interval
+        self.grad_step = 0
+
+    def compute_target(self, b: Batch, noise: Noise):
+        """TD3Impl.compute_target (algos/torch/td3_impl.py:61-78)."""
+        with torch.no_grad():
+            action = deterministic_policy(self.targ_pi, b.next_observations)
+            n = noise.normal(*action.shape)
+            clipped_noise = (self.sigma * n).clamp(-self.clip, self.clip)
+            a = (action + clipped_noise).clamp(-1.0, 1.0)
+            return q_continuous(self.targ_q, b.next_observations, a, "min")
+
+    def compute_critic_loss(self, b: Batch, q_tpn):
+        """DDPGBaseImpl.compute_critic_loss (algos/torch/ddpg_impl.py:154-165)."""
+        return td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+
+    def compute_actor_loss(self, b: Batch):
+        """TD3PlusBCImpl.compute_actor_loss (algos/torch/td3_plus_bc_impl.py:64-70)."""
+        action = deterministic_policy(self.pi, b.observations)
+        q_t = q_continuous(self.q, b.observations, action, "none")[0]
+        lam = self.alpha / (q_t.abs().mean()).detach()
+        return lam * -q_t.mean() + ((b.actions - action) ** 2).mean()
+
+    def update_critic(self, b, noise):
+        self.critic_optim.zero_grad()
+        loss = self.compute_critic_loss(b, self.compute_target(b, noise))
+        loss.backward()
+        self.critic_optim.step()
+        return float(loss.detach())
+
+    def update_actor(self, b):
+        self.actor_optim.zero_grad()
+        loss = self.compute_actor_loss(b)
+        loss.backward()
+        for v in self.q.values():  # critic grads produced here are discarded by the next zero_grad
+            v.grad = None
+        self.actor_optim.step()
+        return float(loss.detach())
+
+    def _update(self, b, noise):
+        m = {"critic_loss": self.update_critic(b, noise)}
+        if self.grad_step % self.update_actor_interval == 0:
+            m["actor_loss"] = self.update_actor(b)
+            soft_sync(self.targ_q, self.q, self.tau)
+            soft_sync(self.targ_pi, self.pi, self.tau)
+        return m
+
+
+class CQL(_Algo):
+    """CQL._update (algos/cql.py:234-258) over CQLImpl/SACImpl."""
+
+    def __init__(self, obs, act, hidden=(256, 256, 256), n_critics=2, actor_lr=1e-4, critic_lr=3e-4,
+                 temp_lr=1e-4, alpha_lr=1e-4, gamma=0.99, tau=0.005, initial_temperature=1.0,
+                 initial_alpha=1.0, alpha_threshold=10.0, conservative_weight=5.0, n_action_samples=10,
+                 soft_q_backup=False, seed=0, policy=None, critics=None, actor_hidden=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None
+                               else make_squashed_normal_policy(obs, act, actor_hidden or hidden, gen))
+        self.targ_q = clone_params(self.q, False)
+        self.targ_pi = clone_params(self.pi, False)
+        self.log_temp = {"_parameter": torch.full((1, 1), math.log(initial_temperature)).requires_grad_(True)}
+        self.log_alpha = {"_parameter": torch.full((1, 1), math.log(initial_alpha)).requires_grad_(True)}
+        self.critic_optim = make_adam(self.q, critic_lr)
+        self.actor_optim = make_adam(self.pi, actor_lr)
+        self.temp_optim = make_adam(self.log_temp, temp_lr)
+        self.alpha_optim = make_adam(self.log_alpha, alpha_lr)
+        self.temp_lr, self.alpha_lr = temp_lr, alpha_lr
+        self.gamma, self.tau = gamma, tau
+        self.alpha_threshold, self.conservative_weight = alpha_threshold, conservative_weight
+        self.n, self.soft_q_backup, self.act = n_action_samples, soft_q_backup, act
+        self.n_critics = n_members(self.q)
+        self.grad_step = 0
+
+    # -- SAC pieces (algos/torch/sac_impl.py:114-162)
+    def update_temp(self, b, noise):
+        self.temp_optim.zero_grad()
+        with torch.no_grad():
+            _, log_prob = policy_sample_with_log_prob(self.pi, b.observations, noise.normal(*b.actions.shape))
+            targ_temp = log_prob - self.act
+        loss = -(self.log_temp["_parameter"].exp() * targ_temp).mean()
+        loss.backward()
+        self.temp_optim.step()
+        return float(loss.detach()), float(self.log_temp["_parameter"].exp().detach()[0][0])
+
+    def compute_actor_loss(self, b, noise):
+        action, log_prob = policy_sample_with_log_prob(self.pi, b.observations, noise.normal(*b.actions.shape))
+        entropy = self.log_temp["_parameter"].exp() * log_prob
+        q_t = q_continuous(self.q, b.observations, action, "min")
+        return (entropy - q_t).mean()
+
+    # -- CQL pieces (algos/torch/cql_impl.py:110-243)
+    def _policy_is_values(self, policy_obs, value_obs, noise):
+        B = value_obs.shape[0]
+        with torch.no_grad():
+            acts, lps = policy_sample_n_with_log_prob(self.pi, policy_obs, noise.normal(self.n, B, self.act))
+        flat_obs = value_obs.expand(self.n, *value_obs.shape).transpose(0, 1).reshape(-1, value_obs.shape[1])
+        vals = q_continuous(self.q, flat_obs, acts.reshape(-1, self.act), "none").view(self.n_critics, B, self.n)
+        return vals - lps.reshape(1, -1, self.n)
+
+    def _random_is_values(self, obs, noise):
+        B = obs.shape[0]
+        flat_obs = obs.expand(self.n, *obs.shape).transpose(0, 1).reshape(-1, obs.shape[1])
+        rand = noise.uniform(B * self.n, self.act)
+        vals = q_continuous(self.q, flat_obs, rand, "none").view(self.n_critics, B, self.n)
+        return vals - math.log(0.5 ** self.act)
+
+    def conservative_loss(self, obs_t, act_t, obs_tp1, noise):
+        v_t = self._policy_is_values(obs_t, obs_t, noise)
+        v_tp1 = self._policy_is_values(obs_tp1, obs_t, noise)
+        v_r = self._random_is_values(obs_t, noise)
+        target_values = torch.cat([v_t, v_tp1, v_r], dim=2)
+        lse = torch.logsumexp(target_values, dim=2, keepdim=True)
+        data_values = q_continuous(self.q, obs_t, act_t, "none")
+        loss = lse.mean(dim=0).mean() - data_values.mean(dim=0).mean()
+        scaled = self.conservative_weight * loss
+        clipped_alpha = self.log_alpha["_parameter"].exp().clamp(0, 1e6)[0][0]
+        return clipped_alpha * (scaled - self.alpha_threshold)
+
+    def update_alpha(self, b, noise):
+        self.alpha_optim.zero_grad()
+        loss = -self.conservative_loss(b.observations, b.actions, b.next_observations, noise)
+        loss.backward()
+        for v in self.q.values():
+            v.grad = None
+        self.alpha_optim.step()
+        return float(loss.detach()), float(self.log_alpha["_parameter"].exp().detach()[0][0])
+
+    def compute_target(self, b, noise):
+        with torch.no_grad():
+            if self.soft_q_backup:
+                a, lp = policy_sample_with_log_prob(self.pi, b.next_observations, noise.normal(*b.actions.shape))
+                ent = self.log_temp["_parameter"].exp() * lp
+                return q_continuous(self.targ_q, b.next_observations, a, "min") - ent
+            a = policy_best_action(self.pi, b.next_observations)
+            return q_continuous(self.targ_q, b.next_observations, a, "min")
+
+    def compute_critic_loss(self, b, q_tpn, noise):
+        td = td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                 self.gamma ** b.n_steps)
+        return td + self.conservative_loss(b.observations, b.actions, b.next_observations, noise)
+
+    def update_critic(self, b, noise):
+        self.critic_optim.zero_grad()
+        q_tpn = self.compute_target(b, noise)
+        loss = self.compute_critic_loss(b, q_tpn, noise)
+        loss.backward()
+        self.log_alpha["_parameter"].grad = None
+        self.critic_optim.step()
+        return float(loss.detach())
+
+    def update_actor(self, b, noise):
+        self.actor_optim.zero_grad()
+        loss = self.compute_actor_loss(b, noise)
+        loss.backward()
+        for v in self.q.values():
+            v.grad = None
+        self.log_temp["_parameter"].grad = None
+        self.actor_optim.step()
+        return float(loss.detach())
+
+    def _update(self, b, noise):
+        m = {}
+        if self.temp_lr > 0:
+            m["temp_loss"], m["temp"] = self.update_temp(b, noise)
+        if self.alpha_lr > 0:
+            m["alpha_loss"], m["alpha"] = self.update_alpha(b, noise)
+        m["critic_loss"] = self.update_critic(b, noise)
+        m["actor_loss"] = self.update_actor(b, noise)
+        soft_sync(self.targ_q, self.q, self.tau)
+        soft_sync(self.targ_pi, self.pi, self.tau)
+        return m
+
+
+class BCQ(_Algo):
+    """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
+
+    def __init__(self, obs, act, hidden=(400, 300), vae_hidden=(750, 750), n_critics=2, actor_lr=1e-3,
+                 critic_lr=1e-3, imitator_lr=1e-3, gamma=0.99, tau=0.005, lam=0.75, n_action_samples=100,
+                 action_flexibility=0.05, beta=0.5, update_actor_interval=1, rl_start_step=0, seed=0,
+                 policy=None, critics=None, imitator=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.imitator = clone_params(imitator if imitator is not None else make_cvae(obs, act, 2 * act, vae_hidden, gen))
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_residual_policy(obs, act, hidden, gen))
+        self.targ_q = clone_params(self.q, False)
+        self.targ_pi = clone_params(self.pi, False)
+        self.critic_optim = make_adam(self.q, critic_lr)
+        self.actor_optim = make_adam(self.pi, actor_lr)
+        self.imitator_optim = make_adam(self.imitator, imitator_lr)
+        self.gamma, self.tau, self.lam, self.n, self.flex, self.beta = gamma, tau, lam, n_action_samples, action_flexibility, beta
+        self.update_actor_interval, self.rl_start_step, self.act = update_actor_interval, rl_start_step, act
+        self.grad_step = 0
+
+    def update_imitator(self, b, noise):
+        self.imitator_optim.zero_grad()
+        loss = vae_error(self.imitator, b.observations, b.actions, noise.normal(b.observations.shape[0], 2 * self.act), self.beta)
+        loss.backward()
+        self.imitator_optim.step()
+        return float(loss.detach())
+
+    def compute_target(self, b, noise):
+        """bcq_impl.py:163-187,215-226 + compute_max_with_n_actions (q_functions/__init__.py:8-63)."""
+        with torch.no_grad():
+            x = b.next_observations
+            B = x.shape[0]
+            flat_x = x.view(B, 1, -1).expand(B, self.n, x.shape[1]).reshape(-1, x.shape[1])
+            latent = noise.normal(B * self.n, 2 * self.act).clamp(-0.5, 0.5)
+            sampled = vae_decode(self.imitator, flat_x, latent)
+            actions = residual_policy(self.targ_pi, flat_x, sampled, self.flex)
+            vals = q_continuous(self.targ_q, flat_x, actions, "none")  # (E, B*N, 1)
+            E = vals.shape[0]
+            values = vals.view(E, B, self.n, 1).transpose(0, 1)  # (B,E,N,1)
+            mean_values = values.mean(dim=3)
+            max_values, max_idx = mean_values.max(dim=1)
+            min_values, min_idx = mean_values.min(dim=1)
+            mix = (1.0 - self.lam) * max_values + self.lam * min_values
+            action_idx = mix.argmax(dim=1)
+            flat_values = values.transpose(1, 2).reshape(B * self.n, E, -1)
+            bn = torch.arange(B * self.n)
+            mx = flat_values[bn, max_idx.reshape(-1)].view(B, self.n, -1)
+            mn = flat_values[bn, min_idx.reshape(-1)].view(B, self.n, -1)
+            mix_values = (1.0 - self.lam) * mx + self.lam * mn
+            return mix_values[torch.arange(B), action_idx]
+
+    def update_critic(self, b, noise):
+        self.critic_optim.zero_grad()
+        q_tpn = self.compute_target(b, noise)
+        loss = td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+        loss.backward()
+        self.critic_optim.step()
+        return float(loss.detach())
+
+    def compute_actor_loss(self, b, noise):
+        latent = noise.normal(b.observations.shape[0], 2 * self.act).clamp(-0.5, 0.5)
+        sampled = vae_decode(self.imitator, b.observations, latent)
+        action = residual_policy(self.pi, b.observations, sampled, self.flex)
+        return -q_continuous(self.q, b.observations, action, "none")[0].mean()
+
+    def update_actor(self, b, noise):
+        self.actor_optim.zero_grad()
+        loss = self.compute_actor_loss(b, noise)
+        loss.backward()
+        for v in list(self.q.values()) + list(self.imitator.values()):
+            v.grad = None
+        self.actor_optim.step()
+        return float(loss.detach())
+
+    def _update(self, b, noise):
+        m = {"imitator_loss": self.update_imitator(b, noise)}
+        if self.grad_step >= self.rl_start_step:
+            m["critic_loss"] = self.update_critic(b, noise)
+            if self.grad_step % self.update_actor_interval == 0:
+                m["actor_loss"] = self.update_actor(b, noise)
+                soft_sync(self.targ_pi, self.pi, self.tau)
+                soft_sync(self.targ_q, self.q, self.tau)
+        return m
+
+
+class DiscreteCQL(_Algo):
+    """DQN._update (algos/dqn.py:127-132) over DiscreteCQLImpl/DoubleDQNImpl
+    (algos/torch/cql_impl.py:279-302, dqn_impl.py:97-171)."""
+
+    def __init__(self, obs_shape, act, n_critics=1, lr=6.25e-5, gamma=0.99, target_update_interval=8000,
+                 alpha=1.0, seed=0, critics=None, hidden=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None
+                              else make_discrete_critics(tuple(obs_shape), act, n_critics, gen, hidden))
+        self.targ_q = clone_params(self.q, False)
+        self.optim = make_adam(self.q, lr)
+        self.gamma, self.interval, self.alpha, self.act = gamma, target_update_interval, alpha, act
+        self.grad_step = 0
+
+    def compute_target(self, b):
+        with torch.no_grad():
+            action = q_discrete(self.q, b.next_observations).argmax(dim=1)
+            vals = q_discrete(self.targ_q, b.next_observations, "none")  # (E,B,A)
+            one_hot = F.one_hot(action.view(-1), num_classes=self.act).float()
+            picked = (vals * one_hot.unsqueeze(0)).sum(dim=2, keepdim=True)  # pick_value_by_action per member
+            return reduce_ensemble(picked, "min")
+
+    def compute_loss(self, b, q_tpn):
+        act_long = b.actions.long()
+        loss = td_error_discrete(self.q, b.observations, act_long, b.rewards, q_tpn, b.terminals,
+                                 self.gamma ** b.n_steps)
+        policy_values = q_discrete(self.q, b.observations)
+        lse = torch.logsumexp(policy_values, dim=1, keepdim=True)
+        one_hot = F.one_hot(act_long.view(-1), num_classes=self.act)
+        data_values = (q_discrete(self.q, b.observations) * one_hot).sum(dim=1, keepdim=True)
+        return loss + self.alpha * (lse - data_values).mean()
+
+    def _update(self, b, noise=None):
+        self.optim.zero_grad()
+        loss = self.compute_loss(b, self.compute_target(b))
+        loss.backward()
+        self.optim.step()
+        if self.grad_step % self.interval == 0:
+            hard_sync(self.targ_q, self.q)
+        return {"loss": float(loss.detach())}

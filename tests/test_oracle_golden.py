@@ -1,0 +1,69 @@
+"""CPU: the oracle restatement vs the golden vectors produced by the live reference
+(tests/golden/make_golden.py).  This is what pins the oracle where the reference is absent."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler as osampler
+from oracle import update as oupdate
+from tests.golden_io import Case, load_sampler, load_update
+
+
+def test_sampler_matches_reference_golden():
+    z = load_sampler()
+    for name in [str(c) for c in z["cases"]]:
+        d = lambda k: z[f"{name}/data/{k}"]
+        replay = osampler.FlatReplay(d("observations"), d("actions"), d("rewards"), d("terminals"), d("episode_terminals"))
+        n_frames, n_steps = [int(v) for v in z[f"{name}/cfg"]]
+        out = osampler.gather(replay, z[f"{name}/indices"], n_frames, n_steps, 0.99)
+        for k, v in out.items():
+            ref = z[f"{name}/ref/{k}"]
+            assert ref.dtype == v.dtype and ref.shape == v.shape, (name, k)
+            if k == "rewards":
+                np.testing.assert_allclose(v, ref, rtol=1e-6, atol=1e-7, err_msg=f"{name}/{k}")
+            else:
+                assert np.array_equal(v, ref), (name, k)
+
+
+def _build(case: Case):
+    n, c = case.name, case.cfg
+    g = lambda grp: case.group("init", grp)
+    if n == "td3bc":
+        algo = oupdate.TD3PlusBC(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"))
+        scaler = oupdate.standard_scaler(case.z["td3bc/scaler_mean"], case.z["td3bc/scaler_std"])
+        return algo, scaler
+    if n.startswith("cql"):
+        return oupdate.CQL(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"), n_action_samples=int(c["n"]),
+                           soft_q_backup=bool(c["soft_q_backup"])), None
+    if n == "bcq":
+        return oupdate.BCQ(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"), imitator=g("imitator"),
+                           n_action_samples=int(c["n"])), None
+    if n == "dcql_vec":
+        return oupdate.DiscreteCQL((int(c["obs"]),), int(c["act"]), critics=g("q"),
+                                   target_update_interval=int(c["interval"])), None
+    if n == "dcql_pix":
+        hw = int(c["hw"])
+        return oupdate.DiscreteCQL((int(c["n_frames"]), hw, hw), int(c["act"]), critics=g("q")), oupdate.pixel_scaler()
+    raise KeyError(n)
+
+
+@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix"])
+def test_update_matches_reference_golden(name):
+    torch.set_num_threads(1)
+    case = Case(load_update(), name)
+    algo, scaler = _build(case)
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s), scaler), oupdate.Noise(injected=case.noise(s)))
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref)
+        for k in ref:
+            assert abs(m[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k])), (name, s, k, m[k], ref[k])
+    groups = {"q": "q", "pi": "pi", "targ_q": "targ_q", "targ_pi": "targ_pi", "imitator": "imitator",
+              "log_temp": "log_temp", "log_alpha": "log_alpha"}
+    for grp, attr in groups.items():
+        ref = case.group("final", grp)
+        if not ref:
+            continue
+        got = getattr(algo, attr)
+        for k, v in ref.items():
+            torch.testing.assert_close(got[k].detach(), v, rtol=1e-5, atol=2e-6, msg=f"{name}/{grp}/{k}")
