@@ -1,0 +1,103 @@
+"""ctypes binding of libd3b.so — the C ABI declared in include/d3rlpy_b200.h.
+
+Prototypes are parsed from the header so the Python side can never drift from the
+declared ABI.  There is NO fallback: if the library is missing or a call fails, we raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from typing import Dict, List, Tuple
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HEADER = os.path.join(HERE, "..", "include", "d3rlpy_b200.h")
+LIB_PATH = os.path.join(HERE, "libd3b.so")
+
+_SCALARS = {
+    "int": ctypes.c_int, "unsigned": ctypes.c_uint, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64,
+    "float": ctypes.c_float, "double": ctypes.c_double,
+}
+
+
+class D3BError(RuntimeError):
+    pass
+
+
+def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
+    """Returns {name: (return_type, [(ctype, argname), ...])} for every d3b_* prototype."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([\w\s\*]+?)\b(d3b_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        parsed = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                mm = re.match(r"(.+?)\s*(\w+)$", a)
+                parsed.append((mm.group(1).strip(), mm.group(2)))
+        protos[name] = (ret, parsed)
+    return protos
+
+
+def _ctype(t: str):
+    if "*" in t:
+        return ctypes.c_void_p
+    t = t.replace("const", "").strip()
+    return _SCALARS[t]
+
+
+class Lib:
+    dry = False
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise D3BError(
+                f"{path} not found: build it with `python -m d3rlpy_b200.build` (nvcc, sm_100a). "
+                "d3rlpy_b200 has no CPU or PyTorch fallback.")
+        self._dll = ctypes.CDLL(path)
+        self.protos = parse_header()
+        self._dll.d3b_last_error.restype = ctypes.c_char_p
+        for name, (ret, args) in self.protos.items():
+            fn = getattr(self._dll, name)  # AttributeError if the .so does not export a declared symbol
+            if name == "d3b_last_error":
+                continue
+            fn.argtypes = [_ctype(t) for t, _ in args]
+            fn.restype = ctypes.c_int64 if ret == "int64_t" else ctypes.c_int
+        if self._dll.d3b_abi_version() != 1:
+            raise D3BError("libd3b.so ABI version mismatch; rebuild")
+
+    def last_error(self) -> str:
+        return self._dll.d3b_last_error().decode()
+
+    def raw(self, name: str):
+        return getattr(self._dll, name)
+
+    def __getattr__(self, name: str):
+        fn = getattr(self._dll, "d3b_" + name)
+
+        def call(*args):
+            if self.dry:  # allocation-only pass before CUDA-graph capture (no launches)
+                return 0
+            rc = fn(*args)
+            if rc != 0:
+                raise D3BError(f"d3b_{name} failed ({rc}): {self.last_error()}")
+            return rc
+
+        call.__name__ = name
+        setattr(self, name, call)
+        return call
+
+    def launch_count(self) -> int:
+        return int(self._dll.d3b_launch_count())
+
+
+_LIB = None
+
+
+def lib() -> Lib:
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB

@@ -1,0 +1,3 @@
+from .base import VectorEncoderFactory  # noqa: F401
+from .cql import CQL  # noqa: F401
+from .td3_plus_bc import TD3PlusBC  # noqa: F401

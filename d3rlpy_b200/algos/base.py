@@ -1,0 +1,138 @@
+"""User-facing algorithm base: mirrors LearnableBase/AlgoBase (d3rlpy/base.py:124-758,
+d3rlpy/algos/base.py) for the part of the API on the update path: constructor kwargs,
+`create_impl`, `build_with_dataset`, `update(batch)` with the pre-increment `grad_step`
+schedule (base.py:746-758), and a minimal `fit()` loop over a device-resident replay."""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+IMPL_NOT_INITIALIZED_ERROR = "The neural network parameters are not initialized. Pleaes call build_with_dataset, build_with_env, or directly call fit or fit_online method."
+
+
+def _hidden_units(factory, default):
+    """Accepts "default", a sequence of hidden sizes, or an object with `hidden_units`
+    (VectorEncoderFactory, d3rlpy/models/encoders.py:170-260).  BN / dropout / dense encoders are
+    outside the hot path and rejected here, before any kernel runs."""
+    if factory is None or factory == "default":
+        return list(default)
+    if isinstance(factory, (list, tuple)):
+        return list(factory)
+    hu = getattr(factory, "hidden_units", None) or getattr(factory, "_hidden_units", None)
+    if hu is None:
+        raise ValueError(f"unsupported encoder factory {factory!r}")
+    for flag in ("use_batch_norm", "_use_batch_norm", "use_dense", "_use_dense"):
+        if getattr(factory, flag, False):
+            raise ValueError("batch-norm / dense encoders are not supported by the B200 path")
+    if getattr(factory, "dropout_rate", None) or getattr(factory, "_dropout_rate", None):
+        raise ValueError("dropout encoders are not supported by the B200 path")
+    return list(hu)
+
+
+class VectorEncoderFactory:
+    """Same constructor as d3rlpy.models.encoders.VectorEncoderFactory (hidden_units only)."""
+
+    TYPE = "vector"
+
+    def __init__(self, hidden_units: Optional[Sequence[int]] = None, activation: str = "relu",
+                 use_batch_norm: bool = False, dropout_rate: Optional[float] = None, use_dense: bool = False):
+        if activation != "relu" or use_batch_norm or dropout_rate is not None or use_dense:
+            raise ValueError("B200 path supports ReLU MLP encoders without BN/dropout/dense")
+        self.hidden_units = list(hidden_units) if hidden_units is not None else [256, 256]
+
+
+class AlgoBase:
+    _impl = None
+
+    def __init__(self, batch_size: int, n_frames: int, n_steps: int, gamma: float, scaler=None, action_scaler=None,
+                 reward_scaler=None, use_gpu=0, kwargs: Optional[Dict[str, Any]] = None):
+        self._batch_size, self._n_frames, self._n_steps, self._gamma = batch_size, n_frames, n_steps, gamma
+        self._scaler, self._action_scaler, self._reward_scaler = scaler, action_scaler, reward_scaler
+        self._use_gpu = use_gpu
+        self._grad_step = 0
+        self._kwargs = kwargs or {}
+        if action_scaler is not None or reward_scaler is not None:
+            raise ValueError("action/reward scalers are not on the accelerated path yet")
+
+    # ------------------------------------------------------------------ reference API
+    @property
+    def batch_size(self):
+        return self._batch_size
+
+    @property
+    def n_frames(self):
+        return self._n_frames
+
+    @property
+    def n_steps(self):
+        return self._n_steps
+
+    @property
+    def gamma(self):
+        return self._gamma
+
+    @property
+    def scaler(self):
+        return self._scaler
+
+    @property
+    def impl(self):
+        return self._impl
+
+    @property
+    def grad_step(self) -> int:
+        return self._grad_step
+
+    def set_grad_step(self, grad_step: int) -> None:
+        self._grad_step = grad_step
+
+    def create_impl(self, observation_shape: Sequence[int], action_size: int) -> None:
+        if self._impl:
+            return
+        self._create_impl(tuple(observation_shape), action_size)
+
+    def _get_shape(self, observation_shape):
+        """_process_observation_shape (base.py:735-744): frame stacking multiplies channels."""
+        if len(observation_shape) == 3:
+            return (self._n_frames * observation_shape[0],) + tuple(observation_shape[1:])
+        return tuple(observation_shape)
+
+    def build_with_dataset(self, dataset) -> None:
+        self.create_impl(self._get_shape(dataset.get_observation_shape()), dataset.get_action_size())
+
+    def update(self, batch) -> Dict[str, float]:
+        """LearnableBase.update (base.py:746-758): `_update` then grad_step += 1."""
+        loss = self._update(batch)
+        self._grad_step += 1
+        return loss
+
+    def _update(self, batch) -> Dict[str, float]:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ fit over an HBM-resident replay
+    def fit(self, dataset, n_steps: int, n_steps_per_epoch: int = 10000, shuffle: bool = True,
+            seed: Optional[int] = None, verbose: bool = False) -> List[Dict[str, float]]:
+        """Minimal `fit()` (base.py:349-687 without logger/scorers): RandomIterator index stream
+        (np.random.randint per sample, iterators/random_iterator.py:38-41) -> device gather -> update."""
+        from ..dataset import TransitionMiniBatch
+
+        if self._scaler is not None and hasattr(self._scaler, "fit_dataset"):
+            self._scaler.fit_dataset(dataset)
+        self.build_with_dataset(dataset)
+        replay = dataset.device_replay(self._impl._device)
+        rng = np.random if seed is None else np.random.RandomState(seed)
+        history: List[Dict[str, float]] = []
+        acc: Dict[str, List[float]] = {}
+        for step in range(1, n_steps + 1):
+            idx = np.array([rng.randint(len(replay)) for _ in range(self._batch_size)], dtype=np.int64)
+            batch = TransitionMiniBatch.from_indices(replay, idx, n_frames=self._n_frames, n_steps=self._n_steps,
+                                                     gamma=self._gamma, scaler=self._scaler,
+                                                     out=self._impl.device_batch(self._batch_size))
+            m = self.update(batch)
+            for k, v in m.items():
+                acc.setdefault(k, []).append(float(v))
+            if step % n_steps_per_epoch == 0 or step == n_steps:
+                history.append({k: float(np.mean(v)) for k, v in acc.items()})
+                acc = {}
+        return history

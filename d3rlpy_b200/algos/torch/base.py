@@ -1,0 +1,304 @@
+"""Shared host machinery of the B200 impls: device batch staging, noise arena, metric slots,
+step counters and whole-update CUDA-graph capture (K12).
+
+Mirrors the role of TorchImplBase + @torch_api/@train_api (d3rlpy/algos/torch/base.py:20-142,
+d3rlpy/torch_utility.py:152-299): turns a TransitionMiniBatch into float32 device tensors
+(applying the scalers), and returns losses as numpy scalars.  Unlike the reference it converts the
+batch ONCE per update, and reads every metric back with ONE pinned D2H copy.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..._lib import D3BError, lib
+
+
+def _align4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+class DeviceBatch:
+    """One contiguous float32 HBM buffer holding the six minibatch arrays
+    [obs | next_obs | actions | rewards | terminals | n_steps] (vector observations), mirrored by a
+    pinned host staging buffer of the same layout (single H2D copy per update)."""
+
+    def __init__(self, batch: int, obs_dim: int, act_dim: int, device, pixel_shape=None, discrete=False):
+        self.B, self.O, self.A = batch, obs_dim, act_dim
+        self.pixel_shape = tuple(pixel_shape) if pixel_shape else None
+        self.discrete = discrete
+        o = 0
+        self.off = {}
+        fields = [("obs", 0 if pixel_shape else batch * obs_dim), ("next_obs", 0 if pixel_shape else batch * obs_dim),
+                  ("act", batch * (1 if discrete else act_dim)), ("rew", batch), ("term", batch), ("nsteps", batch)]
+        for name, n in fields:
+            self.off[name] = o
+            o = _align4(o + n)
+        self.nfloat = o
+        self.dev = torch.zeros(o, dtype=torch.float32, device=device)
+        self.host = torch.zeros(o, dtype=torch.float32).pin_memory() if device.type == "cuda" else torch.zeros(o)
+        self.host_np = self.host.numpy()
+        if pixel_shape:
+            n = batch * int(np.prod(pixel_shape))
+            self.pix_dev = torch.zeros(2 * n, dtype=torch.uint8, device=device)
+            self.pix_host = torch.zeros(2 * n, dtype=torch.uint8).pin_memory()
+            self.pix_host_np = self.pix_host.numpy()
+            self.npix = n
+
+    def ptr(self, name: str) -> int:
+        if self.pixel_shape and name in ("obs", "next_obs"):
+            return self.pix_dev.data_ptr() + (self.npix if name == "next_obs" else 0)
+        return self.dev.data_ptr() + 4 * self.off[name]
+
+    def view(self, name: str) -> torch.Tensor:
+        B = self.B
+        if self.pixel_shape and name in ("obs", "next_obs"):
+            s = self.npix if name == "next_obs" else 0
+            return self.pix_dev[s:s + self.npix].view(B, *self.pixel_shape)
+        shape = {"obs": (B, self.O), "next_obs": (B, self.O), "act": (B,) if self.discrete else (B, self.A),
+                 "rew": (B, 1), "term": (B, 1), "nsteps": (B, 1)}[name]
+        n = int(np.prod(shape))
+        return self.dev[self.off[name]:self.off[name] + n].view(shape)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return 4 * self.nfloat + (2 * self.npix if self.pixel_shape else 0)
+
+    def stage_host(self, batch) -> None:
+        """numpy TransitionMiniBatch-like -> pinned staging (float32 casts as _convert_to_torch,
+        d3rlpy/torch_utility.py:146-149; uint8 frames stay uint8 on the wire)."""
+        h, off, B = self.host_np, self.off, self.B
+        if self.pixel_shape:
+            self.pix_host_np[:self.npix] = np.asarray(batch.observations).reshape(-1)
+            self.pix_host_np[self.npix:] = np.asarray(batch.next_observations).reshape(-1)
+        else:
+            h[off["obs"]:off["obs"] + B * self.O] = np.asarray(batch.observations, dtype=np.float32).reshape(-1)
+            h[off["next_obs"]:off["next_obs"] + B * self.O] = np.asarray(batch.next_observations,
+                                                                         dtype=np.float32).reshape(-1)
+        na = B * (1 if self.discrete else self.A)
+        h[off["act"]:off["act"] + na] = np.asarray(batch.actions, dtype=np.float32).reshape(-1)
+        h[off["rew"]:off["rew"] + B] = np.asarray(batch.rewards, dtype=np.float32).reshape(-1)
+        h[off["term"]:off["term"] + B] = np.asarray(batch.terminals, dtype=np.float32).reshape(-1)
+        h[off["nsteps"]:off["nsteps"] + B] = np.asarray(batch.n_steps, dtype=np.float32).reshape(-1)
+
+
+class ImplBase:
+    """Common state: device, stream, counters, metric slots, noise arena, graphs."""
+
+    METRICS: Sequence[str] = ()
+    N_COUNTERS = 8
+
+    def __init__(self, observation_shape, action_size, use_gpu=0, scaler=None, action_scaler=None,
+                 reward_scaler=None, world_size: int = 1, rank: int = 0):
+        if not torch.cuda.is_available():
+            raise D3BError("d3rlpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = lib()
+        dev_id = 0 if use_gpu in (None, False, True) else int(getattr(use_gpu, "get_id", lambda: use_gpu)())
+        self._device = torch.device("cuda", dev_id)
+        torch.cuda.set_device(self._device)
+        self._observation_shape = tuple(observation_shape)
+        self._action_size = int(action_size)
+        self._scaler, self._action_scaler, self._reward_scaler = scaler, action_scaler, reward_scaler
+        self._stream_obj = torch.cuda.Stream(device=self._device)
+        self._stream = self._stream_obj.cuda_stream
+        self._counters = torch.zeros(self.N_COUNTERS, dtype=torch.int32, device=self._device)
+        self._slots = torch.zeros(64, dtype=torch.float32, device=self._device)  # [0:32) metrics, [32:64) sums
+        self._slots_host = torch.zeros(64, dtype=torch.float32).pin_memory()
+        self._graphs: Dict[tuple, int] = {}
+        self._graph_nodes: Dict[tuple, int] = {}
+        self._batch: Optional[DeviceBatch] = None
+        self._noise: Optional[torch.Tensor] = None
+        self._noise_injected = False
+        self._seed = 0
+        self._ws: Dict[str, torch.Tensor] = {}
+        self.world_size, self.rank = world_size, rank
+        self.use_graph = True
+
+    # ------------------------------------------------------------------ small helpers
+    @property
+    def device(self) -> str:
+        return str(self._device)
+
+    @property
+    def observation_shape(self):
+        return self._observation_shape
+
+    @property
+    def action_size(self) -> int:
+        return self._action_size
+
+    @property
+    def scaler(self):
+        return self._scaler
+
+    @property
+    def action_scaler(self):
+        return self._action_scaler
+
+    @property
+    def reward_scaler(self):
+        return self._reward_scaler
+
+    def ws(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
+        t = self._ws.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(*shape, dtype=dtype, device=self._device)
+            self._ws[name] = t
+        return t
+
+    def counter_ptr(self, i: int) -> int:
+        return self._counters.data_ptr() + 4 * i
+
+    def metric_ptr(self, i: int) -> int:
+        return self._slots.data_ptr() + 4 * i
+
+    def sums_ptr(self, i: int) -> int:
+        return self._slots.data_ptr() + 4 * (32 + i)
+
+    def zero_slots(self):
+        self._lib.memset_zero(self._slots.data_ptr(), 4 * 64, self._stream)
+
+    def sync(self):
+        self._lib.stream_sync(self._stream)
+
+    def read_slots(self) -> np.ndarray:
+        self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
+        self.sync()
+        return self._slots_host.numpy()
+
+    # ------------------------------------------------------------------ batches
+    def _make_batch(self, B: int) -> DeviceBatch:
+        pixel = self._observation_shape if len(self._observation_shape) == 3 else None
+        O = 0 if pixel else self._observation_shape[0]
+        return DeviceBatch(B, O, self._action_size, self._device, pixel_shape=pixel, discrete=self.DISCRETE)
+
+    DISCRETE = False
+
+    def device_batch(self, B: int) -> DeviceBatch:
+        if self._batch is None or self._batch.B != B:
+            self._batch = self._make_batch(B)
+            self._graphs_invalidate()
+        return self._batch
+
+    def load_batch(self, batch) -> DeviceBatch:
+        """Accepts a host minibatch (numpy properties, e.g. the reference's TransitionMiniBatch or ours)
+        or our device-resident TransitionMiniBatch (already gathered in HBM)."""
+        dev = getattr(batch, "_device_batch", None)
+        if dev is not None:
+            if self._batch is not dev:
+                self._batch = dev
+                self._graphs_invalidate()
+            return dev
+        B = len(batch.rewards) if hasattr(batch, "rewards") else len(batch)
+        db = self.device_batch(B)
+        db.stage_host(batch)
+        self._lib.copy_h2d(db.dev.data_ptr(), db.host.data_ptr(), 4 * db.nfloat, self._stream)
+        if db.pixel_shape:
+            self._lib.copy_h2d(db.pix_dev.data_ptr(), db.pix_host.data_ptr(), 2 * db.npix, self._stream)
+        self._apply_scalers(db)
+        return db
+
+    def _apply_scalers(self, db: DeviceBatch):
+        """scaler.transform on obs/next_obs (d3rlpy/torch_utility.py:179-185).  Standard scaling of a
+        host-staged batch runs as a device kernel; pixel scaling is fused into the first conv load."""
+        sc = self._scaler
+        if sc is None or db.pixel_shape:
+            return
+        mean, std, eps = self._scaler_params()
+        self._lib.standardize(db.ptr("obs"), mean.data_ptr(), std.data_ptr(), eps, 2 * db.B, db.O, self._stream)
+
+    def _scaler_params(self):
+        sc = self._scaler
+        if getattr(self, "_scaler_dev", None) is None:
+            mean = torch.tensor(np.asarray(sc._mean, dtype=np.float32).reshape(-1), device=self._device)
+            std = torch.tensor(np.asarray(sc._std, dtype=np.float32).reshape(-1), device=self._device)
+            self._scaler_dev = (mean, std, float(sc._eps))
+        return self._scaler_dev
+
+    # ------------------------------------------------------------------ noise
+    def noise_layout(self, B: int) -> Dict[str, tuple]:
+        """name -> (kind, shape) in reference draw order; overridden per algorithm."""
+        return {}
+
+    def _noise_plan(self, B: int):
+        layout = self.noise_layout(B)
+        normals = [(k, s) for k, (kind, s) in layout.items() if kind == "normal"]
+        uniforms = [(k, s) for k, (kind, s) in layout.items() if kind == "uniform"]
+        off, plan = 0, {}
+        for k, s in normals + uniforms:
+            plan[k] = (off, s)
+            off += int(np.prod(s))
+        n_normal = sum(int(np.prod(s)) for _, s in normals)
+        return plan, n_normal, off - n_normal, list(layout.keys())
+
+    def noise_view(self, name: str, B: int) -> torch.Tensor:
+        plan, n_norm, n_uni, _ = self._noise_plan(B)
+        if self._noise is None or self._noise.numel() < n_norm + n_uni:
+            self._noise = torch.zeros(max(4, _align4(n_norm + n_uni)), dtype=torch.float32, device=self._device)
+        off, shape = plan[name]
+        return self._noise[off:off + int(np.prod(shape))].view(shape)
+
+    def inject_noise(self, tensors: List[torch.Tensor], B: int, names: Optional[List[str]] = None):
+        """Parity mode: replay recorded draws (in reference draw order) instead of Philox."""
+        order = names or self._noise_plan(B)[3]
+        assert len(order) == len(tensors), (order, [tuple(t.shape) for t in tensors])
+        for name, t in zip(order, tensors):
+            v = self.noise_view(name, B)
+            assert v.numel() == t.numel(), (name, tuple(v.shape), tuple(t.shape))
+            v.copy_(t.to(self._device, torch.float32).reshape(v.shape))
+        torch.cuda.current_stream(self._device).synchronize()
+        if not self._noise_injected:
+            self._noise_injected = True
+            self._graphs_invalidate()
+
+    def clear_injected_noise(self):
+        if self._noise_injected:
+            self._noise_injected = False
+            self._graphs_invalidate()
+
+    def fill_noise(self, B: int):
+        plan, n_norm, n_uni, _ = self._noise_plan(B)
+        if n_norm + n_uni == 0 or self._noise_injected:
+            return
+        self.noise_view(next(iter(plan)), B)  # ensure allocation
+        self._lib.noise_fill(self._noise.data_ptr(), n_norm, n_uni, self._seed, self.counter_ptr(0), self._stream)
+
+    # ------------------------------------------------------------------ graphs
+    def _graphs_invalidate(self):
+        for g in self._graphs.values():
+            self._lib.graph_destroy(g)
+        self._graphs.clear()
+        self._graph_nodes.clear()
+
+    def run_program(self, key: tuple, program) -> None:
+        """Runs `program()` (a sequence of launches on self._stream) — captured once per `key` as a CUDA
+        graph and replayed afterwards."""
+        if not self.use_graph:
+            program()
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            import ctypes
+
+            # allocation-only pass: every workspace the program touches is created now, because
+            # allocating inside stream capture is illegal
+            self._lib.dry = True
+            try:
+                program()
+            finally:
+                self._lib.dry = False
+            torch.cuda.synchronize(self._device)
+            self._lib.graph_begin(self._stream)
+            try:
+                program()
+            finally:
+                exec_ = ctypes.c_void_p()
+                nodes = ctypes.c_int()
+                self._lib.graph_end(self._stream, ctypes.byref(exec_), ctypes.byref(nodes))
+            g = exec_.value
+            self._graphs[key] = g
+            self._graph_nodes[key] = nodes.value
+        self._lib.graph_launch(g, self._stream)
+

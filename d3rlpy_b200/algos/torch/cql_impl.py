@@ -1,0 +1,325 @@
+"""CQL (SAC-based) on B200: mirrors CQLImpl / SACImpl
+(d3rlpy/algos/torch/cql_impl.py:21-243, sac_impl.py:33-162).
+
+One update = ONE policy-trunk forward over [obs; next_obs] (the policy does not change until
+update_actor, so temp/alpha/critic/actor steps share it), two critic passes over the
+B(1+3N) importance-sampling rows (alpha step: forward only; critic step: forward + backward), a
+B-row target pass and a B-row actor pass with data-gradient only — the reference's wasted critic
+backward in update_alpha and the unused critic weight-gradients in update_actor are not computed
+(SURVEY.md §8d "req").
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from ...nets import DenseNet
+from .ddpg_impl import C_ACTOR, C_ALPHA, C_CRITIC, C_DRAW, C_TEMP, DDPGBaseImpl
+
+M_TEMP_LOSS, M_TEMP, M_ALPHA_LOSS, M_ALPHA, M_CRITIC, M_ACTOR = 0, 1, 2, 3, 4, 5
+S_ALPHA, S_CRITIC, S_ACTOR = 0, 4, 8
+MIN_LOGSTD, MAX_LOGSTD = -20.0, 2.0  # create_squashed_normal_policy defaults (models/builders.py:105-121)
+
+
+class _Scalar:
+    """A (1,1) nn.Parameter-like scalar (d3rlpy/models/torch/parameters.py:5-21) with Adam state."""
+
+    def __init__(self, value: float, device, step_view):
+        self.buf = torch.zeros(16, dtype=torch.float32, device=device)  # p, g, m, v at 16B-aligned slots
+        self.buf[0] = value
+        self.step = step_view
+
+    def ptr(self, which: str) -> int:
+        return self.buf.data_ptr() + 16 * {"p": 0, "g": 1, "m": 2, "v": 3}[which]
+
+    @property
+    def data(self) -> torch.Tensor:
+        return self.buf[0:1].view(1, 1)
+
+    def state_dict(self):
+        return {"_parameter": self.data}
+
+    def load_state_dict(self, sd):
+        self.buf[0] = float(sd["_parameter"].reshape(-1)[0])
+
+
+class CQLImpl(DDPGBaseImpl):
+    def __init__(self, *, temp_learning_rate=1e-4, alpha_learning_rate=1e-4, initial_temperature=1.0,
+                 initial_alpha=1.0, alpha_threshold=10.0, conservative_weight=5.0, n_action_samples=10,
+                 soft_q_backup=False, **kw):
+        super().__init__(**kw)
+        self._temp_learning_rate, self._alpha_learning_rate = temp_learning_rate, alpha_learning_rate
+        self._initial_temperature, self._initial_alpha = initial_temperature, initial_alpha
+        self._alpha_threshold, self._conservative_weight = alpha_threshold, conservative_weight
+        self._n_action_samples, self._soft_q_backup = n_action_samples, soft_q_backup
+
+    def build(self) -> None:
+        super().build()
+        self._log_temp = _Scalar(math.log(self._initial_temperature), self._device, self._counters[C_TEMP:C_TEMP + 1])
+        self._log_alpha = _Scalar(math.log(self._initial_alpha), self._device, self._counters[C_ALPHA:C_ALPHA + 1])
+
+    def _build_actor(self) -> None:
+        O, A = self._observation_shape[0], self._action_size
+        self._policy = DenseNet(O, self._actor_hidden, [("_mu", A), ("_logstd", A)], 1, self._device,
+                                trunk_prefix="_encoder.", with_target=True, seed_gen=self._gen)
+
+    def noise_layout(self, B):
+        """Reference draw order per update."""
+        A, N = self._action_size, self._n_action_samples
+        lay = {}
+        if self._temp_learning_rate > 0:
+            lay["temp"] = ("normal", (B, A))
+        if self._alpha_learning_rate > 0:
+            lay["alpha_t"] = ("normal", (N, B, A))
+            lay["alpha_tp1"] = ("normal", (N, B, A))
+            lay["alpha_rand"] = ("uniform", (B * N, A))
+        if self._soft_q_backup:
+            lay["soft"] = ("normal", (B, A))
+        lay["critic_t"] = ("normal", (N, B, A))
+        lay["critic_tp1"] = ("normal", (N, B, A))
+        lay["critic_rand"] = ("uniform", (B * N, A))
+        lay["actor"] = ("normal", (B, A))
+        return lay
+
+    # ------------------------------------------------------------------ program pieces
+    def _p_policy(self, db):
+        """Policy trunk + (mu|logstd) head on [obs; next_obs] (contiguous in the device batch)."""
+        B, O, A = db.B, db.O, self._action_size
+        acts = [self.ws(f"pi_act{i}", 1, 2 * B, h) for i, h in enumerate(self._actor_hidden)]
+        head = self.ws("pi_head", 1, 2 * B, 2 * A)
+        assert db.off["next_obs"] == db.off["obs"] + B * O, "obs/next_obs must be contiguous"
+        self._policy.forward("params", db.ptr("obs"), O, 0, 2 * B, acts, head, self._stream)
+        return acts, head
+
+    def _p_temp(self, db, head):
+        """update_temp (sac_impl.py:123-146)."""
+        B, A, L, st = db.B, self._action_size, self._lib, self._stream
+        lp = self.ws("temp_lp", B)
+        L.policy_sample_rows(head.data_ptr(), 2 * A, self.noise_view("temp", B).data_ptr(), None, 0, None, 0, None,
+                             lp.data_ptr(), B, 1, 0, A, MIN_LOGSTD, MAX_LOGSTD, 0, st)
+        self._allreduce_pre_scalar(lp, B)
+        t = self._log_temp
+        L.sac_temp_loss(lp.data_ptr(), t.ptr("p"), B, A, 1.0 / (B * self.world_size), self.metric_ptr(M_TEMP_LOSS), t.ptr("g"), 0, st)
+        self._allreduce_scalar_grad(t, M_TEMP_LOSS)
+        L.scalar_adam(t.ptr("p"), t.ptr("g"), t.ptr("m"), t.ptr("v"), self.counter_ptr(C_TEMP),
+                      self._temp_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_TEMP), st)
+
+    def _p_rows(self, db, head, tag):
+        """Critic input rows [data | pi(s_t) | pi(s_t+1) | random] at obs_t (cql_impl.py:143-204)."""
+        B, O, A, N, L, st = db.B, db.O, self._action_size, self._n_action_samples, self._lib, self._stream
+        R = B * (1 + 3 * N)
+        ld = O + A
+        x = self.ws("x_is", R, ld)
+        lp = self.ws("lp_is", 2, B * N)
+        xp = x.data_ptr()
+        L.concat_rows(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, xp, ld, B, 1, O, A, st)
+        L.policy_sample_rows(head.data_ptr(), 2 * A, self.noise_view(f"{tag}_t", B).data_ptr(), db.ptr("obs"), O,
+                             xp + 4 * ld * B, ld, None, lp.data_ptr(), B, N, O, A, MIN_LOGSTD, MAX_LOGSTD, 0, st)
+        L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, self.noise_view(f"{tag}_tp1", B).data_ptr(),
+                             db.ptr("obs"), O, xp + 4 * ld * (B + B * N), ld, None, lp.data_ptr() + 4 * B * N, B, N, O,
+                             A, MIN_LOGSTD, MAX_LOGSTD, 0, st)
+        L.concat_rows(db.ptr("obs"), O, self.noise_view(f"{tag}_rand", B).data_ptr(), A, None, 0.0, 0.0, 0.0,
+                      xp + 4 * ld * (B + 2 * B * N), ld, B, N, O, A, st)
+        return x, lp, R
+
+    def _p_alpha(self, db, head):
+        """update_alpha (cql_impl.py:119-141): forward only — the alpha gradient needs no critic backward."""
+        B, A, N, L, st, E = db.B, self._action_size, self._n_action_samples, self._lib, self._stream, self._n_critics
+        x, lp, R = self._p_rows(db, head, "alpha")
+        _, q = self._critic_rows_forward("params", x, R, "is")
+        inv_b = 1.0 / (B * self.world_size)
+        la = self._log_alpha
+        L.critic_loss(q.data_ptr(), R, None, 0, 0, None, None, None, None, self._gamma, lp.data_ptr(),
+                      lp.data_ptr() + 4 * B * N, N, A, la.ptr("p"), self._conservative_weight, None, 0,
+                      self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, st)
+        self._allreduce(self._slots[32 + S_ALPHA:32 + S_ALPHA + 3])
+        L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
+                       self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
+        L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
+                      self._alpha_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_ALPHA), st)
+
+    def _p_target(self, db, head):
+        """compute_target (cql_impl.py:225-243): deterministic backup tanh(mu(s')) through target critics."""
+        B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
+        assert not self._soft_q_backup, "soft_q_backup is not implemented yet"
+        xt = self.ws("xt", B, O + A)
+        L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, None, db.ptr("next_obs"), O, xt.data_ptr(),
+                             O + A, None, None, B, 1, O, A, MIN_LOGSTD, MAX_LOGSTD, 1, st)
+        _, q_t = self._critic_rows_forward("target", xt, B, "tq")
+        return q_t
+
+    def _p_critic(self, db, head, q_t=None, q_tpn=None, backward=True, sync_target=True, conservative=True,
+                  td=True):
+        """compute_critic_loss (cql_impl.py:110-117) [+ backward + Adam (ddpg_impl.py:138-152)]."""
+        B, A, N, L, st, E = db.B, self._action_size, self._n_action_samples, self._lib, self._stream, self._n_critics
+        x, lp, R = self._p_rows(db, head, "critic")
+        acts, q = self._critic_rows_forward("params", x, R, "is")
+        dq = self.ws("is_dq", E, R)
+        inv_b = 1.0 / (B * self.world_size)
+        la = self._log_alpha
+        L.critic_loss(q.data_ptr(), R, q_t.data_ptr() if q_t is not None else None, B, E,
+                      q_tpn.data_ptr() if q_tpn is not None else None, db.ptr("rew"), db.ptr("term"),
+                      db.ptr("nsteps"), self._gamma, lp.data_ptr(), lp.data_ptr() + 4 * B * N, N if conservative else 0,
+                      A, la.ptr("p"), self._conservative_weight, dq.data_ptr(), R, self.sums_ptr(S_CRITIC), None, B, E,
+                      inv_b, 1 if td else 0, st)
+        self._allreduce(self._slots[32 + S_CRITIC:32 + S_CRITIC + 3])
+        L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
+                       self._alpha_threshold, 0, 1 if conservative else 0, self.metric_ptr(M_CRITIC), None, st)
+        if backward:
+            self._q_func.backward(x, self._q_func.in_dim, 0, R, acts, dq, self._critic_scratch(R), st, d_head_ld=1,
+                                  d_head_stride=R)
+            self._allreduce(self._q_func.arena.grads)
+            self._q_func.adam(self._critic_learning_rate, st, tau=self._tau if sync_target else None)
+
+    def _p_actor(self, db, acts_p, head, sync_target=True):
+        """compute_actor_loss (sac_impl.py:114-121) + backward + Adam (ddpg_impl.py:167-183)."""
+        B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics
+        xa = self.ws("xa", B, O + A)
+        lp = self.ws("a_lp", B)
+        eps = self.noise_view("actor", B)
+        L.policy_sample_rows(head.data_ptr(), 2 * A, eps.data_ptr(), db.ptr("obs"), O, xa.data_ptr(), O + A, None,
+                             lp.data_ptr(), B, 1, O, A, MIN_LOGSTD, MAX_LOGSTD, 0, st)
+        acts_c, q = self._critic_rows_forward("params", xa, B, "aq")
+        dq = self.ws("a_dq", E, B)
+        inv_b = 1.0 / (B * self.world_size)
+        t = self._log_temp
+        L.sac_actor_loss(q.data_ptr(), B, lp.data_ptr(), t.ptr("p"), dq.data_ptr(), B, self.sums_ptr(S_ACTOR), B, E,
+                         inv_b, st)
+        self._allreduce(self._slots[32 + S_ACTOR:32 + S_ACTOR + 1])
+        L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
+        dxa = self.ws("a_dx", E, B, A)
+        self._q_func.backward(xa, O + A, 0, B, acts_c, dq, self._critic_scratch(B), st, weight_grads=False, dx=dxa,
+                              lddx=A, stride_dx=B * A, dx_col0=O, dx_cols=A, d_head_ld=1, d_head_stride=B)
+        dhead = self.ws("pi_dhead", 1, B, 2 * A)
+        L.sac_actor_backward(head.data_ptr(), 2 * A, eps.data_ptr(), dxa.data_ptr(), A, B * A, E, t.ptr("p"),
+                             dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
+        # policy backward over the first B rows (obs_t) of the shared [obs; next_obs] forward
+        self._policy_backward_rows(db, acts_p, dhead, B)
+        self._allreduce(self._policy.arena.grads)
+        self._policy.adam(self._actor_learning_rate, st, tau=self._tau if sync_target else None)
+
+    def _policy_backward_rows(self, db, acts_p, dhead, B):
+        """acts_p hold 2B rows ([obs; next_obs]); E == 1 so the first B rows are a contiguous prefix."""
+        self._policy.backward(db.ptr("obs"), db.O, 0, B, acts_p, dhead, self._policy_scratch(B), self._stream)
+
+    def _allreduce(self, t):
+        if self.world_size > 1:
+            from ...parallel import allreduce_sum
+
+            allreduce_sum(t, self._stream_obj)
+
+    def _allreduce_pre_scalar(self, lp, B):
+        pass
+
+    def _allreduce_scalar_grad(self, scalar, metric_slot):
+        if self.world_size > 1:
+            from ...parallel import allreduce_sum
+
+            allreduce_sum(scalar.buf[4:5], self._stream_obj)
+            allreduce_sum(self._slots[metric_slot:metric_slot + 1], self._stream_obj)
+
+    # ------------------------------------------------------------------ fused update (CQL._update, cql.py:234-258)
+    def update_fused(self, batch):
+        db = self.load_batch(batch)
+        do_temp, do_alpha = self._temp_learning_rate > 0, self._alpha_learning_rate > 0
+
+        def program():
+            ticks = [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else [])
+            self._tick(*ticks)
+            self.zero_slots()
+            self.fill_noise(db.B)
+            acts_p, head = self._p_policy(db)
+            if do_temp:
+                self._p_temp(db, head)
+            if do_alpha:
+                self._p_alpha(db, head)
+            q_t = self._p_target(db, head)
+            self._p_critic(db, head, q_t=q_t)
+            self._p_actor(db, acts_p, head)
+
+        self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected), program)
+        names = []
+        if do_temp:
+            names += [(M_TEMP_LOSS, "temp_loss"), (M_TEMP, "temp")]
+        if do_alpha:
+            names += [(M_ALPHA_LOSS, "alpha_loss"), (M_ALPHA, "alpha")]
+        names += [(M_CRITIC, "critic_loss"), (M_ACTOR, "actor_loss")]
+        return self._metrics_dict(names)
+
+    # ------------------------------------------------------------------ reference hooks (eager, one sync each)
+    def _begin(self, batch, *ticks):
+        db = self.load_batch(batch)
+        if ticks:
+            self._tick(*ticks)
+        self.zero_slots()
+        self.fill_noise(db.B)
+        return db
+
+    def update_temp(self, batch):
+        db = self._begin(batch, C_DRAW, C_TEMP)
+        _, head = self._p_policy(db)
+        self._p_temp(db, head)
+        v = self.read_slots()
+        return v[M_TEMP_LOSS].copy(), v[M_TEMP].copy()
+
+    def update_alpha(self, batch):
+        db = self._begin(batch, C_DRAW, C_ALPHA)
+        _, head = self._p_policy(db)
+        self._p_alpha(db, head)
+        v = self.read_slots()
+        return v[M_ALPHA_LOSS].copy(), v[M_ALPHA].copy()
+
+    def compute_target(self, batch) -> torch.Tensor:
+        db = self._begin(batch)
+        _, head = self._p_policy(db)
+        q_t = self._p_target(db, head)
+        self.sync()
+        return q_t.min(dim=0).values.view(-1, 1).clone()
+
+    def compute_critic_loss(self, batch, q_tpn: torch.Tensor) -> torch.Tensor:
+        db = self._begin(batch)
+        _, head = self._p_policy(db)
+        self._p_critic(db, head, q_tpn=q_tpn.to(self._device).reshape(-1).contiguous(), backward=False)
+        self.sync()
+        return self._slots[M_CRITIC].clone()
+
+    def _compute_conservative_loss(self, obs_t=None, act_t=None, obs_tp1=None, batch=None) -> torch.Tensor:
+        """cql_impl.py:196-223.  Accepts either the reference's three tensors or a minibatch."""
+        if batch is None:
+            batch = _TensorBatch(obs_t, act_t, obs_tp1)
+        db = self._begin(batch)
+        _, head = self._p_policy(db)
+        self._p_critic(db, head, q_tpn=self.ws("zero_tpn", db.B), backward=False, td=False)
+        self.sync()
+        return self._slots[M_CRITIC].clone()
+
+    def update_critic(self, batch) -> np.ndarray:
+        db = self._begin(batch, C_DRAW, C_CRITIC)
+        _, head = self._p_policy(db)
+        q_t = self._p_target(db, head)
+        self._p_critic(db, head, q_t=q_t, sync_target=False)
+        return self.read_slots()[M_CRITIC].copy()
+
+    def compute_actor_loss(self, batch) -> torch.Tensor:
+        raise NotImplementedError("use update_actor(); the standalone loss hook is not split out yet")
+
+    def update_actor(self, batch) -> np.ndarray:
+        db = self._begin(batch, C_DRAW, C_ACTOR)
+        acts_p, head = self._p_policy(db)
+        self._p_actor(db, acts_p, head, sync_target=False)
+        return self.read_slots()[M_ACTOR].copy()
+
+
+class _TensorBatch:
+    """Adapter so the three-tensor `_compute_conservative_loss(obs_t, act_t, obs_tp1)` signature can
+    reuse the minibatch staging path."""
+
+    def __init__(self, obs_t, act_t, obs_tp1):
+        n = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        self.observations, self.actions, self.next_observations = n(obs_t), n(act_t), n(obs_tp1)
+        B = self.observations.shape[0]
+        self.rewards = np.zeros((B, 1), np.float32)
+        self.terminals = np.zeros((B, 1), np.float32)
+        self.n_steps = np.ones((B, 1), np.float32)

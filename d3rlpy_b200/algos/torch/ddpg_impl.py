@@ -1,0 +1,141 @@
+"""Actor-critic impl base: critic ensemble + policy over flat arenas; mirrors DDPGBaseImpl
+(d3rlpy/algos/torch/ddpg_impl.py:29-229) — same hook names, hand-written backward instead of
+autograd, one launch per layer for all ensemble members."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from ...nets import DenseNet
+from .base import ImplBase
+
+# counter slots (device int32): 0 = noise epoch; the rest are Adam step counts
+C_DRAW, C_CRITIC, C_ACTOR, C_TEMP, C_ALPHA, C_IMITATOR = 0, 1, 2, 3, 4, 5
+
+
+class _ModuleView:
+    """Minimal stand-in for the nn.Module the reference exposes through `impl.q_function` /
+    `impl.policy`: `state_dict()`, `load_state_dict()`, `parameters()` over arena views."""
+
+    def __init__(self, net: DenseNet, which: str = "params"):
+        self._net, self._which = net, which
+
+    def state_dict(self):
+        return self._net.arena.state_dict(self._which)
+
+    def load_state_dict(self, sd):
+        self._net.arena.load_state_dict(sd, self._which)
+
+    def parameters(self):
+        return list(self.state_dict().values())
+
+
+class _OptimView:
+    """`torch.optim.Adam.state_dict()`-shaped view of the fused optimizer state."""
+
+    def __init__(self, net: DenseNet, lr: float):
+        self._net, self.lr = net, lr
+
+    def state_dict(self):
+        a = self._net.arena
+        keys = list(a.state_dict().keys())
+        m, v = a.state_dict("exp_avg"), a.state_dict("exp_avg_sq")
+        step = int(a.step.item())
+        state = {i: {"step": torch.tensor(float(step)), "exp_avg": m[k], "exp_avg_sq": v[k]} for i, k in enumerate(keys)}
+        return {"state": state if step > 0 else {},
+                "param_groups": [{"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0,
+                                  "amsgrad": False, "params": list(range(len(keys)))}]}
+
+
+class DDPGBaseImpl(ImplBase):
+    def __init__(self, observation_shape, action_size, actor_learning_rate, critic_learning_rate,
+                 actor_hidden: Sequence[int], critic_hidden: Sequence[int], gamma, tau, n_critics, use_gpu=0,
+                 scaler=None, action_scaler=None, reward_scaler=None, seed: int = 0, **kw):
+        super().__init__(observation_shape, action_size, use_gpu, scaler, action_scaler, reward_scaler, **kw)
+        assert len(self._observation_shape) == 1, "vector observations only for actor-critic impls"
+        self._actor_learning_rate, self._critic_learning_rate = actor_learning_rate, critic_learning_rate
+        self._actor_hidden, self._critic_hidden = list(actor_hidden), list(critic_hidden)
+        self._gamma, self._tau, self._n_critics = gamma, tau, n_critics
+        self._gen = torch.Generator().manual_seed(seed)
+        self._seed = seed
+        self._q_func: Optional[DenseNet] = None
+        self._policy: Optional[DenseNet] = None
+
+    # ------------------------------------------------------------------ build
+    def build(self) -> None:
+        O, A = self._observation_shape[0], self._action_size
+        self._q_func = DenseNet(O + A, self._critic_hidden, [("_fc", 1)], self._n_critics, self._device,
+                                trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}", with_target=True,
+                                seed_gen=self._gen)
+        self._build_actor()
+        self._q_func.arena.step = self._counters[C_CRITIC:C_CRITIC + 1]
+        self._policy.arena.step = self._counters[C_ACTOR:C_ACTOR + 1]
+
+    def _build_actor(self) -> None:
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ reference-visible properties
+    @property
+    def policy(self):
+        return _ModuleView(self._policy)
+
+    @property
+    def targ_policy(self):
+        return _ModuleView(self._policy, "target")
+
+    @property
+    def q_function(self):
+        return _ModuleView(self._q_func)
+
+    @property
+    def targ_q_function(self):
+        return _ModuleView(self._q_func, "target")
+
+    @property
+    def policy_optim(self):
+        return _OptimView(self._policy, self._actor_learning_rate)
+
+    @property
+    def q_function_optim(self):
+        return _OptimView(self._q_func, self._critic_learning_rate)
+
+    # ------------------------------------------------------------------ shared program pieces
+    def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0):
+        """Runs the critic trunk+head on `rows` shared input rows; returns (acts, q[E,rows])."""
+        E = members or self._n_critics
+        acts = [self.ws(f"{tag}_act{i}", E, rows, h) for i, h in enumerate(self._critic_hidden)]
+        q = self.ws(f"{tag}_q", E, rows)
+        self._q_func.forward(which, x, self._q_func.in_dim, 0, rows, acts, q, self._stream, members=E,
+                             member0=member0)
+        return acts, q
+
+    def _critic_scratch(self, rows: int, members=None):
+        E = members or self._n_critics
+        hm = max(self._critic_hidden)
+        return (self.ws("c_scr0", E, rows, hm), self.ws("c_scr1", E, rows, hm))
+
+    def _policy_scratch(self, rows: int):
+        hm = max(self._actor_hidden)
+        return (self.ws("p_scr0", 1, rows, hm), self.ws("p_scr1", 1, rows, hm))
+
+    def update_critic_target(self) -> None:
+        """soft_sync(targ_q_func, q_func, tau) (ddpg_impl.py:201-204)."""
+        a = self._q_func.arena
+        self._lib.soft_sync(a.target.data_ptr(), a.params.data_ptr(), a.size, self._tau, self._stream)
+
+    def update_actor_target(self) -> None:
+        """soft_sync(targ_policy, policy, tau) (ddpg_impl.py:206-209)."""
+        a = self._policy.arena
+        self._lib.soft_sync(a.target.data_ptr(), a.params.data_ptr(), a.size, self._tau, self._stream)
+
+    def _tick(self, *slots):
+        mask = 0
+        for s in slots:
+            mask |= 1 << s
+        self._lib.tick(self._counters.data_ptr(), self.N_COUNTERS, mask, self._stream)
+
+    def _metrics_dict(self, names):
+        vals = self.read_slots()
+        return {n: np.float32(vals[i]) for i, n in names}

@@ -1,0 +1,152 @@
+"""TD3+BC on B200: mirrors TD3PlusBCImpl/TD3Impl/DDPGImpl
+(d3rlpy/algos/torch/td3_plus_bc_impl.py:16-70, td3_impl.py:15-78, ddpg_impl.py:138-209)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ...nets import DenseNet
+from .ddpg_impl import C_ACTOR, C_CRITIC, C_DRAW, DDPGBaseImpl
+
+M_CRITIC, M_ACTOR = 0, 1
+S_TD, S_ACT = 0, 4  # sums slots: TD uses [0..2], actor stats [4..6]
+
+
+class TD3PlusBCImpl(DDPGBaseImpl):
+    def __init__(self, *, target_smoothing_sigma=0.2, target_smoothing_clip=0.5, alpha=2.5, **kw):
+        super().__init__(**kw)
+        self._target_smoothing_sigma = target_smoothing_sigma
+        self._target_smoothing_clip = target_smoothing_clip
+        self._alpha = alpha
+
+    def _build_actor(self) -> None:
+        O, A = self._observation_shape[0], self._action_size
+        self._policy = DenseNet(O, self._actor_hidden, [("_fc", A)], 1, self._device, trunk_prefix="_encoder.",
+                                with_target=True, seed_gen=self._gen)
+
+    def noise_layout(self, B):
+        return {"target": ("normal", (B, self._action_size))}
+
+    # ------------------------------------------------------------------ program pieces
+    def _p_target(self, db):
+        """TD3Impl.compute_target (td3_impl.py:61-78) -> q_t[E,B] (min is taken inside critic_loss)."""
+        B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
+        acts = [self.ws(f"tp_act{i}", 1, B, h) for i, h in enumerate(self._actor_hidden)]
+        a_next = self.ws("tp_a", 1, B, A)
+        self._policy.forward("target", db.ptr("next_obs"), O, 0, B, acts, a_next, st, head_tanh=True)
+        xt = self.ws("xt", B, O + A)
+        L.concat_rows(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
+                      self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt.data_ptr(), O + A, B, 1, O, A,
+                      st)
+        _, q_t = self._critic_rows_forward("target", xt, B, "tq")
+        return q_t
+
+    def _p_critic(self, db, q_t=None, q_tpn=None, sync_target=False):
+        B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics
+        xc = self.ws("xc", B, O + A)
+        L.concat_rows(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, xc.data_ptr(), O + A, B, 1, O, A, st)
+        acts, q = self._critic_rows_forward("params", xc, B, "cq")
+        dq = self.ws("dq", E, B)
+        inv_b = 1.0 / (B * self.world_size)
+        L.critic_loss(q.data_ptr(), B, q_t.data_ptr() if q_t is not None else None, B, E,
+                      q_tpn.data_ptr() if q_tpn is not None else None, db.ptr("rew"), db.ptr("term"),
+                      db.ptr("nsteps"), self._gamma, None, None, 0, A, None, 0.0, dq.data_ptr(), B,
+                      self.sums_ptr(S_TD), None, B, E, inv_b, 1, st)
+        L.cql_finalize(self.sums_ptr(S_TD), None, inv_b, E, 0.0, 0.0, 0, 0, self.metric_ptr(M_CRITIC), None, st)
+        return xc, acts, dq
+
+    def _p_critic_step(self, db, xc, acts, dq, sync_target):
+        B = db.B
+        self._q_func.backward(xc, self._q_func.in_dim, 0, B, acts, dq, self._critic_scratch(B), self._stream,
+                              d_head_ld=1, d_head_stride=B)
+        self._allreduce(self._q_func.arena.grads)
+        self._q_func.adam(self._critic_learning_rate, self._stream, tau=self._tau if sync_target else None)
+
+    def _p_actor(self, db):
+        """compute_actor_loss (td3_plus_bc_impl.py:64-70) + backward + Adam; only member 0 is evaluated."""
+        B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
+        acts_p = [self.ws(f"pi_act{i}", 1, B, h) for i, h in enumerate(self._actor_hidden)]
+        a = self.ws("pi_a", 1, B, A)
+        self._policy.forward("params", db.ptr("obs"), O, 0, B, acts_p, a, st, head_tanh=True)
+        xa = self.ws("xa", B, O + A)
+        L.concat_rows(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa.data_ptr(), O + A, B, 1, O, A, st)
+        acts_c, q0 = self._critic_rows_forward("params", xa, B, "aq", members=1)
+        L.td3bc_actor_stats(q0.data_ptr(), a.data_ptr(), A, db.ptr("act"), A, self.sums_ptr(S_ACT), B, A, st)
+        self._allreduce(self._slots[32 + S_ACT:32 + S_ACT + 3])
+        inv_b = 1.0 / (B * self.world_size)
+        dq = self.ws("a_dq", 1, B)
+        L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq.data_ptr(), B, B, 1,
+                           self.metric_ptr(M_ACTOR), st)
+        dxa = self.ws("a_dx", B, A)
+        self._q_func.backward(xa, O + A, 0, B, acts_c, dq, self._critic_scratch(B, 1), st, weight_grads=False,
+                              dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O, dx_cols=A, members=1, d_head_ld=1,
+                              d_head_stride=B)
+        dz = self.ws("pi_dz", 1, B, A)
+        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, inv_b, st)
+        self._policy.backward(db.ptr("obs"), O, 0, B, acts_p, dz, self._policy_scratch(B), st)
+        self._allreduce(self._policy.arena.grads)
+        self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
+
+    def _allreduce(self, t):
+        if self.world_size > 1:
+            from ...parallel import allreduce_sum
+
+            allreduce_sum(t, self._stream_obj)
+
+    # ------------------------------------------------------------------ fused update (TD3PlusBC._update)
+    def update_fused(self, batch, actor_step: bool):
+        db = self.load_batch(batch)
+
+        def program():
+            self._tick(C_DRAW, C_CRITIC, *([C_ACTOR] if actor_step else []))
+            self.zero_slots()
+            self.fill_noise(db.B)
+            q_t = self._p_target(db)
+            xc, acts, dq = self._p_critic(db, q_t=q_t)
+            self._p_critic_step(db, xc, acts, dq, sync_target=actor_step)
+            if actor_step:
+                self._p_actor(db)
+
+        self.run_program(("td3bc", db.B, actor_step, self._noise_injected), program)
+        names = [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
+        return self._metrics_dict(names)
+
+    # ------------------------------------------------------------------ reference hooks (eager)
+    def compute_target(self, batch) -> torch.Tensor:
+        db = self.load_batch(batch)
+        self.fill_noise(db.B)
+        q_t = self._p_target(db)
+        self.sync()
+        return q_t.min(dim=0).values.view(-1, 1).clone()
+
+    def compute_critic_loss(self, batch, q_tpn: torch.Tensor) -> torch.Tensor:
+        db = self.load_batch(batch)
+        self.zero_slots()
+        self._p_critic(db, q_tpn=q_tpn.to(self._device).reshape(-1).contiguous())
+        self.sync()
+        return self._slots[M_CRITIC].clone()
+
+    def update_critic(self, batch) -> np.ndarray:
+        db = self.load_batch(batch)
+        self._tick(C_DRAW, C_CRITIC)
+        self.zero_slots()
+        self.fill_noise(db.B)
+        q_t = self._p_target(db)
+        xc, acts, dq = self._p_critic(db, q_t=q_t)
+        self._p_critic_step(db, xc, acts, dq, sync_target=False)
+        return self.read_slots()[M_CRITIC].copy()
+
+    def update_actor(self, batch) -> np.ndarray:
+        db = self.load_batch(batch)
+        self._tick(C_ACTOR)
+        self.zero_slots()
+        saved = self._tau
+        self._p_actor_no_sync(db)
+        return self.read_slots()[M_ACTOR].copy()
+
+    def _p_actor_no_sync(self, db):
+        tau, self._tau = self._tau, None
+        try:
+            self._p_actor(db)
+        finally:
+            self._tau = tau

@@ -1,0 +1,165 @@
+// Narrow output heads (out_features <= 32): Q head (256->1), policy mu|logstd (256->2A), VAE heads,
+// discrete Q head (512->A).  These are GEMV-shaped, so they run as warp-shuffle reductions instead of
+// wasting GEMM tiles.  Replaces the `_fc` / `_mu` / `_logstd` nn.Linear calls of
+//   d3rlpy/models/torch/q_functions/mean_q_function.py:21,24,69,72
+//   d3rlpy/models/torch/policies.py:55-59,92-97,153-181
+//   d3rlpy/models/torch/imitators.py:45-54,63-72
+#include "common.cuh"
+
+namespace d3b {
+
+constexpr int HEAD_MAX_N = 32;
+
+// One warp per (member,row).  Y[e][m][n] = act(X[e][m][:] . W[e][n][:] + b[e][n])
+__global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ X, long long ldx, long long sX,
+                                                           const float* __restrict__ W, long long ldw, long long sW,
+                                                           const float* __restrict__ bias, long long sB,
+                                                           float* __restrict__ Y, long long ldy, long long sY, int M,
+                                                           int N, int K, int E, int act_tanh) {
+  int lane = threadIdx.x & 31;
+  long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)M * E) return;
+  int e = (int)(wid / M), m = (int)(wid % M);
+  const float* x = X + (long long)e * sX + (long long)m * ldx;
+  const float* w = W + (long long)e * sW;
+  float mine = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* wr = w + (long long)n * ldw;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + k), __ldg(wr + k), s);
+    s = warp_sum(s);
+    if (lane == n) mine = s;
+  }
+  if (lane < N) {
+    float v = mine + (bias ? __ldg(bias + (long long)e * sB + lane) : 0.f);
+    if (act_tanh) v = tanhf(v);
+    Y[(long long)e * sY + (long long)m * ldy + lane] = v;
+  }
+}
+
+// dX[e][m][k] = (sum_n dY[e][m][n] W[e][n][k]) * [src[e][m][k] > 0]
+__global__ void __launch_bounds__(256) head_backward_data_kernel(
+    const float* __restrict__ dY, long long lddy, long long sdY, const float* __restrict__ W, long long ldw,
+    long long sW, float* __restrict__ dX, long long lddx, long long sdX, const float* __restrict__ src,
+    long long ldsrc, long long sSrc, int M, int N, int K, int E) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)E * M * K;
+  if (idx >= total) return;
+  int k = (int)(idx % K);
+  long long t = idx / K;
+  int m = (int)(t % M), e = (int)(t / M);
+  const float* dy = dY + (long long)e * sdY + (long long)m * lddy;
+  const float* w = W + (long long)e * sW + k;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(__ldg(dy + n), __ldg(w + (long long)n * ldw), s);
+  if (src && !(__ldg(src + (long long)e * sSrc + (long long)m * ldsrc + k) > 0.f)) s = 0.f;
+  dX[(long long)e * sdX + (long long)m * lddx + k] = s;
+}
+
+// dW[e][n][k] += sum_m dY[e][m][n] X[e][m][k];  db[e][n] += sum_m dY[e][m][n]
+// grid: (ceil(K/256), row chunks, E); dY chunk staged in shared memory.
+template <int NMAX>
+__global__ void __launch_bounds__(256) head_backward_weight_kernel(
+    const float* __restrict__ dY, long long lddy, long long sdY, const float* __restrict__ X, long long ldx,
+    long long sX, float* __restrict__ dW, long long lddw, long long sdW, float* __restrict__ db, long long sdb, int M,
+    int N, int K, int rows_per_block) {
+  extern __shared__ float sdy[];  // [rows_per_block][N]
+  int e = blockIdx.z;
+  int m0 = blockIdx.y * rows_per_block;
+  int rows = min(rows_per_block, M - m0);
+  const float* dy = dY + (long long)e * sdY + (long long)m0 * lddy;
+  for (int i = threadIdx.x; i < rows * N; i += blockDim.x) {
+    int r = i / N, n = i % N;
+    sdy[i] = __ldg(dy + (long long)r * lddy + n);
+  }
+  __syncthreads();
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    const float* x = X + (long long)e * sX + (long long)m0 * ldx + k;
+    for (int r = 0; r < rows; ++r) {
+      float xv = __ldg(x + (long long)r * ldx);
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(sdy[r * N + n], xv, acc[n]);
+    }
+    float* dw = dW + (long long)e * sdW + k;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) atomicAdd(dw + (long long)n * lddw, acc[n]);
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < N) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += sdy[r * N + threadIdx.x];
+    atomicAdd(db + (long long)e * sdb + threadIdx.x, s);
+  }
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+extern "C" int d3b_head_forward(const float* x, int64_t ldx, int64_t stride_x, const float* w, int64_t ldw,
+                                int64_t stride_w, const float* bias, int64_t stride_b, float* y, int64_t ldy,
+                                int64_t stride_y, int rows, int out_features, int in_features, int members,
+                                int act_tanh, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0, "head_forward: bad sizes");
+  D3B_REQUIRE(out_features >= 1 && out_features <= HEAD_MAX_N, "head_forward: out_features %d not in 1..%d",
+              out_features, HEAD_MAX_N);
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(x && w && y, "head_forward: null pointer");
+  long long warps = (long long)rows * members;
+  head_forward_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features, in_features, members,
+      act_tanh);
+  return check_launch("head_forward");
+}
+
+extern "C" int d3b_head_backward_data(const float* dy, int64_t lddy, int64_t stride_dy, const float* w, int64_t ldw,
+                                      int64_t stride_w, float* dx, int64_t lddx, int64_t stride_dx,
+                                      const float* relu_src, int64_t ld_src, int64_t stride_src, int rows,
+                                      int out_features, int in_features, int members, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0 && out_features >= 1, "head_backward_data: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dy && w && dx, "head_backward_data: null pointer");
+  long long total = (long long)rows * in_features * members;
+  head_backward_data_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      dy, lddy, stride_dy, w, ldw, stride_w, dx, lddx, stride_dx, relu_src, ld_src, stride_src, rows, out_features,
+      in_features, members);
+  return check_launch("head_backward_data");
+}
+
+extern "C" int d3b_head_backward_weight(const float* dy, int64_t lddy, int64_t stride_dy, const float* x,
+                                        int64_t ldx, int64_t stride_x, float* dw, int64_t lddw, int64_t stride_dw,
+                                        float* dbias, int64_t stride_db, int rows, int out_features, int in_features,
+                                        int members, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0, "head_backward_weight: bad sizes");
+  D3B_REQUIRE(out_features >= 1 && out_features <= HEAD_MAX_N, "head_backward_weight: out_features %d not in 1..%d",
+              out_features, HEAD_MAX_N);
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dy && x && dw, "head_backward_weight: null pointer");
+  int kblocks = ceil_div(in_features, 256);
+  int rpb = rows / (2 * kNumSM / (kblocks * members) + 1);
+  if (rpb < 4) rpb = 4;
+  if (rpb > 64) rpb = 64;
+  dim3 grid(kblocks, ceil_div(rows, rpb), members);
+  size_t smem = (size_t)rpb * out_features * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_features <= 1)
+    head_backward_weight_kernel<1><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw, stride_dw,
+                                                            dbias, stride_db, rows, out_features, in_features, rpb);
+  else if (out_features <= 8)
+    head_backward_weight_kernel<8><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw, stride_dw,
+                                                            dbias, stride_db, rows, out_features, in_features, rpb);
+  else if (out_features <= 16)
+    head_backward_weight_kernel<16><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw,
+                                                             stride_dw, dbias, stride_db, rows, out_features,
+                                                             in_features, rpb);
+  else
+    head_backward_weight_kernel<32><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw,
+                                                             stride_dw, dbias, stride_db, rows, out_features,
+                                                             in_features, rpb);
+  return check_launch("head_backward_weight");
+}

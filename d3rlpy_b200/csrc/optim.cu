@@ -1,0 +1,214 @@
+// K10: fused multi-tensor Adam (+ optional Polyak soft_sync in the same pass), hard_sync, step
+// counters and the Philox noise fill.  HBM-bandwidth bound: one pass over flat parameter arenas
+// (28 B/param for Adam, +8 B/param when the target arena is synced in the same pass).
+//
+// Adam arithmetic restates torch 2.11 `_single_tensor_adam`, the optimizer the
+// reference builds through AdamFactory (d3rlpy/models/optimizers.py:106-138):
+//   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); denom = sqrt(v)/sqrt(1-b2^t) + eps;
+//   p.addcdiv_(m, denom, value=-lr/(1-b1^t))
+// soft_sync restates d3rlpy/torch_utility.py:27-33 (two separately-rounded steps).
+#include "common.cuh"
+
+namespace d3b {
+
+struct AdamScalars {
+  float one_minus_b1, b2, one_minus_b2, eps, neg_step_size, inv_bc2_sqrt_den;  // den: divide by bc2_sqrt
+};
+
+__device__ __forceinline__ void adam_scalars(const int* step, double lr, double b1, double b2, double eps,
+                                             float& w1, float& fb2, float& w2, float& feps, float& neg_ss,
+                                             float& bc2_sqrt) {
+  int t = *step;
+  double bc1 = 1.0 - pow(b1, (double)t);
+  double bc2 = 1.0 - pow(b2, (double)t);
+  w1 = (float)(1.0 - b1);
+  fb2 = (float)b2;
+  w2 = (float)(1.0 - b2);
+  feps = (float)eps;
+  neg_ss = (float)(-(lr / bc1));
+  bc2_sqrt = (float)sqrt(bc2);
+}
+
+__device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float w1, float fb2, float w2,
+                                          float feps, float neg_ss, float bc2_sqrt) {
+  // lerp (weight < 0.5 branch of ATen's lerp; its vectorised CPU form is fmadd(w, g - m, m))
+  m = __fmaf_rn(w1, __fsub_rn(g, m), m);
+  v = __fmul_rn(v, fb2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(w2, g), g));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), feps);
+  return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_ss, m), denom));
+}
+
+// grid-stride, float4 main body + scalar tail.  `targ` (nullable) gets soft-synced with the NEW p.
+// grads are zeroed after use so the next backward can accumulate with atomics (wgrad split-K).
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   float* __restrict__ targ, long long n, const int* step, double lr,
+                                                   double b1, double b2, double eps, float tau, int zero_grad) {
+  float w1, fb2, w2, feps, neg_ss, bc2s;
+  adam_scalars(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
+  long long n4 = n >> 2;
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += stride) {
+    float4 P = ((float4*)p)[i], G = ((float4*)g)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+    P.x = adam_one(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.y = adam_one(P.y, G.y, M.y, V.y, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.z = adam_one(P.z, G.z, M.z, V.z, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.w = adam_one(P.w, G.w, M.w, V.w, w1, fb2, w2, feps, neg_ss, bc2s);
+    ((float4*)p)[i] = P;
+    ((float4*)m)[i] = M;
+    ((float4*)v)[i] = V;
+    if (zero_grad) ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (targ) {
+      float4 T = ((float4*)targ)[i];
+      T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(tau, P.x));
+      T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(tau, P.y));
+      T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(tau, P.z));
+      T.w = __fadd_rn(__fmul_rn(T.w, one_m_tau), __fmul_rn(tau, P.w));
+      ((float4*)targ)[i] = T;
+    }
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += stride) {
+    float M = m[i], V = v[i];
+    float P = adam_one(p[i], g[i], M, V, w1, fb2, w2, feps, neg_ss, bc2s);
+    p[i] = P;
+    m[i] = M;
+    v[i] = V;
+    if (zero_grad) g[i] = 0.f;
+    if (targ) targ[i] = __fadd_rn(__fmul_rn(targ[i], one_m_tau), __fmul_rn(tau, P));
+  }
+}
+
+__global__ void __launch_bounds__(256) soft_sync_kernel(float* __restrict__ targ, const float* __restrict__ p,
+                                                        long long n, float tau) {
+  float one_m_tau = (float)(1.0 - (double)tau);
+  long long n4 = n >> 2;
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += stride) {
+    float4 T = ((float4*)targ)[i];
+    float4 P = __ldg((const float4*)p + i);
+    T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(tau, P.x));
+    T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(tau, P.y));
+    T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(tau, P.z));
+    T.w = __fadd_rn(__fmul_rn(T.w, one_m_tau), __fmul_rn(tau, P.w));
+    ((float4*)targ)[i] = T;
+  }
+  for (long long i = (n4 << 2) + tid; i < n; i += stride)
+    targ[i] = __fadd_rn(__fmul_rn(targ[i], one_m_tau), __fmul_rn(tau, __ldg(p + i)));
+}
+
+__global__ void tick_kernel(int* counters, int n, unsigned mask) {
+  int i = threadIdx.x;
+  if (i < n && ((mask >> i) & 1u)) counters[i] += 1;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 noise fill
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// segment layout: first n_normal floats ~ N(0,1), next n_uniform floats ~ U(-1,1).
+// counter = (*draw_counter) so that graph replays advance the stream; bumped by tick_kernel.
+__global__ void __launch_bounds__(256) noise_fill_kernel(float* __restrict__ out, long long n_normal,
+                                                         long long n_uniform, unsigned long long seed,
+                                                         const int* draw_counter) {
+  long long n = n_normal + n_uniform;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call -> 4 floats
+  long long stride = (long long)gridDim.x * blockDim.x;
+  uint32_t epoch = (uint32_t)(*draw_counter);
+  for (; (q << 2) < n; q += stride) {
+    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), epoch, 0x5eedu};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float r[4];
+    long long base = q << 2;
+    // Box-Muller on pairs; uniform section gets 2u-1
+    float u0 = u01(c[0]), u1 = u01(c[1]), u2 = u01(c[2]), u3 = u01(c[3]);
+    float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.f * u1, &s0, &c0);
+    sincospif(2.f * u3, &s1, &c1);
+    float nrm[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+    float uni[4] = {2.f * u0 - 1.f, 2.f * u1 - 1.f, 2.f * u2 - 1.f, 2.f * u3 - 1.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      long long i = base + j;
+      r[j] = (i < n_normal) ? nrm[j] : uni[j];
+      if (i < n) out[i] = r[j];
+    }
+  }
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+
+static int grid_for(long long n, int per_thread) {
+  long long blocks = ceil_div_ll(n, 256LL * per_thread);
+  long long cap = (long long)kNumSM * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+extern "C" int d3b_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target,
+                             int64_t n, const int* step, double lr, double beta1, double beta2, double eps,
+                             float tau, int zero_grad, void* stream) {
+  D3B_REQUIRE(n >= 0, "adam_step: n < 0");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(params && grads && exp_avg && exp_avg_sq && step, "adam_step: null pointer");
+  D3B_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
+               (uintptr_t)target) % 16 == 0,
+              "adam_step: arenas must be 16-byte aligned");
+  adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
+                                                                lr, beta1, beta2, eps, tau, zero_grad);
+  return check_launch("adam_step");
+}
+
+extern "C" int d3b_soft_sync(float* target, const float* params, int64_t n, float tau, void* stream) {
+  D3B_REQUIRE(n >= 0, "soft_sync: n < 0");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(target && params, "soft_sync: null pointer");
+  D3B_REQUIRE(((uintptr_t)target | (uintptr_t)params) % 16 == 0, "soft_sync: arenas must be 16-byte aligned");
+  soft_sync_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(target, params, n, tau);
+  return check_launch("soft_sync");
+}
+
+extern "C" int d3b_hard_sync(float* target, const float* params, int64_t n, void* stream) {
+  D3B_REQUIRE(n >= 0, "hard_sync: n < 0");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(target && params, "hard_sync: null pointer");
+  D3B_CUDA(cudaMemcpyAsync(target, params, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_tick(int* counters, int n, unsigned mask, void* stream) {
+  D3B_REQUIRE(counters && n > 0 && n <= 32, "tick: need 1..32 counters");
+  tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, n, mask);
+  return check_launch("tick");
+}
+
+extern "C" int d3b_noise_fill(float* out, int64_t n_normal, int64_t n_uniform, uint64_t seed,
+                              const int* draw_counter, void* stream) {
+  D3B_REQUIRE(n_normal >= 0 && n_uniform >= 0, "noise_fill: negative count");
+  long long n = n_normal + n_uniform;
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(out && draw_counter, "noise_fill: null pointer");
+  noise_fill_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(out, n_normal, n_uniform, seed, draw_counter);
+  return check_launch("noise_fill");
+}

@@ -1,0 +1,107 @@
+// Library plumbing: error text, launch counter, stream/graph helpers, staged copies.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace d3b {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+char* err_buf() { return g_err; }
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
+}  // namespace d3b
+
+using namespace d3b;
+
+extern "C" const char* d3b_last_error(void) { return err_buf(); }
+extern "C" int d3b_abi_version(void) { return D3B_ABI_VERSION; }
+extern "C" int64_t d3b_launch_count(void) { return launches(); }
+
+extern "C" int d3b_device_info(int device, int* sm_count, int* cc_major, int* cc_minor) {
+  cudaDeviceProp p;
+  D3B_CUDA(cudaGetDeviceProperties(&p, device));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return D3B_OK;
+}
+
+extern "C" int d3b_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0 && (ptr || bytes == 0), "memset_zero: bad arguments");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+  count_launch();
+  return D3B_OK;
+}
+
+extern "C" int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0, "copy_h2d: bytes < 0");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemcpyAsync(dst, src_pinned, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0, "copy_d2h: bytes < 0");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemcpyAsync(dst_pinned, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0, "copy_d2d: bytes < 0");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  count_launch();
+  return D3B_OK;
+}
+
+extern "C" int d3b_stream_sync(void* stream) {
+  D3B_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_graph_begin(void* stream) {
+  D3B_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  return D3B_OK;
+}
+
+extern "C" int d3b_graph_end(void* stream, void** graph_exec, int* n_nodes) {
+  D3B_REQUIRE(graph_exec, "graph_end: null out pointer");
+  cudaGraph_t graph = nullptr;
+  D3B_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+  size_t n = 0;
+  cudaGraphGetNodes(graph, nullptr, &n);
+  if (n_nodes) *n_nodes = (int)n;
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return set_err(D3B_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+  *graph_exec = (void*)exec;
+  return D3B_OK;
+}
+
+extern "C" int d3b_graph_launch(void* graph_exec, void* stream) {
+  D3B_REQUIRE(graph_exec, "graph_launch: null graph");
+  D3B_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_graph_destroy(void* graph_exec) {
+  if (graph_exec) D3B_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return D3B_OK;
+}

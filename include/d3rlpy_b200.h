@@ -1,0 +1,168 @@
+/*
+ * d3rlpy_b200 — C ABI of the B200-native offline-RL update path.
+ *
+ * Plain pointers and sizes only: every pointer is a DEVICE pointer unless its name
+ * says `pinned`/`host`; `stream` is a cudaStream_t passed as void*.  All calls are
+ * asynchronous on `stream`, allocate nothing, and return 0 (D3B_OK) or a negative
+ * code with text available from d3b_last_error().  No exceptions, no aborts, no
+ * CPU fallback.  Row-major fp32 everywhere; `ld*` are leading dimensions in
+ * elements; `stride_*` are per-ensemble-member strides in elements (0 = operand
+ * shared by all members).
+ *
+ * The reference (thanhkaist/d3rlpy 1.1.0) has no FFI for this path — its boundary
+ * is a Python class API — so each entry point cites the reference code it
+ * replaces (paths relative to the reference root).
+ */
+#ifndef D3RLPY_B200_H
+#define D3RLPY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3B_ABI_VERSION 1
+#define D3B_OK 0
+#define D3B_ERR_ARG (-1)     /* bad shape / null pointer / unsupported configuration */
+#define D3B_ERR_CUDA (-2)    /* CUDA runtime error (text in d3b_last_error) */
+
+/* ---- library ------------------------------------------------------------------ */
+const char* d3b_last_error(void);
+int d3b_abi_version(void);
+int64_t d3b_launch_count(void); /* kernels + memset/copy nodes issued by this library so far */
+int d3b_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1/K1b: replay-buffer gather ---------------------------------------------
+ * Replaces TransitionMiniBatch.__cinit__/_assign_to_batch/_assign_observation/
+ * _assign_action (d3rlpy/dataset.pyx:1139-1342) and _stack_frames
+ * (d3rlpy/dataset.pyx:1051-1096); optional fused StandardScaler.transform
+ * (d3rlpy/preprocessing/scalers.py:350-354) when scaler_mean/std are non-NULL.
+ * `meta` is int32[T][4] = {step, episode_start_step, episode_last_step, terminal}
+ * per transition; `indices` int64[batch] are transition indices. */
+int d3b_gather_vector(const float* obs, int obs_dim, const void* actions, int act_dim, int discrete,
+                      const float* rewards, const void* meta, const int64_t* indices, int batch, int n_steps,
+                      float gamma, float* out_obs, void* out_act, float* out_rew, float* out_next, float* out_term,
+                      float* out_nsteps, const float* scaler_mean, const float* scaler_std, float scaler_eps,
+                      void* stream);
+int d3b_gather_frames(const uint8_t* frames, int frame_bytes, const void* meta, const int64_t* indices, int batch,
+                      int n_frames, int n_steps, uint8_t* out_obs, uint8_t* out_next, void* stream);
+
+/* StandardScaler.transform (d3rlpy/preprocessing/scalers.py:350-354) for a host-staged batch. */
+int d3b_standardize(float* x, const float* mean, const float* std, float eps, int rows, int dim, void* stream);
+
+/* ---- K2/K3: batched-ensemble dense layers (fp32 mode) ---------------------------
+ * forward:  y[e] = act(x[e] w[e]^T + b[e])      replaces nn.Linear + ReLU in
+ *           _VectorEncoder._fc_encode (d3rlpy/models/torch/encoders.py:265-275) and the
+ *           Python loop over members (q_functions/ensemble_q_function.py:144-146,168-170).
+ * backward_data:   dx[e] = (dy[e] w[e]) * [relu_src[e] > 0]      (autograd of the above)
+ * backward_weight: dw[e] += dy[e]^T x[e]; dbias[e] += colsum(dy[e])  (accumulates with RED) */
+int d3b_linear_forward(const float* x, int64_t ldx, int64_t stride_x, const float* w, int64_t ldw, int64_t stride_w,
+                       const float* bias, int64_t stride_b, float* y, int64_t ldy, int64_t stride_y, int rows,
+                       int out_features, int in_features, int members, int relu, void* stream);
+int d3b_linear_backward_data(const float* dy, int64_t lddy, int64_t stride_dy, const float* w, int64_t ldw,
+                             int64_t stride_w, float* dx, int64_t lddx, int64_t stride_dx, const float* relu_src,
+                             int64_t ld_src, int64_t stride_src, int rows, int out_features, int in_features,
+                             int members, void* stream);
+int d3b_linear_backward_weight(const float* dy, int64_t lddy, int64_t stride_dy, const float* x, int64_t ldx,
+                               int64_t stride_x, float* dw, int64_t lddw, int64_t stride_dw, float* dbias,
+                               int64_t stride_db, int rows, int out_features, int in_features, int members,
+                               void* stream);
+
+/* Narrow heads (out_features <= 32): Q head, mu|logstd, VAE heads, discrete Q head.
+ * Replace `_fc/_mu/_logstd` (q_functions/mean_q_function.py:21,69; policies.py:55,92,153-158;
+ * imitators.py:45-54). act_tanh fuses DeterministicPolicy's tanh (policies.py:57-59). */
+int d3b_head_forward(const float* x, int64_t ldx, int64_t stride_x, const float* w, int64_t ldw, int64_t stride_w,
+                     const float* bias, int64_t stride_b, float* y, int64_t ldy, int64_t stride_y, int rows,
+                     int out_features, int in_features, int members, int act_tanh, void* stream);
+int d3b_head_backward_data(const float* dy, int64_t lddy, int64_t stride_dy, const float* w, int64_t ldw,
+                           int64_t stride_w, float* dx, int64_t lddx, int64_t stride_dx, const float* relu_src,
+                           int64_t ld_src, int64_t stride_src, int rows, int out_features, int in_features,
+                           int members, void* stream);
+int d3b_head_backward_weight(const float* dy, int64_t lddy, int64_t stride_dy, const float* x, int64_t ldx,
+                             int64_t stride_x, float* dw, int64_t lddw, int64_t stride_dw, float* dbias,
+                             int64_t stride_db, int rows, int out_features, int in_features, int members,
+                             void* stream);
+
+/* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
+ * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
+ *   VectorEncoderWithAction.forward (encoders.py:328-339) plus the repeat/transpose/reshape of
+ *   cql_impl.py:153-161,176-180, bcq_impl.py:163-168; f = TD3 target smoothing
+ *   (td3_impl.py:66-73) when `noise` != NULL, or clamp(+-act_clip) (bcq_impl.py:141,181). */
+int d3b_concat_rows(const float* obs, int64_t ldo, const float* act, int64_t lda, const float* noise, float sigma,
+                    float noise_clip, float act_clip, float* x, int64_t ldx, int batch, int n_repeat, int obs_dim,
+                    int act_dim, void* stream);
+/* policy_sample_rows: SquashedNormalPolicy sample_with_log_prob / sample_n_with_log_prob /
+ *   best_action (policies.py:167-249, distributions.py:91-143).  head = [mu | raw logstd],
+ *   eps laid out [n][batch][act] as Normal.rsample((n,)). */
+int d3b_policy_sample_rows(const float* head, int64_t ld_head, const float* eps, const float* obs, int64_t ldo,
+                           float* x, int64_t ldx, float* act_out, float* logp, int batch, int n_samples, int obs_dim,
+                           int act_dim, float min_logstd, float max_logstd, int deterministic, void* stream);
+/* critic_loss: TD error summed over members (ddpg_impl.py:154-165, ensemble_q_function.py:81-106,
+ *   mean_q_function.py:74-87) + CQL conservative term with its softmax gradient
+ *   (cql_impl.py:196-223); q rows = [data B | pi(s_t) B*N | pi(s_t+1) B*N | random B*N].
+ *   sums[0..2] += {sum (q-y)^2, sum logsumexp, sum q_data}. */
+int d3b_critic_loss(const float* q, int64_t stride_q, const float* q_targ, int64_t stride_qt, int targ_members,
+                    const float* q_tpn, const float* rewards, const float* terminals, const float* n_steps,
+                    float gamma, const float* logp_t, const float* logp_tp1, int n_action_samples, int act_dim,
+                    const float* log_alpha, float conservative_weight, float* dq, int64_t stride_dq, float* sums,
+                    float* y_out, int batch, int members, float inv_batch, int td_enabled, void* stream);
+/* cql_finalize: scalar tail of compute_critic_loss (mode 0) / update_alpha (mode 1)
+ *   (cql_impl.py:110-141,217-223). */
+int d3b_cql_finalize(const float* sums, const float* log_alpha, float inv_batch, int members,
+                     float conservative_weight, float alpha_threshold, int mode, int conservative, float* metric,
+                     float* grad_log_alpha, void* stream);
+int d3b_scalar_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int* step, double lr,
+                    double beta1, double beta2, double eps, float* out_exp, void* stream);
+/* SACImpl.compute_actor_loss / update_temp (sac_impl.py:114-146) */
+int d3b_sac_actor_loss(const float* q, int64_t stride_q, const float* logp, const float* log_temp, float* dq,
+                       int64_t stride_dq, float* loss_sum, int batch, int members, float inv_batch, void* stream);
+int d3b_sac_actor_backward(const float* head, int64_t ld_head, const float* eps, const float* dx_action,
+                           int64_t lddx, int64_t stride_dx, int members, const float* log_temp, float* dhead,
+                           int64_t ld_dhead, int batch, int act_dim, float min_logstd, float max_logstd,
+                           float inv_batch, void* stream);
+int d3b_sac_temp_loss(const float* logp, const float* log_temp, int batch, int act_dim, float inv_batch,
+                      float* metric, float* grad, int accumulate, void* stream);
+/* TD3PlusBCImpl.compute_actor_loss (td3_plus_bc_impl.py:64-70) in three phases so the
+ * batch-global lambda can be all-reduced between stats and seed when the batch is sharded. */
+int d3b_td3bc_actor_stats(const float* q0, const float* a, int64_t lda, const float* a_data, int64_t ldd,
+                          float* sums, int batch, int act_dim, void* stream);
+int d3b_td3bc_actor_seed(const float* sums, float alpha, float inv_batch, int act_dim, float* dq, int64_t stride_dq,
+                         int batch, int members, float* metric, void* stream);
+int d3b_td3bc_actor_backward(const float* a, int64_t lda, const float* a_data, int64_t ldd, const float* dx_action,
+                             int64_t lddx, float* dz, int64_t lddz, int batch, int act_dim, float inv_batch,
+                             void* stream);
+
+/* ---- K10: optimizer / target sync ----------------------------------------------
+ * adam_step: torch.optim.Adam.step as built by AdamFactory (d3rlpy/models/optimizers.py:106-138;
+ *   call sites ddpg_impl.py:150,181, sac_impl.py:141, cql_impl.py:137, bcq_impl.py:159,
+ *   dqn_impl.py:109) over one flat arena; `step` is a device int holding t (already
+ *   incremented by d3b_tick); `target` != NULL fuses soft_sync of the new params.
+ * soft_sync / hard_sync: d3rlpy/torch_utility.py:27-41. */
+int d3b_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
+                  const int* step, double lr, double beta1, double beta2, double eps, float tau, int zero_grad,
+                  void* stream);
+int d3b_soft_sync(float* target, const float* params, int64_t n, float tau, void* stream);
+int d3b_hard_sync(float* target, const float* params, int64_t n, void* stream);
+int d3b_tick(int* counters, int n, unsigned mask, void* stream);
+/* Philox4x32-10 fill: first n_normal floats ~ N(0,1), next n_uniform ~ U(-1,1); replaces
+ * torch.randn / uniform_ / Normal.rsample draws (td3_impl.py:67, cql_impl.py:186,
+ * distributions.py:105,118, bcq_impl.py:136,178, imitators.py:85). */
+int d3b_noise_fill(float* out, int64_t n_normal, int64_t n_uniform, uint64_t seed, const int* draw_counter,
+                   void* stream);
+
+/* ---- plumbing: staged copies, CUDA-graph capture of a whole update ------------------ */
+int d3b_memset_zero(void* ptr, int64_t bytes, void* stream);
+int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream);
+int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream);
+int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+int d3b_stream_sync(void* stream);
+int d3b_graph_begin(void* stream);
+int d3b_graph_end(void* stream, void** graph_exec, int* n_nodes);
+int d3b_graph_launch(void* graph_exec, void* stream);
+int d3b_graph_destroy(void* graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3RLPY_B200_H */

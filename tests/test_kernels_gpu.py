@@ -1,0 +1,244 @@
+"""GPU: each CUDA kernel, called through the C ABI, against a plain fp32/fp64 PyTorch statement of
+the same op.  Tolerance for fp32 mode: 1e-5 relative (north_star)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _close(a, b, rtol=RTOL, atol=None, msg=""):
+    b = b.to(a.dtype)
+    scale = max(1.0, float(b.abs().max()))
+    err = float((a - b).abs().max())
+    assert err <= (atol if atol is not None else rtol * scale), f"{msg} max err {err} scale {scale}"
+
+
+@pytest.mark.parametrize("M,N,K,E,shared", [(256, 256, 23, 2, True), (7936, 256, 256, 2, False), (33, 70, 19, 3, False),
+                                            (512, 300, 400, 1, False), (1000, 256, 256, 10, False)])
+def test_linear_forward_backward(M, N, K, E, shared):
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(1 if shared else E, M, K, generator=g).to(dev)
+    w = (torch.randn(E, N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(E, N, generator=g).to(dev)
+    y = torch.empty(E, M, N, device=dev)
+    sx = 0 if shared else M * K
+    L.linear_forward(x.data_ptr(), K, sx, w.data_ptr(), K, N * K, b.data_ptr(), N, y.data_ptr(), N, M * N, M, N, K, E,
+                     1, _st())
+    xe = x.expand(E, M, K).double()
+    ref = torch.relu(torch.einsum("emk,enk->emn", xe, w.double()) + b.double()[:, None, :])
+    _close(y, ref, msg="forward")
+
+    dy = torch.randn(E, M, N, generator=g).to(dev)
+    dx = torch.empty(E, M, K, device=dev)
+    src = torch.randn(E, M, K, generator=g).to(dev)
+    L.linear_backward_data(dy.data_ptr(), N, M * N, w.data_ptr(), K, N * K, dx.data_ptr(), K, M * K, src.data_ptr(),
+                           K, M * K, M, N, K, E, _st())
+    ref = torch.einsum("emn,enk->emk", dy.double(), w.double()) * (src > 0).double()
+    _close(dx, ref, msg="dgrad")
+
+    # column-restricted dgrad without mask (action columns of layer 1)
+    if K > 8:
+        c0, nc = K - 6, 6
+        dxa = torch.empty(E, M, nc, device=dev)
+        L.linear_backward_data(dy.data_ptr(), N, M * N, w.data_ptr() + 4 * c0, K, N * K, dxa.data_ptr(), nc, M * nc,
+                               None, 0, 0, M, N, nc, E, _st())
+        ref = torch.einsum("emn,enk->emk", dy.double(), w.double()[:, :, c0:c0 + nc])
+        _close(dxa, ref, msg="dgrad cols")
+
+    dw = torch.zeros(E, N, K, device=dev)
+    db = torch.zeros(E, N, device=dev)
+    L.linear_backward_weight(dy.data_ptr(), N, M * N, x.data_ptr(), K, sx, dw.data_ptr(), K, N * K, db.data_ptr(), N,
+                             M, N, K, E, _st())
+    refw = torch.einsum("emn,emk->enk", dy.double(), xe)
+    _close(dw, refw, rtol=2e-5, msg="wgrad")
+    _close(db, dy.double().sum(1), rtol=2e-5, msg="bgrad")
+
+
+@pytest.mark.parametrize("M,N,K,E,tanh", [(7936, 1, 256, 2, False), (512, 12, 256, 1, False), (100, 6, 300, 1, True),
+                                          (77, 24, 750, 1, False)])
+def test_head_forward_backward(M, N, K, E, tanh):
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    g = torch.Generator().manual_seed(N * 7 + K)
+    x = torch.relu(torch.randn(E, M, K, generator=g)).to(dev)
+    w = (torch.randn(E, N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(E, N, generator=g).to(dev)
+    y = torch.empty(E, M, N, device=dev)
+    L.head_forward(x.data_ptr(), K, M * K, w.data_ptr(), K, N * K, b.data_ptr(), N, y.data_ptr(), N, M * N, M, N, K, E,
+                   int(tanh), _st())
+    ref = torch.einsum("emk,enk->emn", x.double(), w.double()) + b.double()[:, None, :]
+    if tanh:
+        ref = torch.tanh(ref)
+    _close(y, ref, msg="head fwd")
+    dy = torch.randn(E, M, N, generator=g).to(dev)
+    dx = torch.empty(E, M, K, device=dev)
+    L.head_backward_data(dy.data_ptr(), N, M * N, w.data_ptr(), K, N * K, dx.data_ptr(), K, M * K, x.data_ptr(), K,
+                         M * K, M, N, K, E, _st())
+    ref = torch.einsum("emn,enk->emk", dy.double(), w.double()) * (x > 0).double()
+    _close(dx, ref, msg="head dgrad")
+    dw = torch.zeros(E, N, K, device=dev)
+    db = torch.zeros(E, N, device=dev)
+    L.head_backward_weight(dy.data_ptr(), N, M * N, x.data_ptr(), K, M * K, dw.data_ptr(), K, N * K, db.data_ptr(), N,
+                           M, N, K, E, _st())
+    _close(dw, torch.einsum("emn,emk->enk", dy.double(), x.double()), rtol=2e-5, msg="head wgrad")
+    _close(db, dy.double().sum(1), rtol=2e-5, msg="head bgrad")
+
+
+@pytest.mark.parametrize("n", [1, 7, 4096, 415_248])
+def test_adam_and_soft_sync_match_torch(n):
+    """params, exp_avg, exp_avg_sq after 3 steps vs torch.optim.Adam (CPU, the reference's optimizer),
+    and target vs soft_sync's closed form (tests/test_torch_utility.py:30-57 of the reference)."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    g = torch.Generator().manual_seed(n)
+    p0 = torch.randn(n, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=3e-4)
+    targ_ref = torch.randn(n, generator=g)
+    p = p0.clone().to(dev)
+    targ = targ_ref.clone().to(dev)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    step = torch.zeros(1, dtype=torch.int32, device=dev)
+    tau = 0.005
+    for it in range(3):
+        grad = torch.randn(n, generator=g) * (10.0 ** (it - 1))
+        p_ref.grad = grad.clone()
+        opt.step()
+        with torch.no_grad():
+            targ_ref.mul_(1 - tau)
+            targ_ref.add_(tau * p_ref.data)
+        gd = grad.to(dev)
+        L.tick(step.data_ptr(), 1, 1, _st())
+        L.adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), targ.data_ptr(), n, step.data_ptr(), 3e-4,
+                    0.9, 0.999, 1e-8, tau, 1, _st())
+        assert float(gd.abs().max()) == 0.0  # grads are cleared for the next accumulation
+    st = opt.state[p_ref]
+    torch.testing.assert_close(p.cpu(), p_ref.data, rtol=1e-6, atol=1e-7)
+    # moments: 1e-5 relative (fp32-mode tolerance); the CPU lerp/addcmul differ from ours only by FMA contraction
+    torch.testing.assert_close(m.cpu(), st["exp_avg"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(v.cpu(), st["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(targ.cpu(), targ_ref, rtol=1e-6, atol=1e-7)
+    # stand-alone soft_sync and hard_sync
+    t2 = torch.randn(n, generator=g)
+    t2d = t2.clone().to(dev)
+    L.soft_sync(t2d.data_ptr(), p.data_ptr(), n, tau, _st())
+    expect = t2 * (1 - tau) + tau * p.cpu()
+    torch.testing.assert_close(t2d.cpu(), expect, rtol=1e-6, atol=1e-7)
+    L.hard_sync(t2d.data_ptr(), p.data_ptr(), n, _st())
+    assert torch.equal(t2d, p)
+
+
+def test_policy_sample_rows_matches_squashed_gaussian():
+    """tanh-Gaussian sample + log-prob vs the oracle's restatement of SquashedGaussianDistribution
+    (reference test: tests/models/torch/test_distributions.py:51-96, atol 1e-2; here 1e-5)."""
+    from d3rlpy_b200._lib import lib
+    from oracle import update as ou
+
+    L, dev = lib(), _dev()
+    B, N, O, A = 37, 5, 9, 6
+    g = torch.Generator().manual_seed(5)
+    head = torch.randn(B, 2 * A, generator=g) * 2.0
+    head[0, A:] = 5.0    # clamps at max_logstd
+    head[1, A:] = -30.0  # clamps at min_logstd
+    eps = torch.randn(N, B, A, generator=g)
+    obs = torch.randn(B, O, generator=g)
+    x = torch.zeros(B * N, O + A, device=dev)
+    lp = torch.zeros(B * N, device=dev)
+    head_d, eps_d, obs_d = head.to(dev), eps.to(dev), obs.to(dev)  # keep the device copies alive
+    L.policy_sample_rows(head_d.data_ptr(), 2 * A, eps_d.data_ptr(), obs_d.data_ptr(), O,
+                         x.data_ptr(), O + A, None, lp.data_ptr(), B, N, O, A, -20.0, 2.0, 0, _st())
+    torch.cuda.synchronize()
+    mu, std = head[:, :A], head[:, A:].clamp(-20, 2).exp()
+    raw = mu.unsqueeze(0) + eps * std.unsqueeze(0)
+    ref_a = torch.tanh(raw).transpose(0, 1).reshape(B * N, A)
+    ref_lp = ou.squashed_log_prob(mu.unsqueeze(0), std.unsqueeze(0), raw).transpose(0, 1).reshape(B * N)
+    _close(x[:, O:].cpu(), ref_a, msg="action")
+    _close(x[:, :O].cpu(), obs.repeat_interleave(N, 0), atol=0.0, msg="obs")
+    _close(lp.cpu(), ref_lp, rtol=2e-5, msg="logp")
+
+
+def test_critic_loss_and_gradient_vs_autograd():
+    """TD (sum over members of batch means) + CQL conservative term and dL/dQ vs torch autograd."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    B, N, A, E = 19, 4, 3, 3
+    R = B * (1 + 3 * N)
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(E, R, generator=g) * 3).requires_grad_(True)
+    qt = torch.randn(E, B, generator=g)
+    rew, term = torch.randn(B, generator=g), (torch.rand(B, generator=g) < 0.3).float()
+    ns = torch.randint(1, 4, (B,), generator=g).float()
+    lp1, lp2 = torch.randn(B, N, generator=g), torch.randn(B, N, generator=g)
+    log_alpha = torch.tensor([0.3])
+    gamma, cw, thr = 0.99, 5.0, 10.0
+    y = rew + (gamma ** ns) * qt.min(0).values * (1 - term)
+    td = sum(F.mse_loss(q[e, :B], y, reduction="none").mean() for e in range(E))
+    v1 = q[:, B:B + B * N].view(E, B, N) - lp1
+    v2 = q[:, B + B * N:B + 2 * B * N].view(E, B, N) - lp2
+    v3 = q[:, B + 2 * B * N:].view(E, B, N) - math.log(0.5 ** A)
+    lse = torch.logsumexp(torch.cat([v1, v2, v3], 2), 2, keepdim=True)
+    cons = log_alpha.exp().clamp(0, 1e6)[0] * (cw * (lse.mean(0).mean() - q[:, :B].mean(0).mean()) - thr)
+    loss = td + cons
+    loss.backward()
+    qd = q.detach().to(dev)
+    dq = torch.zeros(E, R, device=dev)
+    sums = torch.zeros(4, device=dev)
+    metric = torch.zeros(2, device=dev)
+    la = log_alpha.to(dev)
+    lps = torch.stack([lp1.reshape(-1), lp2.reshape(-1)]).to(dev)
+    d = lambda t: t.to(dev).data_ptr()
+    keep = [qt.to(dev), rew.to(dev), term.to(dev), ns.to(dev)]
+    L.critic_loss(qd.data_ptr(), R, keep[0].data_ptr(), B, E, None, keep[1].data_ptr(), keep[2].data_ptr(),
+                  keep[3].data_ptr(), gamma, lps.data_ptr(), lps.data_ptr() + 4 * B * N, N, A, la.data_ptr(), cw,
+                  dq.data_ptr(), R, sums.data_ptr(), None, B, E, 1.0 / B, 1, _st())
+    L.cql_finalize(sums.data_ptr(), la.data_ptr(), 1.0 / B, E, cw, thr, 0, 1, metric.data_ptr(), None, _st())
+    _close(metric[0].cpu(), loss.detach(), msg="loss")
+    _close(dq.cpu(), q.grad, rtol=2e-5, msg="dq")
+    # alpha mode: loss = -cons, d/dlog_alpha
+    la_t = log_alpha.clone().requires_grad_(True)
+    cons2 = la_t.exp().clamp(0, 1e6)[0] * (cw * (lse.detach().mean(0).mean() - q.detach()[:, :B].mean(0).mean()) - thr)
+    (-cons2).backward()
+    L.cql_finalize(sums.data_ptr(), la.data_ptr(), 1.0 / B, E, cw, thr, 1, 1, metric.data_ptr(),
+                   metric.data_ptr() + 4, _st())
+    _close(metric[0].cpu(), -cons2.detach(), msg="alpha loss")
+    _close(metric[1].cpu(), la_t.grad[0], msg="alpha grad")
+
+
+def test_noise_fill_statistics():
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    nn_, nu = 1_000_001, 500_003
+    out = torch.zeros(nn_ + nu, device=dev)
+    ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.noise_fill(out.data_ptr(), nn_, nu, 1234, ctr.data_ptr(), _st())
+    a = out[:nn_].double()
+    u = out[nn_:].double()
+    assert abs(float(a.mean())) < 5e-3 and abs(float(a.std()) - 1) < 5e-3
+    assert abs(float((a ** 4).mean()) - 3.0) < 0.1
+    assert float(u.min()) >= -1 and float(u.max()) <= 1 and abs(float(u.mean())) < 5e-3
+    assert abs(float(u.var()) - 1 / 3) < 5e-3
+    first = out.clone()
+    ctr += 1
+    L.noise_fill(out.data_ptr(), nn_, nu, 1234, ctr.data_ptr(), _st())
+    assert float((first == out).float().mean()) < 1e-3  # a new epoch gives a new stream

@@ -1,0 +1,175 @@
+"""GPU: whole `algo.update(batch)` through the public API vs (1) the golden vectors recorded from the
+unmodified reference (identical weights, minibatches and injected noise) and (2) the oracle at the
+BASELINE shapes.  fp32 mode tolerance: 1e-5 relative on metrics, gradients' effect (post-step
+parameters, Adam state) and targets — stated per assertion."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import update as ou
+from tests.golden_io import Case, load_update
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def _ns(arrays):
+    return SimpleNamespace(**arrays)
+
+
+def _assert_params(got_sd, ref_sd, what, rel=REL, abs_floor=2e-6):
+    for k, v in ref_sd.items():
+        g = got_sd[k].detach().cpu()
+        v = v.detach().cpu().reshape(g.shape)
+        scale = max(1.0, float(v.abs().max()))
+        err = float((g - v).abs().max())
+        assert err <= max(rel * scale, abs_floor), f"{what}/{k}: err {err:.3e} scale {scale:.3e}"
+
+
+def _assert_metrics(m, ref, what, rel=REL):
+    assert set(m) == set(ref), (what, set(m), set(ref))
+    for k in ref:
+        assert abs(float(m[k]) - ref[k]) <= rel * max(1.0, abs(ref[k])) + 1e-6, (what, k, float(m[k]), ref[k])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_td3bc_matches_reference_golden(use_graph):
+    from d3rlpy_b200.algos import TD3PlusBC
+    from d3rlpy_b200.preprocessing import StandardScaler
+
+    case = Case(load_update(), "td3bc")
+    c = case.cfg
+    sc = StandardScaler(mean=case.z["td3bc/scaler_mean"], std=case.z["td3bc/scaler_std"])
+    algo = TD3PlusBC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
+                     scaler=sc)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    impl.policy.load_state_dict(case.group("init", "pi"))
+    impl.targ_policy.load_state_dict(case.group("init", "pi"))
+    for s in range(case.steps):
+        impl.inject_noise(case.noise(s), int(c["batch"]))
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"td3bc step {s}")
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q")
+    _assert_params(impl.policy.state_dict(), case.group("final", "pi"), "pi")
+    _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q")
+    _assert_params(impl.targ_policy.state_dict(), case.group("final", "targ_pi"), "targ_pi")
+    assert algo.grad_step == case.steps
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_cql_matches_reference_golden(use_graph):
+    from d3rlpy_b200.algos import CQL
+
+    case = Case(load_update(), "cql")
+    c = case.cfg
+    algo = CQL(actor_encoder_factory=[32, 32, 32], critic_encoder_factory=[32, 32, 32], batch_size=int(c["batch"]),
+               n_action_samples=int(c["n"]), n_steps=3)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    impl.policy.load_state_dict(case.group("init", "pi"))
+    impl.targ_policy.load_state_dict(case.group("init", "pi"))
+    for s in range(case.steps):
+        impl.inject_noise(case.noise(s), int(c["batch"]))
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"cql step {s}")
+    for grp, view in (("q", impl.q_function), ("pi", impl.policy), ("targ_q", impl.targ_q_function),
+                      ("targ_pi", impl.targ_policy), ("log_temp", impl._log_temp), ("log_alpha", impl._log_alpha)):
+        _assert_params(view.state_dict(), case.group("final", grp), grp)
+
+
+def _synthetic_batch(rs, B, O, A):
+    return dict(observations=rs.randn(B, O).astype(np.float32), actions=rs.uniform(-1, 1, (B, A)).astype(np.float32),
+                rewards=rs.randn(B, 1).astype(np.float32), next_observations=rs.randn(B, O).astype(np.float32),
+                terminals=(rs.rand(B, 1) < 0.05).astype(np.float32), n_steps=np.ones((B, 1), np.float32))
+
+
+def test_cql_c2_shape_vs_oracle_three_steps():
+    """BASELINE config c2 (obs 17, act 6, B 256, N 10, 2 critics, 3x256): metrics, post-step parameters,
+    Adam moments and targets vs the oracle on identical weights / batches / injected noise."""
+    from d3rlpy_b200.algos import CQL
+
+    O, A, B, N, H = 17, 6, 256, 10, [256, 256, 256]
+    torch.set_num_threads(8)
+    orc = ou.CQL(O, A, hidden=H, n_action_samples=N, seed=5)
+    algo = CQL(actor_encoder_factory=H, critic_encoder_factory=H, n_action_samples=N)
+    algo.create_impl((O,), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    impl.policy.load_state_dict(orc.pi)
+    impl.targ_policy.load_state_dict(orc.pi)
+    rs = np.random.RandomState(0)
+    for s in range(3):
+        arrays = _synthetic_batch(rs, B, O, A)
+        noise = ou.Noise(seed=100 + s)
+        ref = orc.update(ou.Batch(arrays), noise)
+        impl.inject_noise(noise.log, B)
+        m = algo.update(_ns(arrays))
+        _assert_metrics(m, ref, f"c2 step {s}", rel=2e-5)
+    _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=2e-5)
+    _assert_params(impl.policy.state_dict(), orc.pi, "pi", rel=2e-5)
+    _assert_params(impl.targ_q_function.state_dict(), orc.targ_q, "targ_q", rel=2e-5)
+    _assert_params(impl.targ_policy.state_dict(), orc.targ_pi, "targ_pi", rel=2e-5)
+    # Adam moments of the critic ensemble vs torch.optim.Adam state
+    m_sd = impl._q_func.arena.state_dict("exp_avg")
+    for k, p in orc.q.items():
+        st = orc.critic_optim.state[p]
+        ref_m = st["exp_avg"]
+        err = float((m_sd[k].cpu() - ref_m).abs().max())
+        assert err <= 2e-5 * max(1.0, float(ref_m.abs().max())) + 1e-7, (k, err)
+
+
+def test_td3bc_c1_shape_vs_oracle_four_steps():
+    """BASELINE config c1 (obs 11, act 3, B 256, 2 critics, 256x256); four steps so that the %2 actor
+    schedule and both Adam step counters advance."""
+    from d3rlpy_b200.algos import TD3PlusBC
+
+    O, A, B = 11, 3, 256
+    orc = ou.TD3PlusBC(O, A, seed=2)
+    algo = TD3PlusBC(scaler=None)
+    algo.create_impl((O,), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    impl.policy.load_state_dict(orc.pi)
+    impl.targ_policy.load_state_dict(orc.pi)
+    rs = np.random.RandomState(1)
+    for s in range(4):
+        arrays = _synthetic_batch(rs, B, O, A)
+        noise = ou.Noise(seed=7 + s)
+        ref = orc.update(ou.Batch(arrays), noise)
+        impl.inject_noise(noise.log, B)
+        m = algo.update(_ns(arrays))
+        _assert_metrics(m, ref, f"c1 step {s}", rel=2e-5)
+    for grp, view, refp in (("q", impl.q_function, orc.q), ("pi", impl.policy, orc.pi),
+                            ("targ_q", impl.targ_q_function, orc.targ_q), ("targ_pi", impl.targ_policy, orc.targ_pi)):
+        _assert_params(view.state_dict(), refp, grp, rel=2e-5)
+    assert int(impl._counters[1]) == 4 and int(impl._counters[2]) == 2  # critic / actor Adam steps
+
+
+def test_update_from_device_gather_and_philox_noise_runs():
+    """fit()-style path: HBM replay -> gather kernel -> update graph, device-generated noise."""
+    from d3rlpy_b200.algos import CQL
+    from d3rlpy_b200.dataset import MDPDataset
+
+    rs = np.random.RandomState(0)
+    S, O, A = 20_000, 17, 6
+    ds = MDPDataset(rs.randn(S, O).astype(np.float32), rs.uniform(-1, 1, (S, A)).astype(np.float32),
+                    rs.randn(S).astype(np.float32), (np.arange(S) % 1000 == 999).astype(np.float32))
+    algo = CQL(actor_encoder_factory=[64, 64], critic_encoder_factory=[64, 64], batch_size=64, n_action_samples=4)
+    hist = algo.fit(ds, n_steps=20, n_steps_per_epoch=10, seed=0)
+    assert len(hist) == 2 and algo.grad_step == 20
+    for h in hist:
+        assert set(h) == {"temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss"}
+        assert all(np.isfinite(v) for v in h.values())
+    assert hist[1]["temp"] < 1.0 and hist[1]["alpha"] != 1.0
