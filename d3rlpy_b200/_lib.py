@@ -50,6 +50,39 @@ def _ctype(t: str):
 
 class Lib:
     dry = False
+    _prof = None
+    _FLOP_ARGS = {"linear_forward": (11, 12, 13, 14), "linear_backward_data": (12, 13, 14, 15),
+                  "linear_backward_weight": (11, 12, 13, 14), "head_forward": (11, 12, 13, 14),
+                  "head_backward_data": (12, 13, 14, 15), "head_backward_weight": (11, 12, 13, 14)}
+
+    def start_profile(self, stream_obj) -> None:
+        """Bracket every launch with CUDA events recorded on `stream_obj` (the launching stream)."""
+        self._prof = []
+        self._prof_stream = stream_obj
+
+    def stop_profile(self):
+        import torch
+
+        torch.cuda.synchronize()
+        recs = [(n, f, a.elapsed_time(b)) for n, f, a, b in self._prof]
+        self._prof = None
+        return recs
+
+    def _profiled(self, name, fn, args):
+        import torch
+
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(self._prof_stream)
+        rc = fn(*args)
+        b.record(self._prof_stream)
+        if rc != 0:
+            raise D3BError(f"d3b_{name} failed ({rc}): {self.last_error()}")
+        flops = 0.0
+        if name in self._FLOP_ARGS:
+            i = self._FLOP_ARGS[name]
+            flops = 2.0 * args[i[0]] * args[i[1]] * args[i[2]] * args[i[3]]
+        self._prof.append((name, flops, a, b))
+        return rc
 
     def __init__(self, path: str = LIB_PATH):
         if not os.path.exists(path):
@@ -80,6 +113,8 @@ class Lib:
         def call(*args):
             if self.dry:  # allocation-only pass before CUDA-graph capture (no launches)
                 return 0
+            if self._prof is not None:
+                return self._profiled(name, fn, args)
             rc = fn(*args)
             if rc != 0:
                 raise D3BError(f"d3b_{name} failed ({rc}): {self.last_error()}")

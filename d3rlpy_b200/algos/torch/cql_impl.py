@@ -222,6 +222,11 @@ class CQLImpl(DDPGBaseImpl):
 
     # ------------------------------------------------------------------ fused update (CQL._update, cql.py:234-258)
     def update_fused(self, batch):
+        names = self.update_fused_async(batch)
+        return self._metrics_dict(names)
+
+    def update_fused_async(self, batch):
+        """Enqueue one whole update (no host sync); returns the metric slot names."""
         db = self.load_batch(batch)
         do_temp, do_alpha = self._temp_learning_rate > 0, self._alpha_learning_rate > 0
 
@@ -246,7 +251,7 @@ class CQLImpl(DDPGBaseImpl):
         if do_alpha:
             names += [(M_ALPHA_LOSS, "alpha_loss"), (M_ALPHA, "alpha")]
         names += [(M_CRITIC, "critic_loss"), (M_ACTOR, "actor_loss")]
-        return self._metrics_dict(names)
+        return names
 
     # ------------------------------------------------------------------ reference hooks (eager, one sync each)
     def _begin(self, batch, *ticks):

@@ -95,6 +95,10 @@ class TD3PlusBCImpl(DDPGBaseImpl):
 
     # ------------------------------------------------------------------ fused update (TD3PlusBC._update)
     def update_fused(self, batch, actor_step: bool):
+        return self._metrics_dict(self.update_fused_async(batch, actor_step))
+
+    def update_fused_async(self, batch, actor_step: bool):
+        """Enqueue one whole update (no host sync); returns the metric slot names."""
         db = self.load_batch(batch)
 
         def program():
@@ -108,8 +112,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
                 self._p_actor(db)
 
         self.run_program(("td3bc", db.B, actor_step, self._noise_injected), program)
-        names = [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
-        return self._metrics_dict(names)
+        return [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
 
     # ------------------------------------------------------------------ reference hooks (eager)
     def compute_target(self, batch) -> torch.Tensor:
