@@ -1,0 +1,275 @@
+// bf16-mode support kernels around the tcgen05 GEMM (umma_gemm.cu): fp32 -> bf16 shadows (+ transposed
+// copies so that every GEMM operand is K-major), narrow heads reading bf16 activations, bias-gradient
+// column sums.  All HBM/L2-bandwidth bound element-wise or reduction work.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace d3b {
+
+struct ShadowEntry {
+  long long src_off;  // fp32 offset inside one member block
+  int rows, cols;     // matrix [rows][cols], src leading dim == cols
+  long long dst_off, ldd;    // bf16 row-major copy (ld >= cols), -1 = skip
+  long long dstT_off, ldt;   // bf16 transposed copy [cols][ldt], -1 = skip
+};
+constexpr int MAX_SHADOW = 16;
+struct ShadowTable {
+  ShadowEntry e[MAX_SHADOW];
+  int n;
+};
+
+// grid: (blocks over elements, table entry, member)
+__global__ void __launch_bounds__(256) shadow_kernel(const float* __restrict__ src, long long src_member_stride,
+                                                     __nv_bfloat16* __restrict__ dst, long long dst_member_stride,
+                                                     ShadowTable t) {
+  const ShadowEntry& s = t.e[blockIdx.y];
+  long long total = (long long)s.rows * s.cols;
+  const float* sp = src + (long long)blockIdx.z * src_member_stride + s.src_off;
+  __nv_bfloat16* dp = dst + (long long)blockIdx.z * dst_member_stride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(i / s.cols), c = (int)(i % s.cols);
+    __nv_bfloat16 v = __float2bfloat16_rn(__ldg(sp + i));
+    if (s.dst_off >= 0) dp[s.dst_off + (long long)r * s.ldd + c] = v;
+    if (s.dstT_off >= 0) dp[s.dstT_off + (long long)c * s.ldt + r] = v;
+  }
+}
+
+// fp32 [rows][cols] (ld lds) -> bf16 [rows][ldd] and/or transposed bf16 [cols][ldt]; 32x32 smem tile transpose.
+__global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
+                                                      __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                      __nv_bfloat16* __restrict__ dstT, long long ldt) {
+  __shared__ float tile[32][33];
+  int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + tx;
+    float v = (r < rows && c < cols) ? __ldg(src + (long long)r * lds + c) : 0.f;
+    tile[i][tx] = v;
+    if (dst && r < rows && c < cols) dst[(long long)r * ldd + c] = __float2bfloat16_rn(v);
+  }
+  if (!dstT) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + tx;
+    if (r < rows && c < cols) dstT[(long long)c * ldt + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+// One warp per (member,row): Y[e][m][n] = act(X_bf16[e][m][:] . W[e][n][:] + b[e][n]), fp32 weights.
+__global__ void __launch_bounds__(256) head_forward_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
+                                                                long long sX, const float* __restrict__ W,
+                                                                long long ldw, long long sW,
+                                                                const float* __restrict__ bias, long long sB,
+                                                                float* __restrict__ Y, long long ldy, long long sY,
+                                                                int M, int N, int K, int E, int act_tanh) {
+  int lane = threadIdx.x & 31;
+  long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)M * E) return;
+  int e = (int)(wid / M), m = (int)(wid % M);
+  const __nv_bfloat16* x = X + (long long)e * sX + (long long)m * ldx;
+  const float* w = W + (long long)e * sW;
+  float mine = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* wr = w + (long long)n * ldw;
+    float s = 0.f;
+    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(x[k]), __ldg(wr + k), s);
+    s = warp_sum(s);
+    if (lane == n) mine = s;
+  }
+  if (lane < N) {
+    float v = mine + (bias ? __ldg(bias + (long long)e * sB + lane) : 0.f);
+    if (act_tanh) v = tanhf(v);
+    Y[(long long)e * sY + (long long)m * ldy + lane] = v;
+  }
+}
+
+// dX_bf16[e][m][k] = (sum_n dY[e][m][n] W[e][n][k]) * [src_bf16[e][m][k] > 0]  (+ transposed copy [k][m])
+// 32x32 tiles so that both the row-major and the transposed store are coalesced.
+__global__ void __launch_bounds__(256) head_backward_data_bf16_kernel(
+    const float* __restrict__ dY, long long lddy, long long sdY, const float* __restrict__ W, long long ldw,
+    long long sW, __nv_bfloat16* __restrict__ dX, long long lddx, long long sdX, __nv_bfloat16* __restrict__ dXT,
+    long long ldt, long long sdXT, const __nv_bfloat16* __restrict__ src, long long ldsrc, long long sSrc, int M,
+    int N, int K) {
+  __shared__ float tile[32][33];
+  int e = blockIdx.z;
+  int m0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* w = W + (long long)e * sW;
+  for (int i = ty; i < 32; i += 8) {
+    int m = m0 + i, k = k0 + tx;
+    float s = 0.f;
+    if (m < M && k < K) {
+      const float* dy = dY + (long long)e * sdY + (long long)m * lddy;
+      for (int n = 0; n < N; ++n) s = fmaf(__ldg(dy + n), __ldg(w + (long long)n * ldw + k), s);
+      if (src && !(__bfloat162float(src[(long long)e * sSrc + (long long)m * ldsrc + k]) > 0.f)) s = 0.f;
+      dX[(long long)e * sdX + (long long)m * lddx + k] = __float2bfloat16_rn(s);
+    }
+    tile[i][tx] = s;
+  }
+  if (!dXT) return;
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    int k = k0 + i, m = m0 + tx;
+    if (m < M && k < K) dXT[(long long)e * sdXT + (long long)k * ldt + m] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
+template <int NMAX>
+__global__ void __launch_bounds__(256) head_backward_weight_bf16_kernel(
+    const float* __restrict__ dY, long long lddy, long long sdY, const __nv_bfloat16* __restrict__ X, long long ldx,
+    long long sX, float* __restrict__ dW, long long lddw, long long sdW, float* __restrict__ db, long long sdb, int M,
+    int N, int K, int rows_per_block) {
+  extern __shared__ float sdy[];
+  int e = blockIdx.z;
+  int m0 = blockIdx.y * rows_per_block;
+  int rows = min(rows_per_block, M - m0);
+  const float* dy = dY + (long long)e * sdY + (long long)m0 * lddy;
+  for (int i = threadIdx.x; i < rows * N; i += blockDim.x) sdy[i] = __ldg(dy + (long long)(i / N) * lddy + (i % N));
+  __syncthreads();
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < K) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    const __nv_bfloat16* x = X + (long long)e * sX + (long long)m0 * ldx + k;
+    for (int r = 0; r < rows; ++r) {
+      float xv = __bfloat162float(x[(long long)r * ldx]);
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(sdy[r * N + n], xv, acc[n]);
+    }
+    float* dw = dW + (long long)e * sdW + k;
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) atomicAdd(dw + (long long)n * lddw, acc[n]);
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x < N) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += sdy[r * N + threadIdx.x];
+    atomicAdd(db + (long long)e * sdb + threadIdx.x, s);
+  }
+}
+
+// db[e][n] += sum_m dZ_bf16[e][m][n]; grid (ceil(N/256), row chunks, E)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ dZ, long long ld,
+                                                          long long sZ, float* __restrict__ db, long long sdb, int M,
+                                                          int N, int rows_per_block) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int m0 = blockIdx.y * rows_per_block;
+  int m1 = min(M, m0 + rows_per_block);
+  const __nv_bfloat16* z = dZ + (long long)blockIdx.z * sZ + n;
+  float s = 0.f;
+  for (int m = m0; m < m1; ++m) s += __bfloat162float(z[(long long)m * ld]);
+  atomicAdd(db + (long long)blockIdx.z * sdb + n, s);
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+#define ST ((cudaStream_t)stream)
+
+// table: int64[n][7] = {src_off, rows, cols, dst_off, ldd, dstT_off, ldt} (host memory)
+extern "C" int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16,
+                                  int64_t dst_member_stride, const int64_t* table_host, int n_entries, int members,
+                                  void* stream) {
+  D3B_REQUIRE(src && dst_bf16 && table_host, "shadow_weights: null pointer");
+  D3B_REQUIRE(n_entries >= 1 && n_entries <= MAX_SHADOW && members >= 1, "shadow_weights: 1..%d entries", MAX_SHADOW);
+  ShadowTable t{};
+  t.n = n_entries;
+  long long biggest = 0;
+  for (int i = 0; i < n_entries; ++i) {
+    const int64_t* r = table_host + 7 * i;
+    t.e[i] = ShadowEntry{r[0], (int)r[1], (int)r[2], r[3], r[4], r[5], r[6]};
+    long long sz = r[1] * r[2];
+    if (sz > biggest) biggest = sz;
+  }
+  dim3 grid((unsigned)std::min<long long>(ceil_div_ll(biggest, 256), 256), n_entries, members);
+  shadow_kernel<<<grid, 256, 0, ST>>>(src, src_member_stride, (__nv_bfloat16*)dst_bf16, dst_member_stride, t);
+  return check_launch("shadow_weights");
+}
+
+extern "C" int d3b_to_bf16(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* dst_t,
+                           int64_t ldt, void* stream) {
+  D3B_REQUIRE(rows >= 0 && cols >= 1, "to_bf16: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(src && (dst || dst_t), "to_bf16: null pointer");
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
+  to_bf16_kernel<<<grid, 256, 0, ST>>>(src, lds, rows, cols, (__nv_bfloat16*)dst, ldd, (__nv_bfloat16*)dst_t, ldt);
+  return check_launch("to_bf16");
+}
+
+extern "C" int d3b_head_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, const float* w, int64_t ldw,
+                                     int64_t stride_w, const float* bias, int64_t stride_b, float* y, int64_t ldy,
+                                     int64_t stride_y, int rows, int out_features, int in_features, int members,
+                                     int act_tanh, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0, "head_forward_bf16: bad sizes");
+  D3B_REQUIRE(out_features >= 1 && out_features <= 32, "head_forward_bf16: out_features %d not in 1..32",
+              out_features);
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(x && w && y, "head_forward_bf16: null pointer");
+  long long warps = (long long)rows * members;
+  head_forward_bf16_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(
+      (const __nv_bfloat16*)x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features,
+      in_features, members, act_tanh);
+  return check_launch("head_forward_bf16");
+}
+
+extern "C" int d3b_head_backward_data_bf16(const float* dy, int64_t lddy, int64_t stride_dy, const float* w,
+                                           int64_t ldw, int64_t stride_w, void* dx, int64_t lddx, int64_t stride_dx,
+                                           void* dx_t, int64_t ldt, int64_t stride_dxt, const void* relu_src,
+                                           int64_t ld_src, int64_t stride_src, int rows, int out_features,
+                                           int in_features, int members, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0 && out_features >= 1, "head_backward_data_bf16: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dy && w && dx, "head_backward_data_bf16: null pointer");
+  dim3 grid(ceil_div(in_features, 32), ceil_div(rows, 32), members);
+  head_backward_data_bf16_kernel<<<grid, 256, 0, ST>>>(dy, lddy, stride_dy, w, ldw, stride_w, (__nv_bfloat16*)dx, lddx,
+                                                       stride_dx, (__nv_bfloat16*)dx_t, ldt, stride_dxt,
+                                                       (const __nv_bfloat16*)relu_src, ld_src, stride_src, rows,
+                                                       out_features, in_features);
+  return check_launch("head_backward_data_bf16");
+}
+
+extern "C" int d3b_head_backward_weight_bf16(const float* dy, int64_t lddy, int64_t stride_dy, const void* x,
+                                             int64_t ldx, int64_t stride_x, float* dw, int64_t lddw,
+                                             int64_t stride_dw, float* dbias, int64_t stride_db, int rows,
+                                             int out_features, int in_features, int members, void* stream) {
+  D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0, "head_backward_weight_bf16: bad sizes");
+  D3B_REQUIRE(out_features >= 1 && out_features <= 32, "head_backward_weight_bf16: out_features %d not in 1..32",
+              out_features);
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dy && x && dw, "head_backward_weight_bf16: null pointer");
+  int kblocks = ceil_div(in_features, 256);
+  int rpb = rows / (2 * kNumSM / (kblocks * members) + 1);
+  if (rpb < 4) rpb = 4;
+  if (rpb > 64) rpb = 64;
+  dim3 grid(kblocks, ceil_div(rows, rpb), members);
+  size_t smem = (size_t)rpb * out_features * sizeof(float);
+  const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+#define HBW(NM)                                                                                                   \
+  head_backward_weight_bf16_kernel<NM><<<grid, 256, smem, ST>>>(dy, lddy, stride_dy, xb, ldx, stride_x, dw, lddw, \
+                                                                stride_dw, dbias, stride_db, rows, out_features,  \
+                                                                in_features, rpb)
+  if (out_features <= 1) HBW(1);
+  else if (out_features <= 8) HBW(8);
+  else if (out_features <= 16) HBW(16);
+  else HBW(32);
+#undef HBW
+  return check_launch("head_backward_weight_bf16");
+}
+
+extern "C" int d3b_colsum_bf16(const void* dz, int64_t ld, int64_t stride_z, float* dbias, int64_t stride_db,
+                               int rows, int cols, int members, void* stream) {
+  D3B_REQUIRE(rows >= 0 && cols >= 1 && members >= 1, "colsum_bf16: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dz && dbias, "colsum_bf16: null pointer");
+  int nblocks = ceil_div(cols, 256);
+  int rpb = rows / (kNumSM / (nblocks * members) + 1);
+  if (rpb < 8) rpb = 8;
+  dim3 grid(nblocks, ceil_div(rows, rpb), members);
+  colsum_bf16_kernel<<<grid, 256, 0, ST>>>((const __nv_bfloat16*)dz, ld, stride_z, dbias, stride_db, rows, cols, rpb);
+  return check_launch("colsum_bf16");
+}

@@ -1,0 +1,353 @@
+// K2/K3 (bf16 mode): batched-ensemble dense layers on the 5th-gen tensor cores.
+//
+//   C[e][m][n] = sum_k A[e][m][k] * B[e][n][k]          (both operands K-major bf16, fp32 accumulate)
+//
+// tcgen05.mma (cta_group::1, M=128, N=BN<=256, K=16) issued by one elected thread, operands staged
+// by TMA (cp.async.bulk.tensor, SWIZZLE_128B) through a 4-stage mbarrier ring, accumulator in TMEM,
+// epilogue warps read it back with tcgen05.ld and fuse bias / ReLU / ReLU-mask / bf16 conversion /
+// transposed copy / fp32 RED accumulation.  All three layer GEMMs are expressed in this one form by
+// keeping K-major shadows (DESIGN.md §bf16 mode):
+//   forward : A = H_{l-1} [rows,K]      B = W_l   [N,K]      -> H_l   (+ H_l^T)
+//   dgrad   : A = dZ_l    [rows,N]      B = W_l^T [K,N]      -> dZ_{l-1} * [H_{l-1}>0] (+ transposed)
+//   wgrad   : A = dZ_l^T  [N,rows]      B = H_{l-1}^T [K,rows], split over rows -> RED.ADD into dW_l (fp32)
+// Replaces nn.Linear fwd/bwd of d3rlpy/models/torch/encoders.py:265-275 for every ensemble member
+// (q_functions/ensemble_q_function.py:144-146,168-170) in one launch.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace d3b {
+namespace umma {
+
+constexpr int BM = 128;       // UMMA_M
+constexpr int BK = 64;        // one 128-byte swizzle atom of bf16 along K
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+struct Params {
+  int M, N, K;            // logical sizes (C is M x N, reduction K)
+  int BN;                 // tile N (32/64/128/256)
+  int splits, kb_per_split;
+  int a_shared, b_shared; // operand shared by all members -> member coordinate 0
+  // epilogue
+  const float* bias; long long sBias; int relu;
+  const __nv_bfloat16* mask; long long ldmask, sMask;  // keep value where mask > 0
+  __nv_bfloat16* out_bf16; long long ldo, sO;
+  __nv_bfloat16* outT_bf16; long long ldt, sT;          // transposed copy [N][M]
+  float* out_f32; long long ldf, sF; int atomic;        // fp32 store or RED.ADD
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a pipeline bug becomes a trapped launch error instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 24)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100): 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address
+  d |= (uint64_t)0 << 16;                             // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// warps 0-3: epilogue (TMEM lanes 32w..32w+31), warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer
+__global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_stage_bytes = p.BN * BK * 2;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(smB + STAGES * b_stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
+  const int e = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int kb_begin = split * p.kb_per_split;
+  const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
+  const uint32_t tmem_cols = p.BN < 32 ? 32 : p.BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int ea = p.a_shared ? 0 : e, eb = p.b_shared ? 0 : e;
+      const uint32_t bytes = A_STAGE_BYTES + b_stage_bytes;
+      for (int kb = kb_begin, i = 0; kb < kb_end; ++kb, ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(empty + s, phase ^ 1);
+        mbar_expect_tx(full + s, bytes);
+        tma_load_3d(smA + s * A_STAGE_BYTES, &tmA, full + s, kb * BK, m0, ea);
+        tma_load_3d(smB + s * b_stage_bytes, &tmB, full + s, kb * BK, n0, eb);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int kb = kb_begin, i = 0; kb < kb_end; ++kb, ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (i / STAGES) & 1;
+        mbar_wait(full + s, phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint64_t adesc = make_desc(smem_u32(smA + s * A_STAGE_BYTES));
+        uint64_t bdesc = make_desc(smem_u32(smB + s * b_stage_bytes));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
+          mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(empty + s);  // frees the smem stage when these MMAs retire
+      }
+      mma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ---- epilogue: thread owns tile row 32*warp + lane
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const float* bias = p.bias ? p.bias + (long long)e * p.sBias : nullptr;
+    for (int c = 0; c < p.BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+      const int n = n0 + c;
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (bias && n + j < p.N) x += __ldg(bias + n + j);
+        if (p.relu) x = fmaxf(x, 0.f);
+        f[j] = x;
+      }
+      if (p.mask && row_ok) {
+        const __nv_bfloat16* mk = p.mask + (long long)e * p.sMask + (long long)m * p.ldmask + n;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j < p.N && !(__bfloat162float(mk[j]) > 0.f)) f[j] = 0.f;
+      }
+      if (p.out_bf16 && row_ok) {
+        __nv_bfloat16* o = p.out_bf16 + (long long)e * p.sO + (long long)m * p.ldo + n;
+        if (n + 31 < p.N && ((p.ldo & 7) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 u = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
+                                 pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
+            *reinterpret_cast<uint4*>(o + j) = u;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+        }
+      }
+      if (p.outT_bf16 && row_ok) {
+        __nv_bfloat16* o = p.outT_bf16 + (long long)e * p.sT + m;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n + j < p.N) o[(long long)(n + j) * p.ldt] = __float2bfloat16_rn(f[j]);
+      }
+      if (p.out_f32 && row_ok) {
+        float* o = p.out_f32 + (long long)e * p.sF + (long long)m * p.ldf + n;
+        if (p.atomic) {
+          if (n + 31 < p.N && ((p.ldf & 3) == 0) && ((((uintptr_t)o) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]),
+                           "f"(f[j + 2]), "f"(f[j + 3])
+                           : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) atomicAdd(o + j, f[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n + j < p.N) o[j] = f[j];
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 5) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// K-major bf16 operand [members][rows][k] with leading dim ld and member stride `stride` (elements).
+static int make_map(CUtensorMap* map, const void* base, int k, int rows, int members, long long ld, long long stride,
+                    int box_rows, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (((uintptr_t)base & 15) || (ld & 7) || (members > 1 && (stride & 7)))
+    return set_err(D3B_ERR_ARG, "umma_gemm: %s must be 16-byte aligned with ld/stride multiples of 8 bf16", what);
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)(members < 1 ? 1 : members)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)((members > 1 ? stride : ld * (long long)rows) * 2)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+  return D3B_OK;
+}
+
+}  // namespace umma
+}  // namespace d3b
+
+using namespace d3b;
+using namespace d3b::umma;
+
+// C[e] (M x N) = A[e] (M x K, ld lda) * B[e] (N x K, ldb)^T, bf16 operands.  stride_* == 0 => shared.
+// Outputs are optional: bf16 row-major, bf16 transposed, fp32 (store or RED.ADD when `atomic`).
+// splits > 1 partitions K (only meaningful with atomic fp32 output).
+extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const void* b, int64_t ldb,
+                             int64_t stride_b, int m, int n, int k, int members, int splits, const float* bias,
+                             int64_t stride_bias, int relu, const void* mask, int64_t ld_mask, int64_t stride_mask,
+                             void* out_bf16, int64_t ldo, int64_t stride_o, void* out_t_bf16, int64_t ldt,
+                             int64_t stride_t, float* out_f32, int64_t ldf, int64_t stride_f, int atomic,
+                             void* stream) {
+  D3B_REQUIRE(m >= 0 && n > 0 && k > 0 && members > 0, "umma_gemm: bad sizes");
+  if (m == 0) return D3B_OK;
+  D3B_REQUIRE(a && b, "umma_gemm: null operand");
+  D3B_REQUIRE(out_bf16 || out_t_bf16 || out_f32, "umma_gemm: no output requested");
+  D3B_REQUIRE(splits >= 1 && (splits == 1 || (atomic && out_f32 && !out_bf16 && !out_t_bf16 && !bias && !relu)),
+              "umma_gemm: split-K needs a pure fp32 RED epilogue");
+  int BN = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
+  Params p{};
+  p.M = m; p.N = n; p.K = k; p.BN = BN;
+  int num_kb = ceil_div(k, BK);
+  if (splits > num_kb) splits = num_kb;
+  p.kb_per_split = ceil_div(num_kb, splits);
+  p.splits = ceil_div(num_kb, p.kb_per_split);
+  p.a_shared = stride_a == 0; p.b_shared = stride_b == 0;
+  p.bias = bias; p.sBias = stride_bias; p.relu = relu;
+  p.mask = (const __nv_bfloat16*)mask; p.ldmask = ld_mask; p.sMask = stride_mask;
+  p.out_bf16 = (__nv_bfloat16*)out_bf16; p.ldo = ldo; p.sO = stride_o;
+  p.outT_bf16 = (__nv_bfloat16*)out_t_bf16; p.ldt = ldt; p.sT = stride_t;
+  p.out_f32 = out_f32; p.ldf = ldf; p.sF = stride_f; p.atomic = atomic;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a, k, m, p.a_shared ? 1 : members, lda, stride_a, BM, "A");
+  if (rc) return rc;
+  rc = make_map(&tmB, b, k, n, p.b_shared ? 1 : members, ldb, stride_b, BN, "B");
+  if (rc) return rc;
+  size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 2) + 16 * sizeof(uint64_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
+  umma_gemm_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("umma_gemm");
+}

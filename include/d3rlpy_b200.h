@@ -84,6 +84,39 @@ int d3b_head_backward_weight(const float* dy, int64_t lddy, int64_t stride_dy, c
                              int64_t stride_db, int rows, int out_features, int in_features, int members,
                              void* stream);
 
+/* ---- K2/K3 (bf16 mode): tcgen05 tensor-core dense layers ----------------------------
+ * umma_gemm: c[e] (m x n) = a[e] (m x k) * b[e] (n x k)^T with bf16 K-major operands staged by TMA and
+ *   fp32 accumulation in TMEM; stride_* == 0 shares the operand across members.  Forward, dgrad and
+ *   wgrad of nn.Linear (encoders.py:265-275, every ensemble member of ensemble_q_function.py:144-170 in
+ *   one launch) are all expressed in this form over K-major shadows.  Optional fused epilogue: +bias,
+ *   ReLU, ReLU-mask (keep where mask>0), bf16 output, transposed bf16 output, fp32 store / RED.ADD
+ *   (split-K over `splits` when accumulating weight gradients).
+ * shadow_weights / to_bf16: fp32 -> bf16 (+ transposed) shadows of parameters and first-layer inputs.
+ * head_*_bf16 / colsum_bf16: narrow heads and bias gradients over bf16 activations. */
+int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const void* b, int64_t ldb, int64_t stride_b, int m,
+                  int n, int k, int members, int splits, const float* bias, int64_t stride_bias, int relu,
+                  const void* mask, int64_t ld_mask, int64_t stride_mask, void* out_bf16, int64_t ldo,
+                  int64_t stride_o, void* out_t_bf16, int64_t ldt, int64_t stride_t, float* out_f32, int64_t ldf,
+                  int64_t stride_f, int atomic, void* stream);
+int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
+                       const int64_t* table_host, int n_entries, int members, void* stream);
+int d3b_to_bf16(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* dst_t, int64_t ldt,
+                void* stream);
+int d3b_head_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, const float* w, int64_t ldw,
+                          int64_t stride_w, const float* bias, int64_t stride_b, float* y, int64_t ldy,
+                          int64_t stride_y, int rows, int out_features, int in_features, int members, int act_tanh,
+                          void* stream);
+int d3b_head_backward_data_bf16(const float* dy, int64_t lddy, int64_t stride_dy, const float* w, int64_t ldw,
+                                int64_t stride_w, void* dx, int64_t lddx, int64_t stride_dx, void* dx_t, int64_t ldt,
+                                int64_t stride_dxt, const void* relu_src, int64_t ld_src, int64_t stride_src,
+                                int rows, int out_features, int in_features, int members, void* stream);
+int d3b_head_backward_weight_bf16(const float* dy, int64_t lddy, int64_t stride_dy, const void* x, int64_t ldx,
+                                  int64_t stride_x, float* dw, int64_t lddw, int64_t stride_dw, float* dbias,
+                                  int64_t stride_db, int rows, int out_features, int in_features, int members,
+                                  void* stream);
+int d3b_colsum_bf16(const void* dz, int64_t ld, int64_t stride_z, float* dbias, int64_t stride_db, int rows,
+                    int cols, int members, void* stream);
+
 /* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
  * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
  *   VectorEncoderWithAction.forward (encoders.py:328-339) plus the repeat/transpose/reshape of

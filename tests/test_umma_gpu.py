@@ -1,0 +1,176 @@
+"""GPU: the tcgen05/TMA/TMEM GEMM (bf16 operands, fp32 accumulate) and the bf16 support kernels vs
+torch on the same bf16-rounded operands.  Tolerance: accumulation-order only for fp32 outputs
+(1e-4 relative to the row scale), one bf16 ulp (2^-8) for bf16 outputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf(t):
+    return t.to(torch.bfloat16)
+
+
+def _gemm(L, a, b, m, n, k, E, *, lda, sa, ldb, sb, splits=1, bias=None, relu=0, mask=None, out_bf16=None,
+          out_t=None, out_f32=None, atomic=0):
+    p = lambda t: None if t is None else t.data_ptr()
+    L.umma_gemm(p(a), lda, sa, p(b), ldb, sb, m, n, k, E, splits, p(bias), 0 if bias is None else bias.shape[-1], relu,
+                p(mask), 0 if mask is None else mask.shape[-1], 0 if mask is None else mask.shape[-1] * mask.shape[-2],
+                p(out_bf16), 0 if out_bf16 is None else out_bf16.shape[-1],
+                0 if out_bf16 is None else out_bf16.shape[-1] * out_bf16.shape[-2],
+                p(out_t), 0 if out_t is None else out_t.shape[-1], 0 if out_t is None else out_t.shape[-1] * out_t.shape[-2],
+                p(out_f32), 0 if out_f32 is None else out_f32.shape[-1],
+                0 if out_f32 is None else out_f32.shape[-1] * out_f32.shape[-2], atomic, _st())
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K,E", [(300, 256, 256, 2), (128, 64, 64, 1), (7936, 256, 256, 2), (1000, 400, 320, 1)])
+def test_umma_forward_bias_relu_bf16_and_transposed(M, N, K, E):
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N)
+    a = _bf(torch.randn(E, M, K, generator=g)).to(dev)
+    b = _bf(torch.randn(E, N, K, generator=g) / math.sqrt(K)).to(dev)
+    bias = torch.randn(E, N, generator=g).to(dev)
+    Mp = (M + 7) // 8 * 8
+    out = torch.zeros(E, M, N, dtype=torch.bfloat16, device=dev)
+    out_t = torch.zeros(E, N, Mp, dtype=torch.bfloat16, device=dev)
+    out_f = torch.zeros(E, M, N, device=dev)
+    _gemm(L, a, b, M, N, K, E, lda=K, sa=M * K, ldb=K, sb=N * K, bias=bias, relu=1, out_bf16=out, out_t=out_t,
+          out_f32=out_f)
+    ref = torch.relu(torch.einsum("emk,enk->emn", a.float(), b.float()) + bias[:, None, :])
+    err = (out_f - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+    assert torch.equal(out, _bf(out_f))
+    assert torch.equal(out_t[:, :, :M], out.transpose(1, 2))
+
+
+def test_umma_small_k_zero_fill_shared_a_and_mask():
+    """First layer: K=23 (ld 24, TMA zero-fills to 64), input shared by all members; dgrad-style ReLU mask."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    M, N, K, E, ld = 520, 256, 23, 3, 24
+    g = torch.Generator().manual_seed(3)
+    a = torch.zeros(M, ld, dtype=torch.bfloat16)
+    a[:, :K] = _bf(torch.randn(M, K, generator=g))
+    a[:, K:] = 7.0  # padding garbage must be ignored: the tensor map's extent is K, not ld
+    b = torch.zeros(E, N, ld, dtype=torch.bfloat16)
+    b[:, :, :K] = _bf(torch.randn(E, N, K, generator=g))
+    b[:, :, K:] = -3.0
+    a, b = a.to(dev), b.to(dev)
+    mask = _bf(torch.randn(E, M, N, generator=g)).to(dev)
+    out = torch.zeros(E, M, N, dtype=torch.bfloat16, device=dev)
+    out_f = torch.zeros(E, M, N, device=dev)
+    _gemm(L, a, b, M, N, K, E, lda=ld, sa=0, ldb=ld, sb=N * ld, mask=mask, out_bf16=out, out_f32=out_f)
+    ref = torch.einsum("mk,enk->emn", a[:, :K].float(), b[:, :, :K].float()) * (mask.float() > 0)
+    assert (out_f - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    assert torch.equal(out, _bf(out_f))
+
+
+@pytest.mark.parametrize("R,No,Ki,E", [(7936, 256, 256, 2), (7936, 256, 23, 2), (256, 256, 17, 1), (200, 40, 24, 1)])
+def test_umma_wgrad_split_k_red_accumulate(R, No, Ki, E):
+    """dW[No][Ki] += dZ^T[No][R] . (X^T[Ki][R])^T over row splits, RED.ADD into a pre-loaded fp32 buffer."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R + Ki)
+    Rp = (R + 7) // 8 * 8
+    dzt = torch.zeros(E, No, Rp, dtype=torch.bfloat16)
+    dzt[:, :, :R] = _bf(torch.randn(E, No, R, generator=g) * 0.1)
+    xt = torch.zeros(E, Ki, Rp, dtype=torch.bfloat16)
+    xt[:, :, :R] = _bf(torch.randn(E, Ki, R, generator=g))
+    dzt, xt = dzt.to(dev), xt.to(dev)
+    dw0 = torch.randn(E, No, Ki, generator=g).to(dev)
+    dw = dw0.clone()
+    _gemm(L, dzt, xt, No, Ki, R, E, lda=Rp, sa=No * Rp, ldb=Rp, sb=Ki * Rp, splits=37, out_f32=dw, atomic=1)
+    ref = dw0 + torch.einsum("enr,ekr->enk", dzt[:, :, :R].float(), xt[:, :, :R].float())
+    assert (dw - ref).abs().max().item() <= 2e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_umma_narrow_n_fp32_store():
+    """dgrad restricted to the 6 action columns of layer 1 (B operand = rows [O, O+A) of W1^T)."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    M, H, O, A, E = 256, 256, 17, 6, 2
+    g = torch.Generator().manual_seed(9)
+    dz = _bf(torch.randn(E, M, H, generator=g)).to(dev)
+    w1t = _bf(torch.randn(E, O + A, H, generator=g)).to(dev)   # [K_in][N_out] = W1^T
+    dx = torch.full((E, M, A), 5.0, device=dev)
+    bview = w1t[:, O:, :]
+    L.umma_gemm(dz.data_ptr(), H, M * H, bview.data_ptr(), H, (O + A) * H, M, A, H, E, 1, None, 0, 0, None, 0, 0, None,
+                0, 0, None, 0, 0, dx.data_ptr(), A, M * A, 0, _st())
+    torch.cuda.synchronize()
+    ref = torch.einsum("emh,eah->ema", dz.float(), w1t[:, O:, :].float())
+    assert (dx - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+def test_bf16_support_kernels():
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    # to_bf16 with transposed copy
+    R, C = 523, 23
+    src = torch.randn(R, C, generator=g).to(dev)
+    dst = torch.zeros(R, 24, dtype=torch.bfloat16, device=dev)
+    dst_t = torch.zeros(C, 528, dtype=torch.bfloat16, device=dev)
+    L.to_bf16(src.data_ptr(), C, R, C, dst.data_ptr(), 24, dst_t.data_ptr(), 528, _st())
+    torch.cuda.synchronize()
+    assert torch.equal(dst[:, :C], _bf(src)) and torch.equal(dst_t[:, :R], _bf(src).t())
+    # colsum
+    E, M, N = 2, 1000, 256
+    dz = _bf(torch.randn(E, M, N, generator=g)).to(dev)
+    db = torch.zeros(E, N, device=dev)
+    L.colsum_bf16(dz.data_ptr(), N, M * N, db.data_ptr(), N, M, N, E, _st())
+    torch.cuda.synchronize()
+    ref = dz.float().sum(1)
+    assert (db - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    # shadow table: one 5x7 matrix -> row-major ld 8 and transposed ld 8, two members
+    msize = 64
+    params = torch.randn(2 * msize, generator=g).to(dev)
+    shadow = torch.zeros(2 * 128, dtype=torch.bfloat16, device=dev)
+    table = torch.tensor([[3 + 1, 5, 7, 0, 8, 40, 8]], dtype=torch.int64)  # src_off 4
+    L.shadow_weights(params.data_ptr(), msize, shadow.data_ptr(), 128, table.data_ptr(), 1, 2, _st())
+    torch.cuda.synchronize()
+    for e in range(2):
+        w = params[e * msize + 4:e * msize + 4 + 35].view(5, 7)
+        assert torch.equal(shadow[e * 128:e * 128 + 40].view(5, 8)[:, :7], _bf(w))
+        assert torch.equal(shadow[e * 128 + 40:e * 128 + 96].view(7, 8)[:, :5], _bf(w).t())
+    # heads over bf16 activations
+    M, K, N, E = 300, 256, 12, 2
+    x = _bf(torch.relu(torch.randn(E, M, K, generator=g))).to(dev)
+    w = (torch.randn(E, N, K, generator=g) / 16).to(dev)
+    b = torch.randn(E, N, generator=g).to(dev)
+    y = torch.zeros(E, M, N, device=dev)
+    L.head_forward_bf16(x.data_ptr(), K, M * K, w.data_ptr(), K, N * K, b.data_ptr(), N, y.data_ptr(), N, M * N, M, N,
+                        K, E, 0, _st())
+    ref = torch.einsum("emk,enk->emn", x.float(), w) + b[:, None, :]
+    torch.cuda.synchronize()
+    assert (y - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    dy = torch.randn(E, M, N, generator=g).to(dev)
+    Mp = (M + 7) // 8 * 8
+    dx = torch.zeros(E, M, K, dtype=torch.bfloat16, device=dev)
+    dxt = torch.zeros(E, K, Mp, dtype=torch.bfloat16, device=dev)
+    L.head_backward_data_bf16(dy.data_ptr(), N, M * N, w.data_ptr(), K, N * K, dx.data_ptr(), K, M * K,
+                              dxt.data_ptr(), Mp, K * Mp, x.data_ptr(), K, M * K, M, N, K, E, _st())
+    torch.cuda.synchronize()
+    ref = torch.einsum("emn,enk->emk", dy, w) * (x.float() > 0)
+    assert (dx.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
+    assert torch.equal(dxt[:, :, :M], dx.transpose(1, 2))
+    dw = torch.zeros(E, N, K, device=dev)
+    dbias = torch.zeros(E, N, device=dev)
+    L.head_backward_weight_bf16(dy.data_ptr(), N, M * N, x.data_ptr(), K, M * K, dw.data_ptr(), K, N * K,
+                                dbias.data_ptr(), N, M, N, K, E, _st())
+    torch.cuda.synchronize()
+    ref = torch.einsum("emn,emk->enk", dy, x.float())
+    assert (dw - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert (dbias - dy.sum(1)).abs().max().item() <= 1e-4 * dy.sum(1).abs().max().item()
