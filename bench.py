@@ -182,10 +182,11 @@ def run_reference(args, w):
 
 
 # ----------------------------------------------------------------------------------- our arm
-def build_algo(w, world_size=1, rank=0):
+def build_algo(w, world_size=1, rank=0, precision="bf16"):
     from d3rlpy_b200.algos import CQL, TD3PlusBC
 
     kw = dict(world_size=world_size, rank=rank) if world_size > 1 else {}
+    kw["precision"] = precision
     if w["algo"] == "cql":
         algo = CQL(actor_encoder_factory=w["hidden"], critic_encoder_factory=w["hidden"], batch_size=w["batch"],
                    n_action_samples=w["n"], n_critics=w["critics"], use_gpu=int(os.environ.get("LOCAL_RANK", "0")), **kw)
@@ -235,7 +236,7 @@ def run_ours(args, w):
     from d3rlpy_b200.dataset import MDPDataset, TransitionMiniBatch
 
     dev = torch.device("cuda", local)
-    algo = build_algo(w, world, rank)
+    algo = build_algo(w, world, rank, args.precision)
     impl = algo.impl
     B = w["batch"]  # per-GPU rows (weak scaling: global batch = B * world)
     obs, act, rew, term = make_dataset(w)
@@ -322,7 +323,7 @@ def run_ours(args, w):
     if rank == 0 and world == 1:
         # ---- roofline of the dominant kernel family (dense layers), measured live with CUDA events
         prof = kernel_profile(algo, hbs[0])
-        gemm = [v for k, v in prof.items() if k.startswith("linear_")]
+        gemm = [v for k, v in prof.items() if k.startswith("linear_") or k == "umma_gemm"]
         gemm_us = sum(v["us_per_update"] for v in gemm)
         all_us = sum(v["us_per_update"] for v in prof.values())
         peaks = {}
@@ -333,7 +334,9 @@ def run_ours(args, w):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         flops = req_gemm_flops(w)
         achieved = flops / (gemm_us * 1e-6) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_f32_kernel (linear_forward/backward_data/backward_weight)",
+        roof = {"bound": "tensor",
+                "kernel": "umma_gemm_kernel (tcgen05.mma, all dense-layer fwd/dgrad/wgrad launches)"
+                if args.precision == "bf16" else "gemm_f32_kernel (linear_forward/backward_data/backward_weight)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s",
                 "traffic": None, "algorithmic_gflop_per_update": flops / 1e9, "gemm_us_per_update": gemm_us,
@@ -353,8 +356,10 @@ def run_ours(args, w):
         line = {
             "metric": METRIC, "value": world * K / (total_ms * 1e-3), "unit": "updates/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "per_gpu_batch": B, "global_batch": B * world,
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "per_gpu_batch": B,
+                       "precision": "bf16 operands / fp32 accumulate, fp32 master weights and optimizer"
+                       if args.precision == "bf16" else "fp32", "global_batch": B * world,
                        "units": "updates of 256-transition minibatches per second, summed over ranks",
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
@@ -376,6 +381,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tensor-core GEMMs (bf16 operands, fp32 accumulate; parity 1e-2); "
+                         "fp32: SIMT GEMMs (parity 1e-5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     w = WORKLOADS[args.workload]

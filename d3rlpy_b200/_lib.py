@@ -53,7 +53,8 @@ class Lib:
     _prof = None
     _FLOP_ARGS = {"linear_forward": (11, 12, 13, 14), "linear_backward_data": (12, 13, 14, 15),
                   "linear_backward_weight": (11, 12, 13, 14), "head_forward": (11, 12, 13, 14),
-                  "head_backward_data": (12, 13, 14, 15), "head_backward_weight": (11, 12, 13, 14)}
+                  "head_backward_data": (12, 13, 14, 15), "head_backward_weight": (11, 12, 13, 14),
+                  "umma_gemm": (6, 7, 8, 9)}
 
     def start_profile(self, stream_obj) -> None:
         """Bracket every launch with CUDA events recorded on `stream_obj` (the launching stream)."""

@@ -63,7 +63,8 @@ class CQLImpl(DDPGBaseImpl):
     def _build_actor(self) -> None:
         O, A = self._observation_shape[0], self._action_size
         self._policy = DenseNet(O, self._actor_hidden, [("_mu", A), ("_logstd", A)], 1, self._device,
-                                trunk_prefix="_encoder.", with_target=True, seed_gen=self._gen)
+                                trunk_prefix="_encoder.", with_target=True, seed_gen=self._gen,
+                                precision=self._precision)
 
     def noise_layout(self, B):
         """Reference draw order per update."""
@@ -87,10 +88,10 @@ class CQLImpl(DDPGBaseImpl):
     def _p_policy(self, db):
         """Policy trunk + (mu|logstd) head on [obs; next_obs] (contiguous in the device batch)."""
         B, O, A = db.B, db.O, self._action_size
-        acts = [self.ws(f"pi_act{i}", 1, 2 * B, h) for i, h in enumerate(self._actor_hidden)]
+        acts = self._policy.ctx("pi", 2 * B, 1, True)
         head = self.ws("pi_head", 1, 2 * B, 2 * A)
         assert db.off["next_obs"] == db.off["obs"] + B * O, "obs/next_obs must be contiguous"
-        self._policy.forward("params", db.ptr("obs"), O, 0, 2 * B, acts, head, self._stream)
+        self._policy.forward("params", db.ptr("obs"), O, 2 * B, acts, head, self._stream)
         return acts, head
 
     def _p_temp(self, db, head):
@@ -147,7 +148,7 @@ class CQLImpl(DDPGBaseImpl):
         xt = self.ws("xt", B, O + A)
         L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, None, db.ptr("next_obs"), O, xt.data_ptr(),
                              O + A, None, None, B, 1, O, A, MIN_LOGSTD, MAX_LOGSTD, 1, st)
-        _, q_t = self._critic_rows_forward("target", xt, B, "tq")
+        _, q_t = self._critic_rows_forward("target", xt, B, "tq", train=False)
         return q_t
 
     def _p_critic(self, db, head, q_t=None, q_tpn=None, backward=True, sync_target=True, conservative=True,
@@ -168,8 +169,7 @@ class CQLImpl(DDPGBaseImpl):
         L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
                        self._alpha_threshold, 0, 1 if conservative else 0, self.metric_ptr(M_CRITIC), None, st)
         if backward:
-            self._q_func.backward(x, self._q_func.in_dim, 0, R, acts, dq, self._critic_scratch(R), st, d_head_ld=1,
-                                  d_head_stride=R)
+            self._q_func.backward(x, self._q_func.in_dim, R, acts, dq, st)
             self._allreduce(self._q_func.arena.grads)
             self._q_func.adam(self._critic_learning_rate, st, tau=self._tau if sync_target else None)
 
@@ -190,8 +190,8 @@ class CQLImpl(DDPGBaseImpl):
         self._allreduce(self._slots[32 + S_ACTOR:32 + S_ACTOR + 1])
         L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
         dxa = self.ws("a_dx", E, B, A)
-        self._q_func.backward(xa, O + A, 0, B, acts_c, dq, self._critic_scratch(B), st, weight_grads=False, dx=dxa,
-                              lddx=A, stride_dx=B * A, dx_col0=O, dx_cols=A, d_head_ld=1, d_head_stride=B)
+        self._q_func.backward(xa, O + A, B, acts_c, dq, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A,
+                              dx_col0=O, dx_cols=A)
         dhead = self.ws("pi_dhead", 1, B, 2 * A)
         L.sac_actor_backward(head.data_ptr(), 2 * A, eps.data_ptr(), dxa.data_ptr(), A, B * A, E, t.ptr("p"),
                              dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
@@ -202,7 +202,7 @@ class CQLImpl(DDPGBaseImpl):
 
     def _policy_backward_rows(self, db, acts_p, dhead, B):
         """acts_p hold 2B rows ([obs; next_obs]); E == 1 so the first B rows are a contiguous prefix."""
-        self._policy.backward(db.ptr("obs"), db.O, 0, B, acts_p, dhead, self._policy_scratch(B), self._stream)
+        self._policy.backward(db.ptr("obs"), db.O, B, acts_p, dhead, self._stream)
 
     def _allreduce(self, t):
         if self.world_size > 1:

@@ -27,6 +27,9 @@ class _ModuleView:
 
     def load_state_dict(self, sd):
         self._net.arena.load_state_dict(sd, self._which)
+        st = torch.cuda.current_stream(self._net.device)
+        self._net.refresh_shadow(self._which, st.cuda_stream)
+        st.synchronize()
 
     def parameters(self):
         return list(self.state_dict().values())
@@ -52,8 +55,9 @@ class _OptimView:
 class DDPGBaseImpl(ImplBase):
     def __init__(self, observation_shape, action_size, actor_learning_rate, critic_learning_rate,
                  actor_hidden: Sequence[int], critic_hidden: Sequence[int], gamma, tau, n_critics, use_gpu=0,
-                 scaler=None, action_scaler=None, reward_scaler=None, seed: int = 0, **kw):
+                 scaler=None, action_scaler=None, reward_scaler=None, seed: int = 0, precision: str = "fp32", **kw):
         super().__init__(observation_shape, action_size, use_gpu, scaler, action_scaler, reward_scaler, **kw)
+        self._precision = precision
         assert len(self._observation_shape) == 1, "vector observations only for actor-critic impls"
         self._actor_learning_rate, self._critic_learning_rate = actor_learning_rate, critic_learning_rate
         self._actor_hidden, self._critic_hidden = list(actor_hidden), list(critic_hidden)
@@ -68,10 +72,14 @@ class DDPGBaseImpl(ImplBase):
         O, A = self._observation_shape[0], self._action_size
         self._q_func = DenseNet(O + A, self._critic_hidden, [("_fc", 1)], self._n_critics, self._device,
                                 trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}", with_target=True,
-                                seed_gen=self._gen)
+                                seed_gen=self._gen, precision=self._precision)
         self._build_actor()
         self._q_func.arena.step = self._counters[C_CRITIC:C_CRITIC + 1]
         self._policy.arena.step = self._counters[C_ACTOR:C_ACTOR + 1]
+        for net in (self._q_func, self._policy):
+            net.refresh_shadow("params", self._stream)
+            net.refresh_shadow("target", self._stream)
+        self.sync()
 
     def _build_actor(self) -> None:
         raise NotImplementedError
@@ -102,33 +110,25 @@ class DDPGBaseImpl(ImplBase):
         return _OptimView(self._q_func, self._critic_learning_rate)
 
     # ------------------------------------------------------------------ shared program pieces
-    def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0):
-        """Runs the critic trunk+head on `rows` shared input rows; returns (acts, q[E,rows])."""
+    def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0, train=True):
+        """Runs the critic trunk+head on `rows` shared input rows; returns (ctx, q[E,rows])."""
         E = members or self._n_critics
-        acts = [self.ws(f"{tag}_act{i}", E, rows, h) for i, h in enumerate(self._critic_hidden)]
+        ctx = self._q_func.ctx(tag, rows, E, train)
         q = self.ws(f"{tag}_q", E, rows)
-        self._q_func.forward(which, x, self._q_func.in_dim, 0, rows, acts, q, self._stream, members=E,
-                             member0=member0)
-        return acts, q
-
-    def _critic_scratch(self, rows: int, members=None):
-        E = members or self._n_critics
-        hm = max(self._critic_hidden)
-        return (self.ws("c_scr0", E, rows, hm), self.ws("c_scr1", E, rows, hm))
-
-    def _policy_scratch(self, rows: int):
-        hm = max(self._actor_hidden)
-        return (self.ws("p_scr0", 1, rows, hm), self.ws("p_scr1", 1, rows, hm))
+        self._q_func.forward(which, x, self._q_func.in_dim, rows, ctx, q, self._stream, member0=member0)
+        return ctx, q
 
     def update_critic_target(self) -> None:
         """soft_sync(targ_q_func, q_func, tau) (ddpg_impl.py:201-204)."""
         a = self._q_func.arena
         self._lib.soft_sync(a.target.data_ptr(), a.params.data_ptr(), a.size, self._tau, self._stream)
+        self._q_func.refresh_shadow("target", self._stream)
 
     def update_actor_target(self) -> None:
         """soft_sync(targ_policy, policy, tau) (ddpg_impl.py:206-209)."""
         a = self._policy.arena
         self._lib.soft_sync(a.target.data_ptr(), a.params.data_ptr(), a.size, self._tau, self._stream)
+        self._policy.refresh_shadow("target", self._stream)
 
     def _tick(self, *slots):
         mask = 0

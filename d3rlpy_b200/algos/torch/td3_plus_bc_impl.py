@@ -22,7 +22,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
     def _build_actor(self) -> None:
         O, A = self._observation_shape[0], self._action_size
         self._policy = DenseNet(O, self._actor_hidden, [("_fc", A)], 1, self._device, trunk_prefix="_encoder.",
-                                with_target=True, seed_gen=self._gen)
+                                with_target=True, seed_gen=self._gen, precision=self._precision)
 
     def noise_layout(self, B):
         return {"target": ("normal", (B, self._action_size))}
@@ -31,14 +31,14 @@ class TD3PlusBCImpl(DDPGBaseImpl):
     def _p_target(self, db):
         """TD3Impl.compute_target (td3_impl.py:61-78) -> q_t[E,B] (min is taken inside critic_loss)."""
         B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
-        acts = [self.ws(f"tp_act{i}", 1, B, h) for i, h in enumerate(self._actor_hidden)]
         a_next = self.ws("tp_a", 1, B, A)
-        self._policy.forward("target", db.ptr("next_obs"), O, 0, B, acts, a_next, st, head_tanh=True)
+        self._policy.forward("target", db.ptr("next_obs"), O, B, self._policy.ctx("tp", B, 1, False), a_next, st,
+                             head_tanh=True)
         xt = self.ws("xt", B, O + A)
         L.concat_rows(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
                       self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt.data_ptr(), O + A, B, 1, O, A,
                       st)
-        _, q_t = self._critic_rows_forward("target", xt, B, "tq")
+        _, q_t = self._critic_rows_forward("target", xt, B, "tq", train=False)
         return q_t
 
     def _p_critic(self, db, q_t=None, q_tpn=None, sync_target=False):
@@ -57,17 +57,16 @@ class TD3PlusBCImpl(DDPGBaseImpl):
 
     def _p_critic_step(self, db, xc, acts, dq, sync_target):
         B = db.B
-        self._q_func.backward(xc, self._q_func.in_dim, 0, B, acts, dq, self._critic_scratch(B), self._stream,
-                              d_head_ld=1, d_head_stride=B)
+        self._q_func.backward(xc, self._q_func.in_dim, B, acts, dq, self._stream)
         self._allreduce(self._q_func.arena.grads)
         self._q_func.adam(self._critic_learning_rate, self._stream, tau=self._tau if sync_target else None)
 
     def _p_actor(self, db):
         """compute_actor_loss (td3_plus_bc_impl.py:64-70) + backward + Adam; only member 0 is evaluated."""
         B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
-        acts_p = [self.ws(f"pi_act{i}", 1, B, h) for i, h in enumerate(self._actor_hidden)]
+        acts_p = self._policy.ctx("pi", B, 1, True)
         a = self.ws("pi_a", 1, B, A)
-        self._policy.forward("params", db.ptr("obs"), O, 0, B, acts_p, a, st, head_tanh=True)
+        self._policy.forward("params", db.ptr("obs"), O, B, acts_p, a, st, head_tanh=True)
         xa = self.ws("xa", B, O + A)
         L.concat_rows(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa.data_ptr(), O + A, B, 1, O, A, st)
         acts_c, q0 = self._critic_rows_forward("params", xa, B, "aq", members=1)
@@ -78,12 +77,11 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq.data_ptr(), B, B, 1,
                            self.metric_ptr(M_ACTOR), st)
         dxa = self.ws("a_dx", B, A)
-        self._q_func.backward(xa, O + A, 0, B, acts_c, dq, self._critic_scratch(B, 1), st, weight_grads=False,
-                              dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O, dx_cols=A, members=1, d_head_ld=1,
-                              d_head_stride=B)
+        self._q_func.backward(xa, O + A, B, acts_c, dq, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A,
+                              dx_col0=O, dx_cols=A)
         dz = self.ws("pi_dz", 1, B, A)
         L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, inv_b, st)
-        self._policy.backward(db.ptr("obs"), O, 0, B, acts_p, dz, self._policy_scratch(B), st)
+        self._policy.backward(db.ptr("obs"), O, B, acts_p, dz, st)
         self._allreduce(self._policy.arena.grads)
         self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
 

@@ -23,12 +23,14 @@ namespace umma {
 constexpr int BM = 128;       // UMMA_M
 constexpr int BK = 64;        // one 128-byte swizzle atom of bf16 along K
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
 struct Params {
   int M, N, K;            // logical sizes (C is M x N, reduction K)
   int BN;                 // tile N (32/64/128/256)
+  int lg_bn;              // log2(BN)
+  int stages;             // operand ring depth (3 when a mask tile needs the space, else 4)
   int splits, kb_per_split;
   int a_shared, b_shared; // operand shared by all members -> member coordinate 0
   // epilogue
@@ -37,6 +39,7 @@ struct Params {
   __nv_bfloat16* out_bf16; long long ldo, sO;
   __nv_bfloat16* outT_bf16; long long ldt, sT;          // transposed copy [N][M]
   float* out_f32; long long ldf, sF; int atomic;        // fp32 store or RED.ADD
+  long long* dbg;                                       // optional: per-CTA phase timestamps (8 slots)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -115,21 +118,27 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// warps 0-3: epilogue (TMEM lanes 32w..32w+31), warp 4: TMA producer, warp 5: TMEM alloc + MMA issuer
-__global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+// warps 0-7: epilogue (TMEM lanes 32(w%4).., column half w/4), warp 8: TMA producer, warp 9: TMEM alloc + MMA issuer
+constexpr int EPI_THREADS = 256;
+constexpr int NTHREADS = EPI_THREADS + 64;
+
+__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                            const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = p.BN * BK * 2;
   uint8_t* smA = smem;
+  const int STAGES = p.stages;
   uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = (uint64_t*)(smB + STAGES * b_stage_bytes);
+  uint64_t* bars = (uint64_t*)(smB + STAGES * b_stage_bytes);  // 256 B reserved: barriers + TMEM slot
   uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tmem_full = bars + 2 * MAX_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = p.dbg ? p.dbg + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
   const int e = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 5) {
+  if (warp == 9) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(tmem_cols)
                  : "memory");
@@ -156,8 +165,9 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();  // setup done
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       const int ea = p.a_shared ? 0 : e, eb = p.b_shared ? 0 : e;
       const uint32_t bytes = A_STAGE_BYTES + b_stage_bytes;
@@ -169,8 +179,9 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         tma_load_3d(smA + s * A_STAGE_BYTES, &tmA, full + s, kb * BK, m0, ea);
         tma_load_3d(smB + s * b_stage_bytes, &tmB, full + s, kb * BK, n0, eb);
       }
+      if (dbg) dbg[2] = clock64();  // all TMA issued
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         int s = i % STAGES;
         uint32_t phase = (i / STAGES) & 1;
         mbar_wait(full + s, phase);
+        if (dbg && i == 0) dbg[3] = clock64();  // first stage landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t adesc = make_desc(smem_u32(smA + s * A_STAGE_BYTES));
         uint64_t bdesc = make_desc(smem_u32(smB + s * b_stage_bytes));
@@ -190,79 +202,216 @@ __global__ void __launch_bounds__(192, 1) umma_gemm_kernel(const __grid_constant
         mma_commit(empty + s);  // frees the smem stage when these MMAs retire
       }
       mma_commit(tmem_full);    // accumulator complete
+      if (dbg) dbg[4] = clock64();  // all MMAs issued
     }
   } else {
-    // ---- epilogue: thread owns tile row 32*warp + lane
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    const float* bias = p.bias ? p.bias + (long long)e * p.sBias : nullptr;
-    for (int c = 0; c < p.BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-      const int n = n0 + c;
-      float f[32];
+    // ---- epilogue (warps 0-7, 256 threads).  Phase 0 (overlaps the mainloop): stage bias and the ReLU
+    // mask tile in shared memory with coalesced loads.  Phase 1: thread owns tile row 32*warp+lane, reads
+    // the accumulator from TMEM, applies bias/ReLU/mask and writes the tile (row-major bf16, transposed
+    // bf16 or fp32) into the now-free operand stages.  Phase 2: fully coalesced 16-byte global stores / REDs.
+    const int t = threadIdx.x;  // 0..EPI_THREADS-1
+    const int BN = p.BN;
+    const int ldc = BN + 8, ldts = BM + 8, ldfs = BN + 4;
+    float* bias_s = (float*)(smem + p.stages * (A_STAGE_BYTES + b_stage_bytes) + 256);
+    __nv_bfloat16* mask_s = (__nv_bfloat16*)((uint8_t*)bias_s + 1024);
+    __nv_bfloat16* c_s = (__nv_bfloat16*)smem;
+    __nv_bfloat16* t_s = c_s + BM * ldc;
+    float* f_s = (float*)smem;
+    const int lg_nvec = p.lg_bn - 3;           // BN/8 bf16 vectors per tile row (BN is a power of two)
+    const int nvec_mask = (1 << lg_nvec) - 1;
+    if (p.bias) {
+      const float* bias = p.bias + (long long)e * p.sBias;
+      for (int j = t; j < BN; j += EPI_THREADS) bias_s[j] = (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
+    }
+    if (p.mask) {
+      // coalesced 16-byte loads, 8 in flight per thread
+      const __nv_bfloat16* mk = p.mask + (long long)e * p.sMask;
+      const bool vec_ok = ((p.ldmask & 7) == 0) && ((((uintptr_t)mk) & 15) == 0);
+      const int total = BM << lg_nvec;
+      for (int v0 = t; v0 < total; v0 += EPI_THREADS * 8) {
+        uint4 val[8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (bias && n + j < p.N) x += __ldg(bias + n + j);
-        if (p.relu) x = fmaxf(x, 0.f);
-        f[j] = x;
-      }
-      if (p.mask && row_ok) {
-        const __nv_bfloat16* mk = p.mask + (long long)e * p.sMask + (long long)m * p.ldmask + n;
+        for (int u = 0; u < 8; ++u) {
+          int v = v0 + u * EPI_THREADS;
+          int r = v >> lg_nvec, cv = (v & nvec_mask) << 3;
+          int m = m0 + r, n = n0 + cv;
+          val[u] = make_uint4(0, 0, 0, 0);
+          if (v < total && m < p.M) {
+            const __nv_bfloat16* src = mk + (long long)m * p.ldmask + n;
+            if (vec_ok && n + 7 < p.N) {
+              val[u] = __ldg((const uint4*)src);
+            } else {
+              __nv_bfloat16 tmp[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n + j < p.N && !(__bfloat162float(mk[j]) > 0.f)) f[j] = 0.f;
-      }
-      if (p.out_bf16 && row_ok) {
-        __nv_bfloat16* o = p.out_bf16 + (long long)e * p.sO + (long long)m * p.ldo + n;
-        if (n + 31 < p.N && ((p.ldo & 7) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 u = make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]),
-                                 pack_bf16(f[j + 4], f[j + 5]), pack_bf16(f[j + 6], f[j + 7]));
-            *reinterpret_cast<uint4*>(o + j) = u;
+              for (int j = 0; j < 8; ++j) tmp[j] = (n + j < p.N) ? src[j] : __float2bfloat16_rn(0.f);
+              val[u] = *reinterpret_cast<uint4*>(tmp);
+            }
           }
-        } else {
+        }
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n + j < p.N) o[j] = __float2bfloat16_rn(f[j]);
+        for (int u = 0; u < 8; ++u) {
+          int v = v0 + u * EPI_THREADS;
+          if (v < total) *reinterpret_cast<uint4*>(mask_s + (v >> lg_nvec) * ldc + ((v & nvec_mask) << 3)) = val[u];
         }
       }
-      if (p.outT_bf16 && row_ok) {
-        __nv_bfloat16* o = p.outT_bf16 + (long long)e * p.sT + m;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mbar_wait(tmem_full, 0);
+    if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // accumulator ready
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // thread owns tile row 32*(warp%4)+lane and the column half warp/4 (BN=32: a single half)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int half_cols = BN >= 64 ? (BN >> 1) : BN;
+    const int c_begin = (warp >> 2) * half_cols;
+    const int c_end = (BN >= 64 || warp < 4) ? c_begin + half_cols : c_begin;
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+      float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n + j < p.N) o[(long long)(n + j) * p.ldt] = __float2bfloat16_rn(f[j]);
+      for (int j = 0; j < 32; j += 4) {
+        float4 bv = p.bias ? *reinterpret_cast<const float4*>(bias_s + c + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[j] = __uint_as_float(v[j]) + bv.x;
+        f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+        f[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
+        f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
       }
-      if (p.out_f32 && row_ok) {
-        float* o = p.out_f32 + (long long)e * p.sF + (long long)m * p.ldf + n;
-        if (p.atomic) {
-          if (n + 31 < p.N && ((p.ldf & 3) == 0) && ((((uintptr_t)o) & 15) == 0)) {
+      if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(f[j]), "f"(f[j + 1]),
-                           "f"(f[j + 2]), "f"(f[j + 3])
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (p.mask) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 mv = *reinterpret_cast<const uint4*>(mask_s + row * ldc + c + j);
+          const __nv_bfloat16* mb = reinterpret_cast<const __nv_bfloat16*>(&mv);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (!(__bfloat162float(mb[q]) > 0.f)) f[j + q] = 0.f;
+        }
+      }
+      if (p.out_f32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(f_s + row * ldfs + c + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+        if (p.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(c_s + row * ldc + c + j) =
+                make_uint4(pack_bf16(f[j], f[j + 1]), pack_bf16(f[j + 2], f[j + 3]), pack_bf16(f[j + 4], f[j + 5]),
+                           pack_bf16(f[j + 6], f[j + 7]));
+        }
+        if (p.outT_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) t_s[(c + j) * ldts + row] = __float2bfloat16_rn(f[j]);
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- phase 2: coalesced global traffic (shift/mask indexing, 4 vectors in flight per thread)
+    if (p.out_f32) {
+      float* o = p.out_f32 + (long long)e * p.sF;
+      const bool vec_ok = ((p.ldf & 3) == 0) && ((((uintptr_t)o) & 15) == 0);
+      const int lg4 = p.lg_bn - 2, m4 = (1 << lg4) - 1;
+      const int total = BM << lg4;
+      for (int v0 = t; v0 < total; v0 += EPI_THREADS * 4) {
+        float4 val[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int v = v0 + u * EPI_THREADS;
+          if (v < total) val[u] = *reinterpret_cast<const float4*>(f_s + (v >> lg4) * ldfs + ((v & m4) << 2));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          int v = v0 + u * EPI_THREADS;
+          int m = m0 + (v >> lg4), n = n0 + ((v & m4) << 2);
+          if (v >= total || m >= p.M || n >= p.N) continue;
+          float* dst = o + (long long)m * p.ldf + n;
+          if (vec_ok && n + 3 < p.N) {
+            if (p.atomic)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(val[u].x), "f"(val[u].y),
+                           "f"(val[u].z), "f"(val[u].w)
                            : "memory");
+            else
+              *reinterpret_cast<float4*>(dst) = val[u];
           } else {
+            float tmp[4] = {val[u].x, val[u].y, val[u].z, val[u].w};
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) atomicAdd(o + j, f[j]);
+            for (int j = 0; j < 4; ++j) {
+              if (n + j < p.N) {
+                if (p.atomic) atomicAdd(dst + j, tmp[j]);
+                else dst[j] = tmp[j];
+              }
+            }
           }
-        } else {
+        }
+      }
+    } else {
+      if (p.out_bf16) {
+        __nv_bfloat16* o = p.out_bf16 + (long long)e * p.sO;
+        const bool vec_ok = ((p.ldo & 7) == 0) && ((((uintptr_t)o) & 15) == 0);
+        const int total = BM << lg_nvec;
+        for (int v0 = t; v0 < total; v0 += EPI_THREADS * 4) {
+          uint4 val[4];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n + j < p.N) o[j] = f[j];
+          for (int u = 0; u < 4; ++u) {
+            int v = v0 + u * EPI_THREADS;
+            if (v < total) val[u] = *reinterpret_cast<const uint4*>(c_s + (v >> lg_nvec) * ldc + ((v & nvec_mask) << 3));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int v = v0 + u * EPI_THREADS;
+            int m = m0 + (v >> lg_nvec), n = n0 + ((v & nvec_mask) << 3);
+            if (v >= total || m >= p.M || n >= p.N) continue;
+            __nv_bfloat16* dst = o + (long long)m * p.ldo + n;
+            if (vec_ok && n + 7 < p.N) {
+              *reinterpret_cast<uint4*>(dst) = val[u];
+            } else {
+              const __nv_bfloat16* tb = reinterpret_cast<const __nv_bfloat16*>(&val[u]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (n + j < p.N) dst[j] = tb[j];
+            }
+          }
+        }
+      }
+      if (p.outT_bf16) {
+        __nv_bfloat16* o = p.outT_bf16 + (long long)e * p.sT;
+        const bool vec_ok = ((p.ldt & 7) == 0) && ((((uintptr_t)o) & 15) == 0);
+        const int total = BN << 4;  // BM/8 = 16 vectors of 8 rows per output row
+        for (int v0 = t; v0 < total; v0 += EPI_THREADS * 4) {
+          uint4 val[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int v = v0 + u * EPI_THREADS;
+            if (v < total) val[u] = *reinterpret_cast<const uint4*>(t_s + (v >> 4) * ldts + ((v & 15) << 3));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            int v = v0 + u * EPI_THREADS;
+            int n = n0 + (v >> 4), m = m0 + ((v & 15) << 3);
+            if (v >= total || n >= p.N || m >= p.M) continue;
+            __nv_bfloat16* dst = o + (long long)n * p.ldt + m;
+            if (vec_ok && m + 7 < p.M) {
+              *reinterpret_cast<uint4*>(dst) = val[u];
+            } else {
+              const __nv_bfloat16* tb = reinterpret_cast<const __nv_bfloat16*>(&val[u]);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (m + j < p.M) dst[j] = tb[j];
+            }
+          }
         }
       }
     }
   }
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();  // epilogue (warp 0) done
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 5) {
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+  if (warp == 9) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -308,6 +457,13 @@ static int make_map(CUtensorMap* map, const void* base, int k, int rows, int mem
 using namespace d3b;
 using namespace d3b::umma;
 
+static long long* g_umma_dbg = nullptr;
+// test/profiling hook: device buffer receiving 8 clock64() phase stamps per CTA of the next launches
+extern "C" int d3b_umma_set_debug(void* device_buffer) {
+  g_umma_dbg = (long long*)device_buffer;
+  return D3B_OK;
+}
+
 // C[e] (M x N) = A[e] (M x K, ld lda) * B[e] (N x K, ldb)^T, bf16 operands.  stride_* == 0 => shared.
 // Outputs are optional: bf16 row-major, bf16 transposed, fp32 (store or RED.ADD when `atomic`).
 // splits > 1 partitions K (only meaningful with atomic fp32 output).
@@ -321,11 +477,16 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
   if (m == 0) return D3B_OK;
   D3B_REQUIRE(a && b, "umma_gemm: null operand");
   D3B_REQUIRE(out_bf16 || out_t_bf16 || out_f32, "umma_gemm: no output requested");
+  D3B_REQUIRE(!(out_f32 && (out_bf16 || out_t_bf16)), "umma_gemm: fp32 and bf16 outputs are mutually exclusive");
   D3B_REQUIRE(splits >= 1 && (splits == 1 || (atomic && out_f32 && !out_bf16 && !out_t_bf16 && !bias && !relu)),
               "umma_gemm: split-K needs a pure fp32 RED epilogue");
   int BN = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
+  // Few tiles: halve the tile so that twice as many CTAs exist and two of them fit on one SM
+  // (~100 KB shared memory, 128 TMEM columns each) — one CTA's epilogue overlaps the other's mainloop.
+  if (BN == 256 && (long long)ceil_div(m, BM) * ceil_div(n, 256) * members * splits < 2LL * kNumSM) BN = 128;
   Params p{};
   p.M = m; p.N = n; p.K = k; p.BN = BN;
+  p.lg_bn = BN == 256 ? 8 : (BN == 128 ? 7 : (BN == 64 ? 6 : 5));
   int num_kb = ceil_div(k, BK);
   if (splits > num_kb) splits = num_kb;
   p.kb_per_split = ceil_div(num_kb, splits);
@@ -336,18 +497,32 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
   p.out_bf16 = (__nv_bfloat16*)out_bf16; p.ldo = ldo; p.sO = stride_o;
   p.outT_bf16 = (__nv_bfloat16*)out_t_bf16; p.ldt = ldt; p.sT = stride_t;
   p.out_f32 = out_f32; p.ldf = ldf; p.sF = stride_f; p.atomic = atomic;
+  p.dbg = g_umma_dbg;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a, k, m, p.a_shared ? 1 : members, lda, stride_a, BM, "A");
   if (rc) return rc;
   rc = make_map(&tmB, b, k, n, p.b_shared ? 1 : members, ldb, stride_b, BN, "B");
   if (rc) return rc;
-  size_t smem = 1024 + (size_t)STAGES * (A_STAGE_BYTES + BN * BK * 2) + 16 * sizeof(uint64_t);
+  // epilogue staging needs: bf16 tile (+ transposed tile) or fp32 tile inside the operand stages, and
+  // bias (1 KB) + mask tile after them
+  size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)BN * BK * 2;
+  size_t need_epi = out_f32 ? (size_t)BM * (BN + 4) * 4
+                            : (size_t)BM * (BN + 8) * 2 + (out_t_bf16 ? (size_t)BN * (BM + 8) * 2 : 0);
+  size_t tail = 256 + 1024 + (mask ? (size_t)BM * (BN + 8) * 2 : 0);
+  int stages = BN == 256 ? MAX_STAGES : 3;
+  if (mask && !out_t_bf16 && BN <= 128) stages = 2;  // keeps two CTAs per SM with the mask tile resident
+  while (stages > 2 && 1024 + stages * stage_bytes + tail > 227 * 1024) --stages;
+  while ((size_t)stages * stage_bytes < need_epi) ++stages;  // tiny tiles: stages are smaller than the C tile
+  D3B_REQUIRE(stages <= MAX_STAGES && 1024 + stages * stage_bytes + tail <= 227 * 1024,
+              "umma_gemm: tile does not fit shared memory (BN=%d)", BN);
+  p.stages = stages;
+  size_t smem = 1024 + stages * stage_bytes + tail;
   static bool attr_set = false;
   if (!attr_set) {
     D3B_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
-  umma_gemm_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("umma_gemm");
 }

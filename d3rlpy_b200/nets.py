@@ -3,11 +3,16 @@ one launch per layer.  Mirrors VectorEncoder/VectorEncoderWithAction + `_fc`/`_m
 (d3rlpy/models/torch/encoders.py:236-339, q_functions/mean_q_function.py:61-72,
 policies.py:47-59,82-97,127-181, imitators.py:13-72) without nn.Module or autograd: forward and the
 hand-written backward are sequences of C-ABI kernel launches on the caller's stream.
+
+Two arithmetic modes:
+  * "fp32": SIMT FFMA GEMMs, everything fp32 (parity tolerance 1e-5).
+  * "bf16": tcgen05 tensor-core GEMMs over bf16 K-major shadows of weights/activations with fp32
+    accumulation, fp32 master weights, fp32 heads/losses/optimizer (parity tolerance 1e-2).
 """
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
@@ -23,16 +28,50 @@ def _p(t) -> Optional[int]:
     return t.data_ptr()
 
 
+def _a8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+class Ctx:
+    """Per-call-site workspace of one forward(/backward): saved activations and gradient scratch."""
+
+    def __init__(self, net: "DenseNet", rows: int, members: int, train: bool):
+        self.rows, self.members, self.train = rows, members, train
+        dev, E = net.device, members
+        hid = net.hidden
+        if net.precision == "fp32":
+            self.acts = [torch.zeros(E, rows, h, dtype=torch.float32, device=dev) for h in hid]
+            hm = max(hid)
+            self.scratch = (torch.zeros(E, rows, hm, dtype=torch.float32, device=dev),
+                            torch.zeros(E, rows, hm, dtype=torch.float32, device=dev)) if train else None
+        else:
+            bf = torch.bfloat16
+            self.ldr = _a8(rows)
+            self.ldk0 = _a8(net.in_dim)
+            self.xb = torch.zeros(rows, self.ldk0, dtype=bf, device=dev)
+            self.xbt = torch.zeros(net.in_dim, self.ldr, dtype=bf, device=dev) if train else None
+            self.hb = [torch.zeros(E, rows, _a8(h), dtype=bf, device=dev) for h in hid]
+            # H_l^T feeds the weight gradient of layer l+1 (the last trunk output feeds the narrow head instead)
+            self.hbt = [torch.zeros(E, h, self.ldr, dtype=bf, device=dev) if train and i < len(hid) - 1 else None
+                        for i, h in enumerate(hid)]
+            if train:
+                hm = _a8(max(hid + [net.in_dim]))
+                self.dz = (torch.zeros(E, rows, hm, dtype=bf, device=dev), torch.zeros(E, rows, hm, dtype=bf, device=dev))
+                self.dzt = torch.zeros(E, hm, self.ldr, dtype=bf, device=dev)
+
+
 class DenseNet:
     """trunk: in_dim -> hidden[0] -> ... -> hidden[-1] (ReLU), head: hidden[-1] -> head_out."""
 
     def __init__(self, in_dim: int, hidden: Sequence[int], heads: Sequence[Tuple[str, int]], members: int,
                  device, trunk_prefix: str, member_key: str = "{name}", with_target: bool = False,
-                 seed_gen: Optional[torch.Generator] = None):
+                 seed_gen: Optional[torch.Generator] = None, precision: str = "fp32"):
+        assert precision in ("fp32", "bf16")
         self.in_dim, self.hidden, self.members = in_dim, list(hidden), members
         self.heads = list(heads)
         self.head_out = sum(n for _, n in heads)
         self.trunk_prefix = trunk_prefix
+        self.precision = precision
         entries = []
         d = in_dim
         for i, h in enumerate(self.hidden):
@@ -55,7 +94,10 @@ class DenseNet:
                                 exports=exports)
         self.feat = d
         self.device = device
+        self._ctx: Dict[str, Ctx] = {}
         self._init_params(seed_gen)
+        if precision == "bf16":
+            self._build_shadow(with_target)
 
     def _init_params(self, gen):
         """nn.Linear default init: U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias."""
@@ -68,6 +110,45 @@ class DenseNet:
                     v = (torch.rand(shape, generator=gen) * 2 - 1) * bound
                     a.view(name, e).copy_(v)
         a.sync_target_from_params()
+
+    # ------------------------------------------------------------------ bf16 shadows of the trunk weights
+    def _build_shadow(self, with_target: bool):
+        """Per member: for every trunk layer a row-major bf16 copy W [N][ld8(K)] (forward B operand) and a
+        transposed copy W^T [K][ld8(N)] (dgrad B operand) — both K-major for the tcgen05 GEMM."""
+        rows, off = [], 0
+        self._sh_w, self._sh_wt = [], []
+        d = self.in_dim
+        for i, h in enumerate(self.hidden):
+            ldk, ldn = _a8(d), _a8(h)
+            w_off = off
+            off += h * ldk
+            wt_off = off
+            off += d * ldn
+            self._sh_w.append((w_off, ldk))
+            self._sh_wt.append((wt_off, ldn))
+            rows.append([self.arena.offsets[f"{self.trunk_prefix}_fcs.{i}.weight"], h, d, w_off, ldk, wt_off, ldn])
+            d = h
+        self.shadow_member = _a8(off)
+        self._table = torch.tensor(rows, dtype=torch.int64)
+        n = self.shadow_member * self.members
+        self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.shadow_target = torch.zeros(n, dtype=torch.bfloat16, device=self.device) if with_target else None
+
+    def refresh_shadow(self, which: str, stream: int):
+        """Re-derive the bf16 shadows from the fp32 master weights (after Adam / soft_sync / load)."""
+        if self.precision != "bf16":
+            return
+        src = self.arena.params if which == "params" else self.arena.target
+        dst = self.shadow if which == "params" else self.shadow_target
+        lib().shadow_weights(_p(src), self.arena.member_size, _p(dst), self.shadow_member, self._table.data_ptr(),
+                             self._table.shape[0], self.members, stream)
+
+    def _sw(self, which, i, member0=0):
+        base = self.shadow if which == "params" else self.shadow_target
+        return base.data_ptr() + 2 * (member0 * self.shadow_member + self._sh_w[i][0]), self._sh_w[i][1]
+
+    def _swt(self, i, member0=0):
+        return self.shadow.data_ptr() + 2 * (member0 * self.shadow_member + self._sh_wt[i][0]), self._sh_wt[i][1]
 
     # ------------------------------------------------------------------ pointers
     def _w(self, which, i, member=0):
@@ -82,78 +163,132 @@ class DenseNet:
     def _hb(self, which, member=0):
         return self.arena.addr(which, "__head.bias", member)
 
-    def alloc_acts(self, rows: int, members: Optional[int] = None) -> List[torch.Tensor]:
+    def ctx(self, tag: str, rows: int, members: Optional[int] = None, train: bool = True) -> Ctx:
         E = members or self.members
-        return [torch.empty(E, rows, h, dtype=torch.float32, device=self.device) for h in self.hidden]
+        c = self._ctx.get(tag)
+        if c is None or c.rows != rows or c.members != E or c.train != train:
+            c = Ctx(self, rows, E, train)
+            self._ctx[tag] = c
+        return c
 
     # ------------------------------------------------------------------ forward
-    def forward(self, which: str, x, ldx: int, stride_x: int, rows: int, acts: List[torch.Tensor], head_out,
-                stream: int, head_tanh: bool = False, members: Optional[int] = None, member0: int = 0):
-        """x: tensor or raw pointer, [rows, ldx] (stride_x=0: same input for every member).
-        acts[l]: [E, rows, hidden[l]]; head_out: [E, rows, head_out]."""
+    def forward(self, which: str, x, ldx: int, rows: int, ctx: Ctx, head_out, stream: int,
+                head_tanh: bool = False, member0: int = 0):
+        """x: fp32 [rows, ldx], shared by all members.  Saves activations in ctx; head_out: fp32
+        [E, rows, head_out] (None = trunk only)."""
         L = lib()
-        E = members or self.members
-        ms = self.arena.member_size
-        cur, ld, sx = _p(x), ldx, stride_x
-        d = self.in_dim
-        for i, h in enumerate(self.hidden):
-            y = acts[i]
-            L.linear_forward(cur, ld, sx, self._w(which, i, member0), d, ms, self._b(which, i, member0), ms,
-                             _p(y), h, rows * h, rows, h, d, E, 1, stream)
-            cur, ld, sx, d = _p(y), h, rows * h, h
-        if head_out is not None:
-            n = self.head_out
-            L.head_forward(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
-                           _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
-
-    # ------------------------------------------------------------------ backward
-    def backward(self, x, ldx: int, stride_x: int, rows: int, acts: List[torch.Tensor], d_head,
-                 scratch: Tuple[torch.Tensor, torch.Tensor], stream: int, weight_grads: bool = True,
-                 dx=None, lddx: int = 0, stride_dx: int = 0, dx_col0: int = 0, dx_cols: int = 0,
-                 members: Optional[int] = None, member0: int = 0, d_head_ld: Optional[int] = None,
-                 d_head_stride: Optional[int] = None):
-        """d_head: [E, rows, head_out] gradient w.r.t. the (pre-activation) head output.
-        Accumulates dW/db into arena.grads (RED) when weight_grads; optionally writes the gradient
-        w.r.t. input columns [dx_col0, dx_col0+dx_cols) into dx."""
-        L = lib()
-        E = members or self.members
+        E = ctx.members
         ms = self.arena.member_size
         n = self.head_out
-        feat = self.feat
-        ldh = d_head_ld if d_head_ld is not None else n
-        sdh = d_head_stride if d_head_stride is not None else rows * n
-        last = acts[-1]
-        if weight_grads:
-            L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, rows * feat, self._hw("grads", member0), feat,
-                                   ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
-        dcur = scratch[0]
-        L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat, rows * feat,
-                             _p(last), feat, rows * feat, rows, n, feat, E, stream)
-        which = 0
-        for i in range(len(self.hidden) - 1, -1, -1):
-            h = self.hidden[i]
-            d_in = self.hidden[i - 1] if i > 0 else self.in_dim
-            if i > 0:
-                inp, ldi, si = _p(acts[i - 1]), d_in, rows * d_in
-            else:
-                inp, ldi, si = _p(x), ldx, stride_x
+        if self.precision == "fp32":
+            cur, ld, sx = _p(x), ldx, 0
+            d = self.in_dim
+            for i, h in enumerate(self.hidden):
+                y = ctx.acts[i]
+                L.linear_forward(cur, ld, sx, self._w(which, i, member0), d, ms, self._b(which, i, member0), ms,
+                                 _p(y), h, rows * h, rows, h, d, E, 1, stream)
+                cur, ld, sx, d = _p(y), h, rows * h, h
+            if head_out is not None:
+                L.head_forward(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
+                               _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
+            return
+        # ---- bf16 mode
+        L.to_bf16(_p(x), ldx, rows, self.in_dim, _p(ctx.xb), ctx.ldk0, _p(ctx.xbt), ctx.ldr if ctx.train else 0, stream)
+        cur, ld, sx = _p(ctx.xb), ctx.ldk0, 0
+        d = self.in_dim
+        sms = self.shadow_member
+        for i, h in enumerate(self.hidden):
+            wptr, ldw = self._sw(which, i, member0)
+            y, yt = ctx.hb[i], ctx.hbt[i]
+            lh = _a8(h)
+            L.umma_gemm(cur, ld, sx, wptr, ldw, sms, rows, h, d, E, 1, self._b(which, i, member0), ms, 1,
+                        None, 0, 0, _p(y), lh, rows * lh, _p(yt), ctx.ldr if yt is not None else 0,
+                        h * ctx.ldr if yt is not None else 0, None, 0, 0, 0, stream)
+            cur, ld, sx, d = _p(y), lh, rows * lh, h
+        if head_out is not None:
+            L.head_forward_bf16(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
+                                _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, x, ldx: int, rows: int, ctx: Ctx, d_head, stream: int, weight_grads: bool = True,
+                 dx=None, lddx: int = 0, stride_dx: int = 0, dx_col0: int = 0, dx_cols: int = 0, member0: int = 0):
+        """d_head: fp32 [E, rows, head_out] gradient w.r.t. the (pre-activation) head output.
+        Accumulates dW/db into arena.grads (RED) when weight_grads; optionally writes the gradient
+        w.r.t. input columns [dx_col0, dx_col0+dx_cols) into dx (fp32 [E, rows, dx_cols])."""
+        L = lib()
+        E = ctx.members
+        ms = self.arena.member_size
+        n, feat = self.head_out, self.feat
+        ldh, sdh = n, rows * n
+        nl = len(self.hidden)
+        if self.precision == "fp32":
+            last = ctx.acts[-1]
             if weight_grads:
-                L.linear_backward_weight(_p(dcur), h, rows * h, inp, ldi, si, self._w("grads", i, member0), d_in, ms,
-                                         self._b("grads", i, member0), ms, rows, h, d_in, E, stream)
+                L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, rows * feat, self._hw("grads", member0),
+                                       feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
+            dcur = ctx.scratch[0]
+            L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat,
+                                 rows * feat, _p(last), feat, rows * feat, rows, n, feat, E, stream)
+            which = 0
+            for i in range(nl - 1, -1, -1):
+                h = self.hidden[i]
+                d_in = self.hidden[i - 1] if i > 0 else self.in_dim
+                if i > 0:
+                    inp, ldi, si = _p(ctx.acts[i - 1]), d_in, rows * d_in
+                else:
+                    inp, ldi, si = _p(x), ldx, 0
+                if weight_grads:
+                    L.linear_backward_weight(_p(dcur), h, rows * h, inp, ldi, si, self._w("grads", i, member0), d_in,
+                                             ms, self._b("grads", i, member0), ms, rows, h, d_in, E, stream)
+                if i > 0:
+                    dnext = ctx.scratch[1 - which]
+                    L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", i, member0), d_in, ms, _p(dnext),
+                                           d_in, rows * d_in, inp, ldi, si, rows, h, d_in, E, stream)
+                    dcur, which = dnext, 1 - which
+                elif dx is not None:
+                    L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", 0, member0) + 4 * dx_col0, d_in,
+                                           ms, _p(dx), lddx, stride_dx, None, 0, 0, rows, h, dx_cols, E, stream)
+            return
+        # ---- bf16 mode: every GEMM is C = A B^T over K-major bf16 operands
+        last = ctx.hb[-1]
+        sms = self.shadow_member
+        ldr = ctx.ldr
+        lf = _a8(feat)
+        if weight_grads:
+            L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),
+                                        feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
+        dcur, which = ctx.dz[0], 0
+        L.head_backward_data_bf16(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), lf,
+                                  rows * lf, _p(ctx.dzt) if weight_grads else None, ldr, feat * ldr, _p(last), lf,
+                                  rows * lf, rows, n, feat, E, stream)
+        for i in range(nl - 1, -1, -1):
+            h = self.hidden[i]
+            lh = _a8(h)
+            d_in = self.hidden[i - 1] if i > 0 else self.in_dim
+            ldi = _a8(d_in)
+            if weight_grads:
+                L.colsum_bf16(_p(dcur), lh, rows * lh, self._b("grads", i, member0), ms, rows, h, E, stream)
+                if i > 0:
+                    bt, sbt = _p(ctx.hbt[i - 1]), d_in * ldr
+                else:
+                    bt, sbt = _p(ctx.xbt), 0
+                tiles = -(-h // 128) * -(-d_in // 256) * E
+                splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
+                # dW_i[h][d_in] += dZ_i^T[h][rows] . (H_{i-1}^T[d_in][rows])^T
+                L.umma_gemm(_p(ctx.dzt), ldr, h * ldr, bt, ldr, sbt, h, d_in, rows, E, splits, None, 0, 0, None, 0, 0,
+                            None, 0, 0, None, 0, 0, self._w("grads", i, member0), d_in, ms, 1, stream)
             if i > 0:
-                dnext = scratch[1 - which]
-                L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", i, member0), d_in, ms, _p(dnext), d_in,
-                                       rows * d_in, inp, ldi, si, rows, h, d_in, E, stream)
+                dnext = ctx.dz[1 - which]
+                wt, ldwt = self._swt(i, member0)
+                # dZ_{i-1} = (dZ_i W_i) * [H_{i-1} > 0]   (B operand = W_i^T [d_in][h])
+                L.umma_gemm(_p(dcur), lh, rows * lh, wt, ldwt, sms, rows, d_in, h, E, 1, None, 0, 0, _p(ctx.hb[i - 1]),
+                            ldi, rows * ldi, _p(dnext), ldi, rows * ldi,
+                            _p(ctx.dzt) if weight_grads else None, ldr, d_in * ldr, None, 0, 0, 0, stream)
                 dcur, which = dnext, 1 - which
             elif dx is not None:
-                L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", 0, member0) + 4 * dx_col0, d_in, ms,
-                                       _p(dx), lddx, stride_dx, None, 0, 0, rows, h, dx_cols, E, stream)
-
-    def alloc_scratch(self, rows: int, members: Optional[int] = None):
-        E = members or self.members
-        hm = max(self.hidden)
-        return (torch.empty(E, rows, hm, dtype=torch.float32, device=self.device),
-                torch.empty(E, rows, hm, dtype=torch.float32, device=self.device))
+                wt, ldwt = self._swt(0, member0)
+                L.umma_gemm(_p(dcur), lh, rows * lh, wt + 2 * dx_col0 * ldwt, ldwt, sms, rows, dx_cols, h, E, 1, None, 0,
+                            0, None, 0, 0, None, 0, 0, None, 0, 0, _p(dx), lddx, stride_dx, 0, stream)
 
     # ------------------------------------------------------------------ optimizer
     def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
@@ -161,3 +296,6 @@ class DenseNet:
         lib().adam_step(_p(a.params), _p(a.grads), _p(a.exp_avg), _p(a.exp_avg_sq),
                         _p(a.target) if tau is not None else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
                         tau if tau is not None else 0.0, 1, stream)
+        self.refresh_shadow("params", stream)
+        if tau is not None and a.target is not None:
+            self.refresh_shadow("target", stream)

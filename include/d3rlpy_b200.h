@@ -98,6 +98,7 @@ int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const void* b, i
                   const void* mask, int64_t ld_mask, int64_t stride_mask, void* out_bf16, int64_t ldo,
                   int64_t stride_o, void* out_t_bf16, int64_t ldt, int64_t stride_t, float* out_f32, int64_t ldf,
                   int64_t stride_f, int atomic, void* stream);
+int d3b_umma_set_debug(void* device_buffer); /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);
 int d3b_to_bf16(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* dst_t, int64_t ldt,

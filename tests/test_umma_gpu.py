@@ -43,8 +43,8 @@ def test_umma_forward_bias_relu_bf16_and_transposed(M, N, K, E):
     out = torch.zeros(E, M, N, dtype=torch.bfloat16, device=dev)
     out_t = torch.zeros(E, N, Mp, dtype=torch.bfloat16, device=dev)
     out_f = torch.zeros(E, M, N, device=dev)
-    _gemm(L, a, b, M, N, K, E, lda=K, sa=M * K, ldb=K, sb=N * K, bias=bias, relu=1, out_bf16=out, out_t=out_t,
-          out_f32=out_f)
+    _gemm(L, a, b, M, N, K, E, lda=K, sa=M * K, ldb=K, sb=N * K, bias=bias, relu=1, out_bf16=out, out_t=out_t)
+    _gemm(L, a, b, M, N, K, E, lda=K, sa=M * K, ldb=K, sb=N * K, bias=bias, relu=1, out_f32=out_f)
     ref = torch.relu(torch.einsum("emk,enk->emn", a.float(), b.float()) + bias[:, None, :])
     err = (out_f - ref).abs().max().item()
     assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
@@ -69,7 +69,8 @@ def test_umma_small_k_zero_fill_shared_a_and_mask():
     mask = _bf(torch.randn(E, M, N, generator=g)).to(dev)
     out = torch.zeros(E, M, N, dtype=torch.bfloat16, device=dev)
     out_f = torch.zeros(E, M, N, device=dev)
-    _gemm(L, a, b, M, N, K, E, lda=ld, sa=0, ldb=ld, sb=N * ld, mask=mask, out_bf16=out, out_f32=out_f)
+    _gemm(L, a, b, M, N, K, E, lda=ld, sa=0, ldb=ld, sb=N * ld, mask=mask, out_bf16=out)
+    _gemm(L, a, b, M, N, K, E, lda=ld, sa=0, ldb=ld, sb=N * ld, mask=mask, out_f32=out_f)
     ref = torch.einsum("mk,enk->emn", a[:, :K].float(), b[:, :, :K].float()) * (mask.float() > 0)
     assert (out_f - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
     assert torch.equal(out, _bf(out_f))
