@@ -167,6 +167,40 @@ int d3b_td3bc_actor_backward(const float* a, int64_t lda, const float* a_data, i
                              int64_t lddx, float* dz, int64_t lddz, int batch, int act_dim, float inv_batch,
                              void* stream);
 
+/* ---- K8: BCQ (imitators.py:63-86, bcq_impl.py:115-226, policies.py:94-97, q_functions/__init__.py:8-63) --
+ * vae_sample_rows: z = mu + exp(clamp(logstd)) eps, decoder rows [obs | z], KL(N(mu,sd)||N(0,1)) sum.
+ * vae_recon / vae_backward / vae_finalize: MSE + beta*KL loss of ConditionalVAE.compute_error and its gradient.
+ * residual_rows / residual_backward: a = clamp(sampled + scale*tanh(z), -1, 1) of DeterministicResidualPolicy.
+ * bcq_target_reduce: max over sampled actions of (1-lam) max_e Q + lam min_e Q.
+ * neg_mean_seed: actor loss -mean(Q_0) and its seed gradient. */
+int d3b_vae_sample_rows(const float* head, int64_t ld_head, const float* eps, const float* obs, int64_t ldo, float* x,
+                        int64_t ldx, float* kl_sum, int batch, int obs_dim, int latent, float min_logstd,
+                        float max_logstd, void* stream);
+int d3b_vae_recon(const float* y, const float* actions, int64_t lda, float* dpre, float* sq_sum, int batch,
+                  int act_dim, float inv_batch, void* stream);
+int d3b_vae_backward(const float* head, int64_t ld_head, const float* eps, const float* dz, int64_t lddz,
+                     float* dhead, int64_t ld_dhead, int batch, int latent, float min_logstd, float max_logstd,
+                     float beta, float inv_batch, void* stream);
+int d3b_vae_finalize(const float* sums, int act_dim, int latent, float beta, float inv_batch, float* metric,
+                     void* stream);
+int d3b_residual_rows(const float* z, int64_t ldz, const float* sampled, int64_t lds, const float* obs, int64_t ldo,
+                      float* x, int64_t ldx, float scale, int rows, int n_repeat, int obs_dim, int act_dim,
+                      void* stream);
+int d3b_residual_backward(const float* z, int64_t ldz, const float* sampled, int64_t lds, const float* da,
+                          int64_t ldda, float* dz, int64_t lddz, float scale, int batch, int act_dim, void* stream);
+int d3b_bcq_target_reduce(const float* q, int64_t stride_q, float* q_tpn, int batch, int n_actions, int members,
+                          float lam, void* stream);
+int d3b_neg_mean_seed(const float* q0, float* dq, float* loss_sum, int batch, float inv_batch, void* stream);
+/* ---- K9 (loss side): DQN/DoubleDQN target and DiscreteCQL loss (dqn_impl.py:97-171, cql_impl.py:279-302,
+ * mean_q_function.py:26-42, utility.py:27-32) */
+int d3b_dqn_target(const float* q_online, int64_t stride_qo, const float* q_targ, int64_t stride_qt, float* q_tpn,
+                   int batch, int n_actions, int members, void* stream);
+int d3b_dcql_loss(const float* q, int64_t stride_q, const float* q_tpn, const float* actions, const float* rewards,
+                  const float* terminals, const float* n_steps, float gamma, float alpha, float* dq,
+                  int64_t stride_dq, float* sums, int batch, int n_actions, int members, float inv_batch,
+                  int conservative, void* stream);
+int d3b_dcql_finalize(const float* sums, float inv_batch, float alpha, int conservative, float* metric, void* stream);
+
 /* ---- K10: optimizer / target sync ----------------------------------------------
  * adam_step: torch.optim.Adam.step as built by AdamFactory (d3rlpy/models/optimizers.py:106-138;
  *   call sites ddpg_impl.py:150,181, sac_impl.py:141, cql_impl.py:137, bcq_impl.py:159,
