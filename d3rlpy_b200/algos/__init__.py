@@ -1,3 +1,5 @@
 from .base import VectorEncoderFactory  # noqa: F401
+from .bcq import BCQ  # noqa: F401
 from .cql import CQL  # noqa: F401
+from .dqn import DQN, DiscreteCQL, DoubleDQN, PixelEncoderFactory  # noqa: F401
 from .td3_plus_bc import TD3PlusBC  # noqa: F401

@@ -1,0 +1,79 @@
+"""DQN / DoubleDQN / DiscreteCQL: same constructors/defaults as d3rlpy.algos.{DQN,DoubleDQN,DiscreteCQL}
+(d3rlpy/algos/dqn.py:69-202, d3rlpy/algos/cql.py:317-372)."""
+from __future__ import annotations
+
+from typing import Any, Dict
+
+from .base import IMPL_NOT_INITIALIZED_ERROR, AlgoBase, _hidden_units
+from .torch.dqn_impl import DiscreteCQLImpl, DoubleDQNImpl, DQNImpl
+
+
+class PixelEncoderFactory:
+    """Same constructor as d3rlpy.models.encoders.PixelEncoderFactory (filters, feature_size)."""
+
+    TYPE = "pixel"
+
+    def __init__(self, filters=None, feature_size: int = 512, activation: str = "relu", use_batch_norm: bool = False,
+                 dropout_rate=None):
+        if activation != "relu" or use_batch_norm or dropout_rate is not None:
+            raise ValueError("B200 path supports ReLU conv encoders without BN/dropout")
+        self.filters = list(filters) if filters is not None else [(32, 8, 4), (64, 4, 2), (64, 3, 1)]
+        self.feature_size = feature_size
+
+
+class DQN(AlgoBase):
+    IMPL = DQNImpl
+
+    def __init__(self, *, learning_rate: float = 6.25e-5, optim_factory=None, encoder_factory="default",
+                 q_func_factory="mean", batch_size: int = 32, n_frames: int = 1, n_steps: int = 1, gamma: float = 0.99,
+                 n_critics: int = 1, target_update_interval: int = 8000, use_gpu=0, scaler=None, reward_scaler=None,
+                 impl=None, seed: int = 0, **kwargs: Any):
+        super().__init__(batch_size, n_frames, n_steps, gamma, scaler, None, reward_scaler, use_gpu, kwargs)
+        if q_func_factory != "mean":
+            raise ValueError("only the mean Q function is on the accelerated path")
+        if optim_factory is not None:
+            raise ValueError("only AdamFactory() defaults are on the accelerated path")
+        self._learning_rate, self._n_critics = learning_rate, n_critics
+        self._target_update_interval = target_update_interval
+        self._encoder_factory = encoder_factory
+        self._impl, self._seed = impl, seed
+
+    def _impl_kwargs(self) -> Dict[str, Any]:
+        return {}
+
+    def _create_impl(self, observation_shape, action_size) -> None:
+        ef = self._encoder_factory
+        kw = dict(self._kwargs)
+        if len(observation_shape) == 3:
+            if isinstance(ef, PixelEncoderFactory) or hasattr(ef, "feature_size") or hasattr(ef, "_feature_size"):
+                kw["feature_size"] = getattr(ef, "feature_size", None) or getattr(ef, "_feature_size")
+                kw["filters"] = getattr(ef, "filters", None) or getattr(ef, "_filters", None)
+            hidden = []
+        else:
+            hidden = _hidden_units(ef, [256, 256])
+        kw.update(self._impl_kwargs())
+        self._impl = self.IMPL(observation_shape=observation_shape, action_size=action_size,
+                               learning_rate=self._learning_rate, hidden=hidden, gamma=self._gamma,
+                               n_critics=self._n_critics, use_gpu=self._use_gpu, scaler=self._scaler,
+                               reward_scaler=self._reward_scaler, seed=self._seed, **kw)
+        self._impl.build()
+
+    def _update(self, batch) -> Dict[str, float]:
+        """dqn.py:127-132: update, then hard target copy when grad_step % interval == 0 (pre-increment)."""
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        return self._impl.update_fused(batch, self._grad_step % self._target_update_interval == 0)
+
+
+class DoubleDQN(DQN):
+    IMPL = DoubleDQNImpl
+
+
+class DiscreteCQL(DoubleDQN):
+    IMPL = DiscreteCQLImpl
+
+    def __init__(self, *, alpha: float = 1.0, **kw: Any):
+        super().__init__(**kw)
+        self._alpha = alpha
+
+    def _impl_kwargs(self):
+        return {"alpha": self._alpha}

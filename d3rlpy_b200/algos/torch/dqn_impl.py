@@ -1,0 +1,203 @@
+"""DQN / DoubleDQN / DiscreteCQL on B200: mirrors DQNImpl, DoubleDQNImpl (d3rlpy/algos/torch/dqn_impl.py:19-171)
+and DiscreteCQLImpl (d3rlpy/algos/torch/cql_impl.py:246-302).
+
+One update = online-net forward on s' (Double-DQN action), target-net forward on s', ONE online-net
+forward + backward on s shared by the Huber TD term and the conservative term (the reference evaluates
+`self._q_func(obs_t)` twice, cql_impl.py:295,300, with identical values), Adam, and the hard target copy
+when `grad_step % target_update_interval == 0` (pre-increment, dqn.py:130-131)."""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from ...nets import ConvNet, DenseNet
+from .base import ImplBase
+from .ddpg_impl import C_CRITIC, _ModuleView, _OptimView
+
+M_LOSS = 0
+S_LOSS = 0
+
+
+class DQNImpl(ImplBase):
+    DISCRETE = True
+    DOUBLE = False
+    CONSERVATIVE = False
+
+    def __init__(self, observation_shape, action_size, learning_rate, hidden: Sequence[int], gamma, n_critics,
+                 feature_size: int = 512, filters=None, use_gpu=0, scaler=None, reward_scaler=None, seed: int = 0,
+                 precision: str = "fp32", alpha: float = 1.0, **kw):
+        super().__init__(observation_shape, action_size, use_gpu, scaler, None, reward_scaler, **kw)
+        self._learning_rate, self._hidden, self._gamma, self._n_critics = learning_rate, list(hidden), gamma, n_critics
+        self._feature_size, self._filters = feature_size, filters
+        self._precision, self._alpha = precision, alpha
+        self._gen = torch.Generator().manual_seed(seed)
+        self._seed = seed
+        self._q_func = None
+
+    @property
+    def _pixel(self) -> bool:
+        return len(self._observation_shape) == 3
+
+    def build(self) -> None:
+        A, E = self._action_size, self._n_critics
+        if self._pixel:
+            sc = self._scaler
+            is_pixel_scaler = sc == "pixel" or getattr(sc, "TYPE", None) == "pixel"
+            if sc is not None and not is_pixel_scaler:
+                raise ValueError("pixel observations support scaler=None or 'pixel'")
+            self._q_func = ConvNet(self._observation_shape, [("_fc", A)], E, self._device,
+                                   feature_size=self._feature_size, filters=self._filters,
+                                   member_key="_q_funcs.{e}.{name}", with_target=True, seed_gen=self._gen,
+                                   precision="fp32", input_divisor=255.0 if is_pixel_scaler else 1.0)
+        else:
+            self._q_func = DenseNet(self._observation_shape[0], self._hidden, [("_fc", A)], E, self._device,
+                                    trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}", with_target=True,
+                                    seed_gen=self._gen, precision=self._precision)
+        self._q_func.arena.step = self._counters[C_CRITIC:C_CRITIC + 1]
+        self._q_func.refresh_shadow("params", self._stream)
+        self._q_func.refresh_shadow("target", self._stream)
+        self.sync()
+
+    def _apply_scalers(self, db):
+        if not self._pixel:
+            super()._apply_scalers(db)
+
+    # ------------------------------------------------------------------ reference-visible properties
+    @property
+    def q_function(self):
+        return _ModuleView(self._q_func)
+
+    @property
+    def targ_q_function(self):
+        return _ModuleView(self._q_func, "target")
+
+    @property
+    def q_function_optim(self):
+        return _OptimView(self._q_func, self._learning_rate)
+
+    # ------------------------------------------------------------------ program pieces
+    def _forward(self, which, db, field, tag, train):
+        """Q values [E, B, A] of the chosen parameter set on obs / next_obs."""
+        B, A, E, st = db.B, self._action_size, self._n_critics, self._stream
+        q = self.ws(f"{tag}_q", E, B, A)
+        if self._pixel:
+            ctx = self._q_func.ctx(tag, B, E, train)
+            self._q_func.forward(which, db.ptr(field), B, ctx, q, st)
+        else:
+            ctx = self._q_func.ctx(tag, B, E, train)
+            self._q_func.forward(which, db.ptr(field), db.O, B, ctx, q, st)
+        return ctx, q
+
+    def _p_target(self, db):
+        """DQNImpl.compute_target (dqn_impl.py:133-141) / DoubleDQNImpl.compute_target (:162-171)."""
+        B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
+        _, q_t = self._forward("target", db, "next_obs", "tq", False)
+        q_sel = self._forward("params", db, "next_obs", "oq", False)[1] if self.DOUBLE else q_t
+        q_tpn = self.ws("q_tpn", B)
+        L.dqn_target(q_sel.data_ptr(), B * A, q_t.data_ptr(), B * A, q_tpn.data_ptr(), B, A, E, st)
+        return q_tpn
+
+    def _p_loss(self, db, q_tpn, step=True):
+        """compute_loss (dqn_impl.py:113-131; cql_impl.py:279-302) [+ backward + Adam (dqn_impl.py:97-111)]."""
+        B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
+        ctx, q = self._forward("params", db, "obs", "lq", True)
+        dq = self.ws("dq", E, B, A)
+        inv_b = 1.0 / (B * self.world_size)
+        cons = 1 if self.CONSERVATIVE else 0
+        L.dcql_loss(q.data_ptr(), B * A, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
+                    db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A, self.sums_ptr(S_LOSS), B, A, E,
+                    inv_b, cons, st)
+        self._allreduce(self._slots[32 + S_LOSS:32 + S_LOSS + 2])
+        L.dcql_finalize(self.sums_ptr(S_LOSS), inv_b, self._alpha, cons, self.metric_ptr(M_LOSS), st)
+        if step:
+            if self._pixel:
+                self._q_func.backward(B, ctx, dq, st)
+            else:
+                self._q_func.backward(db.ptr("obs"), db.O, B, ctx, dq, st)
+            self._allreduce(self._q_func.arena.grads)
+            self._q_func.adam(self._learning_rate, st)
+
+    def _p_hard_sync(self):
+        a = self._q_func.arena
+        self._lib.hard_sync(a.target.data_ptr(), a.params.data_ptr(), a.size, self._stream)
+        self._q_func.refresh_shadow("target", self._stream)
+
+    def _allreduce(self, t):
+        if self.world_size > 1:
+            from ...parallel import allreduce_sum
+
+            allreduce_sum(t, self._stream_obj)
+
+    def _tick(self, *slots):
+        mask = 0
+        for s in slots:
+            mask |= 1 << s
+        self._lib.tick(self._counters.data_ptr(), self.N_COUNTERS, mask, self._stream)
+
+    # ------------------------------------------------------------------ fused update (DQN._update, dqn.py:127-132)
+    def update_fused(self, batch, sync_target: bool):
+        self.update_fused_async(batch, sync_target)
+        return {"loss": np.float32(self.read_slots()[M_LOSS])}
+
+    def update_fused_async(self, batch, sync_target: bool):
+        db = self.load_batch(batch)
+
+        def program():
+            self._tick(C_CRITIC)
+            self.zero_slots()
+            self._p_loss(db, self._p_target(db))
+            if sync_target:
+                self._p_hard_sync()
+
+        self.run_program(("dqn", db.B, sync_target), program)
+        return [(M_LOSS, "loss")]
+
+    # ------------------------------------------------------------------ reference hooks (eager)
+    def update(self, batch) -> np.ndarray:
+        db = self.load_batch(batch)
+        self._tick(C_CRITIC)
+        self.zero_slots()
+        self._p_loss(db, self._p_target(db))
+        return self.read_slots()[M_LOSS].copy()
+
+    def compute_target(self, batch) -> torch.Tensor:
+        db = self.load_batch(batch)
+        q = self._p_target(db)
+        self.sync()
+        return q.view(-1, 1).clone()
+
+    def compute_loss(self, batch, q_tpn: torch.Tensor) -> torch.Tensor:
+        db = self.load_batch(batch)
+        self.zero_slots()
+        self._p_loss(db, q_tpn.to(self._device).reshape(-1).contiguous(), step=False)
+        self.sync()
+        return self._slots[M_LOSS].clone()
+
+    def update_target(self) -> None:
+        """hard_sync(targ_q_func, q_func) (dqn_impl.py:143-145)."""
+        self._p_hard_sync()
+
+
+class DoubleDQNImpl(DQNImpl):
+    DOUBLE = True
+
+
+class DiscreteCQLImpl(DoubleDQNImpl):
+    CONSERVATIVE = True
+
+    def _compute_conservative_loss(self, obs_t, act_t) -> torch.Tensor:
+        """cql_impl.py:290-302: mean_b(logsumexp_a Qbar(s) - Qbar(s, a_data)), Qbar = ensemble mean."""
+        from types import SimpleNamespace
+
+        n = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+        B = n(obs_t).shape[0]
+        batch = SimpleNamespace(observations=n(obs_t), actions=n(act_t), next_observations=n(obs_t),
+                                rewards=np.zeros((B, 1), np.float32), terminals=np.zeros((B, 1), np.float32),
+                                n_steps=np.ones((B, 1), np.float32))
+        db = self.load_batch(batch)
+        self.zero_slots()
+        self._p_loss(db, self.ws("zero_tpn", B), step=False)
+        self.sync()
+        return (self._slots[32 + S_LOSS + 1] / B).clone()

@@ -299,3 +299,159 @@ class DenseNet:
         self.refresh_shadow("params", stream)
         if tau is not None and a.target is not None:
             self.refresh_shadow("target", stream)
+
+
+NATURE_FILTERS = [(32, 8, 4), (64, 4, 2), (64, 3, 1)]  # PixelEncoderFactory defaults (models/encoders.py:100-120)
+
+
+class ConvCtx:
+    """Workspace of one ConvNet forward(/backward): patch matrices and NHWC activations per layer."""
+
+    def __init__(self, net: "ConvNet", images: int, members: int, train: bool):
+        self.images, self.members, self.train = images, members, train
+        dev, E = net.device, members
+        f32 = torch.float32
+        self.patches, self.acts = [], []
+        for i, (C, H, W, oc, k, s, OH, OW) in enumerate(net.layers):
+            rows, K = images * OH * OW, C * k * k
+            self.patches.append(torch.zeros(1 if i == 0 else E, rows, K, dtype=f32, device=dev))
+            self.acts.append(torch.zeros(E, rows, oc, dtype=f32, device=dev))
+        if train:
+            self.dacts = [torch.zeros(E, images * OH * OW, oc, dtype=f32, device=dev)
+                          for (_, _, _, oc, _, _, OH, OW) in net.layers]
+            kmax = max(images * OH * OW * C * k * k for (C, _, _, _, k, _, OH, OW) in net.layers[1:])
+            self.dpatch = torch.zeros(E * kmax, dtype=f32, device=dev)
+
+
+class ConvNet:
+    """Nature-DQN pixel encoder + narrow head for all ensemble members (PixelEncoder + DiscreteMeanQFunction,
+    d3rlpy/models/torch/encoders.py:43-162, q_functions/mean_q_function.py:13-24).  Every layer — the three
+    convolutions and the flatten+fc — is `im2col` followed by the batched dense-layer GEMM; activations
+    are NHWC.  Input is the uint8 NCHW frame stack straight from the gather kernel."""
+
+    def __init__(self, obs_shape, heads: Sequence[Tuple[str, int]], members: int, device, feature_size: int = 512,
+                 filters=None, member_key: str = "{name}", with_target: bool = False,
+                 seed_gen: Optional[torch.Generator] = None, precision: str = "fp32", input_divisor: float = 1.0):
+        if precision != "fp32":
+            raise ValueError("the convolutional encoder runs in fp32 mode (tensor-core conv path: DESIGN.md §next)")
+        C, H, W = obs_shape
+        self.obs_shape, self.members, self.device = (C, H, W), members, device
+        self.precision, self.input_divisor = precision, input_divisor
+        self.heads = list(heads)
+        self.head_out = sum(n for _, n in heads)
+        filters = list(filters) if filters is not None else NATURE_FILTERS
+        self.layers = []
+        entries = []
+        for l, (oc, k, s) in enumerate(filters):
+            OH, OW = (H - k) // s + 1, (W - k) // s + 1
+            self.layers.append((C, H, W, oc, k, s, OH, OW))
+            entries.append((f"_encoder._convs.{l}.weight", (oc, C, k, k)))
+            entries.append((f"_encoder._convs.{l}.bias", (oc,)))
+            C, H, W = oc, OH, OW
+        assert H == W, "square feature maps only"
+        self.layers.append((C, H, W, feature_size, H, 1, 1, 1))  # flatten + fc as a whole-map convolution
+        entries.append(("_encoder._fc.weight", (feature_size, C * H * W)))
+        entries.append(("_encoder._fc.bias", (feature_size,)))
+        self._names = [f"_encoder._convs.{l}" for l in range(len(filters))] + ["_encoder._fc"]
+        self.feat = feature_size
+        entries.append(("__head.weight", (self.head_out, feature_size)))
+        entries.append(("__head.bias", (self.head_out,)))
+        exports, r0 = [], 0
+        for name, n in self.heads:
+            exports.append((f"{name}.weight", "__head.weight", r0, n))
+            r0 += n
+        r0 = 0
+        for name, n in self.heads:
+            exports.append((f"{name}.bias", "__head.bias", r0, n))
+            r0 += n
+        self.arena = ParamArena(entries, members, device, with_target=with_target, member_key=member_key,
+                                exports=exports)
+        self._ctx: Dict[str, ConvCtx] = {}
+        self._init_params(seed_gen)
+
+    def _init_params(self, gen):
+        a = self.arena
+        with torch.no_grad():
+            for e in range(self.members):
+                for name, shape in a.shapes.items():
+                    wshape = shape if len(shape) > 1 else a.shapes[name[:-4] + "weight"]
+                    fan_in = 1
+                    for s in wshape[1:]:
+                        fan_in *= s
+                    bound = 1.0 / math.sqrt(fan_in)
+                    a.view(name, e).copy_((torch.rand(shape, generator=gen) * 2 - 1) * bound)
+        a.sync_target_from_params()
+
+    def refresh_shadow(self, which: str, stream: int):
+        return
+
+    def ctx(self, tag: str, images: int, members: Optional[int] = None, train: bool = True) -> ConvCtx:
+        E = members or self.members
+        c = self._ctx.get(tag)
+        if c is None or c.images != images or c.members != E or c.train != train:
+            c = ConvCtx(self, images, E, train)
+            self._ctx[tag] = c
+        return c
+
+    def _w(self, which, l, member=0):
+        return self.arena.addr(which, self._names[l] + ".weight", member)
+
+    def _b(self, which, l, member=0):
+        return self.arena.addr(which, self._names[l] + ".bias", member)
+
+    def forward(self, which: str, x_u8, images: int, ctx: ConvCtx, head_out, stream: int, x_is_u8: bool = True):
+        """x_u8: NCHW frame stack [images, C, H, W] (uint8, or fp32 when x_is_u8 is False)."""
+        L, E, ms = lib(), ctx.members, self.arena.member_size
+        for i, (C, H, W, oc, k, s, OH, OW) in enumerate(self.layers):
+            rows, K = images * OH * OW, C * k * k
+            p, y = ctx.patches[i], ctx.acts[i]
+            if i == 0:
+                L.im2col(_p(x_u8), 1 if x_is_u8 else 0, 0, C * H * W, H * W, W, 1, _p(p), 0, K, 0, images, C, H, W, k, s,
+                         self.input_divisor, 1, stream)
+                sx = 0
+            else:
+                prev = ctx.acts[i - 1]
+                L.im2col(_p(prev), 0, prev.shape[1] * C, H * W * C, 1, W * C, C, _p(p), 0, K, p.shape[1] * K, images, C,
+                         H, W, k, s, 1.0, E, stream)
+                sx = p.shape[1] * K
+            L.linear_forward(_p(p), K, sx, self._w(which, i), K, ms, self._b(which, i), ms, _p(y), oc,
+                             y.shape[1] * oc, rows, oc, K, E, 1, stream)
+        if head_out is not None:
+            last, n, d = ctx.acts[-1], self.head_out, self.feat
+            L.head_forward(_p(last), d, last.shape[1] * d, self.arena.addr(which, "__head.weight"), d, ms,
+                           self.arena.addr(which, "__head.bias"), ms, _p(head_out), n, images * n, images, n, d, E, 0,
+                           stream)
+
+    def backward(self, images: int, ctx: ConvCtx, d_head, stream: int):
+        """d_head: fp32 [E, images, head_out].  Accumulates every dW/db into arena.grads."""
+        L, E, ms = lib(), ctx.members, self.arena.member_size
+        n, d = self.head_out, self.feat
+        last = ctx.acts[-1]
+        L.head_backward_weight(_p(d_head), n, images * n, _p(last), d, last.shape[1] * d,
+                               self.arena.addr("grads", "__head.weight"), d, ms, self.arena.addr("grads", "__head.bias"),
+                               ms, images, n, d, E, stream)
+        dcur = ctx.dacts[-1]
+        L.head_backward_data(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms, _p(dcur), d,
+                             dcur.shape[1] * d, _p(last), d, last.shape[1] * d, images, n, d, E, stream)
+        for i in range(len(self.layers) - 1, -1, -1):
+            C, H, W, oc, k, s, OH, OW = self.layers[i]
+            rows, K = images * OH * OW, C * k * k
+            p = ctx.patches[i]
+            sx = 0 if i == 0 else p.shape[1] * K
+            L.linear_backward_weight(_p(dcur), oc, dcur.shape[1] * oc, _p(p), K, sx, self._w("grads", i), K, ms,
+                                     self._b("grads", i), ms, rows, oc, K, E, stream)
+            if i == 0:
+                break
+            sdp = p.shape[1] * K
+            L.linear_backward_data(_p(dcur), oc, dcur.shape[1] * oc, self._w("params", i), K, ms, _p(ctx.dpatch), K,
+                                   sdp, None, 0, 0, rows, oc, K, E, stream)
+            prev, dprev = ctx.acts[i - 1], ctx.dacts[i - 1]
+            L.col2im(_p(ctx.dpatch), K, sdp, _p(prev), 0, C, prev.shape[1] * C, _p(dprev), C, dprev.shape[1] * C,
+                     images, C, H, W, k, s, E, stream)
+            dcur = dprev
+
+    def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
+        a = self.arena
+        lib().adam_step(_p(a.params), _p(a.grads), _p(a.exp_avg), _p(a.exp_avg_sq),
+                        _p(a.target) if tau is not None else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
+                        tau if tau is not None else 0.0, 1, stream)

@@ -267,3 +267,129 @@ def test_cql_c2_shape_bf16_vs_oracle():
     _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=BF16_REL)
     _assert_params(impl.policy.state_dict(), orc.pi, "pi", rel=BF16_REL)
     _assert_params(impl.targ_q_function.state_dict(), orc.targ_q, "targ_q", rel=BF16_REL)
+
+
+# ----------------------------------------------------------------------------------------- BCQ / DQN family
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_bcq_matches_reference_golden(use_graph):
+    from d3rlpy_b200.algos import BCQ
+
+    case = Case(load_update(), "bcq")
+    c = case.cfg
+    h, v = [int(c["h0"]), int(c["h1"])], [int(c["v0"]), int(c["v1"])]
+    algo = BCQ(actor_encoder_factory=h, critic_encoder_factory=h, imitator_encoder_factory=v,
+               batch_size=int(c["batch"]), n_action_samples=int(c["n"]))
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    impl.policy.load_state_dict(case.group("init", "pi"))
+    impl.targ_policy.load_state_dict(case.group("init", "pi"))
+    impl.imitator.load_state_dict(case.group("init", "imitator"))
+    for s in range(case.steps):
+        impl.inject_noise(case.noise(s), int(c["batch"]))
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"bcq step {s}")
+    for grp, view in (("q", impl.q_function), ("pi", impl.policy), ("imitator", impl.imitator),
+                      ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy)):
+        _assert_params(view.state_dict(), case.group("final", grp), grp)
+
+
+def test_bcq_c3_shape_vs_oracle_two_steps():
+    """BASELINE config c3 shapes (obs 17, act 6, N 100, 750x750 VAE, 400x300 actor/critic) at batch 64."""
+    from d3rlpy_b200.algos import BCQ
+
+    O, A, B, N = 17, 6, 64, 100
+    torch.set_num_threads(8)
+    orc = ou.BCQ(O, A, n_action_samples=N, seed=3)
+    algo = BCQ(actor_encoder_factory=[400, 300], critic_encoder_factory=[400, 300],
+               imitator_encoder_factory=[750, 750], batch_size=B, n_action_samples=N)
+    algo.create_impl((O,), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    impl.policy.load_state_dict(orc.pi)
+    impl.targ_policy.load_state_dict(orc.pi)
+    impl.imitator.load_state_dict(orc.imitator)
+    rs = np.random.RandomState(4)
+    for s in range(2):
+        arrays = _synthetic_batch(rs, B, O, A)
+        noise = ou.Noise(seed=50 + s)
+        ref = orc.update(ou.Batch(arrays), noise)
+        impl.inject_noise(noise.log, B)
+        m = algo.update(_ns(arrays))
+        _assert_metrics(m, ref, f"c3 step {s}", rel=2e-5)
+    for grp, view, refp in (("q", impl.q_function, orc.q), ("pi", impl.policy, orc.pi),
+                            ("imitator", impl.imitator, orc.imitator), ("targ_q", impl.targ_q_function, orc.targ_q),
+                            ("targ_pi", impl.targ_policy, orc.targ_pi)):
+        _assert_params(view.state_dict(), refp, grp, rel=2e-5)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_discrete_cql_vector_matches_reference_golden(use_graph):
+    from d3rlpy_b200.algos import DiscreteCQL
+
+    case = Case(load_update(), "dcql_vec")
+    c = case.cfg
+    algo = DiscreteCQL(encoder_factory=[int(c["h0"]), int(c["h1"])], batch_size=int(c["batch"]),
+                       n_critics=int(c["n_critics"]), target_update_interval=int(c["interval"]))
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    for s in range(case.steps):
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"dcql_vec step {s}")
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q")
+    _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q")
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_discrete_cql_pixel_matches_reference_golden(use_graph):
+    """uint8 frame stacks -> fused /255 -> Nature-DQN convs (im2col + GEMM) -> Huber + conservative loss."""
+    from d3rlpy_b200.algos import DiscreteCQL, PixelEncoderFactory
+
+    case = Case(load_update(), "dcql_pix")
+    c = case.cfg
+    hw, nf = int(c["hw"]), int(c["n_frames"])
+    algo = DiscreteCQL(encoder_factory=PixelEncoderFactory(feature_size=int(c["feature"])),
+                       batch_size=int(c["batch"]), n_frames=nf, scaler="pixel")
+    algo.create_impl((nf, hw, hw), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    for s in range(case.steps):
+        b = case.batch(s)
+        assert b["observations"].dtype == np.uint8
+        m = algo.update(_ns(b))
+        _assert_metrics(m, case.step_metrics(s), f"dcql_pix step {s}")
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q")
+    _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q")
+
+
+def test_discrete_cql_c4_shape_vs_oracle():
+    """BASELINE config c4: 4x84x84 uint8 stacks, Nature DQN (fc 512), batch 32, one critic."""
+    from d3rlpy_b200.algos import DiscreteCQL
+
+    B, A = 32, 4
+    torch.set_num_threads(8)
+    orc = ou.DiscreteCQL((4, 84, 84), A, seed=9)
+    algo = DiscreteCQL(batch_size=B, n_frames=4, scaler="pixel")
+    algo.create_impl((4, 84, 84), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    rs = np.random.RandomState(7)
+    for s in range(2):
+        arrays = dict(observations=rs.randint(0, 256, (B, 4, 84, 84)).astype(np.uint8),
+                      actions=rs.randint(0, A, B).astype(np.int32), rewards=(rs.rand(B, 1) < 0.1).astype(np.float32),
+                      next_observations=rs.randint(0, 256, (B, 4, 84, 84)).astype(np.uint8),
+                      terminals=(rs.rand(B, 1) < 0.05).astype(np.float32), n_steps=np.ones((B, 1), np.float32))
+        ref = orc.update(ou.Batch(arrays, ou.pixel_scaler()), None)
+        m = algo.update(_ns(arrays))
+        _assert_metrics(m, ref, f"c4 step {s}", rel=2e-5)
+    _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=2e-5)
+    _assert_params(impl.targ_q_function.state_dict(), orc.targ_q, "targ_q", rel=2e-5)
