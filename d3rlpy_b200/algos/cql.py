@@ -23,8 +23,6 @@ class CQL(AlgoBase):
         for f in (actor_optim_factory, critic_optim_factory, temp_optim_factory, alpha_optim_factory):
             if f is not None:
                 raise ValueError("only AdamFactory() defaults are on the accelerated path")
-        if soft_q_backup:
-            raise NotImplementedError("soft_q_backup=True is not on the accelerated path yet")
         self._actor_learning_rate, self._critic_learning_rate = actor_learning_rate, critic_learning_rate
         self._temp_learning_rate, self._alpha_learning_rate = temp_learning_rate, alpha_learning_rate
         self._actor_hidden = _hidden_units(actor_encoder_factory, [256, 256])

@@ -95,7 +95,7 @@ class ImplBase:
         if not torch.cuda.is_available():
             raise D3BError("d3rlpy_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._lib = lib()
-        dev_id = 0 if use_gpu in (None, False, True) else int(getattr(use_gpu, "get_id", lambda: use_gpu)())
+        dev_id = 0 if (use_gpu is None or isinstance(use_gpu, bool)) else int(getattr(use_gpu, "get_id", lambda: use_gpu)())
         self._device = torch.device("cuda", dev_id)
         torch.cuda.set_device(self._device)
         self._observation_shape = tuple(observation_shape)
@@ -114,6 +114,10 @@ class ImplBase:
         self._seed = 0
         self._ws: Dict[str, torch.Tensor] = {}
         self.world_size, self.rank = world_size, rank
+        if world_size > 1:
+            from ... import parallel
+
+            parallel.init(world_size, rank)  # library-owned NCCL communicator (K11)
         self.use_graph = True
 
     # ------------------------------------------------------------------ small helpers
@@ -263,7 +267,9 @@ class ImplBase:
         if n_norm + n_uni == 0 or self._noise_injected:
             return
         self.noise_view(next(iter(plan)), B)  # ensure allocation
-        self._lib.noise_fill(self._noise.data_ptr(), n_norm, n_uni, self._seed, self.counter_ptr(0), self._stream)
+        # per-rank Philox key: ranks draw independent noise for their own rows
+        seed = (self._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF
+        self._lib.noise_fill(self._noise.data_ptr(), n_norm, n_uni, seed, self.counter_ptr(0), self._stream)
 
     # ------------------------------------------------------------------ graphs
     def _graphs_invalidate(self):

@@ -142,14 +142,25 @@ class CQLImpl(DDPGBaseImpl):
                       self._alpha_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_ALPHA), st)
 
     def _p_target(self, db, head):
-        """compute_target (cql_impl.py:225-243): deterministic backup tanh(mu(s')) through target critics."""
+        """compute_target (cql_impl.py:225-243): deterministic backup tanh(mu(s')) through the target critics
+        (returns q_t[E,B]; the min over members is taken inside critic_loss), or with soft_q_backup the SAC
+        target min_e Q' - exp(log_temp) logp with a sampled action (sac_impl.py:148-162; returns q_tpn[B])."""
         B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
-        assert not self._soft_q_backup, "soft_q_backup is not implemented yet"
         xt = self.ws("xt", B, O + A)
-        L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, None, db.ptr("next_obs"), O, xt.data_ptr(),
-                             O + A, None, None, B, 1, O, A, MIN_LOGSTD, MAX_LOGSTD, 1, st)
+        if not self._soft_q_backup:
+            L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, None, db.ptr("next_obs"), O, xt.data_ptr(),
+                                 O + A, None, None, B, 1, O, A, MIN_LOGSTD, MAX_LOGSTD, 1, st)
+            _, q_t = self._critic_rows_forward("target", xt, B, "tq", train=False)
+            return q_t, None
+        lp = self.ws("soft_lp", B)
+        L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, self.noise_view("soft", B).data_ptr(),
+                             db.ptr("next_obs"), O, xt.data_ptr(), O + A, None, lp.data_ptr(), B, 1, O, A, MIN_LOGSTD,
+                             MAX_LOGSTD, 0, st)
         _, q_t = self._critic_rows_forward("target", xt, B, "tq", train=False)
-        return q_t
+        q_tpn = self.ws("soft_tpn", B)
+        L.sac_soft_backup(q_t.data_ptr(), B, self._n_critics, lp.data_ptr(), self._log_temp.ptr("p"),
+                          q_tpn.data_ptr(), B, st)
+        return None, q_tpn
 
     def _p_critic(self, db, head, q_t=None, q_tpn=None, backward=True, sync_target=True, conservative=True,
                   td=True):
@@ -240,8 +251,8 @@ class CQLImpl(DDPGBaseImpl):
                 self._p_temp(db, head)
             if do_alpha:
                 self._p_alpha(db, head)
-            q_t = self._p_target(db, head)
-            self._p_critic(db, head, q_t=q_t)
+            q_t, q_tpn = self._p_target(db, head)
+            self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn)
             self._p_actor(db, acts_p, head)
 
         self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected), program)
@@ -279,9 +290,9 @@ class CQLImpl(DDPGBaseImpl):
     def compute_target(self, batch) -> torch.Tensor:
         db = self._begin(batch)
         _, head = self._p_policy(db)
-        q_t = self._p_target(db, head)
+        q_t, q_tpn = self._p_target(db, head)
         self.sync()
-        return q_t.min(dim=0).values.view(-1, 1).clone()
+        return (q_t.min(dim=0).values if q_tpn is None else q_tpn).view(-1, 1).clone()
 
     def compute_critic_loss(self, batch, q_tpn: torch.Tensor) -> torch.Tensor:
         db = self._begin(batch)
@@ -303,8 +314,8 @@ class CQLImpl(DDPGBaseImpl):
     def update_critic(self, batch) -> np.ndarray:
         db = self._begin(batch, C_DRAW, C_CRITIC)
         _, head = self._p_policy(db)
-        q_t = self._p_target(db, head)
-        self._p_critic(db, head, q_t=q_t, sync_target=False)
+        q_t, q_tpn = self._p_target(db, head)
+        self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn, sync_target=False)
         return self.read_slots()[M_CRITIC].copy()
 
     def compute_actor_loss(self, batch) -> torch.Tensor:

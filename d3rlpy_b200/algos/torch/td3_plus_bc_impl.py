@@ -52,6 +52,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
                       q_tpn.data_ptr() if q_tpn is not None else None, db.ptr("rew"), db.ptr("term"),
                       db.ptr("nsteps"), self._gamma, None, None, 0, A, None, 0.0, dq.data_ptr(), B,
                       self.sums_ptr(S_TD), None, B, E, inv_b, 1, st)
+        self._allreduce(self._slots[32 + S_TD:32 + S_TD + 3])
         L.cql_finalize(self.sums_ptr(S_TD), None, inv_b, E, 0.0, 0.0, 0, 0, self.metric_ptr(M_CRITIC), None, st)
         return xc, acts, dq
 

@@ -273,6 +273,18 @@ __global__ void __launch_bounds__(1024) sac_temp_loss_kernel(const float* __rest
   }
 }
 
+// SACImpl.compute_target (sac_impl.py:148-162): q_tpn[b] = min_e Q'_e(s', a') - exp(log_temp) * logp(a'|s')
+__global__ void __launch_bounds__(256) sac_soft_backup_kernel(const float* __restrict__ q_targ, long long sQ, int E,
+                                                              const float* __restrict__ logp,
+                                                              const float* __restrict__ log_temp,
+                                                              float* __restrict__ q_tpn, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m = __ldg(q_targ + b);
+  for (int e = 1; e < E; ++e) m = fminf(m, __ldg(q_targ + (long long)e * sQ + b));
+  q_tpn[b] = m - expf(__ldg(log_temp)) * __ldg(logp + b);
+}
+
 // TD3+BC actor, phase 1: sums[0] += sum|q0|, sums[1] += sum q0, sums[2] += sum (a_data - a)^2
 __global__ void __launch_bounds__(256) td3bc_actor_stats_kernel(const float* __restrict__ q0,
                                                                 const float* __restrict__ a, long long lda,
@@ -475,4 +487,13 @@ extern "C" int d3b_td3bc_actor_backward(const float* a, int64_t lda, const float
   td3bc_actor_backward_kernel<<<ceil_div(batch * act_dim, 256), 256, 0, ST>>>(
       a, lda, a_data, ldd, dx_action, lddx, dz, lddz, batch, act_dim, inv_batch / (float)act_dim);
   return check_launch("td3bc_actor_backward");
+}
+
+extern "C" int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int members, const float* logp,
+                                   const float* log_temp, float* q_tpn, int batch, void* stream) {
+  D3B_REQUIRE(batch >= 0 && members >= 1, "sac_soft_backup: bad sizes");
+  if (batch == 0) return D3B_OK;
+  D3B_REQUIRE(q_targ && logp && log_temp && q_tpn, "sac_soft_backup: null pointer");
+  sac_soft_backup_kernel<<<ceil_div(batch, 256), 256, 0, ST>>>(q_targ, stride_q, members, logp, log_temp, q_tpn, batch);
+  return check_launch("sac_soft_backup");
 }

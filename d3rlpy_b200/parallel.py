@@ -1,0 +1,103 @@
+"""Data-parallel plumbing: one process per GPU, the minibatch sharded by rows, one sum all-reduce per
+optimizer step.  The reference has no distributed path; this is new.
+
+* `shard_rows(B, world, rank)` — rank r owns rows [r*B/W, (r+1)*B/W) of the SAME global index vector
+  (all ranks draw identical indices from a shared seed; the replay buffer is replicated per GPU).
+* `shard_noise(t, kind, B, N, world, rank)` — slices injected global noise so that a sharded update
+  reproduces the single-GPU update bit-for-bit up to summation order (row = b*N + k keeps a sample's N
+  actions on one rank).
+* `init(world, rank)` / `allreduce_sum(tensor, stream)` — NCCL communicator owned by the C-ABI library
+  (d3b_comm_*), rendezvous of the 128-byte unique id through torch.distributed (any backend).
+"""
+from __future__ import annotations
+
+import ctypes
+import glob
+import os
+from typing import Optional, Tuple
+
+import torch
+
+from ._lib import D3BError, lib
+
+_COMM: Optional[int] = None
+_WORLD = 1
+_RANK = 0
+
+
+def shard_rows(batch: int, world: int, rank: int) -> Tuple[int, int]:
+    if batch % world:
+        raise ValueError(f"global batch {batch} is not divisible by world size {world}")
+    per = batch // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_noise(t: torch.Tensor, shape_kind: str, batch: int, n: int, world: int, rank: int) -> torch.Tensor:
+    """shape_kind: "B*" (B, ...) rows;  "NB*" (N, B, ...) as Normal.rsample((N,));  "BN*" (B*N, ...) with
+    row = b*N + k (cql_impl.py:155-161,176-186)."""
+    lo, hi = shard_rows(batch, world, rank)
+    if shape_kind == "B*":
+        return t[lo:hi].contiguous()
+    if shape_kind == "NB*":
+        return t[:, lo:hi].contiguous()
+    if shape_kind == "BN*":
+        return t[lo * n:hi * n].contiguous()
+    raise ValueError(shape_kind)
+
+
+def _find_nccl() -> str:
+    try:
+        import nvidia.nccl  # the copy torch itself loaded
+
+        cands = glob.glob(os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so*"))
+        if cands:
+            return sorted(cands)[0]
+    except Exception:  # noqa: BLE001
+        pass
+    return "libnccl.so.2"
+
+
+def init(world_size: int, rank: int) -> None:
+    """Creates the library-owned NCCL communicator.  torch.distributed must already be initialised (it is
+    only used to broadcast the unique id)."""
+    global _COMM, _WORLD, _RANK
+    if _COMM is not None or world_size <= 1:
+        _WORLD, _RANK = max(world_size, 1), rank
+        return
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        raise D3BError("parallel.init needs an initialised torch.distributed process group for the rendezvous")
+    L = lib()
+    L.comm_load(_find_nccl().encode())
+    buf = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        L.comm_unique_id(ctypes.addressof(buf))
+    obj = [bytes(buf)]
+    dist.broadcast_object_list(obj, src=0)
+    ctypes.memmove(ctypes.addressof(buf), obj[0], 128)
+    comm = ctypes.c_void_p()
+    L.comm_init(ctypes.addressof(buf), world_size, rank, ctypes.byref(comm))
+    _COMM, _WORLD, _RANK = comm.value, world_size, rank
+
+
+def world() -> Tuple[int, int]:
+    return _WORLD, _RANK
+
+
+def allreduce_sum(t: torch.Tensor, stream) -> None:
+    """In-place sum over ranks of a contiguous fp32 device tensor, on `stream` (graph-capturable)."""
+    if _WORLD <= 1:
+        return
+    if _COMM is None:
+        raise D3BError("parallel.allreduce_sum before parallel.init")
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    cs = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    lib().allreduce_sum(_COMM, t.data_ptr(), t.numel(), cs)
+
+
+def destroy() -> None:
+    global _COMM
+    if _COMM is not None:
+        lib().comm_destroy(_COMM)
+        _COMM = None

@@ -157,6 +157,9 @@ int d3b_sac_actor_backward(const float* head, int64_t ld_head, const float* eps,
                            float inv_batch, void* stream);
 int d3b_sac_temp_loss(const float* logp, const float* log_temp, int batch, int act_dim, float inv_batch,
                       float* metric, float* grad, int accumulate, void* stream);
+/* SACImpl.compute_target, soft backup (sac_impl.py:148-162; CQL soft_q_backup=True, cql_impl.py:225-231) */
+int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int members, const float* logp, const float* log_temp,
+                        float* q_tpn, int batch, void* stream);
 /* TD3PlusBCImpl.compute_actor_loss (td3_plus_bc_impl.py:64-70) in three phases so the
  * batch-global lambda can be all-reduced between stats and seed when the batch is sharded. */
 int d3b_td3bc_actor_stats(const float* q0, const float* a, int64_t lda, const float* a_data, int64_t ldd,
@@ -232,6 +235,16 @@ int d3b_tick(int* counters, int n, unsigned mask, void* stream);
  * distributions.py:105,118, bcq_impl.py:136,178, imitators.py:85). */
 int d3b_noise_fill(float* out, int64_t n_normal, int64_t n_uniform, uint64_t seed, const int* draw_counter,
                    void* stream);
+
+/* ---- K11: data-parallel exchange (new: the reference is single-device) -------------
+ * One sum all-reduce per optimizer step over the flat gradient arena (+ the loss partial sums), on the
+ * update stream, capturable into the update's CUDA graph.  NCCL is bound with dlopen at run time;
+ * `id` is a 128-byte ncclUniqueId created on rank 0 and distributed by the host (torch.distributed). */
+int d3b_comm_load(const char* libnccl_path);
+int d3b_comm_unique_id(void* id_out_128);
+int d3b_comm_init(const void* id_128, int world_size, int rank, void** comm_out);
+int d3b_allreduce_sum(void* comm, float* buf, int64_t n, void* stream);
+int d3b_comm_destroy(void* comm);
 
 /* ---- plumbing: staged copies, CUDA-graph capture of a whole update ------------------ */
 int d3b_memset_zero(void* ptr, int64_t bytes, void* stream);

@@ -63,14 +63,14 @@ def test_td3bc_matches_reference_golden(use_graph):
     assert algo.grad_step == case.steps
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_cql_matches_reference_golden(use_graph):
+@pytest.mark.parametrize("use_graph,name", [(False, "cql"), (True, "cql"), (True, "cql_softq")])
+def test_cql_matches_reference_golden(use_graph, name):
     from d3rlpy_b200.algos import CQL
 
-    case = Case(load_update(), "cql")
+    case = Case(load_update(), name)
     c = case.cfg
     algo = CQL(actor_encoder_factory=[32, 32, 32], critic_encoder_factory=[32, 32, 32], batch_size=int(c["batch"]),
-               n_action_samples=int(c["n"]), n_steps=3)
+               n_action_samples=int(c["n"]), n_steps=3, soft_q_backup=bool(c["soft_q_backup"]))
     algo.create_impl((int(c["obs"]),), int(c["act"]))
     impl = algo.impl
     impl.use_graph = use_graph
