@@ -54,7 +54,7 @@ class Lib:
     _FLOP_ARGS = {"linear_forward": (11, 12, 13, 14), "linear_backward_data": (12, 13, 14, 15),
                   "linear_backward_weight": (11, 12, 13, 14), "head_forward": (11, 12, 13, 14),
                   "head_backward_data": (12, 13, 14, 15), "head_backward_weight": (11, 12, 13, 14),
-                  "umma_gemm": (6, 7, 8, 9)}
+                  "umma_gemm": (6, 7, 8, 9), "umma_gemm_tn": (6, 7, 8, 9)}
 
     def start_profile(self, stream_obj) -> None:
         """Bracket every launch with CUDA events recorded on `stream_obj` (the launching stream)."""
@@ -82,6 +82,10 @@ class Lib:
         if name in self._FLOP_ARGS:
             i = self._FLOP_ARGS[name]
             flops = 2.0 * args[i[0]] * args[i[1]] * args[i[2]] * args[i[3]]
+        elif name == "mlp_forward_bf16":  # rows, members, n_layers, dims[] (+ head: n_head at 18)
+            dims = list(args[6])
+            mac = sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1] * args[18]
+            flops = 2.0 * args[3] * args[4] * mac
         self._prof.append((name, flops, a, b))
         return rc
 

@@ -1,0 +1,469 @@
+// K2 (bf16 mode, fused): the whole ReLU-MLP trunk + narrow head of one network, for every ensemble member,
+// in ONE persistent launch.
+//
+//   unit = (128-row tile, member).  Per unit the layers are chained on-chip:
+//     layer 0 : A = x tile (TMA, zero-filled to 64-column K blocks)        B = W_0 K blocks (TMA ring)
+//     layer l : A = relu(H_{l-1}) written by the epilogue warps straight into the SWIZZLE_128B K-major
+//               operand buffer (never leaves shared memory)                 B = W_l K blocks (TMA ring)
+//     tcgen05.mma M128 x N_l x K16, fp32 accumulators ping-ponging between two 256-column TMEM buffers.
+//   Epilogue (8 warps, thread = accumulator row): tcgen05.ld -> +bias -> ReLU -> bf16 -> operand buffer;
+//   the same buffer is TMA-stored to H_l in global memory when the backward pass will need it; on the last
+//   layer the head (N <= 32 outputs: Q value, mu|logstd, action, VAE heads) is reduced per row from the
+//   registers and written as fp32 (optionally through tanh).
+// Replaces, per call: VectorEncoder[WithAction].forward (d3rlpy/models/torch/encoders.py:265-339), the Python
+// loop over members of EnsembleContinuous/DiscreteQFunction (q_functions/ensemble_q_function.py:141-175) and the
+// `_fc` / `_mu` / `_logstd` heads (mean_q_function.py:21,69; policies.py:55,92,153-158; imitators.py:45-54).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace d3b {
+namespace fused {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int MAX_LAYERS = 4;
+constexpr int A_KB_BYTES = BM * BK * 2;      // one 64-column K block of the operand buffer: 16 KB
+constexpr int MAX_KB = 4;                    // layer widths <= 256
+constexpr int MAXW = MAX_KB * BK;            // 256
+constexpr int W_STAGE_BYTES = MAXW * BK * 2; // 32 KB
+constexpr int W_STAGES = 3;
+constexpr int EPI_THREADS = 256, NTHREADS = EPI_THREADS + 64;
+
+struct Maps {
+  CUtensorMap x;
+  CUtensorMap w[MAX_LAYERS];
+  CUtensorMap h[MAX_LAYERS];
+};
+
+struct FwdParams {
+  int rows, members, tiles, n_layers;
+  int K[MAX_LAYERS], N[MAX_LAYERS];
+  const float* bias[MAX_LAYERS];
+  long long bias_stride;
+  int x_shared, save_mask;
+  const float* head_w;
+  const float* head_b;
+  long long head_stride;
+  int n_head, head_tanh;
+  float* head_out;  // [members][rows][n_head]
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a pipeline bug becomes a trapped launch error instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins) {
+    if (spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// K-major SWIZZLE_128B operand: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// barrier slots
+enum { B_WFULL = 0, B_WEMPTY = W_STAGES, B_XFULL = 2 * W_STAGES, B_AFREE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
+       B_ACTREADY = B_TEMPTY + 2, B_COUNT };
+
+template <int NH>
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;
+  uint8_t* smW = smem + MAX_KB * A_KB_BYTES;
+  float* head_w_s = (float*)(smW + W_STAGES * W_STAGE_BYTES);  // [NH][MAXW]
+  float* bias_s = head_w_s + NH * MAXW;                        // [MAX_LAYERS][MAXW]
+  float* head_part = bias_s + MAX_LAYERS * MAXW;               // [128][NH]
+  uint64_t* bars = (uint64_t*)(head_part + BM * NH);
+  uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.n_layers;
+  const int units = p.tiles * p.members;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ================= TMA producer: x tile, then the weight K blocks of every layer through the ring
+    if (lane == 0) {
+      uint32_t wi = 0, it = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
+        mbar_wait(bars + B_AFREE, (it & 1) ^ 1);
+        const int nkb0 = (p.K[0] + BK - 1) / BK;
+        mbar_expect_tx(bars + B_XFULL, nkb0 * A_KB_BYTES);
+        for (int kb = 0; kb < nkb0; ++kb)
+          tma_load_3d(smA + kb * A_KB_BYTES, &maps.x, bars + B_XFULL, kb * BK, m0, p.x_shared ? 0 : e);
+        for (int l = 0; l < L; ++l) {
+          const int nkb = (p.K[l] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const uint32_t s = wi % W_STAGES, ph = (wi / W_STAGES) & 1;
+            mbar_wait(bars + B_WEMPTY + s, ph ^ 1);
+            mbar_expect_tx(bars + B_WFULL + s, p.N[l] * BK * 2);
+            tma_load_3d(smW + s * W_STAGE_BYTES, &maps.w[l], bars + B_WFULL + s, kb * BK, 0, e);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      uint32_t g = 0, wi = 0, it = 0, act_cnt = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        for (int l = 0; l < L; ++l, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait(bars + B_TEMPTY + buf, ((g >> 1) & 1) ^ 1);
+          if (l == 0) {
+            mbar_wait(bars + B_XFULL, it & 1);
+          } else {
+            mbar_wait(bars + B_ACTREADY, act_cnt & 1);
+            ++act_cnt;
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N[l] >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+          const int nkb = (p.K[l] + BK - 1) / BK;
+          const int ksteps = (p.K[l] + UMMA_K - 1) / UMMA_K;
+          const uint32_t d_tmem = tmem_base + buf * 256;
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const uint32_t s = wi % W_STAGES, ph = (wi / W_STAGES) & 1;
+            mbar_wait(bars + B_WFULL + s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = make_desc(smem_u32(smA + kb * A_KB_BYTES));
+            const uint64_t bdesc = make_desc(smem_u32(smW + s * W_STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (kb * (BK / UMMA_K) + k < ksteps)
+                mma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(bars + B_WEMPTY + s);
+          }
+          mma_commit(bars + B_ACCFULL + buf);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps 0-7: thread = accumulator row 32*(warp%4)+lane, column half warp/4
+    const int t = threadIdx.x;
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    uint32_t g = 0;
+    int cur_member = -1;
+    bool stores_pending = false;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
+      if (e != cur_member) {
+        epi_sync();  // nobody is still reading the previous member's constants
+        for (int l = 0; l < L; ++l) {
+          const float* b = p.bias[l] + (long long)e * p.bias_stride;
+          for (int j = t; j < p.N[l]; j += EPI_THREADS) bias_s[l * MAXW + j] = __ldg(b + j);
+        }
+        if (NH > 0 && p.n_head > 0) {
+          const int feat = p.N[L - 1];
+          const float* hw = p.head_w + (long long)e * p.head_stride;
+          for (int i = t; i < NH * MAXW; i += EPI_THREADS) {
+            int j = i / MAXW, c = i % MAXW;
+            head_w_s[i] = (j < p.n_head && c < feat) ? __ldg(hw + (long long)j * feat + c) : 0.f;
+          }
+        }
+        epi_sync();
+        cur_member = e;
+      }
+      for (int l = 0; l < L; ++l, ++g) {
+        const uint32_t buf = g & 1;
+        const bool last = (l == L - 1);
+        const bool store = (p.save_mask >> l) & 1;
+        const bool writeA = !last || store;
+        const int N = p.N[l];
+        mbar_wait(bars + B_ACCFULL + buf, (g >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (last && !store && t == 0) mbar_arrive(bars + B_AFREE);  // operand buffer no longer needed by this unit
+        if (writeA && stores_pending) {
+          if (t == 0) tma_store_wait_read();  // the previous layer's TMA stores finished reading the buffer
+          epi_sync();
+          stores_pending = false;
+        }
+        const int cph = ((N + 31) / 32) * 16;
+        const int c_begin = half ? cph : 0;
+        const int c_end = half ? N : (cph < N ? cph : N);
+        const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+        float acc[NH > 0 ? NH : 1];
+#pragma unroll
+        for (int j = 0; j < (NH > 0 ? NH : 1); ++j) acc[j] = 0.f;
+        for (int c = c_begin; c < c_end; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + (uint32_t)c, v);
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            float f0 = fmaxf(__uint_as_float(v[i]) + bias_s[l * MAXW + c + i], 0.f);
+            float f1 = fmaxf(__uint_as_float(v[i + 1]) + bias_s[l * MAXW + c + i + 1], 0.f);
+            pk[i >> 1] = pack_bf16(f0, f1);
+          }
+          if (writeA) {
+            const int kb = c >> 6, j0 = (c & 63) >> 3;
+            uint8_t* base = smA + kb * A_KB_BYTES + row * 128;
+            *reinterpret_cast<uint4*>(base + ((j0 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+          if (NH > 0 && last && p.n_head > 0) {
+            float hv[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              hv[2 * i] = bf16_lo(pk[i]);
+              hv[2 * i + 1] = bf16_hi(pk[i]);
+            }
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              const float4* w4 = reinterpret_cast<const float4*>(head_w_s + j * MAXW + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 w = w4[i];
+                acc[j] = fmaf(hv[4 * i], w.x, acc[j]);
+                acc[j] = fmaf(hv[4 * i + 1], w.y, acc[j]);
+                acc[j] = fmaf(hv[4 * i + 2], w.z, acc[j]);
+                acc[j] = fmaf(hv[4 * i + 3], w.w, acc[j]);
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (writeA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (NH > 0 && last && p.n_head > 0 && half == 1) {
+#pragma unroll
+          for (int j = 0; j < NH; ++j) head_part[row * NH + j] = acc[j];
+        }
+        epi_sync();
+        if (t == 0) {
+          mbar_arrive(bars + B_TEMPTY + buf);
+          if (!last) mbar_arrive(bars + B_ACTREADY);
+          if (store) {
+            const int nkb_out = (N + BK - 1) / BK;
+            for (int kb = 0; kb < nkb_out; ++kb) tma_store_3d(&maps.h[l], smA + kb * A_KB_BYTES, kb * BK, m0, e);
+            tma_store_commit();
+            if (last) {
+              tma_store_wait_read();
+              mbar_arrive(bars + B_AFREE);
+            }
+          }
+        }
+        stores_pending = store && !last;
+        if (NH > 0 && last && p.n_head > 0 && half == 0 && m0 + row < p.rows) {
+          const float* hb = p.head_b + (long long)e * p.head_stride;
+          float* o = p.head_out + ((long long)e * p.rows + m0 + row) * p.n_head;
+#pragma unroll
+          for (int j = 0; j < NH; ++j) {
+            if (j < p.n_head) {
+              float val = acc[j] + head_part[row * NH + j] + __ldg(hb + j);
+              o[j] = p.head_tanh ? tanhf(val) : val;
+            }
+          }
+        }
+      }
+      if (L == 1) epi_sync();  // head_part is rewritten by the very next layer
+    }
+    if (t == 0) tma_store_wait_all();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace fused
+}  // namespace d3b
+
+using namespace d3b;
+using namespace d3b::fused;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// bf16 tensor [members][rows][cols] (row-major, leading dim ld, member stride `stride`), box {64, box_rows, 1}
+int make_map(CUtensorMap* map, const void* base, int cols, int rows, int members, long long ld, long long stride,
+             int box_rows, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (((uintptr_t)base & 15) || (ld & 7) || (members > 1 && (stride & 7)))
+    return set_err(D3B_ERR_ARG, "mlp_fused: %s must be 16-byte aligned with ld/stride multiples of 8 bf16", what);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(members < 1 ? 1 : members)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)((members > 1 ? stride : ld * (long long)rows) * 2)};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+  return D3B_OK;
+}
+
+template <int NH>
+size_t fwd_smem() {
+  return 1024 + (size_t)MAX_KB * A_KB_BYTES + (size_t)W_STAGES * W_STAGE_BYTES +
+         sizeof(float) * ((size_t)NH * MAXW + MAX_LAYERS * MAXW + (size_t)BM * NH) + 8 * B_COUNT + 64;
+}
+
+template <int NH>
+int launch_fwd(const Maps& maps, const FwdParams& p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fwd_smem<NH>()));
+    attr_set = true;
+  }
+  mlp_forward_kernel<NH><<<grid, NTHREADS, fwd_smem<NH>(), st>>>(maps, p);
+  return check_launch("mlp_forward_bf16");
+}
+
+}  // namespace
+
+// dims_host = {K_0, N_0, N_1, ..., N_{L-1}} (K_l = N_{l-1}); w_host[l] / bias_host[l] / acts_host[l] point at
+// member 0 of layer l; acts_host may be NULL (nothing saved) and individual entries may be NULL.
+extern "C" int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, int rows, int members, int n_layers,
+                                    const int* dims_host, const void* const* w_host, const int64_t* ldw_host,
+                                    int64_t stride_w, const float* const* bias_host, int64_t stride_bias,
+                                    void* const* acts_host, const int64_t* ld_act_host,
+                                    const int64_t* stride_act_host, const float* head_w, const float* head_b,
+                                    int64_t stride_head, int n_head, int head_tanh, float* head_out, void* stream) {
+  D3B_REQUIRE(rows >= 0 && members >= 1 && n_layers >= 1 && n_layers <= MAX_LAYERS, "mlp_forward_bf16: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(x && dims_host && w_host && ldw_host && bias_host, "mlp_forward_bf16: null pointer");
+  D3B_REQUIRE(n_head >= 0 && n_head <= 32, "mlp_forward_bf16: n_head must be <= 32");
+  D3B_REQUIRE(n_head == 0 || (head_w && head_b && head_out), "mlp_forward_bf16: null head pointer");
+  FwdParams p{};
+  Maps maps;
+  p.rows = rows; p.members = members; p.tiles = ceil_div(rows, BM); p.n_layers = n_layers;
+  p.x_shared = stride_x == 0;
+  p.bias_stride = stride_bias;
+  p.head_w = head_w; p.head_b = head_b; p.head_stride = stride_head; p.n_head = n_head; p.head_tanh = head_tanh;
+  p.head_out = head_out;
+  int k = dims_host[0];
+  D3B_REQUIRE(k >= 1 && k <= MAXW, "mlp_forward_bf16: input width must be in [1,256]");
+  int rc = make_map(&maps.x, x, k, rows, p.x_shared ? 1 : members, ldx, stride_x, BM, "x");
+  if (rc) return rc;
+  for (int l = 0; l < n_layers; ++l) {
+    int n = dims_host[l + 1];
+    D3B_REQUIRE(n >= 16 && n <= MAXW && n % 16 == 0, "mlp_forward_bf16: layer widths must be multiples of 16 in [16,256]");
+    D3B_REQUIRE(w_host[l] && bias_host[l], "mlp_forward_bf16: null layer pointer");
+    p.K[l] = k; p.N[l] = n; p.bias[l] = bias_host[l];
+    rc = make_map(&maps.w[l], w_host[l], k, n, members, ldw_host[l], stride_w, n, "W");
+    if (rc) return rc;
+    if (acts_host && acts_host[l]) {
+      rc = make_map(&maps.h[l], acts_host[l], n, rows, members, ld_act_host[l], stride_act_host[l], BM, "H");
+      if (rc) return rc;
+      p.save_mask |= 1 << l;
+    } else {
+      maps.h[l] = maps.x;
+    }
+    k = n;
+  }
+  for (int l = n_layers; l < MAX_LAYERS; ++l) { maps.w[l] = maps.x; maps.h[l] = maps.x; }
+  int units = p.tiles * members;
+  int grid = units < kNumSM ? units : kNumSM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_head == 0) return launch_fwd<0>(maps, p, grid, st);
+  if (n_head == 1) return launch_fwd<1>(maps, p, grid, st);
+  if (n_head <= 8) return launch_fwd<8>(maps, p, grid, st);
+  if (n_head <= 16) return launch_fwd<16>(maps, p, grid, st);
+  return launch_fwd<32>(maps, p, grid, st);
+}

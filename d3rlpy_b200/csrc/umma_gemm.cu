@@ -33,6 +33,7 @@ struct Params {
   int stages;             // operand ring depth (3 when a mask tile needs the space, else 4)
   int splits, kb_per_split;
   int a_shared, b_shared; // operand shared by all members -> member coordinate 0
+  int mn_major;           // 1: both operands are MN-major in memory (A [K][M], B [K][N]) — the weight-gradient form
   // epilogue
   const float* bias; long long sBias; int relu;
   const __nv_bfloat16* mask; long long ldmask, sMask;  // keep value where mask > 0
@@ -87,6 +88,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major, SWIZZLE_128B: atoms of 64 MN-elements (128 B) x 8 K-rows (1024 B); consecutive 8-row groups along K
+// are SBO = 1024 B apart, consecutive 64-element groups along MN are LBO = one TMA box (BK rows x 128 B) apart.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((BK * 128) >> 4) << 16;             // leading byte offset: next 64-wide MN group
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: next 8 K-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
@@ -126,7 +139,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
                                                            const __grid_constant__ CUtensorMap tmB, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int b_stage_bytes = p.BN * BK * 2;
+  const int b_stage_bytes = (p.mn_major && p.BN < 64 ? 64 : p.BN) * BK * 2;
   uint8_t* smA = smem;
   const int STAGES = p.stages;
   uint8_t* smB = smem + STAGES * A_STAGE_BYTES;
@@ -176,8 +189,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
         uint32_t phase = (i / STAGES) & 1;
         mbar_wait(empty + s, phase ^ 1);
         mbar_expect_tx(full + s, bytes);
-        tma_load_3d(smA + s * A_STAGE_BYTES, &tmA, full + s, kb * BK, m0, ea);
-        tma_load_3d(smB + s * b_stage_bytes, &tmB, full + s, kb * BK, n0, eb);
+        if (p.mn_major) {
+          // boxes of {64 MN-elements, BK reduction rows}: coordinates (mn, k, member)
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_3d(smA + s * A_STAGE_BYTES + j * (BK * 128), &tmA, full + s, m0 + 64 * j, kb * BK, ea);
+          for (int j = 0; j < (p.BN + 63) / 64; ++j)
+            tma_load_3d(smB + s * b_stage_bytes + j * (BK * 128), &tmB, full + s, n0 + 64 * j, kb * BK, eb);
+        } else {
+          tma_load_3d(smA + s * A_STAGE_BYTES, &tmA, full + s, kb * BK, m0, ea);
+          tma_load_3d(smB + s * b_stage_bytes, &tmB, full + s, kb * BK, n0, eb);
+        }
       }
       if (dbg) dbg[2] = clock64();  // all TMA issued
     }
@@ -185,19 +206,29 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BM >> 4) << 24) | (p.mn_major ? ((1u << 15) | (1u << 16)) : 0u);
       for (int kb = kb_begin, i = 0; kb < kb_end; ++kb, ++i) {
         int s = i % STAGES;
         uint32_t phase = (i / STAGES) & 1;
         mbar_wait(full + s, phase);
         if (dbg && i == 0) dbg[3] = clock64();  // first stage landed
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint64_t adesc = make_desc(smem_u32(smA + s * A_STAGE_BYTES));
-        uint64_t bdesc = make_desc(smem_u32(smB + s * b_stage_bytes));
+        if (p.mn_major) {
+          uint64_t adesc = make_desc_mn(smem_u32(smA + s * A_STAGE_BYTES));
+          uint64_t bdesc = make_desc_mn(smem_u32(smB + s * b_stage_bytes));
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
-          mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 reduction rows (16 x 128 B = 2048 B): +128 in the (>>4) address field
+            mma_bf16(tmem_base, adesc + 128 * k, bdesc + 128 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+        } else {
+          uint64_t adesc = make_desc(smem_u32(smA + s * A_STAGE_BYTES));
+          uint64_t bdesc = make_desc(smem_u32(smB + s * b_stage_bytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (>>4) address field
+            mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         mma_commit(empty + s);  // frees the smem stage when these MMAs retire
       }
@@ -451,6 +482,24 @@ static int make_map(CUtensorMap* map, const void* base, int k, int rows, int mem
   return D3B_OK;
 }
 
+// MN-major bf16 operand [members][k_rows][mn] (row-major, reduction index on rows) with leading dim ld.
+static int make_map_mn(CUtensorMap* map, const void* base, int mn, int k_rows, int members, long long ld,
+                       long long stride, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (((uintptr_t)base & 15) || (ld & 7) || (members > 1 && (stride & 7)))
+    return set_err(D3B_ERR_ARG, "umma_gemm_tn: %s must be 16-byte aligned with ld/stride multiples of 8 bf16", what);
+  cuuint64_t dims[3] = {(cuuint64_t)mn, (cuuint64_t)k_rows, (cuuint64_t)(members < 1 ? 1 : members)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)((members > 1 ? stride : ld * (long long)k_rows) * 2)};
+  cuuint32_t box[3] = {64, (cuuint32_t)BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
+  return D3B_OK;
+}
+
 }  // namespace umma
 }  // namespace d3b
 
@@ -525,4 +574,52 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
   umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("umma_gemm");
+}
+
+// Weight-gradient form: C[e] (m x n) (+)= A[e]^T B[e] with A [k][m] and B [k][n] row-major bf16 (the saved
+// dZ_l and H_{l-1} of a layer, reduction over the k = minibatch rows).  Both operands are fed to
+// tcgen05.mma as MN-major tiles straight from those row-major tensors: no transposed copies.
+extern "C" int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, const void* b, int64_t ldb,
+                                int64_t stride_b, int m, int n, int k, int members, int splits, float* out_f32,
+                                int64_t ldf, int64_t stride_f, int atomic, void* stream) {
+  D3B_REQUIRE(m > 0 && n > 0 && k >= 0 && members > 0, "umma_gemm_tn: bad sizes");
+  if (k == 0) return D3B_OK;
+  D3B_REQUIRE(a && b && out_f32, "umma_gemm_tn: null pointer");
+  D3B_REQUIRE(splits >= 1 && (splits == 1 || atomic), "umma_gemm_tn: split-K needs the RED epilogue");
+  int BN = n > 128 ? 256 : (n > 64 ? 128 : (n > 32 ? 64 : 32));
+  if (BN == 256 && (long long)ceil_div(m, BM) * ceil_div(n, 256) * members * splits < 2LL * kNumSM) BN = 128;
+  Params p{};
+  p.M = m; p.N = n; p.K = k; p.BN = BN; p.mn_major = 1;
+  p.lg_bn = BN == 256 ? 8 : (BN == 128 ? 7 : (BN == 64 ? 6 : 5));
+  int num_kb = ceil_div(k, BK);
+  if (splits > num_kb) splits = num_kb;
+  p.kb_per_split = ceil_div(num_kb, splits);
+  p.splits = ceil_div(num_kb, p.kb_per_split);
+  p.a_shared = stride_a == 0; p.b_shared = stride_b == 0;
+  p.out_f32 = out_f32; p.ldf = ldf; p.sF = stride_f; p.atomic = atomic;
+  p.dbg = g_umma_dbg;
+  CUtensorMap tmA, tmB;
+  int rc = make_map_mn(&tmA, a, m, k, p.a_shared ? 1 : members, lda, stride_a, "A");
+  if (rc) return rc;
+  rc = make_map_mn(&tmB, b, n, k, p.b_shared ? 1 : members, ldb, stride_b, "B");
+  if (rc) return rc;
+  size_t b_stage = (size_t)(BN < 64 ? 64 : BN) * BK * 2;
+  size_t stage_bytes = (size_t)A_STAGE_BYTES + b_stage;
+  size_t need_epi = (size_t)BM * (BN + 4) * 4;
+  size_t tail = 256 + 1024;
+  int stages = BN == 256 ? MAX_STAGES : 3;
+  while (stages > 2 && 1024 + stages * stage_bytes + tail > 227 * 1024) --stages;
+  while ((size_t)stages * stage_bytes < need_epi) ++stages;
+  D3B_REQUIRE(stages <= MAX_STAGES && 1024 + stages * stage_bytes + tail <= 227 * 1024,
+              "umma_gemm_tn: tile does not fit shared memory (BN=%d)", BN);
+  p.stages = stages;
+  size_t smem = 1024 + stages * stage_bytes + tail;
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
+  umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  return check_launch("umma_gemm_tn");
 }

@@ -46,18 +46,14 @@ class Ctx:
                             torch.zeros(E, rows, hm, dtype=torch.float32, device=dev)) if train else None
         else:
             bf = torch.bfloat16
-            self.ldr = _a8(rows)
             self.ldk0 = _a8(net.in_dim)
             self.xb = torch.zeros(rows, self.ldk0, dtype=bf, device=dev)
-            self.xbt = torch.zeros(net.in_dim, self.ldr, dtype=bf, device=dev) if train else None
+            # saved activations H_l (row-major bf16): ReLU masks and weight-gradient operands of the backward pass
             self.hb = [torch.zeros(E, rows, _a8(h), dtype=bf, device=dev) for h in hid]
-            # H_l^T feeds the weight gradient of layer l+1 (the last trunk output feeds the narrow head instead)
-            self.hbt = [torch.zeros(E, h, self.ldr, dtype=bf, device=dev) if train and i < len(hid) - 1 else None
-                        for i, h in enumerate(hid)]
             if train:
                 hm = _a8(max(hid + [net.in_dim]))
-                self.dz = (torch.zeros(E, rows, hm, dtype=bf, device=dev), torch.zeros(E, rows, hm, dtype=bf, device=dev))
-                self.dzt = torch.zeros(E, hm, self.ldr, dtype=bf, device=dev)
+                # dZ_l for every layer (the weight-gradient GEMMs read them after the data-gradient chain)
+                self.dz = [torch.zeros(E, rows, _a8(h), dtype=bf, device=dev) for h in hid]
 
 
 class DenseNet:
@@ -94,6 +90,9 @@ class DenseNet:
                                 exports=exports)
         self.feat = d
         self.device = device
+        # whole-network fused forward (csrc/mlp_fused.cu): widths multiples of 16 and <= 256, <= 4 layers, head <= 32
+        self.fused_ok = (precision == "bf16" and 1 <= len(self.hidden) <= 4 and in_dim <= 256 and self.head_out <= 32
+                         and all(h % 16 == 0 and 16 <= h <= 256 for h in self.hidden))
         self._ctx: Dict[str, Ctx] = {}
         self._init_params(seed_gen)
         if precision == "bf16":
@@ -193,17 +192,37 @@ class DenseNet:
                                _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
             return
         # ---- bf16 mode
-        L.to_bf16(_p(x), ldx, rows, self.in_dim, _p(ctx.xb), ctx.ldk0, _p(ctx.xbt), ctx.ldr if ctx.train else 0, stream)
+        L.to_bf16(_p(x), ldx, rows, self.in_dim, _p(ctx.xb), ctx.ldk0, None, 0, stream)
+        sms = self.shadow_member
+        if self.fused_ok:
+            # ONE persistent launch: trunk + head for all members, activations chained on-chip
+            import ctypes
+
+            nl = len(self.hidden)
+            dims = (ctypes.c_int * (nl + 1))(self.in_dim, *self.hidden)
+            wp = (ctypes.c_void_p * nl)(*[self._sw(which, i, member0)[0] for i in range(nl)])
+            ldw = (ctypes.c_int64 * nl)(*[self._sw(which, i, member0)[1] for i in range(nl)])
+            bp = (ctypes.c_void_p * nl)(*[self._b(which, i, member0) for i in range(nl)])
+            if ctx.train:
+                ap = (ctypes.c_void_p * nl)(*[_p(t) for t in ctx.hb])
+                lda = (ctypes.c_int64 * nl)(*[_a8(h) for h in self.hidden])
+                sa = (ctypes.c_int64 * nl)(*[rows * _a8(h) for h in self.hidden])
+            else:
+                ap, lda, sa = None, None, None
+            with_head = head_out is not None
+            L.mlp_forward_bf16(_p(ctx.xb), ctx.ldk0, 0, rows, E, nl, dims, wp, ldw, sms, bp, ms, ap, lda, sa,
+                               self._hw(which, member0) if with_head else None,
+                               self._hb(which, member0) if with_head else None, ms, n if with_head else 0,
+                               1 if head_tanh else 0, _p(head_out) if with_head else None, stream)
+            return
         cur, ld, sx = _p(ctx.xb), ctx.ldk0, 0
         d = self.in_dim
-        sms = self.shadow_member
         for i, h in enumerate(self.hidden):
             wptr, ldw = self._sw(which, i, member0)
-            y, yt = ctx.hb[i], ctx.hbt[i]
+            y = ctx.hb[i]
             lh = _a8(h)
             L.umma_gemm(cur, ld, sx, wptr, ldw, sms, rows, h, d, E, 1, self._b(which, i, member0), ms, 1,
-                        None, 0, 0, _p(y), lh, rows * lh, _p(yt), ctx.ldr if yt is not None else 0,
-                        h * ctx.ldr if yt is not None else 0, None, 0, 0, 0, stream)
+                        None, 0, 0, _p(y), lh, rows * lh, None, 0, 0, None, 0, 0, 0, stream)
             cur, ld, sx, d = _p(y), lh, rows * lh, h
         if head_out is not None:
             L.head_forward_bf16(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
@@ -249,18 +268,17 @@ class DenseNet:
                     L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", 0, member0) + 4 * dx_col0, d_in,
                                            ms, _p(dx), lddx, stride_dx, None, 0, 0, rows, h, dx_cols, E, stream)
             return
-        # ---- bf16 mode: every GEMM is C = A B^T over K-major bf16 operands
+        # ---- bf16 mode.  dgrad: C = A B^T over K-major operands (dZ_l, W_l^T shadow); wgrad: C += A^T B with
+        # both operands row-major (MN-major UMMA tiles): dW_l = dZ_l^T H_{l-1}, reduction over the minibatch rows
         last = ctx.hb[-1]
         sms = self.shadow_member
-        ldr = ctx.ldr
         lf = _a8(feat)
         if weight_grads:
             L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),
                                         feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
-        dcur, which = ctx.dz[0], 0
+        dcur = ctx.dz[nl - 1]
         L.head_backward_data_bf16(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), lf,
-                                  rows * lf, _p(ctx.dzt) if weight_grads else None, ldr, feat * ldr, _p(last), lf,
-                                  rows * lf, rows, n, feat, E, stream)
+                                  rows * lf, None, 0, 0, _p(last), lf, rows * lf, rows, n, feat, E, stream)
         for i in range(nl - 1, -1, -1):
             h = self.hidden[i]
             lh = _a8(h)
@@ -269,22 +287,20 @@ class DenseNet:
             if weight_grads:
                 L.colsum_bf16(_p(dcur), lh, rows * lh, self._b("grads", i, member0), ms, rows, h, E, stream)
                 if i > 0:
-                    bt, sbt = _p(ctx.hbt[i - 1]), d_in * ldr
+                    bsrc, ldb, sb = _p(ctx.hb[i - 1]), ldi, rows * ldi
                 else:
-                    bt, sbt = _p(ctx.xbt), 0
+                    bsrc, ldb, sb = _p(ctx.xb), ctx.ldk0, 0
                 tiles = -(-h // 128) * -(-d_in // 256) * E
                 splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
-                # dW_i[h][d_in] += dZ_i^T[h][rows] . (H_{i-1}^T[d_in][rows])^T
-                L.umma_gemm(_p(ctx.dzt), ldr, h * ldr, bt, ldr, sbt, h, d_in, rows, E, splits, None, 0, 0, None, 0, 0,
-                            None, 0, 0, None, 0, 0, self._w("grads", i, member0), d_in, ms, 1, stream)
+                L.umma_gemm_tn(_p(dcur), lh, rows * lh, bsrc, ldb, sb, h, d_in, rows, E, splits,
+                               self._w("grads", i, member0), d_in, ms, 1, stream)
             if i > 0:
-                dnext = ctx.dz[1 - which]
+                dnext = ctx.dz[i - 1]
                 wt, ldwt = self._swt(i, member0)
                 # dZ_{i-1} = (dZ_i W_i) * [H_{i-1} > 0]   (B operand = W_i^T [d_in][h])
                 L.umma_gemm(_p(dcur), lh, rows * lh, wt, ldwt, sms, rows, d_in, h, E, 1, None, 0, 0, _p(ctx.hb[i - 1]),
-                            ldi, rows * ldi, _p(dnext), ldi, rows * ldi,
-                            _p(ctx.dzt) if weight_grads else None, ldr, d_in * ldr, None, 0, 0, 0, stream)
-                dcur, which = dnext, 1 - which
+                            ldi, rows * ldi, _p(dnext), ldi, rows * ldi, None, 0, 0, None, 0, 0, 0, stream)
+                dcur = dnext
             elif dx is not None:
                 wt, ldwt = self._swt(0, member0)
                 L.umma_gemm(_p(dcur), lh, rows * lh, wt + 2 * dx_col0 * ldwt, ldwt, sms, rows, dx_cols, h, E, 1, None, 0,

@@ -98,6 +98,23 @@ int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const void* b, i
                   const void* mask, int64_t ld_mask, int64_t stride_mask, void* out_bf16, int64_t ldo,
                   int64_t stride_o, void* out_t_bf16, int64_t ldt, int64_t stride_t, float* out_f32, int64_t ldf,
                   int64_t stride_f, int atomic, void* stream);
+/* weight-gradient form c[e] (m x n) (+)= a[e]^T b[e], a [k][m] and b [k][n] row-major bf16 (MN-major UMMA
+ * operands loaded by TMA straight from the saved dZ_l / H_{l-1}; no transposed copies) */
+int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, const void* b, int64_t ldb, int64_t stride_b, int m,
+                     int n, int k, int members, int splits, float* out_f32, int64_t ldf, int64_t stride_f, int atomic,
+                     void* stream);
+/* mlp_forward_bf16: the whole ReLU trunk + narrow head of one network for all members in ONE persistent launch
+ * (activations chained through shared memory / TMEM; H_l TMA-stored only when acts_host[l] != NULL).
+ * Host arrays: dims_host = {K_0, N_0..N_{L-1}}; w_host/bias_host/acts_host[l] = member-0 pointers of layer l
+ * (bf16 K-major weight shadows, fp32 biases, bf16 [members][rows][ld_act] outputs).  Layer widths must be
+ * multiples of 16 and <= 256, n_layers <= 4, n_head <= 32 (0 = trunk only).  Replaces encoders.py:265-339 +
+ * ensemble_q_function.py:141-175 + the `_fc/_mu/_logstd` heads in one call. */
+int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, int rows, int members, int n_layers,
+                         const int* dims_host, const void* const* w_host, const int64_t* ldw_host, int64_t stride_w,
+                         const float* const* bias_host, int64_t stride_bias, void* const* acts_host,
+                         const int64_t* ld_act_host, const int64_t* stride_act_host, const float* head_w,
+                         const float* head_b, int64_t stride_head, int n_head, int head_tanh, float* head_out,
+                         void* stream);
 int d3b_umma_set_debug(void* device_buffer); /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);

@@ -175,3 +175,111 @@ def test_bf16_support_kernels():
     ref = torch.einsum("emn,emk->enk", dy, x.float())
     assert (dw - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
     assert (dbias - dy.sum(1)).abs().max().item() <= 1e-4 * dy.sum(1).abs().max().item()
+
+
+@pytest.mark.parametrize("R,No,Ki,E,shared_b", [(7936, 256, 256, 2, False), (7936, 256, 23, 2, True),
+                                                 (256, 256, 17, 1, False), (200, 48, 24, 1, False),
+                                                 (1000, 32, 32, 3, False), (130, 256, 119, 2, True)])
+def test_umma_wgrad_mn_major_operands(R, No, Ki, E, shared_b):
+    """dW[No][Ki] += dZ[R][No]^T . X[R][Ki] with both operands row-major (MN-major UMMA tiles, no transposes)."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(R + Ki)
+    ldn, ldk = (No + 7) // 8 * 8, (Ki + 7) // 8 * 8
+    dz = torch.full((E, R, ldn), 5.0, dtype=torch.bfloat16)      # padding garbage must be ignored
+    dz[:, :, :No] = _bf(torch.randn(E, R, No, generator=g) * 0.1)
+    Eb = 1 if shared_b else E
+    x = torch.full((Eb, R, ldk), -2.0, dtype=torch.bfloat16)
+    x[:, :, :Ki] = _bf(torch.randn(Eb, R, Ki, generator=g))
+    dz, x = dz.to(dev), x.to(dev)
+    dw0 = torch.randn(E, No, Ki, generator=g).to(dev)
+    for splits in (1, 37):
+        dw = dw0.clone()
+        L.umma_gemm_tn(dz.data_ptr(), ldn, R * ldn, x.data_ptr(), ldk, 0 if shared_b else R * ldk, No, Ki, R, E, splits,
+                       dw.data_ptr(), Ki, No * Ki, 1, _st())
+        torch.cuda.synchronize()
+        ref = dw0 + torch.einsum("ern,erk->enk", dz[:, :, :No].float(), x[:, :, :Ki].float().expand(E, R, Ki))
+        err = (dw - ref).abs().max().item()
+        assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (splits, err)
+
+
+@pytest.mark.parametrize("rows,E,in_dim,hidden,n_head,tanh,shared", [
+    (7936, 2, 23, [256, 256, 256], 1, False, True),     # c2 critic on the importance-sampling rows
+    (512, 1, 17, [256, 256, 256], 12, False, True),     # c2 policy (mu|logstd)
+    (300, 3, 14, [256, 256], 1, False, True),           # c1 critic, ragged last tile
+    (256, 1, 11, [256, 256], 3, True, True),            # c1 actor with tanh head
+    (100, 2, 9, [32, 32, 32], 1, False, True),          # golden-test widths
+    (1000, 2, 119, [64, 128, 16, 256], 24, False, True),  # 4 layers, mixed widths, wide head
+    (200, 2, 40, [64], 0, False, False),                # single layer, trunk only, per-member input
+    (40000, 2, 23, [256, 256, 256], 1, False, True),    # several units per CTA (persistent loop, phase wrap)
+])
+def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, shared):
+    """csrc/mlp_fused.cu vs torch on the same bf16-rounded operands (fp32 accumulate, bf16 activations):
+    saved activations within one bf16 ulp of the reference chain, head within 2e-3 of its scale."""
+    import ctypes
+
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(rows + in_dim)
+    a8 = lambda v: (v + 7) // 8 * 8
+    Ex = 1 if shared else E
+    x = torch.full((Ex, rows, a8(in_dim)), 3.0, dtype=torch.bfloat16)   # padding garbage must be ignored
+    x[:, :, :in_dim] = _bf(torch.randn(Ex, rows, in_dim, generator=g))
+    dims = [in_dim] + hidden
+    # one flat bf16 shadow and one flat fp32 arena per member, like ParamArena / DenseNet._build_shadow
+    w_off, off = [], 0
+    for k, n in zip(dims[:-1], dims[1:]):
+        w_off.append(off)
+        off += n * a8(k)
+    sms = a8(off)
+    shadow = torch.full((E, sms), -1.0, dtype=torch.bfloat16)
+    ws = []
+    for o, k, n in zip(w_off, dims[:-1], dims[1:]):
+        w = _bf(torch.randn(E, n, k, generator=g) / math.sqrt(k))
+        ws.append(w)
+        shadow[:, o:o + n * a8(k)].view(E, n, a8(k))[:, :, :k] = w
+    feat = hidden[-1]
+    nh = max(n_head, 1)
+    b_off, off = [], 0
+    for n in hidden:
+        b_off.append(off)
+        off += n
+    hw_off, hb_off = off, off + nh * feat
+    ms = hb_off + nh
+    arena = torch.zeros(E, ms)
+    bs = [torch.randn(E, n, generator=g) * 0.1 for n in hidden]
+    for o, b in zip(b_off, bs):
+        arena[:, o:o + b.shape[1]] = b
+    hw = torch.randn(E, nh, feat, generator=g) / math.sqrt(feat)
+    hb = torch.randn(E, nh, generator=g) * 0.1
+    arena[:, hw_off:hw_off + nh * feat] = hw.reshape(E, -1)
+    arena[:, hb_off:hb_off + nh] = hb
+    x, shadow, arena = x.to(dev), shadow.to(dev), arena.to(dev)
+    acts = [torch.zeros(E, rows, a8(n), dtype=torch.bfloat16, device=dev) for n in hidden]
+    out = torch.zeros(E, rows, nh, device=dev)
+    nl = len(hidden)
+    arr = lambda T, vals: (T * len(vals))(*vals)
+    L.mlp_forward_bf16(x.data_ptr(), a8(in_dim), 0 if shared else rows * a8(in_dim), rows, E, nl,
+                       arr(ctypes.c_int, dims), arr(ctypes.c_void_p, [shadow.data_ptr() + 2 * o for o in w_off]),
+                       arr(ctypes.c_int64, [a8(k) for k in dims[:-1]]), sms,
+                       arr(ctypes.c_void_p, [arena.data_ptr() + 4 * o for o in b_off]), ms,
+                       arr(ctypes.c_void_p, [a.data_ptr() for a in acts]), arr(ctypes.c_int64, [a.shape[2] for a in acts]),
+                       arr(ctypes.c_int64, [a.shape[1] * a.shape[2] for a in acts]),
+                       arena.data_ptr() + 4 * hw_off, arena.data_ptr() + 4 * hb_off, ms, n_head, 1 if tanh else 0,
+                       out.data_ptr(), _st())
+    torch.cuda.synchronize()
+    h = x[:, :, :in_dim].float().expand(E, rows, in_dim)
+    for l, (w, b) in enumerate(zip(ws, bs)):
+        ref = torch.relu(torch.einsum("erk,enk->ern", h, w.to(dev).float()) + b.to(dev)[:, None, :])
+        got = acts[l][:, :, :hidden[l]].float()
+        scale = max(1.0, ref.abs().max().item())
+        assert (got - ref).abs().max().item() <= 2.0 ** -7 * scale, (l, (got - ref).abs().max().item())
+        h = got  # continue from the kernel's own bf16 activations so that errors do not compound in the check
+    if n_head:
+        ref = torch.einsum("erk,ejk->erj", h, hw.to(dev)) + hb.to(dev)[:, None, :]
+        if tanh:
+            ref = torch.tanh(ref)
+        err = (out - ref).abs().max().item()
+        assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
