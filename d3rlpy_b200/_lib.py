@@ -82,6 +82,12 @@ class Lib:
         if name in self._FLOP_ARGS:
             i = self._FLOP_ARGS[name]
             flops = 2.0 * args[i[0]] * args[i[1]] * args[i[2]] * args[i[3]]
+        elif name == "mlp_backward_bf16":  # rows, members, n_layers, dims[]; dgrad chain (+ head) (+ dx columns)
+            dims = list(args[3])
+            mac = sum(a * b for a, b in zip(dims[1:-1], dims[2:])) + dims[-1] * args[16]
+            if args[21]:
+                mac += dims[1] * args[25]
+            flops = 2.0 * args[0] * args[1] * mac
         elif name == "mlp_forward_bf16":  # rows, members, n_layers, dims[] (+ head: n_head at 18)
             dims = list(args[6])
             mac = sum(a * b for a, b in zip(dims[:-1], dims[1:])) + dims[-1] * args[18]

@@ -355,6 +355,336 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ backward (data)
+// One persistent launch for the whole data-gradient chain of a network (autograd of the forward above):
+//   dZ_{L-1} = (d_head . W_head) * [H_{L-1} > 0]            computed by the epilogue warps (thread = row)
+//   dZ_{l-1} = (dZ_l . W_l) * [H_{l-1} > 0]                 tcgen05.mma: A = dZ_l in the operand buffer,
+//                                                           B = W_l row-major = MN-major tiles (no W^T copy)
+//   dX[:, col0:col0+cols] = dZ_0 . W_0[:, col0:col0+cols]   optional (gradient w.r.t. the action input)
+// and, when weight gradients are wanted: every dZ_l is TMA-stored for the weight-gradient GEMM, bias
+// gradients (column sums of dZ_l) and the head's dW/db are reduced per tile and RED-added to the arena.
+// H_l tiles (ReLU masks) are TMA-loaded into a second operand-layout buffer.
+constexpr int BW_STAGES = 2;
+enum { C_WFULL = 0, C_WEMPTY = BW_STAGES, C_MFULL = 2 * BW_STAGES, C_MEMPTY, C_ACCFULL, C_TEMPTY = C_ACCFULL + 2,
+       C_ACTREADY = C_TEMPTY + 2, C_COUNT };
+
+struct BwdMaps {
+  CUtensorMap w[MAX_LAYERS];
+  CUtensorMap h[MAX_LAYERS];
+  CUtensorMap dz[MAX_LAYERS];
+};
+
+struct BwdParams {
+  int rows, members, tiles, n_layers;
+  int K[MAX_LAYERS], N[MAX_LAYERS];
+  const float* d_head;   // [members][rows][n_head]
+  const float* head_w;   // [n_head][feat] per member
+  long long head_stride;
+  int n_head;
+  int weight_grads;
+  float* dbias[MAX_LAYERS];
+  float* d_head_w;
+  float* d_head_b;
+  long long grad_stride;
+  float* dx;             // [members][rows][dx_cols] (lddx), may be null
+  long long lddx, dx_stride;
+  int dx_col0, dx_cols;
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((BK * 128) >> 4) << 16;  // next 64-wide MN group (one TMA box of 64 reduction rows)
+  d |= (uint64_t)(1024 >> 4) << 32;        // next 8 reduction rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ const __nv_bfloat16* swz_ptr(const uint8_t* buf, int r, int c) {
+  return reinterpret_cast<const __nv_bfloat16*>(buf + (c >> 6) * A_KB_BYTES + r * 128 +
+                                                ((((c & 63) >> 3) ^ (r & 7)) << 4) + (c & 7) * 2);
+}
+
+template <int NH>
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_constant__ BwdMaps maps, BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smA = smem;                                   // dZ_l operand buffer (4 K blocks)
+  uint8_t* smM = smem + MAX_KB * A_KB_BYTES;             // H_l tile (same layout): ReLU mask
+  uint8_t* smW = smM + MAX_KB * A_KB_BYTES;              // weight ring
+  float* head_w_s = (float*)(smW + BW_STAGES * W_STAGE_BYTES);  // [NH][MAXW]
+  float* dhead_s = head_w_s + NH * MAXW;                        // [128][NH]
+  uint64_t* bars = (uint64_t*)(dhead_s + BM * NH);
+  uint32_t* tmem_slot = (uint32_t*)(bars + C_COUNT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = p.n_layers;
+  const int units = p.tiles * p.members;
+  const bool has_dx = p.dx != nullptr;
+  // TMA box starts must be 16-byte aligned: load from the 8-column boundary below dx_col0 and skip `dx_shift`
+  // accumulator columns in the epilogue
+  const int dx_shift = p.dx_col0 & 7;
+  const int dx_w = has_dx ? ((dx_shift + p.dx_cols + 15) / 16) * 16 : 0;
+  const int n_steps = (L - 1) + (has_dx ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C_COUNT; ++i) mbar_init(bars + i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ================= TMA producer: mask tiles H_l (l = L-1..0) interleaved with the weight blocks of each step
+    if (lane == 0) {
+      uint32_t wi = 0, mi = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
+        for (int l = L - 1; l >= 0; --l) {
+          // mask for dZ_l
+          mbar_wait(bars + C_MEMPTY, (mi & 1) ^ 1);
+          const int nkbm = (p.N[l] + BK - 1) / BK;
+          mbar_expect_tx(bars + C_MFULL, nkbm * A_KB_BYTES);
+          for (int kb = 0; kb < nkbm; ++kb) tma_load_3d(smM + kb * A_KB_BYTES, &maps.h[l], bars + C_MFULL, kb * BK, m0, e);
+          ++mi;
+          // weights of the step that consumes dZ_l: W_l (l >= 1), or the dx columns of W_0
+          if (l == 0 && !has_dx) break;
+          const int outw = l > 0 ? p.K[l] : dx_w;
+          const int col0 = l > 0 ? 0 : (p.dx_col0 & ~7);
+          const int nbox = (outw + 63) / 64;
+          const int nkb = (p.N[l] + BK - 1) / BK;
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const uint32_t s = wi % BW_STAGES, ph = (wi / BW_STAGES) & 1;
+            mbar_wait(bars + C_WEMPTY + s, ph ^ 1);
+            mbar_expect_tx(bars + C_WFULL + s, nbox * (BK * 128));
+            for (int j = 0; j < nbox; ++j)
+              tma_load_3d(smW + s * W_STAGE_BYTES + j * (BK * 128), &maps.w[l], bars + C_WFULL + s, col0 + 64 * j,
+                          kb * BK, e);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================= MMA issuer: step s consumes dZ_l (l = L-1-s; the last optional step is the dx step on dZ_0)
+    if (lane == 0) {
+      uint32_t g = 0, wi = 0, act_cnt = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        for (int s_ = 0; s_ < n_steps; ++s_, ++g) {
+          const int l = L - 1 - s_;
+          const int outw = l > 0 ? p.K[l] : dx_w;
+          const uint32_t buf = g & 1;
+          mbar_wait(bars + C_TEMPTY + buf, ((g >> 1) & 1) ^ 1);
+          mbar_wait(bars + C_ACTREADY, act_cnt & 1);
+          ++act_cnt;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(outw >> 3) << 17) |
+                                 ((uint32_t)(BM >> 4) << 24);
+          const int nkb = (p.N[l] + BK - 1) / BK;
+          const int ksteps = (p.N[l] + UMMA_K - 1) / UMMA_K;
+          const uint32_t d_tmem = tmem_base + buf * 256;
+          for (int kb = 0; kb < nkb; ++kb, ++wi) {
+            const uint32_t s = wi % BW_STAGES, ph = (wi / BW_STAGES) & 1;
+            mbar_wait(bars + C_WFULL + s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t adesc = make_desc(smem_u32(smA + kb * A_KB_BYTES));
+            const uint64_t bdesc = make_desc_mn(smem_u32(smW + s * W_STAGE_BYTES));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (kb * (BK / UMMA_K) + k < ksteps)
+                mma_bf16(d_tmem, adesc + 2 * k, bdesc + 128 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            mma_commit(bars + C_WEMPTY + s);
+          }
+          mma_commit(bars + C_ACCFULL + buf);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps
+    const int t = threadIdx.x;
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    uint32_t g = 0, mi = 0;
+    int cur_member = -1;
+    bool stores_pending = false;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
+      const int feat = p.N[L - 1];
+      if (e != cur_member) {
+        epi_sync();
+        const float* hw = p.head_w + (long long)e * p.head_stride;
+        for (int i = t; i < NH * MAXW; i += EPI_THREADS) {
+          int j = i / MAXW, c = i % MAXW;
+          head_w_s[i] = (j < p.n_head && c < feat) ? __ldg(hw + (long long)j * feat + c) : 0.f;
+        }
+        cur_member = e;
+      }
+      // d_head row -> registers (+ shared copy for the column passes)
+      float dh[NH];
+      {
+        const bool live = m0 + row < p.rows;
+        const float* src = p.d_head + ((long long)e * p.rows + m0 + row) * p.n_head;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) dh[j] = (live && j < p.n_head) ? __ldg(src + j) : 0.f;
+        if (half == 0) {
+#pragma unroll
+          for (int j = 0; j < NH; ++j) dhead_s[row * NH + j] = dh[j];
+        }
+      }
+      if (stores_pending) {
+        if (t == 0) tma_store_wait_read();
+        stores_pending = false;
+      }
+      epi_sync();  // head_w_s / dhead_s visible; previous unit's stores done reading the operand buffer
+      for (int l = L - 1; l >= 0; --l) {
+        // ---- produce dZ_l into the operand buffer
+        const int N = p.N[l];
+        const bool top = (l == L - 1);
+        uint32_t buf = 0;
+        if (!top) {
+          buf = g & 1;
+          mbar_wait(bars + C_ACCFULL + buf, (g >> 1) & 1);  // (dZ_{l+1} W_{l+1}) ready; MMA finished reading the buffer
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (stores_pending) {
+            if (t == 0) tma_store_wait_read();
+            epi_sync();
+            stores_pending = false;
+          }
+        }
+        mbar_wait(bars + C_MFULL, mi & 1);
+        ++mi;
+        const int cph = ((N + 31) / 32) * 16;
+        const int c_begin = half ? cph : 0;
+        const int c_end = half ? N : (cph < N ? cph : N);
+        const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+        for (int c = c_begin; c < c_end; c += 16) {
+          float f[16];
+          if (top) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              const float4* w4 = reinterpret_cast<const float4*>(head_w_s + j * MAXW + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 w = w4[i];
+                f[4 * i] = fmaf(dh[j], w.x, f[4 * i]);
+                f[4 * i + 1] = fmaf(dh[j], w.y, f[4 * i + 1]);
+                f[4 * i + 2] = fmaf(dh[j], w.z, f[4 * i + 2]);
+                f[4 * i + 3] = fmaf(dh[j], w.w, f[4 * i + 3]);
+              }
+            }
+          } else {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          }
+          const int kb = c >> 6, j0 = (c & 63) >> 3;
+          const int off0 = kb * A_KB_BYTES + row * 128 + ((j0 ^ (row & 7)) << 4);
+          const int off1 = kb * A_KB_BYTES + row * 128 + (((j0 + 1) ^ (row & 7)) << 4);
+          uint4 m0v = *reinterpret_cast<const uint4*>(smM + off0);
+          uint4 m1v = *reinterpret_cast<const uint4*>(smM + off1);
+          const uint32_t mk[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = bf16_lo(mk[i]) > 0.f ? f[2 * i] : 0.f;
+            float b = bf16_hi(mk[i]) > 0.f ? f[2 * i + 1] : 0.f;
+            pk[i] = pack_bf16(a, b);
+          }
+          *reinterpret_cast<uint4*>(smA + off0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(smA + off1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (!top) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_sync();
+        const bool mma_follows = (l > 0) || has_dx;
+        if (t == 0) {
+          if (!top) mbar_arrive(bars + C_TEMPTY + buf);
+          if (mma_follows) mbar_arrive(bars + C_ACTREADY);
+          if (p.weight_grads) {
+            const int nkb_out = (N + BK - 1) / BK;
+            for (int kb = 0; kb < nkb_out; ++kb) tma_store_3d(&maps.dz[l], smA + kb * A_KB_BYTES, kb * BK, m0, e);
+            tma_store_commit();
+          }
+        }
+        if (!top) ++g;
+        stores_pending = p.weight_grads != 0;
+        // ---- column passes over the tile (thread = column), overlapping the MMA of the next step
+        if (p.weight_grads) {
+          if (t < N) {
+            float s = 0.f;
+            for (int r = 0; r < BM; ++r) s += __bfloat162float(*swz_ptr(smA, r, t));
+            atomicAdd(p.dbias[l] + (long long)e * p.grad_stride + t, s);
+          }
+          if (top) {
+            if (t < N) {
+              float a[NH];
+#pragma unroll
+              for (int j = 0; j < NH; ++j) a[j] = 0.f;
+              for (int r = 0; r < BM; ++r) {
+                float hv = __bfloat162float(*swz_ptr(smM, r, t));
+#pragma unroll
+                for (int j = 0; j < NH; ++j) a[j] = fmaf(dhead_s[r * NH + j], hv, a[j]);
+              }
+#pragma unroll
+              for (int j = 0; j < NH; ++j)
+                if (j < p.n_head) atomicAdd(p.d_head_w + (long long)e * p.grad_stride + (long long)j * feat + t, a[j]);
+            }
+            if (t < p.n_head) {
+              float s = 0.f;
+              for (int r = 0; r < BM; ++r) s += dhead_s[r * NH + t];
+              atomicAdd(p.d_head_b + (long long)e * p.grad_stride + t, s);
+            }
+          }
+        }
+        // the mask tile has been consumed (by the element pass and the head column pass)
+        epi_sync();
+        if (t == 0) mbar_arrive(bars + C_MEMPTY);
+      }
+      if (has_dx) {
+        const uint32_t buf = g & 1;
+        mbar_wait(bars + C_ACCFULL + buf, (g >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+        if (half == 0) {
+          for (int c = 0; c < dx_w; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)c, v);
+            if (m0 + row < p.rows) {
+              float* o = p.dx + (long long)e * p.dx_stride + (long long)(m0 + row) * p.lddx;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c + i >= dx_shift && c + i < dx_shift + p.dx_cols) o[c + i - dx_shift] = __uint_as_float(v[i]);
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        epi_sync();
+        if (t == 0) mbar_arrive(bars + C_TEMPTY + buf);
+        ++g;
+      }
+    }
+    if (t == 0) tma_store_wait_all();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace fused
 }  // namespace d3b
 
@@ -466,4 +796,105 @@ extern "C" int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x
   if (n_head <= 8) return launch_fwd<8>(maps, p, grid, st);
   if (n_head <= 16) return launch_fwd<16>(maps, p, grid, st);
   return launch_fwd<32>(maps, p, grid, st);
+}
+
+namespace {
+
+// row-major bf16 weight [members][n_rows][cols] used as an MN-major operand: boxes of {64 cols, 64 reduction rows}
+int make_map_w_mn(CUtensorMap* map, const void* base, int cols, int n_rows, int members, long long ld,
+                  long long stride) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (((uintptr_t)base & 15) || (ld & 7) || (members > 1 && (stride & 7)))
+    return set_err(D3B_ERR_ARG, "mlp_backward: W must be 16-byte aligned with ld/stride multiples of 8 bf16");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)n_rows, (cuuint64_t)(members < 1 ? 1 : members)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)((members > 1 ? stride : ld * (long long)n_rows) * 2)};
+  cuuint32_t box[3] = {64, (cuuint32_t)BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(D3B_ERR_CUDA, "cuTensorMapEncodeTiled(W mn) failed: %d", (int)r);
+  return D3B_OK;
+}
+
+template <int NH>
+size_t bwd_smem() {
+  return 1024 + (size_t)2 * MAX_KB * A_KB_BYTES + (size_t)BW_STAGES * W_STAGE_BYTES +
+         sizeof(float) * ((size_t)NH * MAXW + (size_t)BM * NH) + 8 * C_COUNT + 64;
+}
+
+template <int NH>
+int launch_bwd(const BwdMaps& maps, const BwdParams& p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(mlp_backward_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)bwd_smem<NH>()));
+    attr_set = true;
+  }
+  mlp_backward_kernel<NH><<<grid, NTHREADS, bwd_smem<NH>(), st>>>(maps, p);
+  return check_launch("mlp_backward_bf16");
+}
+
+}  // namespace
+
+// Data-gradient chain of the network evaluated by d3b_mlp_forward_bf16 (same dims / weight shadows / saved
+// activations).  d_head: fp32 [members][rows][n_head] gradient w.r.t. the head's pre-activation output.
+// dbias_host != NULL selects the training form: dZ_l are stored to dz_host[l] (bf16, for the weight-gradient
+// GEMMs d3b_umma_gemm_tn), bias and head gradients are RED-added into the gradient arena (member stride
+// stride_grad).  dx != NULL additionally returns the gradient w.r.t. input columns [dx_col0, dx_col0+dx_cols).
+extern "C" int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const int* dims_host,
+                                     const void* const* w_host, const int64_t* ldw_host, int64_t stride_w,
+                                     const void* const* acts_host, const int64_t* ld_act_host,
+                                     const int64_t* stride_act_host, void* const* dz_host, const int64_t* ld_dz_host,
+                                     const int64_t* stride_dz_host, const float* d_head, const float* head_w,
+                                     int64_t stride_head, int n_head, float* const* dbias_host, float* d_head_w,
+                                     float* d_head_b, int64_t stride_grad, float* dx, int64_t lddx, int64_t stride_dx,
+                                     int dx_col0, int dx_cols, void* stream) {
+  D3B_REQUIRE(rows >= 0 && members >= 1 && n_layers >= 1 && n_layers <= MAX_LAYERS, "mlp_backward_bf16: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dims_host && w_host && ldw_host && acts_host && ld_act_host && stride_act_host && d_head && head_w,
+              "mlp_backward_bf16: null pointer");
+  D3B_REQUIRE(n_head >= 1 && n_head <= 16, "mlp_backward_bf16: n_head must be in [1,16]");
+  const bool wg = dbias_host != nullptr;
+  D3B_REQUIRE(!wg || (dz_host && ld_dz_host && stride_dz_host && d_head_w && d_head_b),
+              "mlp_backward_bf16: weight-gradient form needs dz / head gradient pointers");
+  D3B_REQUIRE(!dx || (dx_cols >= 1 && dx_col0 >= 0 && dx_col0 + dx_cols <= dims_host[0] && dx_cols + 7 <= MAXW),
+              "mlp_backward_bf16: bad dx column range");
+  BwdParams p{};
+  BwdMaps maps;
+  p.rows = rows; p.members = members; p.tiles = ceil_div(rows, BM); p.n_layers = n_layers;
+  p.d_head = d_head; p.head_w = head_w; p.head_stride = stride_head; p.n_head = n_head;
+  p.weight_grads = wg ? 1 : 0;
+  p.d_head_w = d_head_w; p.d_head_b = d_head_b; p.grad_stride = stride_grad;
+  p.dx = dx; p.lddx = lddx; p.dx_stride = stride_dx; p.dx_col0 = dx_col0; p.dx_cols = dx_cols;
+  int k = dims_host[0];
+  D3B_REQUIRE(k >= 1 && k <= MAXW, "mlp_backward_bf16: input width must be in [1,256]");
+  int rc;
+  for (int l = 0; l < n_layers; ++l) {
+    int n = dims_host[l + 1];
+    D3B_REQUIRE(n >= 16 && n <= MAXW && n % 16 == 0, "mlp_backward_bf16: layer widths must be multiples of 16 in [16,256]");
+    D3B_REQUIRE(w_host[l] && acts_host[l], "mlp_backward_bf16: null layer pointer");
+    p.K[l] = k; p.N[l] = n;
+    rc = make_map_w_mn(&maps.w[l], w_host[l], k, n, members, ldw_host[l], stride_w);
+    if (rc) return rc;
+    rc = make_map(&maps.h[l], acts_host[l], n, rows, members, ld_act_host[l], stride_act_host[l], BM, "H");
+    if (rc) return rc;
+    if (wg) {
+      D3B_REQUIRE(dz_host[l] && dbias_host[l], "mlp_backward_bf16: null dz / dbias pointer");
+      rc = make_map(&maps.dz[l], dz_host[l], n, rows, members, ld_dz_host[l], stride_dz_host[l], BM, "dZ");
+      if (rc) return rc;
+      p.dbias[l] = dbias_host[l];
+    } else {
+      maps.dz[l] = maps.h[l];
+    }
+    k = n;
+  }
+  for (int l = n_layers; l < MAX_LAYERS; ++l) { maps.w[l] = maps.w[0]; maps.h[l] = maps.h[0]; maps.dz[l] = maps.h[0]; }
+  int units = p.tiles * members;
+  int grid = units < kNumSM ? units : kNumSM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_head == 1) return launch_bwd<1>(maps, p, grid, st);
+  if (n_head <= 8) return launch_bwd<8>(maps, p, grid, st);
+  return launch_bwd<16>(maps, p, grid, st);
 }

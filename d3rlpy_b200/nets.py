@@ -205,8 +205,8 @@ class DenseNet:
             bp = (ctypes.c_void_p * nl)(*[self._b(which, i, member0) for i in range(nl)])
             if ctx.train:
                 ap = (ctypes.c_void_p * nl)(*[_p(t) for t in ctx.hb])
-                lda = (ctypes.c_int64 * nl)(*[_a8(h) for h in self.hidden])
-                sa = (ctypes.c_int64 * nl)(*[rows * _a8(h) for h in self.hidden])
+                lda = (ctypes.c_int64 * nl)(*[t.shape[2] for t in ctx.hb])
+                sa = (ctypes.c_int64 * nl)(*[t.shape[1] * t.shape[2] for t in ctx.hb])
             else:
                 ap, lda, sa = None, None, None
             with_head = head_out is not None
@@ -270,8 +270,45 @@ class DenseNet:
             return
         # ---- bf16 mode.  dgrad: C = A B^T over K-major operands (dZ_l, W_l^T shadow); wgrad: C += A^T B with
         # both operands row-major (MN-major UMMA tiles): dW_l = dZ_l^T H_{l-1}, reduction over the minibatch rows
-        last = ctx.hb[-1]
         sms = self.shadow_member
+        if self.fused_ok and n <= 16:
+            # ONE persistent launch for the whole data-gradient chain (+ bias / head gradients), then one
+            # MN-major weight-gradient GEMM per layer over the stored dZ_l and saved H_{l-1}
+            import ctypes
+
+            dims = (ctypes.c_int * (nl + 1))(self.in_dim, *self.hidden)
+            wp = (ctypes.c_void_p * nl)(*[self._sw("params", i, member0)[0] for i in range(nl)])
+            ldw = (ctypes.c_int64 * nl)(*[self._sw("params", i, member0)[1] for i in range(nl)])
+            ap = (ctypes.c_void_p * nl)(*[_p(t) for t in ctx.hb])
+            lda = (ctypes.c_int64 * nl)(*[t.shape[2] for t in ctx.hb])
+            sa = (ctypes.c_int64 * nl)(*[t.shape[1] * t.shape[2] for t in ctx.hb])
+            if weight_grads:
+                dzp = (ctypes.c_void_p * nl)(*[_p(t) for t in ctx.dz])
+                lddz = (ctypes.c_int64 * nl)(*[t.shape[2] for t in ctx.dz])
+                sdz = (ctypes.c_int64 * nl)(*[t.shape[1] * t.shape[2] for t in ctx.dz])
+                dbp = (ctypes.c_void_p * nl)(*[self._b("grads", i, member0) for i in range(nl)])
+            else:
+                dzp = lddz = sdz = dbp = None
+            L.mlp_backward_bf16(rows, E, nl, dims, wp, ldw, sms, ap, lda, sa, dzp, lddz, sdz, _p(d_head),
+                                self._hw("params", member0), ms, n, dbp,
+                                self._hw("grads", member0) if weight_grads else None,
+                                self._hb("grads", member0) if weight_grads else None, ms,
+                                _p(dx) if dx is not None else None, lddx, stride_dx, dx_col0, dx_cols, stream)
+            if weight_grads:
+                for i in range(nl):
+                    h, d_in = self.hidden[i], (self.hidden[i - 1] if i > 0 else self.in_dim)
+                    dz = ctx.dz[i]
+                    if i > 0:
+                        prev = ctx.hb[i - 1]
+                        bsrc, ldb, sb = _p(prev), prev.shape[2], prev.shape[1] * prev.shape[2]
+                    else:
+                        bsrc, ldb, sb = _p(ctx.xb), ctx.ldk0, 0
+                    tiles = -(-h // 128) * -(-d_in // 256) * E
+                    splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
+                    L.umma_gemm_tn(_p(dz), dz.shape[2], dz.shape[1] * dz.shape[2], bsrc, ldb, sb, h, d_in, rows, E,
+                                   splits, self._w("grads", i, member0), d_in, ms, 1, stream)
+            return
+        last = ctx.hb[-1]
         lf = _a8(feat)
         if weight_grads:
             L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),

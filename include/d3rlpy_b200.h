@@ -115,6 +115,17 @@ int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, int rows,
                          const int64_t* ld_act_host, const int64_t* stride_act_host, const float* head_w,
                          const float* head_b, int64_t stride_head, int n_head, int head_tanh, float* head_out,
                          void* stream);
+/* mlp_backward_bf16: autograd of mlp_forward_bf16 w.r.t. activations in ONE persistent launch: dZ_{L-1} from
+ * d_head and the head weights, then dZ_{l-1} = (dZ_l W_l) * [H_{l-1} > 0] with W_l fed as MN-major tiles, optional
+ * dX for input columns [dx_col0, dx_col0+dx_cols).  dbias_host != NULL: also store every dZ_l (operands of the
+ * weight-gradient GEMMs d3b_umma_gemm_tn) and RED-add bias / head gradients into the gradient arena. */
+int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const int* dims_host, const void* const* w_host,
+                          const int64_t* ldw_host, int64_t stride_w, const void* const* acts_host,
+                          const int64_t* ld_act_host, const int64_t* stride_act_host, void* const* dz_host,
+                          const int64_t* ld_dz_host, const int64_t* stride_dz_host, const float* d_head,
+                          const float* head_w, int64_t stride_head, int n_head, float* const* dbias_host,
+                          float* d_head_w, float* d_head_b, int64_t stride_grad, float* dx, int64_t lddx,
+                          int64_t stride_dx, int dx_col0, int dx_cols, void* stream);
 int d3b_umma_set_debug(void* device_buffer); /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);

@@ -283,3 +283,99 @@ def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, 
             ref = torch.tanh(ref)
         err = (out - ref).abs().max().item()
         assert err <= 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+@pytest.mark.parametrize("rows,E,in_dim,hidden,n_head,wg,dxr", [
+    (7936, 2, 23, [256, 256, 256], 1, True, None),       # c2 critic step
+    (256, 2, 23, [256, 256, 256], 1, False, (17, 6)),    # c2 actor step: dX of the action columns only
+    (256, 1, 17, [256, 256, 256], 12, True, None),       # c2 policy
+    (300, 3, 14, [256, 256], 1, True, (11, 3)),          # ragged tile, weight grads + dx
+    (100, 2, 9, [32, 32, 32], 1, True, None),            # golden-test widths
+    (1000, 2, 119, [64, 128, 16, 256], 8, True, (100, 19)),
+    (200, 2, 40, [64], 3, True, (0, 40)),                # single layer
+    (40000, 2, 23, [256, 256, 256], 1, True, None),      # several units per CTA
+])
+def test_fused_mlp_backward_matches_torch(rows, E, in_dim, hidden, n_head, wg, dxr):
+    """csrc/mlp_fused.cu backward chain vs torch on the same bf16 operands, stage by stage."""
+    import ctypes
+
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(rows + in_dim + 1)
+    a8 = lambda v: (v + 7) // 8 * 8
+    dims = [in_dim] + hidden
+    nl = len(hidden)
+    w_off, off = [], 0
+    for k, n in zip(dims[:-1], dims[1:]):
+        w_off.append(off)
+        off += n * a8(k)
+    sms = a8(off)
+    shadow = torch.full((E, sms), -1.0, dtype=torch.bfloat16)
+    ws = []
+    for o, k, n in zip(w_off, dims[:-1], dims[1:]):
+        w = _bf(torch.randn(E, n, k, generator=g) / math.sqrt(k))
+        ws.append(w.to(dev))
+        shadow[:, o:o + n * a8(k)].view(E, n, a8(k))[:, :, :k] = w
+    shadow = shadow.to(dev)
+    feat = hidden[-1]
+    # saved activations: random bf16 with ~half of the entries <= 0 (the ReLU mask only looks at the sign)
+    acts = []
+    for n in hidden:
+        a = torch.zeros(E, rows, a8(n), dtype=torch.bfloat16)
+        a[:, :, :n] = _bf(torch.relu(torch.randn(E, rows, n, generator=g)))
+        acts.append(a.to(dev))
+    # gradient arena layout: [b_0 .. b_{L-1} | head_w | head_b]
+    b_off, off = [], 0
+    for n in hidden:
+        b_off.append(off)
+        off += n
+    hw_off, hb_off = off, off + n_head * feat
+    ms = (hb_off + n_head + 3) // 4 * 4
+    params = torch.zeros(E, ms)
+    hw = torch.randn(E, n_head, feat, generator=g) / math.sqrt(feat)
+    params[:, hw_off:hw_off + n_head * feat] = hw.reshape(E, -1)
+    params = params.to(dev)
+    hw = hw.to(dev)
+    grads = torch.zeros(E, ms, device=dev)
+    d_head = (torch.randn(E, rows, n_head, generator=g) / rows).to(dev)
+    dz = [torch.zeros(E, rows, a8(n), dtype=torch.bfloat16, device=dev) for n in hidden]
+    dx = torch.zeros(E, rows, dxr[1], device=dev) if dxr else None
+    arr = lambda T, vals: (T * len(vals))(*vals)
+    L.mlp_backward_bf16(rows, E, nl, arr(ctypes.c_int, dims),
+                        arr(ctypes.c_void_p, [shadow.data_ptr() + 2 * o for o in w_off]),
+                        arr(ctypes.c_int64, [a8(k) for k in dims[:-1]]), sms,
+                        arr(ctypes.c_void_p, [a.data_ptr() for a in acts]), arr(ctypes.c_int64, [a.shape[2] for a in acts]),
+                        arr(ctypes.c_int64, [a.shape[1] * a.shape[2] for a in acts]),
+                        arr(ctypes.c_void_p, [d.data_ptr() for d in dz]) if wg else None,
+                        arr(ctypes.c_int64, [d.shape[2] for d in dz]) if wg else None,
+                        arr(ctypes.c_int64, [d.shape[1] * d.shape[2] for d in dz]) if wg else None,
+                        d_head.data_ptr(), params.data_ptr() + 4 * hw_off, ms, n_head,
+                        arr(ctypes.c_void_p, [grads.data_ptr() + 4 * o for o in b_off]) if wg else None,
+                        grads.data_ptr() + 4 * hw_off if wg else None, grads.data_ptr() + 4 * hb_off if wg else None, ms,
+                        dx.data_ptr() if dxr else None, dxr[1] if dxr else 0, rows * dxr[1] if dxr else 0,
+                        dxr[0] if dxr else 0, dxr[1] if dxr else 0, _st())
+    torch.cuda.synchronize()
+
+    def close(got, ref, tol, what):
+        err = (got - ref).abs().max().item()
+        assert err <= tol * max(ref.abs().max().item(), 1e-30), (what, err, ref.abs().max().item())
+
+    # reference chain in fp32 over the same bf16 operands
+    cur = (torch.einsum("erj,ejc->erc", d_head, hw) * (acts[-1][:, :, :feat].float() > 0))
+    for l in range(nl - 1, -1, -1):
+        n = hidden[l]
+        cur_b = _bf(cur).float()
+        if wg:
+            close(dz[l][:, :, :n].float(), cur_b, 2.0 ** -7, f"dz{l}")
+            cur_b = dz[l][:, :, :n].float()  # continue from the kernel's own rounding
+            close(grads[:, b_off[l]:b_off[l] + n], cur_b.sum(1), 2e-3, f"dbias{l}")
+        if l > 0:
+            cur = torch.einsum("ern,enk->erk", cur_b, ws[l].float()) * (acts[l - 1][:, :, :hidden[l - 1]].float() > 0)
+        elif dxr:
+            ref = torch.einsum("ern,enk->erk", cur_b, ws[0].float()[:, :, dxr[0]:dxr[0] + dxr[1]])
+            close(dx, ref, 2.0 ** -6 if not wg else 2e-3, "dx")
+    if wg:
+        close(grads[:, hw_off:hw_off + n_head * feat].view(E, n_head, feat),
+              torch.einsum("erj,erc->ejc", d_head, acts[-1][:, :, :feat].float()), 2e-3, "d_head_w")
+        close(grads[:, hb_off:hb_off + n_head], d_head.sum(1), 2e-3, "d_head_b")
