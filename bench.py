@@ -209,6 +209,9 @@ def kernel_profile(algo, batch_np, n_iter=5):
     algo.update(batch_np)  # warm
     L.start_profile(impl._stream_obj)
     for _ in range(n_iter):
+        # a 3 ms busy-wait kernel first: the host enqueues the whole update behind it, so the per-launch event
+        # durations below are device execution times, not host launch latency
+        L.raw("d3b_spin")(3_000_000, impl._stream)
         algo.update(batch_np)
     recs = L.stop_profile()
     impl.use_graph = saved

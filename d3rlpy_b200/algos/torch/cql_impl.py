@@ -231,6 +231,88 @@ class CQLImpl(DDPGBaseImpl):
             allreduce_sum(scalar.buf[4:5], self._stream_obj)
             allreduce_sum(self._slots[metric_slot:metric_slot + 1], self._stream_obj)
 
+    # ------------------------------------------------------------------ single-GPU tensor-core program
+    fused_glue = True  # collapse the glue between the GEMM launches (csrc/cql_fused.cu); False = generic path
+
+    def _program_fused(self, db, do_temp, do_alpha):
+        """The same update as `program` in update_fused_async with ~half the launches: one row-assembly
+        kernel, the alpha-step and critic-step critic forwards in ONE launch, loss + scalar tails fused."""
+        import ctypes
+
+        B, O, A, N, E = db.B, db.O, self._action_size, self._n_action_samples, self._n_critics
+        L, st = self._lib, self._stream
+        bf = torch.bfloat16
+        R = B * (1 + 3 * N)
+        G = 2 if do_alpha else 1
+        ld = (O + A + 7) // 8 * 8
+        X = self.ws("xf_rows", G * R + 2 * B, ld, dtype=bf)
+        lp = self.ws("xf_lp", 4, B * N)
+        lpm = self.ws("xf_lpm", 3, B)  # soft-backup, actor, temp log-probs
+        done = self.ws("xf_done", 4, dtype=torch.int32)
+        inv_b = 1.0 / B
+        mask = 0
+        for c in [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else []):
+            mask |= 1 << c
+        L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
+        self.fill_noise(B)
+        acts_p, head = self._p_policy(db)
+        nv = lambda name: self.noise_view(name, B).data_ptr()
+        soft = self._soft_q_backup
+        ptrs = [nv("critic_t"), nv("critic_tp1"), nv("critic_rand"), lp[0].data_ptr(), lp[1].data_ptr()]
+        ptrs += [nv("alpha_t"), nv("alpha_tp1"), nv("alpha_rand"), lp[2].data_ptr(), lp[3].data_ptr()] if do_alpha \
+            else [None] * 5
+        ptrs += [nv("soft") if soft else None, lpm[0].data_ptr() if soft else None, nv("actor"), lpm[1].data_ptr(),
+                 nv("temp") if do_temp else None, lpm[2].data_ptr() if do_temp else None]
+        t_row0, a_row0 = G * R, G * R + B
+        L.cql_rows(head.data_ptr(), db.ptr("obs"), db.ptr("next_obs"), db.ptr("act"), B, N, O, A, MIN_LOGSTD,
+                   MAX_LOGSTD, X.data_ptr(), ld, G, (ctypes.c_void_p * 16)(*ptrs),
+                   (ctypes.c_int64 * 4)(0, R, t_row0, a_row0), st)
+        la, lt = self._log_alpha, self._log_temp
+        if do_temp:
+            L.sac_temp_step(lpm[2].data_ptr(), lt.buf.data_ptr(), self.counter_ptr(C_TEMP), B, A, inv_b,
+                            self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS), self.metric_ptr(M_TEMP), st)
+        # critic-step rows [0,R) (activations saved) and alpha-step rows [R,2R) (forward only): one launch
+        q_net = self._q_func
+        ctx = q_net.ctx("is2", G * R, E, True)
+        q = self.ws("is2_q", E, G * R)
+        q_net.forward("params", None, 0, G * R, ctx, q, st, x_bf16=(X.data_ptr(), ld), save_rows=R)
+        if do_alpha:
+            L.cql_loss_step(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma,
+                            lp[2].data_ptr(), lp[3].data_ptr(), N, A, la.buf.data_ptr(), self._conservative_weight,
+                            self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done.data_ptr(), B, E, inv_b, 1,
+                            self.counter_ptr(C_ALPHA), self._alpha_learning_rate, self.metric_ptr(M_ALPHA_LOSS),
+                            self.metric_ptr(M_ALPHA), st)
+        ctx_t = q_net.ctx("tq", B, E, False)
+        q_t = self.ws("tq_q", E, B)
+        q_net.forward("target", None, 0, B, ctx_t, q_t, st, x_bf16=(X.data_ptr() + 2 * t_row0 * ld, ld))
+        q_tpn = None
+        if soft:
+            q_tpn = self.ws("soft_tpn", B)
+            L.sac_soft_backup(q_t.data_ptr(), B, E, lpm[0].data_ptr(), lt.ptr("p"), q_tpn.data_ptr(), B, st)
+        dq = self.ws("is2_dq", E, R)
+        L.cql_loss_step(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
+                        q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
+                        self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.buf.data_ptr(),
+                        self._conservative_weight, self._alpha_threshold, dq.data_ptr(), R, self.sums_ptr(S_CRITIC),
+                        done.data_ptr() + 4, B, E, inv_b, 0, None, 0.0, self.metric_ptr(M_CRITIC), None, st)
+        q_net.backward(None, 0, R, ctx, dq, st)
+        q_net.adam(self._critic_learning_rate, st, tau=self._tau)
+        # actor step on the updated critics
+        ctx_a = q_net.ctx("aq", B, E, True)
+        qa = self.ws("aq_q", E, B)
+        q_net.forward("params", None, 0, B, ctx_a, qa, st, x_bf16=(X.data_ptr() + 2 * a_row0 * ld, ld))
+        dqa = self.ws("a_dq", E, B)
+        L.sac_actor_step(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B, self.sums_ptr(S_ACTOR),
+                         done.data_ptr() + 8, self.metric_ptr(M_ACTOR), B, E, inv_b, st)
+        dxa = self.ws("a_dx", E, B, A)
+        q_net.backward(None, 0, B, ctx_a, dqa, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
+                       dx_cols=A)
+        dhead = self.ws("pi_dhead", 1, B, 2 * A)
+        L.sac_actor_backward(head.data_ptr(), 2 * A, nv("actor"), dxa.data_ptr(), A, B * A, E, lt.ptr("p"),
+                             dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
+        self._policy_backward_rows(db, acts_p, dhead, B)
+        self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
+
     # ------------------------------------------------------------------ fused update (CQL._update, cql.py:234-258)
     def update_fused(self, batch):
         names = self.update_fused_async(batch)
@@ -255,7 +337,10 @@ class CQLImpl(DDPGBaseImpl):
             self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn)
             self._p_actor(db, acts_p, head)
 
-        self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected), program)
+        fused = (self._precision == "bf16" and self.world_size == 1 and self._q_func.fused_ok
+                 and self._policy.fused_ok and self.fused_glue)
+        self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected, fused),
+                         (lambda: self._program_fused(db, do_temp, do_alpha)) if fused else program)
         names = []
         if do_temp:
             names += [(M_TEMP_LOSS, "temp_loss"), (M_TEMP, "temp")]

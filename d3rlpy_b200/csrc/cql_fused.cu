@@ -1,0 +1,409 @@
+// CQL/SAC update, fused "glue" kernels: at batch 256 the update is launch-latency bound, so everything that
+// sits between the tensor-core launches is collapsed into a handful of kernels:
+//   begin_step      : Adam/noise counters += mask, loss partial sums zeroed            (was tick + memset)
+//   cql_rows        : every row the critics see in one update — [data | pi(s_t) | pi(s_t+1) | random] for the
+//                     critic step and for the alpha step, the target row tanh(mu(s')) (or a sampled one for
+//                     soft_q_backup) and the actor row — written as bf16 straight into the GEMM operand, with
+//                     all tanh-Gaussian log-probs (cql_impl.py:143-204, policies.py:167-249,
+//                     distributions.py:91-143).                                       (was 15 launches)
+//   sac_temp_step   : update_temp loss + d/dlog_temp + Adam (sac_impl.py:123-146)      (was 2)
+//   cql_loss_step   : IS-logsumexp conservative term + TD term + softmax gradient seed, then — by the last block
+//                     to finish — the scalar tail: critic metric, or alpha loss + d/dlog_alpha + Adam
+//                     (cql_impl.py:110-141,196-223)                                    (was 2-3)
+//   sac_actor_step  : actor loss + arg-min routing of dQ + metric                      (was 2)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace d3b {
+
+__device__ __forceinline__ float clampf3(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float softplusf3(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+__global__ void begin_step_kernel(int* counters, int n, unsigned mask, float* slots, int n_slots) {
+  int i = threadIdx.x;
+  if (i < n && ((mask >> i) & 1u)) counters[i] += 1;
+  for (int j = i; j < n_slots; j += blockDim.x) slots[j] = 0.f;
+}
+
+struct RowsParams {
+  const float* head;      // [2B][2A]: rows 0..B-1 = policy(obs_t), rows B..2B-1 = policy(obs_tp1)
+  const float* obs;       // [B][O]
+  const float* next_obs;  // [B][O]
+  const float* act;       // [B][A]
+  int B, N, O, A;
+  float min_logstd, max_logstd;
+  __nv_bfloat16* X;       // [rows_total][ldx]
+  long long ldx;
+  // per IS group g (0 = critic step, 1 = alpha step): noise and log-prob outputs
+  const float* eps_t[2];      // [N][B][A]
+  const float* eps_tp1[2];    // [N][B][A]
+  const float* rand_act[2];   // [B*N][A] uniform(-1,1)
+  float* logp_t[2];           // [B*N]
+  float* logp_tp1[2];         // [B*N]
+  int n_groups;
+  long long group_row0[2];    // first row of each group in X
+  long long target_row0;      // B rows [next_obs | a'] ; a' = tanh(mu) or a sample (soft backup)
+  const float* eps_soft;      // null = deterministic backup
+  float* logp_soft;
+  long long actor_row0;       // B rows [obs | a]
+  const float* eps_actor;
+  float* logp_actor;
+  const float* eps_temp;      // update_temp sample: log-prob only
+  float* logp_temp;
+};
+
+// tanh-Gaussian sample + log-prob for the lanes of one warp (A <= 32 per pass); returns this lane's partial logp
+__device__ __forceinline__ float sample_action(const float* __restrict__ head_row, int A, int j, float e,
+                                               float min_ls, float max_ls, float& a_out) {
+  float mu = __ldg(head_row + j);
+  float ls = clampf3(__ldg(head_row + A + j), min_ls, max_ls);
+  float sd = expf(ls);
+  float u = mu + e * sd;
+  a_out = tanhf(u);
+  float d = u - mu;
+  float nlp = -(d * d) / (2.f * sd * sd) - ls - 0.91893853320467267f;
+  float jac = 2.f * (0.69314718055994529f - u - softplusf3(-2.f * u));
+  return nlp - jac;
+}
+
+// one warp per work item; items: per group R = B(1+3N) rows, then B target rows, B actor rows, B temp items
+__global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int B = p.B, N = p.N, O = p.O, A = p.A;
+  const long long BN = (long long)B * N;
+  const long long R = (long long)B + 3 * BN;
+  const long long n_is = R * p.n_groups;
+  const float* obs_row;
+  __nv_bfloat16* x = nullptr;
+  // decode
+  int kind;         // 0 data, 1 pi(s_t), 2 pi(s_tp1), 3 random, 4 target, 5 actor, 6 temp
+  int b, k = 0, g = 0;
+  if (item < n_is) {
+    g = (int)(item / R);
+    long long r = item - (long long)g * R;
+    if (r < B) { kind = 0; b = (int)r; }
+    else {
+      r -= B;
+      kind = 1 + (int)(r / BN);
+      r -= (long long)(kind - 1) * BN;
+      b = (int)(r / N);
+      k = (int)(r % N);
+    }
+    x = p.X + (p.group_row0[g] + (item - (long long)g * R)) * p.ldx;
+    obs_row = p.obs + (long long)b * O;
+  } else {
+    long long r = item - n_is;
+    if (r < B) { kind = 4; b = (int)r; x = p.X + (p.target_row0 + b) * p.ldx; obs_row = p.next_obs + (long long)b * O; }
+    else if (r < 2LL * B) { kind = 5; b = (int)(r - B); x = p.X + (p.actor_row0 + b) * p.ldx; obs_row = p.obs + (long long)b * O; }
+    else if (r < 3LL * B && p.eps_temp) { kind = 6; b = (int)(r - 2LL * B); obs_row = nullptr; }
+    else return;
+  }
+  if (x) {
+    for (int j = lane; j < O; j += 32) x[j] = __float2bfloat16_rn(__ldg(obs_row + j));
+  }
+  float lp = 0.f;
+  for (int j = lane; j < A; j += 32) {
+    float a = 0.f;
+    switch (kind) {
+      case 0: a = __ldg(p.act + (long long)b * A + j); break;
+      case 1: lp += sample_action(p.head + (long long)b * 2 * A, A, j, __ldg(p.eps_t[g] + ((long long)k * B + b) * A + j),
+                                  p.min_logstd, p.max_logstd, a); break;
+      case 2: lp += sample_action(p.head + (long long)(B + b) * 2 * A, A, j,
+                                  __ldg(p.eps_tp1[g] + ((long long)k * B + b) * A + j), p.min_logstd, p.max_logstd, a);
+              break;
+      case 3: a = __ldg(p.rand_act[g] + ((long long)b * N + k) * A + j); break;
+      case 4:
+        if (p.eps_soft) lp += sample_action(p.head + (long long)(B + b) * 2 * A, A, j,
+                                            __ldg(p.eps_soft + (long long)b * A + j), p.min_logstd, p.max_logstd, a);
+        else a = tanhf(__ldg(p.head + (long long)(B + b) * 2 * A + j));
+        break;
+      case 5: lp += sample_action(p.head + (long long)b * 2 * A, A, j, __ldg(p.eps_actor + (long long)b * A + j),
+                                  p.min_logstd, p.max_logstd, a); break;
+      default: lp += sample_action(p.head + (long long)b * 2 * A, A, j, __ldg(p.eps_temp + (long long)b * A + j),
+                                   p.min_logstd, p.max_logstd, a); break;
+    }
+    if (x) x[O + j] = __float2bfloat16_rn(a);
+  }
+  if (kind == 1 || kind == 2 || kind >= 4) {
+    lp = warp_sum(lp);
+    if (lane == 0) {
+      if (kind == 1) p.logp_t[g][(long long)b * N + k] = lp;
+      else if (kind == 2) p.logp_tp1[g][(long long)b * N + k] = lp;
+      else if (kind == 4) { if (p.logp_soft) p.logp_soft[b] = lp; }
+      else if (kind == 5) p.logp_actor[b] = lp;
+      else p.logp_temp[b] = lp;
+    }
+  }
+}
+
+// exact restatement of torch.optim.Adam's single-tensor step for a scalar
+__device__ __forceinline__ float scalar_adam_update(float* p, float G, float* m, float* v, int t, double lr, double b1,
+                                                    double b2, double eps) {
+  double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2);
+  float M = *m, V = *v;
+  M = __fmaf_rn(w1, __fsub_rn(G, M), M);
+  V = __fmul_rn(V, fb2);
+  V = __fadd_rn(V, __fmul_rn(__fmul_rn(w2, G), G));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V), (float)sqrt(bc2)), (float)eps);
+  float P = __fadd_rn(*p, __fdiv_rn(__fmul_rn((float)(-(lr / bc1)), M), denom));
+  *p = P;
+  *m = M;
+  *v = V;
+  return P;
+}
+
+// update_temp: loss = -(exp(log_temp) (logp - A)).mean(); grad == loss; Adam; metrics {loss, exp(new log_temp)}
+__global__ void __launch_bounds__(1024) sac_temp_step_kernel(const float* __restrict__ logp, float* scalar /*p,g,m,v at stride 4*/,
+                                                             const int* step, int B, int A, float inv_b, double lr,
+                                                             float* metric_loss, float* metric_exp) {
+  float s = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) s += __ldg(logp + b) - (float)A;
+  s = block_sum(s);
+  if (threadIdx.x == 0) {
+    float l = -expf(scalar[0]) * s * inv_b;
+    *metric_loss = l;
+    float P = scalar_adam_update(scalar + 0, l, scalar + 8, scalar + 12, *step, lr, 0.9, 0.999, 1e-8);
+    scalar[4] = 0.f;
+    *metric_exp = expf(P);
+  }
+}
+
+struct LossParams {
+  const float* q; long long sQ;            // [E][R] rows: data B | pi_t BN | pi_tp1 BN | random BN
+  const float* q_targ; long long sQt; int Et;   // target critics on the target rows [Et][B] (min inside), or
+  const float* q_tpn;                      // a ready target [B] (soft backup / injected), or both null (no TD)
+  const float* rew; const float* term; const float* nsteps; float gamma;
+  const float* logp_t; const float* logp_tp1; int N, A;
+  float* scalar_alpha;                     // log_alpha {p,g,m,v} at float stride 4
+  float cw, threshold;
+  float* dq; long long sDq;                // gradient seed [E][R] (critic mode) or null
+  float* sums;                             // 3 partial sums
+  unsigned* done;                          // block completion counter (self-resetting)
+  int B, E; float inv_b, inv_eb;
+  int mode;                                // 0 critic loss metric; 1 alpha loss + Adam on log_alpha
+  const int* step_alpha; double lr_alpha;
+  float* metric; float* metric_exp;
+};
+
+__global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
+  const int B = p.B, E = p.E, N = p.N;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float td = 0.f, lse_v = 0.f, data_v = 0.f;
+  const bool td_enabled = p.mode == 0 && (p.q_targ || p.q_tpn);
+  if (idx < B * E) {
+    int e = idx / B, b = idx % B;
+    const float* qe = p.q + (long long)e * p.sQ;
+    float* dqe = p.dq ? p.dq + (long long)e * p.sDq : nullptr;
+    float qd = __ldg(qe + b);
+    float g = 0.f;
+    if (td_enabled) {
+      float tq;
+      if (p.q_tpn) tq = __ldg(p.q_tpn + b);
+      else {
+        tq = __ldg(p.q_targ + b);
+        for (int i = 1; i < p.Et; ++i) tq = fminf(tq, __ldg(p.q_targ + (long long)i * p.sQt + b));
+      }
+      float n = __ldg(p.nsteps + b);
+      float gp = n == 1.f ? p.gamma : powf(p.gamma, n);
+      float y = __ldg(p.rew + b) + gp * tq * (1.f - __ldg(p.term + b));
+      float d = qd - y;
+      td = d * d;
+      g = 2.f * p.inv_b * d;
+    }
+    float ca = clampf3(expf(p.scalar_alpha[0]), 0.f, 1e6f);
+    float c = ca * p.cw * p.inv_eb;
+    float rand_lp = (float)p.A * -0.69314718055994529f;
+    const float* q1 = qe + B + (long long)b * N;
+    const float* q2 = q1 + (long long)B * N;
+    const float* q3 = q2 + (long long)B * N;
+    const float* l1 = p.logp_t + (long long)b * N;
+    const float* l2 = p.logp_tp1 + (long long)b * N;
+    float mx = -INFINITY;
+    for (int k = 0; k < N; ++k) {
+      mx = fmaxf(mx, __ldg(q1 + k) - __ldg(l1 + k));
+      mx = fmaxf(mx, __ldg(q2 + k) - __ldg(l2 + k));
+      mx = fmaxf(mx, __ldg(q3 + k) - rand_lp);
+    }
+    float s = 0.f;
+    for (int k = 0; k < N; ++k) {
+      s += expf(__ldg(q1 + k) - __ldg(l1 + k) - mx);
+      s += expf(__ldg(q2 + k) - __ldg(l2 + k) - mx);
+      s += expf(__ldg(q3 + k) - rand_lp - mx);
+    }
+    lse_v = mx + logf(s);
+    data_v = qd;
+    g -= c;
+    if (dqe) {
+      float inv_s = c / s;
+      float* d1 = dqe + B + (long long)b * N;
+      float* d2 = d1 + (long long)B * N;
+      float* d3 = d2 + (long long)B * N;
+      for (int k = 0; k < N; ++k) {
+        d1[k] = expf(__ldg(q1 + k) - __ldg(l1 + k) - mx) * inv_s;
+        d2[k] = expf(__ldg(q2 + k) - __ldg(l2 + k) - mx) * inv_s;
+        d3[k] = expf(__ldg(q3 + k) - rand_lp - mx) * inv_s;
+      }
+      dqe[b] = g;
+    }
+  }
+  td = block_sum(td);
+  if (threadIdx.x == 0 && td_enabled) atomicAdd(p.sums + 0, td);
+  lse_v = block_sum(lse_v);
+  if (threadIdx.x == 0) atomicAdd(p.sums + 1, lse_v);
+  data_v = block_sum(data_v);
+  __shared__ bool is_last;
+  if (threadIdx.x == 0) {
+    atomicAdd(p.sums + 2, data_v);
+    __threadfence();
+    unsigned prev = atomicAdd(p.done, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  // ---- scalar tail, executed once by the last block to finish (cql_impl.py:217-223, 119-141)
+  __threadfence();
+  volatile float* sv = p.sums;
+  float tdm = sv[0] * p.inv_b;
+  float ea = expf(p.scalar_alpha[0]);
+  float ca = clampf3(ea, 0.f, 1e6f);
+  float scaled = p.cw * (sv[1] * p.inv_eb - sv[2] * p.inv_eb);
+  float cons = ca * (scaled - p.threshold);
+  if (p.mode == 0) {
+    *p.metric = tdm + cons;
+  } else {
+    *p.metric = -cons;
+    float inside = (ea >= 0.f && ea <= 1e6f) ? 1.f : 0.f;
+    float G = -inside * ea * (scaled - p.threshold);
+    float P = scalar_adam_update(p.scalar_alpha + 0, G, p.scalar_alpha + 8, p.scalar_alpha + 12, *p.step_alpha,
+                                 p.lr_alpha, 0.9, 0.999, 1e-8);
+    p.scalar_alpha[4] = 0.f;
+    *p.metric_exp = expf(P);
+  }
+  *p.done = 0u;
+}
+
+// SAC actor loss (sac_impl.py:114-121): mean_b(exp(log_temp) logp_b - min_e Q_e); dQ to the arg-min member.
+__global__ void __launch_bounds__(256) sac_actor_step_kernel(const float* __restrict__ q, long long sQ,
+                                                             const float* __restrict__ logp,
+                                                             const float* __restrict__ log_temp,
+                                                             float* __restrict__ dq, long long sDq,
+                                                             float* __restrict__ loss_sum, unsigned* done,
+                                                             float* metric, int B, int E, float inv_b) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (b < B) {
+    float qm = __ldg(q + b);
+    int arg = 0;
+    for (int e = 1; e < E; ++e) {
+      float v = __ldg(q + (long long)e * sQ + b);
+      if (v < qm) { qm = v; arg = e; }
+    }
+    for (int e = 0; e < E; ++e) dq[(long long)e * sDq + b] = (e == arg) ? -inv_b : 0.f;
+    l = (expf(__ldg(log_temp)) * __ldg(logp + b) - qm) * inv_b;
+  }
+  l = block_sum(l);
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, l);
+    __threadfence();
+    unsigned prev = atomicAdd(done, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence();
+      *metric = *(volatile float*)loss_sum;
+      *done = 0u;
+    }
+  }
+}
+
+}  // namespace d3b
+
+using namespace d3b;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int d3b_begin_step(int* counters, int n, unsigned mask, float* slots, int n_slots, void* stream) {
+  D3B_REQUIRE(counters && n >= 0 && n <= 32 && slots && n_slots >= 0, "begin_step: bad arguments");
+  begin_step_kernel<<<1, 64, 0, ST>>>(counters, n, mask, slots, n_slots);
+  return check_launch("begin_step");
+}
+
+// ptrs_host: 16 device pointers in the order
+//   {eps_t[0], eps_tp1[0], rand[0], logp_t[0], logp_tp1[0], eps_t[1], eps_tp1[1], rand[1], logp_t[1], logp_tp1[1],
+//    eps_soft, logp_soft, eps_actor, logp_actor, eps_temp, logp_temp}
+// rows_host: {group_row0[0], group_row0[1], target_row0, actor_row0}
+extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+                            int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd,
+                            void* x_bf16, int64_t ldx, int n_groups, const void* const* ptrs_host,
+                            const int64_t* rows_host, void* stream) {
+  D3B_REQUIRE(batch >= 0 && n_action_samples >= 1 && obs_dim >= 1 && act_dim >= 1, "cql_rows: bad sizes");
+  D3B_REQUIRE(n_groups >= 1 && n_groups <= 2, "cql_rows: n_groups must be 1 or 2");
+  if (batch == 0) return D3B_OK;
+  D3B_REQUIRE(head && obs && next_obs && act && x_bf16 && ptrs_host && rows_host, "cql_rows: null pointer");
+  RowsParams p{};
+  p.head = head; p.obs = obs; p.next_obs = next_obs; p.act = act;
+  p.B = batch; p.N = n_action_samples; p.O = obs_dim; p.A = act_dim;
+  p.min_logstd = min_logstd; p.max_logstd = max_logstd;
+  p.X = (__nv_bfloat16*)x_bf16; p.ldx = ldx; p.n_groups = n_groups;
+  for (int g = 0; g < 2; ++g) {
+    p.eps_t[g] = (const float*)ptrs_host[5 * g + 0];
+    p.eps_tp1[g] = (const float*)ptrs_host[5 * g + 1];
+    p.rand_act[g] = (const float*)ptrs_host[5 * g + 2];
+    p.logp_t[g] = (float*)ptrs_host[5 * g + 3];
+    p.logp_tp1[g] = (float*)ptrs_host[5 * g + 4];
+    p.group_row0[g] = rows_host[g];
+    if (g < n_groups)
+      D3B_REQUIRE(p.eps_t[g] && p.eps_tp1[g] && p.rand_act[g] && p.logp_t[g] && p.logp_tp1[g], "cql_rows: null group pointer");
+  }
+  p.eps_soft = (const float*)ptrs_host[10]; p.logp_soft = (float*)ptrs_host[11];
+  p.eps_actor = (const float*)ptrs_host[12]; p.logp_actor = (float*)ptrs_host[13];
+  p.eps_temp = (const float*)ptrs_host[14]; p.logp_temp = (float*)ptrs_host[15];
+  D3B_REQUIRE(p.eps_actor && p.logp_actor, "cql_rows: null actor pointers");
+  D3B_REQUIRE(!p.eps_temp || p.logp_temp, "cql_rows: null temp log-prob pointer");
+  D3B_REQUIRE(!p.eps_soft || p.logp_soft, "cql_rows: null soft-backup log-prob pointer");
+  p.target_row0 = rows_host[2]; p.actor_row0 = rows_host[3];
+  long long items = ((long long)batch + 3LL * batch * n_action_samples) * n_groups + 3LL * batch;
+  cql_rows_kernel<<<(unsigned)ceil_div_ll(items, 8), 256, 0, ST>>>(p);
+  return check_launch("cql_rows");
+}
+
+extern "C" int d3b_sac_temp_step(const float* logp, float* scalar, const int* step, int batch, int act_dim,
+                                 float inv_batch, double lr, float* metric_loss, float* metric_exp, void* stream) {
+  D3B_REQUIRE(logp && scalar && step && metric_loss && metric_exp && batch >= 1, "sac_temp_step: bad arguments");
+  sac_temp_step_kernel<<<1, 1024, 0, ST>>>(logp, scalar, step, batch, act_dim, inv_batch, lr, metric_loss, metric_exp);
+  return check_launch("sac_temp_step");
+}
+
+extern "C" int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* q_targ, int64_t stride_qt,
+                                 int targ_members, const float* q_tpn, const float* rewards, const float* terminals,
+                                 const float* n_steps, float gamma, const float* logp_t, const float* logp_tp1,
+                                 int n_action_samples, int act_dim, float* scalar_alpha, float conservative_weight,
+                                 float alpha_threshold, float* dq, int64_t stride_dq, float* sums, void* done_counter,
+                                 int batch, int members, float inv_batch, int mode, const int* step_alpha,
+                                 double lr_alpha, float* metric, float* metric_exp, void* stream) {
+  D3B_REQUIRE(batch >= 1 && members >= 1 && n_action_samples >= 1, "cql_loss_step: bad sizes");
+  D3B_REQUIRE(q && logp_t && logp_tp1 && scalar_alpha && sums && done_counter && metric, "cql_loss_step: null pointer");
+  D3B_REQUIRE(mode == 0 || (step_alpha && metric_exp), "cql_loss_step: alpha mode needs the step counter / metric slot");
+  D3B_REQUIRE(!(q_targ || q_tpn) || (rewards && terminals && n_steps), "cql_loss_step: TD term needs the minibatch");
+  LossParams p{};
+  p.q = q; p.sQ = stride_q; p.q_targ = q_targ; p.sQt = stride_qt; p.Et = targ_members; p.q_tpn = q_tpn;
+  p.rew = rewards; p.term = terminals; p.nsteps = n_steps; p.gamma = gamma;
+  p.logp_t = logp_t; p.logp_tp1 = logp_tp1; p.N = n_action_samples; p.A = act_dim;
+  p.scalar_alpha = scalar_alpha; p.cw = conservative_weight; p.threshold = alpha_threshold;
+  p.dq = dq; p.sDq = stride_dq; p.sums = sums; p.done = (unsigned*)done_counter;
+  p.B = batch; p.E = members; p.inv_b = inv_batch; p.inv_eb = inv_batch / (float)members;
+  p.mode = mode; p.step_alpha = step_alpha; p.lr_alpha = lr_alpha; p.metric = metric; p.metric_exp = metric_exp;
+  cql_loss_step_kernel<<<ceil_div(batch * members, 256), 256, 0, ST>>>(p);
+  return check_launch("cql_loss_step");
+}
+
+extern "C" int d3b_sac_actor_step(const float* q, int64_t stride_q, const float* logp, const float* log_temp,
+                                  float* dq, int64_t stride_dq, float* loss_sum, void* done_counter, float* metric,
+                                  int batch, int members, float inv_batch, void* stream) {
+  D3B_REQUIRE(batch >= 1 && members >= 1, "sac_actor_step: bad sizes");
+  D3B_REQUIRE(q && logp && log_temp && dq && loss_sum && done_counter && metric, "sac_actor_step: null pointer");
+  sac_actor_step_kernel<<<ceil_div(batch, 256), 256, 0, ST>>>(q, stride_q, logp, log_temp, dq, stride_dq, loss_sum,
+                                                             (unsigned*)done_counter, metric, batch, members,
+                                                             inv_batch);
+  return check_launch("sac_actor_step");
+}

@@ -42,6 +42,7 @@ struct FwdParams {
   const float* bias[MAX_LAYERS];
   long long bias_stride;
   int x_shared, save_mask;
+  int save_rows;  // activations are stored only for tiles starting below this row (rows: all)
   const float* head_w;
   const float* head_b;
   long long head_stride;
@@ -245,10 +246,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
         if (NH > 0 && p.n_head > 0) {
           const int feat = p.N[L - 1];
           const float* hw = p.head_w + (long long)e * p.head_stride;
-          for (int i = t; i < NH * MAXW; i += EPI_THREADS) {
-            int j = i / MAXW, c = i % MAXW;
-            head_w_s[i] = (j < p.n_head && c < feat) ? __ldg(hw + (long long)j * feat + c) : 0.f;
-          }
+          // NH x 256 staging: all loads of a thread are issued before the stores (NH global loads in flight)
+          float tmp[NH > 0 ? NH : 1];
+#pragma unroll
+          for (int j = 0; j < NH; ++j) tmp[j] = (j < p.n_head && t < feat) ? __ldg(hw + (long long)j * feat + t) : 0.f;
+#pragma unroll
+          for (int j = 0; j < NH; ++j) head_w_s[j * MAXW + t] = tmp[j];
         }
         epi_sync();
         cur_member = e;
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
       for (int l = 0; l < L; ++l, ++g) {
         const uint32_t buf = g & 1;
         const bool last = (l == L - 1);
-        const bool store = (p.save_mask >> l) & 1;
+        const bool store = ((p.save_mask >> l) & 1) && m0 < p.save_rows;
         const bool writeA = !last || store;
         const int N = p.N[l];
         mbar_wait(bars + B_ACCFULL + buf, (g >> 1) & 1);
@@ -523,10 +526,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
       if (e != cur_member) {
         epi_sync();
         const float* hw = p.head_w + (long long)e * p.head_stride;
-        for (int i = t; i < NH * MAXW; i += EPI_THREADS) {
-          int j = i / MAXW, c = i % MAXW;
-          head_w_s[i] = (j < p.n_head && c < feat) ? __ldg(hw + (long long)j * feat + c) : 0.f;
-        }
+        float tmp[NH];
+#pragma unroll
+        for (int j = 0; j < NH; ++j) tmp[j] = (j < p.n_head && t < feat) ? __ldg(hw + (long long)j * feat + t) : 0.f;
+#pragma unroll
+        for (int j = 0; j < NH; ++j) head_w_s[j * MAXW + t] = tmp[j];
         cur_member = e;
       }
       // d_head row -> registers (+ shared copy for the column passes)
@@ -754,7 +758,8 @@ extern "C" int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x
                                     int64_t stride_w, const float* const* bias_host, int64_t stride_bias,
                                     void* const* acts_host, const int64_t* ld_act_host,
                                     const int64_t* stride_act_host, const float* head_w, const float* head_b,
-                                    int64_t stride_head, int n_head, int head_tanh, float* head_out, void* stream) {
+                                    int64_t stride_head, int n_head, int head_tanh, float* head_out, int save_rows,
+                                    void* stream) {
   D3B_REQUIRE(rows >= 0 && members >= 1 && n_layers >= 1 && n_layers <= MAX_LAYERS, "mlp_forward_bf16: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && dims_host && w_host && ldw_host && bias_host, "mlp_forward_bf16: null pointer");
@@ -767,6 +772,7 @@ extern "C" int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x
   p.bias_stride = stride_bias;
   p.head_w = head_w; p.head_b = head_b; p.head_stride = stride_head; p.n_head = n_head; p.head_tanh = head_tanh;
   p.head_out = head_out;
+  p.save_rows = (save_rows > 0 && save_rows < rows) ? save_rows : rows;
   int k = dims_host[0];
   D3B_REQUIRE(k >= 1 && k <= MAXW, "mlp_forward_bf16: input width must be in [1,256]");
   int rc = make_map(&maps.x, x, k, rows, p.x_shared ? 1 : members, ldx, stride_x, BM, "x");

@@ -75,6 +75,24 @@ extern "C" int d3b_stream_sync(void* stream) {
   return D3B_OK;
 }
 
+namespace {
+__global__ void spin_kernel(long long ns) {
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while ((long long)(t1 - t0) < ns);
+}
+}  // namespace
+
+// measurement helper: keeps the stream busy for `ns` so that the host can enqueue a whole update behind it and
+// per-kernel CUDA-event durations are not inflated by launch starvation (bench.py kernel_profile)
+extern "C" int d3b_spin(int64_t ns, void* stream) {
+  D3B_REQUIRE(ns >= 0 && ns <= 50000000, "spin: ns out of range");
+  spin_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long)ns);
+  return check_launch("spin");
+}
+
 extern "C" int d3b_graph_begin(void* stream) {
   D3B_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
   return D3B_OK;

@@ -172,7 +172,7 @@ class DenseNet:
 
     # ------------------------------------------------------------------ forward
     def forward(self, which: str, x, ldx: int, rows: int, ctx: Ctx, head_out, stream: int,
-                head_tanh: bool = False, member0: int = 0):
+                head_tanh: bool = False, member0: int = 0, x_bf16=None, save_rows: int = 0):
         """x: fp32 [rows, ldx], shared by all members.  Saves activations in ctx; head_out: fp32
         [E, rows, head_out] (None = trunk only)."""
         L = lib()
@@ -191,8 +191,13 @@ class DenseNet:
                 L.head_forward(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
                                _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
             return
-        # ---- bf16 mode
-        L.to_bf16(_p(x), ldx, rows, self.in_dim, _p(ctx.xb), ctx.ldk0, None, 0, stream)
+        # ---- bf16 mode.  x_bf16 = (device pointer, ld): rows already assembled as bf16 GEMM operands
+        if x_bf16 is not None:
+            ctx.x_src = (int(x_bf16[0]), int(x_bf16[1]))
+        else:
+            L.to_bf16(_p(x), ldx, rows, self.in_dim, _p(ctx.xb), ctx.ldk0, None, 0, stream)
+            ctx.x_src = (_p(ctx.xb), ctx.ldk0)
+        xs, xld = ctx.x_src
         sms = self.shadow_member
         if self.fused_ok:
             # ONE persistent launch: trunk + head for all members, activations chained on-chip
@@ -210,12 +215,12 @@ class DenseNet:
             else:
                 ap, lda, sa = None, None, None
             with_head = head_out is not None
-            L.mlp_forward_bf16(_p(ctx.xb), ctx.ldk0, 0, rows, E, nl, dims, wp, ldw, sms, bp, ms, ap, lda, sa,
+            L.mlp_forward_bf16(xs, xld, 0, rows, E, nl, dims, wp, ldw, sms, bp, ms, ap, lda, sa,
                                self._hw(which, member0) if with_head else None,
                                self._hb(which, member0) if with_head else None, ms, n if with_head else 0,
-                               1 if head_tanh else 0, _p(head_out) if with_head else None, stream)
+                               1 if head_tanh else 0, _p(head_out) if with_head else None, save_rows, stream)
             return
-        cur, ld, sx = _p(ctx.xb), ctx.ldk0, 0
+        cur, ld, sx = xs, xld, 0
         d = self.in_dim
         for i, h in enumerate(self.hidden):
             wptr, ldw = self._sw(which, i, member0)
@@ -302,7 +307,7 @@ class DenseNet:
                         prev = ctx.hb[i - 1]
                         bsrc, ldb, sb = _p(prev), prev.shape[2], prev.shape[1] * prev.shape[2]
                     else:
-                        bsrc, ldb, sb = _p(ctx.xb), ctx.ldk0, 0
+                        bsrc, ldb, sb = ctx.x_src[0], ctx.x_src[1], 0
                     tiles = -(-h // 128) * -(-d_in // 256) * E
                     splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
                     L.umma_gemm_tn(_p(dz), dz.shape[2], dz.shape[1] * dz.shape[2], bsrc, ldb, sb, h, d_in, rows, E,
@@ -326,7 +331,7 @@ class DenseNet:
                 if i > 0:
                     bsrc, ldb, sb = _p(ctx.hb[i - 1]), ldi, rows * ldi
                 else:
-                    bsrc, ldb, sb = _p(ctx.xb), ctx.ldk0, 0
+                    bsrc, ldb, sb = ctx.x_src[0], ctx.x_src[1], 0
                 tiles = -(-h // 128) * -(-d_in // 256) * E
                 splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
                 L.umma_gemm_tn(_p(dcur), lh, rows * lh, bsrc, ldb, sb, h, d_in, rows, E, splits,

@@ -107,14 +107,15 @@ int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, const void* b
  * (activations chained through shared memory / TMEM; H_l TMA-stored only when acts_host[l] != NULL).
  * Host arrays: dims_host = {K_0, N_0..N_{L-1}}; w_host/bias_host/acts_host[l] = member-0 pointers of layer l
  * (bf16 K-major weight shadows, fp32 biases, bf16 [members][rows][ld_act] outputs).  Layer widths must be
- * multiples of 16 and <= 256, n_layers <= 4, n_head <= 32 (0 = trunk only).  Replaces encoders.py:265-339 +
+ * multiples of 16 and <= 256, n_layers <= 4, n_head <= 32 (0 = trunk only); save_rows > 0 limits the stored
+ * activations to the first save_rows rows (the rest of the rows are forward-only).  Replaces encoders.py:265-339 +
  * ensemble_q_function.py:141-175 + the `_fc/_mu/_logstd` heads in one call. */
 int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, int rows, int members, int n_layers,
                          const int* dims_host, const void* const* w_host, const int64_t* ldw_host, int64_t stride_w,
                          const float* const* bias_host, int64_t stride_bias, void* const* acts_host,
                          const int64_t* ld_act_host, const int64_t* stride_act_host, const float* head_w,
                          const float* head_b, int64_t stride_head, int n_head, int head_tanh, float* head_out,
-                         void* stream);
+                         int save_rows, void* stream);
 /* mlp_backward_bf16: autograd of mlp_forward_bf16 w.r.t. activations in ONE persistent launch: dZ_{L-1} from
  * d_head and the head weights, then dZ_{l-1} = (dZ_l W_l) * [H_{l-1} > 0] with W_l fed as MN-major tiles, optional
  * dX for input columns [dx_col0, dx_col0+dx_cols).  dbias_host != NULL: also store every dZ_l (operands of the
@@ -188,6 +189,32 @@ int d3b_sac_temp_loss(const float* logp, const float* log_temp, int batch, int a
 /* SACImpl.compute_target, soft backup (sac_impl.py:148-162; CQL soft_q_backup=True, cql_impl.py:225-231) */
 int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int members, const float* logp, const float* log_temp,
                         float* q_tpn, int batch, void* stream);
+/* ---- fused glue kernels of the CQL/SAC update (single-GPU bf16 path; csrc/cql_fused.cu) -------------------
+ * begin_step: counters[i] += 1 for the bits of mask, loss partial sums zeroed.
+ * cql_rows: all critic input rows of one update (critic-step and alpha-step importance-sampling groups
+ *   [data | pi(s_t) | pi(s_t+1) | random], target row, actor row) as bf16 GEMM operands + every tanh-Gaussian
+ *   log-prob (cql_impl.py:143-204, policies.py:167-249, distributions.py:91-143).  ptrs_host / rows_host: see .cu.
+ * sac_temp_step: update_temp loss + gradient + Adam (sac_impl.py:123-146); scalar = {p,g,m,v} at float stride 4.
+ * cql_loss_step: conservative + TD loss and gradient seed, then the scalar tail by the last block: mode 0 critic
+ *   metric (cql_impl.py:110-117), mode 1 alpha loss + Adam on log_alpha (cql_impl.py:119-141).
+ * sac_actor_step: SACImpl.compute_actor_loss (sac_impl.py:114-121) + gradient seed + metric. */
+int d3b_begin_step(int* counters, int n, unsigned mask, float* slots, int n_slots, void* stream);
+int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+                 int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd, void* x_bf16,
+                 int64_t ldx, int n_groups, const void* const* ptrs_host, const int64_t* rows_host, void* stream);
+int d3b_sac_temp_step(const float* logp, float* scalar, const int* step, int batch, int act_dim, float inv_batch,
+                      double lr, float* metric_loss, float* metric_exp, void* stream);
+int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* q_targ, int64_t stride_qt, int targ_members,
+                      const float* q_tpn, const float* rewards, const float* terminals, const float* n_steps,
+                      float gamma, const float* logp_t, const float* logp_tp1, int n_action_samples, int act_dim,
+                      float* scalar_alpha, float conservative_weight, float alpha_threshold, float* dq,
+                      int64_t stride_dq, float* sums, void* done_counter, int batch, int members, float inv_batch,
+                      int mode, const int* step_alpha, double lr_alpha, float* metric, float* metric_exp,
+                      void* stream);
+int d3b_sac_actor_step(const float* q, int64_t stride_q, const float* logp, const float* log_temp, float* dq,
+                       int64_t stride_dq, float* loss_sum, void* done_counter, float* metric, int batch, int members,
+                       float inv_batch, void* stream);
+
 /* TD3PlusBCImpl.compute_actor_loss (td3_plus_bc_impl.py:64-70) in three phases so the
  * batch-global lambda can be all-reduced between stats and seed when the batch is sharded. */
 int d3b_td3bc_actor_stats(const float* q0, const float* a, int64_t lda, const float* a_data, int64_t ldd,
@@ -280,6 +307,7 @@ int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream)
 int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream);
 int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
 int d3b_stream_sync(void* stream);
+int d3b_spin(int64_t ns, void* stream); /* measurement helper: busy-wait kernel (keeps the stream ahead of the host) */
 int d3b_graph_begin(void* stream);
 int d3b_graph_end(void* stream, void** graph_exec, int* n_nodes);
 int d3b_graph_launch(void* graph_exec, void* stream);

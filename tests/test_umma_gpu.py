@@ -268,7 +268,7 @@ def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, 
                        arr(ctypes.c_void_p, [a.data_ptr() for a in acts]), arr(ctypes.c_int64, [a.shape[2] for a in acts]),
                        arr(ctypes.c_int64, [a.shape[1] * a.shape[2] for a in acts]),
                        arena.data_ptr() + 4 * hw_off, arena.data_ptr() + 4 * hb_off, ms, n_head, 1 if tanh else 0,
-                       out.data_ptr(), _st())
+                       out.data_ptr(), 0, _st())
     torch.cuda.synchronize()
     h = x[:, :, :in_dim].float().expand(E, rows, in_dim)
     for l, (w, b) in enumerate(zip(ws, bs)):
