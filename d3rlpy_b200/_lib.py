@@ -82,6 +82,8 @@ class Lib:
         if name in self._FLOP_ARGS:
             i = self._FLOP_ARGS[name]
             flops = 2.0 * args[i[0]] * args[i[1]] * args[i[2]] * args[i[3]]
+        elif name == "umma_gemm_tn_batched":  # m[], n[] at 7, 8; k, members at 9, 10
+            flops = 2.0 * args[9] * args[10] * sum(a * b for a, b in zip(list(args[7]), list(args[8])))
         elif name == "mlp_backward_bf16":  # rows, members, n_layers, dims[]; dgrad chain (+ head) (+ dx columns)
             dims = list(args[3])
             mac = sum(a * b for a, b in zip(dims[1:-1], dims[2:])) + dims[-1] * args[16]

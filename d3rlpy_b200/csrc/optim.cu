@@ -7,6 +7,8 @@
 //   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2); denom = sqrt(v)/sqrt(1-b2^t) + eps;
 //   p.addcdiv_(m, denom, value=-lr/(1-b1^t))
 // soft_sync restates d3rlpy/torch_utility.py:27-33 (two separately-rounded steps).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace d3b {
@@ -78,6 +80,79 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     v[i] = V;
     if (zero_grad) g[i] = 0.f;
     if (targ) targ[i] = __fadd_rn(__fmul_rn(targ[i], one_m_tau), __fmul_rn(tau, P));
+  }
+}
+
+
+// Adam (+ Polyak) pass that also refreshes the bf16 K-major weight shadows the tensor-core kernels read
+// (row-major W [N][ld8(K)] per trunk layer, for the params and — when synced — the target arena), so no
+// separate conversion launch is needed after the optimizer step.
+constexpr int MAX_SEG = 8;
+struct ShadowSegs {
+  long long param_off[MAX_SEG];  // fp32 offset inside one member block (multiple of 4)
+  long long count[MAX_SEG];      // rows * cols
+  int cols[MAX_SEG];
+  long long shadow_off[MAX_SEG]; // bf16 offset inside one member's shadow block
+  int ld[MAX_SEG];
+  int n;
+  long long member_size, shadow_member;
+};
+
+__global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ p, float* __restrict__ g,
+                                                          float* __restrict__ m, float* __restrict__ v,
+                                                          float* __restrict__ targ, long long n, const int* step,
+                                                          double lr, double b1, double b2, double eps, float tau,
+                                                          __nv_bfloat16* __restrict__ sh_p,
+                                                          __nv_bfloat16* __restrict__ sh_t, ShadowSegs segs) {
+  float w1, fb2, w2, feps, neg_ss, bc2s;
+  adam_scalars(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  float one_m_tau = (float)(1.0 - (double)tau);
+  long long n4 = n >> 2;  // arenas are padded to multiples of 4 floats per member
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += stride) {
+    float4 P = ((float4*)p)[i], G = ((float4*)g)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+    P.x = adam_one(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.y = adam_one(P.y, G.y, M.y, V.y, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.z = adam_one(P.z, G.z, M.z, V.z, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.w = adam_one(P.w, G.w, M.w, V.w, w1, fb2, w2, feps, neg_ss, bc2s);
+    ((float4*)p)[i] = P;
+    ((float4*)m)[i] = M;
+    ((float4*)v)[i] = V;
+    ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 T = P;
+    if (targ) {
+      T = ((float4*)targ)[i];
+      T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(tau, P.x));
+      T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(tau, P.y));
+      T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(tau, P.z));
+      T.w = __fadd_rn(__fmul_rn(T.w, one_m_tau), __fmul_rn(tau, P.w));
+      ((float4*)targ)[i] = T;
+    }
+    // shadow refresh: the 4 elements belong to one allocation of one member (allocations are 4-aligned)
+    long long e0 = i << 2;
+    long long member = e0 / segs.member_size, off = e0 - member * segs.member_size;
+    int sidx = -1;
+#pragma unroll
+    for (int k = 0; k < MAX_SEG; ++k)
+      if (k < segs.n && off >= segs.param_off[k] && off < segs.param_off[k] + segs.count[k]) sidx = k;
+    if (sidx >= 0) {
+      long long rel = off - segs.param_off[sidx];
+      int cols = segs.cols[sidx], ld = segs.ld[sidx];
+      long long base = member * segs.shadow_member + segs.shadow_off[sidx];
+      const float pv[4] = {P.x, P.y, P.z, P.w}, tv[4] = {T.x, T.y, T.z, T.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        long long r = rel + q;
+        if (r < segs.count[sidx]) {
+          long long row = r / cols;
+          int c = (int)(r - row * cols);
+          long long d = base + row * ld + c;
+          sh_p[d] = __float2bfloat16_rn(pv[q]);
+          if (sh_t && targ) sh_t[d] = __float2bfloat16_rn(tv[q]);
+        }
+      }
+    }
   }
 }
 
@@ -178,6 +253,34 @@ extern "C" int d3b_adam_step(float* params, float* grads, float* exp_avg, float*
   adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
                                                                 lr, beta1, beta2, eps, tau, zero_grad);
   return check_launch("adam_step");
+}
+
+// adam_step + bf16 shadow refresh in one pass.  table_host: n_segments x {param_off, rows, cols, shadow_off, ld}
+// (int64), one entry per trunk weight matrix; shadow_target may be NULL.
+extern "C" int d3b_adam_step_shadow(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target,
+                                    int64_t n, const int* step, double lr, double beta1, double beta2, double eps,
+                                    float tau, void* shadow_params, void* shadow_target, const int64_t* table_host,
+                                    int n_segments, int64_t member_size, int64_t shadow_member, void* stream) {
+  D3B_REQUIRE(n >= 0 && n % 4 == 0 && member_size > 0 && member_size % 4 == 0, "adam_step_shadow: arenas must be padded to 4 floats");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(params && grads && exp_avg && exp_avg_sq && step && shadow_params && table_host,
+              "adam_step_shadow: null pointer");
+  D3B_REQUIRE(n_segments >= 1 && n_segments <= MAX_SEG, "adam_step_shadow: 1..8 shadow segments");
+  D3B_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
+               (uintptr_t)target) % 16 == 0,
+              "adam_step_shadow: arenas must be 16-byte aligned");
+  ShadowSegs segs{};
+  segs.n = n_segments; segs.member_size = member_size; segs.shadow_member = shadow_member;
+  for (int k = 0; k < n_segments; ++k) {
+    const int64_t* t = table_host + 5 * k;
+    D3B_REQUIRE(t[0] % 4 == 0 && t[1] > 0 && t[2] > 0 && t[4] >= t[2], "adam_step_shadow: bad segment");
+    segs.param_off[k] = t[0]; segs.count[k] = t[1] * t[2]; segs.cols[k] = (int)t[2];
+    segs.shadow_off[k] = t[3]; segs.ld[k] = (int)t[4];
+  }
+  adam_shadow_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, exp_avg, exp_avg_sq, target, n, step, lr, beta1, beta2, eps, tau, (__nv_bfloat16*)shadow_params,
+      (__nv_bfloat16*)shadow_target, segs);
+  return check_launch("adam_step_shadow");
 }
 
 extern "C" int d3b_soft_sync(float* target, const float* params, int64_t n, float tau, void* stream) {

@@ -135,8 +135,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 constexpr int EPI_THREADS = 256;
 constexpr int NTHREADS = EPI_THREADS + 64;
 
-__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                           const __grid_constant__ CUtensorMap tmB, Params p) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtensorMap* tmB_p, const Params& p,
+                                          const int bx, const int by, const int bz, const int cta_linear) {
+  const CUtensorMap& tmA = *tmA_p;
+  const CUtensorMap& tmB = *tmB_p;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = (p.mn_major && p.BN < 64 ? 64 : p.BN) * BK * 2;
@@ -150,10 +152,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * MAX_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = p.dbg ? p.dbg + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  long long* dbg = p.dbg ? p.dbg + 8 * cta_linear : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.BN;
-  const int e = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int m0 = bx * BM, n0 = by * p.BN;
+  const int e = bz / p.splits, split = bz % p.splits;
   const int num_kb = (p.K + BK - 1) / BK;
   const int kb_begin = split * p.kb_per_split;
   const int kb_end = min(num_kb, kb_begin + p.kb_per_split);
@@ -447,6 +449,34 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
   }
 }
 
+__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                           const __grid_constant__ CUtensorMap tmB, Params p) {
+  gemm_body(&tmA, &tmB, p, blockIdx.x, blockIdx.y, blockIdx.z,
+            blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+}
+
+// Several independent weight-gradient GEMMs (one per layer of a network) in ONE launch: blockIdx.z enumerates
+// (problem, member, split); CTAs outside a problem's tile range exit immediately.
+constexpr int MAX_BATCH = 4;
+struct BatchMaps {
+  CUtensorMap a[MAX_BATCH];
+  CUtensorMap b[MAX_BATCH];
+};
+struct BatchParams {
+  Params p[MAX_BATCH];
+  int z_begin[MAX_BATCH + 1];
+  int mtiles[MAX_BATCH], ntiles[MAX_BATCH];
+  int n;
+};
+__global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_batched_kernel(const __grid_constant__ BatchMaps maps,
+                                                                   const __grid_constant__ BatchParams bp) {
+  int l = 0;
+  while (l + 1 < bp.n && (int)blockIdx.z >= bp.z_begin[l + 1]) ++l;
+  if ((int)blockIdx.x >= bp.mtiles[l] || (int)blockIdx.y >= bp.ntiles[l]) return;
+  gemm_body(&maps.a[l], &maps.b[l], bp.p[l], blockIdx.x, blockIdx.y, blockIdx.z - bp.z_begin[l],
+            blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z));
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -622,4 +652,71 @@ extern "C" int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, co
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
   umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
   return check_launch("umma_gemm_tn");
+}
+
+// Batched weight-gradient form: problem i computes c_i[e] (m_i x n_i) += a_i[e]^T b_i[e] over k rows (same k and
+// member count for all problems: the layers of one network).  All arrays are host arrays of length n_problems;
+// stride_b_host[i] == 0 marks an operand shared by the members (the network input).
+extern "C" int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const int64_t* lda_host,
+                                        const int64_t* stride_a_host, const void* const* b_host,
+                                        const int64_t* ldb_host, const int64_t* stride_b_host, const int* m_host,
+                                        const int* n_host, int k, int members, float* const* out_host,
+                                        const int64_t* ldf_host, int64_t stride_f, void* stream) {
+  D3B_REQUIRE(n_problems >= 1 && n_problems <= MAX_BATCH && k >= 0 && members >= 1, "umma_gemm_tn_batched: bad sizes");
+  if (k == 0) return D3B_OK;
+  D3B_REQUIRE(a_host && lda_host && stride_a_host && b_host && ldb_host && stride_b_host && m_host && n_host &&
+                  out_host && ldf_host,
+              "umma_gemm_tn_batched: null pointer");
+  static BatchMaps maps;   // host staging (launches are serialised by the caller's stream-ordered use)
+  static BatchParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.n = n_problems;
+  int num_kb = ceil_div(k, BK);
+  int gx = 1, gy = 1, z = 0;
+  size_t smem = 0;
+  // total CTA budget: ~2 CTAs per SM over all problems
+  for (int i = 0; i < n_problems; ++i) {
+    int m = m_host[i], n = n_host[i];
+    D3B_REQUIRE(m > 0 && n > 0 && a_host[i] && b_host[i] && out_host[i], "umma_gemm_tn_batched: bad problem");
+    int BN = n > 64 ? 128 : (n > 32 ? 64 : 32);
+    Params& p = bp.p[i];
+    p.M = m; p.N = n; p.K = k; p.BN = BN; p.mn_major = 1;
+    p.lg_bn = BN == 128 ? 7 : (BN == 64 ? 6 : 5);
+    int tiles = ceil_div(m, BM) * ceil_div(n, BN) * members;
+    int splits = (2 * kNumSM) / (tiles * n_problems);
+    if (splits < 1) splits = 1;
+    if (splits > num_kb) splits = num_kb;
+    p.kb_per_split = ceil_div(num_kb, splits);
+    p.splits = ceil_div(num_kb, p.kb_per_split);
+    p.a_shared = stride_a_host[i] == 0; p.b_shared = stride_b_host[i] == 0;
+    p.out_f32 = out_host[i]; p.ldf = ldf_host[i]; p.sF = stride_f; p.atomic = 1;
+    p.dbg = nullptr;
+    int rc = make_map_mn(&maps.a[i], a_host[i], m, k, p.a_shared ? 1 : members, lda_host[i], stride_a_host[i], "A");
+    if (rc) return rc;
+    rc = make_map_mn(&maps.b[i], b_host[i], n, k, p.b_shared ? 1 : members, ldb_host[i], stride_b_host[i], "B");
+    if (rc) return rc;
+    size_t b_stage = (size_t)(BN < 64 ? 64 : BN) * BK * 2;
+    size_t stage_bytes = (size_t)A_STAGE_BYTES + b_stage;
+    size_t need_epi = (size_t)BM * (BN + 4) * 4;
+    int stages = 3;
+    while ((size_t)stages * stage_bytes < need_epi) ++stages;
+    D3B_REQUIRE(stages <= MAX_STAGES, "umma_gemm_tn_batched: tile does not fit shared memory");
+    p.stages = stages;
+    size_t need = 1024 + stages * stage_bytes + 256 + 1024;
+    if (need > smem) smem = need;
+    bp.mtiles[i] = ceil_div(m, BM); bp.ntiles[i] = ceil_div(n, BN);
+    if (bp.mtiles[i] > gx) gx = bp.mtiles[i];
+    if (bp.ntiles[i] > gy) gy = bp.ntiles[i];
+    bp.z_begin[i] = z;
+    z += members * p.splits;
+  }
+  bp.z_begin[n_problems] = z;
+  for (int i = n_problems; i < MAX_BATCH; ++i) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
+  static bool attr_set = false;
+  if (!attr_set) {
+    D3B_CUDA(cudaFuncSetAttribute(umma_gemm_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  umma_gemm_batched_kernel<<<dim3(gx, gy, z), NTHREADS, smem, (cudaStream_t)stream>>>(maps, bp);
+  return check_launch("umma_gemm_tn_batched");
 }

@@ -300,18 +300,24 @@ class DenseNet:
                                 self._hb("grads", member0) if weight_grads else None, ms,
                                 _p(dx) if dx is not None else None, lddx, stride_dx, dx_col0, dx_cols, stream)
             if weight_grads:
+                # every dW_l = dZ_l^T H_{l-1} of the network in one launch (MN-major operands, split-K RED)
+                a_p, a_ld, a_s, b_p, b_ld, b_s, ms_, ns_, o_p, o_ld = [], [], [], [], [], [], [], [], [], []
                 for i in range(nl):
                     h, d_in = self.hidden[i], (self.hidden[i - 1] if i > 0 else self.in_dim)
                     dz = ctx.dz[i]
+                    a_p.append(_p(dz)); a_ld.append(dz.shape[2]); a_s.append(dz.shape[1] * dz.shape[2])
                     if i > 0:
                         prev = ctx.hb[i - 1]
-                        bsrc, ldb, sb = _p(prev), prev.shape[2], prev.shape[1] * prev.shape[2]
+                        b_p.append(_p(prev)); b_ld.append(prev.shape[2]); b_s.append(prev.shape[1] * prev.shape[2])
                     else:
-                        bsrc, ldb, sb = ctx.x_src[0], ctx.x_src[1], 0
-                    tiles = -(-h // 128) * -(-d_in // 256) * E
-                    splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
-                    L.umma_gemm_tn(_p(dz), dz.shape[2], dz.shape[1] * dz.shape[2], bsrc, ldb, sb, h, d_in, rows, E,
-                                   splits, self._w("grads", i, member0), d_in, ms, 1, stream)
+                        b_p.append(ctx.x_src[0]); b_ld.append(ctx.x_src[1]); b_s.append(0)
+                    ms_.append(h); ns_.append(d_in)
+                    o_p.append(self._w("grads", i, member0)); o_ld.append(d_in)
+                arr = lambda T, v: (T * len(v))(*v)
+                L.umma_gemm_tn_batched(nl, arr(ctypes.c_void_p, a_p), arr(ctypes.c_int64, a_ld), arr(ctypes.c_int64, a_s),
+                                       arr(ctypes.c_void_p, b_p), arr(ctypes.c_int64, b_ld), arr(ctypes.c_int64, b_s),
+                                       arr(ctypes.c_int, ms_), arr(ctypes.c_int, ns_), rows, E,
+                                       arr(ctypes.c_void_p, o_p), arr(ctypes.c_int64, o_ld), ms, stream)
             return
         last = ctx.hb[-1]
         lf = _a8(feat)
@@ -351,11 +357,24 @@ class DenseNet:
     # ------------------------------------------------------------------ optimizer
     def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
         a = self.arena
+        sync = tau is not None and a.target is not None
+        if self.precision == "bf16" and self.fused_ok and self.head_out <= 16:
+            # the fused kernels only read the row-major W shadows: refresh them inside the Adam pass
+            import ctypes
+
+            t = self._table
+            seg = (ctypes.c_int64 * (5 * t.shape[0]))(*[int(v) for r in t.tolist() for v in (r[0], r[1], r[2], r[3], r[4])])
+            lib().adam_step_shadow(_p(a.params), _p(a.grads), _p(a.exp_avg), _p(a.exp_avg_sq),
+                                   _p(a.target) if sync else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
+                                   tau if sync else 0.0, _p(self.shadow),
+                                   _p(self.shadow_target) if sync and self.shadow_target is not None else None, seg,
+                                   t.shape[0], a.member_size, self.shadow_member, stream)
+            return
         lib().adam_step(_p(a.params), _p(a.grads), _p(a.exp_avg), _p(a.exp_avg_sq),
-                        _p(a.target) if tau is not None else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
-                        tau if tau is not None else 0.0, 1, stream)
+                        _p(a.target) if sync else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
+                        tau if sync else 0.0, 1, stream)
         self.refresh_shadow("params", stream)
-        if tau is not None and a.target is not None:
+        if sync:
             self.refresh_shadow("target", stream)
 
 

@@ -127,6 +127,12 @@ int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const int* dims_h
                           const float* head_w, int64_t stride_head, int n_head, float* const* dbias_host,
                           float* d_head_w, float* d_head_b, int64_t stride_grad, float* dx, int64_t lddx,
                           int64_t stride_dx, int dx_col0, int dx_cols, void* stream);
+/* all weight-gradient GEMMs of one network in one launch (host arrays of length n_problems <= 4; same k rows and
+ * member count; RED.ADD into the gradient arena, split-K chosen so that ~2 CTAs per SM are in flight) */
+int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const int64_t* lda_host,
+                             const int64_t* stride_a_host, const void* const* b_host, const int64_t* ldb_host,
+                             const int64_t* stride_b_host, const int* m_host, const int* n_host, int k, int members,
+                             float* const* out_host, const int64_t* ldf_host, int64_t stride_f, void* stream);
 int d3b_umma_set_debug(void* device_buffer); /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);
@@ -282,6 +288,12 @@ int d3b_col2im(const float* dpatch, int64_t ldp, int64_t stride_p, const void* y
 int d3b_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
                   const int* step, double lr, double beta1, double beta2, double eps, float tau, int zero_grad,
                   void* stream);
+/* adam_step that also rewrites the bf16 K-major weight shadows (params and, when synced, target) in the same
+ * pass; table_host: n_segments x {param_off, rows, cols, shadow_off, ld} int64 per trunk weight matrix. */
+int d3b_adam_step_shadow(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
+                         const int* step, double lr, double beta1, double beta2, double eps, float tau,
+                         void* shadow_params, void* shadow_target, const int64_t* table_host, int n_segments,
+                         int64_t member_size, int64_t shadow_member, void* stream);
 int d3b_soft_sync(float* target, const float* params, int64_t n, float tau, void* stream);
 int d3b_hard_sync(float* target, const float* params, int64_t n, void* stream);
 int d3b_tick(int* counters, int n, unsigned mask, void* stream);
