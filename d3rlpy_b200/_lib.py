@@ -87,8 +87,8 @@ class Lib:
         elif name == "mlp_backward_bf16":  # rows, members, n_layers, dims[]; dgrad chain (+ head) (+ dx columns)
             dims = list(args[3])
             mac = sum(a * b for a, b in zip(dims[1:-1], dims[2:])) + dims[-1] * args[16]
-            if args[21]:
-                mac += dims[1] * args[25]
+            if args[22]:
+                mac += dims[1] * args[26]
             flops = 2.0 * args[0] * args[1] * mac
         elif name == "mlp_forward_bf16":  # rows, members, n_layers, dims[] (+ head: n_head at 18)
             dims = list(args[6])

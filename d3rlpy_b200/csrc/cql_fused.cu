@@ -188,16 +188,19 @@ struct LossParams {
   float* metric; float* metric_exp;
 };
 
+// One WARP per (member e, batch row b): the 3N importance-sampling values are spread over the lanes (coalesced
+// loads), max / sum-exp by warp shuffles, softmax gradient written back by the same lanes.
 __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
   const int B = p.B, E = p.E, N = p.N;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   float td = 0.f, lse_v = 0.f, data_v = 0.f;
   const bool td_enabled = p.mode == 0 && (p.q_targ || p.q_tpn);
-  if (idx < B * E) {
-    int e = idx / B, b = idx % B;
+  if (item < B * E) {
+    const int e = item / B, b = item % B;
     const float* qe = p.q + (long long)e * p.sQ;
     float* dqe = p.dq ? p.dq + (long long)e * p.sDq : nullptr;
-    float qd = __ldg(qe + b);
+    const float qd = __ldg(qe + b);
     float g = 0.f;
     if (td_enabled) {
       float tq;
@@ -213,40 +216,46 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
       td = d * d;
       g = 2.f * p.inv_b * d;
     }
-    float ca = clampf3(expf(p.scalar_alpha[0]), 0.f, 1e6f);
-    float c = ca * p.cw * p.inv_eb;
-    float rand_lp = (float)p.A * -0.69314718055994529f;
-    const float* q1 = qe + B + (long long)b * N;
-    const float* q2 = q1 + (long long)B * N;
-    const float* q3 = q2 + (long long)B * N;
-    const float* l1 = p.logp_t + (long long)b * N;
-    const float* l2 = p.logp_tp1 + (long long)b * N;
+    const float ca = clampf3(expf(p.scalar_alpha[0]), 0.f, 1e6f);
+    const float c = ca * p.cw * p.inv_eb;
+    const float rand_lp = (float)p.A * -0.69314718055994529f;
+    const long long BN = (long long)B * N;
+    // value index v in [0, 3N): group = v / N (pi(s_t), pi(s_tp1), random), sample k = v % N
     float mx = -INFINITY;
-    for (int k = 0; k < N; ++k) {
-      mx = fmaxf(mx, __ldg(q1 + k) - __ldg(l1 + k));
-      mx = fmaxf(mx, __ldg(q2 + k) - __ldg(l2 + k));
-      mx = fmaxf(mx, __ldg(q3 + k) - rand_lp);
+    for (int v = lane; v < 3 * N; v += 32) {
+      int grp = v / N, k = v - grp * N;
+      float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
+      float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                           : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+      mx = fmaxf(mx, q - off);
     }
+    mx = warp_max(mx);
     float s = 0.f;
-    for (int k = 0; k < N; ++k) {
-      s += expf(__ldg(q1 + k) - __ldg(l1 + k) - mx);
-      s += expf(__ldg(q2 + k) - __ldg(l2 + k) - mx);
-      s += expf(__ldg(q3 + k) - rand_lp - mx);
+    for (int v = lane; v < 3 * N; v += 32) {
+      int grp = v / N, k = v - grp * N;
+      float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
+      float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                           : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+      s += expf(q - off - mx);
     }
-    lse_v = mx + logf(s);
-    data_v = qd;
-    g -= c;
+    s = warp_sum(s);
     if (dqe) {
-      float inv_s = c / s;
-      float* d1 = dqe + B + (long long)b * N;
-      float* d2 = d1 + (long long)B * N;
-      float* d3 = d2 + (long long)B * N;
-      for (int k = 0; k < N; ++k) {
-        d1[k] = expf(__ldg(q1 + k) - __ldg(l1 + k) - mx) * inv_s;
-        d2[k] = expf(__ldg(q2 + k) - __ldg(l2 + k) - mx) * inv_s;
-        d3[k] = expf(__ldg(q3 + k) - rand_lp - mx) * inv_s;
+      const float inv_s = c / s;
+      for (int v = lane; v < 3 * N; v += 32) {
+        int grp = v / N, k = v - grp * N;
+        long long idx = B + grp * BN + (long long)b * N + k;
+        float q = __ldg(qe + idx);
+        float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                             : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+        dqe[idx] = expf(q - off - mx) * inv_s;
       }
-      dqe[b] = g;
+      if (lane == 0) dqe[b] = g - c;
+    }
+    if (lane == 0) {
+      lse_v = mx + logf(s);
+      data_v = qd;
+    } else {
+      td = 0.f;
     }
   }
   td = block_sum(td);
@@ -393,7 +402,7 @@ extern "C" int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* 
   p.dq = dq; p.sDq = stride_dq; p.sums = sums; p.done = (unsigned*)done_counter;
   p.B = batch; p.E = members; p.inv_b = inv_batch; p.inv_eb = inv_batch / (float)members;
   p.mode = mode; p.step_alpha = step_alpha; p.lr_alpha = lr_alpha; p.metric = metric; p.metric_exp = metric_exp;
-  cql_loss_step_kernel<<<ceil_div(batch * members, 256), 256, 0, ST>>>(p);
+  cql_loss_step_kernel<<<ceil_div(batch * members, 8), 256, 0, ST>>>(p);
   return check_launch("cql_loss_step");
 }
 

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < NH; ++j) tmp[j] = (j < p.n_head && t < feat) ? __ldg(hw + (long long)j * feat + t) : 0.f;
 #pragma unroll
-          for (int j = 0; j < NH; ++j) head_w_s[j * MAXW + t] = tmp[j];
+          for (int j = 0; j < NH; ++j) head_w_s[t * NH + j] = tmp[j];  // [column][head]: one row of NH weights per column
         }
         epi_sync();
         cur_member = e;
@@ -300,16 +300,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
               hv[2 * i] = bf16_lo(pk[i]);
               hv[2 * i + 1] = bf16_hi(pk[i]);
             }
+            // column-outer: the NH accumulators are independent FMA chains; weights of one column are contiguous
 #pragma unroll
-            for (int j = 0; j < NH; ++j) {
-              const float4* w4 = reinterpret_cast<const float4*>(head_w_s + j * MAXW + c);
+            for (int i = 0; i < 16; ++i) {
+              const float* wrow = head_w_s + (c + i) * NH;
+              if constexpr (NH % 4 == 0) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 w = w4[i];
-                acc[j] = fmaf(hv[4 * i], w.x, acc[j]);
-                acc[j] = fmaf(hv[4 * i + 1], w.y, acc[j]);
-                acc[j] = fmaf(hv[4 * i + 2], w.z, acc[j]);
-                acc[j] = fmaf(hv[4 * i + 3], w.w, acc[j]);
+                for (int j4 = 0; j4 < NH / 4; ++j4) {
+                  float4 w = reinterpret_cast<const float4*>(wrow)[j4];
+                  acc[4 * j4] = fmaf(hv[i], w.x, acc[4 * j4]);
+                  acc[4 * j4 + 1] = fmaf(hv[i], w.y, acc[4 * j4 + 1]);
+                  acc[4 * j4 + 2] = fmaf(hv[i], w.z, acc[4 * j4 + 2]);
+                  acc[4 * j4 + 3] = fmaf(hv[i], w.w, acc[4 * j4 + 3]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < NH; ++j) acc[j] = fmaf(hv[i], wrow[j], acc[j]);
               }
             }
           }
@@ -390,6 +396,8 @@ struct BwdParams {
   float* d_head_w;
   float* d_head_b;
   long long grad_stride;
+  __nv_bfloat16* d_head_bf16;  // optional [members][rows][16] bf16 copy of d_head: the head's dW then comes from
+                               // the batched weight-gradient GEMM instead of the in-kernel column pass
   float* dx;             // [members][rows][dx_cols] (lddx), may be null
   long long lddx, dx_stride;
   int dx_col0, dx_cols;
@@ -543,6 +551,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
         if (half == 0) {
 #pragma unroll
           for (int j = 0; j < NH; ++j) dhead_s[row * NH + j] = dh[j];
+          if constexpr (NH > 1) {
+            if (p.d_head_bf16 && live) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(2 * j < NH ? dh[2 * j] : 0.f, 2 * j + 1 < NH ? dh[2 * j + 1] : 0.f);
+              uint4* dst = reinterpret_cast<uint4*>(p.d_head_bf16 + ((long long)e * p.rows + m0 + row) * 16);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          }
         }
       }
       if (stores_pending) {
@@ -633,7 +651,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
             atomicAdd(p.dbias[l] + (long long)e * p.grad_stride + t, s);
           }
           if (top) {
-            if (t < N) {
+            if (t < N && !p.d_head_bf16) {
               float a[NH];
 #pragma unroll
               for (int j = 0; j < NH; ++j) a[j] = 0.f;
@@ -855,8 +873,8 @@ extern "C" int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const 
                                      const int64_t* stride_act_host, void* const* dz_host, const int64_t* ld_dz_host,
                                      const int64_t* stride_dz_host, const float* d_head, const float* head_w,
                                      int64_t stride_head, int n_head, float* const* dbias_host, float* d_head_w,
-                                     float* d_head_b, int64_t stride_grad, float* dx, int64_t lddx, int64_t stride_dx,
-                                     int dx_col0, int dx_cols, void* stream) {
+                                     float* d_head_b, int64_t stride_grad, void* d_head_bf16, float* dx,
+                                     int64_t lddx, int64_t stride_dx, int dx_col0, int dx_cols, void* stream) {
   D3B_REQUIRE(rows >= 0 && members >= 1 && n_layers >= 1 && n_layers <= MAX_LAYERS, "mlp_backward_bf16: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dims_host && w_host && ldw_host && acts_host && ld_act_host && stride_act_host && d_head && head_w,
@@ -873,6 +891,7 @@ extern "C" int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const 
   p.d_head = d_head; p.head_w = head_w; p.head_stride = stride_head; p.n_head = n_head;
   p.weight_grads = wg ? 1 : 0;
   p.d_head_w = d_head_w; p.d_head_b = d_head_b; p.grad_stride = stride_grad;
+  p.d_head_bf16 = (wg && n_head > 1) ? (__nv_bfloat16*)d_head_bf16 : nullptr;
   p.dx = dx; p.lddx = lddx; p.dx_stride = stride_dx; p.dx_col0 = dx_col0; p.dx_cols = dx_cols;
   int k = dims_host[0];
   D3B_REQUIRE(k >= 1 && k <= MAXW, "mlp_backward_bf16: input width must be in [1,256]");

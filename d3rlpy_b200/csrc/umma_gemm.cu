@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) umma_gemm_kernel(const __grid_con
 
 // Several independent weight-gradient GEMMs (one per layer of a network) in ONE launch: blockIdx.z enumerates
 // (problem, member, split); CTAs outside a problem's tile range exit immediately.
-constexpr int MAX_BATCH = 4;
+constexpr int MAX_BATCH = 5;
 struct BatchMaps {
   CUtensorMap a[MAX_BATCH];
   CUtensorMap b[MAX_BATCH];

@@ -294,10 +294,15 @@ class DenseNet:
                 dbp = (ctypes.c_void_p * nl)(*[self._b("grads", i, member0) for i in range(nl)])
             else:
                 dzp = lddz = sdz = dbp = None
+            dh16 = None
+            if weight_grads and n > 1:
+                if getattr(ctx, "dh16", None) is None:
+                    ctx.dh16 = torch.zeros(E, ctx.rows, 16, dtype=torch.bfloat16, device=self.device)
+                dh16 = ctx.dh16
             L.mlp_backward_bf16(rows, E, nl, dims, wp, ldw, sms, ap, lda, sa, dzp, lddz, sdz, _p(d_head),
                                 self._hw("params", member0), ms, n, dbp,
                                 self._hw("grads", member0) if weight_grads else None,
-                                self._hb("grads", member0) if weight_grads else None, ms,
+                                self._hb("grads", member0) if weight_grads else None, ms, _p(dh16),
                                 _p(dx) if dx is not None else None, lddx, stride_dx, dx_col0, dx_cols, stream)
             if weight_grads:
                 # every dW_l = dZ_l^T H_{l-1} of the network in one launch (MN-major operands, split-K RED)
@@ -313,8 +318,14 @@ class DenseNet:
                         b_p.append(ctx.x_src[0]); b_ld.append(ctx.x_src[1]); b_s.append(0)
                     ms_.append(h); ns_.append(d_in)
                     o_p.append(self._w("grads", i, member0)); o_ld.append(d_in)
+                if dh16 is not None:  # head dW = d_head^T H_{L-1} as one more problem of the same launch
+                    last = ctx.hb[-1]
+                    a_p.append(_p(dh16)); a_ld.append(16); a_s.append(rows * 16)
+                    b_p.append(_p(last)); b_ld.append(last.shape[2]); b_s.append(last.shape[1] * last.shape[2])
+                    ms_.append(n); ns_.append(feat)
+                    o_p.append(self._hw("grads", member0)); o_ld.append(feat)
                 arr = lambda T, v: (T * len(v))(*v)
-                L.umma_gemm_tn_batched(nl, arr(ctypes.c_void_p, a_p), arr(ctypes.c_int64, a_ld), arr(ctypes.c_int64, a_s),
+                L.umma_gemm_tn_batched(len(a_p), arr(ctypes.c_void_p, a_p), arr(ctypes.c_int64, a_ld), arr(ctypes.c_int64, a_s),
                                        arr(ctypes.c_void_p, b_p), arr(ctypes.c_int64, b_ld), arr(ctypes.c_int64, b_s),
                                        arr(ctypes.c_int, ms_), arr(ctypes.c_int, ns_), rows, E,
                                        arr(ctypes.c_void_p, o_p), arr(ctypes.c_int64, o_ld), ms, stream)

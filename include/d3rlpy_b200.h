@@ -119,15 +119,17 @@ int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x, int rows,
 /* mlp_backward_bf16: autograd of mlp_forward_bf16 w.r.t. activations in ONE persistent launch: dZ_{L-1} from
  * d_head and the head weights, then dZ_{l-1} = (dZ_l W_l) * [H_{l-1} > 0] with W_l fed as MN-major tiles, optional
  * dX for input columns [dx_col0, dx_col0+dx_cols).  dbias_host != NULL: also store every dZ_l (operands of the
- * weight-gradient GEMMs d3b_umma_gemm_tn) and RED-add bias / head gradients into the gradient arena. */
+ * weight-gradient GEMMs d3b_umma_gemm_tn) and RED-add bias / head gradients into the gradient arena; with
+ * d_head_bf16 != NULL (n_head > 1) a bf16 [members][rows][16] copy of d_head is written instead of reducing the
+ * head's dW in-kernel, and the caller adds {d_head_bf16, H_{L-1}} as one more weight-gradient GEMM problem. */
 int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const int* dims_host, const void* const* w_host,
                           const int64_t* ldw_host, int64_t stride_w, const void* const* acts_host,
                           const int64_t* ld_act_host, const int64_t* stride_act_host, void* const* dz_host,
                           const int64_t* ld_dz_host, const int64_t* stride_dz_host, const float* d_head,
                           const float* head_w, int64_t stride_head, int n_head, float* const* dbias_host,
-                          float* d_head_w, float* d_head_b, int64_t stride_grad, float* dx, int64_t lddx,
-                          int64_t stride_dx, int dx_col0, int dx_cols, void* stream);
-/* all weight-gradient GEMMs of one network in one launch (host arrays of length n_problems <= 4; same k rows and
+                          float* d_head_w, float* d_head_b, int64_t stride_grad, void* d_head_bf16, float* dx,
+                          int64_t lddx, int64_t stride_dx, int dx_col0, int dx_cols, void* stream);
+/* all weight-gradient GEMMs of one network in one launch (host arrays of length n_problems <= 5; same k rows and
  * member count; RED.ADD into the gradient arena, split-K chosen so that ~2 CTAs per SM are in flight) */
 int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const int64_t* lda_host,
                              const int64_t* stride_a_host, const void* const* b_host, const int64_t* ldb_host,

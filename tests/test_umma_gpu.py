@@ -353,7 +353,7 @@ def test_fused_mlp_backward_matches_torch(rows, E, in_dim, hidden, n_head, wg, d
                         d_head.data_ptr(), params.data_ptr() + 4 * hw_off, ms, n_head,
                         arr(ctypes.c_void_p, [grads.data_ptr() + 4 * o for o in b_off]) if wg else None,
                         grads.data_ptr() + 4 * hw_off if wg else None, grads.data_ptr() + 4 * hb_off if wg else None, ms,
-                        dx.data_ptr() if dxr else None, dxr[1] if dxr else 0, rows * dxr[1] if dxr else 0,
+                        None, dx.data_ptr() if dxr else None, dxr[1] if dxr else 0, rows * dxr[1] if dxr else 0,
                         dxr[0] if dxr else 0, dxr[1] if dxr else 0, _st())
     torch.cuda.synchronize()
 
