@@ -40,6 +40,8 @@ __global__ void __launch_bounds__(256) shadow_kernel(const float* __restrict__ s
 __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ src, long long lds, int rows, int cols,
                                                       __nv_bfloat16* __restrict__ dst, long long ldd,
                                                       __nv_bfloat16* __restrict__ dstT, long long ldt) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -197,7 +199,8 @@ extern "C" int d3b_to_bf16(const float* src, int64_t lds, int rows, int cols, vo
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(src && (dst || dst_t), "to_bf16: null pointer");
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32));
-  to_bf16_kernel<<<grid, 256, 0, ST>>>(src, lds, rows, cols, (__nv_bfloat16*)dst, ldd, (__nv_bfloat16*)dst_t, ldt);
+  launch_pdl(to_bf16_kernel, grid, dim3(256), 0, ST, src, (long long)lds, rows, cols, (__nv_bfloat16*)dst, (long long)ldd,
+             (__nv_bfloat16*)dst_t, (long long)ldt);
   return check_launch("to_bf16");
 }
 

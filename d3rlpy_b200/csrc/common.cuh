@@ -38,6 +38,31 @@ __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { ret
 
 constexpr int kNumSM = 148;  // B200
 
+// ---- programmatic dependent launch (PDL): batch-256 updates are launch-latency bound, so consecutive kernels of
+// the update graph overlap the prologue of kernel N+1 (barrier init, TMEM allocation, descriptor prefetch, block
+// scheduling) with the tail of kernel N.  Every kernel launched through launch_pdl() calls pdl_trigger() first
+// and pdl_wait() before its first global-memory access (griddepcontrol.wait returns once all prerequisite grids
+// have completed and their writes are visible).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -21,6 +21,8 @@ __device__ __forceinline__ float clampf3(float x, float lo, float hi) { return f
 __device__ __forceinline__ float softplusf3(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
 __global__ void begin_step_kernel(int* counters, int n, unsigned mask, float* slots, int n_slots) {
+  pdl_trigger();
+  pdl_wait();
   int i = threadIdx.x;
   if (i < n && ((mask >> i) & 1u)) counters[i] += 1;
   for (int j = i; j < n_slots; j += blockDim.x) slots[j] = 0.f;
@@ -69,6 +71,8 @@ __device__ __forceinline__ float sample_action(const float* __restrict__ head_ro
 
 // one warp per work item; items: per group R = B(1+3N) rows, then B target rows, B actor rows, B temp items
 __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int B = p.B, N = p.N, O = p.O, A = p.A;
@@ -159,6 +163,8 @@ __device__ __forceinline__ float scalar_adam_update(float* p, float G, float* m,
 __global__ void __launch_bounds__(1024) sac_temp_step_kernel(const float* __restrict__ logp, float* scalar /*p,g,m,v at stride 4*/,
                                                              const int* step, int B, int A, float inv_b, double lr,
                                                              float* metric_loss, float* metric_exp) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += __ldg(logp + b) - (float)A;
   s = block_sum(s);
@@ -191,6 +197,8 @@ struct LossParams {
 // One WARP per (member e, batch row b): the 3N importance-sampling values are spread over the lanes (coalesced
 // loads), max / sum-exp by warp shuffles, softmax gradient written back by the same lanes.
 __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int B = p.B, E = p.E, N = p.N;
   const int lane = threadIdx.x & 31;
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -301,6 +309,8 @@ __global__ void __launch_bounds__(256) sac_actor_step_kernel(const float* __rest
                                                              float* __restrict__ dq, long long sDq,
                                                              float* __restrict__ loss_sum, unsigned* done,
                                                              float* metric, int B, int E, float inv_b) {
+  pdl_trigger();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -333,7 +343,7 @@ using namespace d3b;
 
 extern "C" int d3b_begin_step(int* counters, int n, unsigned mask, float* slots, int n_slots, void* stream) {
   D3B_REQUIRE(counters && n >= 0 && n <= 32 && slots && n_slots >= 0, "begin_step: bad arguments");
-  begin_step_kernel<<<1, 64, 0, ST>>>(counters, n, mask, slots, n_slots);
+  launch_pdl(begin_step_kernel, dim3(1), dim3(64), 0, ST, counters, n, mask, slots, n_slots);
   return check_launch("begin_step");
 }
 
@@ -372,14 +382,15 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
   D3B_REQUIRE(!p.eps_soft || p.logp_soft, "cql_rows: null soft-backup log-prob pointer");
   p.target_row0 = rows_host[2]; p.actor_row0 = rows_host[3];
   long long items = ((long long)batch + 3LL * batch * n_action_samples) * n_groups + 3LL * batch;
-  cql_rows_kernel<<<(unsigned)ceil_div_ll(items, 8), 256, 0, ST>>>(p);
+  launch_pdl(cql_rows_kernel, dim3((unsigned)ceil_div_ll(items, 8)), dim3(256), 0, ST, p);
   return check_launch("cql_rows");
 }
 
 extern "C" int d3b_sac_temp_step(const float* logp, float* scalar, const int* step, int batch, int act_dim,
                                  float inv_batch, double lr, float* metric_loss, float* metric_exp, void* stream) {
   D3B_REQUIRE(logp && scalar && step && metric_loss && metric_exp && batch >= 1, "sac_temp_step: bad arguments");
-  sac_temp_step_kernel<<<1, 1024, 0, ST>>>(logp, scalar, step, batch, act_dim, inv_batch, lr, metric_loss, metric_exp);
+  launch_pdl(sac_temp_step_kernel, dim3(1), dim3(1024), 0, ST, logp, scalar, step, batch, act_dim, inv_batch, lr, metric_loss,
+             metric_exp);
   return check_launch("sac_temp_step");
 }
 
@@ -402,7 +413,7 @@ extern "C" int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* 
   p.dq = dq; p.sDq = stride_dq; p.sums = sums; p.done = (unsigned*)done_counter;
   p.B = batch; p.E = members; p.inv_b = inv_batch; p.inv_eb = inv_batch / (float)members;
   p.mode = mode; p.step_alpha = step_alpha; p.lr_alpha = lr_alpha; p.metric = metric; p.metric_exp = metric_exp;
-  cql_loss_step_kernel<<<ceil_div(batch * members, 8), 256, 0, ST>>>(p);
+  launch_pdl(cql_loss_step_kernel, dim3(ceil_div(batch * members, 8)), dim3(256), 0, ST, p);
   return check_launch("cql_loss_step");
 }
 
@@ -411,8 +422,7 @@ extern "C" int d3b_sac_actor_step(const float* q, int64_t stride_q, const float*
                                   int batch, int members, float inv_batch, void* stream) {
   D3B_REQUIRE(batch >= 1 && members >= 1, "sac_actor_step: bad sizes");
   D3B_REQUIRE(q && logp && log_temp && dq && loss_sum && done_counter && metric, "sac_actor_step: null pointer");
-  sac_actor_step_kernel<<<ceil_div(batch, 256), 256, 0, ST>>>(q, stride_q, logp, log_temp, dq, stride_dq, loss_sum,
-                                                             (unsigned*)done_counter, metric, batch, members,
-                                                             inv_batch);
+  launch_pdl(sac_actor_step_kernel, dim3(ceil_div(batch, 256)), dim3(256), 0, ST, q, (long long)stride_q, logp, log_temp, dq,
+             (long long)stride_dq, loss_sum, (unsigned*)done_counter, metric, batch, members, inv_batch);
   return check_launch("sac_actor_step");
 }

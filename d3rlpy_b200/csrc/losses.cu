@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(256) sac_actor_backward_kernel(
     const float* __restrict__ head, long long ldh, const float* __restrict__ eps, const float* __restrict__ dX,
     long long lddx, long long sdX, int E, const float* __restrict__ log_temp, float* __restrict__ dhead,
     long long lddh, int B, int A, float min_logstd, float max_logstd, float inv_b) {
+  pdl_trigger();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * A) return;
   int b = idx / A, j = idx % A;
@@ -278,6 +280,8 @@ __global__ void __launch_bounds__(256) sac_soft_backup_kernel(const float* __res
                                                               const float* __restrict__ logp,
                                                               const float* __restrict__ log_temp,
                                                               float* __restrict__ q_tpn, int B) {
+  pdl_trigger();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float m = __ldg(q_targ + b);
@@ -447,9 +451,8 @@ extern "C" int d3b_sac_actor_backward(const float* head, int64_t ld_head, const 
   D3B_REQUIRE(batch >= 0 && act_dim >= 1 && members >= 1, "sac_actor_backward: bad sizes");
   if (batch == 0) return D3B_OK;
   D3B_REQUIRE(head && eps && dx_action && log_temp && dhead, "sac_actor_backward: null pointer");
-  sac_actor_backward_kernel<<<ceil_div(batch * act_dim, 256), 256, 0, ST>>>(
-      head, ld_head, eps, dx_action, lddx, stride_dx, members, log_temp, dhead, ld_dhead, batch, act_dim, min_logstd,
-      max_logstd, inv_batch);
+  launch_pdl(sac_actor_backward_kernel, dim3(ceil_div(batch * act_dim, 256)), dim3(256), 0, ST, head, ld_head, eps, dx_action,
+             lddx, stride_dx, members, log_temp, dhead, ld_dhead, batch, act_dim, min_logstd, max_logstd, inv_batch);
   return check_launch("sac_actor_backward");
 }
 
@@ -494,6 +497,7 @@ extern "C" int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int me
   D3B_REQUIRE(batch >= 0 && members >= 1, "sac_soft_backup: bad sizes");
   if (batch == 0) return D3B_OK;
   D3B_REQUIRE(q_targ && logp && log_temp && q_tpn, "sac_soft_backup: null pointer");
-  sac_soft_backup_kernel<<<ceil_div(batch, 256), 256, 0, ST>>>(q_targ, stride_q, members, logp, log_temp, q_tpn, batch);
+  launch_pdl(sac_soft_backup_kernel, dim3(ceil_div(batch, 256)), dim3(256), 0, ST, q_targ, stride_q, members, logp, log_temp,
+             q_tpn, batch);
   return check_launch("sac_soft_backup");
 }

@@ -138,6 +138,7 @@ enum { B_WFULL = 0, B_WEMPTY = W_STAGES, B_XFULL = 2 * W_STAGES, B_AFREE, B_ACCF
 
 template <int NH>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 8) {
     // ================= TMA producer: x tile, then the weight K blocks of every layer through the ring
@@ -419,6 +421,7 @@ __device__ __forceinline__ const __nv_bfloat16* swz_ptr(const uint8_t* buf, int 
 
 template <int NH>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_constant__ BwdMaps maps, BwdParams p) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smA = smem;                                   // dZ_l operand buffer (4 K blocks)
@@ -454,6 +457,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 8) {
     // ================= TMA producer: mask tiles H_l (l = L-1..0) interleaved with the weight blocks of each step
@@ -763,7 +767,7 @@ int launch_fwd(const Maps& maps, const FwdParams& p, int grid, cudaStream_t st) 
                                   (int)fwd_smem<NH>()));
     attr_set = true;
   }
-  mlp_forward_kernel<NH><<<grid, NTHREADS, fwd_smem<NH>(), st>>>(maps, p);
+  launch_pdl(mlp_forward_kernel<NH>, dim3(grid), dim3(NTHREADS), fwd_smem<NH>(), st, maps, p);
   return check_launch("mlp_forward_bf16");
 }
 
@@ -856,7 +860,7 @@ int launch_bwd(const BwdMaps& maps, const BwdParams& p, int grid, cudaStream_t s
                                   (int)bwd_smem<NH>()));
     attr_set = true;
   }
-  mlp_backward_kernel<NH><<<grid, NTHREADS, bwd_smem<NH>(), st>>>(maps, p);
+  launch_pdl(mlp_backward_kernel<NH>, dim3(grid), dim3(NTHREADS), bwd_smem<NH>(), st, maps, p);
   return check_launch("mlp_backward_bf16");
 }
 

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ p,
                                                           double lr, double b1, double b2, double eps, float tau,
                                                           __nv_bfloat16* __restrict__ sh_p,
                                                           __nv_bfloat16* __restrict__ sh_t, ShadowSegs segs) {
+  pdl_trigger();
+  pdl_wait();
   float w1, fb2, w2, feps, neg_ss, bc2s;
   adam_scalars(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
   float one_m_tau = (float)(1.0 - (double)tau);
@@ -203,6 +205,8 @@ __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5
 __global__ void __launch_bounds__(256) noise_fill_kernel(float* __restrict__ out, long long n_normal,
                                                          long long n_uniform, unsigned long long seed,
                                                          const int* draw_counter) {
+  pdl_trigger();
+  pdl_wait();
   long long n = n_normal + n_uniform;
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call -> 4 floats
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -277,9 +281,9 @@ extern "C" int d3b_adam_step_shadow(float* params, float* grads, float* exp_avg,
     segs.param_off[k] = t[0]; segs.count[k] = t[1] * t[2]; segs.cols[k] = (int)t[2];
     segs.shadow_off[k] = t[3]; segs.ld[k] = (int)t[4];
   }
-  adam_shadow_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(
-      params, grads, exp_avg, exp_avg_sq, target, n, step, lr, beta1, beta2, eps, tau, (__nv_bfloat16*)shadow_params,
-      (__nv_bfloat16*)shadow_target, segs);
+  launch_pdl(adam_shadow_kernel, dim3(grid_for(n, 4)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq,
+             target, (long long)n, step, lr, beta1, beta2, eps, tau, (__nv_bfloat16*)shadow_params,
+             (__nv_bfloat16*)shadow_target, segs);
   return check_launch("adam_step_shadow");
 }
 
@@ -312,6 +316,7 @@ extern "C" int d3b_noise_fill(float* out, int64_t n_normal, int64_t n_uniform, u
   long long n = n_normal + n_uniform;
   if (n == 0) return D3B_OK;
   D3B_REQUIRE(out && draw_counter, "noise_fill: null pointer");
-  noise_fill_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(out, n_normal, n_uniform, seed, draw_counter);
+  launch_pdl(noise_fill_kernel, dim3(grid_for(n, 4)), dim3(256), 0, (cudaStream_t)stream, out, (long long)n_normal,
+             (long long)n_uniform, (unsigned long long)seed, draw_counter);
   return check_launch("noise_fill");
 }

@@ -139,6 +139,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
                                           const int bx, const int by, const int bz, const int cta_linear) {
   const CUtensorMap& tmA = *tmA_p;
   const CUtensorMap& tmB = *tmB_p;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int b_stage_bytes = (p.mn_major && p.BN < 64 ? 64 : p.BN) * BK * 2;
@@ -180,6 +181,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();  // setup done
 
   if (warp == 8) {
@@ -602,7 +604,7 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
     attr_set = true;
   }
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
-  umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  launch_pdl(umma_gemm_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, tmA, tmB, p);
   return check_launch("umma_gemm");
 }
 
@@ -650,7 +652,7 @@ extern "C" int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, co
     attr_set = true;
   }
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
-  umma_gemm_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, p);
+  launch_pdl(umma_gemm_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, tmA, tmB, p);
   return check_launch("umma_gemm_tn");
 }
 
@@ -717,6 +719,6 @@ extern "C" int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_hos
     D3B_CUDA(cudaFuncSetAttribute(umma_gemm_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  umma_gemm_batched_kernel<<<dim3(gx, gy, z), NTHREADS, smem, (cudaStream_t)stream>>>(maps, bp);
+  launch_pdl(umma_gemm_batched_kernel, dim3(gx, gy, z), dim3(NTHREADS), smem, (cudaStream_t)stream, maps, bp);
   return check_launch("umma_gemm_tn_batched");
 }

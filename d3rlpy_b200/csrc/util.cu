@@ -27,6 +27,17 @@ long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 using namespace d3b;
 
+namespace d3b {
+static bool g_pdl = true;
+bool pdl_enabled() { return g_pdl; }
+}  // namespace d3b
+
+// programmatic dependent launch between the kernels of an update (on by default); 0 restores plain stream order
+extern "C" int d3b_set_pdl(int enabled) {
+  d3b::g_pdl = enabled != 0;
+  return D3B_OK;
+}
+
 extern "C" const char* d3b_last_error(void) { return err_buf(); }
 extern "C" int d3b_abi_version(void) { return D3B_ABI_VERSION; }
 extern "C" int64_t d3b_launch_count(void) { return launches(); }

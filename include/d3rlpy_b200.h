@@ -32,6 +32,7 @@ const char* d3b_last_error(void);
 int d3b_abi_version(void);
 int64_t d3b_launch_count(void); /* kernels + memset/copy nodes issued by this library so far */
 int d3b_device_info(int device, int* sm_count, int* cc_major, int* cc_minor);
+int d3b_set_pdl(int enabled); /* programmatic dependent launch between the update's kernels (default on) */
 
 /* ---- K1/K1b: replay-buffer gather ---------------------------------------------
  * Replaces TransitionMiniBatch.__cinit__/_assign_to_batch/_assign_observation/
