@@ -234,6 +234,11 @@ class CQLImpl(DDPGBaseImpl):
     # ------------------------------------------------------------------ single-GPU tensor-core program
     fused_glue = True  # collapse the glue between the GEMM launches (csrc/cql_fused.cu); False = generic path
 
+    def _side_stream(self) -> int:
+        if getattr(self, "_side_obj", None) is None:
+            self._side_obj = torch.cuda.Stream(device=self._device)
+        return self._side_obj.cuda_stream
+
     def _program_fused(self, db, do_temp, do_alpha):
         """The same update as `program` in update_fused_async with ~half the launches: one row-assembly
         kernel, the alpha-step and critic-step critic forwards in ONE launch, loss + scalar tails fused."""
@@ -268,11 +273,21 @@ class CQLImpl(DDPGBaseImpl):
                    MAX_LOGSTD, X.data_ptr(), ld, G, (ctypes.c_void_p * 16)(*ptrs),
                    (ctypes.c_int64 * 4)(0, R, t_row0, a_row0), st)
         la, lt = self._log_alpha, self._log_temp
+        q_net = self._q_func
+        # ---- side branch (independent of the importance-sampling pass): temperature step, target critics
+        side = self._side_stream()
+        L.stream_fork(st, side)
         if do_temp:
             L.sac_temp_step(lpm[2].data_ptr(), lt.buf.data_ptr(), self.counter_ptr(C_TEMP), B, A, inv_b,
-                            self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS), self.metric_ptr(M_TEMP), st)
-        # critic-step rows [0,R) (activations saved) and alpha-step rows [R,2R) (forward only): one launch
-        q_net = self._q_func
+                            self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS), self.metric_ptr(M_TEMP), side)
+        ctx_t = q_net.ctx("tq", B, E, False)
+        q_t = self.ws("tq_q", E, B)
+        q_net.forward("target", None, 0, B, ctx_t, q_t, side, x_bf16=(X.data_ptr() + 2 * t_row0 * ld, ld))
+        q_tpn = None
+        if soft:
+            q_tpn = self.ws("soft_tpn", B)
+            L.sac_soft_backup(q_t.data_ptr(), B, E, lpm[0].data_ptr(), lt.ptr("p"), q_tpn.data_ptr(), B, side)
+        # ---- main branch: critic-step rows [0,R) (activations saved) and alpha-step rows [R,2R) (forward only)
         ctx = q_net.ctx("is2", G * R, E, True)
         q = self.ws("is2_q", E, G * R)
         q_net.forward("params", None, 0, G * R, ctx, q, st, x_bf16=(X.data_ptr(), ld), save_rows=R)
@@ -282,13 +297,7 @@ class CQLImpl(DDPGBaseImpl):
                             self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done.data_ptr(), B, E, inv_b, 1,
                             self.counter_ptr(C_ALPHA), self._alpha_learning_rate, self.metric_ptr(M_ALPHA_LOSS),
                             self.metric_ptr(M_ALPHA), st)
-        ctx_t = q_net.ctx("tq", B, E, False)
-        q_t = self.ws("tq_q", E, B)
-        q_net.forward("target", None, 0, B, ctx_t, q_t, st, x_bf16=(X.data_ptr() + 2 * t_row0 * ld, ld))
-        q_tpn = None
-        if soft:
-            q_tpn = self.ws("soft_tpn", B)
-            L.sac_soft_backup(q_t.data_ptr(), B, E, lpm[0].data_ptr(), lt.ptr("p"), q_tpn.data_ptr(), B, st)
+        L.stream_join(st, side)
         dq = self.ws("is2_dq", E, R)
         L.cql_loss_step(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
                         q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),

@@ -104,6 +104,33 @@ extern "C" int d3b_spin(int64_t ns, void* stream) {
   return check_launch("spin");
 }
 
+// fork/join of a side stream (also inside stream capture, where they become graph branches): work enqueued on
+// `side` between fork and join runs concurrently with the work on `main_stream`.
+namespace {
+cudaEvent_t g_fork_evt = nullptr, g_join_evt = nullptr;
+int ensure_events() {
+  if (!g_fork_evt) {
+    if (cudaEventCreateWithFlags(&g_fork_evt, cudaEventDisableTiming) != cudaSuccess) return -1;
+    if (cudaEventCreateWithFlags(&g_join_evt, cudaEventDisableTiming) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" int d3b_stream_fork(void* main_stream, void* side_stream) {
+  D3B_REQUIRE(ensure_events() == 0, "stream_fork: cannot create events");
+  D3B_CUDA(cudaEventRecord(g_fork_evt, (cudaStream_t)main_stream));
+  D3B_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, g_fork_evt, 0));
+  return D3B_OK;
+}
+
+extern "C" int d3b_stream_join(void* main_stream, void* side_stream) {
+  D3B_REQUIRE(ensure_events() == 0, "stream_join: cannot create events");
+  D3B_CUDA(cudaEventRecord(g_join_evt, (cudaStream_t)side_stream));
+  D3B_CUDA(cudaStreamWaitEvent((cudaStream_t)main_stream, g_join_evt, 0));
+  return D3B_OK;
+}
+
 extern "C" int d3b_graph_begin(void* stream) {
   D3B_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
   return D3B_OK;

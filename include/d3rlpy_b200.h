@@ -323,6 +323,9 @@ int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream)
 int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
 int d3b_stream_sync(void* stream);
 int d3b_spin(int64_t ns, void* stream); /* measurement helper: busy-wait kernel (keeps the stream ahead of the host) */
+/* fork/join a side stream (graph branches under capture): independent steps of one update run concurrently */
+int d3b_stream_fork(void* main_stream, void* side_stream);
+int d3b_stream_join(void* main_stream, void* side_stream);
 int d3b_graph_begin(void* stream);
 int d3b_graph_end(void* stream, void** graph_exec, int* n_nodes);
 int d3b_graph_launch(void* graph_exec, void* stream);

@@ -242,3 +242,116 @@ def test_noise_fill_statistics():
     ctr += 1
     L.noise_fill(out.data_ptr(), nn_, nu, 1234, ctr.data_ptr(), _st())
     assert float((first == out).float().mean()) < 1e-3  # a new epoch gives a new stream
+
+
+# ----------------------------------------------------------------------------------------- fused CQL glue kernels
+def test_cql_fused_glue_kernels_match_unfused_kernels():
+    """csrc/cql_fused.cu vs the separately-verified kernels it replaces, on identical inputs:
+    cql_rows == concat_rows + policy_sample_rows (+ bf16 rounding of the rows, log-probs to 1e-6);
+    cql_loss_step == critic_loss + cql_finalize (+ scalar_adam in alpha mode); sac_temp_step == sac_temp_loss +
+    scalar_adam; sac_actor_step == sac_actor_loss."""
+    import ctypes
+
+    from d3rlpy_b200._lib import lib
+
+    L, dev, st = lib(), torch.device("cuda:0"), torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(0)
+    B, N, O, A, E = 48, 5, 7, 3, 2
+    R = B * (1 + 3 * N)
+    ld = (O + A + 7) // 8 * 8
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
+    head = rnd(2 * B, 2 * A)
+    obs, nobs = rnd(B, O), rnd(B, O)
+    act = (torch.rand(B, A, generator=g) * 2 - 1).to(dev)
+    eps = {k: rnd(N, B, A) for k in ("ct", "ctp1", "at", "atp1")}
+    rand = {k: (torch.rand(B * N, A, generator=g) * 2 - 1).to(dev) for k in ("c", "a")}
+    eps_soft, eps_actor, eps_temp = rnd(B, A), rnd(B, A), rnd(B, A)
+    X = torch.zeros(2 * R + 2 * B, ld, dtype=torch.bfloat16, device=dev)
+    lp = torch.zeros(4, B * N, device=dev)
+    lpm = torch.zeros(3, B, device=dev)
+    p = lambda t: t.data_ptr()
+    ptrs = [p(eps["ct"]), p(eps["ctp1"]), p(rand["c"]), p(lp[0]), p(lp[1]), p(eps["at"]), p(eps["atp1"]), p(rand["a"]),
+            p(lp[2]), p(lp[3]), p(eps_soft), p(lpm[0]), p(eps_actor), p(lpm[1]), p(eps_temp), p(lpm[2])]
+    L.cql_rows(p(head), p(obs), p(nobs), p(act), B, N, O, A, -20.0, 2.0, p(X), ld, 2, (ctypes.c_void_p * 16)(*ptrs),
+               (ctypes.c_int64 * 4)(0, R, 2 * R, 2 * R + B), st)
+    # reference rows with the unfused kernels (fp32)
+    def ref_group(e_t, e_tp1, rnd_a):
+        x = torch.zeros(R, O + A, device=dev)
+        l = torch.zeros(2, B * N, device=dev)
+        L.concat_rows(p(obs), O, p(act), A, None, 0.0, 0.0, 0.0, p(x), O + A, B, 1, O, A, st)
+        L.policy_sample_rows(p(head), 2 * A, p(e_t), p(obs), O, p(x) + 4 * (O + A) * B, O + A, None, p(l[0]), B, N, O, A,
+                             -20.0, 2.0, 0, st)
+        L.policy_sample_rows(p(head) + 4 * B * 2 * A, 2 * A, p(e_tp1), p(obs), O, p(x) + 4 * (O + A) * (B + B * N), O + A,
+                             None, p(l[1]), B, N, O, A, -20.0, 2.0, 0, st)
+        L.concat_rows(p(obs), O, p(rnd_a), A, None, 0.0, 0.0, 0.0, p(x) + 4 * (O + A) * (B + 2 * B * N), O + A, B, N, O, A, st)
+        return x, l
+    xc, lc = ref_group(eps["ct"], eps["ctp1"], rand["c"])
+    xa, la_ = ref_group(eps["at"], eps["atp1"], rand["a"])
+    xt = torch.zeros(B, O + A, device=dev)
+    lsoft = torch.zeros(B, device=dev)
+    L.policy_sample_rows(p(head) + 4 * B * 2 * A, 2 * A, p(eps_soft), p(nobs), O, p(xt), O + A, None, p(lsoft), B, 1, O, A,
+                         -20.0, 2.0, 0, st)
+    xact = torch.zeros(B, O + A, device=dev)
+    lact, ltemp = torch.zeros(B, device=dev), torch.zeros(B, device=dev)
+    L.policy_sample_rows(p(head), 2 * A, p(eps_actor), p(obs), O, p(xact), O + A, None, p(lact), B, 1, O, A, -20.0, 2.0, 0, st)
+    L.policy_sample_rows(p(head), 2 * A, p(eps_temp), None, 0, None, 0, None, p(ltemp), B, 1, 0, A, -20.0, 2.0, 0, st)
+    torch.cuda.synchronize()
+    W = O + A
+    assert torch.equal(X[:R, :W], xc.to(torch.bfloat16)) and torch.equal(X[R:2 * R, :W], xa.to(torch.bfloat16))
+    assert torch.equal(X[2 * R:2 * R + B, :W], xt.to(torch.bfloat16))
+    assert torch.equal(X[2 * R + B:, :W], xact.to(torch.bfloat16))
+    _close(lp[:2], lc, rtol=1e-6, msg="critic logp")
+    _close(lp[2:], la_, rtol=1e-6, msg="alpha logp")
+    _close(lpm[0], lsoft, rtol=1e-6, msg="soft logp")
+    _close(lpm[1], lact, rtol=1e-6, msg="actor logp")
+    _close(lpm[2], ltemp, rtol=1e-6, msg="temp logp")
+
+    # ---- loss kernels
+    q = rnd(E, R) * 3
+    q_t = rnd(E, B)
+    rew, term = rnd(B), (torch.rand(B, generator=g) < 0.2).float().to(dev)
+    nst = torch.randint(1, 4, (B,), generator=g).float().to(dev)
+    for mode in (0, 1):
+        sc_a = torch.zeros(16, device=dev); sc_a[0] = 0.3
+        sc_b = sc_a.clone()
+        steps = torch.tensor([3], dtype=torch.int32, device=dev)
+        sums_a, sums_b = torch.zeros(4, device=dev), torch.zeros(4, device=dev)
+        dq_a, dq_b = torch.zeros(E, R, device=dev), torch.zeros(E, R, device=dev)
+        met_a, met_b = torch.zeros(2, device=dev), torch.zeros(2, device=dev)
+        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        td = mode == 0
+        L.cql_loss_step(p(q), R, p(q_t) if td else None, B, E, None, p(rew) if td else None, p(term) if td else None,
+                        p(nst) if td else None, 0.99, p(lc[0]), p(lc[1]), N, A, p(sc_a), 5.0, 10.0,
+                        p(dq_a) if td else None, R, p(sums_a), p(done), B, E, 1.0 / B, mode, p(steps), 1e-4, p(met_a),
+                        p(met_a) + 4, st)
+        L.critic_loss(p(q), R, p(q_t) if td else None, B, E, None, p(rew), p(term), p(nst), 0.99, p(lc[0]), p(lc[1]), N, A,
+                      p(sc_b), 5.0, p(dq_b) if td else None, R, p(sums_b), None, B, E, 1.0 / B, 1 if td else 0, st)
+        L.cql_finalize(p(sums_b), p(sc_b), 1.0 / B, E, 5.0, 10.0, mode, 1, p(met_b), p(sc_b) + 16 if mode else None, st)
+        if mode:
+            L.scalar_adam(p(sc_b), p(sc_b) + 16, p(sc_b) + 32, p(sc_b) + 48, p(steps), 1e-4, 0.9, 0.999, 1e-8, p(met_b) + 4, st)
+        torch.cuda.synchronize()
+        _close(met_a[:1 + mode], met_b[:1 + mode], rtol=2e-6, msg=f"loss metric mode {mode}")
+        _close(sc_a, sc_b, rtol=1e-6, msg="log_alpha adam state")
+        if td:
+            _close(dq_a, dq_b, rtol=2e-6, msg="dq")
+        assert int(done.item()) == 0
+    # ---- temp / actor
+    sc_a = torch.zeros(16, device=dev); sc_a[0] = -0.2
+    sc_b = sc_a.clone()
+    steps = torch.tensor([2], dtype=torch.int32, device=dev)
+    met_a, met_b = torch.zeros(2, device=dev), torch.zeros(2, device=dev)
+    L.sac_temp_step(p(ltemp), p(sc_a), p(steps), B, A, 1.0 / B, 1e-4, p(met_a), p(met_a) + 4, st)
+    L.sac_temp_loss(p(ltemp), p(sc_b), B, A, 1.0 / B, p(met_b), p(sc_b) + 16, 0, st)
+    L.scalar_adam(p(sc_b), p(sc_b) + 16, p(sc_b) + 32, p(sc_b) + 48, p(steps), 1e-4, 0.9, 0.999, 1e-8, p(met_b) + 4, st)
+    qa = rnd(E, B)
+    dqa, dqb = torch.zeros(E, B, device=dev), torch.zeros(E, B, device=dev)
+    ls_a, ls_b = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    done = torch.zeros(1, dtype=torch.int32, device=dev)
+    m_act = torch.zeros(1, device=dev)
+    L.sac_actor_step(p(qa), B, p(lact), p(sc_a), p(dqa), B, p(ls_a), p(done), p(m_act), B, E, 1.0 / B, st)
+    L.sac_actor_loss(p(qa), B, p(lact), p(sc_a), p(dqb), B, p(ls_b), B, E, 1.0 / B, st)
+    torch.cuda.synchronize()
+    _close(met_a, met_b, rtol=1e-6, msg="temp metrics")
+    _close(sc_a, sc_b, rtol=1e-6, msg="log_temp adam state")
+    assert torch.equal(dqa, dqb)
+    _close(m_act, ls_b, rtol=1e-6, msg="actor loss")
