@@ -141,7 +141,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
   const CUtensorMap& tmB = *tmB_p;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   const int b_stage_bytes = (p.mn_major && p.BN < 64 ? 64 : p.BN) * BK * 2;
   uint8_t* smA = smem;
   const int STAGES = p.stages;

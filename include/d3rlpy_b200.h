@@ -136,7 +136,8 @@ int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const in
                              const int64_t* stride_a_host, const void* const* b_host, const int64_t* ldb_host,
                              const int64_t* stride_b_host, const int* m_host, const int* n_host, int k, int members,
                              float* const* out_host, const int64_t* ldf_host, int64_t stride_f, void* stream);
-int d3b_umma_set_debug(void* device_buffer); /* profiling hook: 8 clock64 phase stamps per CTA */
+int d3b_umma_set_debug(void* device_buffer);
+int d3b_mlp_set_debug(void* device_buffer);  /* profiling hook: 16 clock64 phase stamps per CTA of mlp_forward_bf16 */ /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);
 int d3b_to_bf16(const float* src, int64_t lds, int rows, int cols, void* dst, int64_t ldd, void* dst_t, int64_t ldt,
