@@ -27,7 +27,7 @@ constexpr int A_KB_BYTES = BM * BK * 2;      // one 64-column K block of the ope
 constexpr int MAX_KB = 4;                    // layer widths <= 256
 constexpr int MAXW = MAX_KB * BK;            // 256
 constexpr int W_STAGE_BYTES = MAXW * BK * 2; // 32 KB
-constexpr int W_STAGES = 3;
+constexpr int W_STAGES_MAX = 4;  // forward weight ring: 4 stages when the head staging is small, else 3
 constexpr int EPI_THREADS = 256, NTHREADS = EPI_THREADS + 64;
 
 struct Maps {
@@ -116,12 +116,40 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// the wait names the destination registers as read-write operands so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -134,11 +162,12 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // barrier slots
-enum { B_WFULL = 0, B_WEMPTY = W_STAGES, B_XFULL = 2 * W_STAGES, B_AFREE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
-       B_ACTREADY = B_TEMPTY + 2, B_COUNT };
+enum { B_WFULL = 0, B_WEMPTY = W_STAGES_MAX, B_XFULL = 2 * W_STAGES_MAX, B_AFREE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
+       B_ACTREADY = B_TEMPTY + 2, B_COUNT = B_ACTREADY + MAX_KB };
 
 template <int NH>
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+  constexpr int W_STAGES = NH <= 16 ? 4 : 3;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -199,18 +228,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   } else if (warp == 9) {
     // ================= MMA issuer
     if (lane == 0) {
-      uint32_t g = 0, wi = 0, it = 0, act_cnt = 0;
+      uint32_t g = 0, wi = 0, it = 0;
+      uint32_t act_cnt[MAX_KB] = {0, 0, 0, 0};
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
         for (int l = 0; l < L; ++l, ++g) {
           const uint32_t buf = g & 1;
           mbar_wait(bars + B_TEMPTY + buf, ((g >> 1) & 1) ^ 1);
-          if (l == 0) {
-            mbar_wait(bars + B_XFULL, it & 1);
-          } else {
-            mbar_wait(bars + B_ACTREADY, act_cnt & 1);
-            ++act_cnt;
-          }
+          if (l == 0) mbar_wait(bars + B_XFULL, it & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (dbg && g == 1) dbg[8] = clock64();                      // layer-1 operands ready
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N[l] >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
           const int nkb = (p.K[l] + BK - 1) / BK;
@@ -218,7 +244,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
           const uint32_t d_tmem = tmem_base + buf * 256;
           for (int kb = 0; kb < nkb; ++kb, ++wi) {
             const uint32_t s = wi % W_STAGES, ph = (wi / W_STAGES) & 1;
+            if (l > 0) {  // K block kb of the previous layer's output has been written by the epilogue warps
+              mbar_wait(bars + B_ACTREADY + kb, act_cnt[kb] & 1);
+              ++act_cnt[kb];
+            }
             mbar_wait(bars + B_WFULL + s, ph);
+            if (dbg && g == 1 && kb < 4) dbg[9 + kb] = clock64();     // weight K block kb of layer 1 landed
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t adesc = make_desc(smem_u32(smA + kb * A_KB_BYTES));
             const uint64_t bdesc = make_desc(smem_u32(smW + s * W_STAGE_BYTES));
@@ -230,6 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
             mma_commit(bars + B_WEMPTY + s);
           }
           mma_commit(bars + B_ACCFULL + buf);
+          if (dbg && g == 1) dbg[13] = clock64();                     // all MMAs of layer 1 issued
         }
       }
     }
@@ -277,58 +309,82 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
           epi_sync();
           stores_pending = false;
         }
-        const int cph = ((N + 31) / 32) * 16;
-        const int c_begin = half ? cph : 0;
-        const int c_end = half ? N : (cph < N ? cph : N);
         const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
         float acc[NH > 0 ? NH : 1];
 #pragma unroll
         for (int j = 0; j < (NH > 0 ? NH : 1); ++j) acc[j] = 0.f;
-        for (int c = c_begin; c < c_end; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + (uint32_t)c, v);
-          uint32_t pk[8];
+        // The 64-column K blocks of the operand buffer are produced IN ORDER by all 8 warps (column half `half`
+        // of each block), so that the next layer's MMAs on block kb start while blocks kb+1.. are still in
+        // the epilogue, and the block's TMA store is issued as soon as it is complete.
+        const int nkb_out = (N + BK - 1) / BK;
+        for (int kb = 0; kb < nkb_out; ++kb) {
+          const int cb = kb * BK;
+          const int rem = (N - cb) < BK ? (N - cb) : BK;
+          const int h0 = rem < 32 ? rem : 32;
+          const int c_begin = half ? cb + h0 : cb;
+          const int c_end = half ? cb + rem : cb + h0;
+          for (int c = c_begin; c < c_end; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + (uint32_t)c, v);
+            uint32_t pk[8];
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + l * MAXW + c);
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            float f0 = fmaxf(__uint_as_float(v[i]) + bias_s[l * MAXW + c + i], 0.f);
-            float f1 = fmaxf(__uint_as_float(v[i + 1]) + bias_s[l * MAXW + c + i + 1], 0.f);
-            pk[i >> 1] = pack_bf16(f0, f1);
+            for (int i = 0; i < 16; i += 4) {
+              const float4 bb = b4[i >> 2];
+              float f0 = fmaxf(__uint_as_float(v[i]) + bb.x, 0.f);
+              float f1 = fmaxf(__uint_as_float(v[i + 1]) + bb.y, 0.f);
+              float f2 = fmaxf(__uint_as_float(v[i + 2]) + bb.z, 0.f);
+              float f3 = fmaxf(__uint_as_float(v[i + 3]) + bb.w, 0.f);
+              pk[i >> 1] = pack_bf16(f0, f1);
+              pk[(i >> 1) + 1] = pack_bf16(f2, f3);
+            }
+            if (writeA) {
+              const int j0 = (c & 63) >> 3;
+              uint8_t* base = smA + kb * A_KB_BYTES + row * 128;
+              *reinterpret_cast<uint4*>(base + ((j0 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+            if (NH > 0 && last && p.n_head > 0) {
+              float hv[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                hv[2 * i] = bf16_lo(pk[i]);
+                hv[2 * i + 1] = bf16_hi(pk[i]);
+              }
+              // column-outer: the NH accumulators are independent FMA chains; weights of one column are contiguous
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float* wrow = head_w_s + (c + i) * NH;
+                if constexpr (NH % 4 == 0) {
+#pragma unroll
+                  for (int j4 = 0; j4 < NH / 4; ++j4) {
+                    float4 w = reinterpret_cast<const float4*>(wrow)[j4];
+                    acc[4 * j4] = fmaf(hv[i], w.x, acc[4 * j4]);
+                    acc[4 * j4 + 1] = fmaf(hv[i], w.y, acc[4 * j4 + 1]);
+                    acc[4 * j4 + 2] = fmaf(hv[i], w.z, acc[4 * j4 + 2]);
+                    acc[4 * j4 + 3] = fmaf(hv[i], w.w, acc[4 * j4 + 3]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < NH; ++j) acc[j] = fmaf(hv[i], wrow[j], acc[j]);
+                }
+              }
+            }
           }
           if (writeA) {
-            const int kb = c >> 6, j0 = (c & 63) >> 3;
-            uint8_t* base = smA + kb * A_KB_BYTES + row * 128;
-            *reinterpret_cast<uint4*>(base + ((j0 ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
-          if (NH > 0 && last && p.n_head > 0) {
-            float hv[16];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              hv[2 * i] = bf16_lo(pk[i]);
-              hv[2 * i + 1] = bf16_hi(pk[i]);
-            }
-            // column-outer: the NH accumulators are independent FMA chains; weights of one column are contiguous
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float* wrow = head_w_s + (c + i) * NH;
-              if constexpr (NH % 4 == 0) {
-#pragma unroll
-                for (int j4 = 0; j4 < NH / 4; ++j4) {
-                  float4 w = reinterpret_cast<const float4*>(wrow)[j4];
-                  acc[4 * j4] = fmaf(hv[i], w.x, acc[4 * j4]);
-                  acc[4 * j4 + 1] = fmaf(hv[i], w.y, acc[4 * j4 + 1]);
-                  acc[4 * j4 + 2] = fmaf(hv[i], w.z, acc[4 * j4 + 2]);
-                  acc[4 * j4 + 3] = fmaf(hv[i], w.w, acc[4 * j4 + 3]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < NH; ++j) acc[j] = fmaf(hv[i], wrow[j], acc[j]);
+            // block kb of H_l is complete in shared memory: hand it to the MMA issuer / the TMA store engine
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            epi_sync();
+            if (t == 0) {
+              if (!last) mbar_arrive(bars + B_ACTREADY + kb);
+              if (store) {
+                tma_store_3d(&maps.h[l], smA + kb * A_KB_BYTES, cb, m0, e);
+                tma_store_commit();
               }
             }
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (writeA) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (NH > 0 && last && p.n_head > 0 && half == 1) {
 #pragma unroll
           for (int j = 0; j < NH; ++j) head_part[row * NH + j] = acc[j];
@@ -336,16 +392,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
         epi_sync();
         if (dbg && t == 0 && g < 6) dbg[3 + 2 * g] = clock64();      // epilogue of layer g done
         if (t == 0) {
-          mbar_arrive(bars + B_TEMPTY + buf);
-          if (!last) mbar_arrive(bars + B_ACTREADY);
-          if (store) {
-            const int nkb_out = (N + BK - 1) / BK;
-            for (int kb = 0; kb < nkb_out; ++kb) tma_store_3d(&maps.h[l], smA + kb * A_KB_BYTES, kb * BK, m0, e);
-            tma_store_commit();
-            if (last) {
-              tma_store_wait_read();
-              mbar_arrive(bars + B_AFREE);
-            }
+          mbar_arrive(bars + B_TEMPTY + buf);  // every thread has drained this accumulator buffer
+          if (last && store) {
+            tma_store_wait_read();
+            mbar_arrive(bars + B_AFREE);
           }
         }
         stores_pending = store && !last;
@@ -763,6 +813,7 @@ int make_map(CUtensorMap* map, const void* base, int cols, int rows, int members
 
 template <int NH>
 size_t fwd_smem() {
+  constexpr int W_STAGES = NH <= 16 ? 4 : 3;
   return 1024 + (size_t)MAX_KB * A_KB_BYTES + (size_t)W_STAGES * W_STAGE_BYTES +
          sizeof(float) * ((size_t)NH * MAXW + MAX_LAYERS * MAXW + (size_t)BM * NH) + 8 * B_COUNT + 64;
 }
