@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
 // H_l tiles (ReLU masks) are TMA-loaded into a second operand-layout buffer.
 constexpr int BW_STAGES = 2;
 enum { C_WFULL = 0, C_WEMPTY = BW_STAGES, C_MFULL = 2 * BW_STAGES, C_MEMPTY, C_ACCFULL, C_TEMPTY = C_ACCFULL + 2,
-       C_ACTREADY = C_TEMPTY + 2, C_COUNT };
+       C_ACTREADY = C_TEMPTY + 2, C_COUNT = C_ACTREADY + MAX_KB };
 
 struct BwdMaps {
   CUtensorMap w[MAX_LAYERS];
@@ -550,15 +550,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
   } else if (warp == 9) {
     // ================= MMA issuer: step s consumes dZ_l (l = L-1-s; the last optional step is the dx step on dZ_0)
     if (lane == 0) {
-      uint32_t g = 0, wi = 0, act_cnt = 0;
+      uint32_t g = 0, wi = 0;
+      uint32_t act_cnt[MAX_KB] = {0, 0, 0, 0};
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         for (int s_ = 0; s_ < n_steps; ++s_, ++g) {
           const int l = L - 1 - s_;
           const int outw = l > 0 ? p.K[l] : dx_w;
           const uint32_t buf = g & 1;
           mbar_wait(bars + C_TEMPTY + buf, ((g >> 1) & 1) ^ 1);
-          mbar_wait(bars + C_ACTREADY, act_cnt & 1);
-          ++act_cnt;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(outw >> 3) << 17) |
                                  ((uint32_t)(BM >> 4) << 24);
@@ -567,6 +566,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
           const uint32_t d_tmem = tmem_base + buf * 256;
           for (int kb = 0; kb < nkb; ++kb, ++wi) {
             const uint32_t s = wi % BW_STAGES, ph = (wi / BW_STAGES) & 1;
+            mbar_wait(bars + C_ACTREADY + kb, act_cnt[kb] & 1);  // K block kb of dZ_l is in the operand buffer
+            ++act_cnt[kb];
             mbar_wait(bars + C_WFULL + s, ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t adesc = make_desc(smem_u32(smA + kb * A_KB_BYTES));
@@ -647,61 +648,70 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
         }
         mbar_wait(bars + C_MFULL, mi & 1);
         ++mi;
-        const int cph = ((N + 31) / 32) * 16;
-        const int c_begin = half ? cph : 0;
-        const int c_end = half ? N : (cph < N ? cph : N);
         const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
-        for (int c = c_begin; c < c_end; c += 16) {
-          float f[16];
-          if (top) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < NH; ++j) {
-              const float4* w4 = reinterpret_cast<const float4*>(head_w_s + j * MAXW + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 w = w4[i];
-                f[4 * i] = fmaf(dh[j], w.x, f[4 * i]);
-                f[4 * i + 1] = fmaf(dh[j], w.y, f[4 * i + 1]);
-                f[4 * i + 2] = fmaf(dh[j], w.z, f[4 * i + 2]);
-                f[4 * i + 3] = fmaf(dh[j], w.w, f[4 * i + 3]);
-              }
-            }
-          } else {
-            uint32_t v[16];
-            tmem_ld16(taddr + (uint32_t)c, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          }
-          const int kb = c >> 6, j0 = (c & 63) >> 3;
-          const int off0 = kb * A_KB_BYTES + row * 128 + ((j0 ^ (row & 7)) << 4);
-          const int off1 = kb * A_KB_BYTES + row * 128 + (((j0 + 1) ^ (row & 7)) << 4);
-          uint4 m0v = *reinterpret_cast<const uint4*>(smM + off0);
-          uint4 m1v = *reinterpret_cast<const uint4*>(smM + off1);
-          const uint32_t mk[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a = bf16_lo(mk[i]) > 0.f ? f[2 * i] : 0.f;
-            float b = bf16_hi(mk[i]) > 0.f ? f[2 * i + 1] : 0.f;
-            pk[i] = pack_bf16(a, b);
-          }
-          *reinterpret_cast<uint4*>(smA + off0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(smA + off1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-        if (!top) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        epi_sync();
         const bool mma_follows = (l > 0) || has_dx;
-        if (t == 0) {
-          if (!top) mbar_arrive(bars + C_TEMPTY + buf);
-          if (mma_follows) mbar_arrive(bars + C_ACTREADY);
-          if (p.weight_grads) {
-            const int nkb_out = (N + BK - 1) / BK;
-            for (int kb = 0; kb < nkb_out; ++kb) tma_store_3d(&maps.dz[l], smA + kb * A_KB_BYTES, kb * BK, m0, e);
-            tma_store_commit();
+        const int nkb_out = (N + BK - 1) / BK;
+        // dZ_l is produced K block by K block (all 8 warps on one 64-column block at a time) so that the next
+        // step's MMAs and the block's TMA store start while the remaining blocks are still being masked
+        for (int kb = 0; kb < nkb_out; ++kb) {
+          const int cb = kb * BK;
+          const int rem = (N - cb) < BK ? (N - cb) : BK;
+          const int h0 = rem < 32 ? rem : 32;
+          const int c_begin = half ? cb + h0 : cb;
+          const int c_end = half ? cb + rem : cb + h0;
+          for (int c = c_begin; c < c_end; c += 16) {
+            float f[16];
+            if (top) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.f;
+#pragma unroll
+              for (int j = 0; j < NH; ++j) {
+                const float4* w4 = reinterpret_cast<const float4*>(head_w_s + j * MAXW + c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float4 w = w4[i];
+                  f[4 * i] = fmaf(dh[j], w.x, f[4 * i]);
+                  f[4 * i + 1] = fmaf(dh[j], w.y, f[4 * i + 1]);
+                  f[4 * i + 2] = fmaf(dh[j], w.z, f[4 * i + 2]);
+                  f[4 * i + 3] = fmaf(dh[j], w.w, f[4 * i + 3]);
+                }
+              }
+            } else {
+              uint32_t v[16];
+              tmem_ld16(taddr + (uint32_t)c, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            }
+            const int j0 = (c & 63) >> 3;
+            const int off0 = kb * A_KB_BYTES + row * 128 + ((j0 ^ (row & 7)) << 4);
+            const int off1 = kb * A_KB_BYTES + row * 128 + (((j0 + 1) ^ (row & 7)) << 4);
+            uint4 m0v = *reinterpret_cast<const uint4*>(smM + off0);
+            uint4 m1v = *reinterpret_cast<const uint4*>(smM + off1);
+            const uint32_t mk[8] = {m0v.x, m0v.y, m0v.z, m0v.w, m1v.x, m1v.y, m1v.z, m1v.w};
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float a = bf16_lo(mk[i]) > 0.f ? f[2 * i] : 0.f;
+              float b = bf16_hi(mk[i]) > 0.f ? f[2 * i + 1] : 0.f;
+              pk[i] = pack_bf16(a, b);
+            }
+            *reinterpret_cast<uint4*>(smA + off0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(smA + off1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_sync();
+          if (t == 0) {
+            if (mma_follows) mbar_arrive(bars + C_ACTREADY + kb);
+            if (p.weight_grads) {
+              tma_store_3d(&maps.dz[l], smA + kb * A_KB_BYTES, cb, m0, e);
+              tma_store_commit();
+            }
+          }
+        }
+        if (!top) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          epi_sync();
+          if (t == 0) mbar_arrive(bars + C_TEMPTY + buf);  // every thread has drained this accumulator buffer
         }
         if (!top) ++g;
         stores_pending = p.weight_grads != 0;
