@@ -254,7 +254,8 @@ class CQLImpl(DDPGBaseImpl):
         lp = self.ws("xf_lp", 4, B * N)
         lpm = self.ws("xf_lpm", 3, B)  # soft-backup, actor, temp log-probs
         done = self.ws("xf_done", 4, dtype=torch.int32)
-        inv_b = 1.0 / B
+        dp = self.world_size > 1  # sharded minibatch: sums / gradients are all-reduced between the partial kernels
+        inv_b = 1.0 / (B * self.world_size)
         mask = 0
         for c in [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else []):
             mask |= 1 << c
@@ -276,8 +277,16 @@ class CQLImpl(DDPGBaseImpl):
         q_net = self._q_func
         # ---- side branch (independent of the importance-sampling pass): temperature step, target critics
         side = self._side_stream()
+        if do_temp and dp:
+            # NCCL calls of one communicator must be issued in one order on every rank: keep them on the main
+            # stream (graph branches could reorder them); per-rank partial loss (== gradient) -> all-reduce -> Adam
+            L.sac_temp_loss(lpm[2].data_ptr(), lt.ptr("p"), B, A, inv_b, self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 0, st)
+            self._allreduce(lt.buf[4:5])
+            L.copy_d2d(self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 4, st)
+            L.scalar_adam(lt.ptr("p"), lt.ptr("g"), lt.ptr("m"), lt.ptr("v"), self.counter_ptr(C_TEMP),
+                          self._temp_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_TEMP), st)
         L.stream_fork(st, side)
-        if do_temp:
+        if do_temp and not dp:
             L.sac_temp_step(lpm[2].data_ptr(), lt.buf.data_ptr(), self.counter_ptr(C_TEMP), B, A, inv_b,
                             self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS), self.metric_ptr(M_TEMP), side)
         ctx_t = q_net.ctx("tq", B, E, False)
@@ -291,28 +300,54 @@ class CQLImpl(DDPGBaseImpl):
         ctx = q_net.ctx("is2", G * R, E, True)
         q = self.ws("is2_q", E, G * R)
         q_net.forward("params", None, 0, G * R, ctx, q, st, x_bf16=(X.data_ptr(), ld), save_rows=R)
-        if do_alpha:
+        if do_alpha and not dp:
             L.cql_loss_step(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma,
                             lp[2].data_ptr(), lp[3].data_ptr(), N, A, la.buf.data_ptr(), self._conservative_weight,
                             self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done.data_ptr(), B, E, inv_b, 1,
                             self.counter_ptr(C_ALPHA), self._alpha_learning_rate, self.metric_ptr(M_ALPHA_LOSS),
                             self.metric_ptr(M_ALPHA), st)
+        elif do_alpha:
+            L.critic_loss(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma, lp[2].data_ptr(),
+                          lp[3].data_ptr(), N, A, la.ptr("p"), self._conservative_weight, None, 0,
+                          self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, st)
+            self._allreduce(self._slots[32 + S_ALPHA:32 + S_ALPHA + 3])
+            L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
+                           self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
+            L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
+                          self._alpha_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_ALPHA), st)
         L.stream_join(st, side)
         dq = self.ws("is2_dq", E, R)
-        L.cql_loss_step(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
-                        q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
-                        self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.buf.data_ptr(),
-                        self._conservative_weight, self._alpha_threshold, dq.data_ptr(), R, self.sums_ptr(S_CRITIC),
-                        done.data_ptr() + 4, B, E, inv_b, 0, None, 0.0, self.metric_ptr(M_CRITIC), None, st)
+        if not dp:
+            L.cql_loss_step(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
+                            q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
+                            self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.buf.data_ptr(),
+                            self._conservative_weight, self._alpha_threshold, dq.data_ptr(), R,
+                            self.sums_ptr(S_CRITIC), done.data_ptr() + 4, B, E, inv_b, 0, None, 0.0,
+                            self.metric_ptr(M_CRITIC), None, st)
+        else:
+            L.critic_loss(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
+                          q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
+                          self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.ptr("p"), self._conservative_weight,
+                          dq.data_ptr(), R, self.sums_ptr(S_CRITIC), None, B, E, inv_b, 1, st)
         q_net.backward(None, 0, R, ctx, dq, st)
+        if dp:
+            # the loss partial sums only feed the reported metric: they ride along with the gradient exchange
+            self._allreduce(self._slots[32 + S_CRITIC:32 + S_CRITIC + 3])
+            L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
+                           self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
+            self._allreduce(q_net.arena.grads)
         q_net.adam(self._critic_learning_rate, st, tau=self._tau)
         # actor step on the updated critics
         ctx_a = q_net.ctx("aq", B, E, True)
         qa = self.ws("aq_q", E, B)
         q_net.forward("params", None, 0, B, ctx_a, qa, st, x_bf16=(X.data_ptr() + 2 * a_row0 * ld, ld))
         dqa = self.ws("a_dq", E, B)
-        L.sac_actor_step(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B, self.sums_ptr(S_ACTOR),
-                         done.data_ptr() + 8, self.metric_ptr(M_ACTOR), B, E, inv_b, st)
+        if not dp:
+            L.sac_actor_step(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B,
+                             self.sums_ptr(S_ACTOR), done.data_ptr() + 8, self.metric_ptr(M_ACTOR), B, E, inv_b, st)
+        else:
+            L.sac_actor_loss(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B,
+                             self.sums_ptr(S_ACTOR), B, E, inv_b, st)
         dxa = self.ws("a_dx", E, B, A)
         q_net.backward(None, 0, B, ctx_a, dqa, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
                        dx_cols=A)
@@ -320,6 +355,10 @@ class CQLImpl(DDPGBaseImpl):
         L.sac_actor_backward(head.data_ptr(), 2 * A, nv("actor"), dxa.data_ptr(), A, B * A, E, lt.ptr("p"),
                              dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
         self._policy_backward_rows(db, acts_p, dhead, B)
+        if dp:
+            self._allreduce(self._slots[32 + S_ACTOR:32 + S_ACTOR + 1])
+            L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
+            self._allreduce(self._policy.arena.grads)
         self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
 
     # ------------------------------------------------------------------ fused update (CQL._update, cql.py:234-258)
@@ -346,7 +385,7 @@ class CQLImpl(DDPGBaseImpl):
             self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn)
             self._p_actor(db, acts_p, head)
 
-        fused = (self._precision == "bf16" and self.world_size == 1 and self._q_func.fused_ok
+        fused = (self._precision == "bf16" and self._q_func.fused_ok
                  and self._policy.fused_ok and self.fused_glue)
         self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected, fused),
                          (lambda: self._program_fused(db, do_temp, do_alpha)) if fused else program)

@@ -56,16 +56,30 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     const float* nsrc = obs + (size_t)(r.g2 + 1) * O;
     float* d0 = out_obs + (size_t)b * O;
     float* d1 = out_next + (size_t)b * O;
-    for (int j = lane; j < O; j += 32) {
-      float x = __ldg(src + j);
-      float y = r.terminal ? 0.f : __ldg(nsrc + j);
-      if (sc_mean) {  // StandardScaler.transform fused (preprocessing/scalers.py:350-354)
-        float m = __ldg(sc_mean + j), s = __ldg(sc_std + j) + sc_eps;
-        x = __fdiv_rn(__fsub_rn(x, m), s);
-        y = __fdiv_rn(__fsub_rn(y, m), s);
+    // 4 x 32 columns per pass with every load issued before the first store (8 independent loads in flight per
+    // lane: the row gather is latency-bound on its index -> metadata -> row dependency chain)
+    for (int j0 = 0; j0 < O; j0 += 128) {
+      float xs[4], ys[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = j0 + lane + 32 * u;
+        xs[u] = j < O ? __ldg(src + j) : 0.f;
+        ys[u] = (j < O && !r.terminal) ? __ldg(nsrc + j) : 0.f;
       }
-      d0[j] = x;
-      d1[j] = y;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int j = j0 + lane + 32 * u;
+        if (j < O) {
+          float x = xs[u], y = ys[u];
+          if (sc_mean) {  // StandardScaler.transform fused (preprocessing/scalers.py:350-354)
+            float m = __ldg(sc_mean + j), s = __ldg(sc_std + j) + sc_eps;
+            x = __fdiv_rn(__fsub_rn(x, m), s);
+            y = __fdiv_rn(__fsub_rn(y, m), s);
+          }
+          d0[j] = x;
+          d1[j] = y;
+        }
+      }
     }
   }
   if (discrete) {

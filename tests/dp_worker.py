@@ -73,6 +73,33 @@ def run_gpu(world, rank):
             if err > 2e-5 * max(1.0, float(v.abs().max())):
                 ok = False
                 print(f"[rank {rank}] cql {name}/{k} err {err}", flush=True)
+    # ---- CQL, tensor-core mode: the fused program (one row-assembly kernel, fused forward / backward launches) with
+    # the loss tails split around the all-reduces; tolerance 1e-2 (bf16 operands)
+    O2, A2, B2, N2, H2 = 17, 6, 128, 6, [64, 64, 64]
+    orc = ou.CQL(O2, A2, hidden=H2, n_action_samples=N2, seed=13)
+    algo = CQL(actor_encoder_factory=H2, critic_encoder_factory=H2, batch_size=B2 // world, n_action_samples=N2,
+               use_gpu=rank, world_size=world, rank=rank, precision="bf16")
+    algo.create_impl((O2,), A2)
+    impl = algo.impl
+    for view, p in ((impl.q_function, orc.q), (impl.targ_q_function, orc.q), (impl.policy, orc.pi),
+                    (impl.targ_policy, orc.pi)):
+        view.load_state_dict(p)
+    for s in range(3):
+        arrays = synthetic(rs, B2, O2, A2)
+        noise = ou.Noise(seed=60 + s)
+        ref = orc.update(ou.Batch(arrays), noise)
+        local = [parallel.shard_noise(t, CQL_KINDS[k], B2, N2, world, rank) for k, t in zip(CQL_ORDER, noise.log)]
+        impl.inject_noise(local, B2 // world)
+        m = algo.update(SimpleNamespace(**shard_batch(arrays, world, rank)))
+        for k, v in ref.items():
+            if not close(float(m[k]), v, 1e-2):
+                ok = False
+                print(f"[rank {rank}] cql bf16 step {s} {k}: {float(m[k])} vs {v}", flush=True)
+    for k, v in orc.q.items():
+        g = impl.q_function.state_dict()[k].cpu()
+        if float((g - v.detach()).abs().max()) > 1e-2 * max(1.0, float(v.abs().max())):
+            ok = False
+            print(f"[rank {rank}] cql bf16 q/{k} mismatch", flush=True)
     # ---- TD3+BC (the actor's lambda = alpha / mean|Q| needs the GLOBAL mean)
     orc = ou.TD3PlusBC(O, A, hidden=H, seed=12)
     algo = TD3PlusBC(actor_encoder_factory=H, critic_encoder_factory=H, batch_size=B // world, scaler=None,
