@@ -260,6 +260,13 @@ class CQLImpl(DDPGBaseImpl):
         for c in [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else []):
             mask |= 1 << c
         L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
+        px = getattr(self, "_px", None) if dp else None
+        if px is not None:
+            # peers have finished reading last update's gradients -> zero them for this update's RED accumulation
+            for net in (self._q_func, self._policy):
+                _, fidx, _ = net._peer
+                L.peer_wait_zero(px.flags_ptrs, px.world, px.rank, fidx + 1, self.counter_ptr(C_DRAW),
+                                 net.arena.grads.data_ptr(), net.arena.size, st)
         self.fill_noise(B)
         acts_p, head = self._p_policy(db)
         nv = lambda name: self.noise_view(name, B).data_ptr()
@@ -281,7 +288,7 @@ class CQLImpl(DDPGBaseImpl):
             # NCCL calls of one communicator must be issued in one order on every rank: keep them on the main
             # stream (graph branches could reorder them); per-rank partial loss (== gradient) -> all-reduce -> Adam
             L.sac_temp_loss(lpm[2].data_ptr(), lt.ptr("p"), B, A, inv_b, self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 0, st)
-            self._allreduce(lt.buf[4:5])
+            self._small_allreduce(px, lt.buf[4:5], 0)
             L.copy_d2d(self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 4, st)
             L.scalar_adam(lt.ptr("p"), lt.ptr("g"), lt.ptr("m"), lt.ptr("v"), self.counter_ptr(C_TEMP),
                           self._temp_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_TEMP), st)
@@ -310,7 +317,7 @@ class CQLImpl(DDPGBaseImpl):
             L.critic_loss(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma, lp[2].data_ptr(),
                           lp[3].data_ptr(), N, A, la.ptr("p"), self._conservative_weight, None, 0,
                           self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, st)
-            self._allreduce(self._slots[32 + S_ALPHA:32 + S_ALPHA + 3])
+            self._small_allreduce(px, self._slots[32 + S_ALPHA:32 + S_ALPHA + 3], 1)
             L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
                            self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
             L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
@@ -332,11 +339,12 @@ class CQLImpl(DDPGBaseImpl):
         q_net.backward(None, 0, R, ctx, dq, st)
         if dp:
             # the loss partial sums only feed the reported metric: they ride along with the gradient exchange
-            self._allreduce(self._slots[32 + S_CRITIC:32 + S_CRITIC + 3])
+            self._small_allreduce(px, self._slots[32 + S_CRITIC:32 + S_CRITIC + 3], 2)
             L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
                            self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
-            self._allreduce(q_net.arena.grads)
-        q_net.adam(self._critic_learning_rate, st, tau=self._tau)
+            if px is None:
+                self._allreduce(q_net.arena.grads)
+        q_net.adam(self._critic_learning_rate, st, tau=self._tau, peer=self._peer_args(px, q_net))
         # actor step on the updated critics
         ctx_a = q_net.ctx("aq", B, E, True)
         qa = self.ws("aq_q", E, B)
@@ -356,10 +364,34 @@ class CQLImpl(DDPGBaseImpl):
                              dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
         self._policy_backward_rows(db, acts_p, dhead, B)
         if dp:
-            self._allreduce(self._slots[32 + S_ACTOR:32 + S_ACTOR + 1])
+            self._small_allreduce(px, self._slots[32 + S_ACTOR:32 + S_ACTOR + 1], 3)
             L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
-            self._allreduce(self._policy.arena.grads)
-        self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
+            if px is None:
+                self._allreduce(self._policy.arena.grads)
+        self._policy.adam(self._actor_learning_rate, st, tau=self._tau, peer=self._peer_args(px, self._policy))
+
+    # ---- NVLink peer-memory exchange (csrc/comm.cu): all-reduce fused into the Adam pass, no NCCL in the update
+    def _peer_setup(self):
+        from ... import parallel
+
+        px = parallel.peers(self._device)
+        if px is not None and getattr(self._q_func, "_peer", None) is None:
+            for net in (self._q_func, self._policy):   # collective: same order on every rank
+                net._peer = px.register_arena(net.arena.grads)
+        return px
+
+    def _peer_args(self, px, net):
+        if px is None:
+            return None
+        gptrs, fidx, cptr = net._peer
+        return (px, gptrs, fidx, cptr, self.counter_ptr(C_DRAW))
+
+    def _small_allreduce(self, px, t, channel: int):
+        if px is None:
+            self._allreduce(t)
+        else:
+            self._lib.peer_allreduce_small(t.data_ptr(), t.numel(), px.xchg_ptrs, px.flags_ptrs, px.world, px.rank,
+                                           channel, self.counter_ptr(C_DRAW), self._stream)
 
     # ------------------------------------------------------------------ fused update (CQL._update, cql.py:234-258)
     def update_fused(self, batch):
@@ -387,6 +419,8 @@ class CQLImpl(DDPGBaseImpl):
 
         fused = (self._precision == "bf16" and self._q_func.fused_ok
                  and self._policy.fused_ok and self.fused_glue)
+        if fused and self.world_size > 1 and not hasattr(self, "_px"):
+            self._px = self._peer_setup()  # collective IPC rendezvous: outside the dry pass / graph capture
         self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected, fused),
                          (lambda: self._program_fused(db, do_temp, do_alpha)) if fused else program)
         names = []

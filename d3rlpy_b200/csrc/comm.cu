@@ -93,3 +93,303 @@ extern "C" int d3b_comm_destroy(void* comm) {
   }
   return D3B_OK;
 }
+
+// =====================================================================================================
+// K10+K11 fused over NVLink peer memory: the data-parallel exchange without NCCL.
+//
+// Every rank maps the gradient arenas (and a small flag / exchange block) of all ranks of the box through CUDA
+// IPC.  The optimizer kernel itself performs the all-reduce: after a flag handshake it reads every rank's
+// gradient arena over NVLink in a fixed rank order (so all ranks compute bit-identical sums), applies Adam,
+// the Polyak target sync and the bf16 shadow refresh in the same pass — one kernel instead of
+// ncclAllReduce + Adam.  The few loss partial sums are exchanged by a single-warp kernel of the same kind.
+// Flags are monotonically increasing update epochs: ready[r] >= e  <=>  rank r's gradients of update e are
+// complete; done[r] >= e  <=>  rank r has finished reading everybody's gradients of update e (so they may
+// be zeroed for update e+1; that wait + the zeroing is the first kernel of the next update).
+// =====================================================================================================
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <vector>
+
+namespace {
+
+struct Imported { unsigned char handle[64]; void* base; };
+std::vector<Imported> g_imported;
+
+constexpr int kMaxRanks = 8;
+struct PeerPtrs {
+  const float* grads[kMaxRanks];
+  int* flags[kMaxRanks];
+  int world, rank;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded spin (a rank that never arrives becomes a trapped launch error instead of a hung box)
+__device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
+  for (unsigned spins = 0; ld_acquire_sys(p) < v; ++spins) {
+    if (spins > (1u << 22)) __trap();
+    __nanosleep(64);
+  }
+}
+
+// first kernel of an update: wait until every rank has finished reading this rank's gradients of the previous
+// update, then zero them (the backward kernels accumulate with RED)
+__global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int done_index, const int* epoch,
+                                                             float* __restrict__ grads, long long n) {
+  if (threadIdx.x == 0) {
+    const int prev = *epoch - 1;
+    for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + done_index, prev);
+  }
+  __syncthreads();
+  long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    ((float4*)grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// sum of a short vector over the ranks through the exchange block: slot = epoch & 1
+__global__ void peer_allreduce_small_kernel(float* __restrict__ vec, int n, PeerPtrs ps, int channel, const int* epoch) {
+  const int e = *epoch;
+  const int t = threadIdx.x;
+  float* mine = const_cast<float*>(ps.grads[ps.rank]) + ((channel * 2 + (e & 1)) * 16);
+  if (t < n) mine[t] = vec[t];
+  __threadfence_system();
+  __syncwarp();
+  if (t == 0) st_release_sys(ps.flags[ps.rank] + 2 * channel, e);
+  if (t < ps.world) wait_flag_ge(ps.flags[t] + 2 * channel, e);
+  __syncwarp();
+  if (t < n) {
+    float s = 0.f;
+    for (int r = 0; r < ps.world; ++r) {
+      const volatile float* src = ps.grads[r] + ((channel * 2 + (e & 1)) * 16);
+      s += src[t];
+    }
+    vec[t] = s;
+  }
+}
+
+struct AdamArgs {
+  float* p; float* g; float* m; float* v; float* targ;
+  long long n;
+  const int* step;
+  double lr, b1, b2, eps;
+  float tau;
+  __nv_bfloat16* sh_p; __nv_bfloat16* sh_t;
+};
+constexpr int MAX_SEG2 = 8;
+struct Segs2 {
+  long long param_off[MAX_SEG2], count[MAX_SEG2], shadow_off[MAX_SEG2];
+  int cols[MAX_SEG2], ld[MAX_SEG2];
+  int n;
+  long long member_size, shadow_member;
+};
+
+__device__ __forceinline__ float adam_one2(float p, float g, float& m, float& v, float w1, float fb2, float w2,
+                                           float feps, float neg_ss, float bc2_sqrt) {
+  m = __fmaf_rn(w1, __fsub_rn(g, m), m);
+  v = __fmul_rn(v, fb2);
+  v = __fadd_rn(v, __fmul_rn(__fmul_rn(w2, g), g));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), feps);
+  return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_ss, m), denom));
+}
+
+// all-reduce (over NVLink peer loads) + Adam + Polyak + bf16 shadow refresh in one pass
+__global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 segs, PeerPtrs ps, int flag_index,
+                                                             const int* epoch, unsigned* block_counter) {
+  const int e = *epoch;
+  __shared__ bool last_block;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(ps.flags[ps.rank] + flag_index, e);  // my gradients of update e are complete
+    }
+    for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + flag_index, e);
+  }
+  __syncthreads();
+  const int t = *a.step;
+  const double bc1 = 1.0 - pow(a.b1, (double)t), bc2 = 1.0 - pow(a.b2, (double)t);
+  const float w1 = (float)(1.0 - a.b1), fb2 = (float)a.b2, w2 = (float)(1.0 - a.b2), feps = (float)a.eps;
+  const float neg_ss = (float)(-(a.lr / bc1)), bc2s = (float)sqrt(bc2);
+  const float one_m_tau = (float)(1.0 - (double)a.tau);
+  const long long n4 = a.n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < ps.world; ++r) {  // fixed rank order: every rank computes the same sum bit for bit
+      float4 x = ((const float4*)ps.grads[r])[i];
+      G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+    }
+    float4 P = ((float4*)a.p)[i], M = ((float4*)a.m)[i], V = ((float4*)a.v)[i];
+    P.x = adam_one2(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.y = adam_one2(P.y, G.y, M.y, V.y, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.z = adam_one2(P.z, G.z, M.z, V.z, w1, fb2, w2, feps, neg_ss, bc2s);
+    P.w = adam_one2(P.w, G.w, M.w, V.w, w1, fb2, w2, feps, neg_ss, bc2s);
+    ((float4*)a.p)[i] = P;
+    ((float4*)a.m)[i] = M;
+    ((float4*)a.v)[i] = V;
+    float4 T = P;
+    if (a.targ) {
+      T = ((float4*)a.targ)[i];
+      T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(a.tau, P.x));
+      T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(a.tau, P.y));
+      T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(a.tau, P.z));
+      T.w = __fadd_rn(__fmul_rn(T.w, one_m_tau), __fmul_rn(a.tau, P.w));
+      ((float4*)a.targ)[i] = T;
+    }
+    if (a.sh_p) {
+      long long e0 = i << 2;
+      long long member = e0 / segs.member_size, off = e0 - member * segs.member_size;
+      int sidx = -1;
+#pragma unroll
+      for (int k = 0; k < MAX_SEG2; ++k)
+        if (k < segs.n && off >= segs.param_off[k] && off < segs.param_off[k] + segs.count[k]) sidx = k;
+      if (sidx >= 0) {
+        long long rel = off - segs.param_off[sidx];
+        int cols = segs.cols[sidx], ld = segs.ld[sidx];
+        long long base = member * segs.shadow_member + segs.shadow_off[sidx];
+        const float pv[4] = {P.x, P.y, P.z, P.w}, tv[4] = {T.x, T.y, T.z, T.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          long long r = rel + q;
+          if (r < segs.count[sidx]) {
+            long long row = r / cols;
+            int c = (int)(r - row * cols);
+            long long d = base + row * ld + c;
+            a.sh_p[d] = __float2bfloat16_rn(pv[q]);
+            if (a.sh_t && a.targ) a.sh_t[d] = __float2bfloat16_rn(tv[q]);
+          }
+        }
+      }
+    }
+  }
+  // completion: the last block of this rank announces that it no longer needs anybody's gradients of update e
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned prev = atomicAdd(block_counter, 1u);
+    last_block = (prev == gridDim.x - 1);
+    if (last_block) {
+      *block_counter = 0u;
+      __threadfence_system();
+      st_release_sys(ps.flags[ps.rank] + flag_index + 1, e);
+    }
+  }
+}
+
+int fill_peers(PeerPtrs& ps, const void* const* grads_host, const void* const* flags_host, int world, int rank) {
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !grads_host || !flags_host) return -1;
+  ps.world = world; ps.rank = rank;
+  for (int r = 0; r < kMaxRanks; ++r) {
+    ps.grads[r] = r < world ? (const float*)grads_host[r] : nullptr;
+    ps.flags[r] = r < world ? (int*)flags_host[r] : nullptr;
+    if (r < world && (!ps.grads[r] || !ps.flags[r])) return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int d3b_peer_export(const void* ptr, void* handle_out_64, int64_t* offset_out) {
+  D3B_REQUIRE(ptr && handle_out_64 && offset_out, "peer_export: null pointer");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  // resolved through the runtime so that libd3b.so has no link-time dependency on libcuda.so (CPU-only build hosts)
+  typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static GetRangeFn get_range = nullptr;
+  if (!get_range) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return d3b::set_err(D3B_ERR_CUDA, "peer_export: cuMemGetAddressRange not available from the driver");
+    get_range = (GetRangeFn)fp;
+  }
+  CUresult r = get_range(&base, &size, (CUdeviceptr)ptr);
+  if (r != CUDA_SUCCESS) return d3b::set_err(D3B_ERR_CUDA, "peer_export: cuMemGetAddressRange failed (%d)", (int)r);
+  cudaIpcMemHandle_t h;
+  D3B_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out_64, &h, 64);
+  *offset_out = (int64_t)((CUdeviceptr)ptr - base);
+  return D3B_OK;
+}
+
+extern "C" int d3b_peer_import(const void* handle_64, int64_t offset, void** ptr_out) {
+  D3B_REQUIRE(handle_64 && ptr_out && offset >= 0, "peer_import: bad arguments");
+  for (const Imported& im : g_imported) {
+    if (memcmp(im.handle, handle_64, 64) == 0) {
+      *ptr_out = (char*)im.base + offset;
+      return D3B_OK;
+    }
+  }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_64, 64);
+  void* base = nullptr;
+  D3B_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  Imported im;
+  memcpy(im.handle, handle_64, 64);
+  im.base = base;
+  g_imported.push_back(im);
+  *ptr_out = (char*)base + offset;
+  return D3B_OK;
+}
+
+extern "C" int d3b_peer_wait_zero(const void* const* flags_host, int world, int rank, int done_index,
+                                  const int* epoch, float* grads, int64_t n, void* stream) {
+  D3B_REQUIRE(epoch && grads && n >= 0 && n % 4 == 0, "peer_wait_zero: bad arguments");
+  PeerPtrs ps{};
+  D3B_REQUIRE(fill_peers(ps, flags_host, flags_host, world, rank) == 0, "peer_wait_zero: bad peer table");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 2 * d3b::kNumSM) blocks = 2 * d3b::kNumSM;
+  if (blocks < 1) blocks = 1;
+  peer_wait_zero_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ps, done_index, epoch, grads, (long long)n);
+  return d3b::check_launch("peer_wait_zero");
+}
+
+extern "C" int d3b_peer_allreduce_small(float* vec, int n, const void* const* xchg_host, const void* const* flags_host,
+                                        int world, int rank, int channel, const int* epoch, void* stream) {
+  D3B_REQUIRE(vec && n >= 1 && n <= 16 && channel >= 0 && channel < 4 && epoch, "peer_allreduce_small: bad arguments");
+  PeerPtrs ps{};
+  D3B_REQUIRE(fill_peers(ps, xchg_host, flags_host, world, rank) == 0, "peer_allreduce_small: bad peer table");
+  peer_allreduce_small_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vec, n, ps, channel, epoch);
+  return d3b::check_launch("peer_allreduce_small");
+}
+
+// adam_step_shadow with the gradient all-reduce fused in (see the block comment above).  flag_index: position of
+// this arena's {ready, done} pair in the flag block; block_counter: one zero-initialised uint32 per arena.
+extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
+                                  const int* step, double lr, double beta1, double beta2, double eps, float tau,
+                                  void* shadow_params, void* shadow_target, const int64_t* table_host, int n_segments,
+                                  int64_t member_size, int64_t shadow_member, const void* const* grads_host,
+                                  const void* const* flags_host, int world, int rank, int flag_index,
+                                  const int* epoch, void* block_counter, void* stream) {
+  D3B_REQUIRE(n >= 0 && n % 4 == 0 && params && exp_avg && exp_avg_sq && step && epoch && block_counter,
+              "adam_step_peer: bad arguments");
+  if (n == 0) return D3B_OK;
+  PeerPtrs ps{};
+  D3B_REQUIRE(fill_peers(ps, grads_host, flags_host, world, rank) == 0, "adam_step_peer: bad peer table");
+  AdamArgs a{};
+  a.p = params; a.g = nullptr; a.m = exp_avg; a.v = exp_avg_sq; a.targ = target; a.n = n; a.step = step;
+  a.lr = lr; a.b1 = beta1; a.b2 = beta2; a.eps = eps; a.tau = tau;
+  a.sh_p = (__nv_bfloat16*)shadow_params; a.sh_t = (__nv_bfloat16*)shadow_target;
+  Segs2 segs{};
+  if (shadow_params) {
+    D3B_REQUIRE(table_host && n_segments >= 1 && n_segments <= MAX_SEG2 && member_size > 0, "adam_step_peer: bad shadow table");
+    segs.n = n_segments; segs.member_size = member_size; segs.shadow_member = shadow_member;
+    for (int k = 0; k < n_segments; ++k) {
+      const int64_t* t = table_host + 5 * k;
+      segs.param_off[k] = t[0]; segs.count[k] = t[1] * t[2]; segs.cols[k] = (int)t[2];
+      segs.shadow_off[k] = t[3]; segs.ld[k] = (int)t[4];
+    }
+  }
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 4 * d3b::kNumSM) blocks = 4 * d3b::kNumSM;  // every block spins on the flags: all must be resident
+  adam_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, segs, ps, flag_index, epoch,
+                                                                           (unsigned*)block_counter);
+  return d3b::check_launch("adam_step_peer");
+}

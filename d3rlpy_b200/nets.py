@@ -366,9 +366,32 @@ class DenseNet:
                             0, None, 0, 0, None, 0, 0, None, 0, 0, _p(dx), lddx, stride_dx, 0, stream)
 
     # ------------------------------------------------------------------ optimizer
-    def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
+    def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None, peer=None):
+        """peer = (PeerExchange, grads pointer table, flag index, block-counter pointer, epoch pointer): the gradient
+        all-reduce over NVLink peer memory is fused into the optimizer pass (no NCCL call)."""
         a = self.arena
         sync = tau is not None and a.target is not None
+        if peer is not None:
+            import ctypes
+
+            px, gptrs, fidx, cptr, eptr = peer
+            shadow = self.precision == "bf16" and self.fused_ok and self.head_out <= 16
+            seg, nseg = None, 0
+            if shadow:
+                t = self._table
+                nseg = t.shape[0]
+                seg = (ctypes.c_int64 * (5 * nseg))(*[int(v) for r in t.tolist() for v in r[:5]])
+            lib().adam_step_peer(_p(a.params), _p(a.exp_avg), _p(a.exp_avg_sq), _p(a.target) if sync else None, a.size,
+                                 _p(a.step), lr, betas[0], betas[1], eps, tau if sync else 0.0,
+                                 _p(self.shadow) if shadow else None,
+                                 _p(self.shadow_target) if shadow and sync and self.shadow_target is not None else None,
+                                 seg, nseg, a.member_size, self.shadow_member if shadow else 0, gptrs, px.flags_ptrs,
+                                 px.world, px.rank, fidx, eptr, cptr, stream)
+            if not shadow:
+                self.refresh_shadow("params", stream)
+                if sync:
+                    self.refresh_shadow("target", stream)
+            return
         if self.precision == "bf16" and self.fused_ok and self.head_out <= 16:
             # the fused kernels only read the row-major W shadows: refresh them inside the Adam pass
             import ctypes

@@ -101,3 +101,67 @@ def destroy() -> None:
     if _COMM is not None:
         lib().comm_destroy(_COMM)
         _COMM = None
+
+
+# ----------------------------------------------------------------------------------- NVLink peer-memory exchange
+class PeerExchange:
+    """Maps device buffers of every rank of the box into this process (CUDA IPC) so that kernels can read the
+    other ranks' gradient arenas over NVLink directly (csrc/comm.cu: adam_allreduce / peer_allreduce_small).
+    All methods are collective: every rank must call them in the same order."""
+
+    N_FLAGS = 32          # int32 per rank: {ready, done} pairs; channels 0-3 small vectors, 4.. gradient arenas
+    XCHG_FLOATS = 4 * 2 * 16
+
+    def __init__(self, world_size: int, rank: int, device):
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise D3BError("PeerExchange needs an initialised torch.distributed process group for the rendezvous")
+        self.world, self.rank = world_size, rank
+        self.flags = torch.zeros(self.N_FLAGS, dtype=torch.int32, device=device)
+        self.xchg = torch.zeros(self.XCHG_FLOATS, dtype=torch.float32, device=device)
+        self.counters = torch.zeros(8, dtype=torch.int32, device=device)  # block counters of the fused Adam kernels
+        torch.cuda.synchronize(device)
+        self.flags_ptrs = self.register(self.flags)
+        self.xchg_ptrs = self.register(self.xchg)
+        self._next_arena = 0
+
+    def register(self, t: torch.Tensor):
+        """Returns a ctypes array of `world` device pointers: t of rank r as seen from this process."""
+        import torch.distributed as dist
+
+        L = lib()
+        handle = (ctypes.c_uint8 * 64)()
+        off = ctypes.c_int64()
+        L.peer_export(t.data_ptr(), ctypes.addressof(handle), ctypes.byref(off))
+        mine = (bytes(handle), int(off.value))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine)
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r, (h, o) in enumerate(everyone):
+            if r == self.rank:
+                ptrs[r] = t.data_ptr()
+            else:
+                buf = (ctypes.c_uint8 * 64).from_buffer_copy(h)
+                out = ctypes.c_void_p()
+                L.peer_import(ctypes.addressof(buf), o, ctypes.byref(out))
+                ptrs[r] = out.value
+        return ptrs
+
+    def register_arena(self, grads: torch.Tensor):
+        """Gradient arena -> (peer pointer table, flag index of its {ready, done} pair, block counter pointer)."""
+        i = self._next_arena
+        self._next_arena += 1
+        assert 8 + 2 * i + 1 < self.N_FLAGS
+        return self.register(grads), 8 + 2 * i, self.counters.data_ptr() + 4 * i
+
+
+_PEERS: Optional[PeerExchange] = None
+
+
+def peers(device=None) -> Optional[PeerExchange]:
+    """The process-wide peer exchange (created on first use when world_size > 1 and D3B_PEER != 0)."""
+    global _PEERS
+    if _PEERS is None and _WORLD > 1 and os.environ.get("D3B_PEER", "1") != "0":
+        _PEERS = PeerExchange(_WORLD, _RANK, device)
+    return _PEERS

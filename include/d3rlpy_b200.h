@@ -317,6 +317,22 @@ int d3b_comm_init(const void* id_128, int world_size, int rank, void** comm_out)
 int d3b_allreduce_sum(void* comm, float* buf, int64_t n, void* stream);
 int d3b_comm_destroy(void* comm);
 
+/* ---- K10+K11 fused over NVLink peer memory (CUDA IPC): the optimizer kernel reads every rank's gradient arena
+ * itself (fixed rank order => bit-identical sums on all ranks) and applies Adam + Polyak + shadow refresh — no
+ * NCCL call on the update path.  flags: per-rank int32 block, {ready, done} epoch pairs; epoch: device counter of
+ * the update.  peer_export/import map a device allocation into the other ranks of the box. */
+int d3b_peer_export(const void* ptr, void* handle_out_64, int64_t* offset_out);
+int d3b_peer_import(const void* handle_64, int64_t offset, void** ptr_out);
+int d3b_peer_wait_zero(const void* const* flags_host, int world, int rank, int done_index, const int* epoch,
+                       float* grads, int64_t n, void* stream);
+int d3b_peer_allreduce_small(float* vec, int n, const void* const* xchg_host, const void* const* flags_host, int world,
+                             int rank, int channel, const int* epoch, void* stream);
+int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, float* target, int64_t n, const int* step,
+                       double lr, double beta1, double beta2, double eps, float tau, void* shadow_params,
+                       void* shadow_target, const int64_t* table_host, int n_segments, int64_t member_size,
+                       int64_t shadow_member, const void* const* grads_host, const void* const* flags_host, int world,
+                       int rank, int flag_index, const int* epoch, void* block_counter, void* stream);
+
 /* ---- plumbing: staged copies, CUDA-graph capture of a whole update ------------------ */
 int d3b_memset_zero(void* ptr, int64_t bytes, void* stream);
 int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream);
