@@ -165,8 +165,18 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" :::
 enum { B_WFULL = 0, B_WEMPTY = W_STAGES_MAX, B_XFULL = 2 * W_STAGES_MAX, B_AFREE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
        B_ACTREADY = B_TEMPTY + 2, B_COUNT = B_ACTREADY + MAX_KB };
 
-template <int NH>
-__global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+// EW = number of epilogue warps: 16 (four per TMEM lane quarter, one 16-column chunk of every K block each) hides the
+// tcgen05.ld latency that bounds the epilogue when the per-thread state is small (NH <= 1), 8 otherwise.
+template <int EW>
+__device__ __forceinline__ void epi_sync_n() {
+  asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
+}
+
+template <int NH, int EW>
+__global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+  constexpr int EPI = EW * 32;          // epilogue threads
+  constexpr int NSUB = EW / 4;          // column sub-ranges per K block
+  constexpr int SUBW = BK / NSUB;       // columns of a K block owned by one sub-range
   constexpr int W_STAGES = NH <= 16 ? 4 : 3;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -175,8 +185,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   uint8_t* smW = smem + MAX_KB * A_KB_BYTES;
   float* head_w_s = (float*)(smW + W_STAGES * W_STAGE_BYTES);  // [NH][MAXW]
   float* bias_s = head_w_s + NH * MAXW;                        // [MAX_LAYERS][MAXW]
-  float* head_part = bias_s + MAX_LAYERS * MAXW;               // [128][NH]
-  uint64_t* bars = (uint64_t*)(head_part + BM * NH);
+  float* head_part = bias_s + MAX_LAYERS * MAXW;               // [NSUB-1][128][NH]
+  uint64_t* bars = (uint64_t*)(head_part + (NSUB - 1) * BM * NH);
   uint32_t* tmem_slot = (uint32_t*)(bars + B_COUNT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +198,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == EW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(512)
                  : "memory");
@@ -203,7 +213,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-  if (warp == 8) {
+  if (warp == EW) {
     // ================= TMA producer: x tile, then the weight K blocks of every layer through the ring
     if (lane == 0) {
       uint32_t wi = 0, it = 0;
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == EW + 1) {
     // ================= MMA issuer
     if (lane == 0) {
       uint32_t g = 0, wi = 0, it = 0;
@@ -266,9 +276,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
       }
     }
   } else {
-    // ================= epilogue warps 0-7: thread = accumulator row 32*(warp%4)+lane, column half warp/4
+    // ================= epilogue warps: thread = accumulator row 32*(warp%4)+lane, column sub-range warp/4 of each K block
     const int t = threadIdx.x;
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;
     uint32_t g = 0;
     int cur_member = -1;
@@ -276,12 +286,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
       if (e != cur_member) {
-        epi_sync();  // nobody is still reading the previous member's constants
+        epi_sync_n<EW>();  // nobody is still reading the previous member's constants
         for (int l = 0; l < L; ++l) {
           const float* b = p.bias[l] + (long long)e * p.bias_stride;
-          for (int j = t; j < p.N[l]; j += EPI_THREADS) bias_s[l * MAXW + j] = __ldg(b + j);
+          for (int j = t; j < p.N[l]; j += EPI) bias_s[l * MAXW + j] = __ldg(b + j);
         }
-        if (NH > 0 && p.n_head > 0) {
+        if (NH > 0 && p.n_head > 0 && t < MAXW) {
           const int feat = p.N[L - 1];
           const float* hw = p.head_w + (long long)e * p.head_stride;
           // NH x 256 staging: all loads of a thread are issued before the stores (NH global loads in flight)
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
 #pragma unroll
           for (int j = 0; j < NH; ++j) head_w_s[t * NH + j] = tmp[j];  // [column][head]: one row of NH weights per column
         }
-        epi_sync();
+        epi_sync_n<EW>();
         cur_member = e;
       }
       for (int l = 0; l < L; ++l, ++g) {
@@ -306,23 +316,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
         if (last && !store && t == 0) mbar_arrive(bars + B_AFREE);  // operand buffer no longer needed by this unit
         if (writeA && stores_pending) {
           if (t == 0) tma_store_wait_read();  // the previous layer's TMA stores finished reading the buffer
-          epi_sync();
+          epi_sync_n<EW>();
           stores_pending = false;
         }
         const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
         float acc[NH > 0 ? NH : 1];
 #pragma unroll
         for (int j = 0; j < (NH > 0 ? NH : 1); ++j) acc[j] = 0.f;
-        // The 64-column K blocks of the operand buffer are produced IN ORDER by all 8 warps (column half `half`
-        // of each block), so that the next layer's MMAs on block kb start while blocks kb+1.. are still in
+        // The 64-column K blocks of the operand buffer are produced IN ORDER by all epilogue warps (column
+        // sub-range `sub` of each block), so that the next layer's MMAs on block kb start while blocks kb+1.. are still in
         // the epilogue, and the block's TMA store is issued as soon as it is complete.
         const int nkb_out = (N + BK - 1) / BK;
         for (int kb = 0; kb < nkb_out; ++kb) {
           const int cb = kb * BK;
           const int rem = (N - cb) < BK ? (N - cb) : BK;
-          const int h0 = rem < 32 ? rem : 32;
-          const int c_begin = half ? cb + h0 : cb;
-          const int c_end = half ? cb + rem : cb + h0;
+          const int lo = sub * SUBW, hi = (sub + 1) * SUBW;
+          const int c_begin = cb + (lo < rem ? lo : rem);
+          const int c_end = cb + (hi < rem ? hi : rem);
           for (int c = c_begin; c < c_end; c += 16) {
             uint32_t v[16];
             tmem_ld16(taddr + (uint32_t)c, v);
@@ -374,7 +384,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
           if (writeA) {
             // block kb of H_l is complete in shared memory: hand it to the MMA issuer / the TMA store engine
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            epi_sync();
+            epi_sync_n<EW>();
             if (t == 0) {
               if (!last) mbar_arrive(bars + B_ACTREADY + kb);
               if (store) {
@@ -385,11 +395,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (NH > 0 && last && p.n_head > 0 && half == 1) {
+        if (NH > 0 && last && p.n_head > 0 && sub > 0) {
 #pragma unroll
-          for (int j = 0; j < NH; ++j) head_part[row * NH + j] = acc[j];
+          for (int j = 0; j < NH; ++j) head_part[((sub - 1) * BM + row) * NH + j] = acc[j];
         }
-        epi_sync();
+        epi_sync_n<EW>();
         if (dbg && t == 0 && g < 6) dbg[3 + 2 * g] = clock64();      // epilogue of layer g done
         if (t == 0) {
           mbar_arrive(bars + B_TEMPTY + buf);  // every thread has drained this accumulator buffer
@@ -399,19 +409,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
           }
         }
         stores_pending = store && !last;
-        if (NH > 0 && last && p.n_head > 0 && half == 0 && m0 + row < p.rows) {
+        if (NH > 0 && last && p.n_head > 0 && sub == 0 && m0 + row < p.rows) {
           const float* hb = p.head_b + (long long)e * p.head_stride;
           float* o = p.head_out + ((long long)e * p.rows + m0 + row) * p.n_head;
 #pragma unroll
           for (int j = 0; j < NH; ++j) {
             if (j < p.n_head) {
-              float val = acc[j] + head_part[row * NH + j] + __ldg(hb + j);
+              float val = acc[j] + __ldg(hb + j);
+#pragma unroll
+              for (int s2 = 0; s2 < NSUB - 1; ++s2) val += head_part[(s2 * BM + row) * NH + j];
               o[j] = p.head_tanh ? tanhf(val) : val;
             }
           }
         }
       }
-      if (L == 1) epi_sync();  // head_part is rewritten by the very next layer
+      if (L == 1) epi_sync_n<EW>();  // head_part is rewritten by the very next layer
     }
     if (t == 0) tma_store_wait_read();  // shared memory may be released once the bulk stores have read it
     if (dbg && t == 0) dbg[14] = clock64();
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(const __grid_c
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[15] = clock64();
-  if (warp == 9) {
+  if (warp == EW + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
@@ -822,21 +834,26 @@ int make_map(CUtensorMap* map, const void* base, int cols, int rows, int members
 }
 
 template <int NH>
+constexpr int fwd_epi_warps() { return NH <= 1 ? 16 : 8; }
+
+template <int NH>
 size_t fwd_smem() {
   constexpr int W_STAGES = NH <= 16 ? 4 : 3;
   return 1024 + (size_t)MAX_KB * A_KB_BYTES + (size_t)W_STAGES * W_STAGE_BYTES +
-         sizeof(float) * ((size_t)NH * MAXW + MAX_LAYERS * MAXW + (size_t)BM * NH) + 8 * B_COUNT + 64;
+         sizeof(float) * ((size_t)NH * MAXW + MAX_LAYERS * MAXW + (size_t)(fwd_epi_warps<NH>() / 4 - 1) * BM * NH) +
+         8 * B_COUNT + 64;
 }
 
 template <int NH>
 int launch_fwd(const Maps& maps, const FwdParams& p, int grid, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    D3B_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    D3B_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<NH, fwd_epi_warps<NH>()>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fwd_smem<NH>()));
     attr_set = true;
   }
-  launch_pdl(mlp_forward_kernel<NH>, dim3(grid), dim3(NTHREADS), fwd_smem<NH>(), st, maps, p);
+  launch_pdl(mlp_forward_kernel<NH, fwd_epi_warps<NH>()>, dim3(grid), dim3(fwd_epi_warps<NH>() * 32 + 64), fwd_smem<NH>(), st,
+             maps, p);
   return check_launch("mlp_forward_bf16");
 }
 
