@@ -125,7 +125,9 @@ class AlgoBase:
         history: List[Dict[str, float]] = []
         acc: Dict[str, List[float]] = {}
         for step in range(1, n_steps + 1):
-            idx = np.array([rng.randint(len(replay)) for _ in range(self._batch_size)], dtype=np.int64)
+            # one vectorised draw == batch_size sequential `np.random.randint(n)` calls of RandomIterator
+            # (iterators/random_iterator.py:38-41): the legacy RandomState consumes the stream element by element
+            idx = rng.randint(len(replay), size=self._batch_size).astype(np.int64)
             batch = TransitionMiniBatch.from_indices(replay, idx, n_frames=self._n_frames, n_steps=self._n_steps,
                                                      gamma=self._gamma, scaler=self._scaler,
                                                      out=self._impl.device_batch(self._batch_size))

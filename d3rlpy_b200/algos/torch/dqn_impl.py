@@ -50,7 +50,7 @@ class DQNImpl(ImplBase):
             self._q_func = ConvNet(self._observation_shape, [("_fc", A)], E, self._device,
                                    feature_size=self._feature_size, filters=self._filters,
                                    member_key="_q_funcs.{e}.{name}", with_target=True, seed_gen=self._gen,
-                                   precision="fp32", input_divisor=255.0 if is_pixel_scaler else 1.0)
+                                   precision=self._precision, input_divisor=255.0 if is_pixel_scaler else 1.0)
         else:
             self._q_func = DenseNet(self._observation_shape[0], self._hidden, [("_fc", A)], E, self._device,
                                     trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}", with_target=True,

@@ -24,6 +24,10 @@ template <>
 __device__ __forceinline__ float load_scaled<float>(const float* p, float scale) {
   return __ldg(p) / scale;
 }
+template <>
+__device__ __forceinline__ float load_scaled<__nv_bfloat16>(const __nv_bfloat16* p, float scale) {
+  return __bfloat162float(*p) / scale;
+}
 
 __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
@@ -60,15 +64,15 @@ __global__ void __launch_bounds__(256) im2col_kernel(const In* __restrict__ x, l
 }
 
 // dx[e][(b,ih,iw)][ic] = [y_prev > 0] * sum_{kh,kw : (ih-kh)%s==0, (iw-kw)%s==0} dpatch[e][(b,oh,ow)][ic*k*k+kh*k+kw]
-template <typename Mask>
+template <typename Mask, typename Out>
 __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ dpatch, long long ldp,
                                                      long long sp_member, const Mask* __restrict__ y_prev,
-                                                     long long ldy, long long sy_member, float* __restrict__ dx,
+                                                     long long ldy, long long sy_member, Out* __restrict__ dx,
                                                      long long lddx, long long sdx_member, int images, int C, int H,
                                                      int W, int OH, int OW, int ksz, int stride) {
   const long long total = (long long)images * H * W * C;
   const float* pe = dpatch + (long long)blockIdx.y * sp_member;
-  float* de = dx + (long long)blockIdx.y * sdx_member;
+  Out* de = dx + (long long)blockIdx.y * sdx_member;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     int ic = (int)(idx % C);
@@ -91,7 +95,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const float* __restrict__ d
         }
       }
     }
-    de[pix * lddx + ic] = acc;
+    store_out(de + pix * lddx + ic, acc);
   }
 }
 
@@ -123,8 +127,11 @@ extern "C" int d3b_im2col(const void* x, int x_is_u8, int64_t stride_x, int64_t 
 #define LAUNCH(IN, OUT)                                                                                          \
   im2col_kernel<IN, OUT><<<grid, 256, 0, ST>>>((const IN*)x, stride_x, sb, sc, sh, sw, (OUT*)out, ldo, stride_o, \
                                                images, channels, OH, OW, ksize, stride, divisor, K_pad)
-  if (x_is_u8 && out_is_bf16) LAUNCH(uint8_t, __nv_bfloat16);
-  else if (x_is_u8) LAUNCH(uint8_t, float);
+  // x_is_u8: 0 = fp32 input, 1 = uint8 input, 2 = bf16 input (NHWC activations of the tensor-core path)
+  if (x_is_u8 == 1 && out_is_bf16) LAUNCH(uint8_t, __nv_bfloat16);
+  else if (x_is_u8 == 1) LAUNCH(uint8_t, float);
+  else if (x_is_u8 == 2 && out_is_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (x_is_u8 == 2) LAUNCH(__nv_bfloat16, float);
   else if (out_is_bf16) LAUNCH(float, __nv_bfloat16);
   else LAUNCH(float, float);
 #undef LAUNCH
@@ -132,7 +139,7 @@ extern "C" int d3b_im2col(const void* x, int x_is_u8, int64_t stride_x, int64_t 
 }
 
 extern "C" int d3b_col2im(const float* dpatch, int64_t ldp, int64_t stride_p, const void* y_prev, int y_is_bf16,
-                          int64_t ldy, int64_t stride_y, float* dx, int64_t lddx, int64_t stride_dx, int images,
+                          int64_t ldy, int64_t stride_y, void* dx, int64_t lddx, int64_t stride_dx, int images,
                           int channels, int height, int width, int ksize, int stride, int members, void* stream) {
   D3B_REQUIRE(images >= 0 && channels >= 1 && ksize >= 1 && stride >= 1 && members >= 1, "col2im: bad sizes");
   D3B_REQUIRE(height >= ksize && width >= ksize, "col2im: kernel larger than the input");
@@ -141,12 +148,14 @@ extern "C" int d3b_col2im(const float* dpatch, int64_t ldp, int64_t stride_p, co
   int OH = (height - ksize) / stride + 1, OW = (width - ksize) / stride + 1;
   long long total = (long long)images * height * width * channels;
   dim3 grid(grid_for(total), members);
+  // bf16 mask => tensor-core path: the gradient is written as bf16 too (operand of the next layer's GEMMs)
   if (y_is_bf16)
-    col2im_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(dpatch, ldp, stride_p, (const __nv_bfloat16*)y_prev, ldy,
-                                                       stride_y, dx, lddx, stride_dx, images, channels, height, width,
-                                                       OH, OW, ksize, stride);
+    col2im_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST>>>(
+        dpatch, ldp, stride_p, (const __nv_bfloat16*)y_prev, ldy, stride_y, (__nv_bfloat16*)dx, lddx, stride_dx, images,
+        channels, height, width, OH, OW, ksize, stride);
   else
-    col2im_kernel<float><<<grid, 256, 0, ST>>>(dpatch, ldp, stride_p, (const float*)y_prev, ldy, stride_y, dx, lddx,
-                                               stride_dx, images, channels, height, width, OH, OW, ksize, stride);
+    col2im_kernel<float, float><<<grid, 256, 0, ST>>>(dpatch, ldp, stride_p, (const float*)y_prev, ldy, stride_y,
+                                                      (float*)dx, lddx, stride_dx, images, channels, height, width, OH,
+                                                      OW, ksize, stride);
   return check_launch("col2im");
 }

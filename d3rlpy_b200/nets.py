@@ -416,22 +416,25 @@ NATURE_FILTERS = [(32, 8, 4), (64, 4, 2), (64, 3, 1)]  # PixelEncoderFactory def
 
 
 class ConvCtx:
-    """Workspace of one ConvNet forward(/backward): patch matrices and NHWC activations per layer."""
+    """Workspace of one ConvNet forward(/backward): patch matrices and NHWC activations per layer (fp32, or bf16
+    with 16-byte padded rows in tensor-core mode)."""
 
     def __init__(self, net: "ConvNet", images: int, members: int, train: bool):
         self.images, self.members, self.train = images, members, train
         dev, E = net.device, members
-        f32 = torch.float32
+        bf = net.precision == "bf16"
+        dt = torch.bfloat16 if bf else torch.float32
+        pad = _a8 if bf else (lambda n: n)
         self.patches, self.acts = [], []
         for i, (C, H, W, oc, k, s, OH, OW) in enumerate(net.layers):
             rows, K = images * OH * OW, C * k * k
-            self.patches.append(torch.zeros(1 if i == 0 else E, rows, K, dtype=f32, device=dev))
-            self.acts.append(torch.zeros(E, rows, oc, dtype=f32, device=dev))
+            self.patches.append(torch.zeros(1 if i == 0 else E, rows, pad(K), dtype=dt, device=dev))
+            self.acts.append(torch.zeros(E, rows, pad(oc), dtype=dt, device=dev))
         if train:
-            self.dacts = [torch.zeros(E, images * OH * OW, oc, dtype=f32, device=dev)
+            self.dacts = [torch.zeros(E, images * OH * OW, pad(oc), dtype=dt, device=dev)
                           for (_, _, _, oc, _, _, OH, OW) in net.layers]
             kmax = max(images * OH * OW * C * k * k for (C, _, _, _, k, _, OH, OW) in net.layers[1:])
-            self.dpatch = torch.zeros(E * kmax, dtype=f32, device=dev)
+            self.dpatch = torch.zeros(E * kmax, dtype=torch.float32, device=dev)
 
 
 class ConvNet:
@@ -443,8 +446,7 @@ class ConvNet:
     def __init__(self, obs_shape, heads: Sequence[Tuple[str, int]], members: int, device, feature_size: int = 512,
                  filters=None, member_key: str = "{name}", with_target: bool = False,
                  seed_gen: Optional[torch.Generator] = None, precision: str = "fp32", input_divisor: float = 1.0):
-        if precision != "fp32":
-            raise ValueError("the convolutional encoder runs in fp32 mode (tensor-core conv path: DESIGN.md §next)")
+        assert precision in ("fp32", "bf16")
         C, H, W = obs_shape
         self.obs_shape, self.members, self.device = (C, H, W), members, device
         self.precision, self.input_divisor = precision, input_divisor
@@ -479,6 +481,35 @@ class ConvNet:
                                 exports=exports)
         self._ctx: Dict[str, ConvCtx] = {}
         self._init_params(seed_gen)
+        if precision == "bf16":
+            self._build_shadow(with_target)
+
+    # ---- bf16 shadows: W [oc][ld8(K)] (forward B operand) and W^T [K][ld8(oc)] (dgrad B operand), K-major both
+    def _build_shadow(self, with_target: bool):
+        rows, off = [], 0
+        self._sh_w, self._sh_wt = [], []
+        for i, (C, H, W, oc, k, s, OH, OW) in enumerate(self.layers):
+            K = C * k * k
+            ldk, ldn = _a8(K), _a8(oc)
+            w_off = off
+            off += oc * ldk
+            wt_off = off
+            off += K * ldn
+            self._sh_w.append((w_off, ldk))
+            self._sh_wt.append((wt_off, ldn))
+            rows.append([self.arena.offsets[self._names[i] + ".weight"], oc, K, w_off, ldk, wt_off, ldn])
+        self.shadow_member = _a8(off)
+        self._table = torch.tensor(rows, dtype=torch.int64)
+        n = self.shadow_member * self.members
+        self.shadow = torch.zeros(n, dtype=torch.bfloat16, device=self.device)
+        self.shadow_target = torch.zeros(n, dtype=torch.bfloat16, device=self.device) if with_target else None
+
+    def _sw(self, which, i):
+        base = self.shadow if which == "params" else self.shadow_target
+        return base.data_ptr() + 2 * self._sh_w[i][0], self._sh_w[i][1]
+
+    def _swt(self, i):
+        return self.shadow.data_ptr() + 2 * self._sh_wt[i][0], self._sh_wt[i][1]
 
     def _init_params(self, gen):
         a = self.arena
@@ -494,7 +525,12 @@ class ConvNet:
         a.sync_target_from_params()
 
     def refresh_shadow(self, which: str, stream: int):
-        return
+        if self.precision != "bf16":
+            return
+        src = self.arena.params if which == "params" else self.arena.target
+        dst = self.shadow if which == "params" else self.shadow_target
+        lib().shadow_weights(_p(src), self.arena.member_size, _p(dst), self.shadow_member, self._table.data_ptr(),
+                             self._table.shape[0], self.members, stream)
 
     def ctx(self, tag: str, images: int, members: Optional[int] = None, train: bool = True) -> ConvCtx:
         E = members or self.members
@@ -513,52 +549,85 @@ class ConvNet:
     def forward(self, which: str, x_u8, images: int, ctx: ConvCtx, head_out, stream: int, x_is_u8: bool = True):
         """x_u8: NCHW frame stack [images, C, H, W] (uint8, or fp32 when x_is_u8 is False)."""
         L, E, ms = lib(), ctx.members, self.arena.member_size
+        bf = self.precision == "bf16"
         for i, (C, H, W, oc, k, s, OH, OW) in enumerate(self.layers):
             rows, K = images * OH * OW, C * k * k
             p, y = ctx.patches[i], ctx.acts[i]
+            ldp, ldy = p.shape[2], y.shape[2]
             if i == 0:
-                L.im2col(_p(x_u8), 1 if x_is_u8 else 0, 0, C * H * W, H * W, W, 1, _p(p), 0, K, 0, images, C, H, W, k, s,
-                         self.input_divisor, 1, stream)
+                L.im2col(_p(x_u8), 1 if x_is_u8 else 0, 0, C * H * W, H * W, W, 1, _p(p), 1 if bf else 0, ldp, 0, images, C,
+                         H, W, k, s, self.input_divisor, 1, stream)
                 sx = 0
             else:
                 prev = ctx.acts[i - 1]
-                L.im2col(_p(prev), 0, prev.shape[1] * C, H * W * C, 1, W * C, C, _p(p), 0, K, p.shape[1] * K, images, C,
-                         H, W, k, s, 1.0, E, stream)
-                sx = p.shape[1] * K
-            L.linear_forward(_p(p), K, sx, self._w(which, i), K, ms, self._b(which, i), ms, _p(y), oc,
-                             y.shape[1] * oc, rows, oc, K, E, 1, stream)
+                ldc = prev.shape[2]  # NHWC rows of ldc (>= C) elements
+                L.im2col(_p(prev), 2 if bf else 0, prev.shape[1] * ldc, H * W * ldc, 1, W * ldc, ldc, _p(p), 1 if bf else 0,
+                         ldp, p.shape[1] * ldp, images, C, H, W, k, s, 1.0, E, stream)
+                sx = p.shape[1] * ldp
+            if bf:
+                wptr, ldw = self._sw(which, i)
+                L.umma_gemm(_p(p), ldp, sx, wptr, ldw, self.shadow_member, rows, oc, K, E, 1, self._b(which, i), ms, 1,
+                            None, 0, 0, _p(y), ldy, y.shape[1] * ldy, None, 0, 0, None, 0, 0, 0, stream)
+            else:
+                L.linear_forward(_p(p), K, sx, self._w(which, i), K, ms, self._b(which, i), ms, _p(y), oc,
+                                 y.shape[1] * oc, rows, oc, K, E, 1, stream)
         if head_out is not None:
             last, n, d = ctx.acts[-1], self.head_out, self.feat
-            L.head_forward(_p(last), d, last.shape[1] * d, self.arena.addr(which, "__head.weight"), d, ms,
-                           self.arena.addr(which, "__head.bias"), ms, _p(head_out), n, images * n, images, n, d, E, 0,
-                           stream)
+            hf = L.head_forward_bf16 if bf else L.head_forward
+            hf(_p(last), last.shape[2], last.shape[1] * last.shape[2], self.arena.addr(which, "__head.weight"), d, ms,
+               self.arena.addr(which, "__head.bias"), ms, _p(head_out), n, images * n, images, n, d, E, 0, stream)
 
     def backward(self, images: int, ctx: ConvCtx, d_head, stream: int):
         """d_head: fp32 [E, images, head_out].  Accumulates every dW/db into arena.grads."""
         L, E, ms = lib(), ctx.members, self.arena.member_size
         n, d = self.head_out, self.feat
+        bf = self.precision == "bf16"
         last = ctx.acts[-1]
-        L.head_backward_weight(_p(d_head), n, images * n, _p(last), d, last.shape[1] * d,
-                               self.arena.addr("grads", "__head.weight"), d, ms, self.arena.addr("grads", "__head.bias"),
-                               ms, images, n, d, E, stream)
+        ldl = last.shape[2]
         dcur = ctx.dacts[-1]
-        L.head_backward_data(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms, _p(dcur), d,
-                             dcur.shape[1] * d, _p(last), d, last.shape[1] * d, images, n, d, E, stream)
+        ldd = dcur.shape[2]
+        hw_g, hb_g = self.arena.addr("grads", "__head.weight"), self.arena.addr("grads", "__head.bias")
+        if bf:
+            L.head_backward_weight_bf16(_p(d_head), n, images * n, _p(last), ldl, last.shape[1] * ldl, hw_g, d, ms, hb_g,
+                                        ms, images, n, d, E, stream)
+            L.head_backward_data_bf16(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms,
+                                      _p(dcur), ldd, dcur.shape[1] * ldd, None, 0, 0, _p(last), ldl, last.shape[1] * ldl,
+                                      images, n, d, E, stream)
+        else:
+            L.head_backward_weight(_p(d_head), n, images * n, _p(last), d, last.shape[1] * d, hw_g, d, ms, hb_g, ms,
+                                   images, n, d, E, stream)
+            L.head_backward_data(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms, _p(dcur),
+                                 d, dcur.shape[1] * d, _p(last), d, last.shape[1] * d, images, n, d, E, stream)
         for i in range(len(self.layers) - 1, -1, -1):
             C, H, W, oc, k, s, OH, OW = self.layers[i]
             rows, K = images * OH * OW, C * k * k
             p = ctx.patches[i]
-            sx = 0 if i == 0 else p.shape[1] * K
-            L.linear_backward_weight(_p(dcur), oc, dcur.shape[1] * oc, _p(p), K, sx, self._w("grads", i), K, ms,
-                                     self._b("grads", i), ms, rows, oc, K, E, stream)
+            ldp, ldd = p.shape[2], dcur.shape[2]
+            sx = 0 if i == 0 else p.shape[1] * ldp
+            if bf:
+                L.colsum_bf16(_p(dcur), ldd, dcur.shape[1] * ldd, self._b("grads", i), ms, rows, oc, E, stream)
+                tiles = -(-oc // 128) * -(-K // 128) * E
+                splits = max(1, min(-(-rows // 64), -(-296 // tiles)))
+                # dW[oc][K] += dY^T patches: both operands row-major => MN-major tensor-core tiles
+                L.umma_gemm_tn(_p(dcur), ldd, dcur.shape[1] * ldd, _p(p), ldp, sx, oc, K, rows, E, splits,
+                               self._w("grads", i), K, ms, 1, stream)
+            else:
+                L.linear_backward_weight(_p(dcur), oc, dcur.shape[1] * oc, _p(p), K, sx, self._w("grads", i), K, ms,
+                                         self._b("grads", i), ms, rows, oc, K, E, stream)
             if i == 0:
                 break
             sdp = p.shape[1] * K
-            L.linear_backward_data(_p(dcur), oc, dcur.shape[1] * oc, self._w("params", i), K, ms, _p(ctx.dpatch), K,
-                                   sdp, None, 0, 0, rows, oc, K, E, stream)
+            if bf:
+                wt, ldwt = self._swt(i)
+                # dpatch[rows][K] = dY[rows][oc] . W[oc][K]   (B operand = W^T [K][oc], K-major)
+                L.umma_gemm(_p(dcur), ldd, dcur.shape[1] * ldd, wt, ldwt, self.shadow_member, rows, K, oc, E, 1, None, 0,
+                            0, None, 0, 0, None, 0, 0, None, 0, 0, _p(ctx.dpatch), K, sdp, 0, stream)
+            else:
+                L.linear_backward_data(_p(dcur), oc, dcur.shape[1] * oc, self._w("params", i), K, ms, _p(ctx.dpatch), K,
+                                       sdp, None, 0, 0, rows, oc, K, E, stream)
             prev, dprev = ctx.acts[i - 1], ctx.dacts[i - 1]
-            L.col2im(_p(ctx.dpatch), K, sdp, _p(prev), 0, C, prev.shape[1] * C, _p(dprev), C, dprev.shape[1] * C,
-                     images, C, H, W, k, s, E, stream)
+            L.col2im(_p(ctx.dpatch), K, sdp, _p(prev), 1 if bf else 0, prev.shape[2], prev.shape[1] * prev.shape[2],
+                     _p(dprev), dprev.shape[2], dprev.shape[1] * dprev.shape[2], images, C, H, W, k, s, E, stream)
             dcur = dprev
 
     def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
@@ -566,3 +635,6 @@ class ConvNet:
         lib().adam_step(_p(a.params), _p(a.grads), _p(a.exp_avg), _p(a.exp_avg_sq),
                         _p(a.target) if tau is not None else None, a.size, _p(a.step), lr, betas[0], betas[1], eps,
                         tau if tau is not None else 0.0, 1, stream)
+        self.refresh_shadow("params", stream)
+        if tau is not None and a.target is not None:
+            self.refresh_shadow("target", stream)

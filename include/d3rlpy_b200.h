@@ -275,12 +275,13 @@ int d3b_dcql_finalize(const float* sums, float inv_batch, float alpha, int conse
  *   strides (sb,sc,sh,sw), so the same call reads the NCHW uint8 minibatch (divisor = 255 fuses PixelScaler,
  *   scalers.py:109-110, and the float cast of torch_utility.py:146-149) and the NHWC fp32 outputs of the
  *   previous layer; the flatten + fc of encoders.py:150-162 is the ksize == height case.
- * col2im: gradient of im2col onto the NHWC input, times the ReLU mask [y_prev > 0] of its producer. */
+ * col2im: gradient of im2col onto the NHWC input, times the ReLU mask [y_prev > 0] of its producer (bf16 mask
+ *   => bf16 gradient output, the tensor-core path).  im2col x_is_u8: 0 fp32, 1 uint8, 2 bf16 input. */
 int d3b_im2col(const void* x, int x_is_u8, int64_t stride_x, int64_t sb, int64_t sc, int64_t sh, int64_t sw,
                void* out, int out_is_bf16, int64_t ldo, int64_t stride_o, int images, int channels, int height,
                int width, int ksize, int stride, float divisor, int members, void* stream);
 int d3b_col2im(const float* dpatch, int64_t ldp, int64_t stride_p, const void* y_prev, int y_is_bf16, int64_t ldy,
-               int64_t stride_y, float* dx, int64_t lddx, int64_t stride_dx, int images, int channels, int height,
+               int64_t stride_y, void* dx, int64_t lddx, int64_t stride_dx, int images, int channels, int height,
                int width, int ksize, int stride, int members, void* stream);
 
 /* ---- K10: optimizer / target sync ----------------------------------------------

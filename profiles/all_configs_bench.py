@@ -84,9 +84,10 @@ for B in (256, 100):
     out[f"c3 BCQ B{B} N100 (cpu oracle)"] = {"us_per_update": us, "updates_timed": n, "threads": os.cpu_count()}
 # c4 DiscreteCQL pixels
 b = [pix_batch(32, 4) for _ in range(4)]
-a = DiscreteCQL(batch_size=32, n_frames=4, scaler="pixel")
-a.create_impl((4, 84, 84), 4)
-out["c4 DiscreteCQL 4x84x84 B32 (fp32 conv path)"] = {"us_per_update": time_gpu(a, b, n=100, warm=10)}
+for prec in ("fp32", "bf16"):
+    a = DiscreteCQL(batch_size=32, n_frames=4, scaler="pixel", precision=prec)
+    a.create_impl((4, 84, 84), 4)
+    out[f"c4 DiscreteCQL 4x84x84 B32 ({prec})"] = {"us_per_update": time_gpu(a, b, n=100, warm=10)}
 us, n = time_cpu(ou.DiscreteCQL((4, 84, 84), 4), b, scaler=ou.pixel_scaler())
 out["c4 DiscreteCQL 4x84x84 B32 (cpu oracle)"] = {"us_per_update": us, "updates_timed": n, "threads": os.cpu_count()}
 for k, v in out.items():

@@ -393,3 +393,47 @@ def test_discrete_cql_c4_shape_vs_oracle():
         _assert_metrics(m, ref, f"c4 step {s}", rel=2e-5)
     _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=2e-5)
     _assert_params(impl.targ_q_function.state_dict(), orc.targ_q, "targ_q", rel=2e-5)
+
+
+def test_discrete_cql_pixel_bf16_tensor_core_conv_path():
+    """Nature-DQN convs as bf16 im2col + tcgen05 GEMMs (forward, dgrad, MN-major wgrad): golden case and the c4
+    shape vs the fp32 oracle within the bf16 tolerance."""
+    from d3rlpy_b200.algos import DiscreteCQL, PixelEncoderFactory
+
+    case = Case(load_update(), "dcql_pix")
+    c = case.cfg
+    hw, nf = int(c["hw"]), int(c["n_frames"])
+    algo = DiscreteCQL(encoder_factory=PixelEncoderFactory(feature_size=int(c["feature"])),
+                       batch_size=int(c["batch"]), n_frames=nf, scaler="pixel", precision="bf16")
+    algo.create_impl((nf, hw, hw), int(c["act"]))
+    impl = algo.impl
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    for s in range(case.steps):
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"dcql_pix bf16 step {s}", rel=BF16_REL)
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q", rel=BF16_REL)
+
+    B, A = 32, 4
+    torch.set_num_threads(8)
+    orc = ou.DiscreteCQL((4, 84, 84), A, seed=9)
+    algo = DiscreteCQL(batch_size=B, n_frames=4, scaler="pixel", precision="bf16")
+    algo.create_impl((4, 84, 84), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    rs = np.random.RandomState(7)
+    arrays = dict(observations=rs.randint(0, 256, (B, 4, 84, 84)).astype(np.uint8),
+                  actions=rs.randint(0, A, B).astype(np.int32), rewards=(rs.rand(B, 1) < 0.1).astype(np.float32),
+                  next_observations=rs.randint(0, 256, (B, 4, 84, 84)).astype(np.uint8),
+                  terminals=(rs.rand(B, 1) < 0.05).astype(np.float32), n_steps=np.ones((B, 1), np.float32))
+    ref = orc.update(ou.Batch(arrays, ou.pixel_scaler()), None)
+    m = algo.update(_ns(arrays))
+    _assert_metrics(m, ref, "c4 bf16", rel=BF16_REL)
+    # first-step gradients through Adam's first moment: direction and size of every tensor
+    m_sd = impl._q_func.arena.state_dict("exp_avg")
+    for k, p in orc.q.items():
+        r = orc.optim.state[p]["exp_avg"]
+        g = m_sd[k].cpu().reshape(r.shape)
+        cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
+        assert cos >= 0.98, (k, cos)
