@@ -38,7 +38,8 @@ __device__ __forceinline__ float nstep_return(const float* __restrict__ rewards,
   return acc;
 }
 
-// One warp per minibatch row.
+// One HALF-warp (16 lanes) per minibatch row: twice as many independent index -> metadata -> row chains in flight
+// per SM as with a warp per row (the gather is latency-bound on that dependency chain).
 __global__ void __launch_bounds__(128) gather_vector_kernel(
     const float* __restrict__ obs, int O, const void* __restrict__ actions, int A, int discrete,
     const float* __restrict__ rewards, const int4* __restrict__ meta, const long long* __restrict__ indices,
@@ -46,8 +47,8 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     float* __restrict__ out_rew, float* __restrict__ out_next, float* __restrict__ out_term,
     float* __restrict__ out_n, const float* __restrict__ sc_mean, const float* __restrict__ sc_std,
     float sc_eps) {
-  int lane = threadIdx.x & 31;
-  int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 15;
+  int b = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
   if (b >= B) return;
   long long t = __ldg(indices + b);
   RowInfo r = row_info(meta, t, n_steps);
@@ -56,19 +57,19 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     const float* nsrc = obs + (size_t)(r.g2 + 1) * O;
     float* d0 = out_obs + (size_t)b * O;
     float* d1 = out_next + (size_t)b * O;
-    // 4 x 32 columns per pass with every load issued before the first store (8 independent loads in flight per
+    // 4 x 16 columns per pass with every load issued before the first store (8 independent loads in flight per
     // lane: the row gather is latency-bound on its index -> metadata -> row dependency chain)
-    for (int j0 = 0; j0 < O; j0 += 128) {
+    for (int j0 = 0; j0 < O; j0 += 64) {
       float xs[4], ys[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        int j = j0 + lane + 32 * u;
+        int j = j0 + lane + 16 * u;
         xs[u] = j < O ? __ldg(src + j) : 0.f;
         ys[u] = (j < O && !r.terminal) ? __ldg(nsrc + j) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        int j = j0 + lane + 32 * u;
+        int j = j0 + lane + 16 * u;
         if (j < O) {
           float x = xs[u], y = ys[u];
           if (sc_mean) {  // StandardScaler.transform fused (preprocessing/scalers.py:350-354)
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     if (lane == 0) ((int*)out_act)[b] = __ldg((const int*)actions + r.g);
   } else {
     const float* a = (const float*)actions + (size_t)r.g * A;
-    for (int j = lane; j < A; j += 32) ((float*)out_act)[(size_t)b * A + j] = __ldg(a + j);
+    for (int j = lane; j < A; j += 16) ((float*)out_act)[(size_t)b * A + j] = __ldg(a + j);
   }
   if (lane == 0) {
     out_rew[b] = nstep_return(rewards, r.g, r.k, gamma);
@@ -143,8 +144,8 @@ extern "C" int d3b_gather_vector(const float* obs, int obs_dim, const void* acti
               "gather_vector: null pointer");
   D3B_REQUIRE(obs_dim == 0 || (obs && out_obs && out_next), "gather_vector: null observation pointer");
   D3B_REQUIRE((scaler_mean == nullptr) == (scaler_std == nullptr), "gather_vector: scaler mean/std must come together");
-  int warps = 4;
-  gather_vector_kernel<<<ceil_div(batch, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+  int rows_per_block = 8;  // 128 threads, 16 lanes per row
+  gather_vector_kernel<<<ceil_div(batch, rows_per_block), rows_per_block * 16, 0, (cudaStream_t)stream>>>(
       obs, obs_dim, actions, act_dim, discrete, rewards, (const int4*)meta, (const long long*)indices, batch, n_steps,
       gamma, out_obs, out_act, out_rew, out_next, out_term, out_nsteps, scaler_mean, scaler_std, scaler_eps);
   return check_launch("gather_vector");
