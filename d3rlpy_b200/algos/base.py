@@ -123,18 +123,62 @@ class AlgoBase:
         replay = dataset.device_replay(self._impl._device)
         rng = np.random if seed is None else np.random.RandomState(seed)
         history: List[Dict[str, float]] = []
-        acc: Dict[str, List[float]] = {}
-        for step in range(1, n_steps + 1):
-            # one vectorised draw == batch_size sequential `np.random.randint(n)` calls of RandomIterator
-            # (iterators/random_iterator.py:38-41): the legacy RandomState consumes the stream element by element
-            idx = rng.randint(len(replay), size=self._batch_size).astype(np.int64)
-            batch = TransitionMiniBatch.from_indices(replay, idx, n_frames=self._n_frames, n_steps=self._n_steps,
-                                                     gamma=self._gamma, scaler=self._scaler,
-                                                     out=self._impl.device_batch(self._batch_size))
-            m = self.update(batch)
-            for k, v in m.items():
-                acc.setdefault(k, []).append(float(v))
-            if step % n_steps_per_epoch == 0 or step == n_steps:
+        impl, B = self._impl, self._batch_size
+        fast = (not replay.is_image) and (not replay.discrete) and self._n_frames == 1
+        done = 0
+        while done < n_steps:
+            chunk = min(n_steps_per_epoch - done % n_steps_per_epoch, n_steps - done)
+            # one vectorised draw == chunk*B sequential `np.random.randint(n)` calls of RandomIterator
+            # (iterators/random_iterator.py:38-41): the legacy RandomState consumes its stream element by element
+            idx = rng.randint(len(replay), size=(chunk, B)).astype(np.int64)
+            if fast:
+                acc = self._fit_chunk_device(replay, idx)
+            else:
+                acc: Dict[str, List[float]] = {}
+                for i in range(chunk):
+                    batch = TransitionMiniBatch.from_indices(replay, idx[i], n_frames=self._n_frames,
+                                                             n_steps=self._n_steps, gamma=self._gamma,
+                                                             scaler=self._scaler, out=impl.device_batch(B))
+                    for k, v in self.update(batch).items():
+                        acc.setdefault(k, []).append(float(v))
+            done += chunk
+            if done % n_steps_per_epoch == 0 or done == n_steps:
                 history.append({k: float(np.mean(v)) for k, v in acc.items()})
-                acc = {}
         return history
+
+    def _fit_chunk_device(self, replay, idx: np.ndarray) -> Dict[str, List[float]]:
+        """Vector observations: the chunk's indices are uploaded once; every step is one gather launch + one graph
+        replay + one 256-byte device-side copy of the metric slots; metrics come back with ONE D2H per chunk
+        (the reference syncs on every loss)."""
+        import torch
+        from types import SimpleNamespace
+
+        impl, B = self._impl, self._batch_size
+        L, st = impl._lib, impl._stream
+        chunk = idx.shape[0]
+        idx_dev = torch.from_numpy(np.ascontiguousarray(idx)).to(impl._device)
+        hist = torch.zeros(chunk, 64, dtype=torch.float32, device=impl._device)
+        db = impl.device_batch(B)
+        holder = SimpleNamespace(_device_batch=db)
+        sc = (None, None, 0.0)
+        if self._scaler is not None and getattr(self._scaler, "TYPE", "") == "standard":
+            m, s, e = replay.scaler_tensors(self._scaler)
+            sc = (m.data_ptr(), s.data_ptr(), e)
+        torch.cuda.current_stream(impl._device).synchronize()
+        names_per_step = []
+        O, A = replay.obs_shape[0], replay.act_dim
+        for i in range(chunk):
+            L.gather_vector(replay.obs.data_ptr(), O, replay.actions.data_ptr(), A, 0, replay.rewards.data_ptr(),
+                            replay.meta.data_ptr(), idx_dev.data_ptr() + 8 * B * i, B, self._n_steps, float(self._gamma),
+                            db.ptr("obs"), db.ptr("act"), db.ptr("rew"), db.ptr("next_obs"), db.ptr("term"),
+                            db.ptr("nsteps"), sc[0], sc[1], sc[2], st)
+            names_per_step.append(self._update_async(holder))
+            self._grad_step += 1
+            L.copy_d2d(hist.data_ptr() + 256 * i, impl._slots.data_ptr(), 256, st)
+        impl.sync()
+        h = hist.cpu().numpy()
+        acc: Dict[str, List[float]] = {}
+        for i, names in enumerate(names_per_step):
+            for slot, key in names:
+                acc.setdefault(key, []).append(float(h[i, slot]))
+        return acc

@@ -52,3 +52,7 @@ class BCQ(AlgoBase):
         rl_step = self._grad_step >= self._rl_start_step
         actor_step = self._grad_step % self._update_actor_interval == 0
         return self._impl.update_fused(batch, rl_step, actor_step)
+
+    def _update_async(self, batch):
+        return self._impl.update_fused_async(batch, self._grad_step >= self._rl_start_step,
+                                             self._grad_step % self._update_actor_interval == 0)

@@ -50,3 +50,6 @@ class CQL(AlgoBase):
         """cql.py:234-258: temp -> alpha -> critic -> actor -> target syncs, as one captured graph."""
         assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
         return self._impl.update_fused(batch)
+
+    def _update_async(self, batch):
+        return self._impl.update_fused_async(batch)

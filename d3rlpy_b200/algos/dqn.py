@@ -63,6 +63,9 @@ class DQN(AlgoBase):
         assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
         return self._impl.update_fused(batch, self._grad_step % self._target_update_interval == 0)
 
+    def _update_async(self, batch):
+        return self._impl.update_fused_async(batch, self._grad_step % self._target_update_interval == 0)
+
 
 class DoubleDQN(DQN):
     IMPL = DoubleDQNImpl

@@ -49,3 +49,6 @@ class TD3PlusBC(AlgoBase):
         assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
         actor_step = self._grad_step % self._update_actor_interval == 0
         return self._impl.update_fused(batch, actor_step)
+
+    def _update_async(self, batch):
+        return self._impl.update_fused_async(batch, self._grad_step % self._update_actor_interval == 0)

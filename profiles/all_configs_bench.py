@@ -90,6 +90,17 @@ for prec in ("fp32", "bf16"):
     out[f"c4 DiscreteCQL 4x84x84 B32 ({prec})"] = {"us_per_update": time_gpu(a, b, n=100, warm=10)}
 us, n = time_cpu(ou.DiscreteCQL((4, 84, 84), 4), b, scaler=ou.pixel_scaler())
 out["c4 DiscreteCQL 4x84x84 B32 (cpu oracle)"] = {"us_per_update": us, "updates_timed": n, "threads": os.cpu_count()}
+# fit(): sampling (numpy index stream) + device gather + update, c2 shapes on a 1M-step replay
+from d3rlpy_b200.dataset import MDPDataset  # noqa: E402
+
+S = 1_000_000
+ds = MDPDataset(rs.randn(S, 17).astype(np.float32), rs.uniform(-1, 1, (S, 6)).astype(np.float32),
+                rs.randn(S).astype(np.float32), (np.arange(S) % 1000 == 999).astype(np.float32))
+a = CQL(actor_encoder_factory=H3, critic_encoder_factory=H3, n_action_samples=10, precision="bf16")
+a.fit(ds, n_steps=200, n_steps_per_epoch=100, seed=0)
+t0 = time.perf_counter()
+a.fit(ds, n_steps=3000, n_steps_per_epoch=1000, seed=1)
+out["c2 CQL fit() sample+gather+update (bf16)"] = {"us_per_update": (time.perf_counter() - t0) / 3000 * 1e6}
 for k, v in out.items():
     v["updates_per_s"] = 1e6 / v["us_per_update"]
 print(json.dumps(out, indent=1))
