@@ -92,6 +92,73 @@ class TD3PlusBCImpl(DDPGBaseImpl):
 
             allreduce_sum(t, self._stream_obj)
 
+    # ------------------------------------------------------------------ single-GPU tensor-core program
+    fused_glue = True
+
+    def _side_stream(self) -> int:
+        if getattr(self, "_side_obj", None) is None:
+            self._side_obj = torch.cuda.Stream(device=self._device)
+        return self._side_obj.cuda_stream
+
+    def _program_fused(self, db, actor_step: bool):
+        """Same update as `program` with the rows written straight as bf16 GEMM operands, the loss tail fused, and
+        the online-critic forward running on a graph branch beside the target path (policy' -> smoothing -> Q')."""
+        B, O, A, E = db.B, db.O, self._action_size, self._n_critics
+        L, st = self._lib, self._stream
+        bf = torch.bfloat16
+        ld = (O + A + 7) // 8 * 8
+        inv_b = 1.0 / B
+        mask = (1 << C_DRAW) | (1 << C_CRITIC) | ((1 << C_ACTOR) if actor_step else 0)
+        L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
+        self.fill_noise(B)
+        X = self.ws("xf_rows", 3 * B, ld, dtype=bf)        # [critic rows | target rows | actor rows]
+        done = self.ws("xf_done", 4, dtype=torch.int32)
+        q_net, pi = self._q_func, self._policy
+        # ---- branch: online critics on (s, a)
+        side = self._side_stream()
+        L.stream_fork(st, side)
+        L.concat_rows_bf16(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, X.data_ptr(), ld, B, 1, O, A, side)
+        ctx_c = q_net.ctx("cq", B, E, True)
+        q = self.ws("cq_q", E, B)
+        q_net.forward("params", None, 0, B, ctx_c, q, side, x_bf16=(X.data_ptr(), ld))
+        # ---- main: target policy -> smoothed action -> target critics
+        a_next = self.ws("tp_a", 1, B, A)
+        pi.forward("target", db.ptr("next_obs"), O, B, pi.ctx("tp", B, 1, False), a_next, st, head_tanh=True)
+        xt = X.data_ptr() + 2 * B * ld
+        L.concat_rows_bf16(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
+                           self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt, ld, B, 1, O, A, st)
+        q_t = self.ws("tq_q", E, B)
+        q_net.forward("target", None, 0, B, q_net.ctx("tq", B, E, False), q_t, st, x_bf16=(xt, ld))
+        L.stream_join(st, side)
+        dq = self.ws("dq", E, B)
+        L.cql_loss_step(q.data_ptr(), B, q_t.data_ptr(), B, E, None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
+                        self._gamma, None, None, 0, A, None, 0.0, 0.0, dq.data_ptr(), B, self.sums_ptr(S_TD),
+                        done.data_ptr(), B, E, inv_b, 0, None, 0.0, self.metric_ptr(M_CRITIC), None, st)
+        q_net.backward(None, 0, B, ctx_c, dq, st)
+        q_net.adam(self._critic_learning_rate, st, tau=self._tau if actor_step else None)
+        if not actor_step:
+            return
+        # ---- actor step (td3_plus_bc_impl.py:64-70): member 0 only
+        acts_p = pi.ctx("pi", B, 1, True)
+        a = self.ws("pi_a", 1, B, A)
+        pi.forward("params", db.ptr("obs"), O, B, acts_p, a, st, head_tanh=True)
+        xa = X.data_ptr() + 2 * 2 * B * ld
+        L.concat_rows_bf16(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, st)
+        ctx_a = q_net.ctx("aq", B, 1, True)
+        q0 = self.ws("aq_q", 1, B)
+        q_net.forward("params", None, 0, B, ctx_a, q0, st, x_bf16=(xa, ld))
+        L.td3bc_actor_stats(q0.data_ptr(), a.data_ptr(), A, db.ptr("act"), A, self.sums_ptr(S_ACT), B, A, st)
+        dq0 = self.ws("a_dq", 1, B)
+        L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq0.data_ptr(), B, B, 1,
+                           self.metric_ptr(M_ACTOR), st)
+        dxa = self.ws("a_dx", B, A)
+        q_net.backward(None, 0, B, ctx_a, dq0, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
+                       dx_cols=A)
+        dz = self.ws("pi_dz", 1, B, A)
+        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, inv_b, st)
+        pi.backward(db.ptr("obs"), O, B, acts_p, dz, st)
+        pi.adam(self._actor_learning_rate, st, tau=self._tau)
+
     # ------------------------------------------------------------------ fused update (TD3PlusBC._update)
     def update_fused(self, batch, actor_step: bool):
         return self._metrics_dict(self.update_fused_async(batch, actor_step))
@@ -110,7 +177,10 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             if actor_step:
                 self._p_actor(db)
 
-        self.run_program(("td3bc", db.B, actor_step, self._noise_injected), program)
+        fused = (self._precision == "bf16" and self.world_size == 1 and self._q_func.fused_ok
+                 and self._policy.fused_ok and self.fused_glue)
+        self.run_program(("td3bc", db.B, actor_step, self._noise_injected, fused),
+                         (lambda: self._program_fused(db, actor_step)) if fused else program)
         return [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
 
     # ------------------------------------------------------------------ reference hooks (eager)

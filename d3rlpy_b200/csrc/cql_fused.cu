@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
       td = d * d;
       g = 2.f * p.inv_b * d;
     }
-    const float ca = clampf3(expf(p.scalar_alpha[0]), 0.f, 1e6f);
+    const float ca = N > 0 ? clampf3(expf(p.scalar_alpha[0]), 0.f, 1e6f) : 0.f;
     const float c = ca * p.cw * p.inv_eb;
     const float rand_lp = (float)p.A * -0.69314718055994529f;
     const long long BN = (long long)B * N;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
       mx = fmaxf(mx, q - off);
     }
     mx = warp_max(mx);
-    float s = 0.f;
+    float s = N > 0 ? 0.f : 1.f;
     for (int v = lane; v < 3 * N; v += 32) {
       int grp = v / N, k = v - grp * N;
       float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
       if (lane == 0) dqe[b] = g - c;
     }
     if (lane == 0) {
-      lse_v = mx + logf(s);
-      data_v = qd;
+      lse_v = N > 0 ? mx + logf(s) : 0.f;
+      data_v = N > 0 ? qd : 0.f;
     } else {
       td = 0.f;
     }
@@ -284,6 +284,11 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
   __threadfence();
   volatile float* sv = p.sums;
   float tdm = sv[0] * p.inv_b;
+  if (N == 0) {  // plain TD loss (no conservative term): TD3+BC / BCQ critics
+    *p.metric = tdm;
+    *p.done = 0u;
+    return;
+  }
   float ea = expf(p.scalar_alpha[0]);
   float ca = clampf3(ea, 0.f, 1e6f);
   float scaled = p.cw * (sv[1] * p.inv_eb - sv[2] * p.inv_eb);
@@ -401,8 +406,9 @@ extern "C" int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* 
                                  float alpha_threshold, float* dq, int64_t stride_dq, float* sums, void* done_counter,
                                  int batch, int members, float inv_batch, int mode, const int* step_alpha,
                                  double lr_alpha, float* metric, float* metric_exp, void* stream) {
-  D3B_REQUIRE(batch >= 1 && members >= 1 && n_action_samples >= 1, "cql_loss_step: bad sizes");
-  D3B_REQUIRE(q && logp_t && logp_tp1 && scalar_alpha && sums && done_counter && metric, "cql_loss_step: null pointer");
+  D3B_REQUIRE(batch >= 1 && members >= 1 && n_action_samples >= 0, "cql_loss_step: bad sizes");
+  D3B_REQUIRE(q && sums && done_counter && metric, "cql_loss_step: null pointer");
+  D3B_REQUIRE(n_action_samples == 0 || (logp_t && logp_tp1 && scalar_alpha), "cql_loss_step: null conservative-term pointer");
   D3B_REQUIRE(mode == 0 || (step_alpha && metric_exp), "cql_loss_step: alpha mode needs the step counter / metric slot");
   D3B_REQUIRE(!(q_targ || q_tpn) || (rewards && terminals && n_steps), "cql_loss_step: TD term needs the minibatch");
   LossParams p{};

@@ -9,9 +9,14 @@
 //   SAC actor / temperature         d3rlpy/algos/torch/sac_impl.py:114-146
 //   CQL conservative term           d3rlpy/algos/torch/cql_impl.py:143-223
 // Gradient formulas: SURVEY.md Appendix C.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace d3b {
+
+__device__ __forceinline__ void put(float* p, float v) { *p = v; }
+__device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ float softplusf(float x) {  // F.softplus, threshold 20
@@ -20,18 +25,21 @@ __device__ __forceinline__ float softplusf(float x) {  // F.softplus, threshold 
 
 // X[(b*N+k)] = [ obs[b] | f(act[b*N+k]) ];  f = optional TD3 smoothing or symmetric clip.
 // One warp per output row.
+template <typename Out>
 __global__ void __launch_bounds__(256) concat_rows_kernel(const float* __restrict__ obs, long long ldo,
                                                           const float* __restrict__ act, long long lda,
                                                           const float* __restrict__ noise, float sigma,
-                                                          float noise_clip, float act_clip, float* __restrict__ X,
+                                                          float noise_clip, float act_clip, Out* __restrict__ X,
                                                           long long ldx, int B, int N, int O, int A) {
+  pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * N) return;
   int b = (int)(row / N);
-  float* x = X + row * ldx;
+  Out* x = X + row * ldx;
   const float* o = obs + (long long)b * ldo;
-  for (int j = lane; j < O; j += 32) x[j] = __ldg(o + j);
+  for (int j = lane; j < O; j += 32) put(x + j, __ldg(o + j));
   if (act) {
     const float* a = act + row * lda;
     for (int j = lane; j < A; j += 32) {
@@ -41,7 +49,7 @@ __global__ void __launch_bounds__(256) concat_rows_kernel(const float* __restric
         v = clampf(v + nz, -1.f, 1.f);
       }
       if (act_clip > 0.f) v = clampf(v, -act_clip, act_clip);
-      x[O + j] = v;
+      put(x + O + j, v);
     }
   }
 }
@@ -375,10 +383,25 @@ extern "C" int d3b_concat_rows(const float* obs, int64_t ldo, const float* act, 
   D3B_REQUIRE(obs && x, "concat_rows: null pointer");
   D3B_REQUIRE(ldx >= obs_dim + (act ? act_dim : 0), "concat_rows: ldx too small");
   long long rows = (long long)batch * n_repeat;
-  concat_rows_kernel<<<(unsigned)ceil_div_ll(rows, 8), 256, 0, ST>>>(obs, ldo, act, lda, noise, sigma, noise_clip,
-                                                                     act_clip, x, ldx, batch, n_repeat, obs_dim,
-                                                                     act_dim);
+  concat_rows_kernel<float><<<(unsigned)ceil_div_ll(rows, 8), 256, 0, ST>>>(obs, ldo, act, lda, noise, sigma,
+                                                                            noise_clip, act_clip, x, ldx, batch,
+                                                                            n_repeat, obs_dim, act_dim);
   return check_launch("concat_rows");
+}
+
+// same rows written as bf16 (GEMM operands of the tensor-core path; no separate conversion launch)
+extern "C" int d3b_concat_rows_bf16(const float* obs, int64_t ldo, const float* act, int64_t lda, const float* noise,
+                                    float sigma, float noise_clip, float act_clip, void* x_bf16, int64_t ldx,
+                                    int batch, int n_repeat, int obs_dim, int act_dim, void* stream) {
+  D3B_REQUIRE(batch >= 0 && n_repeat >= 1 && obs_dim >= 0 && act_dim >= 0, "concat_rows_bf16: bad sizes");
+  if (batch == 0) return D3B_OK;
+  D3B_REQUIRE(obs && x_bf16, "concat_rows_bf16: null pointer");
+  D3B_REQUIRE(ldx >= obs_dim + (act ? act_dim : 0), "concat_rows_bf16: ldx too small");
+  long long rows = (long long)batch * n_repeat;
+  launch_pdl(concat_rows_kernel<__nv_bfloat16>, dim3((unsigned)ceil_div_ll(rows, 8)), dim3(256), 0, ST, obs,
+             (long long)ldo, act, (long long)lda, noise, sigma, noise_clip, act_clip, (__nv_bfloat16*)x_bf16,
+             (long long)ldx, batch, n_repeat, obs_dim, act_dim);
+  return check_launch("concat_rows_bf16");
 }
 
 extern "C" int d3b_policy_sample_rows(const float* head, int64_t ld_head, const float* eps, const float* obs,

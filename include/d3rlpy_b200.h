@@ -165,6 +165,9 @@ int d3b_colsum_bf16(const void* dz, int64_t ld, int64_t stride_z, float* dbias, 
 int d3b_concat_rows(const float* obs, int64_t ldo, const float* act, int64_t lda, const float* noise, float sigma,
                     float noise_clip, float act_clip, float* x, int64_t ldx, int batch, int n_repeat, int obs_dim,
                     int act_dim, void* stream);
+int d3b_concat_rows_bf16(const float* obs, int64_t ldo, const float* act, int64_t lda, const float* noise, float sigma,
+                         float noise_clip, float act_clip, void* x_bf16, int64_t ldx, int batch, int n_repeat,
+                         int obs_dim, int act_dim, void* stream); /* same rows as bf16 GEMM operands */
 /* policy_sample_rows: SquashedNormalPolicy sample_with_log_prob / sample_n_with_log_prob /
  *   best_action (policies.py:167-249, distributions.py:91-143).  head = [mu | raw logstd],
  *   eps laid out [n][batch][act] as Normal.rsample((n,)). */
