@@ -71,8 +71,7 @@ def make_dataset(w, steps_total=1_000_000, seed=0):
     """BASELINE.md synthetic data: N(0,1) observations, U(-1,1) actions, N(0,1) rewards, episodes of 1000."""
     rs = np.random.RandomState(seed)
     S = steps_total
-    obs = rs.standard_normal((S, w["obs"]), dtype=np.float32) if hasattr(rs, "standard_normal") and False else \
-        rs.randn(S, w["obs"]).astype(np.float32)
+    obs = rs.randn(S, w["obs"]).astype(np.float32)
     act = rs.uniform(-1, 1, (S, w["act"])).astype(np.float32)
     rew = rs.randn(S).astype(np.float32)
     term = np.zeros(S, np.float32)

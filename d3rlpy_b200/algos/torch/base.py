@@ -167,8 +167,17 @@ class ImplBase:
     def sync(self):
         self._lib.stream_sync(self._stream)
 
+    def read_slots_after_program(self) -> np.ndarray:
+        """Metrics of the update enqueued by `run_program` (its last node is the pinned D2H of the slots)."""
+        if not getattr(self, "_metrics_on_host", False):
+            return self.read_slots()  # device-resident batch: the graph has no read-back node
+        self.sync()
+        return self._slots_host.numpy()
+
     def read_slots(self) -> np.ndarray:
         self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
+        if not getattr(self, "_metrics_on_host", False):
+            return self.read_slots()  # device-resident batch: the graph has no read-back node
         self.sync()
         return self._slots_host.numpy()
 
@@ -186,9 +195,12 @@ class ImplBase:
             self._graphs_invalidate()
         return self._batch
 
-    def load_batch(self, batch) -> DeviceBatch:
+    def load_batch(self, batch, defer: bool = False) -> DeviceBatch:
         """Accepts a host minibatch (numpy properties, e.g. the reference's TransitionMiniBatch or ours)
-        or our device-resident TransitionMiniBatch (already gathered in HBM)."""
+        or our device-resident TransitionMiniBatch (already gathered in HBM).  defer=True (whole-update
+        graphs): the arrays are only staged in pinned memory; the H2D copy and the scaler become the first nodes
+        of the update graph (`run_program`)."""
+        self._pending_upload = None
         dev = getattr(batch, "_device_batch", None)
         if dev is not None:
             if self._batch is not dev:
@@ -198,11 +210,17 @@ class ImplBase:
         B = len(batch.rewards) if hasattr(batch, "rewards") else len(batch)
         db = self.device_batch(B)
         db.stage_host(batch)
+        if defer:
+            self._pending_upload = db
+        else:
+            self._upload(db)
+        return db
+
+    def _upload(self, db: DeviceBatch) -> None:
         self._lib.copy_h2d(db.dev.data_ptr(), db.host.data_ptr(), 4 * db.nfloat, self._stream)
         if db.pixel_shape:
             self._lib.copy_h2d(db.pix_dev.data_ptr(), db.pix_host.data_ptr(), 2 * db.npix, self._stream)
         self._apply_scalers(db)
-        return db
 
     def _apply_scalers(self, db: DeviceBatch):
         """scaler.transform on obs/next_obs (d3rlpy/torch_utility.py:179-185).  Standard scaling of a
@@ -281,6 +299,19 @@ class ImplBase:
     def run_program(self, key: tuple, program) -> None:
         """Runs `program()` (a sequence of launches on self._stream) — captured once per `key` as a CUDA
         graph and replayed afterwards."""
+        pend = getattr(self, "_pending_upload", None)
+        self._pending_upload = None
+        inner = program
+
+        def program():  # noqa: F811 - host-batch upload in front, metric read-back behind, all in one graph
+            if pend is not None:
+                self._upload(pend)
+            inner()
+            if pend is not None:  # host caller: it will read the metrics right away
+                self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
+
+        key = tuple(key) + (pend is not None,)
+        self._metrics_on_host = pend is not None
         if not self.use_graph:
             program()
             return

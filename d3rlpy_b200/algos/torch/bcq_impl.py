@@ -217,7 +217,7 @@ class BCQImpl(DDPGBaseImpl):
         return self._metrics_dict(self.update_fused_async(batch, rl_step, actor_step))
 
     def update_fused_async(self, batch, rl_step: bool, actor_step: bool):
-        db = self.load_batch(batch)
+        db = self.load_batch(batch, defer=True)
         actor_step = actor_step and rl_step
 
         def program():

@@ -400,7 +400,7 @@ class CQLImpl(DDPGBaseImpl):
 
     def update_fused_async(self, batch):
         """Enqueue one whole update (no host sync); returns the metric slot names."""
-        db = self.load_batch(batch)
+        db = self.load_batch(batch, defer=True)
         do_temp, do_alpha = self._temp_learning_rate > 0, self._alpha_learning_rate > 0
 
         def program():

@@ -137,5 +137,5 @@ class DDPGBaseImpl(ImplBase):
         self._lib.tick(self._counters.data_ptr(), self.N_COUNTERS, mask, self._stream)
 
     def _metrics_dict(self, names):
-        vals = self.read_slots()
+        vals = self.read_slots_after_program()
         return {n: np.float32(vals[i]) for i, n in names}

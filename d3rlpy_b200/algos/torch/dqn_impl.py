@@ -139,10 +139,10 @@ class DQNImpl(ImplBase):
     # ------------------------------------------------------------------ fused update (DQN._update, dqn.py:127-132)
     def update_fused(self, batch, sync_target: bool):
         self.update_fused_async(batch, sync_target)
-        return {"loss": np.float32(self.read_slots()[M_LOSS])}
+        return {"loss": np.float32(self.read_slots_after_program()[M_LOSS])}
 
     def update_fused_async(self, batch, sync_target: bool):
-        db = self.load_batch(batch)
+        db = self.load_batch(batch, defer=True)
 
         def program():
             self._tick(C_CRITIC)

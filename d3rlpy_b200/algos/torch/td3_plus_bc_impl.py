@@ -165,7 +165,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
 
     def update_fused_async(self, batch, actor_step: bool):
         """Enqueue one whole update (no host sync); returns the metric slot names."""
-        db = self.load_batch(batch)
+        db = self.load_batch(batch, defer=True)
 
         def program():
             self._tick(C_DRAW, C_CRITIC, *([C_ACTOR] if actor_step else []))

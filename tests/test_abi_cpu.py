@@ -82,3 +82,26 @@ def test_arena_state_dict_keys_match_reference_names():
     # heads are physically concatenated: mu rows then logstd rows
     hw = pi.arena.view("__head.weight")
     assert torch.equal(hw[:2], sd["_mu.weight"]) and torch.equal(hw[2:], sd["_logstd.weight"])
+
+
+def test_fit_index_stream_equals_random_iterator_draws():
+    """fit() draws one (chunk, batch) block of indices per epoch; the reference's RandomIterator draws them one by
+    one with np.random.randint(n) (iterators/random_iterator.py:38-41).  Same legacy stream => same indices."""
+    n, B, steps = 987_654, 256, 7
+    a, b = np.random.RandomState(11), np.random.RandomState(11)
+    seq = np.array([[a.randint(n) for _ in range(B)] for _ in range(steps)])
+    blk = b.randint(n, size=(steps, B))
+    assert np.array_equal(seq, blk)
+
+
+def test_header_prototypes_parse_and_cover_all_sources():
+    """Every extern "C" d3b_* definition in csrc/ is declared in include/d3rlpy_b200.h (and vice versa)."""
+    import glob
+    import re
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    declared = set(parse_header().keys())
+    defined = set()
+    for f in glob.glob(os.path.join(here, "..", "d3rlpy_b200", "csrc", "*.cu")):
+        defined |= set(re.findall(r'extern "C"\s+[\w\s\*]+?\b(d3b_\w+)\s*\(', open(f).read()))
+    assert declared == defined, (sorted(declared - defined), sorted(defined - declared))
