@@ -212,10 +212,16 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + flag_index, e);
   }
   __syncthreads();
-  const int t = *a.step;
-  const double bc1 = 1.0 - pow(a.b1, (double)t), bc2 = 1.0 - pow(a.b2, (double)t);
+  __shared__ float sc[2];
+  if (threadIdx.x == 0) {  // double pow/sqrt once per block
+    const int t = *a.step;
+    const double bc1 = 1.0 - pow(a.b1, (double)t), bc2 = 1.0 - pow(a.b2, (double)t);
+    sc[0] = (float)(-(a.lr / bc1));
+    sc[1] = (float)sqrt(bc2);
+  }
+  __syncthreads();
   const float w1 = (float)(1.0 - a.b1), fb2 = (float)a.b2, w2 = (float)(1.0 - a.b2), feps = (float)a.eps;
-  const float neg_ss = (float)(-(a.lr / bc1)), bc2s = (float)sqrt(bc2);
+  const float neg_ss = sc[0], bc2s = sc[1];
   const float one_m_tau = (float)(1.0 - (double)a.tau);
   const long long n4 = a.n >> 2;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {

@@ -74,34 +74,35 @@ __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  // 32-bit index arithmetic (the host checks that the row count fits): 64-bit divisions are slow on the GPU
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int B = p.B, N = p.N, O = p.O, A = p.A;
-  const long long BN = (long long)B * N;
-  const long long R = (long long)B + 3 * BN;
-  const long long n_is = R * p.n_groups;
+  const int BN = B * N;
+  const int R = B + 3 * BN;
+  const int n_is = R * p.n_groups;
   const float* obs_row;
   __nv_bfloat16* x = nullptr;
   // decode
   int kind;         // 0 data, 1 pi(s_t), 2 pi(s_tp1), 3 random, 4 target, 5 actor, 6 temp
   int b, k = 0, g = 0;
   if (item < n_is) {
-    g = (int)(item / R);
-    long long r = item - (long long)g * R;
-    if (r < B) { kind = 0; b = (int)r; }
+    g = item >= R ? 1 : 0;
+    int r = item - g * R;
+    if (r < B) { kind = 0; b = r; }
     else {
       r -= B;
-      kind = 1 + (int)(r / BN);
-      r -= (long long)(kind - 1) * BN;
-      b = (int)(r / N);
-      k = (int)(r % N);
+      kind = 1 + r / BN;
+      r -= (kind - 1) * BN;
+      b = r / N;
+      k = r - b * N;
     }
-    x = p.X + (p.group_row0[g] + (item - (long long)g * R)) * p.ldx;
+    x = p.X + (p.group_row0[g] + (long long)(item - g * R)) * p.ldx;
     obs_row = p.obs + (long long)b * O;
   } else {
-    long long r = item - n_is;
-    if (r < B) { kind = 4; b = (int)r; x = p.X + (p.target_row0 + b) * p.ldx; obs_row = p.next_obs + (long long)b * O; }
-    else if (r < 2LL * B) { kind = 5; b = (int)(r - B); x = p.X + (p.actor_row0 + b) * p.ldx; obs_row = p.obs + (long long)b * O; }
-    else if (r < 3LL * B && p.eps_temp) { kind = 6; b = (int)(r - 2LL * B); obs_row = nullptr; }
+    int r = item - n_is;
+    if (r < B) { kind = 4; b = r; x = p.X + (p.target_row0 + b) * p.ldx; obs_row = p.next_obs + (long long)b * O; }
+    else if (r < 2 * B) { kind = 5; b = r - B; x = p.X + (p.actor_row0 + b) * p.ldx; obs_row = p.obs + (long long)b * O; }
+    else if (r < 3 * B && p.eps_temp) { kind = 6; b = r - 2 * B; obs_row = nullptr; }
     else return;
   }
   if (x) {
@@ -387,6 +388,7 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
   D3B_REQUIRE(!p.eps_soft || p.logp_soft, "cql_rows: null soft-backup log-prob pointer");
   p.target_row0 = rows_host[2]; p.actor_row0 = rows_host[3];
   long long items = ((long long)batch + 3LL * batch * n_action_samples) * n_groups + 3LL * batch;
+  D3B_REQUIRE(items < (1LL << 30), "cql_rows: too many rows for one launch");
   launch_pdl(cql_rows_kernel, dim3((unsigned)ceil_div_ll(items, 8)), dim3(256), 0, ST, p);
   return check_launch("cql_rows");
 }

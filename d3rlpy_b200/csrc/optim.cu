@@ -31,6 +31,16 @@ __device__ __forceinline__ void adam_scalars(const int* step, double lr, double 
   bc2_sqrt = (float)sqrt(bc2);
 }
 
+// the bias corrections need double pow/sqrt: evaluate them once per block, not once per thread
+__device__ __forceinline__ void adam_scalars_block(const int* step, double lr, double b1, double b2, double eps,
+                                                   float& w1, float& fb2, float& w2, float& feps, float& neg_ss,
+                                                   float& bc2_sqrt) {
+  __shared__ float sc[6];
+  if (threadIdx.x == 0) adam_scalars(step, lr, b1, b2, eps, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5]);
+  __syncthreads();
+  w1 = sc[0]; fb2 = sc[1]; w2 = sc[2]; feps = sc[3]; neg_ss = sc[4]; bc2_sqrt = sc[5];
+}
+
 __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, float w1, float fb2, float w2,
                                           float feps, float neg_ss, float bc2_sqrt) {
   // lerp (weight < 0.5 branch of ATen's lerp; its vectorised CPU form is fmadd(w, g - m, m))
@@ -48,7 +58,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    float* __restrict__ targ, long long n, const int* step, double lr,
                                                    double b1, double b2, double eps, float tau, int zero_grad) {
   float w1, fb2, w2, feps, neg_ss, bc2s;
-  adam_scalars(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
   float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
   long long n4 = n >> 2;
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,7 +117,7 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ p,
   pdl_trigger();
   pdl_wait();
   float w1, fb2, w2, feps, neg_ss, bc2s;
-  adam_scalars(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
   float one_m_tau = (float)(1.0 - (double)tau);
   long long n4 = n >> 2;  // arenas are padded to multiples of 4 floats per member
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
