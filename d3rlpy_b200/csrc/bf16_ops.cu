@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(256) to_bf16_kernel(const float* __restrict__ 
 }
 
 // One warp per (member,row): Y[e][m][n] = act(X_bf16[e][m][:] . W[e][n][:] + b[e][n]), fp32 weights.
+// The activation row is read ONCE into registers (KPL values per lane); four outputs are accumulated at a time
+// with all their weight loads issued together (4*KPL independent loads in flight per lane).
+template <int KPL>
 __global__ void __launch_bounds__(256) head_forward_bf16_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
                                                                 long long sX, const float* __restrict__ W,
                                                                 long long ldw, long long sW,
@@ -73,12 +76,43 @@ __global__ void __launch_bounds__(256) head_forward_bf16_kernel(const __nv_bfloa
   const __nv_bfloat16* x = X + (long long)e * sX + (long long)m * ldx;
   const float* w = W + (long long)e * sW;
   float mine = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* wr = w + (long long)n * ldw;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(x[k]), __ldg(wr + k), s);
-    s = warp_sum(s);
-    if (lane == n) mine = s;
+  if (K <= 32 * KPL) {
+    float xr[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      int k = lane + 32 * i;
+      xr[i] = k < K ? __bfloat162float(x[k]) : 0.f;
+    }
+    for (int n0 = 0; n0 < N; n0 += 4) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* w0 = w + (long long)n0 * ldw;
+      const float* w1 = w + (long long)(n0 + 1 < N ? n0 + 1 : n0) * ldw;
+      const float* w2 = w + (long long)(n0 + 2 < N ? n0 + 2 : n0) * ldw;
+      const float* w3 = w + (long long)(n0 + 3 < N ? n0 + 3 : n0) * ldw;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        int k = lane + 32 * i;
+        if (k < K) {
+          s0 = fmaf(xr[i], __ldg(w0 + k), s0);
+          s1 = fmaf(xr[i], __ldg(w1 + k), s1);
+          s2 = fmaf(xr[i], __ldg(w2 + k), s2);
+          s3 = fmaf(xr[i], __ldg(w3 + k), s3);
+        }
+      }
+      s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+      if (lane == n0) mine = s0;
+      if (lane == n0 + 1) mine = s1;
+      if (lane == n0 + 2) mine = s2;
+      if (lane == n0 + 3) mine = s3;
+    }
+  } else {
+    for (int n = 0; n < N; ++n) {
+      const float* wr = w + (long long)n * ldw;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s = fmaf(__bfloat162float(x[k]), __ldg(wr + k), s);
+      s = warp_sum(s);
+      if (lane == n) mine = s;
+    }
   }
   if (lane < N) {
     float v = mine + (bias ? __ldg(bias + (long long)e * sB + lane) : 0.f);
@@ -214,9 +248,14 @@ extern "C" int d3b_head_forward_bf16(const void* x, int64_t ldx, int64_t stride_
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && w && y, "head_forward_bf16: null pointer");
   long long warps = (long long)rows * members;
-  head_forward_bf16_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(
-      (const __nv_bfloat16*)x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features,
-      in_features, members, act_tanh);
+  if (in_features <= 256)
+    head_forward_bf16_kernel<8><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(
+        (const __nv_bfloat16*)x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features,
+        in_features, members, act_tanh);
+  else
+    head_forward_bf16_kernel<24><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(
+        (const __nv_bfloat16*)x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features,
+        in_features, members, act_tanh);
   return check_launch("head_forward_bf16");
 }
 

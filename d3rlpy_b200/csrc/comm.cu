@@ -133,9 +133,10 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 }
 // bounded spin (a rank that never arrives becomes a trapped launch error instead of a hung box)
 __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
+  // ~1 minute of tolerated rank skew (e.g. a rank still staging its data) before the trap
   for (unsigned spins = 0; ld_acquire_sys(p) < v; ++spins) {
-    if (spins > (1u << 22)) __trap();
-    __nanosleep(64);
+    if (spins > (1u << 25)) __trap();
+    __nanosleep(spins < 1024 ? 32 : 512);
   }
 }
 
