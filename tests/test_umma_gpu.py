@@ -213,6 +213,10 @@ def test_umma_wgrad_mn_major_operands(R, No, Ki, E, shared_b):
     (1000, 2, 119, [64, 128, 16, 256], 24, False, True),  # 4 layers, mixed widths, wide head
     (200, 2, 40, [64], 0, False, False),                # single layer, trunk only, per-member input
     (40000, 2, 23, [256, 256, 256], 1, False, True),    # several units per CTA (persistent loop, phase wrap)
+    (1, 1, 1, [16], 1, False, True),                    # smallest legal problem
+    (129, 3, 256, [240, 48, 80], 5, True, True),        # widths that are not multiples of 64, K_0 = 256
+    (127, 2, 7, [16, 256, 16], 32, False, False),       # 32 heads (CUDA-core head, 3-stage ring)
+    (513, 1, 65, [192, 192, 192, 192], 2, False, True), # K_0 just above one K block, 4 layers
 ])
 def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, shared):
     """csrc/mlp_fused.cu vs torch on the same bf16-rounded operands (fp32 accumulate, bf16 activations):
@@ -294,6 +298,10 @@ def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, 
     (1000, 2, 119, [64, 128, 16, 256], 8, True, (100, 19)),
     (200, 2, 40, [64], 3, True, (0, 40)),                # single layer
     (40000, 2, 23, [256, 256, 256], 1, True, None),      # several units per CTA
+    (1, 1, 1, [16], 1, True, (0, 1)),                    # smallest legal problem
+    (129, 3, 256, [240, 48, 80], 5, True, (250, 6)),     # widths that are not multiples of 64, dx at the right edge
+    (127, 2, 9, [16, 256, 16], 16, True, (1, 8)),        # 16 heads
+    (513, 1, 65, [192, 192, 192, 192], 2, False, (3, 61)),
 ])
 def test_fused_mlp_backward_matches_torch(rows, E, in_dim, hidden, n_head, wg, dxr):
     """csrc/mlp_fused.cu backward chain vs torch on the same bf16 operands, stage by stage."""
