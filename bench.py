@@ -164,7 +164,9 @@ def run_reference(args, w):
     obs, act, rew, term = make_dataset(w, steps_total=50_000)
     batches = host_batches(w, 4, obs, act, rew, term)
     cores = os.cpu_count() or 1
-    threads = cores
+    # the reference arm gets its best thread count: short probe at {cores/2, cores}, full run with the faster one
+    probes = {th: time_oracle(w, batches, th, 4, 1, budget_s=20.0)[0] for th in sorted({max(1, cores // 2), cores})}
+    threads = max(probes, key=probes.get)
     rate, done, dt = time_oracle(w, batches, threads, args.steps, min(args.warmup, 3), budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "updates/s", "n_gpus": args.gpus,
