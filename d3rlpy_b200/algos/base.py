@@ -110,6 +110,19 @@ class AlgoBase:
     def _update(self, batch) -> Dict[str, float]:
         raise NotImplementedError
 
+    # ------------------------------------------------------------------ evaluation (algos/base.py:predict/predict_value)
+    def predict(self, x):
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        return self._impl.predict_best_action(x)
+
+    def predict_value(self, x, action, with_std: bool = False):
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        return self._impl.predict_value(x, action, with_std)
+
+    def sample_action(self, x):
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        return self._impl.sample_action(x)
+
     # ------------------------------------------------------------------ fit over an HBM-resident replay
     def fit(self, dataset, n_steps: int, n_steps_per_epoch: int = 10000, shuffle: bool = True,
             seed: Optional[int] = None, verbose: bool = False) -> List[Dict[str, float]]:

@@ -495,6 +495,26 @@ class CQLImpl(DDPGBaseImpl):
         return self.read_slots()[M_ACTOR].copy()
 
 
+    # ---- evaluation API
+    def _predict_best_action(self, obs: torch.Tensor) -> torch.Tensor:
+        """SquashedNormalPolicy.best_action = tanh(mu) (policies.py:247-249)."""
+        head = self._policy_head(obs, head_tanh=False)
+        return torch.tanh(head[0, :, :self._action_size])
+
+    def sample_action(self, x) -> np.ndarray:
+        """policy.sample (policies.py:167-181): tanh(mu + exp(clamp(logstd)) eps), eps ~ N(0, 1)."""
+        obs = self._eval_obs(x)
+        n, A = obs.shape[0], self._action_size
+        head = self._policy_head(obs, head_tanh=False)
+        with torch.cuda.stream(self._stream_obj):
+            eps = torch.randn(1, n, A, device=self._device)
+        act = self.ws("eval_act", n, A)
+        self._lib.policy_sample_rows(head.data_ptr(), 2 * A, eps.data_ptr(), None, 0, None, 0, act.data_ptr(), None, n,
+                                     1, 0, A, MIN_LOGSTD, MAX_LOGSTD, 0, self._stream)
+        self.sync()
+        return act.detach().cpu().numpy()
+
+
 class _TensorBatch:
     """Adapter so the three-tensor `_compute_conservative_loss(obs_t, act_t, obs_tp1)` signature can
     reuse the minibatch staging path."""

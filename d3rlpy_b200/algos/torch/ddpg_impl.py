@@ -139,3 +139,48 @@ class DDPGBaseImpl(ImplBase):
     def _metrics_dict(self, names):
         vals = self.read_slots_after_program()
         return {n: np.float32(vals[i]) for i, n in names}
+
+    # ------------------------------------------------------------------ evaluation API (algos/torch/base.py:52-84,
+    # algos/torch/utility.py:51-78): used by scorers / deployment, eager launches + one sync
+    def _eval_obs(self, x) -> torch.Tensor:
+        """numpy / tensor observations -> float32 device rows with the observation scaler applied."""
+        t = torch.as_tensor(np.asarray(x.detach().cpu() if isinstance(x, torch.Tensor) else x), dtype=torch.float32)
+        assert t.ndim > 1, "Input must have batch dimension."
+        with torch.cuda.stream(self._stream_obj):
+            d = t.to(self._device, non_blocking=False).contiguous()
+        if self._scaler is not None:
+            mean, std, eps = self._scaler_params()
+            self._lib.standardize(d.data_ptr(), mean.data_ptr(), std.data_ptr(), eps, d.shape[0], d.shape[1],
+                                  self._stream)
+        return d
+
+    def _policy_head(self, obs: torch.Tensor, head_tanh: bool) -> torch.Tensor:
+        n = obs.shape[0]
+        out = self.ws("eval_head", 1, n, self._policy.head_out)
+        self._policy.forward("params", obs, obs.shape[1], n, self._policy.ctx("eval_pi", n, 1, False), out,
+                             self._stream, head_tanh=head_tanh)
+        return out
+
+    def _predict_best_action(self, obs: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def predict_best_action(self, x) -> np.ndarray:
+        obs = self._eval_obs(x)
+        a = self._predict_best_action(obs)
+        self.sync()
+        return a.detach().cpu().numpy()
+
+    def predict_value(self, x, action, with_std: bool = False):
+        """ContinuousQFunctionMixin.predict_value (algos/torch/utility.py:51-78): mean (and std) over members."""
+        obs = self._eval_obs(x)
+        act = torch.as_tensor(np.asarray(action), dtype=torch.float32).to(self._device).contiguous()
+        assert obs.shape[0] == act.shape[0]
+        n, O, A = obs.shape[0], obs.shape[1], self._action_size
+        rows = self.ws("eval_x", n, O + A)
+        self._lib.concat_rows(obs.data_ptr(), O, act.data_ptr(), A, None, 0.0, 0.0, 0.0, rows.data_ptr(), O + A, n, 1,
+                              O, A, self._stream)
+        _, q = self._critic_rows_forward("params", rows, n, "eval_q", train=False)
+        self.sync()
+        values = q.detach().cpu().numpy()                     # [E, n]
+        mean, std = values.mean(axis=0), values.std(axis=0)
+        return (mean, std) if with_std else mean

@@ -180,6 +180,45 @@ class DQNImpl(ImplBase):
         self._p_hard_sync()
 
 
+class _EvalBatch:
+    """Staging shim: observations only (the evaluation API reuses the minibatch upload path)."""
+
+    def __init__(self, x, n_act=1):
+        x = np.asarray(x)
+        n = x.shape[0]
+        self.observations = self.next_observations = x
+        self.actions = np.zeros(n, np.float32)
+        self.rewards = self.terminals = np.zeros((n, 1), np.float32)
+        self.n_steps = np.ones((n, 1), np.float32)
+
+
+def _dqn_q_values(impl, x) -> np.ndarray:
+    """Q(s, .) of every member: [E, n, A] (eager forward of the online network, one sync)."""
+    db = impl.load_batch(_EvalBatch(x))
+    _, q = impl._forward("params", db, "obs", "eval", False)
+    impl.sync()
+    return q.detach().cpu().numpy()
+
+
+def _dqn_predict_best_action(self, x) -> np.ndarray:
+    """argmax_a mean_e Q_e(s, a) (dqn_impl.py:147-149)."""
+    return _dqn_q_values(self, x).mean(axis=0).argmax(axis=1)
+
+
+def _dqn_predict_value(self, x, action, with_std: bool = False):
+    """DiscreteQFunctionMixin.predict_value (algos/torch/utility.py:22-49)."""
+    values = _dqn_q_values(self, x)                                # [E, n, A]
+    a = np.asarray(action).reshape(-1).astype(np.int64)
+    picked = values[:, np.arange(values.shape[1]), a]              # [E, n]
+    mean, std = picked.mean(axis=0), picked.std(axis=0)
+    return (mean, std) if with_std else mean
+
+
+DQNImpl.predict_best_action = _dqn_predict_best_action
+DQNImpl.sample_action = _dqn_predict_best_action
+DQNImpl.predict_value = _dqn_predict_value
+
+
 class DoubleDQNImpl(DQNImpl):
     DOUBLE = True
 

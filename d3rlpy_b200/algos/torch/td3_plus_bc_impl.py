@@ -222,3 +222,11 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             self._p_actor(db)
         finally:
             self._tau = tau
+
+    # ---- evaluation API
+    def _predict_best_action(self, obs: torch.Tensor) -> torch.Tensor:
+        """DeterministicPolicy.best_action = tanh(fc(encoder(x))) (policies.py:57-79)."""
+        return self._policy_head(obs, head_tanh=True)[0]
+
+    def sample_action(self, x) -> np.ndarray:
+        return self.predict_best_action(x)

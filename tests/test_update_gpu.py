@@ -437,3 +437,50 @@ def test_discrete_cql_pixel_bf16_tensor_core_conv_path():
         g = m_sd[k].cpu().reshape(r.shape)
         cos = float((g * r).sum() / (g.norm() * r.norm() + 1e-30))
         assert cos >= 0.98, (k, cos)
+
+
+def test_predict_api_matches_oracle():
+    """predict / predict_value (algos/base.py, algos/torch/utility.py:22-78) vs the oracle networks."""
+    from d3rlpy_b200.algos import CQL, DiscreteCQL, TD3PlusBC
+
+    rs = np.random.RandomState(3)
+    O, A, n = 9, 4, 37
+    x = rs.randn(n, O).astype(np.float32)
+    a = rs.uniform(-1, 1, (n, A)).astype(np.float32)
+    # CQL
+    orc = ou.CQL(O, A, hidden=[32, 32], n_action_samples=3, seed=1)
+    algo = CQL(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], n_action_samples=3)
+    algo.create_impl((O,), A)
+    algo.impl.q_function.load_state_dict(orc.q)
+    algo.impl.policy.load_state_dict(orc.pi)
+    with torch.no_grad():
+        ref_a = ou.policy_best_action(orc.pi, torch.tensor(x)).numpy()
+        ref_q = ou.q_continuous(orc.q, torch.tensor(x), torch.tensor(a), "none").numpy()[:, :, 0]
+    np.testing.assert_allclose(algo.predict(x), ref_a, rtol=1e-5, atol=1e-6)
+    mean, std = algo.predict_value(x, a, with_std=True)
+    np.testing.assert_allclose(mean, ref_q.mean(0), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(std, ref_q.std(0), rtol=1e-4, atol=1e-5)
+    s = algo.sample_action(x)
+    assert s.shape == (n, A) and np.all(np.abs(s) <= 1.0)
+    # TD3+BC with the standard scaler
+    from d3rlpy_b200.preprocessing import StandardScaler
+
+    mean_o, std_o = x.mean(0), x.std(0)
+    orc = ou.TD3PlusBC(O, A, hidden=[32, 32], seed=2)
+    algo = TD3PlusBC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], scaler=StandardScaler(mean=mean_o, std=std_o))
+    algo.create_impl((O,), A)
+    algo.impl.policy.load_state_dict(orc.pi)
+    xs = ou.standard_scaler(mean_o, std_o)(torch.tensor(x))
+    with torch.no_grad():
+        ref_a = ou.deterministic_policy(orc.pi, xs).numpy()
+    np.testing.assert_allclose(algo.predict(x), ref_a, rtol=1e-5, atol=1e-6)
+    # DiscreteCQL (vector)
+    orc = ou.DiscreteCQL((O,), 5, n_critics=2, hidden=[32, 32], seed=4)
+    algo = DiscreteCQL(encoder_factory=[32, 32], n_critics=2)
+    algo.create_impl((O,), 5)
+    algo.impl.q_function.load_state_dict(orc.q)
+    with torch.no_grad():
+        qv = ou.q_discrete(orc.q, torch.tensor(x), "none").numpy()     # [E, n, A]
+    assert np.array_equal(algo.predict(x), qv.mean(0).argmax(1))
+    act = rs.randint(0, 5, n)
+    np.testing.assert_allclose(algo.predict_value(x, act), qv.mean(0)[np.arange(n), act], rtol=1e-5, atol=1e-5)
