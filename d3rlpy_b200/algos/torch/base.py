@@ -181,6 +181,34 @@ class ImplBase:
         self.sync()
         return self._slots_host.numpy()
 
+    # ------------------------------------------------------------------ checkpoints
+    def _checkpoint_views(self):
+        raise NotImplementedError
+
+    def save_model(self, fname: str) -> None:
+        """torch.save({attr: state_dict}) with the reference's attribute names and state_dict keys
+        (algos/torch/base.py:137-139, torch_utility.py:97-103), so either side can load the other's file."""
+        self.sync()
+        torch.cuda.synchronize(self._device)
+
+        def cpu(o):
+            if isinstance(o, torch.Tensor):
+                return o.detach().cpu().clone()
+            if isinstance(o, dict):
+                return type(o)((k, cpu(v)) for k, v in o.items())
+            if isinstance(o, list):
+                return [cpu(v) for v in o]
+            return o
+
+        torch.save({k: cpu(v.state_dict()) for k, v in self._checkpoint_views().items()}, fname)
+
+    def load_model(self, fname: str) -> None:
+        """set_state_dict (torch_utility.py:106-110): every module / optimizer attribute is restored."""
+        chkpt = torch.load(fname, map_location="cpu", weights_only=False)
+        for k, v in self._checkpoint_views().items():
+            v.load_state_dict(chkpt[k])
+        torch.cuda.synchronize(self._device)
+
     # ------------------------------------------------------------------ batches
     def _make_batch(self, B: int) -> DeviceBatch:
         pixel = self._observation_shape if len(self._observation_shape) == 3 else None

@@ -33,8 +33,8 @@ class _ImitatorView:
     def __init__(self, enc: DenseNet, dec: DenseNet):
         self._enc, self._dec = enc, dec
 
-    def state_dict(self):
-        e, d = self._enc.arena.state_dict(), self._dec.arena.state_dict()
+    def state_dict(self, which: str = "params"):
+        e, d = self._enc.arena.state_dict(which), self._dec.arena.state_dict(which)
         out = OrderedDict()
         for k, v in e.items():
             if k.startswith("_encoder_encoder."):
@@ -90,6 +90,16 @@ class BCQImpl(DDPGBaseImpl):
     @property
     def imitator(self):
         return _ImitatorView(self._vae_enc, self._vae_dec)
+
+    def _checkpoint_views(self):
+        from .ddpg_impl import _OptimView
+
+        v = super()._checkpoint_views()
+        im = self.imitator
+        v.update({"_imitator": im,
+                  "_imitator_optim": _OptimView(lambda which: im.state_dict(which), self._vae_enc.arena.step,
+                                                self._imitator_learning_rate)})
+        return v
 
     def noise_layout(self, B):
         """Draw order: imitator eps (B,2A); critic randn(B*N,2A); actor randn(B,2A)."""

@@ -44,6 +44,17 @@ class _Scalar:
     def load_state_dict(self, sd):
         self.buf[0] = float(sd["_parameter"].reshape(-1)[0])
 
+    def optim_view(self, lr: float):
+        """Adam state of the scalar in torch.optim layout (one (1,1) parameter)."""
+        from collections import OrderedDict
+
+        def sd_of(which):
+            i = {"params": 0, "exp_avg": 8, "exp_avg_sq": 12}[which]
+            return OrderedDict([("_parameter", self.buf[i:i + 1].view(1, 1))])
+
+        from .ddpg_impl import _OptimView
+        return _OptimView(sd_of, self.step, lr)
+
 
 class CQLImpl(DDPGBaseImpl):
     def __init__(self, *, temp_learning_rate=1e-4, alpha_learning_rate=1e-4, initial_temperature=1.0,
@@ -494,6 +505,13 @@ class CQLImpl(DDPGBaseImpl):
         self._p_actor(db, acts_p, head, sync_target=False)
         return self.read_slots()[M_ACTOR].copy()
 
+
+    def _checkpoint_views(self):
+        v = super()._checkpoint_views()
+        v.update({"_log_temp": self._log_temp, "_log_alpha": self._log_alpha,
+                  "_temp_optim": self._log_temp.optim_view(self._temp_learning_rate),
+                  "_alpha_optim": self._log_alpha.optim_view(self._alpha_learning_rate)})
+        return v
 
     # ---- evaluation API
     def _predict_best_action(self, obs: torch.Tensor) -> torch.Tensor:

@@ -36,20 +36,45 @@ class _ModuleView:
 
 
 class _OptimView:
-    """`torch.optim.Adam.state_dict()`-shaped view of the fused optimizer state."""
+    """`torch.optim.Adam.state_dict()` / `load_state_dict()`-shaped view of the fused optimizer state of one parameter
+    group.  `sd_of(which)` returns the OrderedDict of named tensors for which in {params, exp_avg, exp_avg_sq};
+    parameter index i of the torch optimizer == i-th key of the module's state_dict (registration order)."""
 
-    def __init__(self, net: DenseNet, lr: float):
-        self._net, self.lr = net, lr
+    def __init__(self, sd_of, step: torch.Tensor, lr: float):
+        self._sd_of, self._step, self.lr = sd_of, step, lr
 
     def state_dict(self):
-        a = self._net.arena
-        keys = list(a.state_dict().keys())
-        m, v = a.state_dict("exp_avg"), a.state_dict("exp_avg_sq")
-        step = int(a.step.item())
-        state = {i: {"step": torch.tensor(float(step)), "exp_avg": m[k], "exp_avg_sq": v[k]} for i, k in enumerate(keys)}
-        return {"state": state if step > 0 else {},
-                "param_groups": [{"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0,
-                                  "amsgrad": False, "params": list(range(len(keys)))}]}
+        keys = list(self._sd_of("params").keys())
+        m, v = self._sd_of("exp_avg"), self._sd_of("exp_avg_sq")
+        step = int(self._step.item())
+        state = {i: {"step": torch.tensor(float(step)), "exp_avg": m[k].detach().cpu().clone(),
+                     "exp_avg_sq": v[k].detach().cpu().clone()} for i, k in enumerate(keys)}
+        # same group keys as torch 2.11's Adam (tests/golden/checkpoint_keys.json, recorded from the reference)
+        group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(keys)))}
+        return {"state": state if step > 0 else {}, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        keys = list(self._sd_of("params").keys())
+        state = sd.get("state", {})
+        m, v = self._sd_of("exp_avg"), self._sd_of("exp_avg_sq")
+        step = 0
+        with torch.no_grad():
+            for i, k in enumerate(keys):
+                st = state.get(i, state.get(str(i)))
+                if st is None:
+                    m[k].zero_()
+                    v[k].zero_()
+                    continue
+                m[k].copy_(torch.as_tensor(st["exp_avg"]).to(m[k].device, torch.float32).reshape(m[k].shape))
+                v[k].copy_(torch.as_tensor(st["exp_avg_sq"]).to(v[k].device, torch.float32).reshape(v[k].shape))
+                step = int(float(st["step"]))
+            self._step.fill_(step)
+
+
+def _net_optim(net: DenseNet, lr: float) -> _OptimView:
+    return _OptimView(lambda which: net.arena.state_dict(which), net.arena.step, lr)
 
 
 class DDPGBaseImpl(ImplBase):
@@ -103,11 +128,19 @@ class DDPGBaseImpl(ImplBase):
 
     @property
     def policy_optim(self):
-        return _OptimView(self._policy, self._actor_learning_rate)
+        return _net_optim(self._policy, self._actor_learning_rate)
 
     @property
     def q_function_optim(self):
-        return _OptimView(self._q_func, self._critic_learning_rate)
+        return _net_optim(self._q_func, self._critic_learning_rate)
+
+    # ------------------------------------------------------------------ checkpoints (algos/torch/base.py:137-142)
+    def _checkpoint_views(self):
+        """attribute name -> state_dict view, the keys torch_utility.get_state_dict (torch_utility.py:97-110) finds on
+        the reference impl."""
+        return {"_q_func": self.q_function, "_targ_q_func": self.targ_q_function, "_policy": self.policy,
+                "_targ_policy": self.targ_policy, "_critic_optim": self.q_function_optim,
+                "_actor_optim": self.policy_optim}
 
     # ------------------------------------------------------------------ shared program pieces
     def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0, train=True):

@@ -14,7 +14,7 @@ import torch
 
 from ...nets import ConvNet, DenseNet
 from .base import ImplBase
-from .ddpg_impl import C_CRITIC, _ModuleView, _OptimView
+from .ddpg_impl import C_CRITIC, _ModuleView, _net_optim
 
 M_LOSS = 0
 S_LOSS = 0
@@ -75,7 +75,10 @@ class DQNImpl(ImplBase):
 
     @property
     def q_function_optim(self):
-        return _OptimView(self._q_func, self._learning_rate)
+        return _net_optim(self._q_func, self._learning_rate)
+
+    def _checkpoint_views(self):
+        return {"_q_func": self.q_function, "_targ_q_func": self.targ_q_function, "_optim": self.q_function_optim}
 
     # ------------------------------------------------------------------ program pieces
     def _forward(self, which, db, field, tag, train):

@@ -78,12 +78,11 @@ class DenseNet:
         # reference's per-head names are exported as row slices of it
         entries.append(("__head.weight", (self.head_out, d)))
         entries.append(("__head.bias", (self.head_out,)))
+        # registration order of the reference modules: head by head, weight then bias (it is also the parameter
+        # order of the torch optimizers, i.e. the index space of their state_dict)
         exports, r0 = [], 0
         for name, n in self.heads:
             exports.append((f"{name}.weight", "__head.weight", r0, n))
-            r0 += n
-        r0 = 0
-        for name, n in self.heads:
             exports.append((f"{name}.bias", "__head.bias", r0, n))
             r0 += n
         self.arena = ParamArena(entries, members, device, with_target=with_target, member_key=member_key,
@@ -472,9 +471,6 @@ class ConvNet:
         exports, r0 = [], 0
         for name, n in self.heads:
             exports.append((f"{name}.weight", "__head.weight", r0, n))
-            r0 += n
-        r0 = 0
-        for name, n in self.heads:
             exports.append((f"{name}.bias", "__head.bias", r0, n))
             r0 += n
         self.arena = ParamArena(entries, members, device, with_target=with_target, member_key=member_key,
