@@ -295,14 +295,23 @@ class CQLImpl(DDPGBaseImpl):
         q_net = self._q_func
         # ---- side branch (independent of the importance-sampling pass): temperature step, target critics
         side = self._side_stream()
-        if do_temp and dp:
-            # NCCL calls of one communicator must be issued in one order on every rank: keep them on the main
-            # stream (graph branches could reorder them); per-rank partial loss (== gradient) -> all-reduce -> Adam
-            L.sac_temp_loss(lpm[2].data_ptr(), lt.ptr("p"), B, A, inv_b, self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 0, st)
-            self._small_allreduce(px, lt.buf[4:5], 0)
-            L.copy_d2d(self.metric_ptr(M_TEMP_LOSS), lt.ptr("g"), 4, st)
-            L.scalar_adam(lt.ptr("p"), lt.ptr("g"), lt.ptr("m"), lt.ptr("v"), self.counter_ptr(C_TEMP),
+        # data parallel: per-rank partial loss (== gradient of log_temp) -> all-reduce -> Adam.  Collectives stay on
+        # the main stream (graph branches could reorder them across ranks).  Unless the soft backup needs the new
+        # temperature for the target, the exchange is merged with the alpha step's (one rendezvous instead of two):
+        # the temperature partial sum lands in the free fourth float of the alpha sums.
+        temp_merged = do_temp and dp and do_alpha and not soft
+        temp_g = self.sums_ptr(S_ALPHA + 3) if temp_merged else lt.ptr("g")
+
+        def temp_adam():
+            L.copy_d2d(self.metric_ptr(M_TEMP_LOSS), temp_g, 4, st)
+            L.scalar_adam(lt.ptr("p"), temp_g, lt.ptr("m"), lt.ptr("v"), self.counter_ptr(C_TEMP),
                           self._temp_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_TEMP), st)
+
+        if do_temp and dp:
+            L.sac_temp_loss(lpm[2].data_ptr(), lt.ptr("p"), B, A, inv_b, self.metric_ptr(M_TEMP_LOSS), temp_g, 0, st)
+            if not temp_merged:
+                self._small_allreduce(px, lt.buf[4:5], 0)
+                temp_adam()
         L.stream_fork(st, side)
         if do_temp and not dp:
             L.sac_temp_step(lpm[2].data_ptr(), lt.buf.data_ptr(), self.counter_ptr(C_TEMP), B, A, inv_b,
@@ -328,7 +337,9 @@ class CQLImpl(DDPGBaseImpl):
             L.critic_loss(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma, lp[2].data_ptr(),
                           lp[3].data_ptr(), N, A, la.ptr("p"), self._conservative_weight, None, 0,
                           self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, st)
-            self._small_allreduce(px, self._slots[32 + S_ALPHA:32 + S_ALPHA + 3], 1)
+            self._small_allreduce(px, self._slots[32 + S_ALPHA:32 + S_ALPHA + (4 if temp_merged else 3)], 1)
+            if temp_merged:
+                temp_adam()
             L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
                            self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
             L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
@@ -348,14 +359,16 @@ class CQLImpl(DDPGBaseImpl):
                           self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.ptr("p"), self._conservative_weight,
                           dq.data_ptr(), R, self.sums_ptr(S_CRITIC), None, B, E, inv_b, 1, st)
         q_net.backward(None, 0, R, ctx, dq, st)
+        # the loss partial sums only feed the reported metric: with the peer exchange they ride along with the
+        # gradient all-reduce inside the Adam kernel (no rendezvous of their own)
+        csum = self._slots[32 + S_CRITIC:32 + S_CRITIC + 3]
+        if dp and px is None:
+            self._allreduce(csum)
+            self._allreduce(q_net.arena.grads)
+        q_net.adam(self._critic_learning_rate, st, tau=self._tau, peer=self._peer_args(px, q_net, (csum, 2)))
         if dp:
-            # the loss partial sums only feed the reported metric: they ride along with the gradient exchange
-            self._small_allreduce(px, self._slots[32 + S_CRITIC:32 + S_CRITIC + 3], 2)
             L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
                            self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
-            if px is None:
-                self._allreduce(q_net.arena.grads)
-        q_net.adam(self._critic_learning_rate, st, tau=self._tau, peer=self._peer_args(px, q_net))
         # actor step on the updated critics
         ctx_a = q_net.ctx("aq", B, E, True)
         qa = self.ws("aq_q", E, B)
@@ -374,12 +387,14 @@ class CQLImpl(DDPGBaseImpl):
         L.sac_actor_backward(head.data_ptr(), 2 * A, nv("actor"), dxa.data_ptr(), A, B * A, E, lt.ptr("p"),
                              dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
         self._policy_backward_rows(db, acts_p, dhead, B)
+        asum = self._slots[32 + S_ACTOR:32 + S_ACTOR + 1]
+        if dp and px is None:
+            self._allreduce(asum)
+            self._allreduce(self._policy.arena.grads)
+        self._policy.adam(self._actor_learning_rate, st, tau=self._tau,
+                          peer=self._peer_args(px, self._policy, (asum, 3)))
         if dp:
-            self._small_allreduce(px, self._slots[32 + S_ACTOR:32 + S_ACTOR + 1], 3)
             L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
-            if px is None:
-                self._allreduce(self._policy.arena.grads)
-        self._policy.adam(self._actor_learning_rate, st, tau=self._tau, peer=self._peer_args(px, self._policy))
 
     # ---- NVLink peer-memory exchange (csrc/comm.cu): all-reduce fused into the Adam pass, no NCCL in the update
     def _peer_setup(self):
@@ -391,11 +406,11 @@ class CQLImpl(DDPGBaseImpl):
                 net._peer = px.register_arena(net.arena.grads)
         return px
 
-    def _peer_args(self, px, net):
+    def _peer_args(self, px, net, small=None):
         if px is None:
             return None
         gptrs, fidx, cptr = net._peer
-        return (px, gptrs, fidx, cptr, self.counter_ptr(C_DRAW))
+        return (px, gptrs, fidx, cptr, self.counter_ptr(C_DRAW), small)
 
     def _small_allreduce(self, px, t, channel: int):
         if px is None:

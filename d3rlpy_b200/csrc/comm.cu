@@ -122,6 +122,13 @@ struct PeerPtrs {
   int* flags[kMaxRanks];
   int world, rank;
 };
+// optional short vector (loss partial sums) that rides along with a gradient exchange: rank-local values in,
+// all-rank sums out, through the per-rank exchange block (channel, epoch parity)
+struct SmallVec {
+  float* vec;
+  int n, channel;
+  float* xchg[kMaxRanks];
+};
 
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;
@@ -202,9 +209,15 @@ __device__ __forceinline__ float adam_one2(float p, float g, float& m, float& v,
 
 // all-reduce (over NVLink peer loads) + Adam + Polyak + bf16 shadow refresh in one pass
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 segs, PeerPtrs ps, int flag_index,
-                                                             const int* epoch, unsigned* block_counter) {
+                                                             const int* epoch, unsigned* block_counter, SmallVec sv) {
   const int e = *epoch;
   __shared__ bool last_block;
+  const int sv_off = (sv.channel * 2 + (e & 1)) * 16;
+  if (blockIdx.x == 0 && sv.n > 0) {  // publish my partial sums before announcing that my data is ready
+    if ((int)threadIdx.x < sv.n) sv.xchg[ps.rank][sv_off + threadIdx.x] = sv.vec[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+  }
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       __threadfence_system();
@@ -213,6 +226,11 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + flag_index, e);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && (int)threadIdx.x < sv.n) {
+    float acc = 0.f;
+    for (int r = 0; r < ps.world; ++r) acc += ((const volatile float*)sv.xchg[r])[sv_off + threadIdx.x];
+    sv.vec[threadIdx.x] = acc;
+  }
   __shared__ float sc[2];
   if (threadIdx.x == 0) {  // double pow/sqrt once per block
     const int t = *a.step;
@@ -374,7 +392,8 @@ extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_
                                   void* shadow_params, void* shadow_target, const int64_t* table_host, int n_segments,
                                   int64_t member_size, int64_t shadow_member, const void* const* grads_host,
                                   const void* const* flags_host, int world, int rank, int flag_index,
-                                  const int* epoch, void* block_counter, void* stream) {
+                                  const int* epoch, void* block_counter, float* small_vec, int small_n,
+                                  const void* const* xchg_host, int small_channel, void* stream) {
   D3B_REQUIRE(n >= 0 && n % 4 == 0 && params && exp_avg && exp_avg_sq && step && epoch && block_counter,
               "adam_step_peer: bad arguments");
   if (n == 0) return D3B_OK;
@@ -394,9 +413,18 @@ extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_
       segs.shadow_off[k] = t[3]; segs.ld[k] = (int)t[4];
     }
   }
+  SmallVec sv{};
+  if (small_vec && small_n > 0) {
+    D3B_REQUIRE(small_n <= 16 && small_channel >= 0 && small_channel < 4 && xchg_host, "adam_step_peer: bad small vector");
+    sv.vec = small_vec; sv.n = small_n; sv.channel = small_channel;
+    for (int r = 0; r < world; ++r) {
+      sv.xchg[r] = (float*)xchg_host[r];
+      D3B_REQUIRE(sv.xchg[r], "adam_step_peer: null exchange block");
+    }
+  }
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 4 * d3b::kNumSM) blocks = 4 * d3b::kNumSM;  // every block spins on the flags: all must be resident
   adam_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, segs, ps, flag_index, epoch,
-                                                                           (unsigned*)block_counter);
+                                                                           (unsigned*)block_counter, sv);
   return d3b::check_launch("adam_step_peer");
 }

@@ -373,7 +373,8 @@ class DenseNet:
         if peer is not None:
             import ctypes
 
-            px, gptrs, fidx, cptr, eptr = peer
+            px, gptrs, fidx, cptr, eptr = peer[:5]
+            small = peer[5] if len(peer) > 5 else None   # (tensor, channel): sums riding along with the exchange
             shadow = self.precision == "bf16" and self.fused_ok and self.head_out <= 16
             seg, nseg = None, 0
             if shadow:
@@ -385,7 +386,9 @@ class DenseNet:
                                  _p(self.shadow) if shadow else None,
                                  _p(self.shadow_target) if shadow and sync and self.shadow_target is not None else None,
                                  seg, nseg, a.member_size, self.shadow_member if shadow else 0, gptrs, px.flags_ptrs,
-                                 px.world, px.rank, fidx, eptr, cptr, stream)
+                                 px.world, px.rank, fidx, eptr, cptr, _p(small[0]) if small else None,
+                                 small[0].numel() if small else 0, px.xchg_ptrs if small else None,
+                                 small[1] if small else 0, stream)
             if not shadow:
                 self.refresh_shadow("params", stream)
                 if sync:

@@ -335,7 +335,10 @@ int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, float* 
                        double lr, double beta1, double beta2, double eps, float tau, void* shadow_params,
                        void* shadow_target, const int64_t* table_host, int n_segments, int64_t member_size,
                        int64_t shadow_member, const void* const* grads_host, const void* const* flags_host, int world,
-                       int rank, int flag_index, const int* epoch, void* block_counter, void* stream);
+                       int rank, int flag_index, const int* epoch, void* block_counter, float* small_vec, int small_n,
+                       const void* const* xchg_host, int small_channel, void* stream);
+/* small_vec (<= 16 floats, optional): loss partial sums that ride along with the gradient exchange (in: this
+ * rank's values, out: all-rank sums) through exchange channel small_channel. */
 
 /* ---- plumbing: staged copies, CUDA-graph capture of a whole update ------------------ */
 int d3b_memset_zero(void* ptr, int64_t bytes, void* stream);
