@@ -14,7 +14,7 @@ from d3rlpy_b200._lib import lib  # noqa: E402
 L, dev = lib(), torch.device("cuda:0")
 st = torch.cuda.current_stream().cuda_stream
 a8 = lambda v: (v + 7) // 8 * 8
-for rows, E, in_dim, hidden, n_head, save in [(256, 2, 23, [256, 256, 256], 1, True), (512, 1, 17, [256, 256, 256], 12, True),
+for rows, E, in_dim, hidden, n_head, save in [(256, 2, 23, [256, 256, 256], 1, True), (256, 2, 23, [256, 256, 256], 1, False), (512, 1, 17, [256, 256, 256], 12, True),
                                               (7936, 2, 23, [256, 256, 256], 1, True), (15872, 2, 23, [256, 256, 256], 1, True)]:
     g = torch.Generator().manual_seed(0)
     dims = [in_dim] + hidden

@@ -217,6 +217,9 @@ def test_umma_wgrad_mn_major_operands(R, No, Ki, E, shared_b):
     (129, 3, 256, [240, 48, 80], 5, True, True),        # widths that are not multiples of 64, K_0 = 256
     (127, 2, 7, [16, 256, 16], 32, False, False),       # 32 heads (CUDA-core head, 3-stage ring)
     (513, 1, 65, [192, 192, 192, 192], 2, False, True), # K_0 just above one K block, 4 layers
+    (20000, 1, 40, [240, 48, 80, 16], 1, True, True),   # two tiles per unit (157 tiles > SMs), ragged widths, 4 layers
+    (19300, 2, 33, [64, 128], 0, False, False),         # two tiles per unit, odd tile count, trunk only, per-member input
+    (19000, 1, 23, [256, 256, 256], 1, False, True),    # 149 tiles: last unit of the member has a single tile
 ])
 def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, shared):
     """csrc/mlp_fused.cu vs torch on the same bf16-rounded operands (fp32 accumulate, bf16 activations):
