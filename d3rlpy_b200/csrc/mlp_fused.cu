@@ -162,7 +162,7 @@ __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // barrier slots
-enum { B_WFULL = 0, B_WEMPTY = W_STAGES_MAX, B_XFULL = 2 * W_STAGES_MAX, B_AFREE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
+enum { B_WFULL = 0, B_WEMPTY = W_STAGES_MAX, B_XFULL = 2 * W_STAGES_MAX, B_AFREE, B_STDONE, B_ACCFULL, B_TEMPTY = B_ACCFULL + 2,
        B_ACTREADY = B_TEMPTY + 2, B_COUNT = B_ACTREADY + MAX_KB };
 
 // EW = number of epilogue warps: 16 (four per TMEM lane quarter, one 16-column chunk of every K block each) hides the
@@ -173,7 +173,7 @@ __device__ __forceinline__ void epi_sync_n() {
 }
 
 template <int NH, int EW>
-__global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
+__global__ void __launch_bounds__(EW * 32 + 96, 1) mlp_forward_kernel(const __grid_constant__ Maps maps, FwdParams p) {
   constexpr int EPI = EW * 32;          // epilogue threads
   constexpr int NSUB = EW / 4;          // column sub-ranges per K block
   constexpr int SUBW = BK / NSUB;       // columns of a K block owned by one sub-range
@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
   const int units = p.tiles * p.members;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, 1);
+    // TEMPTY / ACTREADY: one arrival per epilogue warp (no block-wide barrier in the layer loop)
+    for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, (i >= B_TEMPTY && i < B_ACTREADY + MAX_KB) ? EW : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -239,8 +240,9 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
     // ================= MMA issuer
     if (lane == 0) {
       uint32_t g = 0, wi = 0, it = 0;
-      uint32_t act_cnt[MAX_KB] = {0, 0, 0, 0};
+      uint32_t act_par = 0;  // phase parity bit per K-block barrier
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+        const int m0 = (u % p.tiles) * BM;
         for (int l = 0; l < L; ++l, ++g) {
           const uint32_t buf = g & 1;
           mbar_wait(bars + B_TEMPTY + buf, ((g >> 1) & 1) ^ 1);
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
           for (int kb = 0; kb < nkb; ++kb, ++wi) {
             const uint32_t s = wi % W_STAGES, ph = (wi / W_STAGES) & 1;
             if (l > 0) {  // K block kb of the previous layer's output has been written by the epilogue warps
-              mbar_wait(bars + B_ACTREADY + kb, act_cnt[kb] & 1);
-              ++act_cnt[kb];
+              mbar_wait(bars + B_ACTREADY + kb, (act_par >> kb) & 1);
+              act_par ^= 1u << kb;
             }
             mbar_wait(bars + B_WFULL + s, ph);
             if (dbg && g == 1 && kb < 4) dbg[9 + kb] = clock64();     // weight K block kb of layer 1 landed
@@ -272,6 +274,37 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
           }
           mma_commit(bars + B_ACCFULL + buf);
           if (dbg && g == 1) dbg[13] = clock64();                     // all MMAs of layer 1 issued
+          if (l == L - 1 && ((p.save_mask >> l) & 1) && m0 < p.save_rows) {
+            // the stored last layer completes one phase of the K-block barriers that only the store thread waits for
+            const int nkb_out = (p.N[l] + BK - 1) / BK;
+            for (int kb = 0; kb < nkb_out; ++kb) act_par ^= 1u << kb;
+          }
+        }
+      }
+    }
+  } else if (warp == EW + 2) {
+    // ================= activation stores: K blocks of H_l -> global memory as soon as they are complete in shared memory
+    if (lane == 0) {
+      uint32_t act_par = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        const int e = u / p.tiles, m0 = (u % p.tiles) * BM;
+        for (int l = 0; l < L; ++l) {
+          const bool last = (l == L - 1);
+          const int nkb_out = (p.N[l] + BK - 1) / BK;
+          const bool store = ((p.save_mask >> l) & 1) && m0 < p.save_rows;
+          if (!store) {
+            if (!last)  // still produced as the next layer's operand: one barrier phase per block
+              for (int kb = 0; kb < nkb_out; ++kb) act_par ^= 1u << kb;
+            continue;
+          }
+          for (int kb = 0; kb < nkb_out; ++kb) {
+            mbar_wait(bars + B_ACTREADY + kb, (act_par >> kb) & 1);
+            act_par ^= 1u << kb;
+            tma_store_3d(&maps.h[l], smA + kb * A_KB_BYTES, kb * BK, m0, e);
+            tma_store_commit();
+          }
+          tma_store_wait_read();  // the bulk stores have read the operand buffer: it may be overwritten / reloaded
+          mbar_arrive(bars + (last ? B_AFREE : B_STDONE));
         }
       }
     }
@@ -280,7 +313,7 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
     const int t = threadIdx.x;
     const int q = warp & 3, sub = warp >> 2;
     const int row = q * 32 + lane;
-    uint32_t g = 0;
+    uint32_t g = 0, sd = 0;  // sd: completed STDONE phases this thread has consumed
     int cur_member = -1;
     bool stores_pending = false;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
@@ -314,9 +347,9 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
         if (dbg && t == 0 && g < 6) dbg[2 + 2 * g] = clock64();      // accumulator of layer g ready
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (last && !store && t == 0) mbar_arrive(bars + B_AFREE);  // operand buffer no longer needed by this unit
-        if (writeA && stores_pending) {
-          if (t == 0) tma_store_wait_read();  // the previous layer's TMA stores finished reading the buffer
-          epi_sync_n<EW>();
+        if (stores_pending) {  // the previous layer's TMA stores have finished reading the operand buffer
+          mbar_wait(bars + B_STDONE, sd & 1);
+          ++sd;
           stores_pending = false;
         }
         const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
@@ -382,33 +415,25 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
             }
           }
           if (writeA) {
-            // block kb of H_l is complete in shared memory: hand it to the MMA issuer / the TMA store engine
+            // this warp's piece of block kb is in shared memory: hand it to the MMA issuer / the store thread
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            epi_sync_n<EW>();
-            if (t == 0) {
-              if (!last) mbar_arrive(bars + B_ACTREADY + kb);
-              if (store) {
-                tma_store_3d(&maps.h[l], smA + kb * A_KB_BYTES, cb, m0, e);
-                tma_store_commit();
-              }
-            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + B_ACTREADY + kb);
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (NH > 0 && last && p.n_head > 0 && sub > 0) {
-#pragma unroll
-          for (int j = 0; j < NH; ++j) head_part[((sub - 1) * BM + row) * NH + j] = acc[j];
-        }
-        epi_sync_n<EW>();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B_TEMPTY + buf);  // this warp has drained its part of the accumulator buffer
         if (dbg && t == 0 && g < 6) dbg[3 + 2 * g] = clock64();      // epilogue of layer g done
-        if (t == 0) {
-          mbar_arrive(bars + B_TEMPTY + buf);  // every thread has drained this accumulator buffer
-          if (last && store) {
-            tma_store_wait_read();
-            mbar_arrive(bars + B_AFREE);
-          }
-        }
         stores_pending = store && !last;
+        const bool head_here = NH > 0 && last && p.n_head > 0;
+        if (head_here) {
+          if (sub > 0) {
+#pragma unroll
+            for (int j = 0; j < NH; ++j) head_part[((sub - 1) * BM + row) * NH + j] = acc[j];
+          }
+          epi_sync_n<EW>();
+        }
         if (NH > 0 && last && p.n_head > 0 && sub == 0 && m0 + row < p.rows) {
           const float* hb = p.head_b + (long long)e * p.head_stride;
           float* o = p.head_out + ((long long)e * p.rows + m0 + row) * p.n_head;
@@ -423,9 +448,8 @@ __global__ void __launch_bounds__(EW * 32 + 64, 1) mlp_forward_kernel(const __gr
           }
         }
       }
-      if (L == 1) epi_sync_n<EW>();  // head_part is rewritten by the very next layer
+      if (NH > 0 && p.n_head > 0) epi_sync_n<EW>();  // head_part is rewritten by the next unit's last layer
     }
-    if (t == 0) tma_store_wait_read();  // shared memory may be released once the bulk stores have read it
     if (dbg && t == 0) dbg[14] = clock64();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -852,7 +876,7 @@ int launch_fwd(const Maps& maps, const FwdParams& p, int grid, cudaStream_t st) 
                                   (int)fwd_smem<NH>()));
     attr_set = true;
   }
-  launch_pdl(mlp_forward_kernel<NH, fwd_epi_warps<NH>()>, dim3(grid), dim3(fwd_epi_warps<NH>() * 32 + 64), fwd_smem<NH>(), st,
+  launch_pdl(mlp_forward_kernel<NH, fwd_epi_warps<NH>()>, dim3(grid), dim3(fwd_epi_warps<NH>() * 32 + 96), fwd_smem<NH>(), st,
              maps, p);
   return check_launch("mlp_forward_bf16");
 }
