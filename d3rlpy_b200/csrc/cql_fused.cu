@@ -230,35 +230,57 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
     const float rand_lp = (float)p.A * -0.69314718055994529f;
     const long long BN = (long long)B * N;
     // value index v in [0, 3N): group = v / N (pi(s_t), pi(s_tp1), random), sample k = v % N
-    float mx = -INFINITY;
-    for (int v = lane; v < 3 * N; v += 32) {
-      int grp = v / N, k = v - grp * N;
-      float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
-      float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
-                           : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
-      mx = fmaxf(mx, q - off);
-    }
-    mx = warp_max(mx);
-    float s = N > 0 ? 0.f : 1.f;
-    for (int v = lane; v < 3 * N; v += 32) {
-      int grp = v / N, k = v - grp * N;
-      float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
-      float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
-                           : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
-      s += expf(q - off - mx);
-    }
-    s = warp_sum(s);
-    if (dqe) {
-      const float inv_s = c / s;
-      for (int v = lane; v < 3 * N; v += 32) {
+    float mx = -INFINITY, s;
+    if (3 * N <= 32) {
+      // one value per lane: a single round of loads feeds the max, the sum and the gradient (default N = 10)
+      const int v = lane;
+      float x = -INFINITY;
+      long long idx = 0;
+      if (v < 3 * N) {
         int grp = v / N, k = v - grp * N;
-        long long idx = B + grp * BN + (long long)b * N + k;
+        idx = B + grp * BN + (long long)b * N + k;
         float q = __ldg(qe + idx);
         float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
                              : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
-        dqe[idx] = expf(q - off - mx) * inv_s;
+        x = q - off;
       }
-      if (lane == 0) dqe[b] = g - c;
+      mx = warp_max(x);
+      const float ex = v < 3 * N ? expf(x - mx) : 0.f;
+      s = N > 0 ? warp_sum(ex) : 1.f;
+      if (dqe) {
+        if (v < 3 * N) dqe[idx] = ex * (c / s);
+        if (lane == 0) dqe[b] = g - c;
+      }
+    } else {
+      for (int v = lane; v < 3 * N; v += 32) {
+        int grp = v / N, k = v - grp * N;
+        float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
+        float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                             : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+        mx = fmaxf(mx, q - off);
+      }
+      mx = warp_max(mx);
+      s = 0.f;
+      for (int v = lane; v < 3 * N; v += 32) {
+        int grp = v / N, k = v - grp * N;
+        float q = __ldg(qe + B + grp * BN + (long long)b * N + k);
+        float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                             : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+        s += expf(q - off - mx);
+      }
+      s = warp_sum(s);
+      if (dqe) {
+        const float inv_s = c / s;
+        for (int v = lane; v < 3 * N; v += 32) {
+          int grp = v / N, k = v - grp * N;
+          long long idx = B + grp * BN + (long long)b * N + k;
+          float q = __ldg(qe + idx);
+          float off = grp == 0 ? __ldg(p.logp_t + (long long)b * N + k)
+                               : (grp == 1 ? __ldg(p.logp_tp1 + (long long)b * N + k) : rand_lp);
+          dqe[idx] = expf(q - off - mx) * inv_s;
+        }
+        if (lane == 0) dqe[b] = g - c;
+      }
     }
     if (lane == 0) {
       lse_v = N > 0 ? mx + logf(s) : 0.f;
@@ -267,14 +289,21 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
       td = 0.f;
     }
   }
-  td = block_sum(td);
-  if (threadIdx.x == 0 && td_enabled) atomicAdd(p.sums + 0, td);
-  lse_v = block_sum(lse_v);
-  if (threadIdx.x == 0) atomicAdd(p.sums + 1, lse_v);
-  data_v = block_sum(data_v);
+  // the three partial sums of the block in one barrier round (lane 0 of each warp holds its row's values)
+  __shared__ float red3[3][8];
+  if (lane == 0) {
+    const int w = threadIdx.x >> 5;
+    red3[0][w] = td; red3[1][w] = lse_v; red3[2][w] = data_v;
+  }
+  __syncthreads();
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
-    atomicAdd(p.sums + 2, data_v);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a0 += red3[0][w]; a1 += red3[1][w]; a2 += red3[2][w]; }
+    if (td_enabled) atomicAdd(p.sums + 0, a0);
+    atomicAdd(p.sums + 1, a1);
+    atomicAdd(p.sums + 2, a2);
     __threadfence();
     unsigned prev = atomicAdd(p.done, 1u);
     is_last = (prev == gridDim.x - 1);
