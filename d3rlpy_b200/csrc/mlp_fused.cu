@@ -728,9 +728,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_backward_kernel(const __grid_
         const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
         const bool mma_follows = (l > 0) || has_dx;
         const int nkb_out = (N + BK - 1) / BK;
+        bool wide_top = false;
+        if constexpr (NH > 2) {
+          // Wide head (policy mu|logstd, VAE heads): dZ_top[r][c] = sum_j d_head[r][j] W_head[j][c] with thread = row is
+          // bound by the broadcast reads of the 4*NH weights per 16 columns; with thread = 4 columns x 32 rows the NH x 4
+          // weights stay in registers and each row costs NH/4 broadcast reads of d_head instead (FMA-bound).
+          if (top) {
+            wide_top = true;
+            const int c4 = (t & 63) * 4, r0 = (t >> 6) * 32;
+            if (c4 < N) {
+              float w[NH][4];
+#pragma unroll
+              for (int j = 0; j < NH; ++j) {
+                const float4 wv = *reinterpret_cast<const float4*>(head_w_s + j * MAXW + c4);
+                w[j][0] = wv.x; w[j][1] = wv.y; w[j][2] = wv.z; w[j][3] = wv.w;
+              }
+              const int coff = (c4 >> 6) * A_KB_BYTES + (c4 & 7) * 2, chunk = (c4 & 63) >> 3;
+#pragma unroll 2
+              for (int r = r0; r < r0 + 32; ++r) {
+                float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                const float4* d4 = reinterpret_cast<const float4*>(dhead_s + r * NH);  // NH % 4 == 0 here, 16-B aligned
+#pragma unroll
+                for (int j4 = 0; j4 < NH / 4; ++j4) {
+                  const float4 dv = d4[j4];
+                  const float dj[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj) {
+                    const int j = 4 * j4 + jj;
+                    f0 = fmaf(dj[jj], w[j][0], f0); f1 = fmaf(dj[jj], w[j][1], f1);
+                    f2 = fmaf(dj[jj], w[j][2], f2); f3 = fmaf(dj[jj], w[j][3], f3);
+                  }
+                }
+                const int off = coff + r * 128 + ((chunk ^ (r & 7)) << 4);
+                const uint2 mv = *reinterpret_cast<const uint2*>(smM + off);
+                const float a0 = bf16_lo(mv.x) > 0.f ? f0 : 0.f, a1 = bf16_hi(mv.x) > 0.f ? f1 : 0.f;
+                const float a2 = bf16_lo(mv.y) > 0.f ? f2 : 0.f, a3 = bf16_hi(mv.y) > 0.f ? f3 : 0.f;
+                *reinterpret_cast<uint2*>(smA + off) = make_uint2(pack_bf16(a0, a1), pack_bf16(a2, a3));
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            epi_sync();
+            if (t == 0) {
+              for (int kb = 0; kb < nkb_out; ++kb) {
+                if (mma_follows) mbar_arrive(bars + C_ACTREADY + kb);
+                if (p.weight_grads && !((p.dz_blocked >> l) & 1)) {
+                  tma_store_4d(&maps.dz[l], smA + kb * A_KB_BYTES, kb * BK, m0, 0, e);
+                  tma_store_commit();
+                }
+              }
+            }
+          }
+        }
         // dZ_l is produced K block by K block (all 8 warps on one 64-column block at a time) so that the next
         // step's MMAs and the block's TMA store start while the remaining blocks are still being masked
-        for (int kb = 0; kb < nkb_out; ++kb) {
+        for (int kb = 0; kb < (wide_top ? 0 : nkb_out); ++kb) {
           const int cb = kb * BK;
           const int rem = (N - cb) < BK ? (N - cb) : BK;
           const int h0 = rem < 32 ? rem : 32;
