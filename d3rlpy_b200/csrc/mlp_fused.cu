@@ -1110,6 +1110,7 @@ extern "C" int d3b_mlp_forward_bf16(const void* x, int64_t ldx, int64_t stride_x
   if (n_head == 0) return launch_fwd<0>(maps, p, grid, st);
   if (n_head == 1) return launch_fwd<1>(maps, p, grid, st);
   if (n_head <= 8) return launch_fwd<8>(maps, p, grid, st);
+  if (n_head <= 12) return launch_fwd<12>(maps, p, grid, st);
   if (n_head <= 16) return launch_fwd<16>(maps, p, grid, st);
   return launch_fwd<32>(maps, p, grid, st);
 }
@@ -1201,5 +1202,6 @@ extern "C" int d3b_mlp_backward_bf16(int rows, int members, int n_layers, const 
   cudaStream_t st = (cudaStream_t)stream;
   if (n_head == 1) return launch_bwd<1>(maps, p, grid, st);
   if (n_head <= 8) return launch_bwd<8>(maps, p, grid, st);
+  if (n_head <= 12) return launch_bwd<12>(maps, p, grid, st);  // 2 x 6 actions: the default policy head
   return launch_bwd<16>(maps, p, grid, st);
 }
