@@ -82,10 +82,11 @@ def make_dataset(w, steps_total=1_000_000, seed=0):
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons during the timed region (NVML)."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.005):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self._stop_evt = index, period, [], set(), threading.Event()
         self.max_mhz = None
+        self.ready = threading.Event()  # NVML initialised: the timed region (tens of ms) starts only after this
 
     def run(self):
         try:
@@ -98,6 +99,7 @@ class ClockSampler(threading.Thread):
                      nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
                      nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            self.ready.set()
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -107,6 +109,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(self.period)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def stop(self):
         self._stop_evt.set()
@@ -301,6 +304,7 @@ def run_ours(args, w):
     # ---- device-resident timing: CUDA events per step on the launching stream, L2 flushed in between
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(5.0)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     n0 = L.launch_count()
     with torch.cuda.stream(impl._stream_obj):

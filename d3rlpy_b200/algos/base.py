@@ -42,6 +42,73 @@ class VectorEncoderFactory:
         self.hidden_units = list(hidden_units) if hidden_units is not None else [256, 256]
 
 
+_ADAM_DEFAULTS = {"optim_cls": "Adam", "betas": [0.9, 0.999], "eps": 1e-08, "weight_decay": 0, "amsgrad": False}
+
+
+def _encoder_to_json(factory) -> Dict[str, Any]:
+    """EncoderFactory -> {"type", "params"} as `_serialize_params` writes it (d3rlpy/base.py:78-98 with
+    models/encoders.py get_type/get_params)."""
+    if factory is None or factory == "default":
+        return {"type": "default", "params": {"activation": "relu", "use_batch_norm": False, "dropout_rate": None}}
+    if hasattr(factory, "filters"):
+        return {"type": "pixel", "params": {"filters": [list(f) for f in factory.filters],
+                                            "feature_size": factory.feature_size, "activation": "relu",
+                                            "use_batch_norm": False, "dropout_rate": None}}
+    hidden = list(factory) if isinstance(factory, (list, tuple)) else _hidden_units(factory, [256, 256])
+    return {"type": "vector", "params": {"hidden_units": hidden, "activation": "relu", "use_batch_norm": False,
+                                         "dropout_rate": None, "use_dense": False}}
+
+
+def _encoder_from_json(doc):
+    if not isinstance(doc, dict):
+        return doc
+    kind, params = doc["type"], dict(doc.get("params", {}))
+    if params.get("activation", "relu") != "relu" or params.get("use_batch_norm") or params.get("dropout_rate") or \
+            params.get("use_dense"):
+        raise ValueError(f"encoder configuration outside the accelerated path: {doc}")
+    if kind == "default":
+        return "default"
+    if kind == "vector":
+        return VectorEncoderFactory(hidden_units=params.get("hidden_units"))
+    if kind == "pixel":
+        from .dqn import PixelEncoderFactory
+
+        return PixelEncoderFactory(filters=[tuple(f) for f in params["filters"]] if params.get("filters") else None,
+                                   feature_size=params.get("feature_size", 512))
+    raise ValueError(f"unsupported encoder type {kind!r}")
+
+
+def _scaler_to_json(scaler):
+    if scaler is None:
+        return None
+    if isinstance(scaler, str):  # create_scaler(name) with default arguments (preprocessing/scalers.py:369-383)
+        if scaler == "pixel":
+            return {"type": "pixel", "params": {}}
+        if scaler == "standard":
+            return {"type": "standard", "params": {"mean": None, "std": None, "eps": 1e-3}}
+        raise ValueError(f"unsupported scaler {scaler!r}")
+    kind = getattr(scaler, "TYPE", None)
+    if kind == "pixel":
+        return {"type": "pixel", "params": {}}
+    if kind == "standard":  # StandardScaler.get_params (preprocessing/scalers.py:356-366)
+        mean = None if scaler._mean is None else np.asarray(scaler._mean).tolist()
+        std = None if scaler._std is None else np.asarray(scaler._std).tolist()
+        return {"type": "standard", "params": {"mean": mean, "std": std, "eps": scaler._eps}}
+    raise ValueError(f"unsupported scaler {scaler!r}")
+
+
+def _scaler_from_json(doc):
+    if doc is None or not isinstance(doc, dict):
+        return doc
+    from ..preprocessing import PixelScaler, StandardScaler
+
+    if doc["type"] == "pixel":
+        return PixelScaler()
+    if doc["type"] == "standard":
+        return StandardScaler(**doc.get("params", {}))
+    raise ValueError(f"scaler {doc['type']!r} is not on the accelerated path")
+
+
 class AlgoBase:
     _impl = None
 
@@ -109,6 +176,95 @@ class AlgoBase:
 
     def _update(self, batch) -> Dict[str, float]:
         raise NotImplementedError
+
+    # ------------------------------------------------------------------ params.json (base.py:188-232, 823-850)
+    def get_params(self, deep: bool = True) -> Dict[str, Any]:
+        """Constructor arguments by name (LearnableBase.get_params, base.py:266-319): every `_x` attribute that is a
+        hyper-parameter, the factories as objects."""
+        skip = {"_impl", "_grad_step", "_kwargs", "_factories", "_use_gpu"}
+        out: Dict[str, Any] = {}
+        for key, value in vars(self).items():
+            if key in skip or not key.startswith("_") or key.endswith("_hidden"):
+                continue
+            out[key[1:]] = value
+        out.update(getattr(self, "_factories", {}))
+        out.update(self._kwargs)
+        out["use_gpu"] = self._use_gpu
+        return out
+
+    def _params_document(self) -> Dict[str, Any]:
+        """The document `save_params` writes: reference keys and value encodings (`_serialize_params`), plus this
+        package's own constructor keys (`seed`, `precision`), which the reference's `from_json` passes through
+        `**kwargs` untouched."""
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        doc: Dict[str, Any] = {"generated_maxlen": 100000, "real_ratio": 1.0, "q_func_factory":
+                               {"type": "mean", "params": {"share_encoder": False}}}
+        for key, value in self.get_params().items():
+            if key.endswith("encoder_factory"):
+                doc[key] = _encoder_to_json(value)
+            elif key in ("scaler", "action_scaler", "reward_scaler"):
+                doc[key] = _scaler_to_json(value)
+            elif key == "use_gpu":
+                doc[key] = None if value is None or value is False else (0 if value is True else int(value))
+            else:
+                doc[key] = value
+            if key.endswith("learning_rate"):
+                doc[key[:-len("learning_rate")] + "optim_factory"] = dict(_ADAM_DEFAULTS)
+        doc = dict(sorted(doc.items()))
+        doc["algorithm"] = type(self).__name__
+        doc["observation_shape"] = list(self._impl.observation_shape)
+        doc["action_size"] = self._impl.action_size
+        return doc
+
+    def save_params(self, logger_or_path) -> None:
+        """LearnableBase.save_params (base.py:823-850): hands the document to `logger.add_params`, or writes it to the
+        given path as `params.json`."""
+        doc = self._params_document()
+        if hasattr(logger_or_path, "add_params"):
+            logger_or_path.add_params(doc)
+            return
+        import json
+
+        with open(logger_or_path, "w") as f:
+            json.dump(doc, f, indent=2)
+
+    @classmethod
+    def from_json(cls, fname: str, use_gpu=0, **overrides: Any):
+        """LearnableBase.from_json (base.py:188-232): rebuilds the algorithm from a `params.json` written by this
+        package or by the reference, then `create_impl`.  Configurations outside the accelerated path raise."""
+        import json
+
+        with open(fname, "r") as f:
+            params = json.load(f)
+        observation_shape = tuple(params.pop("observation_shape"))
+        action_size = params.pop("action_size")
+        name = params.pop("algorithm", cls.__name__)
+        if name != cls.__name__:
+            raise ValueError(f"{fname} was written by {name}, not {cls.__name__}")
+        for key in ("generated_maxlen", "real_ratio"):
+            params.pop(key, None)
+        for key in list(params):
+            value = params[key]
+            if key.endswith("encoder_factory"):
+                params[key] = _encoder_from_json(value)
+            elif key.endswith("optim_factory"):
+                if value is not None and any(value.get(k, v) != v and list(value.get(k, v)) != v
+                                             for k, v in _ADAM_DEFAULTS.items() if not isinstance(v, list)) or \
+                        (value is not None and list(value.get("betas", [0.9, 0.999])) != [0.9, 0.999]):
+                    raise ValueError(f"{key}: only Adam defaults are on the accelerated path, got {value}")
+                params[key] = None
+            elif key == "q_func_factory":
+                kind = value["type"] if isinstance(value, dict) else value
+                if kind != "mean":
+                    raise ValueError("only the mean Q function is on the accelerated path")
+                params[key] = "mean"
+            elif key == "scaler":
+                params[key] = _scaler_from_json(value)
+        params["use_gpu"] = use_gpu
+        params.update(overrides)
+        algo = cls(**params)
+        algo.create_impl(observation_shape, action_size)
+        return algo
 
     # ------------------------------------------------------------------ evaluation (algos/base.py:predict/predict_value)
     def predict(self, x):

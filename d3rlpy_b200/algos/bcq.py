@@ -33,6 +33,8 @@ class BCQ(AlgoBase):
         self._lam, self._n_action_samples, self._action_flexibility = lam, n_action_samples, action_flexibility
         self._rl_start_step, self._beta = rl_start_step, beta
         self._impl, self._seed = impl, seed
+        self._factories = {"actor_encoder_factory": actor_encoder_factory, "critic_encoder_factory": critic_encoder_factory,
+                           "imitator_encoder_factory": imitator_encoder_factory}
 
     def _create_impl(self, observation_shape, action_size) -> None:
         self._impl = BCQImpl(

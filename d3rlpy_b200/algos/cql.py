@@ -32,6 +32,7 @@ class CQL(AlgoBase):
         self._alpha_threshold, self._conservative_weight = alpha_threshold, conservative_weight
         self._n_action_samples, self._soft_q_backup = n_action_samples, soft_q_backup
         self._impl, self._seed = impl, seed
+        self._factories = {"actor_encoder_factory": actor_encoder_factory, "critic_encoder_factory": critic_encoder_factory}
 
     def _create_impl(self, observation_shape, action_size) -> None:
         self._impl = CQLImpl(

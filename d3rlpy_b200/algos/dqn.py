@@ -37,6 +37,7 @@ class DQN(AlgoBase):
         self._target_update_interval = target_update_interval
         self._encoder_factory = encoder_factory
         self._impl, self._seed = impl, seed
+        self._factories = {"encoder_factory": encoder_factory}
 
     def _impl_kwargs(self) -> Dict[str, Any]:
         return {}

@@ -31,6 +31,7 @@ class TD3PlusBC(AlgoBase):
         self._target_smoothing_sigma, self._target_smoothing_clip = target_smoothing_sigma, target_smoothing_clip
         self._alpha, self._update_actor_interval = alpha, update_actor_interval
         self._impl, self._seed = impl, seed
+        self._factories = {"actor_encoder_factory": actor_encoder_factory, "critic_encoder_factory": critic_encoder_factory}
 
     def _create_impl(self, observation_shape, action_size) -> None:
         self._impl = TD3PlusBCImpl(

@@ -557,3 +557,34 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     assert m1.keys() == m2.keys()
     for k in m1:
         assert float(m1[k]) == float(m2[k]), (k, float(m1[k]), float(m2[k]))
+
+
+@pytest.mark.gpu
+def test_from_json_rebuilds_algorithm_from_reference_and_own_params(tmp_path):
+    """`from_json` (d3rlpy/base.py:188-232) on a params.json written by the unmodified reference (golden fixture) and on
+    one written by `save_params`: same hyper-parameters, impl created with the recorded shapes, and together with
+    `load_model` the rebuilt algorithm predicts exactly like the original."""
+    import json
+    import os
+
+    from d3rlpy_b200.algos import CQL, DiscreteCQL
+
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "params_json.json")))
+    f = tmp_path / "ref_params.json"
+    f.write_text(json.dumps(ref["cql"]))
+    algo = CQL.from_json(str(f), use_gpu=0)
+    assert algo.impl is not None and algo.impl.observation_shape == (6,) and algo.impl.action_size == 3
+    assert algo._n_action_samples == 4 and algo._actor_hidden == [32, 32] and algo._critic_hidden == [32, 32]
+    with pytest.raises(ValueError):
+        DiscreteCQL.from_json(str(f))  # written by another algorithm
+
+    rs = np.random.RandomState(0)
+    obs = rs.randn(16, 6).astype(np.float32)
+    algo.update(_ns(_synthetic_batch(rs, 32, 6, 3)))
+    mine, model = tmp_path / "params.json", tmp_path / "model.pt"
+    algo.save_params(str(mine))
+    algo.impl.save_model(str(model))
+    again = CQL.from_json(str(mine), use_gpu=0)
+    again.impl.load_model(str(model))
+    np.testing.assert_array_equal(algo.predict(obs), again.predict(obs))
+    assert json.load(open(mine))["algorithm"] == "CQL"
