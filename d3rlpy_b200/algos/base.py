@@ -109,6 +109,21 @@ def _scaler_from_json(doc):
     raise ValueError(f"scaler {doc['type']!r} is not on the accelerated path")
 
 
+def random_iterator_indices(rng, n_transitions: int, n_steps: int, batch_size: int) -> np.ndarray:
+    """Index stream of RandomIterator for one epoch: one vectorised draw == n_steps*batch_size sequential
+    `np.random.randint(n)` calls (the legacy RandomState consumes its stream element by element)."""
+    return rng.randint(n_transitions, size=(n_steps, batch_size)).astype(np.int64)
+
+
+def round_iterator_indices(rng, n_transitions: int, batch_size: int, shuffle: bool = True) -> np.ndarray:
+    """Index stream of RoundIterator for one epoch (iterators/round_iterator.py:39-55)."""
+    perm = np.arange(n_transitions)
+    if shuffle:
+        rng.shuffle(perm)
+    n_batches = n_transitions // batch_size
+    return perm[:n_batches * batch_size].reshape(n_batches, batch_size).astype(np.int64)
+
+
 class AlgoBase:
     _impl = None
 
@@ -280,40 +295,47 @@ class AlgoBase:
         return self._impl.sample_action(x)
 
     # ------------------------------------------------------------------ fit over an HBM-resident replay
-    def fit(self, dataset, n_steps: int, n_steps_per_epoch: int = 10000, shuffle: bool = True,
-            seed: Optional[int] = None, verbose: bool = False) -> List[Dict[str, float]]:
-        """Minimal `fit()` (base.py:349-687 without logger/scorers): RandomIterator index stream
-        (np.random.randint per sample, iterators/random_iterator.py:38-41) -> device gather -> update."""
-        from ..dataset import TransitionMiniBatch
-
+    def fit(self, dataset, n_epochs: Optional[int] = None, n_steps: Optional[int] = None,
+            n_steps_per_epoch: int = 10000, shuffle: bool = True, seed: Optional[int] = None,
+            verbose: bool = False) -> List[Dict[str, float]]:
+        """Minimal `fit()` (base.py:349-687 without logger/scorers).  `n_steps` selects the RandomIterator index stream
+        (one `np.random.randint` per sample, iterators/random_iterator.py:38-41), `n_epochs` the RoundIterator one
+        (per epoch a `np.random.shuffle`d permutation cut into len//batch_size consecutive batches, the remainder
+        dropped, iterators/round_iterator.py:39-55) -> device gather -> update.  Returns the per-epoch metric means."""
+        if (n_epochs is None) == (n_steps is None):
+            raise ValueError("Either of n_epochs or n_steps must be given.")  # base.py:548-549
         if self._scaler is not None and hasattr(self._scaler, "fit_dataset"):
             self._scaler.fit_dataset(dataset)
         self.build_with_dataset(dataset)
         replay = dataset.device_replay(self._impl._device)
         rng = np.random if seed is None else np.random.RandomState(seed)
         history: List[Dict[str, float]] = []
-        impl, B = self._impl, self._batch_size
-        fast = (not replay.is_image) and (not replay.discrete) and self._n_frames == 1
-        done = 0
-        while done < n_steps:
-            chunk = min(n_steps_per_epoch - done % n_steps_per_epoch, n_steps - done)
-            # one vectorised draw == chunk*B sequential `np.random.randint(n)` calls of RandomIterator
-            # (iterators/random_iterator.py:38-41): the legacy RandomState consumes its stream element by element
-            idx = rng.randint(len(replay), size=(chunk, B)).astype(np.int64)
-            if fast:
-                acc = self._fit_chunk_device(replay, idx)
-            else:
-                acc: Dict[str, List[float]] = {}
-                for i in range(chunk):
-                    batch = TransitionMiniBatch.from_indices(replay, idx[i], n_frames=self._n_frames,
-                                                             n_steps=self._n_steps, gamma=self._gamma,
-                                                             scaler=self._scaler, out=impl.device_batch(B))
-                    for k, v in self.update(batch).items():
-                        acc.setdefault(k, []).append(float(v))
-            done += chunk
-            if done % n_steps_per_epoch == 0 or done == n_steps:
-                history.append({k: float(np.mean(v)) for k, v in acc.items()})
+        B = self._batch_size
+        if n_steps is not None:
+            assert n_steps >= n_steps_per_epoch  # base.py:523
+            for _ in range(n_steps // n_steps_per_epoch):
+                history.append(self._fit_epoch(replay, random_iterator_indices(rng, len(replay), n_steps_per_epoch, B)))
+        else:
+            for _ in range(n_epochs):
+                history.append(self._fit_epoch(replay, round_iterator_indices(rng, len(replay), B, shuffle)))
         return history
+
+    def _fit_epoch(self, replay, idx: np.ndarray) -> Dict[str, float]:
+        """One epoch over the index matrix [steps, batch_size]; the epoch's metric means (base.py:660-676)."""
+        from ..dataset import TransitionMiniBatch
+
+        impl, B = self._impl, self._batch_size
+        if (not replay.is_image) and (not replay.discrete) and self._n_frames == 1:
+            acc = self._fit_chunk_device(replay, idx)
+        else:
+            acc: Dict[str, List[float]] = {}
+            for i in range(idx.shape[0]):
+                batch = TransitionMiniBatch.from_indices(replay, idx[i], n_frames=self._n_frames,
+                                                         n_steps=self._n_steps, gamma=self._gamma,
+                                                         scaler=self._scaler, out=impl.device_batch(B))
+                for k, v in self.update(batch).items():
+                    acc.setdefault(k, []).append(float(v))
+        return {k: float(np.mean(v)) for k, v in acc.items()}
 
     def _fit_chunk_device(self, replay, idx: np.ndarray) -> Dict[str, List[float]]:
         """Vector observations: the chunk's indices are uploaded once; every step is one gather launch + one graph

@@ -274,10 +274,10 @@ class CQLImpl(DDPGBaseImpl):
         px = getattr(self, "_px", None) if dp else None
         if px is not None:
             # peers have finished reading last update's gradients -> zero them for this update's RED accumulation
-            for net in (self._q_func, self._policy):
-                _, fidx, _ = net._peer
-                L.peer_wait_zero(px.flags_ptrs, px.world, px.rank, fidx + 1, self.counter_ptr(C_DRAW),
-                                 net.arena.grads.data_ptr(), net.arena.size, st)
+            (_, fq, _), (_, fp, _) = self._q_func._peer, self._policy._peer
+            L.peer_wait_zero(px.flags_ptrs, px.world, px.rank, fq + 1, self.counter_ptr(C_DRAW),
+                             self._q_func.arena.grads.data_ptr(), self._q_func.arena.size, fp + 1,
+                             self._policy.arena.grads.data_ptr(), self._policy.arena.size, st)
         self.fill_noise(B)
         acts_p, head = self._p_policy(db)
         nv = lambda name: self.noise_view(name, B).data_ptr()
@@ -337,13 +337,22 @@ class CQLImpl(DDPGBaseImpl):
             L.critic_loss(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma, lp[2].data_ptr(),
                           lp[3].data_ptr(), N, A, la.ptr("p"), self._conservative_weight, None, 0,
                           self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, st)
-            self._small_allreduce(px, self._slots[32 + S_ALPHA:32 + S_ALPHA + (4 if temp_merged else 3)], 1)
-            if temp_merged:
-                temp_adam()
-            L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
-                           self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
-            L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
-                          self._alpha_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_ALPHA), st)
+            if px is not None:
+                # exchange + temperature step + alpha step in one launch
+                L.dp_scalar_steps(self.sums_ptr(S_ALPHA), px.xchg_ptrs, px.flags_ptrs, px.world, px.rank, 1,
+                                  self.counter_ptr(C_DRAW), lt.buf.data_ptr() if temp_merged else None,
+                                  self.counter_ptr(C_TEMP), self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS),
+                                  self.metric_ptr(M_TEMP), la.buf.data_ptr(), self.counter_ptr(C_ALPHA),
+                                  self._alpha_learning_rate, inv_b / E, self._conservative_weight,
+                                  self._alpha_threshold, self.metric_ptr(M_ALPHA_LOSS), self.metric_ptr(M_ALPHA), st)
+            else:
+                self._small_allreduce(px, self._slots[32 + S_ALPHA:32 + S_ALPHA + (4 if temp_merged else 3)], 1)
+                if temp_merged:
+                    temp_adam()
+                L.cql_finalize(self.sums_ptr(S_ALPHA), la.ptr("p"), inv_b, E, self._conservative_weight,
+                               self._alpha_threshold, 1, 1, self.metric_ptr(M_ALPHA_LOSS), la.ptr("g"), st)
+                L.scalar_adam(la.ptr("p"), la.ptr("g"), la.ptr("m"), la.ptr("v"), self.counter_ptr(C_ALPHA),
+                              self._alpha_learning_rate, 0.9, 0.999, 1e-8, self.metric_ptr(M_ALPHA), st)
         L.stream_join(st, side)
         dq = self.ws("is2_dq", E, R)
         if not dp:
@@ -366,9 +375,6 @@ class CQLImpl(DDPGBaseImpl):
             self._allreduce(csum)
             self._allreduce(q_net.arena.grads)
         q_net.adam(self._critic_learning_rate, st, tau=self._tau, peer=self._peer_args(px, q_net, (csum, 2)))
-        if dp:
-            L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
-                           self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
         # actor step on the updated critics
         ctx_a = q_net.ctx("aq", B, E, True)
         qa = self.ws("aq_q", E, B)
@@ -394,6 +400,9 @@ class CQLImpl(DDPGBaseImpl):
         self._policy.adam(self._actor_learning_rate, st, tau=self._tau,
                           peer=self._peer_args(px, self._policy, (asum, 3)))
         if dp:
+            # metrics from the all-reduced sums, after everything that is on the critical path
+            L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
+                           self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
             L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
 
     # ---- NVLink peer-memory exchange (csrc/comm.cu): all-reduce fused into the Adam pass, no NCCL in the update

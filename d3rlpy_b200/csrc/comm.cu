@@ -150,15 +150,19 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
 // first kernel of an update: wait until every rank has finished reading this rank's gradients of the previous
 // update, then zero them (the backward kernels accumulate with RED)
 __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int done_index, const int* epoch,
-                                                             float* __restrict__ grads, long long n) {
+                                                             float* __restrict__ grads, long long n, int done_index2,
+                                                             float* __restrict__ grads2, long long n2) {
   if (threadIdx.x == 0) {
     const int prev = *epoch - 1;
     for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + done_index, prev);
+    if (grads2)
+      for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + done_index2, prev);
   }
   __syncthreads();
-  long long n4 = n >> 2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
-    ((float4*)grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = i0; i < (n >> 2); i += stride) ((float4*)grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (grads2)
+    for (long long i = i0; i < (n2 >> 2); i += stride) ((float4*)grads2)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // sum of a short vector over the ranks through the exchange block: slot = epoch & 1
@@ -179,6 +183,70 @@ __global__ void peer_allreduce_small_kernel(float* __restrict__ vec, int n, Peer
       s += src[t];
     }
     vec[t] = s;
+  }
+}
+
+// Data-parallel CQL: the two scalar optimizer steps that need rank sums, in ONE launch (was: small all-reduce, metric
+// copy, scalar Adam, finalize, scalar Adam = five launches on the critical path).
+//   vec[0..2]  alpha-step partial sums {-, sum logsumexp, sum data value}      (cql_impl.py:119-141)
+//   vec[3]     temperature-loss partial sum, which is also d loss / d log_temp  (sac_impl.py:128-146)
+// all-reduce through the exchange block, then (temperature) metric + Adam, (alpha) loss + gradient + Adam.
+// scalar blocks: {p, g, m, v} at float offsets 0, 4, 8, 12.
+__device__ __forceinline__ float scalar_adam2(float* p, float G, float* m, float* v, int t, double lr) {
+  const double b1 = 0.9, b2 = 0.999, eps = 1e-8;
+  double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+  float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2);
+  float M = *m, V = *v;
+  M = __fmaf_rn(w1, __fsub_rn(G, M), M);
+  V = __fmul_rn(V, fb2);
+  V = __fadd_rn(V, __fmul_rn(__fmul_rn(w2, G), G));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V), (float)sqrt(bc2)), (float)eps);
+  float P = __fadd_rn(*p, __fdiv_rn(__fmul_rn((float)(-(lr / bc1)), M), denom));
+  *p = P; *m = M; *v = V;
+  return P;
+}
+
+__global__ void dp_scalar_steps_kernel(float* __restrict__ vec, PeerPtrs ps, int channel, const int* epoch,
+                                       float* temp, const int* step_temp, double lr_temp, float* metric_temp_loss,
+                                       float* metric_temp, float* alpha, const int* step_alpha, double lr_alpha,
+                                       float inv_eb, float cw, float threshold, float* metric_alpha_loss,
+                                       float* metric_alpha) {
+  const int e = *epoch;
+  const int t = threadIdx.x;
+  const int n = temp ? 4 : 3;
+  __shared__ float sum_s[4];
+  float* mine = const_cast<float*>(ps.grads[ps.rank]) + ((channel * 2 + (e & 1)) * 16);
+  if (t < n) mine[t] = vec[t];
+  __threadfence_system();
+  __syncwarp();
+  if (t == 0) st_release_sys(ps.flags[ps.rank] + 2 * channel, e);
+  if (t < ps.world) wait_flag_ge(ps.flags[t] + 2 * channel, e);
+  __syncwarp();
+  if (t < n) {
+    float s = 0.f;
+    for (int r = 0; r < ps.world; ++r) {
+      const volatile float* src = ps.grads[r] + ((channel * 2 + (e & 1)) * 16);
+      s += src[t];
+    }
+    vec[t] = s;
+    sum_s[t] = s;
+  }
+  __syncwarp();
+  if (t == 0 && temp) {  // update_temp: the loss equals its gradient
+    const float G = sum_s[3];
+    *metric_temp_loss = G;
+    *metric_temp = expf(scalar_adam2(temp + 0, G, temp + 8, temp + 12, *step_temp, lr_temp));
+    vec[3] = 0.f;
+  }
+  if (t == 1) {  // update_alpha: loss = -clip(exp(log_alpha)) (scaled - threshold), minimised
+    const float ea = expf(alpha[0]);
+    const float ca = fminf(fmaxf(ea, 0.f), 1e6f);
+    const float scaled = cw * (sum_s[1] * inv_eb - sum_s[2] * inv_eb);
+    *metric_alpha_loss = -(ca * (scaled - threshold));
+    const float inside = (ea >= 0.f && ea <= 1e6f) ? 1.f : 0.f;
+    const float G = -inside * ea * (scaled - threshold);
+    *metric_alpha = expf(scalar_adam2(alpha + 0, G, alpha + 8, alpha + 12, *step_alpha, lr_alpha));
+    alpha[4] = 0.f;
   }
 }
 
@@ -365,15 +433,36 @@ extern "C" int d3b_peer_import(const void* handle_64, int64_t offset, void** ptr
 }
 
 extern "C" int d3b_peer_wait_zero(const void* const* flags_host, int world, int rank, int done_index,
-                                  const int* epoch, float* grads, int64_t n, void* stream) {
+                                  const int* epoch, float* grads, int64_t n, int done_index2, float* grads2,
+                                  int64_t n2, void* stream) {
   D3B_REQUIRE(epoch && grads && n >= 0 && n % 4 == 0, "peer_wait_zero: bad arguments");
+  D3B_REQUIRE(!grads2 || (n2 >= 0 && n2 % 4 == 0), "peer_wait_zero: bad second arena");
   PeerPtrs ps{};
   D3B_REQUIRE(fill_peers(ps, flags_host, flags_host, world, rank) == 0, "peer_wait_zero: bad peer table");
-  long long blocks = (n / 4 + 255) / 256;
+  long long blocks = ((n > n2 || !grads2 ? n : n2) / 4 + 255) / 256;
   if (blocks > 2 * d3b::kNumSM) blocks = 2 * d3b::kNumSM;
   if (blocks < 1) blocks = 1;
-  peer_wait_zero_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ps, done_index, epoch, grads, (long long)n);
+  peer_wait_zero_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ps, done_index, epoch, grads, (long long)n,
+                                                                           done_index2, grads2, (long long)n2);
   return d3b::check_launch("peer_wait_zero");
+}
+
+extern "C" int d3b_dp_scalar_steps(float* vec, const void* const* xchg_host, const void* const* flags_host, int world,
+                                   int rank, int channel, const int* epoch, float* temp_scalar, const int* step_temp,
+                                   double lr_temp, float* metric_temp_loss, float* metric_temp, float* alpha_scalar,
+                                   const int* step_alpha, double lr_alpha, float inv_members_batch,
+                                   float conservative_weight, float alpha_threshold, float* metric_alpha_loss,
+                                   float* metric_alpha, void* stream) {
+  D3B_REQUIRE(vec && epoch && alpha_scalar && step_alpha && metric_alpha_loss && metric_alpha && channel >= 0 && channel < 4,
+              "dp_scalar_steps: bad arguments");
+  D3B_REQUIRE(!temp_scalar || (step_temp && metric_temp_loss && metric_temp), "dp_scalar_steps: null temperature pointers");
+  PeerPtrs ps{};
+  D3B_REQUIRE(fill_peers(ps, xchg_host, flags_host, world, rank) == 0, "dp_scalar_steps: bad peer table");
+  dp_scalar_steps_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vec, ps, channel, epoch, temp_scalar, step_temp, lr_temp,
+                                                              metric_temp_loss, metric_temp, alpha_scalar, step_alpha,
+                                                              lr_alpha, inv_members_batch, conservative_weight,
+                                                              alpha_threshold, metric_alpha_loss, metric_alpha);
+  return d3b::check_launch("dp_scalar_steps");
 }
 
 extern "C" int d3b_peer_allreduce_small(float* vec, int n, const void* const* xchg_host, const void* const* flags_host,

@@ -328,7 +328,17 @@ int d3b_comm_destroy(void* comm);
 int d3b_peer_export(const void* ptr, void* handle_out_64, int64_t* offset_out);
 int d3b_peer_import(const void* handle_64, int64_t offset, void** ptr_out);
 int d3b_peer_wait_zero(const void* const* flags_host, int world, int rank, int done_index, const int* epoch,
-                       float* grads, int64_t n, void* stream);
+                       float* grads, int64_t n, int done_index2, float* grads2, int64_t n2, void* stream);
+/* grads2 (optional): a second arena (its own done flag) waited for and zeroed by the same launch. */
+/* Data-parallel CQL (cql_impl.py:119-141, sac_impl.py:128-146): all-reduce of vec = {-, sum logsumexp, sum data value,
+ * temperature-loss sum} over the exchange block, then the temperature step (loss metric, Adam, exp metric; skipped when
+ * temp_scalar is NULL) and the alpha step (loss, gradient, Adam, exp metric) in one launch.  *_scalar: {p,g,m,v} blocks
+ * at float offsets 0,4,8,12. */
+int d3b_dp_scalar_steps(float* vec, const void* const* xchg_host, const void* const* flags_host, int world, int rank,
+                        int channel, const int* epoch, float* temp_scalar, const int* step_temp, double lr_temp,
+                        float* metric_temp_loss, float* metric_temp, float* alpha_scalar, const int* step_alpha,
+                        double lr_alpha, float inv_members_batch, float conservative_weight, float alpha_threshold,
+                        float* metric_alpha_loss, float* metric_alpha, void* stream);
 int d3b_peer_allreduce_small(float* vec, int n, const void* const* xchg_host, const void* const* flags_host, int world,
                              int rank, int channel, const int* epoch, void* stream);
 int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, float* target, int64_t n, const int* step,

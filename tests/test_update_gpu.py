@@ -173,6 +173,14 @@ def test_update_from_device_gather_and_philox_noise_runs():
         assert set(h) == {"temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss"}
         assert all(np.isfinite(v) for v in h.values())
     assert hist[1]["temp"] < 1.0 and hist[1]["alpha"] != 1.0
+    # RoundIterator mode (n_epochs): every epoch visits len // batch_size shuffled batches
+    small = MDPDataset(rs.randn(2_000, O).astype(np.float32), rs.uniform(-1, 1, (2_000, A)).astype(np.float32),
+                       rs.randn(2_000).astype(np.float32), (np.arange(2_000) % 500 == 499).astype(np.float32))
+    algo2 = CQL(actor_encoder_factory=[64, 64], critic_encoder_factory=[64, 64], batch_size=64, n_action_samples=4)
+    hist2 = algo2.fit(small, n_epochs=2, seed=0)
+    assert len(hist2) == 2 and algo2.grad_step == 2 * (len(small.device_replay(algo2.impl._device)) // 64)
+    with pytest.raises(ValueError):
+        algo2.fit(small)
 
 
 # ----------------------------------------------------------------------------------------- bf16 mode
