@@ -24,6 +24,9 @@ class D3BError(RuntimeError):
     pass
 
 
+_SYNC_EACH = os.environ.get("D3B_SYNC_EACH", "0") == "1"
+
+
 def parse_header(path: str = HEADER) -> Dict[str, Tuple[str, List[Tuple[str, str]]]]:
     """Returns {name: (return_type, [(ctype, argname), ...])} for every d3b_* prototype."""
     text = open(path).read()
@@ -131,6 +134,13 @@ class Lib:
             rc = fn(*args)
             if rc != 0:
                 raise D3BError(f"d3b_{name} failed ({rc}): {self.last_error()}")
+            if _SYNC_EACH:  # debugging aid (D3B_SYNC_EACH=1, eager mode only): attribute an asynchronous fault to its launch
+                import torch
+
+                try:
+                    torch.cuda.synchronize()
+                except Exception as e:  # noqa: BLE001
+                    raise D3BError(f"device fault after d3b_{name}{tuple(a if isinstance(a, (int, float)) else '.' for a in args)}: {e}")
             return rc
 
         call.__name__ = name

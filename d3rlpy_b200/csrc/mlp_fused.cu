@@ -310,8 +310,14 @@ __global__ void __launch_bounds__(EW * 32 + 96, 1) mlp_forward_kernel(const __gr
           const int nkb_out = (p.N[l] + BK - 1) / BK;
           const bool store = ((p.save_mask >> l) & 1) && m0 < p.save_rows;
           if (!store) {
-            if (!last)  // still produced as the next layer's operand: one barrier phase per block
-              for (int kb = 0; kb < nkb_out; ++kb) act_par ^= 1u << kb;
+            // The blocks are still produced as the next layer's operand (one barrier phase each).  The phases must be
+            // WAITED for, not just counted: a parity wait only distinguishes adjacent phases, so a thread that runs two
+            // phases ahead of the barrier would take an older completion for the one it wants.
+            if (!last)
+              for (int kb = 0; kb < nkb_out; ++kb) {
+                mbar_wait(bars + B_ACTREADY + kb, (act_par >> kb) & 1);
+                act_par ^= 1u << kb;
+              }
             continue;
           }
           const bool blocked = (p.h_blocked >> l) & 1;

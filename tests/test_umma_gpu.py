@@ -224,6 +224,18 @@ def test_umma_wgrad_mn_major_operands(R, No, Ki, E, shared_b):
 def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, shared):
     """csrc/mlp_fused.cu vs torch on the same bf16-rounded operands (fp32 accumulate, bf16 activations):
     saved activations within one bf16 ulp of the reference chain, head within 2e-3 of its scale."""
+    _fused_forward_case(rows, E, in_dim, hidden, n_head, tanh, shared, 0)
+
+
+@pytest.mark.parametrize("rows,E,save_rows", [(40000, 3, 20000), (50000, 10, 128 * 7), (15872, 2, 7936)])
+def test_fused_mlp_forward_partial_save(rows, E, save_rows):
+    """`save_rows`: only the tiles below it store their activations (the alpha-step rows of CQL are forward-only).
+    Persistent CTAs then alternate between storing and non-storing units (several members, many tiles): the heads of
+    ALL rows and the activations of the saved rows must still be right, the other activation rows untouched."""
+    _fused_forward_case(rows, E, 23, [256, 256, 256], 1, False, True, save_rows)
+
+
+def _fused_forward_case(rows, E, in_dim, hidden, n_head, tanh, shared, save_rows):
     import ctypes
 
     from d3rlpy_b200._lib import lib
@@ -275,15 +287,18 @@ def test_fused_mlp_forward_matches_torch(rows, E, in_dim, hidden, n_head, tanh, 
                        arr(ctypes.c_void_p, [a.data_ptr() for a in acts]), arr(ctypes.c_int64, [a.shape[2] for a in acts]),
                        arr(ctypes.c_int64, [a.shape[1] * a.shape[2] for a in acts]),
                        arena.data_ptr() + 4 * hw_off, arena.data_ptr() + 4 * hb_off, ms, n_head, 1 if tanh else 0,
-                       out.data_ptr(), 0, _st())
+                       out.data_ptr(), save_rows, _st())
     torch.cuda.synchronize()
+    saved = rows if not save_rows else min(rows, -(-save_rows // 128) * 128)  # storing is decided per 128-row tile
     h = x[:, :, :in_dim].float().expand(E, rows, in_dim)
     for l, (w, b) in enumerate(zip(ws, bs)):
         ref = torch.relu(torch.einsum("erk,enk->ern", h, w.to(dev).float()) + b.to(dev)[:, None, :])
         got = acts[l][:, :, :hidden[l]].float()
         scale = max(1.0, ref.abs().max().item())
-        assert (got - ref).abs().max().item() <= 2.0 ** -7 * scale, (l, (got - ref).abs().max().item())
-        h = got  # continue from the kernel's own bf16 activations so that errors do not compound in the check
+        assert (got[:, :saved] - ref[:, :saved]).abs().max().item() <= 2.0 ** -7 * scale, (l, "saved rows")
+        assert saved == rows or got[:, saved:].abs().max().item() == 0.0, (l, "rows that must not be stored")
+        # continue from the kernel's own bf16 activations so that errors do not compound in the check
+        h = got if saved == rows else torch.cat([got[:, :saved], ref[:, saved:].to(torch.bfloat16).float()], 1)
     if n_head:
         ref = torch.einsum("erk,ejk->erj", h, hw.to(dev)) + hb.to(dev)[:, None, :]
         if tanh:
