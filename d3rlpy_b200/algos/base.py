@@ -294,6 +294,19 @@ class AlgoBase:
         assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
         return self._impl.sample_action(x)
 
+    def save_policy(self, fname: str) -> None:
+        """AlgoBase.save_policy (algos/base.py): greedy policy as TorchScript (.pt) or ONNX (.onnx)."""
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        self._impl.save_policy(fname)
+
+    def save_model(self, fname: str) -> None:
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        self._impl.save_model(fname)
+
+    def load_model(self, fname: str) -> None:
+        assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
+        self._impl.load_model(fname)
+
     # ------------------------------------------------------------------ fit over an HBM-resident replay
     def fit(self, dataset, n_epochs: Optional[int] = None, n_steps: Optional[int] = None,
             n_steps_per_epoch: int = 10000, shuffle: bool = True, seed: Optional[int] = None,

@@ -185,6 +185,22 @@ class ImplBase:
     def _checkpoint_views(self):
         raise NotImplementedError
 
+    # ------------------------------------------------------------------ deployment export (algos/torch/base.py:86-126)
+    POLICY_KIND: str = ""
+
+    def save_policy(self, fname: str) -> None:
+        """Greedy policy (observation scaler included) as TorchScript `.pt` / ONNX `.onnx`; see d3rlpy_b200/export.py."""
+        from ...export import GreedyPolicy, save_policy
+
+        self.sync()
+        pol = getattr(self, "policy", None)
+        imit = getattr(self, "imitator", None)
+        module = GreedyPolicy(self.POLICY_KIND, policy=pol.state_dict() if pol is not None else None,
+                              q=self.q_function.state_dict(), imitator=imit.state_dict() if imit is not None else None,
+                              scaler=self._scaler, n_action_samples=getattr(self, "_n_action_samples", 100),
+                              action_flexibility=getattr(self, "_action_flexibility", 0.05))
+        save_policy(module, self.observation_shape, fname)
+
     def save_model(self, fname: str) -> None:
         """torch.save({attr: state_dict}) with the reference's attribute names and state_dict keys
         (algos/torch/base.py:137-139, torch_utility.py:97-103), so either side can load the other's file."""

@@ -17,6 +17,7 @@ from __future__ import annotations
 from collections import OrderedDict
 
 import numpy as np
+from typing import Optional
 import torch
 
 from ...nets import DenseNet
@@ -61,6 +62,7 @@ class _ImitatorView:
 
 
 class BCQImpl(DDPGBaseImpl):
+    POLICY_KIND = "bcq"
     def __init__(self, *, imitator_learning_rate=1e-3, imitator_hidden=(750, 750), lam=0.75, n_action_samples=100,
                  action_flexibility=0.05, beta=0.5, **kw):
         super().__init__(**kw)
@@ -163,6 +165,39 @@ class BCQImpl(DDPGBaseImpl):
         q_tpn = self.ws("q_tpn", B)
         L.bcq_target_reduce(q.data_ptr(), R, q_tpn.data_ptr(), B, N, self._n_critics, self._lam, st)
         return q_tpn
+
+    # ------------------------------------------------------------------ evaluation (bcq_impl.py:163-211)
+    def _predict_best_action(self, obs: torch.Tensor, latent: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """BCQImpl._predict_best_action: N candidate actions per observation from the decoder on clamp(randn, +-0.5),
+        perturbed by the (online) residual policy, scored by critic 0; returns the arg-max candidate.
+        `latent` ([n*N, 2A], row = observation-major) injects the draws (parity tests); otherwise Philox."""
+        n, O, A, N, L, st = obs.shape[0], obs.shape[1], self._action_size, self._n_action_samples, self._lib, self._stream
+        Lz, R = 2 * A, n * N
+        eps = self.ws("e_eps", R, Lz)
+        if latent is not None:
+            eps.copy_(latent.to(self._device).reshape(R, Lz))
+        else:
+            self._tick(0)
+            seed = (self._seed + 0x51ED270B * (self.rank + 1)) & 0xFFFFFFFFFFFFFFFF
+            L.noise_fill(eps.data_ptr(), R * Lz, 0, seed, self.counter_ptr(0), st)
+        xd = self.ws("e_xd", R, O + Lz)
+        L.concat_rows(obs.data_ptr(), O, eps.data_ptr(), Lz, None, 0.0, 0.0, 0.5, xd.data_ptr(), O + Lz, n, N, O, Lz, st)
+        sampled = self.ws("e_sampled", 1, R, A)
+        self._vae_dec.forward("params", xd, O + Lz, R, self._vae_dec.ctx("e_d", R, 1, False), sampled, st, head_tanh=True)
+        xp = self.ws("e_xp", R, O + A)
+        L.concat_rows(obs.data_ptr(), O, sampled.data_ptr(), A, None, 0.0, 0.0, 0.0, xp.data_ptr(), O + A, n, N, O, A, st)
+        z = self.ws("e_z", 1, R, A)
+        self._policy.forward("params", xp, O + A, R, self._policy.ctx("e_p", R, 1, False), z, st)
+        xq = self.ws("e_xq", R, O + A)
+        L.residual_rows(z.data_ptr(), A, sampled.data_ptr(), A, obs.data_ptr(), O, xq.data_ptr(), O + A,
+                        self._action_flexibility, R, N, O, A, st)
+        _, q = self._critic_rows_forward("params", xq, R, "e_q", train=False)
+        with torch.cuda.stream(self._stream_obj):
+            index = q[0, :R].view(n, N).argmax(dim=1)
+            return xq[:, O:O + A].reshape(n, N, A)[torch.arange(n, device=self._device), index].clone()
+
+    def sample_action(self, x):
+        raise NotImplementedError("BCQ does not support sampling action")  # bcq_impl.py:213-214
 
     def _p_critic(self, db, q_tpn, step=True, sync_target=False):
         B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics

@@ -57,6 +57,7 @@ class _Scalar:
 
 
 class CQLImpl(DDPGBaseImpl):
+    POLICY_KIND = "normal"
     def __init__(self, *, temp_learning_rate=1e-4, alpha_learning_rate=1e-4, initial_temperature=1.0,
                  initial_alpha=1.0, alpha_threshold=10.0, conservative_weight=5.0, n_action_samples=10,
                  soft_q_backup=False, **kw):

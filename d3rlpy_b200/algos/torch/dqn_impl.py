@@ -21,6 +21,7 @@ S_LOSS = 0
 
 
 class DQNImpl(ImplBase):
+    POLICY_KIND = "discrete"
     DISCRETE = True
     DOUBLE = False
     CONSERVATIVE = False

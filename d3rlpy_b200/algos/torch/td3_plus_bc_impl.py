@@ -13,6 +13,7 @@ S_TD, S_ACT = 0, 4  # sums slots: TD uses [0..2], actor stats [4..6]
 
 
 class TD3PlusBCImpl(DDPGBaseImpl):
+    POLICY_KIND = "deterministic"
     def __init__(self, *, target_smoothing_sigma=0.2, target_smoothing_clip=0.5, alpha=2.5, **kw):
         super().__init__(**kw)
         self._target_smoothing_sigma = target_smoothing_sigma

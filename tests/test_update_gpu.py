@@ -492,6 +492,32 @@ def test_predict_api_matches_oracle():
     assert np.array_equal(algo.predict(x), qv.mean(0).argmax(1))
     act = rs.randint(0, 5, n)
     np.testing.assert_allclose(algo.predict_value(x, act), qv.mean(0)[np.arange(n), act], rtol=1e-5, atol=1e-5)
+    # BCQ: sampling-based greedy action (bcq_impl.py:163-211) with the latent draws injected
+    from d3rlpy_b200.algos import BCQ
+
+    N = 7
+    orc = ou.BCQ(O, A, hidden=[32, 32], vae_hidden=[48, 48], n_action_samples=N, seed=5)
+    algo = BCQ(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], imitator_encoder_factory=[48, 48],
+               n_action_samples=N)
+    algo.create_impl((O,), A)
+    algo.impl.q_function.load_state_dict(orc.q)
+    algo.impl.policy.load_state_dict(orc.pi)
+    algo.impl.imitator.load_state_dict(orc.imitator)
+    latent = torch.randn(n * N, 2 * A, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        xr = torch.tensor(x)[:, None, :].expand(n, N, O).reshape(n * N, O)
+        sampled = ou.vae_decode(orc.imitator, xr, latent.clamp(-0.5, 0.5))
+        cand = ou.residual_policy(orc.pi, xr, sampled, 0.05)
+        q0 = ou.q_continuous(orc.q, xr, cand, "none")[0].view(n, N)
+        ref_a = cand.view(n, N, A)[torch.arange(n), q0.argmax(1)].numpy()
+    obs_dev = algo.impl._eval_obs(x)
+    got = algo.impl._predict_best_action(obs_dev, latent=latent)
+    algo.impl.sync()
+    np.testing.assert_allclose(got.cpu().numpy(), ref_a, rtol=1e-5, atol=1e-6)
+    free = algo.predict(x)                                       # Philox draws: shape / range only
+    assert free.shape == (n, A) and np.all(np.abs(free) <= 1.0)
+    with pytest.raises(NotImplementedError):
+        algo.sample_action(x)
 
 
 @pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql"])
@@ -596,3 +622,25 @@ def test_from_json_rebuilds_algorithm_from_reference_and_own_params(tmp_path):
     again.impl.load_model(str(model))
     np.testing.assert_array_equal(algo.predict(obs), again.predict(obs))
     assert json.load(open(mine))["algorithm"] == "CQL"
+
+
+@pytest.mark.gpu
+def test_save_policy_exports_what_predict_computes(tmp_path):
+    """algo.save_policy (algos/torch/base.py:86-126): the TorchScript file evaluates, on the CPU, the same greedy action
+    `algo.predict` computes with the CUDA kernels (fp32 mode), after a few updates so that the weights are not the
+    initial ones."""
+    from d3rlpy_b200.algos import CQL, TD3PlusBC
+
+    rs = np.random.RandomState(0)
+    O, A = 6, 3
+    x = rs.randn(19, O).astype(np.float32)
+    for cls in (CQL, TD3PlusBC):
+        algo = cls(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], scaler=None)
+        algo.create_impl((O,), A)
+        for _ in range(2):
+            algo.update(_ns(_synthetic_batch(rs, 16, O, A)))
+        f = str(tmp_path / f"{cls.__name__}.pt")
+        algo.save_policy(f)
+        with torch.no_grad():
+            exported = torch.jit.load(f)(torch.tensor(x)).numpy()
+        np.testing.assert_allclose(exported, algo.predict(x), rtol=1e-5, atol=1e-6)
