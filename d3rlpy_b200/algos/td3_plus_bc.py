@@ -8,6 +8,8 @@ from .torch.td3_plus_bc_impl import TD3PlusBCImpl
 
 
 class TD3PlusBC(AlgoBase):
+    IMPL = TD3PlusBCImpl
+
     def __init__(self, *, actor_learning_rate: float = 3e-4, critic_learning_rate: float = 3e-4,
                  actor_optim_factory=None, critic_optim_factory=None, actor_encoder_factory="default",
                  critic_encoder_factory="default", q_func_factory="mean", batch_size: int = 256, n_frames: int = 1,
@@ -34,7 +36,7 @@ class TD3PlusBC(AlgoBase):
         self._factories = {"actor_encoder_factory": actor_encoder_factory, "critic_encoder_factory": critic_encoder_factory}
 
     def _create_impl(self, observation_shape, action_size) -> None:
-        self._impl = TD3PlusBCImpl(
+        self._impl = self.IMPL(
             observation_shape=observation_shape, action_size=action_size,
             actor_learning_rate=self._actor_learning_rate, critic_learning_rate=self._critic_learning_rate,
             actor_hidden=self._actor_hidden, critic_hidden=self._critic_hidden, gamma=self._gamma, tau=self._tau,

@@ -125,9 +125,11 @@ class CQLImpl(DDPGBaseImpl):
         R = B * (1 + 3 * N)
         ld = O + A
         x = self.ws("x_is", R, ld)
-        lp = self.ws("lp_is", 2, B * N)
+        lp = self.ws("lp_is", 2, max(B * N, 1))
         xp = x.data_ptr()
         L.concat_rows(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, xp, ld, B, 1, O, A, st)
+        if N == 0:  # plain SAC: the data rows are the whole critic input
+            return x, lp, R
         L.policy_sample_rows(head.data_ptr(), 2 * A, self.noise_view(f"{tag}_t", B).data_ptr(), db.ptr("obs"), O,
                              xp + 4 * ld * B, ld, None, lp.data_ptr(), B, N, O, A, MIN_LOGSTD, MAX_LOGSTD, 0, st)
         L.policy_sample_rows(head.data_ptr() + 4 * (B * 2 * A), 2 * A, self.noise_view(f"{tag}_tp1", B).data_ptr(),
@@ -263,7 +265,7 @@ class CQLImpl(DDPGBaseImpl):
         G = 2 if do_alpha else 1
         ld = (O + A + 7) // 8 * 8
         X = self.ws("xf_rows", G * R + 2 * B, ld, dtype=bf)
-        lp = self.ws("xf_lp", 4, B * N)
+        lp = self.ws("xf_lp", 4, max(B * N, 1))
         lpm = self.ws("xf_lpm", 3, B)  # soft-backup, actor, temp log-probs
         done = self.ws("xf_done", 4, dtype=torch.int32)
         dp = self.world_size > 1  # sharded minibatch: sums / gradients are all-reduced between the partial kernels
@@ -283,7 +285,8 @@ class CQLImpl(DDPGBaseImpl):
         acts_p, head = self._p_policy(db)
         nv = lambda name: self.noise_view(name, B).data_ptr()
         soft = self._soft_q_backup
-        ptrs = [nv("critic_t"), nv("critic_tp1"), nv("critic_rand"), lp[0].data_ptr(), lp[1].data_ptr()]
+        ptrs = [nv("critic_t"), nv("critic_tp1"), nv("critic_rand"), lp[0].data_ptr(), lp[1].data_ptr()] if N > 0 \
+            else [None] * 5  # N == 0: plain SAC (algos/torch/sac_impl.py), data rows only
         ptrs += [nv("alpha_t"), nv("alpha_tp1"), nv("alpha_rand"), lp[2].data_ptr(), lp[3].data_ptr()] if do_alpha \
             else [None] * 5
         ptrs += [nv("soft") if soft else None, lpm[0].data_ptr() if soft else None, nv("actor"), lpm[1].data_ptr(),
@@ -403,7 +406,7 @@ class CQLImpl(DDPGBaseImpl):
         if dp:
             # metrics from the all-reduced sums, after everything that is on the critical path
             L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
-                           self._alpha_threshold, 0, 1, self.metric_ptr(M_CRITIC), None, st)
+                           self._alpha_threshold, 0, 1 if N > 0 else 0, self.metric_ptr(M_CRITIC), None, st)
             L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
 
     # ---- NVLink peer-memory exchange (csrc/comm.cu): all-reduce fused into the Adam pass, no NCCL in the update
@@ -450,14 +453,14 @@ class CQLImpl(DDPGBaseImpl):
             if do_alpha:
                 self._p_alpha(db, head)
             q_t, q_tpn = self._p_target(db, head)
-            self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn)
+            self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn, conservative=self._n_action_samples > 0)
             self._p_actor(db, acts_p, head)
 
         fused = (self._precision == "bf16" and self._q_func.fused_ok
                  and self._policy.fused_ok and self.fused_glue)
         if fused and self.world_size > 1 and not hasattr(self, "_px"):
             self._px = self._peer_setup()  # collective IPC rendezvous: outside the dry pass / graph capture
-        self.run_program(("cql", db.B, do_temp, do_alpha, self._noise_injected, fused),
+        self.run_program((type(self).__name__, db.B, do_temp, do_alpha, self._noise_injected, fused),
                          (lambda: self._program_fused(db, do_temp, do_alpha)) if fused else program)
         names = []
         if do_temp:

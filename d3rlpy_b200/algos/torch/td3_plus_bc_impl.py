@@ -14,11 +14,28 @@ S_TD, S_ACT = 0, 4  # sums slots: TD uses [0..2], actor stats [4..6]
 
 class TD3PlusBCImpl(DDPGBaseImpl):
     POLICY_KIND = "deterministic"
+    BEHAVIOUR_CLONING = True   # TD3Impl below: plain TD3 actor loss -Q_0(s, pi(s)).mean()
+
     def __init__(self, *, target_smoothing_sigma=0.2, target_smoothing_clip=0.5, alpha=2.5, **kw):
         super().__init__(**kw)
         self._target_smoothing_sigma = target_smoothing_sigma
         self._target_smoothing_clip = target_smoothing_clip
         self._alpha = alpha
+
+    def _actor_seed(self, q0, a, db, dq, B, A, inv_b):
+        """Actor loss value + its gradient seed dQ_0.  TD3+BC (td3_plus_bc_impl.py:64-70): lambda = alpha / mean|Q_0|
+        (one extra exchange of the |Q| sums under data parallelism); TD3 (ddpg_impl.py:268-273): -mean Q_0."""
+        L, st = self._lib, self._stream
+        if self.BEHAVIOUR_CLONING:
+            L.td3bc_actor_stats(q0.data_ptr(), a.data_ptr(), A, db.ptr("act"), A, self.sums_ptr(S_ACT), B, A, st)
+            self._allreduce(self._slots[32 + S_ACT:32 + S_ACT + 3])
+            L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq.data_ptr(), B, B, 1,
+                               self.metric_ptr(M_ACTOR), st)
+            return inv_b
+        L.neg_mean_seed(q0.data_ptr(), dq.data_ptr(), self.sums_ptr(S_ACT), B, inv_b, st)
+        self._allreduce(self._slots[32 + S_ACT:32 + S_ACT + 1])
+        L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACT), 4, st)
+        return 0.0  # weight of the (a - pi(s))^2 term in the action gradient
 
     def _build_actor(self) -> None:
         O, A = self._observation_shape[0], self._action_size
@@ -72,17 +89,14 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         xa = self.ws("xa", B, O + A)
         L.concat_rows(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa.data_ptr(), O + A, B, 1, O, A, st)
         acts_c, q0 = self._critic_rows_forward("params", xa, B, "aq", members=1)
-        L.td3bc_actor_stats(q0.data_ptr(), a.data_ptr(), A, db.ptr("act"), A, self.sums_ptr(S_ACT), B, A, st)
-        self._allreduce(self._slots[32 + S_ACT:32 + S_ACT + 3])
         inv_b = 1.0 / (B * self.world_size)
         dq = self.ws("a_dq", 1, B)
-        L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq.data_ptr(), B, B, 1,
-                           self.metric_ptr(M_ACTOR), st)
+        bc_w = self._actor_seed(q0, a, db, dq, B, A, inv_b)
         dxa = self.ws("a_dx", B, A)
         self._q_func.backward(xa, O + A, B, acts_c, dq, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A,
                               dx_col0=O, dx_cols=A)
         dz = self.ws("pi_dz", 1, B, A)
-        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, inv_b, st)
+        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, bc_w, st)
         self._policy.backward(db.ptr("obs"), O, B, acts_p, dz, st)
         self._allreduce(self._policy.arena.grads)
         self._policy.adam(self._actor_learning_rate, st, tau=self._tau)
@@ -148,15 +162,13 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         ctx_a = q_net.ctx("aq", B, 1, True)
         q0 = self.ws("aq_q", 1, B)
         q_net.forward("params", None, 0, B, ctx_a, q0, st, x_bf16=(xa, ld))
-        L.td3bc_actor_stats(q0.data_ptr(), a.data_ptr(), A, db.ptr("act"), A, self.sums_ptr(S_ACT), B, A, st)
         dq0 = self.ws("a_dq", 1, B)
-        L.td3bc_actor_seed(self.sums_ptr(S_ACT), self._alpha, inv_b, A, dq0.data_ptr(), B, B, 1,
-                           self.metric_ptr(M_ACTOR), st)
+        bc_w = self._actor_seed(q0, a, db, dq0, B, A, inv_b)
         dxa = self.ws("a_dx", B, A)
         q_net.backward(None, 0, B, ctx_a, dq0, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
                        dx_cols=A)
         dz = self.ws("pi_dz", 1, B, A)
-        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, inv_b, st)
+        L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, bc_w, st)
         pi.backward(db.ptr("obs"), O, B, acts_p, dz, st)
         pi.adam(self._actor_learning_rate, st, tau=self._tau)
 
@@ -231,3 +243,14 @@ class TD3PlusBCImpl(DDPGBaseImpl):
 
     def sample_action(self, x) -> np.ndarray:
         return self.predict_best_action(x)
+
+
+class TD3Impl(TD3PlusBCImpl):
+    """TD3Impl (d3rlpy/algos/torch/td3_impl.py:15-78): the same target smoothing, critic step and delayed actor step;
+    the actor loss is DDPGImpl's -Q_0(s, pi(s)).mean() (ddpg_impl.py:268-273)."""
+
+    BEHAVIOUR_CLONING = False
+
+    def __init__(self, **kw):
+        kw.pop("alpha", None)
+        super().__init__(alpha=0.0, **kw)

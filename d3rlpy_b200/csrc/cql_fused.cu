@@ -390,7 +390,7 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
                             int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd,
                             void* x_bf16, int64_t ldx, int n_groups, const void* const* ptrs_host,
                             const int64_t* rows_host, void* stream) {
-  D3B_REQUIRE(batch >= 0 && n_action_samples >= 1 && obs_dim >= 1 && act_dim >= 1, "cql_rows: bad sizes");
+  D3B_REQUIRE(batch >= 0 && n_action_samples >= 0 && obs_dim >= 1 && act_dim >= 1, "cql_rows: bad sizes");
   D3B_REQUIRE(n_groups >= 1 && n_groups <= 2, "cql_rows: n_groups must be 1 or 2");
   if (batch == 0) return D3B_OK;
   D3B_REQUIRE(head && obs && next_obs && act && x_bf16 && ptrs_host && rows_host, "cql_rows: null pointer");
@@ -406,7 +406,7 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
     p.logp_t[g] = (float*)ptrs_host[5 * g + 3];
     p.logp_tp1[g] = (float*)ptrs_host[5 * g + 4];
     p.group_row0[g] = rows_host[g];
-    if (g < n_groups)
+    if (g < n_groups && n_action_samples > 0)  // N == 0 (plain SAC): data rows only, no importance-sampling groups
       D3B_REQUIRE(p.eps_t[g] && p.eps_tp1[g] && p.rand_act[g] && p.logp_t[g] && p.logp_tp1[g], "cql_rows: null group pointer");
   }
   p.eps_soft = (const float*)ptrs_host[10]; p.logp_soft = (float*)ptrs_host[11];

@@ -588,6 +588,39 @@ class CQL(_Algo):
         return m
 
 
+class SAC(CQL):
+    """SAC._update (algos/sac.py:177-198) over SACImpl (algos/torch/sac_impl.py:88-162): the update CQL extends --
+    temperature step, TD critic loss against the soft target min_e Q'(s', a') - exp(log_temp) log pi(a'|s') with a
+    sampled a', actor loss, both soft syncs.  No conservative term, no alpha."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4, temp_lr=3e-4,
+                 gamma=0.99, tau=0.005, initial_temperature=1.0, seed=0, policy=None, critics=None):
+        super().__init__(obs, act, hidden=hidden, n_critics=n_critics, actor_lr=actor_lr, critic_lr=critic_lr,
+                         temp_lr=temp_lr, alpha_lr=0.0, gamma=gamma, tau=tau,
+                         initial_temperature=initial_temperature, n_action_samples=0, soft_q_backup=True, seed=seed,
+                         policy=policy, critics=critics)
+
+    def compute_critic_loss(self, b, q_tpn, noise):
+        """DDPGBaseImpl.compute_critic_loss (algos/torch/ddpg_impl.py:154-165)."""
+        return td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+
+
+class TD3(TD3PlusBC):
+    """TD3._update (algos/td3.py:161-176) over TD3Impl (algos/torch/td3_impl.py): TD3+BC without the behaviour-cloning
+    term -- actor loss -Q_0(s, pi(s)).mean() (DDPGImpl.compute_actor_loss, algos/torch/ddpg_impl.py:268-273)."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99,
+                 tau=0.005, sigma=0.2, clip=0.5, update_actor_interval=2, seed=0, policy=None, critics=None):
+        super().__init__(obs, act, hidden=hidden, n_critics=n_critics, actor_lr=actor_lr, critic_lr=critic_lr,
+                         gamma=gamma, tau=tau, sigma=sigma, clip=clip, alpha=0.0,
+                         update_actor_interval=update_actor_interval, seed=seed, policy=policy, critics=critics)
+
+    def compute_actor_loss(self, b: Batch):
+        action = deterministic_policy(self.pi, b.observations)
+        return -q_continuous(self.q, b.observations, action, "none")[0].mean()
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import ref_import  # noqa: E402
 
 ref_import.load()
-from d3rlpy.algos import BCQ, CQL, DiscreteCQL, TD3PlusBC  # noqa: E402
+from d3rlpy.algos import BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
 from d3rlpy.models.encoders import VectorEncoderFactory  # noqa: E402
 
 
@@ -33,6 +33,8 @@ cases = {
     "td3bc": (TD3PlusBC(actor_encoder_factory=enc, critic_encoder_factory=enc, scaler=None), (6,), 3),
     "bcq": (BCQ(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc), (6,), 3),
     "dcql": (DiscreteCQL(encoder_factory=enc, n_critics=2), (6,), 4),
+    "sac": (SAC(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
+    "td3": (TD3(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
 }
 out = {}
 for name, (algo, obs, act) in cases.items():

@@ -40,3 +40,8 @@ def load_update():
 
 def load_sampler():
     return np.load(os.path.join(GOLDEN, "sampler.npz"))
+
+
+def load_siblings():
+    """SAC / TD3 fixtures (tests/golden/make_golden_siblings.py)."""
+    return np.load(os.path.join(GOLDEN, "update_siblings.npz"))

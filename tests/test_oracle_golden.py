@@ -6,7 +6,7 @@ import torch
 
 from oracle import sampler as osampler
 from oracle import update as oupdate
-from tests.golden_io import Case, load_sampler, load_update
+from tests.golden_io import Case, load_sampler, load_siblings, load_update
 
 
 def test_sampler_matches_reference_golden():
@@ -44,13 +44,17 @@ def _build(case: Case):
     if n == "dcql_pix":
         hw = int(c["hw"])
         return oupdate.DiscreteCQL((int(c["n_frames"]), hw, hw), int(c["act"]), critics=g("q")), oupdate.pixel_scaler()
+    if n == "sac":
+        return oupdate.SAC(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
+    if n == "td3":
+        return oupdate.TD3(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
     raise KeyError(n)
 
 
-@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix"])
+@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3"])
 def test_update_matches_reference_golden(name):
     torch.set_num_threads(1)
-    case = Case(load_update(), name)
+    case = Case(load_siblings() if name in ("sac", "td3") else load_update(), name)
     algo, scaler = _build(case)
     for s in range(case.steps):
         m = algo.update(oupdate.Batch(case.batch(s), scaler), oupdate.Noise(injected=case.noise(s)))

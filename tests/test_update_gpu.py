@@ -520,7 +520,7 @@ def test_predict_api_matches_oracle():
         algo.sample_action(x)
 
 
-@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql"])
+@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3"])
 def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     """impl.save_model writes the reference's checkpoint layout (tests/golden/checkpoint_keys.json, recorded from the
     unmodified reference's save_model); load_model restores parameters, targets and optimizer state exactly
@@ -528,7 +528,7 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     import json
     import os
 
-    from d3rlpy_b200.algos import BCQ, CQL, DiscreteCQL, TD3PlusBC
+    from d3rlpy_b200.algos import BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC
 
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "checkpoint_keys.json")))[name]
     H = [32, 32]
@@ -536,6 +536,10 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     def make():
         if name == "cql":
             a = CQL(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "sac":
+            a = SAC(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "td3":
+            a = TD3(actor_encoder_factory=H, critic_encoder_factory=H)
         elif name == "td3bc":
             a = TD3PlusBC(actor_encoder_factory=H, critic_encoder_factory=H, scaler=None)
         elif name == "bcq":
@@ -644,3 +648,41 @@ def test_save_policy_exports_what_predict_computes(tmp_path):
         with torch.no_grad():
             exported = torch.jit.load(f)(torch.tensor(x)).numpy()
         np.testing.assert_allclose(exported, algo.predict(x), rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------- sibling algorithms
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,precision,use_graph", [("sac", "fp32", False), ("sac", "fp32", True), ("sac", "bf16", True),
+                                                      ("td3", "fp32", False), ("td3", "fp32", True), ("td3", "bf16", True)])
+def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
+    """SAC and TD3 reuse the CQL / TD3+BC update graphs (zero importance-sampling groups; no behaviour-cloning term).
+    Fixtures: tests/golden/update_siblings.npz, recorded from the unmodified reference (make_golden_siblings.py)."""
+    from d3rlpy_b200.algos import SAC, TD3
+    from tests.golden_io import load_siblings
+
+    case = Case(load_siblings(), name)
+    c = case.cfg
+    rel = REL if precision == "fp32" else BF16_REL
+    if name == "sac":
+        algo = SAC(actor_encoder_factory=[32, 32, 32], critic_encoder_factory=[32, 32, 32], batch_size=int(c["batch"]),
+                   n_steps=3, precision=precision)
+    else:
+        algo = TD3(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
+                   precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    impl.policy.load_state_dict(case.group("init", "pi"))
+    impl.targ_policy.load_state_dict(case.group("init", "pi"))
+    for s in range(case.steps):
+        impl.inject_noise(case.noise(s), int(c["batch"]))
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    views = [("q", impl.q_function), ("pi", impl.policy), ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy)]
+    if name == "sac":
+        views.append(("log_temp", impl._log_temp))
+    for grp, view in views:
+        _assert_params(view.state_dict(), case.group("final", grp), grp, rel=rel)
+    assert algo.grad_step == case.steps
