@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import ref_import  # noqa: E402
 
 ref_import.load()
-from d3rlpy.algos import BCQ, CQL, DiscreteCQL, TD3PlusBC  # noqa: E402
+from d3rlpy.algos import BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
 from d3rlpy.models.encoders import VectorEncoderFactory  # noqa: E402
 
 
@@ -27,6 +27,8 @@ cases = {
     "bcq": (BCQ(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc), (6,), 3),
     "dcql": (DiscreteCQL(encoder_factory=enc, n_critics=2), (6,), 4),
     "dcql_pixel": (DiscreteCQL(n_frames=4, scaler="pixel"), (4, 84, 84), 4),
+    "sac": (SAC(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
+    "td3": (TD3(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
 }
 out = {}
 for name, (algo, obs, act) in cases.items():
