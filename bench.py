@@ -186,11 +186,12 @@ def run_reference(args, w):
 
 
 # ----------------------------------------------------------------------------------- our arm
-def build_algo(w, world_size=1, rank=0, precision="bf16"):
+def build_algo(w, world_size=1, rank=0, precision="bf16", **extra):
     from d3rlpy_b200.algos import CQL, TD3PlusBC
 
     kw = dict(world_size=world_size, rank=rank) if world_size > 1 else {}
     kw["precision"] = precision
+    kw.update(extra)
     if w["algo"] == "cql":
         algo = CQL(actor_encoder_factory=w["hidden"], critic_encoder_factory=w["hidden"], batch_size=w["batch"],
                    n_action_samples=w["n"], n_critics=w["critics"], use_gpu=int(os.environ.get("LOCAL_RANK", "0")), **kw)
@@ -397,6 +398,35 @@ def run_ours(args, w):
                         "sample": f"{best[2]} full updates (same config, batch 256) of oracle/update.py in {best[3]:.1f}s; "
                                   f"threads swept over {{{max(1, cores // 2)},{cores}}} of {cores} host cores"}
 
+    # ---- second line of SURVEY 8d: the reproduction script's variant (reproductions/offline/cql.py sets
+    # alpha_learning_rate=0.0, so update_alpha and its importance-sampling pass are not executed)
+    variant = None
+    if world == 1 and w["algo"] == "cql" and not strong:
+        algo0 = build_algo(w, 1, 0, args.precision, alpha_learning_rate=0.0)
+        impl0 = algo0.impl
+        holder0 = SimpleNamespace(_device_batch=db)   # same gathered minibatch buffers
+        for i in range(W):
+            gather(i)
+            impl0.update_fused_async(holder0)
+        impl0.sync()
+        ev0 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        with torch.cuda.stream(impl0._stream_obj):
+            for i in range(K):
+                if not args.no_flush:
+                    flush_buf.fill_(float(i))
+                impl0._stream_obj.wait_stream(impl._stream_obj)
+                ev0[i][0].record(impl0._stream_obj)
+                L.gather_vector(replay.obs.data_ptr(), w["obs"], replay.actions.data_ptr(), w["act"], 0,
+                                replay.rewards.data_ptr(), replay.meta.data_ptr(), idx_dev[W + i].data_ptr(), B, 1, 0.99,
+                                db.ptr("obs"), db.ptr("act"), db.ptr("rew"), db.ptr("next_obs"), db.ptr("term"),
+                                db.ptr("nsteps"), None, None, 0.0, impl0._stream)
+                impl0.update_fused_async(holder0)
+                ev0[i][1].record(impl0._stream_obj)
+        torch.cuda.synchronize(dev)
+        ms0 = float(np.sum([a.elapsed_time(b) for a, b in ev0]))
+        variant = {"alpha_learning_rate": 0.0, "updates_per_s": K / (ms0 * 1e-3), "ms_per_step": ms0 / K,
+                   "note": "reproductions/offline/cql.py variant: no update_alpha step"}
+
     if rank == 0:
         line = {
             "metric": METRIC if not strong else "CQL gradient updates/sec at batch 8192 (c5, sharded)", "value": unit_scale * K / (total_ms * 1e-3), "unit": "updates/s", "n_gpus": world,
@@ -409,7 +439,8 @@ def run_ours(args, w):
                        "parallelism": f"dp{world}" if world > 1 else "single",
                        "l2": "flushed (256 MiB write) between timed steps" if not args.no_flush else "not flushed",
                        "timing": "CUDA events per step on the launching stream, max over ranks",
-                       "step_ms_p10_p50_p90": [float(np.percentile(step_ms, p)) for p in (10, 50, 90)]},
+                       "step_ms_p10_p50_p90": [float(np.percentile(step_ms, p)) for p in (10, 50, 90)],
+                       "variant_alpha_lr0": variant},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "graph_nodes_per_update": graph_nodes,
             "roofline": roof, "cpu_baseline": cpu_baseline,
         }

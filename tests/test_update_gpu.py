@@ -686,3 +686,34 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     for grp, view in views:
         _assert_params(view.state_dict(), case.group("final", grp), grp, rel=rel)
     assert algo.grad_step == case.steps
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cql_reproduction_variant_without_alpha_step(precision):
+    """reproductions/offline/cql.py sets alpha_learning_rate=0.0: `update_alpha` (and its importance-sampling pass) is
+    skipped, alpha stays at its initial value inside the critic loss (cql.py:245-248).  vs the oracle, three updates."""
+    from d3rlpy_b200.algos import CQL
+
+    O, A, B, N, H = 11, 4, 64, 5, [64, 64]
+    rel = 2e-5 if precision == "fp32" else BF16_REL
+    orc = ou.CQL(O, A, hidden=H, n_action_samples=N, alpha_lr=0.0, seed=9)
+    algo = CQL(actor_encoder_factory=H, critic_encoder_factory=H, n_action_samples=N, alpha_learning_rate=0.0,
+               batch_size=B, precision=precision)
+    algo.create_impl((O,), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    impl.policy.load_state_dict(orc.pi)
+    impl.targ_policy.load_state_dict(orc.pi)
+    rs = np.random.RandomState(2)
+    for s in range(3):
+        arrays = _synthetic_batch(rs, B, O, A)
+        noise = ou.Noise(seed=50 + s)
+        ref = orc.update(ou.Batch(arrays), noise)
+        impl.inject_noise(noise.log, B)
+        m = algo.update(_ns(arrays))
+        assert "alpha" not in m and "alpha_loss" not in m
+        _assert_metrics(m, ref, f"alpha_lr=0 {precision} step {s}", rel=rel)
+    _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=rel)
+    _assert_params(impl.policy.state_dict(), orc.pi, "pi", rel=rel)
