@@ -45,6 +45,28 @@ class VectorEncoderFactory:
 _ADAM_DEFAULTS = {"optim_cls": "Adam", "betas": [0.9, 0.999], "eps": 1e-08, "weight_decay": 0, "amsgrad": False}
 
 
+def _q_func_to_json(factory) -> Dict[str, Any]:
+    """QFunctionFactory -> {"type", "params"} (models/q_functions.py:60-77,117-121,156-161)."""
+    if factory is None or factory == "mean" or getattr(factory, "TYPE", None) == "mean":
+        return {"type": "mean", "params": {"share_encoder": False}}
+    n = 32 if factory == "qr" else int(factory.n_quantiles)
+    return {"type": "qr", "params": {"share_encoder": False, "n_quantiles": n}}
+
+
+def _q_func_from_json(value, cls):
+    kind = value["type"] if isinstance(value, dict) else value
+    params = value.get("params", {}) if isinstance(value, dict) else {}
+    if params.get("share_encoder", False):
+        raise ValueError("share_encoder is not on the accelerated path")
+    if kind == "mean":
+        return "mean"
+    if kind == "qr" and getattr(cls, "SUPPORTS_QR", False):
+        from .dqn import QRQFunctionFactory
+
+        return QRQFunctionFactory(n_quantiles=int(params.get("n_quantiles", 32)))
+    raise ValueError(f"q_func_factory {kind!r} is not on the accelerated path of {cls.__name__}")
+
+
 def _encoder_to_json(factory) -> Dict[str, Any]:
     """EncoderFactory -> {"type", "params"} as `_serialize_params` writes it (d3rlpy/base.py:78-98 with
     models/encoders.py get_type/get_params)."""
@@ -196,7 +218,7 @@ class AlgoBase:
     def get_params(self, deep: bool = True) -> Dict[str, Any]:
         """Constructor arguments by name (LearnableBase.get_params, base.py:266-319): every `_x` attribute that is a
         hyper-parameter, the factories as objects."""
-        skip = {"_impl", "_grad_step", "_kwargs", "_factories", "_use_gpu"}
+        skip = {"_impl", "_grad_step", "_kwargs", "_factories", "_use_gpu", "_n_quantiles"}
         out: Dict[str, Any] = {}
         for key, value in vars(self).items():
             if key in skip or not key.startswith("_") or key.endswith("_hidden"):
@@ -217,6 +239,8 @@ class AlgoBase:
         for key, value in self.get_params().items():
             if key.endswith("encoder_factory"):
                 doc[key] = _encoder_to_json(value)
+            elif key == "q_func_factory":
+                doc[key] = _q_func_to_json(value)
             elif key in ("scaler", "action_scaler", "reward_scaler"):
                 doc[key] = _scaler_to_json(value)
             elif key == "use_gpu":
@@ -269,10 +293,7 @@ class AlgoBase:
                     raise ValueError(f"{key}: only Adam defaults are on the accelerated path, got {value}")
                 params[key] = None
             elif key == "q_func_factory":
-                kind = value["type"] if isinstance(value, dict) else value
-                if kind != "mean":
-                    raise ValueError("only the mean Q function is on the accelerated path")
-                params[key] = "mean"
+                params[key] = _q_func_from_json(value, cls)
             elif key == "scaler":
                 params[key] = _scaler_from_json(value)
         params["use_gpu"] = use_gpu

@@ -21,23 +21,60 @@ class PixelEncoderFactory:
         self.feature_size = feature_size
 
 
+class QRQFunctionFactory:
+    """Same constructor as d3rlpy.models.q_functions.QRQFunctionFactory (models/q_functions.py:123-165)."""
+
+    TYPE = "qr"
+
+    def __init__(self, share_encoder: bool = False, n_quantiles: int = 32, **kwargs: Any):
+        if share_encoder:
+            raise ValueError("share_encoder is not on the accelerated path")
+        self._share_encoder, self._n_quantiles = share_encoder, n_quantiles
+
+    @property
+    def n_quantiles(self) -> int:
+        return self._n_quantiles
+
+    def get_type(self) -> str:
+        return self.TYPE
+
+    def get_params(self, deep: bool = False) -> Dict[str, Any]:
+        return {"share_encoder": self._share_encoder, "n_quantiles": self._n_quantiles}
+
+
+def _n_quantiles_of(q_func_factory) -> int:
+    """0 for the mean Q function, n_quantiles for "qr" / a QRQFunctionFactory (ours or the reference's)."""
+    f = q_func_factory
+    if f == "mean" or getattr(f, "TYPE", None) == "mean":
+        return 0
+    if f == "qr":
+        return 32  # create_q_func_factory("qr"): QRQFunctionFactory() defaults
+    if getattr(f, "TYPE", None) == "qr":
+        if getattr(f, "share_encoder", False) or getattr(f, "_share_encoder", False):
+            raise ValueError("share_encoder is not on the accelerated path")
+        return int(f.n_quantiles)
+    raise ValueError("the mean and quantile-regression (qr) Q functions are on the accelerated path; iqn/fqf are not")
+
+
 class DQN(AlgoBase):
     IMPL = DQNImpl
+    SUPPORTS_QR = True
 
     def __init__(self, *, learning_rate: float = 6.25e-5, optim_factory=None, encoder_factory="default",
                  q_func_factory="mean", batch_size: int = 32, n_frames: int = 1, n_steps: int = 1, gamma: float = 0.99,
                  n_critics: int = 1, target_update_interval: int = 8000, use_gpu=0, scaler=None, reward_scaler=None,
                  impl=None, seed: int = 0, **kwargs: Any):
+        if kwargs.pop("action_scaler", None) is not None:  # params.json of the reference carries "action_scaler": null
+            raise ValueError("discrete algorithms take no action scaler")
         super().__init__(batch_size, n_frames, n_steps, gamma, scaler, None, reward_scaler, use_gpu, kwargs)
-        if q_func_factory != "mean":
-            raise ValueError("only the mean Q function is on the accelerated path")
+        self._n_quantiles = _n_quantiles_of(q_func_factory)
         if optim_factory is not None:
             raise ValueError("only AdamFactory() defaults are on the accelerated path")
         self._learning_rate, self._n_critics = learning_rate, n_critics
         self._target_update_interval = target_update_interval
         self._encoder_factory = encoder_factory
         self._impl, self._seed = impl, seed
-        self._factories = {"encoder_factory": encoder_factory}
+        self._factories = {"encoder_factory": encoder_factory, "q_func_factory": q_func_factory}
 
     def _impl_kwargs(self) -> Dict[str, Any]:
         return {}
@@ -53,6 +90,7 @@ class DQN(AlgoBase):
         else:
             hidden = _hidden_units(ef, [256, 256])
         kw.update(self._impl_kwargs())
+        kw["n_quantiles"] = self._n_quantiles
         self._impl = self.IMPL(observation_shape=observation_shape, action_size=action_size,
                                learning_rate=self._learning_rate, hidden=hidden, gamma=self._gamma,
                                n_critics=self._n_critics, use_gpu=self._use_gpu, scaler=self._scaler,

@@ -198,7 +198,8 @@ class ImplBase:
         module = GreedyPolicy(self.POLICY_KIND, policy=pol.state_dict() if pol is not None else None,
                               q=self.q_function.state_dict(), imitator=imit.state_dict() if imit is not None else None,
                               scaler=self._scaler, n_action_samples=getattr(self, "_n_action_samples", 100),
-                              action_flexibility=getattr(self, "_action_flexibility", 0.05))
+                              action_flexibility=getattr(self, "_action_flexibility", 0.05),
+                              n_quantiles=getattr(self, "_n_quantiles", 0))
         save_policy(module, self.observation_shape, fname)
 
     def save_model(self, fname: str) -> None:

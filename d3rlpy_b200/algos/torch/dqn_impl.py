@@ -4,7 +4,13 @@ and DiscreteCQLImpl (d3rlpy/algos/torch/cql_impl.py:246-302).
 One update = online-net forward on s' (Double-DQN action), target-net forward on s', ONE online-net
 forward + backward on s shared by the Huber TD term and the conservative term (the reference evaluates
 `self._q_func(obs_t)` twice, cql_impl.py:295,300, with identical values), Adam, and the hard target copy
-when `grad_step % target_update_interval == 0` (pre-increment, dqn.py:130-131)."""
+when `grad_step % target_update_interval == 0` (pre-increment, dqn.py:130-131).
+
+`n_quantiles > 0` switches every member to the quantile-regression Q function (QRQFunctionFactory,
+models/q_functions.py:123-165; DiscreteQRQFunction, q_functions/qr_q_function.py:22-88): the head emits
+A * n_quantiles values per sample (a dense layer on the GEMM kernels), Q(s, a) is the mean over the quantiles, the
+target is the quantile vector of the member with the smallest mean, the TD term is the quantile Huber loss
+(csrc/qr.cu)."""
 from __future__ import annotations
 
 from typing import Sequence
@@ -28,8 +34,9 @@ class DQNImpl(ImplBase):
 
     def __init__(self, observation_shape, action_size, learning_rate, hidden: Sequence[int], gamma, n_critics,
                  feature_size: int = 512, filters=None, use_gpu=0, scaler=None, reward_scaler=None, seed: int = 0,
-                 precision: str = "fp32", alpha: float = 1.0, **kw):
+                 precision: str = "fp32", alpha: float = 1.0, n_quantiles: int = 0, **kw):
         super().__init__(observation_shape, action_size, use_gpu, scaler, None, reward_scaler, **kw)
+        self._n_quantiles = int(n_quantiles or 0)
         self._learning_rate, self._hidden, self._gamma, self._n_critics = learning_rate, list(hidden), gamma, n_critics
         self._feature_size, self._filters = feature_size, filters
         self._precision, self._alpha = precision, alpha
@@ -42,7 +49,7 @@ class DQNImpl(ImplBase):
         return len(self._observation_shape) == 3
 
     def build(self) -> None:
-        A, E = self._action_size, self._n_critics
+        A, E = self._action_size * max(1, self._n_quantiles), self._n_critics
         if self._pixel:
             sc = self._scaler
             is_pixel_scaler = sc == "pixel" or getattr(sc, "TYPE", None) == "pixel"
@@ -83,8 +90,8 @@ class DQNImpl(ImplBase):
 
     # ------------------------------------------------------------------ program pieces
     def _forward(self, which, db, field, tag, train):
-        """Q values [E, B, A] of the chosen parameter set on obs / next_obs."""
-        B, A, E, st = db.B, self._action_size, self._n_critics, self._stream
+        """Q values [E, B, A] (quantiles [E, B, A * n_quantiles]) of the chosen parameter set on obs / next_obs."""
+        B, A, E, st = db.B, self._action_size * max(1, self._n_quantiles), self._n_critics, self._stream
         q = self.ws(f"{tag}_q", E, B, A)
         if self._pixel:
             ctx = self._q_func.ctx(tag, B, E, train)
@@ -99,6 +106,11 @@ class DQNImpl(ImplBase):
         B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
         _, q_t = self._forward("target", db, "next_obs", "tq", False)
         q_sel = self._forward("params", db, "next_obs", "oq", False)[1] if self.DOUBLE else q_t
+        nq = self._n_quantiles
+        if nq:
+            q_tpn = self.ws("q_tpn", B, nq)
+            L.qr_target(q_sel.data_ptr(), B * A * nq, q_t.data_ptr(), B * A * nq, q_tpn.data_ptr(), B, A, nq, E, st)
+            return q_tpn
         q_tpn = self.ws("q_tpn", B)
         L.dqn_target(q_sel.data_ptr(), B * A, q_t.data_ptr(), B * A, q_tpn.data_ptr(), B, A, E, st)
         return q_tpn
@@ -107,12 +119,18 @@ class DQNImpl(ImplBase):
         """compute_loss (dqn_impl.py:113-131; cql_impl.py:279-302) [+ backward + Adam (dqn_impl.py:97-111)]."""
         B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
         ctx, q = self._forward("params", db, "obs", "lq", True)
-        dq = self.ws("dq", E, B, A)
+        nq = self._n_quantiles
+        dq = self.ws("dq", E, B, A * max(1, nq))
         inv_b = 1.0 / (B * self.world_size)
         cons = 1 if self.CONSERVATIVE else 0
-        L.dcql_loss(q.data_ptr(), B * A, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
-                    db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A, self.sums_ptr(S_LOSS), B, A, E,
-                    inv_b, cons, st)
+        if nq:
+            L.qr_loss(q.data_ptr(), B * A * nq, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
+                      db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A * nq, self.sums_ptr(S_LOSS), B,
+                      A, nq, E, inv_b, cons, st)
+        else:
+            L.dcql_loss(q.data_ptr(), B * A, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
+                        db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A, self.sums_ptr(S_LOSS), B, A,
+                        E, inv_b, cons, st)
         self._allreduce(self._slots[32 + S_LOSS:32 + S_LOSS + 2])
         L.dcql_finalize(self.sums_ptr(S_LOSS), inv_b, self._alpha, cons, self.metric_ptr(M_LOSS), st)
         if step:
@@ -170,7 +188,7 @@ class DQNImpl(ImplBase):
         db = self.load_batch(batch)
         q = self._p_target(db)
         self.sync()
-        return q.view(-1, 1).clone()
+        return q.view(-1, self._n_quantiles or 1).clone()  # (B, 1), or (B, n_quantiles) like qr_q_function.py:80-88
 
     def compute_loss(self, batch, q_tpn: torch.Tensor) -> torch.Tensor:
         db = self.load_batch(batch)
@@ -200,6 +218,12 @@ def _dqn_q_values(impl, x) -> np.ndarray:
     """Q(s, .) of every member: [E, n, A] (eager forward of the online network, one sync)."""
     db = impl.load_batch(_EvalBatch(x))
     _, q = impl._forward("params", db, "obs", "eval", False)
+    nq = impl._n_quantiles
+    if nq:  # DiscreteQRQFunction.forward: mean over the quantiles (qr_q_function.py:44-48)
+        E, n, A = q.shape[0], q.shape[1], impl._action_size
+        v = impl.ws("eval_values", E, n, A)
+        impl._lib.qr_values(q.data_ptr(), n * A * nq, v.data_ptr(), n * A, n, A, nq, E, impl._stream)
+        q = v
     impl.sync()
     return q.detach().cpu().numpy()
 
@@ -241,6 +265,6 @@ class DiscreteCQLImpl(DoubleDQNImpl):
                                 n_steps=np.ones((B, 1), np.float32))
         db = self.load_batch(batch)
         self.zero_slots()
-        self._p_loss(db, self.ws("zero_tpn", B), step=False)
+        self._p_loss(db, self.ws("zero_tpn", B * max(1, self._n_quantiles)), step=False)
         self.sync()
         return (self._slots[32 + S_LOSS + 1] / B).clone()

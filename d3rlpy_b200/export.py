@@ -48,9 +48,10 @@ class GreedyPolicy(torch.nn.Module):
     "discrete" (DQN family: argmax of the member-mean Q, dqn_impl.py:131-133), "bcq" (bcq_impl.py:163-211)."""
 
     def __init__(self, kind: str, policy=None, q=None, imitator=None, scaler=None, n_action_samples: int = 100,
-                 action_flexibility: float = 0.05):
+                 action_flexibility: float = 0.05, n_quantiles: int = 0):
         super().__init__()
         self.kind, self.n, self.flex = kind, n_action_samples, action_flexibility
+        self.n_quantiles = n_quantiles  # > 0: QR members, value = mean over the quantiles (qr_q_function.py:44-48)
         self.pi = _cpu(policy) if policy is not None else {}
         self.q = _cpu(q) if q is not None else {}
         self.vae = _cpu(imitator) if imitator is not None else {}
@@ -72,7 +73,10 @@ class GreedyPolicy(torch.nn.Module):
         while f"_q_funcs.{i}._fc.weight" in self.q:
             pre = f"_q_funcs.{i}._encoder."
             h = _encoder(self.q, pre, x if action is None else torch.cat([x, action], dim=1))
-            vals.append(F.linear(h, self.q[f"_q_funcs.{i}._fc.weight"], self.q[f"_q_funcs.{i}._fc.bias"]))
+            v = F.linear(h, self.q[f"_q_funcs.{i}._fc.weight"], self.q[f"_q_funcs.{i}._fc.bias"])
+            if self.n_quantiles > 0:
+                v = v.view(v.shape[0], -1, self.n_quantiles).mean(dim=2)
+            vals.append(v)
             i += 1
         return torch.stack(vals, 0)
 

@@ -32,6 +32,54 @@ def _a8(n: int) -> int:
     return (n + 7) // 8 * 8
 
 
+HEAD_NARROW_MAX = 32  # csrc/heads.cu: warp-per-row GEMV heads; wider heads (quantile heads) run as dense layers
+
+
+def _wide_head_forward(net, which: str, cur, ld: int, sx: int, rows: int, E: int, head_out, stream: int, member0=0):
+    """Head wider than 32 outputs (DiscreteQRQFunction: Linear(feature, A * n_quantiles), qr_q_function.py:33-36):
+    one more dense layer without activation and with fp32 output — SIMT GEMM in fp32 mode, tcgen05 GEMM over the bf16
+    head-weight shadow in bf16 mode."""
+    L, ms, n, d = lib(), net.arena.member_size, net.head_out, net.feat
+    hw = net.arena.addr(which, "__head.weight", member0)
+    hb = net.arena.addr(which, "__head.bias", member0)
+    if net.precision == "fp32":
+        L.linear_forward(cur, ld, sx, hw, d, ms, hb, ms, _p(head_out), n, rows * n, rows, n, d, E, 0, stream)
+        return
+    base = net.shadow if which == "params" else net.shadow_target
+    w_off, ldw = net._sh_w[net._head_shadow]
+    wptr = base.data_ptr() + 2 * (member0 * net.shadow_member + w_off)
+    L.umma_gemm(cur, ld, sx, wptr, ldw, net.shadow_member, rows, n, d, E, 1, hb, ms, 0, None, 0, 0, None, 0, 0,
+                None, 0, 0, _p(head_out), n, rows * n, 0, stream)
+
+
+def _wide_head_backward(net, ctx, rows: int, E: int, d_head, last, ldl: int, sl: int, dcur, ldd: int, sd: int,
+                        stream: int, weight_grads: bool = True, member0=0):
+    """dW_head += d_head^T H, db_head += colsum(d_head), dZ = (d_head W_head) * [H > 0] for a wide head."""
+    L, ms, n, d = lib(), net.arena.member_size, net.head_out, net.feat
+    hw_g = net.arena.addr("grads", "__head.weight", member0)
+    hb_g = net.arena.addr("grads", "__head.bias", member0)
+    if net.precision == "fp32":
+        if weight_grads:
+            L.linear_backward_weight(_p(d_head), n, rows * n, last, ldl, sl, hw_g, d, ms, hb_g, ms, rows, n, d, E, stream)
+        L.linear_backward_data(_p(d_head), n, rows * n, net.arena.addr("params", "__head.weight", member0), d, ms, dcur,
+                               ldd, sd, last, ldl, sl, rows, n, d, E, stream)
+        return
+    ln = _a8(n)
+    dh = getattr(ctx, "dh_wide", None)
+    if dh is None or dh.shape != (E, rows, ln):
+        dh = ctx.dh_wide = torch.zeros(E, rows, ln, dtype=torch.bfloat16, device=net.device)
+    L.to_bf16(_p(d_head), n, E * rows, n, _p(dh), ln, None, 0, stream)
+    if weight_grads:
+        L.colsum_bf16(_p(dh), ln, rows * ln, hb_g, ms, rows, n, E, stream)
+        tiles = -(-n // 128) * -(-d // 256) * E
+        splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
+        L.umma_gemm_tn(_p(dh), ln, rows * ln, last, ldl, sl, n, d, rows, E, splits, hw_g, d, ms, 1, stream)
+    wt_off, ldwt = net._sh_wt[net._head_shadow]
+    wt = net.shadow.data_ptr() + 2 * (member0 * net.shadow_member + wt_off)
+    L.umma_gemm(_p(dh), ln, rows * ln, wt, ldwt, net.shadow_member, rows, d, n, E, 1, None, 0, 0, last, ldl, sl, dcur,
+                ldd, sd, None, 0, 0, None, 0, 0, 0, stream)
+
+
 class Ctx:
     """Per-call-site workspace of one forward(/backward): saved activations and gradient scratch."""
 
@@ -89,6 +137,7 @@ class DenseNet:
                                 exports=exports)
         self.feat = d
         self.device = device
+        self.wide_head = self.head_out > HEAD_NARROW_MAX
         # whole-network fused forward (csrc/mlp_fused.cu): widths multiples of 16 and <= 256, <= 4 layers, head <= 32
         self.fused_ok = (precision == "bf16" and 1 <= len(self.hidden) <= 4 and in_dim <= 256 and self.head_out <= 32
                          and all(h % 16 == 0 and 16 <= h <= 256 for h in self.hidden))
@@ -126,6 +175,13 @@ class DenseNet:
             self._sh_wt.append((wt_off, ldn))
             rows.append([self.arena.offsets[f"{self.trunk_prefix}_fcs.{i}.weight"], h, d, w_off, ldk, wt_off, ldn])
             d = h
+        if self.wide_head:  # a wide head is one more tensor-core layer: shadow its weight like the trunk's
+            ldk, ldn = _a8(d), _a8(self.head_out)
+            self._head_shadow = len(self._sh_w)
+            self._sh_w.append((off, ldk))
+            self._sh_wt.append((off + self.head_out * ldk, ldn))
+            rows.append([self.arena.offsets["__head.weight"], self.head_out, d, off, ldk, off + self.head_out * ldk, ldn])
+            off += self.head_out * ldk + d * ldn
         self.shadow_member = _a8(off)
         self._table = torch.tensor(rows, dtype=torch.int64)
         n = self.shadow_member * self.members
@@ -186,7 +242,10 @@ class DenseNet:
                 L.linear_forward(cur, ld, sx, self._w(which, i, member0), d, ms, self._b(which, i, member0), ms,
                                  _p(y), h, rows * h, rows, h, d, E, 1, stream)
                 cur, ld, sx, d = _p(y), h, rows * h, h
-            if head_out is not None:
+            if head_out is not None and self.wide_head:
+                assert not head_tanh
+                _wide_head_forward(self, which, cur, ld, sx, rows, E, head_out, stream, member0)
+            elif head_out is not None:
                 L.head_forward(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
                                _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
             return
@@ -228,7 +287,10 @@ class DenseNet:
             L.umma_gemm(cur, ld, sx, wptr, ldw, sms, rows, h, d, E, 1, self._b(which, i, member0), ms, 1,
                         None, 0, 0, _p(y), lh, rows * lh, None, 0, 0, None, 0, 0, 0, stream)
             cur, ld, sx, d = _p(y), lh, rows * lh, h
-        if head_out is not None:
+        if head_out is not None and self.wide_head:
+            assert not head_tanh
+            _wide_head_forward(self, which, cur, ld, sx, rows, E, head_out, stream, member0)
+        elif head_out is not None:
             L.head_forward_bf16(cur, ld, sx, self._hw(which, member0), d, ms, self._hb(which, member0), ms,
                                 _p(head_out), n, rows * n, rows, n, d, E, 1 if head_tanh else 0, stream)
 
@@ -246,12 +308,17 @@ class DenseNet:
         nl = len(self.hidden)
         if self.precision == "fp32":
             last = ctx.acts[-1]
-            if weight_grads:
-                L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, rows * feat, self._hw("grads", member0),
-                                       feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
             dcur = ctx.scratch[0]
-            L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat,
-                                 rows * feat, _p(last), feat, rows * feat, rows, n, feat, E, stream)
+            if self.wide_head:
+                _wide_head_backward(self, ctx, rows, E, d_head, _p(last), feat, rows * feat, _p(dcur), feat, rows * feat,
+                                    stream, weight_grads, member0)
+            else:
+                if weight_grads:
+                    L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, rows * feat,
+                                           self._hw("grads", member0), feat, ms, self._hb("grads", member0), ms, rows,
+                                           n, feat, E, stream)
+                L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat,
+                                     rows * feat, _p(last), feat, rows * feat, rows, n, feat, E, stream)
             which = 0
             for i in range(nl - 1, -1, -1):
                 h = self.hidden[i]
@@ -331,12 +398,16 @@ class DenseNet:
             return
         last = ctx.hb[-1]
         lf = _a8(feat)
-        if weight_grads:
-            L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),
-                                        feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
         dcur = ctx.dz[nl - 1]
-        L.head_backward_data_bf16(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), lf,
-                                  rows * lf, None, 0, 0, _p(last), lf, rows * lf, rows, n, feat, E, stream)
+        if self.wide_head:
+            _wide_head_backward(self, ctx, rows, E, d_head, _p(last), lf, rows * lf, _p(dcur), lf, rows * lf, stream,
+                                weight_grads, member0)
+        else:
+            if weight_grads:
+                L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),
+                                            feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
+            L.head_backward_data_bf16(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), lf,
+                                      rows * lf, None, 0, 0, _p(last), lf, rows * lf, rows, n, feat, E, stream)
         for i in range(nl - 1, -1, -1):
             h = self.hidden[i]
             lh = _a8(h)
@@ -478,6 +549,7 @@ class ConvNet:
             r0 += n
         self.arena = ParamArena(entries, members, device, with_target=with_target, member_key=member_key,
                                 exports=exports)
+        self.wide_head = self.head_out > HEAD_NARROW_MAX
         self._ctx: Dict[str, ConvCtx] = {}
         self._init_params(seed_gen)
         if precision == "bf16":
@@ -497,6 +569,14 @@ class ConvNet:
             self._sh_w.append((w_off, ldk))
             self._sh_wt.append((wt_off, ldn))
             rows.append([self.arena.offsets[self._names[i] + ".weight"], oc, K, w_off, ldk, wt_off, ldn])
+        if self.wide_head:
+            d, n = self.feat, self.head_out
+            ldk, ldn = _a8(d), _a8(n)
+            self._head_shadow = len(self._sh_w)
+            self._sh_w.append((off, ldk))
+            self._sh_wt.append((off + n * ldk, ldn))
+            rows.append([self.arena.offsets["__head.weight"], n, d, off, ldk, off + n * ldk, ldn])
+            off += n * ldk + d * ldn
         self.shadow_member = _a8(off)
         self._table = torch.tensor(rows, dtype=torch.int64)
         n = self.shadow_member * self.members
@@ -570,7 +650,11 @@ class ConvNet:
             else:
                 L.linear_forward(_p(p), K, sx, self._w(which, i), K, ms, self._b(which, i), ms, _p(y), oc,
                                  y.shape[1] * oc, rows, oc, K, E, 1, stream)
-        if head_out is not None:
+        if head_out is not None and self.wide_head:
+            last = ctx.acts[-1]
+            _wide_head_forward(self, which, _p(last), last.shape[2], last.shape[1] * last.shape[2], images, E, head_out,
+                               stream)
+        elif head_out is not None:
             last, n, d = ctx.acts[-1], self.head_out, self.feat
             hf = L.head_forward_bf16 if bf else L.head_forward
             hf(_p(last), last.shape[2], last.shape[1] * last.shape[2], self.arena.addr(which, "__head.weight"), d, ms,
@@ -586,7 +670,10 @@ class ConvNet:
         dcur = ctx.dacts[-1]
         ldd = dcur.shape[2]
         hw_g, hb_g = self.arena.addr("grads", "__head.weight"), self.arena.addr("grads", "__head.bias")
-        if bf:
+        if self.wide_head:
+            _wide_head_backward(self, ctx, images, E, d_head, _p(last), ldl, last.shape[1] * ldl, _p(dcur), ldd,
+                                dcur.shape[1] * ldd, stream)
+        elif bf:
             L.head_backward_weight_bf16(_p(d_head), n, images * n, _p(last), ldl, last.shape[1] * ldl, hw_g, d, ms, hb_g,
                                         ms, images, n, d, E, stream)
             L.head_backward_data_bf16(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms,

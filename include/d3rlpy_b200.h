@@ -271,6 +271,25 @@ int d3b_dcql_loss(const float* q, int64_t stride_q, const float* q_tpn, const fl
                   int64_t stride_dq, float* sums, int batch, int n_actions, int members, float inv_batch,
                   int conservative, void* stream);
 int d3b_dcql_finalize(const float* sums, float inv_batch, float alpha, int conservative, float* metric, void* stream);
+/* Quantile-regression Q head (QRQFunctionFactory) of the same algorithms.  theta = the head's outputs
+ * [members][batch][n_actions][n_quantiles] (DiscreteQRQFunction._compute_quantiles, qr_q_function.py:38-42).
+ * qr_target: greedy action of mean_e mean_i theta_select (online net: DoubleDQNImpl.compute_target, dqn_impl.py:162-171;
+ *   target net: DQNImpl.compute_target, :133-141), then the quantiles [batch][n_quantiles] of the member whose mean is
+ *   smallest (pick_quantile_value_by_action utility.py:17-24 + _reduce_quantile_ensemble "min",
+ *   ensemble_q_function.py:47-52).
+ * qr_loss: quantile Huber loss with fixed mid-point taus (qr_q_function.py:15-19,50-78; utility.py:35-61) summed over
+ *   members (ensemble_q_function.py:81-106) [+ the DiscreteCQL term on the quantile means, cql_impl.py:290-302] and the
+ *   gradient w.r.t. every theta; sums[0] += sum_e sum_b L, sums[1] += sum_b (logsumexp - data); dcql_finalize turns
+ *   the sums into the metric.
+ * qr_values: values[e][b][a] = mean_i theta (DiscreteQRQFunction.forward, qr_q_function.py:44-48). */
+int d3b_qr_target(const float* theta_select, int64_t stride_select, const float* theta_targ, int64_t stride_targ,
+                  float* q_tpn, int batch, int n_actions, int n_quantiles, int members, void* stream);
+int d3b_qr_loss(const float* theta, int64_t stride_theta, const float* q_tpn, const float* actions,
+                const float* rewards, const float* terminals, const float* n_steps, float gamma, float alpha,
+                float* dtheta, int64_t stride_dtheta, float* sums, int batch, int n_actions, int n_quantiles,
+                int members, float inv_batch, int conservative, void* stream);
+int d3b_qr_values(const float* theta, int64_t stride_theta, float* values, int64_t stride_values, int batch,
+                  int n_actions, int n_quantiles, int members, void* stream);
 
 /* ---- K9 (encoder side): Nature-DQN convolutions as patch gather + the dense-layer GEMMs above
  * (PixelEncoder.forward, d3rlpy/models/torch/encoders.py:81-162; nn.Conv2d at :100).

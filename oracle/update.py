@@ -128,9 +128,11 @@ def conv_out_hw(h: int, w: int, filters=NATURE_FILTERS):
     return h, w
 
 
-def make_discrete_critics(obs_shape, act: int, n: int, gen, hidden=None, feature_size=512) -> Params:
+def make_discrete_critics(obs_shape, act: int, n: int, gen, hidden=None, feature_size=512,
+                          n_quantiles: Optional[int] = None) -> Params:
     """EnsembleDiscreteQFunction of DiscreteMeanQFunction over PixelEncoder
-    (encoders.py:43-162) or VectorEncoder."""
+    (encoders.py:43-162) or VectorEncoder; with ``n_quantiles`` the members are DiscreteQRQFunction
+    (qr_q_function.py:22-36: head ``Linear(feature, action_size * n_quantiles)``)."""
     p: Params = OrderedDict()
     for i in range(n):
         pre = f"_q_funcs.{i}._encoder."
@@ -149,7 +151,7 @@ def make_discrete_critics(obs_shape, act: int, n: int, gen, hidden=None, feature
             hidden = hidden or [256, 256]
             p.update(make_mlp(pre, obs_shape[0], hidden, gen))
             feat = hidden[-1]
-        p.update(make_head(f"_q_funcs.{i}._fc", act, feat, gen))
+        p.update(make_head(f"_q_funcs.{i}._fc", act * (n_quantiles or 1), feat, gen))
     return p
 
 
@@ -216,15 +218,69 @@ def q_continuous(p: Params, x, action, reduction="mean", lam=0.75) -> torch.Tens
     return reduce_ensemble(torch.cat(vals, dim=0), reduction, lam)
 
 
-def q_discrete(p: Params, x, reduction="mean") -> torch.Tensor:
-    """EnsembleDiscreteQFunction.forward (ensemble_q_function.py:139-146)."""
+def q_discrete(p: Params, x, reduction="mean", n_quantiles: Optional[int] = None) -> torch.Tensor:
+    """EnsembleDiscreteQFunction.forward (ensemble_q_function.py:139-146); QR members return the mean over their
+    quantiles (DiscreteQRQFunction.forward, qr_q_function.py:44-48)."""
     vals = []
     for i in range(n_members(p)):
         pre = f"_q_funcs.{i}._encoder."
         h = pixel_forward(p, pre, x) if f"{pre}_convs.0.weight" in p else mlp_forward(p, pre, x)
         q = F.linear(h, p[f"_q_funcs.{i}._fc.weight"], p[f"_q_funcs.{i}._fc.bias"])
+        if n_quantiles:
+            q = q.view(x.shape[0], -1, n_quantiles).mean(dim=2)
         vals.append(q.view(1, x.shape[0], -1))
     return reduce_ensemble(torch.cat(vals, dim=0), reduction)
+
+
+def quantiles_discrete(p: Params, x, n_quantiles: int) -> torch.Tensor:
+    """DiscreteQRQFunction._compute_quantiles of every member: (E, B, A, n_quantiles) (qr_q_function.py:38-42)."""
+    vals = []
+    for i in range(n_members(p)):
+        pre = f"_q_funcs.{i}._encoder."
+        h = pixel_forward(p, pre, x) if f"{pre}_convs.0.weight" in p else mlp_forward(p, pre, x)
+        q = F.linear(h, p[f"_q_funcs.{i}._fc.weight"], p[f"_q_funcs.{i}._fc.bias"])
+        vals.append(q.view(1, x.shape[0], -1, n_quantiles))
+    return torch.cat(vals, dim=0)
+
+
+def make_taus(n_quantiles: int) -> torch.Tensor:
+    """``_make_taus`` (qr_q_function.py:15-19): mid-points of the n uniform probability bins."""
+    steps = torch.arange(n_quantiles, dtype=torch.float32)
+    taus = ((steps + 1).float() / n_quantiles).view(1, -1)
+    taus_dot = (steps.float() / n_quantiles).view(1, -1)
+    return (taus + taus_dot) / 2.0
+
+
+def quantile_huber_loss(quantiles, rew, target, term, taus, gamma) -> torch.Tensor:
+    """compute_quantile_loss / compute_quantile_huber_loss (q_functions/utility.py:35-61): per sample
+    mean_j sum_i |tau_i - 1[y_j - theta_i < 0]| * huber(y_j - theta_i)."""
+    B, n = quantiles.shape
+    y = rew + gamma * target * (1 - term)
+    th, ey, et = quantiles.view(B, 1, -1), y.view(B, -1, 1), taus.view(-1, 1, n)
+    hub = huber(th, ey)
+    delta = ((ey - th).detach() < 0.0).float()
+    return ((et - delta).abs() * hub).sum(dim=2).mean(dim=1)
+
+
+def td_error_discrete_qr(p: Params, obs, act_long, rew, target, term, gamma, n_quantiles) -> torch.Tensor:
+    """DiscreteQRQFunction.compute_error (qr_q_function.py:50-78) summed over members
+    (EnsembleQFunction.compute_error, ensemble_q_function.py:81-106)."""
+    assert target.shape == (obs.shape[0], n_quantiles)
+    th = quantiles_discrete(p, obs, n_quantiles)
+    one_hot = F.one_hot(act_long.view(-1), num_classes=th.shape[2]).view(-1, th.shape[2], 1).float()
+    taus = make_taus(n_quantiles)
+    total = torch.tensor(0.0)
+    for i in range(th.shape[0]):
+        picked = (th[i] * one_hot).sum(dim=1)  # pick_quantile_value_by_action (utility.py:17-24)
+        total = total + quantile_huber_loss(picked, rew, target, term, taus, gamma).view(-1, 1).mean()
+    return total
+
+
+def reduce_quantile_ensemble_min(y: torch.Tensor) -> torch.Tensor:
+    """``_reduce_quantile_ensemble(.., "min")`` for (E, B, n) (ensemble_q_function.py:27-52): per sample the
+    quantiles of the member whose mean is smallest."""
+    idx = y.mean(dim=-1).min(dim=0).indices
+    return y.transpose(0, 1)[torch.arange(y.shape[1]), idx]
 
 
 def td_error_continuous(p: Params, obs, act, rew, target, term, gamma) -> torch.Tensor:
@@ -712,10 +768,15 @@ class DiscreteCQL(_Algo):
     (algos/torch/cql_impl.py:279-302, dqn_impl.py:97-171)."""
 
     def __init__(self, obs_shape, act, n_critics=1, lr=6.25e-5, gamma=0.99, target_update_interval=8000,
-                 alpha=1.0, seed=0, critics=None, hidden=None):
+                 alpha=1.0, seed=0, critics=None, hidden=None, n_quantiles=None, double=True, conservative=True,
+                 feature_size=512):
+        """n_quantiles: QRQFunctionFactory members; double=False: DQNImpl.compute_target (dqn_impl.py:133-141);
+        conservative=False: DQNImpl.compute_loss (dqn_impl.py:113-131)."""
         gen = torch.Generator().manual_seed(seed)
+        self.nq, self.double, self.conservative = n_quantiles, double, conservative
         self.q = clone_params(critics if critics is not None
-                              else make_discrete_critics(tuple(obs_shape), act, n_critics, gen, hidden))
+                              else make_discrete_critics(tuple(obs_shape), act, n_critics, gen, hidden, feature_size,
+                                                         n_quantiles))
         self.targ_q = clone_params(self.q, False)
         self.optim = make_adam(self.q, lr)
         self.gamma, self.interval, self.alpha, self.act = gamma, target_update_interval, alpha, act
@@ -723,7 +784,12 @@ class DiscreteCQL(_Algo):
 
     def compute_target(self, b):
         with torch.no_grad():
-            action = q_discrete(self.q, b.next_observations).argmax(dim=1)
+            sel = self.q if self.double else self.targ_q
+            action = q_discrete(sel, b.next_observations, n_quantiles=self.nq).argmax(dim=1)
+            if self.nq:
+                th = quantiles_discrete(self.targ_q, b.next_observations, self.nq)  # (E,B,A,n)
+                one_hot = F.one_hot(action.view(-1), num_classes=self.act).view(1, -1, self.act, 1).float()
+                return reduce_quantile_ensemble_min((th * one_hot).sum(dim=2))  # (B,n)
             vals = q_discrete(self.targ_q, b.next_observations, "none")  # (E,B,A)
             one_hot = F.one_hot(action.view(-1), num_classes=self.act).float()
             picked = (vals * one_hot.unsqueeze(0)).sum(dim=2, keepdim=True)  # pick_value_by_action per member
@@ -731,12 +797,18 @@ class DiscreteCQL(_Algo):
 
     def compute_loss(self, b, q_tpn):
         act_long = b.actions.long()
-        loss = td_error_discrete(self.q, b.observations, act_long, b.rewards, q_tpn, b.terminals,
-                                 self.gamma ** b.n_steps)
-        policy_values = q_discrete(self.q, b.observations)
+        if self.nq:
+            loss = td_error_discrete_qr(self.q, b.observations, act_long, b.rewards, q_tpn, b.terminals,
+                                        self.gamma ** b.n_steps, self.nq)
+        else:
+            loss = td_error_discrete(self.q, b.observations, act_long, b.rewards, q_tpn, b.terminals,
+                                     self.gamma ** b.n_steps)
+        if not self.conservative:
+            return loss
+        policy_values = q_discrete(self.q, b.observations, n_quantiles=self.nq)
         lse = torch.logsumexp(policy_values, dim=1, keepdim=True)
         one_hot = F.one_hot(act_long.view(-1), num_classes=self.act)
-        data_values = (q_discrete(self.q, b.observations) * one_hot).sum(dim=1, keepdim=True)
+        data_values = (q_discrete(self.q, b.observations, n_quantiles=self.nq) * one_hot).sum(dim=1, keepdim=True)
         return loss + self.alpha * (lse - data_values).mean()
 
     def _update(self, b, noise=None):

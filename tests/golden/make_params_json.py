@@ -13,6 +13,7 @@ from oracle import ref_import  # noqa: E402
 ref_import.load()
 from d3rlpy.algos import BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
 from d3rlpy.models.encoders import VectorEncoderFactory  # noqa: E402
+from d3rlpy.models.q_functions import QRQFunctionFactory  # noqa: E402
 
 
 class _Logger:
@@ -27,6 +28,7 @@ cases = {
     "bcq": (BCQ(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc), (6,), 3),
     "dcql": (DiscreteCQL(encoder_factory=enc, n_critics=2), (6,), 4),
     "dcql_pixel": (DiscreteCQL(n_frames=4, scaler="pixel"), (4, 84, 84), 4),
+    "dcql_qr": (DiscreteCQL(encoder_factory=enc, q_func_factory=QRQFunctionFactory(n_quantiles=16)), (6,), 4),
     "sac": (SAC(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
     "td3": (TD3(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
 }

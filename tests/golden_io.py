@@ -45,3 +45,8 @@ def load_sampler():
 def load_siblings():
     """SAC / TD3 fixtures (tests/golden/make_golden_siblings.py)."""
     return np.load(os.path.join(GOLDEN, "update_siblings.npz"))
+
+
+def load_qr():
+    """DiscreteCQL / DQN with the quantile-regression Q head (tests/golden/make_golden_qr.py)."""
+    return np.load(os.path.join(GOLDEN, "update_qr.npz"))

@@ -355,3 +355,107 @@ def test_cql_fused_glue_kernels_match_unfused_kernels():
     _close(sc_a, sc_b, rtol=1e-6, msg="log_temp adam state")
     assert torch.equal(dqa, dqb)
     _close(m_act, ls_b, rtol=1e-6, msg="actor loss")
+
+
+# ----------------------------------------------------------------------------------------- quantile-regression head
+@pytest.mark.parametrize("B,A,NQ,E,conservative", [(64, 6, 200, 3, 1), (33, 18, 32, 1, 1), (5, 2, 1, 2, 0),
+                                                   (256, 4, 51, 2, 0)])
+def test_qr_target_loss_values_vs_autograd(B, A, NQ, E, conservative):
+    """csrc/qr.cu through the C ABI vs the oracle's statement of qr_q_function.py / utility.py:35-61 with autograd."""
+    from d3rlpy_b200._lib import lib
+    from oracle import update as ou
+
+    L, dev = lib(), _dev()
+    g = torch.Generator().manual_seed(B * 7 + NQ)
+    th_on = torch.randn(E, B, A, NQ, generator=g)
+    th_tg = torch.randn(E, B, A, NQ, generator=g)
+    act = torch.randint(A, (B,), generator=g)
+    rew, term = torch.randn(B, 1, generator=g), (torch.rand(B, 1, generator=g) < 0.2).float()
+    nsteps = torch.randint(1, 4, (B, 1), generator=g).float()
+    gamma, alpha = 0.99, 0.7
+
+    # ---- target: greedy action of the member-mean values of `select`, quantiles of the min-mean target member
+    a_star = th_on.mean(dim=3).mean(dim=0).argmax(dim=1)
+    one_hot = F.one_hot(a_star, A).view(1, B, A, 1).float()
+    ref_tpn = ou.reduce_quantile_ensemble_min((th_tg * one_hot).sum(dim=2))
+    d_on, d_tg = th_on.to(dev), th_tg.to(dev)
+    q_tpn = torch.empty(B, NQ, device=dev)
+    L.qr_target(d_on.data_ptr(), B * A * NQ, d_tg.data_ptr(), B * A * NQ, q_tpn.data_ptr(), B, A, NQ, E, _st())
+    assert torch.equal(q_tpn.cpu(), ref_tpn)
+
+    # ---- values
+    vals = torch.empty(E, B, A, device=dev)
+    L.qr_values(d_on.data_ptr(), B * A * NQ, vals.data_ptr(), B * A, B, A, NQ, E, _st())
+    _close(vals.cpu(), th_on.mean(dim=3), msg="values")
+
+    # ---- loss + gradient
+    th = th_on.clone().double().requires_grad_(True)
+    taus = ou.make_taus(NQ).double()
+    oh = F.one_hot(act, A).view(B, A, 1).double()
+    td = torch.zeros((), dtype=torch.float64)
+    for e in range(E):
+        picked = (th[e] * oh).sum(dim=1)
+        td = td + ou.quantile_huber_loss(picked, rew.double(), ref_tpn.double(), term.double(), taus,
+                                         (gamma ** nsteps).double()).mean()
+    cons = torch.zeros((), dtype=torch.float64)
+    if conservative:
+        v = th.mean(dim=3).mean(dim=0)
+        cons = (torch.logsumexp(v, dim=1) - (v * F.one_hot(act, A)).sum(dim=1)).mean()
+    total = td + alpha * cons
+    total.backward()
+    sums = torch.zeros(2, device=dev)
+    dth = torch.full((E, B, A, NQ), float("nan"), device=dev)
+    metric = torch.zeros(1, device=dev)
+    t = lambda x: x.to(dev).contiguous()
+    d_act, d_rew, d_term, d_ns = t(act.float()), t(rew), t(term), t(nsteps)
+    L.qr_loss(d_on.data_ptr(), B * A * NQ, q_tpn.data_ptr(), d_act.data_ptr(), d_rew.data_ptr(), d_term.data_ptr(),
+              d_ns.data_ptr(), gamma, alpha, dth.data_ptr(), B * A * NQ, sums.data_ptr(), B, A, NQ, E, 1.0 / B,
+              conservative, _st())
+    L.dcql_finalize(sums.data_ptr(), 1.0 / B, alpha, conservative, metric.data_ptr(), _st())
+    torch.cuda.synchronize()
+    assert abs(float(metric) - float(total)) <= 2e-5 * max(1.0, abs(float(total))), (float(metric), float(total))
+    ref_g = th.grad
+    err = float((dth.cpu().double() - ref_g).abs().max())
+    assert err <= 1e-5 * max(float(ref_g.abs().max()), 1e-12) + 1e-9, (err, float(ref_g.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,feat,n,E", [(32, 64, 96, 2), (100, 256, 800, 1), (7, 48, 40, 3)])
+def test_wide_head_dense_layer_forward_backward(precision, rows, feat, n, E):
+    """nets.DenseNet with a head wider than 32 outputs (quantile heads): forward and backward vs autograd."""
+    from d3rlpy_b200.nets import DenseNet
+
+    dev = _dev()
+    O = 10
+    g = torch.Generator().manual_seed(rows + n)
+    net = DenseNet(O, [feat], [("_fc", n)], E, dev, trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}",
+                   seed_gen=g, precision=precision)
+    assert net.wide_head and not net.fused_ok
+    st = _st()
+    net.refresh_shadow("params", st)
+    x = torch.randn(rows, O, generator=g).to(dev)
+    ctx = net.ctx("t", rows, E, True)
+    out = torch.empty(E, rows, n, device=dev)
+    net.forward("params", x, O, rows, ctx, out, st)
+    d_out = (torch.randn(E, rows, n, generator=g) / n).to(dev)
+    net.arena.grads.zero_()
+    net.backward(x, O, rows, ctx, d_out, st)
+    torch.cuda.synchronize()
+    tol = 1e-5 if precision == "fp32" else 3e-2
+    for e in range(E):
+        p = {k: net.arena.view(k, e).detach().clone().cpu().double().requires_grad_(True)
+             for k in ("_encoder._fcs.0.weight", "_encoder._fcs.0.bias", "__head.weight", "__head.bias")}
+        pre = F.linear(x.cpu().double(), p["_encoder._fcs.0.weight"], p["_encoder._fcs.0.bias"])
+        if precision == "bf16":
+            # bf16 operands move pre-activations by ~1e-2: units within that distance of zero may sit on the other side
+            # of the ReLU; the gradient check uses the mask the kernels actually applied (saved activations)
+            h = pre * (ctx.hb[0][e, :, :feat] > 0).cpu().double()
+        else:
+            h = torch.relu(pre)
+        y = F.linear(h, p["__head.weight"], p["__head.bias"])
+        _close(out[e].cpu().double(), y.detach(), rtol=tol, msg=f"head forward member {e}")
+        (y * d_out[e].cpu().double()).sum().backward()
+        for k, v in p.items():
+            got = net.arena.view(k, e, "grads").cpu().double()
+            scale = max(float(v.grad.abs().max()), 1e-6)
+            assert float((got - v.grad).abs().max()) <= tol * scale + 1e-7, (precision, k, e)

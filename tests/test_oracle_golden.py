@@ -6,7 +6,7 @@ import torch
 
 from oracle import sampler as osampler
 from oracle import update as oupdate
-from tests.golden_io import Case, load_sampler, load_siblings, load_update
+from tests.golden_io import Case, load_qr, load_sampler, load_siblings, load_update
 
 
 def test_sampler_matches_reference_golden():
@@ -44,6 +44,15 @@ def _build(case: Case):
     if n == "dcql_pix":
         hw = int(c["hw"])
         return oupdate.DiscreteCQL((int(c["n_frames"]), hw, hw), int(c["act"]), critics=g("q")), oupdate.pixel_scaler()
+    if n in ("qr_dcql_vec", "qr_dqn_vec"):
+        plain = n == "qr_dqn_vec"
+        return oupdate.DiscreteCQL((int(c["obs"]),), int(c["act"]), critics=g("q"), n_quantiles=int(c["n_quantiles"]),
+                                   target_update_interval=int(c["interval"]), double=not plain,
+                                   conservative=not plain), None
+    if n == "qr_dcql_pix":
+        hw = int(c["hw"])
+        return oupdate.DiscreteCQL((int(c["n_frames"]), hw, hw), int(c["act"]), critics=g("q"),
+                                   n_quantiles=int(c["n_quantiles"])), oupdate.pixel_scaler()
     if n == "sac":
         return oupdate.SAC(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
     if n == "td3":
@@ -51,10 +60,12 @@ def _build(case: Case):
     raise KeyError(n)
 
 
-@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3"])
+@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3",
+                                  "qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix"])
 def test_update_matches_reference_golden(name):
     torch.set_num_threads(1)
-    case = Case(load_siblings() if name in ("sac", "td3") else load_update(), name)
+    z = load_siblings() if name in ("sac", "td3") else load_qr() if name.startswith("qr_") else load_update()
+    case = Case(z, name)
     algo, scaler = _build(case)
     for s in range(case.steps):
         m = algo.update(oupdate.Batch(case.batch(s), scaler), oupdate.Noise(injected=case.noise(s)))

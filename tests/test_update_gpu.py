@@ -717,3 +717,122 @@ def test_cql_reproduction_variant_without_alpha_step(precision):
         _assert_metrics(m, ref, f"alpha_lr=0 {precision} step {s}", rel=rel)
     _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=rel)
     _assert_params(impl.policy.state_dict(), orc.pi, "pi", rel=rel)
+
+
+# ----------------------------------------------------------------------------------------- QR Q functions
+def _qr_algo(name, c, precision, **kw):
+    from d3rlpy_b200.algos import DQN, DiscreteCQL, PixelEncoderFactory, QRQFunctionFactory
+
+    qf = QRQFunctionFactory(n_quantiles=int(c["n_quantiles"]))
+    if name == "qr_dcql_pix":
+        hw, nf = int(c["hw"]), int(c["n_frames"])
+        algo = DiscreteCQL(encoder_factory=PixelEncoderFactory(feature_size=int(c["feature"])), q_func_factory=qf,
+                           batch_size=int(c["batch"]), n_frames=nf, scaler="pixel", precision=precision, **kw)
+        algo.create_impl((nf, hw, hw), int(c["act"]))
+        return algo
+    cls = DQN if name == "qr_dqn_vec" else DiscreteCQL
+    extra = {} if name == "qr_dqn_vec" else {"n_steps": 3}
+    algo = cls(encoder_factory=[int(c["h0"]), int(c["h1"])], q_func_factory="qr" if name == "qr_dqn_vec" else qf,
+               batch_size=int(c["batch"]), n_critics=int(c["n_critics"]), target_update_interval=int(c["interval"]),
+               precision=precision, **extra, **kw)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    return algo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix"])
+@pytest.mark.parametrize("precision,use_graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_qr_discrete_matches_reference_golden(name, precision, use_graph):
+    """DiscreteCQL / DQN with QRQFunctionFactory vs tests/golden/update_qr.npz (unmodified reference, identical
+    weights and minibatches): wide quantile head on the GEMM kernels, qr_target, qr_loss (csrc/qr.cu)."""
+    from tests.golden_io import load_qr
+
+    case = Case(load_qr(), name)
+    rel = REL if precision == "fp32" else BF16_REL
+    algo = _qr_algo(name, case.cfg, precision)
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    for s in range(case.steps):
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q", rel=rel)
+    _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q", rel=rel)
+
+
+@pytest.mark.gpu
+def test_qr_hooks_and_predict_match_oracle(tmp_path):
+    """compute_target -> (B, n_quantiles), compute_loss, _compute_conservative_loss, predict / predict_value and the
+    exported greedy policy of a QR DiscreteCQL against the oracle on the golden weights."""
+    import torch.nn.functional as F
+
+    from tests.golden_io import load_qr
+
+    case = Case(load_qr(), "qr_dcql_vec")
+    c = case.cfg
+    O, A, NQ = int(c["obs"]), int(c["act"]), int(c["n_quantiles"])
+    algo = _qr_algo("qr_dcql_vec", c, "fp32")
+    impl = algo.impl
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    # a different target network, so that min-by-mean member selection and the Double-DQN action matter
+    targ = {k: v * 1.05 + 0.01 for k, v in case.group("init", "q").items()}
+    impl.targ_q_function.load_state_dict(targ)
+    orc = ou.DiscreteCQL((O,), A, critics=case.group("init", "q"), n_quantiles=NQ)
+    orc.targ_q = ou.clone_params(targ, False)
+    arrays = case.batch(0)
+    ob = ou.Batch(arrays)
+    q_tpn = impl.compute_target(_ns(arrays))
+    ref_tpn = orc.compute_target(ob)
+    assert tuple(q_tpn.shape) == (int(c["batch"]), NQ)
+    torch.testing.assert_close(q_tpn.cpu(), ref_tpn, rtol=1e-5, atol=1e-6)
+    loss = impl.compute_loss(_ns(arrays), q_tpn)
+    ref_loss = orc.compute_loss(ob, ref_tpn)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
+    cons = impl._compute_conservative_loss(arrays["observations"], arrays["actions"])
+    pv = ou.q_discrete(orc.q, ob.observations, n_quantiles=NQ)
+    one_hot = F.one_hot(ob.actions.long().view(-1), num_classes=A)
+    ref_cons = (torch.logsumexp(pv, dim=1, keepdim=True) - (pv * one_hot).sum(dim=1, keepdim=True)).mean()
+    assert abs(float(cons) - float(ref_cons)) <= 1e-5 * max(1.0, abs(float(ref_cons)))
+    x = arrays["observations"]
+    np.testing.assert_array_equal(algo.predict(x), pv.argmax(dim=1).numpy())
+    acts = arrays["actions"].reshape(-1).astype(np.int64)
+    per_member = ou.q_discrete(orc.q, ob.observations, "none", n_quantiles=NQ).detach().numpy()
+    np.testing.assert_allclose(algo.predict_value(x, acts), per_member[:, np.arange(len(acts)), acts].mean(axis=0),
+                               rtol=1e-5, atol=1e-6)
+    algo.save_policy(str(tmp_path / "qr.pt"))
+    exported = torch.jit.load(str(tmp_path / "qr.pt"))(torch.tensor(x)).numpy()
+    np.testing.assert_array_equal(exported, algo.predict(x))
+    # params.json round trip keeps the Q-function factory
+    algo.save_params(str(tmp_path / "params.json"))
+    again = type(algo).from_json(str(tmp_path / "params.json"), use_gpu=0)
+    assert again._n_quantiles == NQ and again.impl._q_func.head_out == A * NQ
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_qr_discrete_cql_atari_reproduction_shape_vs_oracle(precision):
+    """reproductions/offline/discrete_cql.py:27-28: Nature-DQN encoder, QRQFunctionFactory(n_quantiles=200), batch 32 of
+    uint8 84x84 frame stacks — head 512 -> 4 * 200.  Two updates against the oracle."""
+    from d3rlpy_b200.algos import DiscreteCQL, QRQFunctionFactory
+
+    B, A, NQ = 32, 4, 200
+    rel = 2e-5 if precision == "fp32" else BF16_REL
+    orc = ou.DiscreteCQL((4, 84, 84), A, seed=9, n_quantiles=NQ)
+    algo = DiscreteCQL(batch_size=B, n_frames=4, scaler="pixel", q_func_factory=QRQFunctionFactory(n_quantiles=NQ),
+                       precision=precision)
+    algo.create_impl((4, 84, 84), A)
+    impl = algo.impl
+    impl.q_function.load_state_dict(orc.q)
+    impl.targ_q_function.load_state_dict(orc.q)
+    rs = np.random.RandomState(3)
+    for s in range(2):
+        arrays = dict(observations=rs.randint(0, 256, size=(B, 4, 84, 84)).astype(np.uint8),
+                      next_observations=rs.randint(0, 256, size=(B, 4, 84, 84)).astype(np.uint8),
+                      actions=rs.randint(A, size=(B,)).astype(np.int32),
+                      rewards=(rs.rand(B, 1) < 0.1).astype(np.float32),
+                      terminals=(rs.rand(B, 1) < 0.05).astype(np.float32), n_steps=np.ones((B, 1), np.float32))
+        ref = orc.update(ou.Batch(arrays, ou.pixel_scaler()), None)
+        m = algo.update(_ns(arrays))
+        _assert_metrics(m, ref, f"qr atari {precision} step {s}", rel=rel)
+    _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=rel)
