@@ -5,3 +5,4 @@ from .dqn import DQN, DiscreteCQL, DoubleDQN, PixelEncoderFactory, QRQFunctionFa
 from .td3_plus_bc import TD3PlusBC  # noqa: F401
 from .sac import SAC  # noqa: F401
 from .td3 import TD3  # noqa: F401
+from .ddpg import DDPG  # noqa: F401

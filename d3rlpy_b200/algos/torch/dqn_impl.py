@@ -125,8 +125,8 @@ class DQNImpl(ImplBase):
         cons = 1 if self.CONSERVATIVE else 0
         if nq:
             L.qr_loss(q.data_ptr(), B * A * nq, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
-                      db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A * nq, self.sums_ptr(S_LOSS), B,
-                      A, nq, E, inv_b, cons, st)
+                      db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A * nq,
+                      self.ws("qr_partials", 2 * B).data_ptr(), self.sums_ptr(S_LOSS), B, A, nq, E, inv_b, cons, st)
         else:
             L.dcql_loss(q.data_ptr(), B * A, q_tpn.data_ptr(), db.ptr("act"), db.ptr("rew"), db.ptr("term"),
                         db.ptr("nsteps"), self._gamma, self._alpha, dq.data_ptr(), B * A, self.sums_ptr(S_LOSS), B, A,

@@ -254,3 +254,8 @@ class TD3Impl(TD3PlusBCImpl):
     def __init__(self, **kw):
         kw.pop("alpha", None)
         super().__init__(alpha=0.0, **kw)
+
+
+class DDPGImpl(TD3Impl):
+    """DDPGImpl (d3rlpy/algos/torch/ddpg_impl.py:255-288): TD3Impl with `target_smoothing_sigma = 0` — the smoothing
+    term `clamp(0 * noise, -c, c)` vanishes and the target action is `clamp(pi'(s'), -1, 1)` (ddpg_impl.py:279-284)."""

@@ -51,14 +51,15 @@ __global__ void __launch_bounds__(256) qr_target_kernel(const float* __restrict_
 //   L[e][b] = (1/n) sum_j sum_i |tau_i - 1[y_j - th_i < 0]| * huber(y_j - th_i),   th = theta[e][b][a_data][:],
 //   y_j = r + gamma^n_steps * q_tpn[b][j] * (1 - terminal),   tau_i = ((i+1)/n + i/n) / 2
 // plus (conservative) alpha * (logsumexp_a Vbar[a] - Vbar[a_data]), Vbar[a] = mean_e mean_i theta[e][b][a][i].
-// Writes d(loss)/d(theta) for every (e, a, i) of the row; sums[0] += sum_e L[e][b], sums[1] += conservative term.
+// Writes d(loss)/d(theta) for every (e, a, i) of the row and the sample's two loss terms to partials[b], partials[B+b];
+// qr_loss_reduce_kernel adds them up in a fixed order (bit-reproducible metric, unlike one atomicAdd per block).
 __global__ void __launch_bounds__(128) qr_loss_kernel(const float* __restrict__ theta, long long sTh,
                                                       const float* __restrict__ q_tpn,
                                                       const float* __restrict__ actions,
                                                       const float* __restrict__ rew, const float* __restrict__ term,
                                                       const float* __restrict__ nsteps, float gamma, float alpha,
                                                       float* __restrict__ dtheta, long long sD,
-                                                      float* __restrict__ sums, int B, int A, int n, int E,
+                                                      float* __restrict__ partials, int B, int A, int n, int E,
                                                       float inv_b, int conservative) {
   extern __shared__ float sm[];
   float* y = sm;           // [n]
@@ -126,8 +127,24 @@ __global__ void __launch_bounds__(128) qr_loss_kernel(const float* __restrict__ 
   }
   loss = block_sum(loss);
   if (tid == 0) {
-    atomicAdd(sums + 0, loss);
-    if (conservative) atomicAdd(sums + 1, cons);
+    partials[b] = loss;
+    partials[B + b] = cons;
+  }
+}
+
+// sums[0] += sum_b partials[b], sums[1] += sum_b partials[B + b]: one block, fixed summation tree.
+__global__ void __launch_bounds__(256) qr_loss_reduce_kernel(const float* __restrict__ partials, float* __restrict__ sums,
+                                                             int B) {
+  float a = 0.f, c = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    a += partials[b];
+    c += partials[B + b];
+  }
+  a = block_sum(a);
+  c = block_sum(c);
+  if (threadIdx.x == 0) {
+    atomicAdd(sums + 0, a);
+    atomicAdd(sums + 1, c);
   }
 }
 
@@ -165,18 +182,23 @@ extern "C" int d3b_qr_target(const float* theta_select, int64_t stride_select, c
 
 extern "C" int d3b_qr_loss(const float* theta, int64_t stride_theta, const float* q_tpn, const float* actions,
                            const float* rewards, const float* terminals, const float* n_steps, float gamma,
-                           float alpha, float* dtheta, int64_t stride_dtheta, float* sums, int batch, int n_actions,
-                           int n_quantiles, int members, float inv_batch, int conservative, void* stream) {
+                           float alpha, float* dtheta, int64_t stride_dtheta, float* partials, float* sums, int batch,
+                           int n_actions, int n_quantiles, int members, float inv_batch, int conservative,
+                           void* stream) {
   D3B_REQUIRE(batch >= 0 && n_actions >= 1 && n_quantiles >= 1 && members >= 1, "qr_loss: bad sizes");
   if (batch == 0) return D3B_OK;
-  D3B_REQUIRE(theta && q_tpn && actions && rewards && terminals && n_steps && dtheta && sums, "qr_loss: null pointer");
+  D3B_REQUIRE(theta && q_tpn && actions && rewards && terminals && n_steps && dtheta && partials && sums,
+              "qr_loss: null pointer");
   size_t smem = ((size_t)n_quantiles + (size_t)members * n_actions + n_actions) * sizeof(float);
   D3B_REQUIRE(smem <= 48 * 1024, "qr_loss: n_quantiles + members * n_actions too large (%zu bytes of shared memory)",
               smem);
   qr_loss_kernel<<<batch, 128, smem, ST>>>(theta, stride_theta, q_tpn, actions, rewards, terminals, n_steps, gamma,
-                                           alpha, dtheta, stride_dtheta, sums, batch, n_actions, n_quantiles, members,
-                                           inv_batch, conservative);
-  return check_launch("qr_loss");
+                                           alpha, dtheta, stride_dtheta, partials, batch, n_actions, n_quantiles,
+                                           members, inv_batch, conservative);
+  int rc = check_launch("qr_loss");
+  if (rc) return rc;
+  qr_loss_reduce_kernel<<<1, 256, 0, ST>>>(partials, sums, batch);
+  return check_launch("qr_loss_reduce");
 }
 
 extern "C" int d3b_qr_values(const float* theta, int64_t stride_theta, float* values, int64_t stride_values, int batch,

@@ -279,15 +279,15 @@ int d3b_dcql_finalize(const float* sums, float inv_batch, float alpha, int conse
  *   ensemble_q_function.py:47-52).
  * qr_loss: quantile Huber loss with fixed mid-point taus (qr_q_function.py:15-19,50-78; utility.py:35-61) summed over
  *   members (ensemble_q_function.py:81-106) [+ the DiscreteCQL term on the quantile means, cql_impl.py:290-302] and the
- *   gradient w.r.t. every theta; sums[0] += sum_e sum_b L, sums[1] += sum_b (logsumexp - data); dcql_finalize turns
- *   the sums into the metric.
+ *   gradient w.r.t. every theta; sums[0] += sum_e sum_b L, sums[1] += sum_b (logsumexp - data), accumulated in a fixed
+ *   order through the workspace partials[2 * batch] (bit-reproducible); dcql_finalize turns the sums into the metric.
  * qr_values: values[e][b][a] = mean_i theta (DiscreteQRQFunction.forward, qr_q_function.py:44-48). */
 int d3b_qr_target(const float* theta_select, int64_t stride_select, const float* theta_targ, int64_t stride_targ,
                   float* q_tpn, int batch, int n_actions, int n_quantiles, int members, void* stream);
 int d3b_qr_loss(const float* theta, int64_t stride_theta, const float* q_tpn, const float* actions,
                 const float* rewards, const float* terminals, const float* n_steps, float gamma, float alpha,
-                float* dtheta, int64_t stride_dtheta, float* sums, int batch, int n_actions, int n_quantiles,
-                int members, float inv_batch, int conservative, void* stream);
+                float* dtheta, int64_t stride_dtheta, float* partials, float* sums, int batch, int n_actions,
+                int n_quantiles, int members, float inv_batch, int conservative, void* stream);
 int d3b_qr_values(const float* theta, int64_t stride_theta, float* values, int64_t stride_values, int batch,
                   int n_actions, int n_quantiles, int members, void* stream);
 

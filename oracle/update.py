@@ -677,6 +677,23 @@ class TD3(TD3PlusBC):
         return -q_continuous(self.q, b.observations, action, "none")[0].mean()
 
 
+class DDPG(TD3):
+    """DDPG._update (algos/ddpg.py:168-176) over DDPGImpl (algos/torch/ddpg_impl.py:255-288): no target smoothing (and
+    no noise draw), actor and both soft syncs on every step."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=1, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99,
+                 tau=0.005, seed=0, policy=None, critics=None):
+        super().__init__(obs, act, hidden=hidden, n_critics=n_critics, actor_lr=actor_lr, critic_lr=critic_lr,
+                         gamma=gamma, tau=tau, sigma=0.0, clip=0.5, update_actor_interval=1, seed=seed, policy=policy,
+                         critics=critics)
+
+    def compute_target(self, b: Batch, noise: Noise):
+        """DDPGImpl.compute_target (algos/torch/ddpg_impl.py:275-284)."""
+        with torch.no_grad():
+            action = deterministic_policy(self.targ_pi, b.next_observations)
+            return q_continuous(self.targ_q, b.next_observations, action.clamp(-1.0, 1.0), "min")
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

@@ -403,13 +403,13 @@ def test_qr_target_loss_values_vs_autograd(B, A, NQ, E, conservative):
         cons = (torch.logsumexp(v, dim=1) - (v * F.one_hot(act, A)).sum(dim=1)).mean()
     total = td + alpha * cons
     total.backward()
-    sums = torch.zeros(2, device=dev)
+    sums, partials = torch.zeros(2, device=dev), torch.empty(2 * B, device=dev)
     dth = torch.full((E, B, A, NQ), float("nan"), device=dev)
     metric = torch.zeros(1, device=dev)
     t = lambda x: x.to(dev).contiguous()
     d_act, d_rew, d_term, d_ns = t(act.float()), t(rew), t(term), t(nsteps)
     L.qr_loss(d_on.data_ptr(), B * A * NQ, q_tpn.data_ptr(), d_act.data_ptr(), d_rew.data_ptr(), d_term.data_ptr(),
-              d_ns.data_ptr(), gamma, alpha, dth.data_ptr(), B * A * NQ, sums.data_ptr(), B, A, NQ, E, 1.0 / B,
+              d_ns.data_ptr(), gamma, alpha, dth.data_ptr(), B * A * NQ, partials.data_ptr(), sums.data_ptr(), B, A, NQ, E, 1.0 / B,
               conservative, _st())
     L.dcql_finalize(sums.data_ptr(), 1.0 / B, alpha, conservative, metric.data_ptr(), _st())
     torch.cuda.synchronize()

@@ -520,7 +520,7 @@ def test_predict_api_matches_oracle():
         algo.sample_action(x)
 
 
-@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3"])
+@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3", "ddpg", "dqn_qr"])
 def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     """impl.save_model writes the reference's checkpoint layout (tests/golden/checkpoint_keys.json, recorded from the
     unmodified reference's save_model); load_model restores parameters, targets and optimizer state exactly
@@ -528,7 +528,7 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     import json
     import os
 
-    from d3rlpy_b200.algos import BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC
+    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, SAC, TD3, DiscreteCQL, TD3PlusBC
 
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "checkpoint_keys.json")))[name]
     H = [32, 32]
@@ -540,13 +540,17 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
             a = SAC(actor_encoder_factory=H, critic_encoder_factory=H)
         elif name == "td3":
             a = TD3(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "ddpg":
+            a = DDPG(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "dqn_qr":
+            a = DQN(encoder_factory=H, q_func_factory="qr")
         elif name == "td3bc":
             a = TD3PlusBC(actor_encoder_factory=H, critic_encoder_factory=H, scaler=None)
         elif name == "bcq":
             a = BCQ(actor_encoder_factory=H, critic_encoder_factory=H, imitator_encoder_factory=H)
         else:
             a = DiscreteCQL(encoder_factory=H, n_critics=2)
-        a.create_impl((6,), 4 if name == "dcql" else 3)
+        a.create_impl((6,), 4 if name in ("dcql", "dqn_qr") else 3)
         return a
 
     rs = np.random.RandomState(0)
@@ -554,7 +558,7 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
 
     def batch():
         d = _synthetic_batch(rs, B, 6, 3)
-        if name == "dcql":
+        if name in ("dcql", "dqn_qr"):
             d["actions"] = rs.randint(0, 4, B).astype(np.int32)
         return _ns(d)
 
@@ -653,11 +657,13 @@ def test_save_policy_exports_what_predict_computes(tmp_path):
 # ----------------------------------------------------------------------------------------- sibling algorithms
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,precision,use_graph", [("sac", "fp32", False), ("sac", "fp32", True), ("sac", "bf16", True),
-                                                      ("td3", "fp32", False), ("td3", "fp32", True), ("td3", "bf16", True)])
+                                                      ("td3", "fp32", False), ("td3", "fp32", True), ("td3", "bf16", True),
+                                                      ("ddpg", "fp32", False), ("ddpg", "fp32", True),
+                                                      ("ddpg", "bf16", True)])
 def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     """SAC and TD3 reuse the CQL / TD3+BC update graphs (zero importance-sampling groups; no behaviour-cloning term).
     Fixtures: tests/golden/update_siblings.npz, recorded from the unmodified reference (make_golden_siblings.py)."""
-    from d3rlpy_b200.algos import SAC, TD3
+    from d3rlpy_b200.algos import DDPG, SAC, TD3
     from tests.golden_io import load_siblings
 
     case = Case(load_siblings(), name)
@@ -666,6 +672,9 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     if name == "sac":
         algo = SAC(actor_encoder_factory=[32, 32, 32], critic_encoder_factory=[32, 32, 32], batch_size=int(c["batch"]),
                    n_steps=3, precision=precision)
+    elif name == "ddpg":
+        algo = DDPG(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
+                    n_steps=2, precision=precision)
     else:
         algo = TD3(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
                    precision=precision)
@@ -677,7 +686,8 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     impl.policy.load_state_dict(case.group("init", "pi"))
     impl.targ_policy.load_state_dict(case.group("init", "pi"))
     for s in range(case.steps):
-        impl.inject_noise(case.noise(s), int(c["batch"]))
+        if name != "ddpg":  # DDPG draws no noise (the graph's own Philox draw is multiplied by sigma = 0)
+            impl.inject_noise(case.noise(s), int(c["batch"]))
         m = algo.update(_ns(case.batch(s)))
         _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
     views = [("q", impl.q_function), ("pi", impl.policy), ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy)]
@@ -836,3 +846,30 @@ def test_qr_discrete_cql_atari_reproduction_shape_vs_oracle(precision):
         m = algo.update(_ns(arrays))
         _assert_metrics(m, ref, f"qr atari {precision} step {s}", rel=rel)
     _assert_params(impl.q_function.state_dict(), orc.q, "q", rel=rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["dqn_vec", "ddqn_vec"])
+@pytest.mark.parametrize("precision,use_graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_dqn_and_double_dqn_match_reference_golden(name, precision, use_graph):
+    """Plain DQN (greedy action of the target network, dqn_impl.py:133-141) and DoubleDQN (online network,
+    :162-171), mean Q function, two critics, n_steps = 2, hard target copy every 2 steps — vs the unmodified reference."""
+    from d3rlpy_b200.algos import DQN, DoubleDQN
+    from tests.golden_io import load_qr
+
+    case = Case(load_qr(), name)
+    c = case.cfg
+    rel = REL if precision == "fp32" else BF16_REL
+    cls = DQN if name == "dqn_vec" else DoubleDQN
+    algo = cls(encoder_factory=[int(c["h0"]), int(c["h1"])], batch_size=int(c["batch"]), n_critics=int(c["n_critics"]),
+               n_steps=2, target_update_interval=int(c["interval"]), precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    for s in range(case.steps):
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q", rel=rel)
+    _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q", rel=rel)
