@@ -4,13 +4,16 @@
 //   _assign_to_batch / _assign_observation / _assign_action  d3rlpy/dataset.pyx:1219-1342
 //   _stack_frames                                            d3rlpy/dataset.pyx:1051-1096
 // Data layout (DESIGN.md §HBM layout): step-indexed arrays O[S,...], A[S,...], R[S] plus one int4
-// per TRANSITION {step, episode_start_step, episode_last_transition_step, terminal}.
+// per TRANSITION {step, episode_start_step, episode_last_transition_step, flags}; flags bit 0 = the transition's
+// `terminal`, bit 1 = its next_observation is the all-zero dummy.  Episode-built data sets both on the last transition
+// of a terminal episode (dataset.pyx:86-96); the online ReplayBuffer also marks the transition INTO the terminal state
+// as terminal while it keeps the real next observation (online/buffers.py:283-300), hence two bits.
 #include "common.cuh"
 
 namespace d3b {
 
 struct RowInfo {
-  int g, start, k, g2, terminal;
+  int g, start, k, g2, terminal, zero_next;
 };
 
 __device__ __forceinline__ RowInfo row_info(const int4* __restrict__ meta, long long t, int n_steps) {
@@ -21,7 +24,9 @@ __device__ __forceinline__ RowInfo row_info(const int4* __restrict__ meta, long 
   int remain = m.z - m.x + 1;
   r.k = n_steps < remain ? n_steps : remain;
   r.g2 = r.g + r.k - 1;
-  r.terminal = (r.k == 1) ? m.w : __ldg(meta + t + (r.k - 1)).w;
+  int flags = (r.k == 1) ? m.w : __ldg(meta + t + (r.k - 1)).w;
+  r.terminal = flags & 1;
+  r.zero_next = (flags >> 1) & 1;  // plain copies take next_observation verbatim (dataset.pyx:1243-1264)
   return r;
 }
 
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
       for (int u = 0; u < 4; ++u) {
         int j = j0 + lane + 16 * u;
         xs[u] = j < O ? __ldg(src + j) : 0.f;
-        ys[u] = (j < O && !r.terminal) ? __ldg(nsrc + j) : 0.f;
+        ys[u] = (j < O && !r.zero_next) ? __ldg(nsrc + j) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -111,7 +116,8 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(
   RowInfo r = row_info(meta, t, n_steps);
   int back = n_frames - 1 - f;  // channel block f holds the frame `back` steps in the past (oldest first)
   uint8_t* dst = (which ? out_next : out_obs) + ((size_t)b * n_frames + f) * frame_bytes;
-  bool zero = which && r.terminal;  // terminal => all-zero next stack (dataset.pyx:1066-1068)
+  // stacking: terminal => all-zero next stack (dataset.pyx:1066-1068); single frames are copied verbatim
+  bool zero = which && (n_frames > 1 ? r.terminal : r.zero_next);
   int j = (which ? r.g2 + 1 : r.g) - back;
   if (j < r.start) j = r.start;     // episode start repeated as padding (dataset.pyx:1089-1095)
   const uint8_t* src = frames + (size_t)j * frame_bytes;

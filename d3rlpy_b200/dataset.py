@@ -20,7 +20,7 @@ from ._lib import D3BError, lib
 
 
 def _transition_meta(terminals: np.ndarray, episode_terminals: np.ndarray):
-    """Per-transition {step, episode_start, episode_last_transition_step, terminal}
+    """Per-transition {step, episode_start, episode_last_transition_step, flags}
     (flat restatement of _to_transitions, d3rlpy/dataset.pyx:70-116): a terminal episode yields
     one transition per step, a truncated episode drops its last step."""
     ends = np.nonzero(episode_terminals)[0]
@@ -40,7 +40,7 @@ def _transition_meta(terminals: np.ndarray, episode_terminals: np.ndarray):
         m[:, 2] = s + n_tr - 1
         m[:, 3] = 0
         if is_term:
-            m[-1, 3] = 1
+            m[-1, 3] = 3  # bit 0: terminal, bit 1: next observation is the zero dummy (csrc/gather.cu)
         meta.append(m)
         ep_ranges.append((t0, t0 + n_tr))
         t0 += n_tr
@@ -119,13 +119,13 @@ class Transition:
     @property
     def next_observation(self):
         m = self._m()
-        if m[3]:
+        if m[3] & 2:
             return np.zeros_like(self._ds.observations[m[0]])  # dummy after terminal (dataset.pyx:86-90)
         return self._ds.observations[m[0] + 1]
 
     @property
     def terminal(self):
-        return float(self._m()[3])
+        return float(self._m()[3] & 1)
 
     @property
     def prev_transition(self):

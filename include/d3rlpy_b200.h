@@ -39,8 +39,10 @@ int d3b_set_pdl(int enabled); /* programmatic dependent launch between the updat
  * _assign_action (d3rlpy/dataset.pyx:1139-1342) and _stack_frames
  * (d3rlpy/dataset.pyx:1051-1096); optional fused StandardScaler.transform
  * (d3rlpy/preprocessing/scalers.py:350-354) when scaler_mean/std are non-NULL.
- * `meta` is int32[T][4] = {step, episode_start_step, episode_last_step, terminal}
- * per transition; `indices` int64[batch] are transition indices. */
+ * `meta` is int32[T][4] = {step, episode_start_step, episode_last_step, flags}
+ * per transition (flags bit 0 = terminal, bit 1 = next_observation is the all-zero dummy: both set on the last
+ * transition of a terminal episode, dataset.pyx:86-96; the online ReplayBuffer sets bit 0 alone on the transition
+ * into the terminal state, online/buffers.py:283-300); `indices` int64[batch] are transition indices. */
 int d3b_gather_vector(const float* obs, int obs_dim, const void* actions, int act_dim, int discrete,
                       const float* rewards, const void* meta, const int64_t* indices, int batch, int n_steps,
                       float gamma, float* out_obs, void* out_act, float* out_rew, float* out_next, float* out_term,

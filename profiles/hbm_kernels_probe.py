@@ -56,7 +56,7 @@ meta = torch.zeros(S, 4, dtype=torch.int32)
 meta[:, 0] = torch.arange(S)
 meta[:, 1] = (torch.arange(S) // 1000) * 1000
 meta[:, 2] = meta[:, 1] + 999
-meta[999::1000, 3] = 1
+meta[999::1000, 3] = 3
 meta = meta.to(dev)
 idx = torch.randint(0, S, (B,), device=dev, dtype=torch.int64)
 o_obs, o_next = torch.empty(B, O, device=dev), torch.empty(B, O, device=dev)
@@ -75,7 +75,7 @@ meta = torch.zeros(S, 4, dtype=torch.int32)
 meta[:, 0] = torch.arange(S)
 meta[:, 1] = (torch.arange(S) // 2000) * 2000
 meta[:, 2] = meta[:, 1] + 1999
-meta[1999::2000, 3] = 1
+meta[1999::2000, 3] = 3
 meta = meta.to(dev)
 idx = torch.randint(0, S, (B,), device=dev, dtype=torch.int64)
 fo, fn_ = torch.empty(B, NF * HW, dtype=torch.uint8, device=dev), torch.empty(B, NF * HW, dtype=torch.uint8, device=dev)

@@ -50,3 +50,8 @@ def load_siblings():
 def load_qr():
     """DiscreteCQL / DQN with the quantile-regression Q head (tests/golden/make_golden_qr.py)."""
     return np.load(os.path.join(GOLDEN, "update_qr.npz"))
+
+
+def load_online():
+    """Online ReplayBuffer scripts and sampled minibatches (tests/golden/make_golden_online.py)."""
+    return np.load(os.path.join(GOLDEN, "online.npz"))

@@ -87,3 +87,27 @@ def test_update_matches_reference_golden(name):
         got = getattr(algo, attr)
         for k, v in ref.items():
             torch.testing.assert_close(got[k].detach(), v, rtol=1e-5, atol=2e-6, msg=f"{name}/{grp}/{k}")
+
+
+def test_online_replay_matches_reference_golden():
+    """oracle/sampler.py:OnlineReplay vs minibatches sampled by the unmodified reference ReplayBuffer
+    (tests/golden/online.npz): ring wrap-around, terminal / time-out episodes, mid-episode sampling."""
+    from tests.golden_io import load_online
+    from tests.online_script import FIELDS, initial_episodes, replay
+
+    z = load_online()
+    for name in [str(c) for c in z["cases"]]:
+        maxlen, _, discrete, _ = [int(v) for v in z[f"{name}/cfg"]]
+        buf = osampler.OnlineReplay(maxlen, z[f"{name}/script/observations"].shape[1:], bool(discrete))
+        for ep in initial_episodes(z, name):
+            buf.append_episode(ep.observations, ep.actions, ep.rewards, bool(ep.terminal))
+        n = 0
+        for j, got, ref in replay(z, name, buf, lambda b, B, f, s: b.sample(B, f, s, 0.99)):
+            for k in FIELDS:
+                assert got[k].dtype == ref[k].dtype and got[k].shape == ref[k].shape, (name, j, k)
+                if k == "rewards":
+                    np.testing.assert_allclose(got[k], ref[k], rtol=1e-6, atol=1e-7)
+                else:
+                    assert np.array_equal(got[k], ref[k]), (name, j, k)
+            n += 1
+        assert n >= 10
