@@ -176,8 +176,6 @@ class ImplBase:
 
     def read_slots(self) -> np.ndarray:
         self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
-        if not getattr(self, "_metrics_on_host", False):
-            return self.read_slots()  # device-resident batch: the graph has no read-back node
         self.sync()
         return self._slots_host.numpy()
 

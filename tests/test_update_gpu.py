@@ -873,3 +873,34 @@ def test_dqn_and_double_dqn_match_reference_golden(name, precision, use_graph):
         _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
     _assert_params(impl.q_function.state_dict(), case.group("final", "q"), "q", rel=rel)
     _assert_params(impl.targ_q_function.state_dict(), case.group("final", "targ_q"), "targ_q", rel=rel)
+
+
+@pytest.mark.gpu
+def test_update_accepts_device_minibatch_like_numpy_minibatch():
+    """The reference's documented flow `algo.update(TransitionMiniBatch(transitions))` (base.py:746-758): a minibatch
+    gathered on the GPU (device-resident, no host copy) gives the same update as the same arrays passed from the host."""
+    from d3rlpy_b200.algos import TD3PlusBC
+    from d3rlpy_b200.dataset import MDPDataset, TransitionMiniBatch
+
+    rs = np.random.RandomState(3)
+    S, O, A, B = 3000, 9, 3, 64
+    ds = MDPDataset(rs.randn(S, O).astype(np.float32), rs.uniform(-1, 1, (S, A)).astype(np.float32),
+                    rs.randn(S).astype(np.float32), (np.arange(S) % 300 == 299).astype(np.float32))
+    trs = ds.transitions()
+    algos = [TD3PlusBC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=B, scaler=None,
+                       n_steps=2, seed=4) for _ in range(2)]
+    for a in algos:
+        a.create_impl((O,), A)
+    noise = [torch.randn(B, A)]
+    for step in range(3):
+        batch = TransitionMiniBatch([trs[i] for i in rs.randint(len(trs), size=B)], n_steps=2)
+        arrays = dict(observations=batch.observations, actions=batch.actions, rewards=batch.rewards,
+                      next_observations=batch.next_observations, terminals=batch.terminals, n_steps=batch.n_steps)
+        for a in algos:
+            a.impl.inject_noise(noise, B)
+        m_dev = algos[0].update(batch)
+        m_host = algos[1].update(_ns(arrays))
+        assert m_dev.keys() == m_host.keys()
+        for k in m_dev:
+            assert abs(float(m_dev[k]) - float(m_host[k])) <= 1e-6 * max(1.0, abs(float(m_host[k]))), (step, k)
+    _assert_params(algos[0].impl.q_function.state_dict(), algos[1].impl.q_function.state_dict(), "q", rel=1e-6)
