@@ -205,6 +205,36 @@ class AlgoBase:
     def build_with_dataset(self, dataset) -> None:
         self.create_impl(self._get_shape(dataset.get_observation_shape()), dataset.get_action_size())
 
+    def build_with_env(self, env) -> None:
+        """LearnableBase.build_with_env (base.py:707-720): shapes from the gym-like environment's spaces."""
+        space = env.action_space
+        action_size = int(space.n) if hasattr(space, "n") else int(space.shape[0])
+        self.create_impl(self._get_shape(env.observation_space.shape), action_size)
+
+    @property
+    def action_size(self) -> Optional[int]:
+        return self._impl.action_size if self._impl is not None else None
+
+    @property
+    def observation_shape(self):
+        return self._impl.observation_shape if self._impl is not None else None
+
+    @property
+    def action_scaler(self):
+        return self._action_scaler
+
+    def fit_online(self, env, buffer=None, explorer=None, n_steps: int = 1000000, n_steps_per_epoch: int = 10000,
+                   update_interval: int = 1, update_start_step: int = 0, random_steps: int = 0,
+                   timelimit_aware: bool = True, callback=None, **unused: Any) -> List[Dict[str, float]]:
+        """AlgoBase.fit_online (algos/base.py:161-247): `train_single_env` with a ReplayBuffer of 1M transitions by
+        default; logging / evaluation arguments of the reference are accepted and ignored."""
+        from ..online import ReplayBuffer, train_single_env
+
+        if buffer is None:
+            buffer = ReplayBuffer(1000000, env=env)
+        return train_single_env(self, env, buffer, explorer, n_steps, n_steps_per_epoch, update_interval,
+                                update_start_step, random_steps, timelimit_aware, callback)
+
     def update(self, batch) -> Dict[str, float]:
         """LearnableBase.update (base.py:746-758): `_update` then grad_step += 1."""
         loss = self._update(batch)

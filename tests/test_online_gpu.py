@@ -87,3 +87,75 @@ def test_online_buffer_long_script_vs_oracle_with_compaction(kind):
         algo.create_impl(oshape, asize)
         m = algo.update(buf.sample(48))
         assert np.isfinite(m["critic_loss"]) and np.isfinite(m["actor_loss"])
+
+
+class _Box:
+    def __init__(self, shape, rs):
+        self.shape, self._rs = shape, rs
+
+    def sample(self):
+        return self._rs.uniform(-1, 1, self.shape).astype(np.float32)
+
+
+class _Discrete:
+    def __init__(self, n, rs):
+        self.n, self._rs = n, rs
+
+    def sample(self):
+        return int(self._rs.randint(self.n))
+
+
+class _PointEnv:
+    """Gym-like toy: a point on a line, reward -|x|, terminal when |x| > 2, time limit of 25 steps."""
+
+    def __init__(self, discrete, seed=0):
+        self._rs = np.random.RandomState(seed)
+        self.observation_space = _Box((3,), self._rs)
+        self.action_space = _Discrete(3, self._rs) if discrete else _Box((1,), self._rs)
+        self._discrete = discrete
+
+    def reset(self):
+        self._x, self._t = float(self._rs.uniform(-1, 1)), 0
+        return np.array([self._x, 0.0, 1.0])
+
+    def step(self, action):
+        a = (int(action) - 1) * 0.3 if self._discrete else float(np.asarray(action).reshape(-1)[0]) * 0.3
+        self._x += a + 0.05 * float(self._rs.randn())
+        self._t += 1
+        obs = np.array([self._x, self._t / 25.0, 1.0])
+        if abs(self._x) > 2:
+            return obs, -abs(self._x), True, {}
+        if self._t == 25:
+            return obs, -abs(self._x), True, {"TimeLimit.truncated": True}
+        return obs, -abs(self._x), False, {}
+
+
+@pytest.mark.parametrize("name", ["ddpg", "sac", "dqn_qr"])
+def test_fit_online_runs_the_update_path_from_the_hbm_buffer(name):
+    """`algo.fit_online(env, buffer, explorer, ...)` (algos/base.py:161-247 -> online/iterators.py:99-287): environment
+    steps into the HBM buffer, minibatches gathered on the device, one update per `update_interval` steps once the
+    buffer holds more than a batch."""
+    from d3rlpy_b200.algos import DDPG, DQN, SAC
+    from d3rlpy_b200.online import LinearDecayEpsilonGreedy, NormalNoise, ReplayBuffer
+
+    H = [32, 32]
+    if name == "ddpg":
+        algo, explorer = DDPG(actor_encoder_factory=H, critic_encoder_factory=H, batch_size=32, n_steps=2), NormalNoise()
+    elif name == "sac":
+        algo, explorer = SAC(actor_encoder_factory=H, critic_encoder_factory=H, batch_size=32), None
+    else:
+        algo = DQN(encoder_factory=H, q_func_factory="qr", batch_size=32, target_update_interval=50)
+        explorer = LinearDecayEpsilonGreedy(1.0, 0.1, 200)
+    env = _PointEnv(discrete=name == "dqn_qr")
+    buffer = ReplayBuffer(200, env=env)
+    np.random.seed(0)
+    hist = algo.fit_online(env, buffer, explorer, n_steps=400, n_steps_per_epoch=100, update_interval=2,
+                           update_start_step=40, random_steps=20)
+    assert len(hist) == 4 and len(buffer) == 200
+    # first update at the first even step > 40 with more than 32 transitions stored
+    assert algo.grad_step == (400 - 40) // 2
+    for h in hist:
+        assert "rollout_return" in h and all(np.isfinite(v) for v in h.values())
+    keys = {"ddpg": {"critic_loss", "actor_loss"}, "sac": {"critic_loss", "actor_loss", "temp", "temp_loss"},
+            "dqn_qr": {"loss"}}[name]
+    assert keys <= set(hist[-1])
