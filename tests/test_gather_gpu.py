@@ -97,3 +97,26 @@ def test_gather_empty_batch_is_noop():
     from d3rlpy_b200._lib import lib
 
     assert lib().gather_frames(None, 16, None, None, 0, 4, 1, None, None, None) == 0
+
+
+@pytest.mark.parametrize("discrete", [False, True])
+def test_gather_vector_large_ragged_batch(discrete):
+    """20 011 rows (not a multiple of the 8 rows per block), n_steps = 3, episodes of random length ending in terminals
+    or time-outs, continuous and discrete actions, vs the oracle."""
+    from d3rlpy_b200.dataset import MDPDataset, TransitionMiniBatch
+
+    rs = np.random.RandomState(11)
+    S, O, A, B = 6000, 13, 2, 20_011
+    obs = rs.randn(S, O).astype(np.float32)
+    act = rs.randint(0, 5, S).astype(np.int32) if discrete else rs.uniform(-1, 1, (S, A)).astype(np.float32)
+    rew = rs.randn(S).astype(np.float32)
+    ends = np.zeros(S, np.float32)
+    ends[np.cumsum(rs.randint(2, 40, size=400))[:-1].clip(max=S - 1)] = 1
+    ends[-1] = 1
+    term = ends * (rs.rand(S) < 0.5)
+    ds = MDPDataset(obs, act, rew, term, ends, discrete_action=discrete)
+    replay = ds.device_replay("cuda:0")
+    idx = rs.randint(len(replay), size=B)
+    batch = TransitionMiniBatch.from_indices(replay, idx, n_steps=3, gamma=0.99)
+    ref = osampler.gather(osampler.FlatReplay(obs, act, rew, term, ends), idx, 1, 3, 0.99)
+    _check(batch, ref, "large ragged batch")
