@@ -43,8 +43,11 @@ __device__ __forceinline__ float nstep_return(const float* __restrict__ rewards,
   return acc;
 }
 
-// One HALF-warp (16 lanes) per minibatch row: twice as many independent index -> metadata -> row chains in flight
-// per SM as with a warp per row (the gather is latency-bound on that dependency chain).
+// LPR lanes per minibatch row (16 = half-warp, 8 = quarter-warp): the fewer lanes per row, the more independent
+// index -> metadata -> row chains are in flight per SM (measured on 1 M random c5 rows: 31 % of the HBM peak with a warp
+// per row, 60 % with a half-warp, 72 % with a quarter-warp and 8 columns per lane; 4 or 2 lanes per row and 16 columns
+// per lane are slower again, profiles/r1_ubench.md).  Every lane keeps 2*U loads in flight per pass of LPR*U columns.
+template <int LPR, int U>
 __global__ void __launch_bounds__(128) gather_vector_kernel(
     const float* __restrict__ obs, int O, const void* __restrict__ actions, int A, int discrete,
     const float* __restrict__ rewards, const int4* __restrict__ meta, const long long* __restrict__ indices,
@@ -52,8 +55,8 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     float* __restrict__ out_rew, float* __restrict__ out_next, float* __restrict__ out_term,
     float* __restrict__ out_n, const float* __restrict__ sc_mean, const float* __restrict__ sc_std,
     float sc_eps) {
-  int lane = threadIdx.x & 15;
-  int b = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  int lane = threadIdx.x & (LPR - 1);
+  int b = blockIdx.x * (blockDim.x / LPR) + threadIdx.x / LPR;
   if (b >= B) return;
   long long t = __ldg(indices + b);
   RowInfo r = row_info(meta, t, n_steps);
@@ -64,17 +67,17 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     float* d1 = out_next + (size_t)b * O;
     // 4 x 16 columns per pass with every load issued before the first store (8 independent loads in flight per
     // lane: the row gather is latency-bound on its index -> metadata -> row dependency chain)
-    for (int j0 = 0; j0 < O; j0 += 64) {
-      float xs[4], ys[4];
+    for (int j0 = 0; j0 < O; j0 += LPR * U) {
+      float xs[U], ys[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int j = j0 + lane + 16 * u;
+      for (int u = 0; u < U; ++u) {
+        int j = j0 + lane + LPR * u;
         xs[u] = j < O ? __ldg(src + j) : 0.f;
         ys[u] = (j < O && !r.zero_next) ? __ldg(nsrc + j) : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int j = j0 + lane + 16 * u;
+      for (int u = 0; u < U; ++u) {
+        int j = j0 + lane + LPR * u;
         if (j < O) {
           float x = xs[u], y = ys[u];
           if (sc_mean) {  // StandardScaler.transform fused (preprocessing/scalers.py:350-354)
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
     if (lane == 0) ((int*)out_act)[b] = __ldg((const int*)actions + r.g);
   } else {
     const float* a = (const float*)actions + (size_t)r.g * A;
-    for (int j = lane; j < A; j += 16) ((float*)out_act)[(size_t)b * A + j] = __ldg(a + j);
+    for (int j = lane; j < A; j += LPR) ((float*)out_act)[(size_t)b * A + j] = __ldg(a + j);
   }
   if (lane == 0) {
     out_rew[b] = nstep_return(rewards, r.g, r.k, gamma);
@@ -150,10 +153,18 @@ extern "C" int d3b_gather_vector(const float* obs, int obs_dim, const void* acti
               "gather_vector: null pointer");
   D3B_REQUIRE(obs_dim == 0 || (obs && out_obs && out_next), "gather_vector: null observation pointer");
   D3B_REQUIRE((scaler_mean == nullptr) == (scaler_std == nullptr), "gather_vector: scaler mean/std must come together");
-  int rows_per_block = 8;  // 128 threads, 16 lanes per row
-  gather_vector_kernel<<<ceil_div(batch, rows_per_block), rows_per_block * 16, 0, (cudaStream_t)stream>>>(
-      obs, obs_dim, actions, act_dim, discrete, rewards, (const int4*)meta, (const long long*)indices, batch, n_steps,
-      gamma, out_obs, out_act, out_rew, out_next, out_term, out_nsteps, scaler_mean, scaler_std, scaler_eps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (batch >= 128 * kNumSM) {
+    // bandwidth regime (every SM holds many blocks): quarter-warp per row, 16 loads in flight per lane
+    gather_vector_kernel<8, 8><<<ceil_div(batch, 16), 128, 0, st>>>(
+        obs, obs_dim, actions, act_dim, discrete, rewards, (const int4*)meta, (const long long*)indices, batch, n_steps,
+        gamma, out_obs, out_act, out_rew, out_next, out_term, out_nsteps, scaler_mean, scaler_std, scaler_eps);
+  } else {
+    // latency regime (batch-256 ... batch-8192 updates): half-warp per row, fewest serial passes over a row
+    gather_vector_kernel<16, 4><<<ceil_div(batch, 8), 128, 0, st>>>(
+        obs, obs_dim, actions, act_dim, discrete, rewards, (const int4*)meta, (const long long*)indices, batch, n_steps,
+        gamma, out_obs, out_act, out_rew, out_next, out_term, out_nsteps, scaler_mean, scaler_std, scaler_eps);
+  }
   return check_launch("gather_vector");
 }
 
