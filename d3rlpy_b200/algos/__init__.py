@@ -1,7 +1,7 @@
 from .base import VectorEncoderFactory  # noqa: F401
 from .bcq import BCQ  # noqa: F401
 from .cql import CQL  # noqa: F401
-from .dqn import DQN, DiscreteCQL, DoubleDQN, PixelEncoderFactory, QRQFunctionFactory  # noqa: F401
+from .dqn import DQN, NFQ, DiscreteCQL, DoubleDQN, PixelEncoderFactory, QRQFunctionFactory  # noqa: F401
 from .td3_plus_bc import TD3PlusBC  # noqa: F401
 from .sac import SAC  # noqa: F401
 from .td3 import TD3  # noqa: F401

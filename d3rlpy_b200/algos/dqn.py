@@ -110,6 +110,21 @@ class DoubleDQN(DQN):
     IMPL = DoubleDQNImpl
 
 
+class NFQ(DQN):
+    """Neural Fitted Q Iteration (d3rlpy/algos/nfq.py:74-131): DQNImpl with the target network copied after EVERY
+    update (`_update`: `impl.update(batch)`, `impl.update_target()`), i.e. DQN's schedule with an interval of one."""
+
+    def __init__(self, **kw: Any):
+        if "target_update_interval" in kw:
+            raise TypeError("NFQ has no `target_update_interval`: the target is synchronised on every update")
+        super().__init__(target_update_interval=1, **kw)
+
+    def get_params(self, deep: bool = True):
+        params = super().get_params(deep)
+        params.pop("target_update_interval", None)
+        return params
+
+
 class DiscreteCQL(DoubleDQN):
     IMPL = DiscreteCQLImpl
 

@@ -19,7 +19,7 @@ oupdate = mg.oupdate
 
 
 def main():
-    from d3rlpy.algos import DQN, DiscreteCQL, DoubleDQN
+    from d3rlpy.algos import DQN, NFQ, DiscreteCQL, DoubleDQN
     from d3rlpy.models.encoders import PixelEncoderFactory, VectorEncoderFactory
     from d3rlpy.models.q_functions import QRQFunctionFactory
 
@@ -95,24 +95,26 @@ def main():
 
     # ---- plain DQN and DoubleDQN with the mean Q function (dqn_impl.py:97-171 without the conservative term): the
     # update.npz fixtures only hold DiscreteCQL, so the two target rules are pinned here
-    for name, cls, double, seed in (("dqn_vec", DQN, False, 10), ("ddqn_vec", DoubleDQN, True, 11)):
+    for name, cls, double, seed in (("dqn_vec", DQN, False, 10), ("ddqn_vec", DoubleDQN, True, 11),
+                                    ("nfq_vec", NFQ, False, 12)):
         O, A, B = 6, 5, 16
         o, a, r, t = mg.vector_dataset(rs, obs=O, act=A, discrete=True)
         trs = mg.ref_transitions(o, a, r, t)
         torch.manual_seed(seed)
-        algo = cls(encoder_factory=VectorEncoderFactory([32, 32]), batch_size=B, n_critics=2, n_steps=2,
-                   target_update_interval=2)
+        interval = 1 if name == "nfq_vec" else 2   # NFQ: target copied after every update (nfq.py:127-131)
+        kw = {} if name == "nfq_vec" else {"target_update_interval": interval}
+        algo = cls(encoder_factory=VectorEncoderFactory([32, 32]), batch_size=B, n_critics=2, n_steps=2, **kw)
         algo.create_impl((O,), A)
         impl = algo._impl
         init = {"q": mg.sd(impl._q_func)}
-        orc = oupdate.DiscreteCQL((O,), A, critics=init["q"], target_update_interval=2, double=double,
+        orc = oupdate.DiscreteCQL((O,), A, critics=init["q"], target_update_interval=interval, double=double,
                                   conservative=False)
         batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
         metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
         final = {"q": mg.sd(impl._q_func), "targ_q": mg.sd(impl._targ_q_func)}
         mg.assert_params_close(final["q"], orc.q, f"{name} q")
         mg.assert_params_close(final["targ_q"], orc.targ_q, f"{name} targ")
-        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, n_critics=2, interval=2,
+        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, n_critics=2, interval=interval,
                                      n_quantiles=0), init, [mg.batch_arrays(b) for b in batches], noises, metrics,
                      final)
         cases.append(name)

@@ -59,7 +59,9 @@ def test_transition_meta_matches_oracle_flat_replay():
     np.testing.assert_array_equal(ds._meta[:, 0], fr.step)
     np.testing.assert_array_equal(ds._meta[:, 1], fr.ep_start)
     np.testing.assert_array_equal(ds._meta[:, 2], fr.ep_last)
-    np.testing.assert_array_equal(ds._meta[:, 3], fr.terminal)
+    # flags: bit 0 = terminal, bit 1 = zero next observation; Episode-built data sets both together
+    np.testing.assert_array_equal(ds._meta[:, 3] & 1, fr.terminal)
+    np.testing.assert_array_equal(ds._meta[:, 3] >> 1, fr.terminal)
     eps = ds.episodes
     assert sum(len(e) for e in eps) == len(fr)
     tr = eps[0].transitions
@@ -115,13 +117,14 @@ def test_params_json_matches_reference_format():
     import os
     from types import SimpleNamespace
 
-    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, SAC, TD3, DiscreteCQL, QRQFunctionFactory, TD3PlusBC
+    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, NFQ, SAC, TD3, DiscreteCQL, QRQFunctionFactory, TD3PlusBC
 
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "params_json.json")))
     enc = [32, 32]
     cases = {
         "ddpg": (DDPG(actor_encoder_factory=enc, critic_encoder_factory=enc, use_gpu=None), (6,), 3),
         "dqn_qr": (DQN(encoder_factory=enc, q_func_factory="qr", use_gpu=None), (6,), 4),
+        "nfq": (NFQ(encoder_factory=enc, use_gpu=None), (6,), 4),
         "dcql_qr": (DiscreteCQL(encoder_factory=enc, q_func_factory=QRQFunctionFactory(n_quantiles=16), use_gpu=None),
                     (6,), 4),
         "cql": (CQL(actor_encoder_factory=enc, critic_encoder_factory=enc, n_action_samples=4, use_gpu=None), (6,), 3),

@@ -49,7 +49,7 @@ def _build(case: Case):
         return oupdate.DiscreteCQL((int(c["obs"]),), int(c["act"]), critics=g("q"), n_quantiles=int(c["n_quantiles"]),
                                    target_update_interval=int(c["interval"]), double=not plain,
                                    conservative=not plain), None
-    if n in ("dqn_vec", "ddqn_vec"):
+    if n in ("dqn_vec", "ddqn_vec", "nfq_vec"):
         return oupdate.DiscreteCQL((int(c["obs"]),), int(c["act"]), critics=g("q"), double=n == "ddqn_vec",
                                    target_update_interval=int(c["interval"]), conservative=False), None
     if n == "qr_dcql_pix":
@@ -66,10 +66,10 @@ def _build(case: Case):
 
 
 @pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3", "ddpg",
-                                  "qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix", "dqn_vec", "ddqn_vec"])
+                                  "qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix", "dqn_vec", "ddqn_vec", "nfq_vec"])
 def test_update_matches_reference_golden(name):
     torch.set_num_threads(1)
-    z = load_siblings() if name in ("sac", "td3", "ddpg") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") else load_update()
+    z = load_siblings() if name in ("sac", "td3", "ddpg") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") or name == "nfq_vec" else load_update()
     case = Case(z, name)
     algo, scaler = _build(case)
     for s in range(case.steps):

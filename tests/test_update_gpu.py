@@ -849,20 +849,21 @@ def test_qr_discrete_cql_atari_reproduction_shape_vs_oracle(precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["dqn_vec", "ddqn_vec"])
+@pytest.mark.parametrize("name", ["dqn_vec", "ddqn_vec", "nfq_vec"])
 @pytest.mark.parametrize("precision,use_graph", [("fp32", False), ("fp32", True), ("bf16", True)])
 def test_dqn_and_double_dqn_match_reference_golden(name, precision, use_graph):
     """Plain DQN (greedy action of the target network, dqn_impl.py:133-141) and DoubleDQN (online network,
     :162-171), mean Q function, two critics, n_steps = 2, hard target copy every 2 steps — vs the unmodified reference."""
-    from d3rlpy_b200.algos import DQN, DoubleDQN
+    from d3rlpy_b200.algos import DQN, NFQ, DoubleDQN
     from tests.golden_io import load_qr
 
     case = Case(load_qr(), name)
     c = case.cfg
     rel = REL if precision == "fp32" else BF16_REL
-    cls = DQN if name == "dqn_vec" else DoubleDQN
+    cls = {"dqn_vec": DQN, "ddqn_vec": DoubleDQN, "nfq_vec": NFQ}[name]
+    kw = {} if name == "nfq_vec" else {"target_update_interval": int(c["interval"])}   # NFQ: every update (nfq.py:127-131)
     algo = cls(encoder_factory=[int(c["h0"]), int(c["h1"])], batch_size=int(c["batch"]), n_critics=int(c["n_critics"]),
-               n_steps=2, target_update_interval=int(c["interval"]), precision=precision)
+               n_steps=2, precision=precision, **kw)
     algo.create_impl((int(c["obs"]),), int(c["act"]))
     impl = algo.impl
     impl.use_graph = use_graph
