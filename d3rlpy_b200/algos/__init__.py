@@ -6,3 +6,4 @@ from .td3_plus_bc import TD3PlusBC  # noqa: F401
 from .sac import SAC  # noqa: F401
 from .td3 import TD3  # noqa: F401
 from .ddpg import DDPG  # noqa: F401
+from .iql import IQL  # noqa: F401

@@ -264,8 +264,9 @@ class AlgoBase:
         package's own constructor keys (`seed`, `precision`), which the reference's `from_json` passes through
         `**kwargs` untouched."""
         assert self._impl is not None, IMPL_NOT_INITIALIZED_ERROR
-        doc: Dict[str, Any] = {"generated_maxlen": 100000, "real_ratio": 1.0, "q_func_factory":
-                               {"type": "mean", "params": {"share_encoder": False}}}
+        doc: Dict[str, Any] = {"generated_maxlen": 100000, "real_ratio": 1.0}
+        if getattr(self, "HAS_Q_FUNC_FACTORY", True):   # IQL's constructor has none (algos/iql.py:109-135)
+            doc["q_func_factory"] = {"type": "mean", "params": {"share_encoder": False}}
         for key, value in self.get_params().items():
             if key.endswith("encoder_factory"):
                 doc[key] = _encoder_to_json(value)

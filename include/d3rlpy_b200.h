@@ -293,6 +293,19 @@ int d3b_qr_loss(const float* theta, int64_t stride_theta, const float* q_tpn, co
 int d3b_qr_values(const float* theta, int64_t stride_theta, float* values, int64_t stride_values, int batch,
                   int n_actions, int n_quantiles, int members, void* stream);
 
+/* ---- IQL (sibling algorithm on the same building blocks; d3rlpy/algos/torch/iql_impl.py:109-141).
+ * iql_value_loss: expectile regression mean_b |expectile - 1[d < 0]| d^2, d = min_e Q'_e(s,a) - V(s); writes dL/dV and
+ *   the metric.
+ * iql_actor_loss: -mean_b w_b log N(a_b; tanh(mu_b), exp(logstd)) with w_b = min(exp(weight_temp (min_e Q'_e - V)),
+ *   max_weight) and logstd = min + sigmoid(param) (max - min) (policies.py:168-181,248-253); writes dL/dmu (pre-tanh),
+ *   ACCUMULATES dL/dparam into dlogstd[act_dim], writes the metric.  One block each, fixed summation order. */
+int d3b_iql_value_loss(const float* q_targ, int64_t stride_q, int members, const float* v, float expectile,
+                       float inv_batch, float* dv, float* metric, int batch, void* stream);
+int d3b_iql_actor_loss(const float* mu, int64_t ld_mu, const float* logstd_param, const float* actions, int64_t ld_act,
+                       const float* q_targ, int64_t stride_q, int members, const float* v, float weight_temp,
+                       float max_weight, float min_logstd, float max_logstd, float inv_batch, float* dmu,
+                       int64_t ld_dmu, float* dlogstd, float* metric, int batch, int act_dim, void* stream);
+
 /* ---- K9 (encoder side): Nature-DQN convolutions as patch gather + the dense-layer GEMMs above
  * (PixelEncoder.forward, d3rlpy/models/torch/encoders.py:81-162; nn.Conv2d at :100).
  * im2col: patches[e][(b,oh,ow)][(ic,kh,kw)] = x[e][b][ic][oh*s+kh][ow*s+kw] / divisor with generic element

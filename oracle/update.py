@@ -694,6 +694,93 @@ class DDPG(TD3):
             return q_continuous(self.targ_q, b.next_observations, action.clamp(-1.0, 1.0), "min")
 
 
+def make_non_squashed_normal_policy(obs: int, act: int, hidden, gen) -> Params:
+    """NonSquashedNormalPolicy with ``use_std_parameter=True`` (policies.py:127-158,274-290): the ``_logstd``
+    nn.Parameter (zeros, shape (1, A)) is registered on the module itself, so it precedes the sub-modules in
+    ``state_dict()`` / ``parameters()`` order."""
+    p: Params = OrderedDict([("_logstd", torch.zeros(1, act))])
+    p.update(make_mlp("_encoder.", obs, hidden, gen))
+    p.update(make_head("_mu", act, hidden[-1], gen))
+    return p
+
+
+def make_value_function(obs: int, hidden, gen) -> Params:
+    """ValueFunction (v_functions.py:10-21): VectorEncoder + Linear(feature, 1)."""
+    p = make_mlp("_encoder.", obs, hidden, gen)
+    p.update(make_head("_fc", 1, hidden[-1], gen))
+    return p
+
+
+def value_function(p: Params, x):
+    return F.linear(mlp_forward(p, "_encoder.", x), p["_fc.weight"], p["_fc.bias"])
+
+
+def non_squashed_policy_dist(p: Params, x, min_logstd=-5.0, max_logstd=2.0):
+    """NormalPolicy.dist with ``squash_distribution=False`` (policies.py:168-181): Normal(tanh(mu), exp(logstd)) with
+    logstd = min + sigmoid(_logstd) * (max - min) (``get_logstd_parameter``, policies.py:248-253)."""
+    mu = F.linear(mlp_forward(p, "_encoder.", x), p["_mu.weight"], p["_mu.bias"])
+    logstd = min_logstd + torch.sigmoid(p["_logstd"]) * (max_logstd - min_logstd)
+    return torch.distributions.Normal(torch.tanh(mu), logstd.exp())
+
+
+class IQL(_Algo):
+    """IQL._update (algos/iql.py:186-199) over IQLImpl (algos/torch/iql_impl.py:74-200): expectile value regression,
+    TD on V(s'), advantage-weighted Gaussian log-likelihood; ONE Adam over the critics and the value function."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99, tau=0.005,
+                 expectile=0.7, weight_temp=3.0, max_weight=100.0, seed=0, policy=None, critics=None, value=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_non_squashed_normal_policy(obs, act, hidden, gen))
+        self.v = clone_params(value if value is not None else make_value_function(obs, hidden, gen))
+        self.targ_q, self.targ_pi = clone_params(self.q, False), clone_params(self.pi, False)
+        self.critic_optim = torch.optim.Adam(list(self.q.values()) + list(self.v.values()), lr=critic_lr)
+        self.actor_optim = make_adam(self.pi, actor_lr)
+        self.gamma, self.tau = gamma, tau
+        self.expectile, self.weight_temp, self.max_weight = expectile, weight_temp, max_weight
+        self.grad_step = 0
+
+    def compute_target(self, b: Batch):
+        with torch.no_grad():
+            return value_function(self.v, b.next_observations)
+
+    def compute_critic_loss(self, b: Batch, q_tpn):
+        return td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+
+    def compute_value_loss(self, b: Batch):
+        q_t = q_continuous(self.targ_q, b.observations, b.actions, "min")
+        v_t = value_function(self.v, b.observations)
+        diff = q_t.detach() - v_t
+        weight = (self.expectile - (diff < 0.0).float()).abs().detach()
+        return (weight * (diff ** 2)).mean()
+
+    def compute_weight(self, b: Batch):
+        q_t = q_continuous(self.targ_q, b.observations, b.actions, "min")
+        v_t = value_function(self.v, b.observations)
+        return (self.weight_temp * (q_t - v_t)).exp().clamp(max=self.max_weight)
+
+    def compute_actor_loss(self, b: Batch):
+        log_probs = non_squashed_policy_dist(self.pi, b.observations).log_prob(b.actions).sum(dim=-1, keepdim=True)
+        with torch.no_grad():
+            weight = self.compute_weight(b)
+        return -(weight * log_probs).mean()
+
+    def _update(self, b, noise=None):
+        self.critic_optim.zero_grad()
+        q_loss = self.compute_critic_loss(b, self.compute_target(b))
+        v_loss = self.compute_value_loss(b)
+        (q_loss + v_loss).backward()
+        self.critic_optim.step()
+        self.actor_optim.zero_grad()
+        a_loss = self.compute_actor_loss(b)
+        a_loss.backward()
+        self.actor_optim.step()
+        soft_sync(self.targ_q, self.q, self.tau)
+        return {"critic_loss": float(q_loss.detach()), "value_loss": float(v_loss.detach()),
+                "actor_loss": float(a_loss.detach())}
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import ref_import  # noqa: E402
 
 ref_import.load()
-from d3rlpy.algos import DDPG, DQN, BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
+from d3rlpy.algos import DDPG, DQN, IQL, BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
 from d3rlpy.models.encoders import VectorEncoderFactory  # noqa: E402
 
 
@@ -36,6 +36,7 @@ cases = {
     "sac": (SAC(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
     "td3": (TD3(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
     "ddpg": (DDPG(actor_encoder_factory=enc, critic_encoder_factory=enc), (6,), 3),
+    "iql": (IQL(actor_encoder_factory=enc, critic_encoder_factory=enc, value_encoder_factory=enc), (6,), 3),
     "dqn_qr": (DQN(encoder_factory=enc, q_func_factory="qr"), (6,), 4),
 }
 out = {}

@@ -18,7 +18,7 @@ oupdate = mg.oupdate
 
 
 def main():
-    from d3rlpy.algos import DDPG, SAC, TD3
+    from d3rlpy.algos import DDPG, IQL, SAC, TD3
     from d3rlpy.models.encoders import VectorEncoderFactory
 
     out, cases = {}, []
@@ -88,6 +88,29 @@ def main():
     mg.pack_case("ddpg", out, dict(obs=O, act=A, batch=B, steps=3, h0=32, h1=32), init,
                  [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     cases.append("ddpg")
+
+    # ---- IQL: value function + expectile regression, advantage-weighted actor, one Adam over critics + value function
+    O, A, B = 6, 3, 16
+    o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+    trs = mg.ref_transitions(o, a, r, t)
+    torch.manual_seed(13)
+    enc = VectorEncoderFactory([32, 32])
+    algo = IQL(actor_encoder_factory=enc, critic_encoder_factory=enc, value_encoder_factory=enc, batch_size=B, n_steps=2,
+               weight_temp=3.0, max_weight=5.0)   # a max_weight some samples actually hit
+    algo.create_impl((O,), A)
+    impl = algo._impl
+    init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "v": mg.sd(impl._value_func)}
+    orc = oupdate.IQL(O, A, critics=init["q"], policy=init["pi"], value=init["v"], max_weight=5.0)
+    batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(3)]
+    metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+    assert all(len(n) == 0 for n in noises)
+    final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "v": mg.sd(impl._value_func),
+             "targ_q": mg.sd(impl._targ_q_func), "targ_pi": mg.sd(impl._targ_policy)}
+    for g, p in (("q", orc.q), ("pi", orc.pi), ("v", orc.v), ("targ_q", orc.targ_q), ("targ_pi", orc.targ_pi)):
+        mg.assert_params_close(final[g], p, f"iql {g}")
+    mg.pack_case("iql", out, dict(obs=O, act=A, batch=B, steps=3, h0=32, h1=32, max_weight=5.0), init,
+                 [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+    cases.append("iql")
 
     out["cases"] = np.array(cases)
     path = os.path.join(HERE, "update_siblings.npz")

@@ -117,7 +117,7 @@ def test_params_json_matches_reference_format():
     import os
     from types import SimpleNamespace
 
-    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, NFQ, SAC, TD3, DiscreteCQL, QRQFunctionFactory, TD3PlusBC
+    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, IQL, NFQ, SAC, TD3, DiscreteCQL, QRQFunctionFactory, TD3PlusBC
 
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "params_json.json")))
     enc = [32, 32]
@@ -125,6 +125,8 @@ def test_params_json_matches_reference_format():
         "ddpg": (DDPG(actor_encoder_factory=enc, critic_encoder_factory=enc, use_gpu=None), (6,), 3),
         "dqn_qr": (DQN(encoder_factory=enc, q_func_factory="qr", use_gpu=None), (6,), 4),
         "nfq": (NFQ(encoder_factory=enc, use_gpu=None), (6,), 4),
+        "iql": (IQL(actor_encoder_factory=enc, critic_encoder_factory=enc, value_encoder_factory=enc, use_gpu=None),
+                (6,), 3),
         "dcql_qr": (DiscreteCQL(encoder_factory=enc, q_func_factory=QRQFunctionFactory(n_quantiles=16), use_gpu=None),
                     (6,), 4),
         "cql": (CQL(actor_encoder_factory=enc, critic_encoder_factory=enc, n_action_samples=4, use_gpu=None), (6,), 3),

@@ -58,6 +58,9 @@ def _build(case: Case):
                                    n_quantiles=int(c["n_quantiles"])), oupdate.pixel_scaler()
     if n == "sac":
         return oupdate.SAC(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
+    if n == "iql":
+        return oupdate.IQL(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"), value=g("v"),
+                           max_weight=float(c["max_weight"])), None
     if n == "ddpg":
         return oupdate.DDPG(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
     if n == "td3":
@@ -65,11 +68,11 @@ def _build(case: Case):
     raise KeyError(n)
 
 
-@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3", "ddpg",
+@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3", "ddpg", "iql",
                                   "qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix", "dqn_vec", "ddqn_vec", "nfq_vec"])
 def test_update_matches_reference_golden(name):
     torch.set_num_threads(1)
-    z = load_siblings() if name in ("sac", "td3", "ddpg") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") or name == "nfq_vec" else load_update()
+    z = load_siblings() if name in ("sac", "td3", "ddpg", "iql") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") or name == "nfq_vec" else load_update()
     case = Case(z, name)
     algo, scaler = _build(case)
     for s in range(case.steps):
@@ -78,7 +81,7 @@ def test_update_matches_reference_golden(name):
         assert set(m) == set(ref)
         for k in ref:
             assert abs(m[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k])), (name, s, k, m[k], ref[k])
-    groups = {"q": "q", "pi": "pi", "targ_q": "targ_q", "targ_pi": "targ_pi", "imitator": "imitator",
+    groups = {"q": "q", "pi": "pi", "v": "v", "targ_q": "targ_q", "targ_pi": "targ_pi", "imitator": "imitator",
               "log_temp": "log_temp", "log_alpha": "log_alpha"}
     for grp, attr in groups.items():
         ref = case.group("final", grp)

@@ -520,7 +520,7 @@ def test_predict_api_matches_oracle():
         algo.sample_action(x)
 
 
-@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3", "ddpg", "dqn_qr"])
+@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3", "ddpg", "dqn_qr", "iql"])
 def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     """impl.save_model writes the reference's checkpoint layout (tests/golden/checkpoint_keys.json, recorded from the
     unmodified reference's save_model); load_model restores parameters, targets and optimizer state exactly
@@ -528,7 +528,7 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     import json
     import os
 
-    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, SAC, TD3, DiscreteCQL, TD3PlusBC
+    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, IQL, SAC, TD3, DiscreteCQL, TD3PlusBC
 
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "checkpoint_keys.json")))[name]
     H = [32, 32]
@@ -542,6 +542,8 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
             a = TD3(actor_encoder_factory=H, critic_encoder_factory=H)
         elif name == "ddpg":
             a = DDPG(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "iql":
+            a = IQL(actor_encoder_factory=H, critic_encoder_factory=H, value_encoder_factory=H)
         elif name == "dqn_qr":
             a = DQN(encoder_factory=H, q_func_factory="qr")
         elif name == "td3bc":
@@ -659,11 +661,12 @@ def test_save_policy_exports_what_predict_computes(tmp_path):
 @pytest.mark.parametrize("name,precision,use_graph", [("sac", "fp32", False), ("sac", "fp32", True), ("sac", "bf16", True),
                                                       ("td3", "fp32", False), ("td3", "fp32", True), ("td3", "bf16", True),
                                                       ("ddpg", "fp32", False), ("ddpg", "fp32", True),
-                                                      ("ddpg", "bf16", True)])
+                                                      ("ddpg", "bf16", True), ("iql", "fp32", False),
+                                                      ("iql", "fp32", True), ("iql", "bf16", True)])
 def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     """SAC and TD3 reuse the CQL / TD3+BC update graphs (zero importance-sampling groups; no behaviour-cloning term).
     Fixtures: tests/golden/update_siblings.npz, recorded from the unmodified reference (make_golden_siblings.py)."""
-    from d3rlpy_b200.algos import DDPG, SAC, TD3
+    from d3rlpy_b200.algos import DDPG, IQL, SAC, TD3
     from tests.golden_io import load_siblings
 
     case = Case(load_siblings(), name)
@@ -675,6 +678,9 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     elif name == "ddpg":
         algo = DDPG(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
                     n_steps=2, precision=precision)
+    elif name == "iql":
+        algo = IQL(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], value_encoder_factory=[32, 32],
+                   batch_size=int(c["batch"]), n_steps=2, max_weight=float(c["max_weight"]), precision=precision)
     else:
         algo = TD3(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
                    precision=precision)
@@ -685,14 +691,18 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     impl.targ_q_function.load_state_dict(case.group("init", "q"))
     impl.policy.load_state_dict(case.group("init", "pi"))
     impl.targ_policy.load_state_dict(case.group("init", "pi"))
+    if name == "iql":
+        impl.value_function.load_state_dict(case.group("init", "v"))
     for s in range(case.steps):
-        if name != "ddpg":  # DDPG draws no noise (the graph's own Philox draw is multiplied by sigma = 0)
+        if name not in ("ddpg", "iql"):  # DDPG and IQL draw no noise (the graph's own Philox draw is multiplied by sigma = 0)
             impl.inject_noise(case.noise(s), int(c["batch"]))
         m = algo.update(_ns(case.batch(s)))
         _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
     views = [("q", impl.q_function), ("pi", impl.policy), ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy)]
     if name == "sac":
         views.append(("log_temp", impl._log_temp))
+    if name == "iql":
+        views.append(("v", impl.value_function))
     for grp, view in views:
         _assert_params(view.state_dict(), case.group("final", grp), grp, rel=rel)
     assert algo.grad_step == case.steps
