@@ -9,6 +9,7 @@ from .torch.td3_plus_bc_impl import TD3PlusBCImpl
 
 class TD3PlusBC(AlgoBase):
     IMPL = TD3PlusBCImpl
+    SUPPORTS_QR = True
 
     def __init__(self, *, actor_learning_rate: float = 3e-4, critic_learning_rate: float = 3e-4,
                  actor_optim_factory=None, critic_optim_factory=None, actor_encoder_factory="default",
@@ -22,8 +23,9 @@ class TD3PlusBC(AlgoBase):
 
             scaler = StandardScaler()
         super().__init__(batch_size, n_frames, n_steps, gamma, scaler, action_scaler, reward_scaler, use_gpu, kwargs)
-        if q_func_factory != "mean":
-            raise ValueError("only the mean Q function is on the accelerated path")
+        from .dqn import _n_quantiles_of
+
+        self._n_quantiles = _n_quantiles_of(q_func_factory)   # "mean", "qr" or QRQFunctionFactory(n_quantiles <= 32)
         if actor_optim_factory is not None or critic_optim_factory is not None:
             raise ValueError("only AdamFactory() defaults are on the accelerated path")
         self._actor_learning_rate, self._critic_learning_rate = actor_learning_rate, critic_learning_rate
@@ -33,7 +35,8 @@ class TD3PlusBC(AlgoBase):
         self._target_smoothing_sigma, self._target_smoothing_clip = target_smoothing_sigma, target_smoothing_clip
         self._alpha, self._update_actor_interval = alpha, update_actor_interval
         self._impl, self._seed = impl, seed
-        self._factories = {"actor_encoder_factory": actor_encoder_factory, "critic_encoder_factory": critic_encoder_factory}
+        self._factories = {"actor_encoder_factory": actor_encoder_factory,
+                           "critic_encoder_factory": critic_encoder_factory, "q_func_factory": q_func_factory}
 
     def _create_impl(self, observation_shape, action_size) -> None:
         self._impl = self.IMPL(
@@ -43,7 +46,7 @@ class TD3PlusBC(AlgoBase):
             n_critics=self._n_critics, target_smoothing_sigma=self._target_smoothing_sigma,
             target_smoothing_clip=self._target_smoothing_clip, alpha=self._alpha, use_gpu=self._use_gpu,
             scaler=self._scaler, action_scaler=self._action_scaler, reward_scaler=self._reward_scaler,
-            seed=self._seed, **self._kwargs)
+            seed=self._seed, n_quantiles=self._n_quantiles, **self._kwargs)
         self._impl.build()
 
     def _update(self, batch) -> Dict[str, float]:

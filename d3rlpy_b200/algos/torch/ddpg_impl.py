@@ -80,9 +80,17 @@ def _net_optim(net: DenseNet, lr: float) -> _OptimView:
 class DDPGBaseImpl(ImplBase):
     def __init__(self, observation_shape, action_size, actor_learning_rate, critic_learning_rate,
                  actor_hidden: Sequence[int], critic_hidden: Sequence[int], gamma, tau, n_critics, use_gpu=0,
-                 scaler=None, action_scaler=None, reward_scaler=None, seed: int = 0, precision: str = "fp32", **kw):
+                 scaler=None, action_scaler=None, reward_scaler=None, seed: int = 0, precision: str = "fp32",
+                 n_quantiles: int = 0, **kw):
         super().__init__(observation_shape, action_size, use_gpu, scaler, action_scaler, reward_scaler, **kw)
         self._precision = precision
+        # > 0: every critic is a ContinuousQRQFunction (qr_q_function.py:91-165) — head Linear(feature, n_quantiles),
+        # Q = mean over the quantiles; only the impls that set SUPPORTS_QR consume it
+        self._n_quantiles = int(n_quantiles or 0)
+        if self._n_quantiles and not getattr(self, "SUPPORTS_QR", False):
+            raise ValueError(f"{type(self).__name__}: quantile-regression critics are not on the accelerated path")
+        if self._n_quantiles > 32:
+            raise ValueError("continuous quantile-regression critics support up to 32 quantiles (narrow-head kernels)")
         assert len(self._observation_shape) == 1, "vector observations only for actor-critic impls"
         self._actor_learning_rate, self._critic_learning_rate = actor_learning_rate, critic_learning_rate
         self._actor_hidden, self._critic_hidden = list(actor_hidden), list(critic_hidden)
@@ -95,7 +103,8 @@ class DDPGBaseImpl(ImplBase):
     # ------------------------------------------------------------------ build
     def build(self) -> None:
         O, A = self._observation_shape[0], self._action_size
-        self._q_func = DenseNet(O + A, self._critic_hidden, [("_fc", 1)], self._n_critics, self._device,
+        self._q_func = DenseNet(O + A, self._critic_hidden, [("_fc", max(1, self._n_quantiles))], self._n_critics,
+                                self._device,
                                 trunk_prefix="_encoder.", member_key="_q_funcs.{e}.{name}", with_target=True,
                                 seed_gen=self._gen, precision=self._precision)
         self._build_actor()
@@ -144,10 +153,11 @@ class DDPGBaseImpl(ImplBase):
 
     # ------------------------------------------------------------------ shared program pieces
     def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0, train=True):
-        """Runs the critic trunk+head on `rows` shared input rows; returns (ctx, q[E,rows])."""
+        """Runs the critic trunk+head on `rows` shared input rows; returns (ctx, q[E,rows]) — (ctx, theta[E,rows,n])
+        for quantile-regression critics."""
         E = members or self._n_critics
         ctx = self._q_func.ctx(tag, rows, E, train)
-        q = self.ws(f"{tag}_q", E, rows)
+        q = self.ws(f"{tag}_q", E, rows, self._n_quantiles) if self._n_quantiles else self.ws(f"{tag}_q", E, rows)
         self._q_func.forward(which, x, self._q_func.in_dim, rows, ctx, q, self._stream, member0=member0)
         return ctx, q
 
@@ -215,5 +225,7 @@ class DDPGBaseImpl(ImplBase):
         _, q = self._critic_rows_forward("params", rows, n, "eval_q", train=False)
         self.sync()
         values = q.detach().cpu().numpy()                     # [E, n]
+        if self._n_quantiles:
+            values = values.mean(axis=2)                      # ContinuousQRQFunction.forward: mean over quantiles
         mean, std = values.mean(axis=0), values.std(axis=0)
         return (mean, std) if with_std else mean

@@ -14,6 +14,7 @@ S_TD, S_ACT = 0, 4  # sums slots: TD uses [0..2], actor stats [4..6]
 
 class TD3PlusBCImpl(DDPGBaseImpl):
     POLICY_KIND = "deterministic"
+    SUPPORTS_QR = True         # ContinuousQRQFunction critics: csrc/qr.cu kernels with a single pseudo-action
     BEHAVIOUR_CLONING = True   # TD3Impl below: plain TD3 actor loss -Q_0(s, pi(s)).mean()
 
     def __init__(self, *, target_smoothing_sigma=0.2, target_smoothing_clip=0.5, alpha=2.5, **kw):
@@ -64,8 +65,22 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         xc = self.ws("xc", B, O + A)
         L.concat_rows(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, xc.data_ptr(), O + A, B, 1, O, A, st)
         acts, q = self._critic_rows_forward("params", xc, B, "cq")
-        dq = self.ws("dq", E, B)
         inv_b = 1.0 / (B * self.world_size)
+        nq = self._n_quantiles
+        if nq:
+            # quantile Huber against the quantile vector of the target member with the smallest mean
+            # (ContinuousQRQFunction.compute_error / compute_target, ensemble_q_function.py:47-52,177-184)
+            if q_tpn is None:
+                q_tpn = self.ws("qr_tpn", B, nq)
+                L.qr_target(q_t.data_ptr(), B * nq, q_t.data_ptr(), B * nq, q_tpn.data_ptr(), B, 1, nq, E, st)
+            dq = self.ws("dq", E, B, nq)
+            L.qr_loss(q.data_ptr(), B * nq, q_tpn.data_ptr(), self.ws("qr_action0", B).data_ptr(), db.ptr("rew"),
+                      db.ptr("term"), db.ptr("nsteps"), self._gamma, 0.0, dq.data_ptr(), B * nq,
+                      self.ws("qr_partials", 2 * B).data_ptr(), self.sums_ptr(S_TD), B, 1, nq, E, inv_b, 0, st)
+            self._allreduce(self._slots[32 + S_TD:32 + S_TD + 3])
+            L.dcql_finalize(self.sums_ptr(S_TD), inv_b, 0.0, 0, self.metric_ptr(M_CRITIC), st)
+            return xc, acts, dq
+        dq = self.ws("dq", E, B)
         L.critic_loss(q.data_ptr(), B, q_t.data_ptr() if q_t is not None else None, B, E,
                       q_tpn.data_ptr() if q_tpn is not None else None, db.ptr("rew"), db.ptr("term"),
                       db.ptr("nsteps"), self._gamma, None, None, 0, A, None, 0.0, dq.data_ptr(), B,
@@ -90,8 +105,15 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         L.concat_rows(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa.data_ptr(), O + A, B, 1, O, A, st)
         acts_c, q0 = self._critic_rows_forward("params", xa, B, "aq", members=1)
         inv_b = 1.0 / (B * self.world_size)
+        nq = self._n_quantiles
+        if nq:   # Q_0 = mean of the quantiles (qr_q_function.py:118-122)
+            theta0, q0 = q0, self.ws("aq_values", 1, B)
+            L.qr_values(theta0.data_ptr(), B * nq, q0.data_ptr(), B, B, 1, nq, 1, st)
         dq = self.ws("a_dq", 1, B)
         bc_w = self._actor_seed(q0, a, db, dq, B, A, inv_b)
+        if nq:
+            dq, dvalues = self.ws("a_dtheta", 1, B, nq), dq
+            L.qr_values_backward(dvalues.data_ptr(), dq.data_ptr(), B, nq, st)
         dxa = self.ws("a_dx", B, A)
         self._q_func.backward(xa, O + A, B, acts_c, dq, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A,
                               dx_col0=O, dx_cols=A)
@@ -191,7 +213,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
                 self._p_actor(db)
 
         fused = (self._precision == "bf16" and self.world_size == 1 and self._q_func.fused_ok
-                 and self._policy.fused_ok and self.fused_glue)
+                 and self._policy.fused_ok and self.fused_glue and not self._n_quantiles)
         self.run_program(("td3bc", db.B, actor_step, self._noise_injected, fused),
                          (lambda: self._program_fused(db, actor_step)) if fused else program)
         return [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
@@ -201,6 +223,13 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         db = self.load_batch(batch)
         self.fill_noise(db.B)
         q_t = self._p_target(db)
+        nq = self._n_quantiles
+        if nq:   # (B, n_quantiles) of the member with the smallest mean (ensemble_q_function.py:47-52)
+            q_tpn = self.ws("qr_tpn", db.B, nq)
+            self._lib.qr_target(q_t.data_ptr(), db.B * nq, q_t.data_ptr(), db.B * nq, q_tpn.data_ptr(), db.B, 1, nq,
+                                self._n_critics, self._stream)
+            self.sync()
+            return q_tpn.clone()
         self.sync()
         return q_t.min(dim=0).values.view(-1, 1).clone()
 

@@ -164,6 +164,13 @@ __global__ void __launch_bounds__(256) qr_values_kernel(const float* __restrict_
   if (lane == 0) values[(long long)e * sV + ba] = s / (float)n;
 }
 
+// d(theta)[v][i] = d(values)[v] / n: backward of `quantiles.mean(dim=-1)` (qr_q_function.py:44-48,118-122).
+__global__ void __launch_bounds__(256) qr_values_backward_kernel(const float* __restrict__ dvalues,
+                                                                 float* __restrict__ dtheta, long long total, int n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) dtheta[i] = __ldg(dvalues + i / n) / (float)n;
+}
+
 }  // namespace d3b
 
 using namespace d3b;
@@ -210,4 +217,14 @@ extern "C" int d3b_qr_values(const float* theta, int64_t stride_theta, float* va
   qr_values_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(theta, stride_theta, values, stride_values, batch,
                                                                     n_actions, n_quantiles, members);
   return check_launch("qr_values");
+}
+
+extern "C" int d3b_qr_values_backward(const float* dvalues, float* dtheta, int64_t n_values, int n_quantiles,
+                                      void* stream) {
+  D3B_REQUIRE(n_values >= 0 && n_quantiles >= 1, "qr_values_backward: bad sizes");
+  if (n_values == 0) return D3B_OK;
+  D3B_REQUIRE(dvalues && dtheta, "qr_values_backward: null pointer");
+  long long total = (long long)n_values * n_quantiles;
+  qr_values_backward_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, ST>>>(dvalues, dtheta, total, n_quantiles);
+  return check_launch("qr_values_backward");
 }

@@ -292,6 +292,10 @@ int d3b_qr_loss(const float* theta, int64_t stride_theta, const float* q_tpn, co
                 int n_quantiles, int members, float inv_batch, int conservative, void* stream);
 int d3b_qr_values(const float* theta, int64_t stride_theta, float* values, int64_t stride_values, int batch,
                   int n_actions, int n_quantiles, int members, void* stream);
+/* backward of qr_values: dtheta[v][i] = dvalues[v] / n_quantiles (the actor losses differentiate through the mean of a
+ * ContinuousQRQFunction's quantiles, qr_q_function.py:118-122).  The continuous QR critics reuse qr_target / qr_loss /
+ * qr_values with n_actions = 1 (ContinuousQRQFunction, qr_q_function.py:91-165). */
+int d3b_qr_values_backward(const float* dvalues, float* dtheta, int64_t n_values, int n_quantiles, void* stream);
 
 /* ---- IQL (sibling algorithm on the same building blocks; d3rlpy/algos/torch/iql_impl.py:109-141).
  * iql_value_loss: expectile regression mean_b |expectile - 1[d < 0]| d^2, d = min_e Q'_e(s,a) - V(s); writes dL/dV and

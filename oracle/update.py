@@ -80,12 +80,13 @@ def make_head(prefix: str, out_f: int, in_f: int, gen) -> Params:
     return OrderedDict([(f"{prefix}.weight", w), (f"{prefix}.bias", b)])
 
 
-def make_critics(obs: int, act: int, hidden, n: int, gen) -> Params:
-    """EnsembleContinuousQFunction of ContinuousMeanQFunction (builders.py:55-77)."""
+def make_critics(obs: int, act: int, hidden, n: int, gen, n_quantiles: Optional[int] = None) -> Params:
+    """EnsembleContinuousQFunction of ContinuousMeanQFunction (builders.py:55-77); with ``n_quantiles`` of
+    ContinuousQRQFunction (qr_q_function.py:101-110: head ``Linear(feature, n_quantiles)``)."""
     p: Params = OrderedDict()
     for i in range(n):
         p.update(make_mlp(f"_q_funcs.{i}._encoder.", obs + act, hidden, gen))
-        p.update(make_head(f"_q_funcs.{i}._fc", 1, hidden[-1], gen))
+        p.update(make_head(f"_q_funcs.{i}._fc", n_quantiles or 1, hidden[-1], gen))
     return p
 
 
@@ -209,13 +210,29 @@ def q_continuous(p: Params, x, action, reduction="mean", lam=0.75) -> torch.Tens
     """EnsembleContinuousQFunction.forward (ensemble_q_function.py:163-170) over
     ContinuousMeanQFunction.forward (mean_q_function.py:71-72) and
     VectorEncoderWithAction.forward (encoders.py:328-339)."""
+    vals = quantiles_continuous(p, x, action).mean(dim=2, keepdim=True)  # QR: mean over quantiles (:118-122)
+    return reduce_ensemble(vals, reduction, lam)
+
+
+def quantiles_continuous(p: Params, x, action) -> torch.Tensor:
+    """Head outputs of every member, (E, B, n): n = 1 for ContinuousMeanQFunction, n_quantiles for
+    ContinuousQRQFunction._compute_quantiles (qr_q_function.py:112-116)."""
     xa = torch.cat([x, action], dim=1)
     vals = []
     for i in range(n_members(p)):
         h = mlp_forward(p, f"_q_funcs.{i}._encoder.", xa)
         q = F.linear(h, p[f"_q_funcs.{i}._fc.weight"], p[f"_q_funcs.{i}._fc.bias"])
-        vals.append(q.view(1, x.shape[0], 1))
-    return reduce_ensemble(torch.cat(vals, dim=0), reduction, lam)
+        vals.append(q.view(1, x.shape[0], -1))
+    return torch.cat(vals, dim=0)
+
+
+def q_target_continuous(p: Params, x, action) -> torch.Tensor:
+    """EnsembleContinuousQFunction.compute_target(x, action, "min") (ensemble_q_function.py:108-134,177-184):
+    (B, 1) minimum over members, or for QR members the (B, n_quantiles) vector of the member with the smallest mean."""
+    th = quantiles_continuous(p, x, action)
+    if th.shape[2] == 1:
+        return reduce_ensemble(th, "min")
+    return reduce_quantile_ensemble_min(th)
 
 
 def q_discrete(p: Params, x, reduction="mean", n_quantiles: Optional[int] = None) -> torch.Tensor:
@@ -288,10 +305,16 @@ def td_error_continuous(p: Params, obs, act, rew, target, term, gamma) -> torch.
     per-member batch-mean MSE (mean_q_function.py:74-87)."""
     assert target.ndim == 2
     total = torch.tensor(0.0)
-    q = q_continuous(p, obs, act, "none")
+    th = quantiles_continuous(p, obs, act)
+    if th.shape[2] > 1:  # ContinuousQRQFunction.compute_error (qr_q_function.py:124-148)
+        assert target.shape == (obs.shape[0], th.shape[2])
+        taus = make_taus(th.shape[2])
+        for i in range(th.shape[0]):
+            total = total + quantile_huber_loss(th[i], rew, target, term, taus, gamma).view(-1, 1).mean()
+        return total
     y = rew + gamma * target * (1 - term)
-    for i in range(q.shape[0]):
-        total = total + F.mse_loss(q[i], y, reduction="none").mean()
+    for i in range(th.shape[0]):
+        total = total + F.mse_loss(th[i], y, reduction="none").mean()
     return total
 
 
@@ -479,7 +502,7 @@ class TD3PlusBC(_Algo):
             n = noise.normal(*action.shape)
             clipped_noise = (self.sigma * n).clamp(-self.clip, self.clip)
             a = (action + clipped_noise).clamp(-1.0, 1.0)
-            return q_continuous(self.targ_q, b.next_observations, a, "min")
+            return q_target_continuous(self.targ_q, b.next_observations, a)
 
     def compute_critic_loss(self, b: Batch, q_tpn):
         """DDPGBaseImpl.compute_critic_loss (algos/torch/ddpg_impl.py:154-165)."""
@@ -691,7 +714,7 @@ class DDPG(TD3):
         """DDPGImpl.compute_target (algos/torch/ddpg_impl.py:275-284)."""
         with torch.no_grad():
             action = deterministic_policy(self.targ_pi, b.next_observations)
-            return q_continuous(self.targ_q, b.next_observations, action.clamp(-1.0, 1.0), "min")
+            return q_target_continuous(self.targ_q, b.next_observations, action.clamp(-1.0, 1.0))
 
 
 def make_non_squashed_normal_policy(obs: int, act: int, hidden, gen) -> Params:

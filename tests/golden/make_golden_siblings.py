@@ -18,7 +18,7 @@ oupdate = mg.oupdate
 
 
 def main():
-    from d3rlpy.algos import DDPG, IQL, SAC, TD3
+    from d3rlpy.algos import DDPG, IQL, SAC, TD3, TD3PlusBC
     from d3rlpy.models.encoders import VectorEncoderFactory
 
     out, cases = {}, []
@@ -111,6 +111,36 @@ def main():
     mg.pack_case("iql", out, dict(obs=O, act=A, batch=B, steps=3, h0=32, h1=32, max_weight=5.0), init,
                  [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     cases.append("iql")
+
+    # ---- quantile-regression critics on the TD3 family (ContinuousQRQFunction, qr_q_function.py:91-165)
+    from d3rlpy.models.q_functions import QRQFunctionFactory
+
+    for name, cls, kw, okw in (
+            ("td3bc_qr", TD3PlusBC, dict(q_func_factory=QRQFunctionFactory(n_quantiles=8), scaler=None, n_steps=2),
+             dict(cls=oupdate.TD3PlusBC, nq=8)),
+            ("ddpg_qr", DDPG, dict(q_func_factory="qr", n_critics=2), dict(cls=oupdate.DDPG, nq=32))):
+        O, A, B = 6, 3, 16
+        o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+        trs = mg.ref_transitions(o, a, r, t)
+        torch.manual_seed(14 if name == "td3bc_qr" else 15)
+        enc = VectorEncoderFactory([32, 32])
+        algo = cls(actor_encoder_factory=enc, critic_encoder_factory=enc, batch_size=B, **kw)
+        algo.create_impl((O,), A)
+        impl = algo._impl
+        init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy)}
+        assert init["q"]["_q_funcs.0._fc.weight"].shape[0] == okw["nq"]
+        orc = okw["cls"](O, A, critics=init["q"], policy=init["pi"], hidden=(32, 32), n_critics=2)
+        n_steps = kw.get("n_steps", 1)
+        batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=n_steps) for _ in range(4)]
+        metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+        final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "targ_q": mg.sd(impl._targ_q_func),
+                 "targ_pi": mg.sd(impl._targ_policy)}
+        for g, p in (("q", orc.q), ("pi", orc.pi), ("targ_q", orc.targ_q), ("targ_pi", orc.targ_pi)):
+            mg.assert_params_close(final[g], p, f"{name} {g}")
+        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=4, h0=32, h1=32, n_quantiles=okw["nq"],
+                                     n_steps=n_steps), init, [mg.batch_arrays(b) for b in batches], noises, metrics,
+                     final)
+        cases.append(name)
 
     out["cases"] = np.array(cases)
     path = os.path.join(HERE, "update_siblings.npz")

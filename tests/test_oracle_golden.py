@@ -61,6 +61,10 @@ def _build(case: Case):
     if n == "iql":
         return oupdate.IQL(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"), value=g("v"),
                            max_weight=float(c["max_weight"])), None
+    if n == "td3bc_qr":   # critics carry 8-quantile heads: the oracle switches on the head width
+        return oupdate.TD3PlusBC(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
+    if n == "ddpg_qr":
+        return oupdate.DDPG(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi"), n_critics=2), None
     if n == "ddpg":
         return oupdate.DDPG(int(c["obs"]), int(c["act"]), critics=g("q"), policy=g("pi")), None
     if n == "td3":
@@ -68,11 +72,11 @@ def _build(case: Case):
     raise KeyError(n)
 
 
-@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3", "ddpg", "iql",
+@pytest.mark.parametrize("name", ["td3bc", "cql", "cql_softq", "bcq", "dcql_vec", "dcql_pix", "sac", "td3", "ddpg", "iql", "td3bc_qr", "ddpg_qr",
                                   "qr_dcql_vec", "qr_dqn_vec", "qr_dcql_pix", "dqn_vec", "ddqn_vec", "nfq_vec"])
 def test_update_matches_reference_golden(name):
     torch.set_num_threads(1)
-    z = load_siblings() if name in ("sac", "td3", "ddpg", "iql") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") or name == "nfq_vec" else load_update()
+    z = load_siblings() if name in ("sac", "td3", "ddpg", "iql", "td3bc_qr", "ddpg_qr") else load_qr() if name.startswith("qr_") or name.endswith("dqn_vec") or name == "nfq_vec" else load_update()
     case = Case(z, name)
     algo, scaler = _build(case)
     for s in range(case.steps):

@@ -662,11 +662,14 @@ def test_save_policy_exports_what_predict_computes(tmp_path):
                                                       ("td3", "fp32", False), ("td3", "fp32", True), ("td3", "bf16", True),
                                                       ("ddpg", "fp32", False), ("ddpg", "fp32", True),
                                                       ("ddpg", "bf16", True), ("iql", "fp32", False),
-                                                      ("iql", "fp32", True), ("iql", "bf16", True)])
+                                                      ("iql", "fp32", True), ("iql", "bf16", True),
+                                                      ("td3bc_qr", "fp32", False), ("td3bc_qr", "fp32", True),
+                                                      ("td3bc_qr", "bf16", True), ("ddpg_qr", "fp32", False),
+                                                      ("ddpg_qr", "fp32", True), ("ddpg_qr", "bf16", True)])
 def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     """SAC and TD3 reuse the CQL / TD3+BC update graphs (zero importance-sampling groups; no behaviour-cloning term).
     Fixtures: tests/golden/update_siblings.npz, recorded from the unmodified reference (make_golden_siblings.py)."""
-    from d3rlpy_b200.algos import DDPG, IQL, SAC, TD3
+    from d3rlpy_b200.algos import DDPG, IQL, SAC, TD3, QRQFunctionFactory, TD3PlusBC
     from tests.golden_io import load_siblings
 
     case = Case(load_siblings(), name)
@@ -678,6 +681,13 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     elif name == "ddpg":
         algo = DDPG(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
                     n_steps=2, precision=precision)
+    elif name == "td3bc_qr":   # quantile-regression critics (ContinuousQRQFunction) on the TD3+BC program
+        algo = TD3PlusBC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
+                         q_func_factory=QRQFunctionFactory(n_quantiles=int(c["n_quantiles"])), scaler=None, n_steps=2,
+                         precision=precision)
+    elif name == "ddpg_qr":
+        algo = DDPG(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=int(c["batch"]),
+                    q_func_factory="qr", n_critics=2, precision=precision)
     elif name == "iql":
         algo = IQL(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], value_encoder_factory=[32, 32],
                    batch_size=int(c["batch"]), n_steps=2, max_weight=float(c["max_weight"]), precision=precision)
@@ -694,7 +704,7 @@ def test_sibling_algorithms_match_reference_golden(name, precision, use_graph):
     if name == "iql":
         impl.value_function.load_state_dict(case.group("init", "v"))
     for s in range(case.steps):
-        if name not in ("ddpg", "iql"):  # DDPG and IQL draw no noise (the graph's own Philox draw is multiplied by sigma = 0)
+        if name not in ("ddpg", "iql", "ddpg_qr"):  # DDPG and IQL draw no noise (the graph's own Philox draw is multiplied by sigma = 0)
             impl.inject_noise(case.noise(s), int(c["batch"]))
         m = algo.update(_ns(case.batch(s)))
         _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
