@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) gather_vector_kernel(
 
 // One CTA per (row, obs|next, frame slot): copies one c*h*w uint8 frame with 16-byte vectors.
 template <bool VEC16>
-__global__ void __launch_bounds__(256) gather_frames_kernel(
+__global__ void __launch_bounds__(128) gather_frames_kernel(
     const uint8_t* __restrict__ frames, int frame_bytes, const int4* __restrict__ meta,
     const long long* __restrict__ indices, int B, int n_frames, int n_steps, uint8_t* __restrict__ out_obs,
     uint8_t* __restrict__ out_next) {
@@ -128,9 +128,20 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(
     int nv = frame_bytes >> 4;
     const uint4* s4 = (const uint4*)src;
     uint4* d4 = (uint4*)dst;
-    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-      uint4 v = zero ? make_uint4(0, 0, 0, 0) : __ldg(s4 + i);
-      d4[i] = v;
+    // 4 independent 16-byte loads in flight per thread before the first store (an 84x84 frame = 441 vectors is one
+    // pass of a 128-thread CTA); 16 such CTAs are resident per SM
+    for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * blockDim.x) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int i = i0 + u * blockDim.x;
+        v[u] = (i < nv && !zero) ? __ldg(s4 + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int i = i0 + u * blockDim.x;
+        if (i < nv) d4[i] = v[u];
+      }
     }
   } else {
     for (int i = threadIdx.x; i < frame_bytes; i += blockDim.x) dst[i] = zero ? 0 : __ldg(src + i);
@@ -178,11 +189,11 @@ extern "C" int d3b_gather_frames(const uint8_t* frames, int frame_bytes, const v
              ((uintptr_t)out_next % 16 == 0);
   int grid = batch * 2 * n_frames;
   if (vec)
-    gather_frames_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, frame_bytes, (const int4*)meta,
+    gather_frames_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(frames, frame_bytes, (const int4*)meta,
                                                                        (const long long*)indices, batch, n_frames,
                                                                        n_steps, out_obs, out_next);
   else
-    gather_frames_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(frames, frame_bytes, (const int4*)meta,
+    gather_frames_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(frames, frame_bytes, (const int4*)meta,
                                                                         (const long long*)indices, batch, n_frames,
                                                                         n_steps, out_obs, out_next);
   return check_launch("gather_frames");
