@@ -100,35 +100,38 @@ def _encoder_from_json(doc):
     raise ValueError(f"unsupported encoder type {kind!r}")
 
 
+def _jsonable(v):
+    """default_json_encoder (d3rlpy/logger.py:21-28): numpy scalars and arrays as python numbers / nested lists."""
+    if isinstance(v, np.ndarray):
+        return v.tolist()
+    if isinstance(v, np.integer):
+        return int(v)
+    if isinstance(v, np.floating):
+        return float(v)
+    return v
+
+
 def _scaler_to_json(scaler):
+    """_serialize_params (base.py:78-98): {"type": get_type(), "params": get_params()}."""
     if scaler is None:
         return None
-    if isinstance(scaler, str):  # create_scaler(name) with default arguments (preprocessing/scalers.py:369-383)
-        if scaler == "pixel":
-            return {"type": "pixel", "params": {}}
-        if scaler == "standard":
-            return {"type": "standard", "params": {"mean": None, "std": None, "eps": 1e-3}}
-        raise ValueError(f"unsupported scaler {scaler!r}")
     kind = getattr(scaler, "TYPE", None)
-    if kind == "pixel":
-        return {"type": "pixel", "params": {}}
-    if kind == "standard":  # StandardScaler.get_params (preprocessing/scalers.py:356-366)
-        mean = None if scaler._mean is None else np.asarray(scaler._mean).tolist()
-        std = None if scaler._std is None else np.asarray(scaler._std).tolist()
-        return {"type": "standard", "params": {"mean": mean, "std": std, "eps": scaler._eps}}
-    raise ValueError(f"unsupported scaler {scaler!r}")
+    if kind is None or not hasattr(scaler, "get_params"):
+        raise ValueError(f"unsupported scaler {scaler!r}")
+    return {"type": kind, "params": {k: _jsonable(v) for k, v in scaler.get_params().items()}}
 
 
-def _scaler_from_json(doc):
+def _scaler_from_json(doc, create=None):
+    """_deseriealize_params (base.py:101-117): create_scaler / create_action_scaler / create_reward_scaler."""
     if doc is None or not isinstance(doc, dict):
         return doc
-    from ..preprocessing import PixelScaler, StandardScaler
+    from .. import preprocessing
 
-    if doc["type"] == "pixel":
-        return PixelScaler()
-    if doc["type"] == "standard":
-        return StandardScaler(**doc.get("params", {}))
-    raise ValueError(f"scaler {doc['type']!r} is not on the accelerated path")
+    create = create or preprocessing.create_scaler
+    try:
+        return create(doc["type"], **doc.get("params", {}))
+    except AssertionError:
+        raise ValueError(f"scaler {doc['type']!r} is not on the accelerated path") from None
 
 
 def random_iterator_indices(rng, n_transitions: int, n_steps: int, batch_size: int) -> np.ndarray:
@@ -152,12 +155,15 @@ class AlgoBase:
     def __init__(self, batch_size: int, n_frames: int, n_steps: int, gamma: float, scaler=None, action_scaler=None,
                  reward_scaler=None, use_gpu=0, kwargs: Optional[Dict[str, Any]] = None):
         self._batch_size, self._n_frames, self._n_steps, self._gamma = batch_size, n_frames, n_steps, gamma
-        self._scaler, self._action_scaler, self._reward_scaler = scaler, action_scaler, reward_scaler
+        from ..preprocessing import check_action_scaler, check_reward_scaler, check_scaler
+
+        # check_scaler / check_action_scaler / check_reward_scaler (base.py:166-168): instance, registered name or None
+        self._scaler = check_scaler(scaler)
+        self._action_scaler = check_action_scaler(action_scaler)
+        self._reward_scaler = check_reward_scaler(reward_scaler)
         self._use_gpu = use_gpu
         self._grad_step = 0
         self._kwargs = kwargs or {}
-        if action_scaler is not None or reward_scaler is not None:
-            raise ValueError("action/reward scalers are not on the accelerated path yet")
 
     # ------------------------------------------------------------------ reference API
     @property
@@ -222,6 +228,10 @@ class AlgoBase:
     @property
     def action_scaler(self):
         return self._action_scaler
+
+    @property
+    def reward_scaler(self):
+        return self._reward_scaler
 
     def fit_online(self, env, buffer=None, explorer=None, n_steps: int = 1000000, n_steps_per_epoch: int = 10000,
                    update_interval: int = 1, update_start_step: int = 0, random_steps: int = 0,
@@ -327,6 +337,14 @@ class AlgoBase:
                 params[key] = _q_func_from_json(value, cls)
             elif key == "scaler":
                 params[key] = _scaler_from_json(value)
+            elif key == "action_scaler":
+                from ..preprocessing import create_action_scaler
+
+                params[key] = _scaler_from_json(value, create_action_scaler)
+            elif key == "reward_scaler":
+                from ..preprocessing import create_reward_scaler
+
+                params[key] = _scaler_from_json(value, create_reward_scaler)
         params["use_gpu"] = use_gpu
         params.update(overrides)
         algo = cls(**params)
@@ -369,8 +387,9 @@ class AlgoBase:
         dropped, iterators/round_iterator.py:39-55) -> device gather -> update.  Returns the per-epoch metric means."""
         if (n_epochs is None) == (n_steps is None):
             raise ValueError("Either of n_epochs or n_steps must be given.")  # base.py:548-549
-        if self._scaler is not None and hasattr(self._scaler, "fit_dataset"):
-            self._scaler.fit_dataset(dataset)
+        for sc in (self._scaler, self._action_scaler, self._reward_scaler):   # base.py:566-585
+            if sc is not None:
+                sc.fit(dataset)
         self.build_with_dataset(dataset)
         replay = dataset.device_replay(self._impl._device)
         rng = np.random if seed is None else np.random.RandomState(seed)
@@ -398,6 +417,8 @@ class AlgoBase:
                 batch = TransitionMiniBatch.from_indices(replay, idx[i], n_frames=self._n_frames,
                                                          n_steps=self._n_steps, gamma=self._gamma,
                                                          scaler=self._scaler, out=impl.device_batch(B))
+                impl.scale_actions_rewards(batch._device_batch)
+                batch.scaled = {"obs", "act_rew"}
                 for k, v in self.update(batch).items():
                     acc.setdefault(k, []).append(float(v))
         return {k: float(np.mean(v)) for k, v in acc.items()}
@@ -415,9 +436,9 @@ class AlgoBase:
         idx_dev = torch.from_numpy(np.ascontiguousarray(idx)).to(impl._device)
         hist = torch.zeros(chunk, 64, dtype=torch.float32, device=impl._device)
         db = impl.device_batch(B)
-        holder = SimpleNamespace(_device_batch=db)
+        holder = SimpleNamespace(_device_batch=db, scaled={"obs", "act_rew"})
         sc = (None, None, 0.0)
-        if self._scaler is not None and getattr(self._scaler, "TYPE", "") == "standard":
+        if self._scaler is not None and hasattr(self._scaler, "affine_f32"):
             m, s, e = replay.scaler_tensors(self._scaler)
             sc = (m.data_ptr(), s.data_ptr(), e)
         torch.cuda.current_stream(impl._device).synchronize()
@@ -428,6 +449,7 @@ class AlgoBase:
                             replay.meta.data_ptr(), idx_dev.data_ptr() + 8 * B * i, B, self._n_steps, float(self._gamma),
                             db.ptr("obs"), db.ptr("act"), db.ptr("rew"), db.ptr("next_obs"), db.ptr("term"),
                             db.ptr("nsteps"), sc[0], sc[1], sc[2], st)
+            impl.scale_actions_rewards(db)
             names_per_step.append(self._update_async(holder))
             self._grad_step += 1
             L.copy_d2d(hist.data_ptr() + 256 * i, impl._slots.data_ptr(), 256, st)

@@ -197,7 +197,7 @@ class ImplBase:
                               q=self.q_function.state_dict(), imitator=imit.state_dict() if imit is not None else None,
                               scaler=self._scaler, n_action_samples=getattr(self, "_n_action_samples", 100),
                               action_flexibility=getattr(self, "_action_flexibility", 0.05),
-                              n_quantiles=getattr(self, "_n_quantiles", 0))
+                              n_quantiles=getattr(self, "_n_quantiles", 0), action_scaler=self._action_scaler)
         save_policy(module, self.observation_shape, fname)
 
     def save_model(self, fname: str) -> None:
@@ -246,6 +246,7 @@ class ImplBase:
         self._pending_upload = None
         dev = getattr(batch, "_device_batch", None)
         if dev is not None:
+            dev = self._scale_device_batch(batch, dev)
             if self._batch is not dev:
                 self._batch = dev
                 self._graphs_invalidate()
@@ -259,6 +260,33 @@ class ImplBase:
             self._upload(db)
         return db
 
+    def _scale_device_batch(self, batch, dev: DeviceBatch) -> DeviceBatch:
+        """A minibatch gathered in HBM carries in `batch.scaled` which of the TorchMiniBatch transforms
+        (torch_utility.py:179-185) were already applied to it (fused into the gather, or by `fit`).  Whatever is
+        missing is applied here.  A buffer owned by the caller (e.g. `TransitionMiniBatch(transitions)`, whose numpy
+        properties must keep showing the raw data) is copied into an impl-owned buffer first."""
+        have = getattr(batch, "scaled", True)   # a bare holder of device buffers: its owner manages the transforms
+        have = {"obs", "act_rew"} if have is True else set(have or ())
+        need_obs = self._vector_scaler() is not None and not dev.pixel_shape and "obs" not in have
+        need_ar = self._scales_actions_rewards(dev) and "act_rew" not in have
+        if not (need_obs or need_ar):
+            return dev
+        if dev is not self._batch or getattr(batch, "_transitions", None) is not None:
+            own = getattr(self, "_own_batch", None)
+            if own is None or own.B != dev.B or own is dev:
+                own = self._own_batch = self._make_batch(dev.B)
+            self._lib.copy_d2d(own.dev.data_ptr(), dev.dev.data_ptr(), 4 * dev.nfloat, self._stream)
+            if dev.pixel_shape:
+                self._lib.copy_d2d(own.pix_dev.data_ptr(), dev.pix_dev.data_ptr(), 2 * dev.npix, self._stream)
+            dev = own
+        else:   # gathered straight into the impl's own buffer: scale in place, once
+            batch.scaled = have | {"obs", "act_rew"}
+        if need_obs:
+            self._scale_observations(dev)
+        if need_ar:
+            self.scale_actions_rewards(dev)
+        return dev
+
     def _upload(self, db: DeviceBatch) -> None:
         self._lib.copy_h2d(db.dev.data_ptr(), db.host.data_ptr(), 4 * db.nfloat, self._stream)
         if db.pixel_shape:
@@ -266,21 +294,60 @@ class ImplBase:
         self._apply_scalers(db)
 
     def _apply_scalers(self, db: DeviceBatch):
-        """scaler.transform on obs/next_obs (d3rlpy/torch_utility.py:179-185).  Standard scaling of a
-        host-staged batch runs as a device kernel; pixel scaling is fused into the first conv load."""
+        """TorchMiniBatch.__init__ (d3rlpy/torch_utility.py:179-185) on a host-staged batch: scaler.transform on
+        obs / next_obs, action_scaler.transform on actions, reward_scaler.transform on rewards, as device kernels;
+        pixel scaling is fused into the first conv load."""
+        self._scale_observations(db)
+        self.scale_actions_rewards(db)
+
+    def _vector_scaler(self):
         sc = self._scaler
-        if sc is None or db.pixel_shape:
+        return sc if sc is not None and hasattr(sc, "affine_f32") else None
+
+    def _scale_observations(self, db: DeviceBatch) -> None:
+        if self._vector_scaler() is None or db.pixel_shape:
             return
         mean, std, eps = self._scaler_params()
         self._lib.standardize(db.ptr("obs"), mean.data_ptr(), std.data_ptr(), eps, 2 * db.B, db.O, self._stream)
 
+    def _scales_actions_rewards(self, db: DeviceBatch) -> bool:
+        return (self._action_scaler is not None and not db.discrete) or self._reward_scaler is not None
+
+    def scale_actions_rewards(self, db: DeviceBatch) -> None:
+        """action_scaler.transform / reward_scaler.transform on the minibatch buffer (torch_utility.py:182-185)."""
+        if self._action_scaler is not None and not db.discrete:
+            mn, mx = self._action_scaler_params()
+            self._lib.scale_actions(db.ptr("act"), mn.data_ptr(), mx.data_ptr(), db.B, db.A, self._stream)
+        if self._reward_scaler is not None:
+            lo, hi, sub, mul, div = self._reward_scaler.constants()
+            self._lib.scale_rewards(db.ptr("rew"), db.B, lo, hi, sub, mul, div, self._stream)
+
     def _scaler_params(self):
-        sc = self._scaler
+        """(subtrahend, divisor, eps) of the observation scaler on the device: StandardScaler (mean, std, eps),
+        MinMaxScaler (min, max - min, 0)."""
         if getattr(self, "_scaler_dev", None) is None:
-            mean = torch.tensor(np.asarray(sc._mean, dtype=np.float32).reshape(-1), device=self._device)
-            std = torch.tensor(np.asarray(sc._std, dtype=np.float32).reshape(-1), device=self._device)
-            self._scaler_dev = (mean, std, float(sc._eps))
+            sub, div, eps = self._scaler.affine_f32()
+            self._scaler_dev = (torch.tensor(sub, device=self._device), torch.tensor(div, device=self._device), eps)
+            torch.cuda.synchronize(self._device)   # one-time upload on torch's stream; the kernels run on ours
         return self._scaler_dev
+
+    def _action_scaler_params(self):
+        if getattr(self, "_action_scaler_dev", None) is None:
+            mn, mx = self._action_scaler.bounds_f32()
+            assert mn.size == self._action_size, "action scaler bounds do not match the action size"
+            self._action_scaler_dev = (torch.tensor(mn, device=self._device), torch.tensor(mx, device=self._device))
+            torch.cuda.synchronize(self._device)
+        return self._action_scaler_dev
+
+    def unscale_actions(self, act: torch.Tensor) -> torch.Tensor:
+        """action_scaler.reverse_transform on predicted / sampled actions (algos/torch/base.py:60-62,77-79), in place
+        on the device before the read-back."""
+        if self._action_scaler is not None:
+            mn, mx = self._action_scaler_params()
+            assert act.is_contiguous() and act.shape[-1] == self._action_size
+            self._lib.unscale_actions(act.data_ptr(), mn.data_ptr(), mx.data_ptr(), act.numel() // self._action_size,
+                                      self._action_size, self._stream)
+        return act
 
     # ------------------------------------------------------------------ noise
     def noise_layout(self, B: int) -> Dict[str, tuple]:

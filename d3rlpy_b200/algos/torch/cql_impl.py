@@ -557,6 +557,7 @@ class CQLImpl(DDPGBaseImpl):
         act = self.ws("eval_act", n, A)
         self._lib.policy_sample_rows(head.data_ptr(), 2 * A, eps.data_ptr(), None, 0, None, 0, act.data_ptr(), None, n,
                                      1, 0, A, MIN_LOGSTD, MAX_LOGSTD, 0, self._stream)
+        self.unscale_actions(act)   # algos/torch/base.py:77-79
         self.sync()
         return act.detach().cpu().numpy()
 

@@ -191,7 +191,7 @@ class DDPGBaseImpl(ImplBase):
         assert t.ndim > 1, "Input must have batch dimension."
         with torch.cuda.stream(self._stream_obj):
             d = t.to(self._device, non_blocking=False).contiguous()
-        if self._scaler is not None:
+        if self._vector_scaler() is not None:   # StandardScaler / MinMaxScaler.transform (torch_api scaler_targets=["x"])
             mean, std, eps = self._scaler_params()
             self._lib.standardize(d.data_ptr(), mean.data_ptr(), std.data_ptr(), eps, d.shape[0], d.shape[1],
                                   self._stream)
@@ -207,17 +207,27 @@ class DDPGBaseImpl(ImplBase):
     def _predict_best_action(self, obs: torch.Tensor) -> torch.Tensor:
         raise NotImplementedError
 
-    def predict_best_action(self, x) -> np.ndarray:
+    def predict_best_action(self, x, normalized: bool = False) -> np.ndarray:
+        """TorchImplBase.predict_best_action (algos/torch/base.py:50-64): greedy action, mapped back to the original
+        range by `action_scaler.reverse_transform` unless `normalized`."""
         obs = self._eval_obs(x)
-        a = self._predict_best_action(obs)
+        with torch.cuda.stream(self._stream_obj):
+            a = self._predict_best_action(obs).contiguous()
+        if not normalized:
+            self.unscale_actions(a)
         self.sync()
         return a.detach().cpu().numpy()
 
     def predict_value(self, x, action, with_std: bool = False):
         """ContinuousQFunctionMixin.predict_value (algos/torch/utility.py:51-78): mean (and std) over members."""
         obs = self._eval_obs(x)
-        act = torch.as_tensor(np.asarray(action), dtype=torch.float32).to(self._device).contiguous()
+        with torch.cuda.stream(self._stream_obj):
+            act = torch.as_tensor(np.asarray(action), dtype=torch.float32).to(self._device).contiguous()
         assert obs.shape[0] == act.shape[0]
+        if self._action_scaler is not None:   # torch_api(action_scaler_targets=["action"]), algos/torch/utility.py:51-55
+            mn, mx = self._action_scaler_params()
+            self._lib.scale_actions(act.data_ptr(), mn.data_ptr(), mx.data_ptr(), act.shape[0], self._action_size,
+                                    self._stream)
         n, O, A = obs.shape[0], obs.shape[1], self._action_size
         rows = self.ws("eval_x", n, O + A)
         self._lib.concat_rows(obs.data_ptr(), O, act.data_ptr(), A, None, 0.0, 0.0, 0.0, rows.data_ptr(), O + A, n, 1,

@@ -68,10 +68,6 @@ class DQNImpl(ImplBase):
         self._q_func.refresh_shadow("target", self._stream)
         self.sync()
 
-    def _apply_scalers(self, db):
-        if not self._pixel:
-            super()._apply_scalers(db)
-
     # ------------------------------------------------------------------ reference-visible properties
     @property
     def q_function(self):

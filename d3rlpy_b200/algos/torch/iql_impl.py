@@ -253,7 +253,14 @@ class IQLImpl(DDPGBaseImpl):
     def sample_action(self, x) -> np.ndarray:
         """dist.sample(): Normal(tanh(mu), exp(logstd)).rsample().clamp(-1, 1) (distributions.py:52-53); the draw is
         taken on the host from numpy's global stream."""
-        mean = self.predict_best_action(x)
+        mean = self.predict_best_action(x, normalized=True)
         p = self._logstd.params[:self._action_size].detach().cpu().numpy()
         std = np.exp(MIN_LOGSTD + (MAX_LOGSTD - MIN_LOGSTD) / (1.0 + np.exp(-p)))
-        return np.clip(mean + std * np.random.randn(*mean.shape), -1.0, 1.0).astype(np.float32)
+        act = np.clip(mean + std * np.random.randn(*mean.shape), -1.0, 1.0).astype(np.float32)
+        if self._action_scaler is None:
+            return act
+        with torch.cuda.stream(self._stream_obj):   # action_scaler.reverse_transform (algos/torch/base.py:77-79)
+            d = torch.from_numpy(act).to(self._device).contiguous()
+        self.unscale_actions(d)
+        self.sync()
+        return d.cpu().numpy()

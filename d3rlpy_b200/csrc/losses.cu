@@ -360,10 +360,63 @@ __global__ void __launch_bounds__(256) standardize_kernel(float* __restrict__ x,
   x[i] = __fdiv_rn(__fsub_rn(x[i], __ldg(mean + j)), __fadd_rn(__ldg(std + j), eps));
 }
 
+// MinMaxActionScaler.transform / reverse_transform, operator order of action_scalers.py:185-206
+template <bool REVERSE>
+__global__ void __launch_bounds__(256) action_scale_kernel(float* __restrict__ a, const float* __restrict__ mn,
+                                                            const float* __restrict__ mx, long long total, int dim) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int j = (int)(i % dim);
+  float lo = __ldg(mn + j), range = __fsub_rn(__ldg(mx + j), lo);
+  if (REVERSE)
+    a[i] = __fadd_rn(__fmul_rn(range, __fdiv_rn(__fadd_rn(a[i], 1.0f), 2.0f)), lo);
+  else
+    a[i] = __fsub_rn(__fmul_rn(__fdiv_rn(__fsub_rn(a[i], lo), range), 2.0f), 1.0f);
+}
+
+// RewardScaler.transform family: (mul * (clamp(r, lo, hi) - sub)) / div; torch.clamp propagates NaN
+__global__ void __launch_bounds__(256) reward_scale_kernel(float* __restrict__ r, int n, float lo, float hi, float sub,
+                                                            float mul, float div) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = r[i];
+  if (v == v) v = fminf(fmaxf(v, lo), hi);
+  r[i] = __fdiv_rn(__fmul_rn(mul, __fsub_rn(v, sub)), div);
+}
+
 }  // namespace d3b
 
 using namespace d3b;
 #define ST ((cudaStream_t)stream)
+
+extern "C" int d3b_scale_actions(float* a, const float* minimum, const float* maximum, int rows, int dim,
+                                 void* stream) {
+  D3B_REQUIRE(rows >= 0 && dim >= 1, "scale_actions: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(a && minimum && maximum, "scale_actions: null pointer");
+  long long total = (long long)rows * dim;
+  action_scale_kernel<false><<<(unsigned)ceil_div_ll(total, 256), 256, 0, ST>>>(a, minimum, maximum, total, dim);
+  return check_launch("scale_actions");
+}
+
+extern "C" int d3b_unscale_actions(float* a, const float* minimum, const float* maximum, int rows, int dim,
+                                   void* stream) {
+  D3B_REQUIRE(rows >= 0 && dim >= 1, "unscale_actions: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(a && minimum && maximum, "unscale_actions: null pointer");
+  long long total = (long long)rows * dim;
+  action_scale_kernel<true><<<(unsigned)ceil_div_ll(total, 256), 256, 0, ST>>>(a, minimum, maximum, total, dim);
+  return check_launch("unscale_actions");
+}
+
+extern "C" int d3b_scale_rewards(float* r, int n, float lo, float hi, float sub, float mul, float div, void* stream) {
+  D3B_REQUIRE(n >= 0, "scale_rewards: bad size");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(r, "scale_rewards: null pointer");
+  D3B_REQUIRE(lo <= hi && div != 0.0f, "scale_rewards: empty clip interval or zero divisor");
+  reward_scale_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ST>>>(r, n, lo, hi, sub, mul, div);
+  return check_launch("scale_rewards");
+}
 
 extern "C" int d3b_standardize(float* x, const float* mean, const float* std, float eps, int rows, int dim,
                                void* stream) {

@@ -76,9 +76,8 @@ class DeviceReplay:
     def scaler_tensors(self, scaler):
         key = id(scaler)
         if key not in self._scaler_cache:
-            mean = torch.tensor(np.asarray(scaler._mean, np.float32).reshape(-1), device=self.device)
-            std = torch.tensor(np.asarray(scaler._std, np.float32).reshape(-1), device=self.device)
-            self._scaler_cache[key] = (mean, std, float(scaler._eps))
+            sub, div, eps = scaler.affine_f32()   # StandardScaler: (mean, std, eps); MinMaxScaler: (min, max - min, 0)
+            self._scaler_cache[key] = (torch.tensor(sub, device=self.device), torch.tensor(div, device=self.device), eps)
         return self._scaler_cache[key]
 
 
@@ -278,11 +277,11 @@ class TransitionMiniBatch:
         idx_dev = torch.empty(B, dtype=torch.int64, device=replay.device)
         L.copy_h2d(idx_dev.data_ptr(), idx_host.data_ptr(), 8 * B, st)
         sc = (None, None, 0.0)
-        self.scaled = False
-        if scaler is not None and not replay.is_image and getattr(scaler, "TYPE", "") == "standard":
+        self.scaled = set()   # which TorchMiniBatch transforms (torch_utility.py:179-185) the buffer already carries
+        if scaler is not None and not replay.is_image and hasattr(scaler, "affine_f32"):
             m, s, e = replay.scaler_tensors(scaler)
             sc = (m.data_ptr(), s.data_ptr(), e)
-            self.scaled = True
+            self.scaled.add("obs")
         self._act_i32 = None
         if replay.discrete:
             self._act_i32 = torch.empty(B, dtype=torch.int32, device=replay.device)

@@ -48,7 +48,7 @@ class GreedyPolicy(torch.nn.Module):
     "discrete" (DQN family: argmax of the member-mean Q, dqn_impl.py:131-133), "bcq" (bcq_impl.py:163-211)."""
 
     def __init__(self, kind: str, policy=None, q=None, imitator=None, scaler=None, n_action_samples: int = 100,
-                 action_flexibility: float = 0.05, n_quantiles: int = 0):
+                 action_flexibility: float = 0.05, n_quantiles: int = 0, action_scaler=None):
         super().__init__()
         self.kind, self.n, self.flex = kind, n_action_samples, action_flexibility
         self.n_quantiles = n_quantiles  # > 0: QR members, value = mean over the quantiles (qr_q_function.py:44-48)
@@ -60,10 +60,19 @@ class GreedyPolicy(torch.nn.Module):
             self.mean = torch.as_tensor(scaler._mean, dtype=torch.float32)
             self.std = torch.as_tensor(scaler._std, dtype=torch.float32)
             self.eps = float(scaler._eps)
+        if self.scaler_kind == "min_max":
+            self.minimum = torch.as_tensor(scaler._minimum, dtype=torch.float32)
+            self.maximum = torch.as_tensor(scaler._maximum, dtype=torch.float32)
+        self.act_min = self.act_max = None
+        if action_scaler is not None and kind != "discrete":
+            self.act_min = torch.as_tensor(action_scaler._minimum, dtype=torch.float32)
+            self.act_max = torch.as_tensor(action_scaler._maximum, dtype=torch.float32)
 
     def _scale(self, x: torch.Tensor) -> torch.Tensor:
         if self.scaler_kind == "standard":  # scalers.py:350-354
             return (x - self.mean) / (self.std + self.eps)
+        if self.scaler_kind == "min_max":   # scalers.py:209-218
+            return (x - self.minimum) / (self.maximum - self.minimum)
         if self.scaler_kind == "pixel":     # scalers.py:109-110
             return x.float() / 255.0
         return x
@@ -81,7 +90,14 @@ class GreedyPolicy(torch.nn.Module):
         return torch.stack(vals, 0)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self._scale(x)
+        """`_func` of TorchImplBase.save_policy (algos/torch/base.py:91-100): scaler.transform, greedy action,
+        action_scaler.reverse_transform."""
+        action = self._greedy(self._scale(x))
+        if self.act_min is not None:   # action_scalers.py:197-206
+            action = ((self.act_max - self.act_min) * ((action + 1.0) / 2.0)) + self.act_min
+        return action
+
+    def _greedy(self, x: torch.Tensor) -> torch.Tensor:
         if self.kind == "normal":
             return torch.tanh(F.linear(_mlp(self.pi, "_encoder.", x), self.pi["_mu.weight"], self.pi["_mu.bias"]))
         if self.kind == "deterministic":

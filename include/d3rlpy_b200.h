@@ -51,8 +51,22 @@ int d3b_gather_vector(const float* obs, int obs_dim, const void* actions, int ac
 int d3b_gather_frames(const uint8_t* frames, int frame_bytes, const void* meta, const int64_t* indices, int batch,
                       int n_frames, int n_steps, uint8_t* out_obs, uint8_t* out_next, void* stream);
 
-/* StandardScaler.transform (d3rlpy/preprocessing/scalers.py:350-354) for a host-staged batch. */
+/* StandardScaler.transform (d3rlpy/preprocessing/scalers.py:350-354) for a host-staged batch: x = (x - mean) / (std + eps).
+ * MinMaxScaler.transform (scalers.py:209-218) is the same call with mean = min, std = max - min (float32), eps = 0. */
 int d3b_standardize(float* x, const float* mean, const float* std, float eps, int rows, int dim, void* stream);
+
+/* MinMaxActionScaler.transform / reverse_transform (d3rlpy/preprocessing/action_scalers.py:185-206), in place on
+ * a[rows][dim]:  scale   a = ((a - min) / (max - min)) * 2 - 1      (TorchMiniBatch, torch_utility.py:182-183)
+ *                unscale a = ((max - min) * ((a + 1) / 2)) + min    (predict_best_action / sample_action,
+ *                                                                    algos/torch/base.py:60-62,77-79) */
+int d3b_scale_actions(float* a, const float* minimum, const float* maximum, int rows, int dim, void* stream);
+int d3b_unscale_actions(float* a, const float* minimum, const float* maximum, int rows, int dim, void* stream);
+
+/* RewardScaler.transform (d3rlpy/preprocessing/reward_scalers.py:125-126,176-177,261-264,356-359,470-472) in place on
+ * r[n]:  r = (mul * (clamp(r, lo, hi) - sub)) / div  -- Multiply (mul), Clip (lo, hi, mul), MinMax (sub = min,
+ * div = max - min), Standard (sub = mean, div = std + eps), ReturnBased (div = return_max - return_min); unused
+ * constants are -inf / +inf / 0 / 1 / 1, which leave the value bit-identical. */
+int d3b_scale_rewards(float* r, int n, float lo, float hi, float sub, float mul, float div, void* stream);
 
 /* ---- K2/K3: batched-ensemble dense layers (fp32 mode) ---------------------------
  * forward:  y[e] = act(x[e] w[e]^T + b[e])      replaces nn.Linear + ReLU in

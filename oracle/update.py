@@ -433,9 +433,9 @@ def hard_sync(targ: Params, src: Params):
 # --------------------------------------------------------------------------- batches / scalers
 class Batch:
     """TorchMiniBatch (torch_utility.py:152-221): every field float32; scaler applied to
-    observations/next_observations, reward scaler to rewards."""
+    observations/next_observations, action scaler to actions, reward scaler to rewards (oracle/scalers.py)."""
 
-    def __init__(self, arrays: dict, scaler=None, reward_scaler=None):
+    def __init__(self, arrays: dict, scaler=None, reward_scaler=None, action_scaler=None):
         f = lambda a: torch.tensor(np.asarray(a)).float()
         self.observations = f(arrays["observations"])
         self.actions = f(arrays["actions"])
@@ -446,6 +446,8 @@ class Batch:
         if scaler is not None:
             self.observations = scaler(self.observations)
             self.next_observations = scaler(self.next_observations)
+        if action_scaler is not None:
+            self.actions = action_scaler(self.actions)
         if reward_scaler is not None:
             self.rewards = reward_scaler(self.rewards)
 

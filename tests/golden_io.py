@@ -55,3 +55,8 @@ def load_qr():
 def load_online():
     """Online ReplayBuffer scripts and sampled minibatches (tests/golden/make_golden_online.py)."""
     return np.load(os.path.join(GOLDEN, "online.npz"))
+
+
+def load_scalers():
+    """Observation / action / reward scaler fixtures (tests/golden/make_golden_scalers.py)."""
+    return np.load(os.path.join(GOLDEN, "scalers.npz"))
