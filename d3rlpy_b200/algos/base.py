@@ -151,6 +151,7 @@ def round_iterator_indices(rng, n_transitions: int, batch_size: int, shuffle: bo
 
 class AlgoBase:
     _impl = None
+    DISCRETE_ACTIONS = False   # get_action_type(): ActionSpace.CONTINUOUS; the DQN family overrides it
 
     def __init__(self, batch_size: int, n_frames: int, n_steps: int, gamma: float, scaler=None, action_scaler=None,
                  reward_scaler=None, use_gpu=0, kwargs: Optional[Dict[str, Any]] = None):
@@ -387,21 +388,39 @@ class AlgoBase:
         dropped, iterators/round_iterator.py:39-55) -> device gather -> update.  Returns the per-epoch metric means."""
         if (n_epochs is None) == (n_steps is None):
             raise ValueError("Either of n_epochs or n_steps must be given.")  # base.py:548-549
+        subset = None
+        if not hasattr(dataset, "device_replay"):   # List[Episode] / List[Transition] (base.py:494-507)
+            from ..dataset import Episode, Transition
+            from ..preprocessing import TransitionSubset
+
+            if not dataset:
+                raise ValueError("empty dataset is not supported.")
+            if not isinstance(dataset[0], (Episode, Transition)):
+                raise ValueError(f"invalid dataset type: {type(dataset)}")
+            subset = TransitionSubset(dataset)
+            dataset = subset._ds
+        discrete = getattr(self, "DISCRETE_ACTIONS", None)   # base.py:509-519
+        if discrete is not None:
+            assert dataset.is_action_discrete() == discrete, \
+                ("The action-space of the given dataset is not compatible with the algorithm. Please use "
+                 + ("discrete" if discrete else "continuous") + " action-space algorithms.")
         for sc in (self._scaler, self._action_scaler, self._reward_scaler):   # base.py:566-585
             if sc is not None:
-                sc.fit(dataset)
+                sc.fit(dataset if subset is None else subset)
         self.build_with_dataset(dataset)
         replay = dataset.device_replay(self._impl._device)
         rng = np.random if seed is None else np.random.RandomState(seed)
         history: List[Dict[str, float]] = []
         B = self._batch_size
+        n = len(replay) if subset is None else len(subset)
+        pick = (lambda idx: idx) if subset is None else (lambda idx: subset._t_index[idx])
         if n_steps is not None:
             assert n_steps >= n_steps_per_epoch  # base.py:523
             for _ in range(n_steps // n_steps_per_epoch):
-                history.append(self._fit_epoch(replay, random_iterator_indices(rng, len(replay), n_steps_per_epoch, B)))
+                history.append(self._fit_epoch(replay, pick(random_iterator_indices(rng, n, n_steps_per_epoch, B))))
         else:
             for _ in range(n_epochs):
-                history.append(self._fit_epoch(replay, round_iterator_indices(rng, len(replay), B, shuffle)))
+                history.append(self._fit_epoch(replay, pick(round_iterator_indices(rng, n, B, shuffle))))
         return history
 
     def _fit_epoch(self, replay, idx: np.ndarray) -> Dict[str, float]:

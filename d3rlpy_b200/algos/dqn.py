@@ -59,6 +59,7 @@ def _n_quantiles_of(q_func_factory) -> int:
 class DQN(AlgoBase):
     IMPL = DQNImpl
     SUPPORTS_QR = True
+    DISCRETE_ACTIONS = True    # get_action_type(): ActionSpace.DISCRETE (algos/dqn.py:134-135)
 
     def __init__(self, *, learning_rate: float = 6.25e-5, optim_factory=None, encoder_factory="default",
                  q_func_factory="mean", batch_size: int = 32, n_frames: int = 1, n_steps: int = 1, gamma: float = 0.99,

@@ -13,14 +13,33 @@ from typing import Any, Dict, Optional
 import numpy as np
 
 
-def _transition_arrays(data):
-    """(observations, actions, rewards, episode id) of every transition, from an MDPDataset or a list of Transitions."""
+def _resolve(data):
+    """(MDPDataset, transition indices) of what `fit` was given: an MDPDataset, a list of Transitions / Episodes of
+    one MDPDataset (base.py:494-507), or the `TransitionSubset` that `AlgoBase.fit` builds from such a list."""
     if hasattr(data, "_meta"):
-        ds, t = data, np.arange(data._meta.shape[0])
-    else:
-        ds = data[0]._ds
-        assert all(tr._ds is ds for tr in data), "transitions must come from one MDPDataset"
-        t = np.fromiter((tr._t for tr in data), dtype=np.int64, count=len(data))
+        return data, np.arange(data._meta.shape[0])
+    if hasattr(data, "_t_index"):
+        return data._ds, data._t_index
+    ds = data[0]._ds
+    assert all(x._ds is ds for x in data), "transitions must come from one MDPDataset"
+    if hasattr(data[0], "_tr"):   # Episodes: all their transitions, in order
+        return ds, np.concatenate([np.arange(*e._tr) for e in data]).astype(np.int64)
+    return ds, np.fromiter((tr._t for tr in data), dtype=np.int64, count=len(data))
+
+
+class TransitionSubset:
+    """The transitions a `fit` call trains on, as indices into one MDPDataset's transition table."""
+
+    def __init__(self, data):
+        self._ds, self._t_index = _resolve(data)
+
+    def __len__(self):
+        return len(self._t_index)
+
+
+def _transition_arrays(data):
+    """(observations, actions, rewards, episode id) of every transition passed."""
+    ds, t = _resolve(data)
     step = ds._meta[t, 0]
     return ds._observations[step], ds._actions[step], ds._rewards[step], ds._meta[t, 1]
 
@@ -264,7 +283,7 @@ class ReturnBasedRewardScaler(_RewardScaler):
         """Whole-episode sums of transition rewards, whichever transitions of an episode were passed (:441-463)."""
         if self._return_max is not None and self._return_min is not None:
             return
-        ds = transitions if hasattr(transitions, "_meta") else transitions[0]._ds
+        ds = _resolve(transitions)[0]
         episodes = np.unique(_transition_arrays(transitions)[3])
         start = ds._meta[:, 1]
         returns = []

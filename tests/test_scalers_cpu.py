@@ -169,3 +169,40 @@ def test_oracle_update_with_scalers_matches_reference(name):
         for k, v in case.group("final", grp).items():
             got = getattr(algo, attr)[k].detach()
             assert float((got - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
+
+
+def test_fit_accepts_episode_and_transition_lists():
+    """LearnableBase.fit takes an MDPDataset, List[Episode] or List[Transition] (base.py:494-507); lists train on
+    exactly their transitions.  Guards that fire before any device work are checked here, the training itself in
+    tests/test_update_gpu.py."""
+    from d3rlpy_b200 import preprocessing as pp
+    from d3rlpy_b200.algos import CQL, DQN
+    from d3rlpy_b200.dataset import MDPDataset
+
+    z = load_scalers()
+    ds = MDPDataset(z["data/observations"], z["data/actions"], z["data/rewards"], z["data/terminals"],
+                    z["data/episode_terminals"])
+    eps = ds.episodes
+    sub = pp.TransitionSubset(eps[2:5])
+    want = np.concatenate([[t._t for t in e.transitions] for e in eps[2:5]])
+    assert sub._ds is ds and np.array_equal(sub._t_index, want) and len(sub) == len(want)
+    trs = [t for e in eps[2:5] for t in e.transitions][::3]
+    sub2 = pp.TransitionSubset(trs)
+    assert np.array_equal(sub2._t_index, want[::3])
+    # scalers fitted on a subset see only that subset (base.py:566-585 passes the transition list)
+    mm = pp.MinMaxScaler()
+    mm.fit(sub)
+    obs = np.stack([t.observation for e in eps[2:5] for t in e.transitions])
+    assert np.array_equal(mm._minimum.reshape(-1), obs.min(0)) and np.array_equal(mm._maximum.reshape(-1), obs.max(0))
+    rb = pp.ReturnBasedRewardScaler()
+    rb.fit(sub2)
+    rets = [sum(t.reward for t in e.transitions) for e in eps[2:5]]
+    assert abs(rb._return_max - max(rets)) < 1e-4 and abs(rb._return_min - min(rets)) < 1e-4
+    with pytest.raises(ValueError, match="empty dataset"):
+        CQL(use_gpu=None).fit([], n_steps=10, n_steps_per_epoch=10)
+    with pytest.raises(ValueError, match="invalid dataset type"):
+        CQL(use_gpu=None).fit([1, 2, 3], n_steps=10, n_steps_per_epoch=10)
+    with pytest.raises(AssertionError, match="not compatible"):
+        DQN(use_gpu=None).fit(eps[:2], n_steps=10, n_steps_per_epoch=10)
+    with pytest.raises(ValueError, match="n_epochs or n_steps"):
+        CQL(use_gpu=None).fit(ds)

@@ -236,3 +236,38 @@ def test_fit_fits_and_applies_scalers():
     seen = dq.impl._batch.view("rew").cpu().numpy()
     assert np.array_equal(seen, np.clip(raw_rewards, -1.0, 1.0))
     assert np.array_equal(np.array(mb.rewards), raw_rewards)
+
+
+def test_fit_over_an_episode_list_trains_on_those_transitions_only():
+    """`fit(train_episodes)` (base.py:494-507), the train/test-split pattern: the index stream runs over the list's
+    transitions; the same stream walked by hand through host minibatches gives the same metrics."""
+    from d3rlpy_b200.algos import DDPG
+    from d3rlpy_b200.algos.base import random_iterator_indices
+    from d3rlpy_b200.dataset import MDPDataset, TransitionMiniBatch
+
+    z = load_scalers()
+    ds = MDPDataset(z["data/observations"], z["data/actions"], z["data/rewards"], z["data/terminals"],
+                    z["data/episode_terminals"])
+    train = ds.episodes[1:5]
+    kw = dict(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=16, scaler="standard",
+              reward_scaler="min_max", n_steps=2)
+    a = DDPG(**kw)
+    hist = a.fit(train, n_steps=4, n_steps_per_epoch=2, seed=9)
+    trs = [t for e in train for t in e.transitions]
+    obs = np.stack([t.observation for t in trs]).astype(np.float64)
+    assert np.allclose(a.scaler._mean, obs.mean(0), rtol=1e-12) and a.reward_scaler._minimum == min(t.reward for t in trs)
+    b = DDPG(**kw)
+    for sc in (b.scaler, b.reward_scaler):
+        sc.fit(trs)
+    b.build_with_dataset(ds)
+    rng = np.random.RandomState(9)
+    for epoch in range(2):
+        acc = {}
+        for ix in random_iterator_indices(rng, len(trs), 2, 16):
+            mb = TransitionMiniBatch([trs[i] for i in ix], n_steps=2, gamma=0.99)
+            host = SimpleNamespace(**{k: np.array(getattr(mb, k)) for k in (
+                "observations", "actions", "rewards", "next_observations", "terminals", "n_steps")})
+            for k, v in b.update(host).items():
+                acc.setdefault(k, []).append(float(v))
+        for k, v in acc.items():
+            assert abs(hist[epoch][k] - np.mean(v)) <= 1e-5 * max(1.0, abs(np.mean(v))), (epoch, k)
