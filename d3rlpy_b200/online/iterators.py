@@ -30,7 +30,12 @@ class StackedObservation:
 
 
 def _setup_algo(algo, env) -> None:
-    """iterators.py:76-96 (scalers fitted from an environment are outside the accelerated path)."""
+    """iterators.py:76-96: observation / action scalers take their bounds from the environment's spaces, then the
+    impl is built."""
+    if algo.scaler:
+        algo.scaler.fit_with_env(env)
+    if algo.action_scaler:
+        algo.action_scaler.fit_with_env(env)
     if algo.impl is None:
         algo.build_with_env(env)
 

@@ -56,6 +56,9 @@ class _Scaler:
     def fit(self, transitions) -> None:
         pass
 
+    def fit_with_env(self, env) -> None:
+        pass
+
     def get_params(self, deep: bool = False) -> Dict[str, Any]:
         return {}
 
@@ -81,6 +84,11 @@ class StandardScaler(_Scaler):
         obs = _transition_arrays(transitions)[0].astype(np.float64)
         self._mean = obs.mean(axis=0)
         self._std = np.sqrt(((obs - self._mean) ** 2).mean(axis=0))
+
+    def fit_with_env(self, env) -> None:
+        if self._mean is not None and self._std is not None:
+            return
+        raise NotImplementedError("standard scaler does not support fit_with_env.")   # scalers.py:345-350
 
     def affine_f32(self):
         """(subtrahend, divisor, eps) of `(x - s) / (d + eps)` as the kernels take them."""

@@ -206,3 +206,25 @@ def test_fit_accepts_episode_and_transition_lists():
         DQN(use_gpu=None).fit(eps[:2], n_steps=10, n_steps_per_epoch=10)
     with pytest.raises(ValueError, match="n_epochs or n_steps"):
         CQL(use_gpu=None).fit(ds)
+
+
+def test_online_setup_fits_scalers_from_the_environment():
+    """_setup_algo (online/iterators.py:76-96): min-max bounds come from the spaces; the standard scaler refuses."""
+    from types import SimpleNamespace
+
+    from d3rlpy_b200 import preprocessing as pp
+    from d3rlpy_b200.online.iterators import _setup_algo
+
+    env = SimpleNamespace(observation_space=SimpleNamespace(shape=(3,), low=np.array([-1, -2, -3], np.float32),
+                                                            high=np.array([1, 2, 3], np.float32)),
+                          action_space=SimpleNamespace(shape=(2,), low=np.array([-2, 0], np.float32),
+                                                       high=np.array([2, 1], np.float32)))
+    algo = SimpleNamespace(scaler=pp.MinMaxScaler(), action_scaler=pp.MinMaxActionScaler(), impl=object())
+    _setup_algo(algo, env)
+    assert algo.scaler._minimum.shape == (1, 3) and np.array_equal(algo.scaler._maximum[0], [1, 2, 3])
+    mn, mx = algo.action_scaler.bounds_f32()
+    assert np.array_equal(mn, [-2, 0]) and np.array_equal(mx, [2, 1])
+    algo = SimpleNamespace(scaler=pp.StandardScaler(), action_scaler=None, impl=object())
+    with pytest.raises(NotImplementedError):
+        _setup_algo(algo, env)
+    _setup_algo(SimpleNamespace(scaler=pp.PixelScaler(), action_scaler=None, impl=object()), env)
