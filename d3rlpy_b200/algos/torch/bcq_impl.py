@@ -216,8 +216,9 @@ class BCQImpl(DDPGBaseImpl):
             self._allreduce(self._q_func.arena.grads)
             self._q_func.adam(self._critic_learning_rate, st, tau=self._tau if sync_target else None)
 
-    def _p_actor(self, db, sync_target=True):
-        """compute_actor_loss (bcq_impl.py:132-146): -Q_0(s, pi(s, decode(s, clamp(randn)))).mean()."""
+    def _p_actor(self, db, sync_target=True, step=True):
+        """compute_actor_loss (bcq_impl.py:132-146): -Q_0(s, pi(s, decode(s, clamp(randn)))).mean(); step=False stops
+        after the loss value."""
         B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
         Lz = 2 * A
         xd = self.ws("a_xd", B, O + Lz)
@@ -241,6 +242,8 @@ class BCQImpl(DDPGBaseImpl):
         L.neg_mean_seed(q0.data_ptr(), dq.data_ptr(), self.sums_ptr(S_ACT), B, inv_b, st)
         self._allreduce(self._slots[32 + S_ACT:32 + S_ACT + 1])
         L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACT), 4, st)
+        if not step:
+            return
         da = self.ws("a_da", B, A)
         self._q_func.backward(xq, O + A, B, cc, dq, st, weight_grads=False, dx=da, lddx=A, stride_dx=B * A,
                               dx_col0=O, dx_cols=A)
@@ -318,6 +321,13 @@ class BCQImpl(DDPGBaseImpl):
         db = self._begin(batch, C_DRAW, C_CRITIC)
         self._p_critic(db, self._p_target(db))
         return self.read_slots()[M_CRITIC].copy()
+
+    def compute_actor_loss(self, batch) -> torch.Tensor:
+        """BCQImpl.compute_actor_loss (bcq_impl.py:132-146); nothing is stepped."""
+        db = self._begin(batch)
+        self._p_actor(db, step=False)
+        self.sync()
+        return self._slots[M_ACTOR].clone()
 
     def update_actor(self, batch) -> np.ndarray:
         db = self._begin(batch, C_DRAW, C_ACTOR)

@@ -198,8 +198,9 @@ class CQLImpl(DDPGBaseImpl):
             self._allreduce(self._q_func.arena.grads)
             self._q_func.adam(self._critic_learning_rate, st, tau=self._tau if sync_target else None)
 
-    def _p_actor(self, db, acts_p, head, sync_target=True):
-        """compute_actor_loss (sac_impl.py:114-121) + backward + Adam (ddpg_impl.py:167-183)."""
+    def _p_actor(self, db, acts_p, head, sync_target=True, step=True):
+        """compute_actor_loss (sac_impl.py:114-121) + backward + Adam (ddpg_impl.py:167-183); step=False stops after
+        the loss value."""
         B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics
         xa = self.ws("xa", B, O + A)
         lp = self.ws("a_lp", B)
@@ -214,6 +215,8 @@ class CQLImpl(DDPGBaseImpl):
                          inv_b, st)
         self._allreduce(self._slots[32 + S_ACTOR:32 + S_ACTOR + 1])
         L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
+        if not step:
+            return
         dxa = self.ws("a_dx", E, B, A)
         self._q_func.backward(xa, O + A, B, acts_c, dq, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A,
                               dx_col0=O, dx_cols=A)
@@ -525,7 +528,13 @@ class CQLImpl(DDPGBaseImpl):
         return self.read_slots()[M_CRITIC].copy()
 
     def compute_actor_loss(self, batch) -> torch.Tensor:
-        raise NotImplementedError("use update_actor(); the standalone loss hook is not split out yet")
+        """SACImpl.compute_actor_loss (sac_impl.py:114-121): mean(exp(log_temp) * log pi(a|s) - min_e Q_e(s, a)) with
+        a freshly sampled a ~ pi(.|s); nothing is stepped."""
+        db = self._begin(batch)
+        acts_p, head = self._p_policy(db)
+        self._p_actor(db, acts_p, head, step=False)
+        self.sync()
+        return self._slots[M_ACTOR].clone()
 
     def update_actor(self, batch) -> np.ndarray:
         db = self._begin(batch, C_DRAW, C_ACTOR)

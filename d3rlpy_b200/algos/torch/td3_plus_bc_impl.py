@@ -95,8 +95,9 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         self._allreduce(self._q_func.arena.grads)
         self._q_func.adam(self._critic_learning_rate, self._stream, tau=self._tau if sync_target else None)
 
-    def _p_actor(self, db):
-        """compute_actor_loss (td3_plus_bc_impl.py:64-70) + backward + Adam; only member 0 is evaluated."""
+    def _p_actor(self, db, step=True):
+        """compute_actor_loss (td3_plus_bc_impl.py:64-70) + backward + Adam; only member 0 is evaluated; step=False
+        stops after the loss value."""
         B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
         acts_p = self._policy.ctx("pi", B, 1, True)
         a = self.ws("pi_a", 1, B, A)
@@ -111,6 +112,8 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             L.qr_values(theta0.data_ptr(), B * nq, q0.data_ptr(), B, B, 1, nq, 1, st)
         dq = self.ws("a_dq", 1, B)
         bc_w = self._actor_seed(q0, a, db, dq, B, A, inv_b)
+        if not step:
+            return
         if nq:
             dq, dvalues = self.ws("a_dtheta", 1, B, nq), dq
             L.qr_values_backward(dvalues.data_ptr(), dq.data_ptr(), B, nq, st)
@@ -250,11 +253,20 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         self._p_critic_step(db, xc, acts, dq, sync_target=False)
         return self.read_slots()[M_CRITIC].copy()
 
+    def compute_actor_loss(self, batch) -> torch.Tensor:
+        """TD3PlusBCImpl.compute_actor_loss (td3_plus_bc_impl.py:64-70): -lambda * mean Q_0(s, pi(s)) + mean((a - pi(s))^2)
+        with lambda = alpha / mean|Q_0| detached; TD3 / DDPG: -mean Q_0(s, pi(s)) (ddpg_impl.py:268-273).  Nothing is
+        stepped."""
+        db = self.load_batch(batch)
+        self.zero_slots()
+        self._p_actor(db, step=False)
+        self.sync()
+        return self._slots[M_ACTOR].clone()
+
     def update_actor(self, batch) -> np.ndarray:
         db = self.load_batch(batch)
         self._tick(C_ACTOR)
         self.zero_slots()
-        saved = self._tau
         self._p_actor_no_sync(db)
         return self.read_slots()[M_ACTOR].copy()
 
