@@ -163,11 +163,25 @@ class Episode:
     def transitions(self) -> List[Transition]:
         return [Transition(self._ds, t) for t in range(*self._tr)]
 
+    def build_transitions(self) -> None:
+        """dataset.pyx:720-734: transitions are handles into the dataset's table, nothing to build."""
+
+    def compute_return(self):
+        """Sum of the episode's step rewards, the dropped last step of a timed-out episode included
+        (dataset.pyx:763-774)."""
+        return np.sum(self.rewards)
+
     def __len__(self):
         return self._tr[1] - self._tr[0]
 
     def size(self):
         return len(self)
+
+    def __getitem__(self, index):
+        return self.transitions[index]
+
+    def __iter__(self):
+        return iter(self.transitions)
 
     def get_observation_shape(self):
         return self._ds.get_observation_shape()
@@ -184,6 +198,9 @@ class MDPDataset:
         assert observations.dtype in (np.uint8, np.float32) or observations.ndim == 2
         if observations.dtype != np.uint8:
             observations = observations.astype(np.float32)
+        for a in (observations, actions, rewards, terminals):   # check nan (dataset.pyx:207-210); integers cannot be
+            a = np.asarray(a)
+            assert a.dtype.kind != "f" or not np.isnan(a).any()
         self._observations = np.ascontiguousarray(observations)
         actions = np.asarray(actions)
         if discrete_action is None:  # _check_discrete_action (dataset.pyx:119-122)
@@ -194,8 +211,80 @@ class MDPDataset:
         self._terminals = np.asarray(terminals, dtype=np.float32).reshape(-1)
         self._episode_terminals = self._terminals if episode_terminals is None else \
             np.asarray(episode_terminals, dtype=np.float32).reshape(-1)
+        self._rebuild()
+
+    def _rebuild(self) -> None:
+        """Transition table of the current step arrays; HBM replicas of the old arrays are dropped."""
         self._meta, self._ep_ranges = _transition_meta(self._terminals, self._episode_terminals)
         self._replays = {}
+
+    def build_episodes(self) -> None:
+        """dataset.pyx:575-590: episodes are views computed on access, nothing to build."""
+
+    def append(self, observations, actions, rewards, terminals, episode_terminals=None) -> None:
+        """dataset.pyx:424-485: new steps behind the existing ones; the transition table is rebuilt and the replay is
+        uploaded again on its next use."""
+        import warnings
+
+        observations, actions = np.asarray(observations), np.asarray(actions)
+        for observation, action in zip(observations, actions):
+            assert observation.shape == self.get_observation_shape(), \
+                f"Observation shape must be {self.get_observation_shape()}."
+            if self._discrete:
+                if int(action) >= self.get_action_size():
+                    warnings.warn(f"New action size is higher than {self.get_action_size()}.")
+            else:
+                assert action.shape == (self.get_action_size(),), f"Action size must be {self.get_action_size()}."
+        obs_dtype = self._observations.dtype
+        self._observations = np.ascontiguousarray(np.vstack([self._observations, observations]).astype(obs_dtype))
+        if self._discrete:
+            self._actions = np.hstack([self._actions, actions.reshape(-1)]).astype(np.int32)
+        else:
+            self._actions = np.vstack([self._actions, actions]).astype(np.float32)
+        if episode_terminals is None:
+            episode_terminals = terminals
+        own_episode_terminals = self._episode_terminals
+        self._rewards = np.hstack([self._rewards, np.asarray(rewards).reshape(-1)]).astype(np.float32)
+        self._terminals = np.hstack([self._terminals, np.asarray(terminals).reshape(-1)]).astype(np.float32)
+        self._episode_terminals = np.hstack([own_episode_terminals,
+                                             np.asarray(episode_terminals).reshape(-1)]).astype(np.float32)
+        self._rebuild()
+
+    def extend(self, dataset) -> None:
+        """dataset.pyx:487-505."""
+        assert self.is_action_discrete() == dataset.is_action_discrete(), "Dataset must have discrete action-space."
+        assert self.get_observation_shape() == dataset.get_observation_shape(), \
+            f"Observation shape must be {self.get_observation_shape()}"
+        self.append(dataset.observations, dataset.actions, dataset.rewards, dataset.terminals,
+                    dataset.episode_terminals)
+
+    def compute_stats(self):
+        """dataset.pyx:336-422: return / reward / action / observation statistics with the reference's keys."""
+        episode_returns = [episode.compute_return() for episode in self.episodes]
+        stats = {
+            "return": {"mean": np.mean(episode_returns), "std": np.std(episode_returns),
+                       "min": np.min(episode_returns), "max": np.max(episode_returns),
+                       "histogram": np.histogram(episode_returns, bins=20)},
+            "reward": {"mean": np.mean(self._rewards), "std": np.std(self._rewards), "min": np.min(self._rewards),
+                       "max": np.max(self._rewards), "histogram": np.histogram(self._rewards, bins=20)},
+        }
+        if not self._discrete:
+            stats["action"] = {"mean": np.mean(self.actions, axis=0), "std": np.std(self.actions, axis=0),
+                               "min": np.min(self.actions, axis=0), "max": np.max(self.actions, axis=0),
+                               "histogram": [np.histogram(self.actions[:, i], bins=20)
+                                             for i in range(self.get_action_size())]}
+        else:
+            freqs = [(self.actions == i).sum() for i in range(self.get_action_size())]
+            stats["action"] = {"histogram": [freqs, np.arange(self.get_action_size())]}
+        stats["observation"] = {"mean": np.mean(self.observations, axis=0), "std": np.std(self.observations, axis=0),
+                                "min": np.min(self.observations, axis=0), "max": np.max(self.observations, axis=0)}
+        return stats
+
+    def __getitem__(self, index):
+        return self.episodes[index]
+
+    def __iter__(self):
+        return iter(self.episodes)
 
     observations = property(lambda self: self._observations)
     actions = property(lambda self: self._actions)
