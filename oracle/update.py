@@ -806,6 +806,81 @@ class IQL(_Algo):
                 "actor_loss": float(a_loss.detach())}
 
 
+class AWAC(_Algo):
+    """AWAC._update (algos/awac.py:176-191) over AWACImpl (algos/torch/awac_impl.py:18-154), which is SACImpl with a
+    frozen temperature exp(log 1e-20), a NonSquashedNormalPolicy whose logstd is a parameter squashed into [-6, 0], and
+    an actor Adam with weight_decay 1e-4 (algos/awac.py:105).  Oracle only: the CUDA path for AWAC is not built yet
+    (DESIGN.md section 6b); this class and its golden case pin what that path has to reproduce."""
+
+    MIN_LOGSTD, MAX_LOGSTD = -6.0, 0.0
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99, tau=0.005,
+                 lam=1.0, n_action_samples=1, update_actor_interval=1, actor_weight_decay=1e-4, seed=0, policy=None,
+                 critics=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_non_squashed_normal_policy(obs, act, hidden, gen))
+        self.targ_q, self.targ_pi = clone_params(self.q, False), clone_params(self.pi, False)
+        self.critic_optim = make_adam(self.q, critic_lr)
+        self.actor_optim = torch.optim.Adam(list(self.pi.values()), lr=actor_lr, weight_decay=actor_weight_decay)
+        self.log_temp = torch.full((1, 1), math.log(1e-20))   # temp_learning_rate = 0 and never stepped
+        self.gamma, self.tau, self.lam, self.n, self.act = gamma, tau, lam, n_action_samples, act
+        self.update_actor_interval = update_actor_interval
+        self.grad_step = 0
+
+    def _dist(self, x):
+        return non_squashed_policy_dist(self.pi, x, self.MIN_LOGSTD, self.MAX_LOGSTD)
+
+    def compute_target(self, b: Batch, noise: Noise):
+        """SACImpl.compute_target (sac_impl.py:148-162) with GaussianDistribution.sample_with_log_prob
+        (distributions.py:52-57,83-84): a' = clamp(tanh(mu) + std * eps, -1, 1)."""
+        with torch.no_grad():
+            dist = self._dist(b.next_observations)
+            action = (dist.loc + noise.normal(*b.actions.shape) * dist.scale).clamp(-1.0, 1.0)
+            log_prob = dist.log_prob(action).sum(dim=-1, keepdim=True)
+            entropy = self.log_temp.exp() * log_prob
+            return q_target_continuous(self.targ_q, b.next_observations, action) - entropy
+
+    def compute_critic_loss(self, b: Batch, q_tpn):
+        return td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+
+    def compute_weights(self, b: Batch, noise: Noise):
+        """AWACImpl._compute_weights (awac_impl.py:118-154): softmax over the batch of (Q - V) / lam, times the batch
+        size; V(s) = mean over n sampled actions of min_e Q_e(s, a_n)."""
+        with torch.no_grad():
+            B = b.observations.shape[0]
+            q_values = q_continuous(self.q, b.observations, b.actions, "min")
+            dist = self._dist(b.observations)
+            acts_T = (dist.loc + noise.normal(self.n, B, self.act) * dist.scale).clamp(-1.0, 1.0)   # (n, B, A)
+            flat_actions = acts_T.transpose(0, 1).reshape(-1, self.act)
+            flat_obs = b.observations.view(B, 1, -1).expand(B, self.n, b.observations.shape[1]).reshape(B * self.n, -1)
+            v_values = q_continuous(self.q, flat_obs, flat_actions, "min").view(B, -1, 1).mean(dim=1)
+            adv = (q_values - v_values).view(-1)
+            return F.softmax(adv / self.lam, dim=0).view(-1, 1) * adv.numel()
+
+    def compute_actor_loss(self, b: Batch, noise: Noise):
+        log_probs = self._dist(b.observations).log_prob(b.actions).sum(dim=-1, keepdim=True)
+        return -(log_probs * self.compute_weights(b, noise)).sum()
+
+    def _update(self, b, noise):
+        self.critic_optim.zero_grad()
+        loss = self.compute_critic_loss(b, self.compute_target(b, noise))
+        loss.backward()
+        self.critic_optim.step()
+        m = {"critic_loss": float(loss.detach())}
+        if self.grad_step % self.update_actor_interval == 0:
+            self.actor_optim.zero_grad()
+            a_loss = self.compute_actor_loss(b, noise)
+            a_loss.backward()
+            self.actor_optim.step()
+            logstd = self.MIN_LOGSTD + torch.sigmoid(self.pi["_logstd"]) * (self.MAX_LOGSTD - self.MIN_LOGSTD)
+            m["actor_loss"], m["mean_std"] = float(a_loss.detach()), float(logstd.exp().mean().detach())
+            soft_sync(self.targ_q, self.q, self.tau)
+            soft_sync(self.targ_pi, self.pi, self.tau)
+        return m
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

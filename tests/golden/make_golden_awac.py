@@ -1,0 +1,56 @@
+"""Golden fixture for AWAC, recorded from the LIVE unmodified reference like
+tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
+(oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
+batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
+
+    python tests/golden/make_golden_awac.py        (build container only: needs /root/reference)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden as mg  # noqa: E402
+
+oupdate = mg.oupdate
+
+
+def main():
+    from d3rlpy.algos import AWAC
+    from d3rlpy.models.encoders import VectorEncoderFactory
+
+    out, cases = {}, []
+    rs = np.random.RandomState(51)
+    for name, n_samples, interval, lam, seed in (("awac", 1, 1, 1.0, 61), ("awac_n4", 4, 2, 0.5, 62)):
+        O, A, B, steps = 6, 3, 16, 4
+        o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+        trs = mg.ref_transitions(o, a, r, t)
+        torch.manual_seed(seed)
+        enc = VectorEncoderFactory([32, 32])
+        algo = AWAC(actor_encoder_factory=enc, critic_encoder_factory=enc, batch_size=B, n_steps=2,
+                    n_action_samples=n_samples, update_actor_interval=interval, lam=lam)
+        algo.create_impl((O,), A)
+        impl = algo._impl
+        init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy)}
+        orc = oupdate.AWAC(O, A, critics=init["q"], policy=init["pi"], n_action_samples=n_samples,
+                           update_actor_interval=interval, lam=lam)
+        batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+        metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+        final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "targ_q": mg.sd(impl._targ_q_func),
+                 "targ_pi": mg.sd(impl._targ_policy)}
+        for g, p in (("q", orc.q), ("pi", orc.pi), ("targ_q", orc.targ_q), ("targ_pi", orc.targ_pi)):
+            mg.assert_params_close(final[g], p, f"{name} {g}")
+        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, n_action_samples=n_samples,
+                                     update_actor_interval=interval, lam=lam), init,
+                     [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+        cases.append(name)
+    out["cases"] = np.array(cases)
+    np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)
+    print("update_awac.npz:", cases)
+
+
+if __name__ == "__main__":
+    main()

@@ -60,3 +60,8 @@ def load_online():
 def load_scalers():
     """Observation / action / reward scaler fixtures (tests/golden/make_golden_scalers.py)."""
     return np.load(os.path.join(GOLDEN, "scalers.npz"))
+
+
+def load_awac():
+    """AWAC fixtures (tests/golden/make_golden_awac.py); oracle-only until the CUDA path exists."""
+    return np.load(os.path.join(GOLDEN, "update_awac.npz"))

@@ -118,3 +118,25 @@ def test_online_replay_matches_reference_golden():
                     assert np.array_equal(got[k], ref[k]), (name, j, k)
             n += 1
         assert n >= 10
+
+
+@pytest.mark.parametrize("name", ["awac", "awac_n4"])
+def test_awac_oracle_matches_reference_golden(name):
+    """AWAC is pinned ahead of its CUDA path: oracle/update.py:AWAC against the unmodified
+    reference's metrics and post-step parameters (actor Adam with weight decay, batch-softmax weights, delayed actor)."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), name)
+    c = case.cfg
+    algo = oupdate.AWAC(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"), policy=case.group("init", "pi"),
+                        n_action_samples=int(c["n_action_samples"]),
+                        update_actor_interval=int(c["update_actor_interval"]), lam=float(c["lam"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), oupdate.Noise(injected=case.noise(s)))
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref), (s, set(m), set(ref))
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (name, s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
