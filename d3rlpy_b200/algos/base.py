@@ -380,12 +380,22 @@ class AlgoBase:
 
     # ------------------------------------------------------------------ fit over an HBM-resident replay
     def fit(self, dataset, n_epochs: Optional[int] = None, n_steps: Optional[int] = None,
-            n_steps_per_epoch: int = 10000, shuffle: bool = True, seed: Optional[int] = None,
-            verbose: bool = False) -> List[Dict[str, float]]:
-        """Minimal `fit()` (base.py:349-687 without logger/scorers).  `n_steps` selects the RandomIterator index stream
-        (one `np.random.randint` per sample, iterators/random_iterator.py:38-41), `n_epochs` the RoundIterator one
-        (per epoch a `np.random.shuffle`d permutation cut into len//batch_size consecutive batches, the remainder
-        dropped, iterators/round_iterator.py:39-55) -> device gather -> update.  Returns the per-epoch metric means."""
+            n_steps_per_epoch: int = 10000, **kwargs: Any):
+        """LearnableBase.fit (base.py:349-434): `list(self.fitter(...))` -- one `(epoch, metrics)` pair per epoch."""
+        return list(self.fitter(dataset, n_epochs, n_steps, n_steps_per_epoch, **kwargs))
+
+    def fitter(self, dataset, n_epochs: Optional[int] = None, n_steps: Optional[int] = None,
+               n_steps_per_epoch: int = 10000, shuffle: bool = True, seed: Optional[int] = None,
+               eval_episodes=None, scorers: Optional[Dict[str, Any]] = None, callback=None, **unused: Any):
+        """LearnableBase.fitter (base.py:436-687) without the logger: a generator over epochs yielding
+        `(epoch, metrics)`, metrics = the epoch's mean of every loss `update` returned plus one entry per scorer
+        (`scorer(algo, eval_episodes)`, base.py:760-771); `callback(algo, epoch, total_step)` runs after every step.
+        `n_steps` selects the RandomIterator index stream (one `np.random.randint` per sample,
+        iterators/random_iterator.py:38-41), `n_epochs` the RoundIterator one (per epoch a `np.random.shuffle`d
+        permutation cut into len // batch_size consecutive batches, the remainder dropped,
+        iterators/round_iterator.py:39-55) -> device gather -> update.  `seed` (ours) draws the index stream from a
+        private RandomState instead of numpy's global one; the reference's logging arguments are accepted and
+        ignored."""
         if (n_epochs is None) == (n_steps is None):
             raise ValueError("Either of n_epochs or n_steps must be given.")  # base.py:548-549
         subset = None
@@ -410,26 +420,36 @@ class AlgoBase:
         self.build_with_dataset(dataset)
         replay = dataset.device_replay(self._impl._device)
         rng = np.random if seed is None else np.random.RandomState(seed)
-        history: List[Dict[str, float]] = []
         B = self._batch_size
         n = len(replay) if subset is None else len(subset)
         pick = (lambda idx: idx) if subset is None else (lambda idx: subset._t_index[idx])
         if n_steps is not None:
             assert n_steps >= n_steps_per_epoch  # base.py:523
-            for _ in range(n_steps // n_steps_per_epoch):
-                history.append(self._fit_epoch(replay, pick(random_iterator_indices(rng, n, n_steps_per_epoch, B))))
+            n_epochs = n_steps // n_steps_per_epoch
+            draw = lambda: random_iterator_indices(rng, n, n_steps_per_epoch, B)   # noqa: E731
         else:
-            for _ in range(n_epochs):
-                history.append(self._fit_epoch(replay, pick(round_iterator_indices(rng, n, B, shuffle))))
-        return history
+            draw = lambda: round_iterator_indices(rng, n, B, shuffle)              # noqa: E731
+        progress = {"epoch": 0, "total_step": 0}
 
-    def _fit_epoch(self, replay, idx: np.ndarray) -> Dict[str, float]:
+        def after_step():
+            progress["total_step"] += 1
+            callback(self, progress["epoch"], progress["total_step"])
+
+        for epoch in range(1, n_epochs + 1):
+            progress["epoch"] = epoch
+            metrics = self._fit_epoch(replay, pick(draw()), after_step if callback else None)
+            if scorers and eval_episodes:
+                for name, scorer in scorers.items():
+                    metrics[name] = scorer(self, eval_episodes)
+            yield epoch, metrics
+
+    def _fit_epoch(self, replay, idx: np.ndarray, after_step=None) -> Dict[str, float]:
         """One epoch over the index matrix [steps, batch_size]; the epoch's metric means (base.py:660-676)."""
         from ..dataset import TransitionMiniBatch
 
         impl, B = self._impl, self._batch_size
         if (not replay.is_image) and (not replay.discrete) and self._n_frames == 1:
-            acc = self._fit_chunk_device(replay, idx)
+            acc = self._fit_chunk_device(replay, idx, after_step)
         else:
             acc: Dict[str, List[float]] = {}
             for i in range(idx.shape[0]):
@@ -440,9 +460,11 @@ class AlgoBase:
                 batch.scaled = {"obs", "act_rew"}
                 for k, v in self.update(batch).items():
                     acc.setdefault(k, []).append(float(v))
+                if after_step:
+                    after_step()
         return {k: float(np.mean(v)) for k, v in acc.items()}
 
-    def _fit_chunk_device(self, replay, idx: np.ndarray) -> Dict[str, List[float]]:
+    def _fit_chunk_device(self, replay, idx: np.ndarray, after_step=None) -> Dict[str, List[float]]:
         """Vector observations: the chunk's indices are uploaded once; every step is one gather launch + one graph
         replay + one 256-byte device-side copy of the metric slots; metrics come back with ONE D2H per chunk
         (the reference syncs on every loss)."""
@@ -472,6 +494,8 @@ class AlgoBase:
             names_per_step.append(self._update_async(holder))
             self._grad_step += 1
             L.copy_d2d(hist.data_ptr() + 256 * i, impl._slots.data_ptr(), 256, st)
+            if after_step:
+                after_step()
         impl.sync()
         h = hist.cpu().numpy()
         acc: Dict[str, List[float]] = {}

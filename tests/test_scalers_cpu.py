@@ -228,3 +228,62 @@ def test_online_setup_fits_scalers_from_the_environment():
     with pytest.raises(NotImplementedError):
         _setup_algo(algo, env)
     _setup_algo(SimpleNamespace(scaler=pp.PixelScaler(), action_scaler=None, impl=object()), env)
+
+
+def test_fitter_epochs_callbacks_scorers_and_index_streams():
+    """LearnableBase.fitter / fit (base.py:349-687) control flow with the device work stubbed out: `(epoch, metrics)`
+    pairs, scorer entries merged into the metrics, `callback(algo, epoch, total_step)` after every step, the
+    RandomIterator / RoundIterator index streams (restricted to the list's transitions when a list is given)."""
+    from types import SimpleNamespace
+
+    from d3rlpy_b200.algos import CQL
+    from d3rlpy_b200.algos.base import random_iterator_indices, round_iterator_indices
+    from d3rlpy_b200.dataset import MDPDataset
+
+    z = load_scalers()
+    ds = MDPDataset(z["data/observations"], z["data/actions"], z["data/rewards"], z["data/terminals"],
+                    z["data/episode_terminals"])
+    n_tr = ds._meta.shape[0]
+
+    class Replay:
+        def __len__(self):
+            return n_tr
+
+    ds.device_replay = lambda device=None: Replay()
+
+    class Probe(CQL):
+        def build_with_dataset(self, dataset):
+            self._impl = SimpleNamespace(_device="cpu")
+
+        def _fit_epoch(self, replay, idx, after_step=None):
+            self.batches.append(np.array(idx))
+            for _ in range(idx.shape[0]):
+                self._grad_step += 1
+                if after_step:
+                    after_step()
+            return {"loss": float(idx.shape[0])}
+
+    algo = Probe(batch_size=8, use_gpu=None)
+    algo.batches, seen = [], []
+    out = algo.fit(ds, n_steps=12, n_steps_per_epoch=4, seed=3, eval_episodes=ds.episodes[:2],
+                   scorers={"n_eval": lambda a, eps: float(len(eps))},
+                   callback=lambda a, e, t: seen.append((e, t, a.grad_step)),
+                   save_metrics=False, experiment_name="ignored", verbose=False, show_progress=False)
+    assert [e for e, _ in out] == [1, 2, 3] and all(m == {"loss": 4.0, "n_eval": 2.0} for _, m in out)
+    assert seen == [(1 + (t - 1) // 4, t, t) for t in range(1, 13)]
+    rng = np.random.RandomState(3)
+    for got in algo.batches:
+        assert np.array_equal(got, random_iterator_indices(rng, n_tr, 4, 8))
+    # generator form: work happens epoch by epoch, as the caller pulls
+    algo = Probe(batch_size=8, use_gpu=None)
+    algo.batches = []
+    gen = algo.fitter(ds.episodes[1:4], n_epochs=2, seed=4)
+    assert algo.batches == []
+    epoch, metrics = next(gen)
+    assert epoch == 1 and len(algo.batches) == 1
+    assert [e for e, _ in gen] == [2] and len(algo.batches) == 2
+    sub = np.concatenate([[t._t for t in e.transitions] for e in ds.episodes[1:4]])
+    rng = np.random.RandomState(4)
+    for got in algo.batches:
+        want = sub[round_iterator_indices(rng, len(sub), 8, True)]
+        assert np.array_equal(got, want) and set(got.reshape(-1)) <= set(sub)

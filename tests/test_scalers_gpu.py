@@ -217,7 +217,7 @@ def test_fit_fits_and_applies_scalers():
             for k, v in b.update(host).items():
                 acc.setdefault(k, []).append(float(v))
         for k, v in acc.items():
-            assert abs(hist[epoch][k] - np.mean(v)) <= 1e-5 * max(1.0, abs(np.mean(v))), (epoch, k)
+            assert abs(hist[epoch][1][k] - np.mean(v)) <= 1e-5 * max(1.0, abs(np.mean(v))), (epoch, k)
     # pixels + reward clipping (the Atari reproduction's pairing): rewards are scaled, frames left to the conv load
     from d3rlpy_b200.algos import DQN
     from d3rlpy_b200.preprocessing import ClipRewardScaler
@@ -270,4 +270,4 @@ def test_fit_over_an_episode_list_trains_on_those_transitions_only():
             for k, v in b.update(host).items():
                 acc.setdefault(k, []).append(float(v))
         for k, v in acc.items():
-            assert abs(hist[epoch][k] - np.mean(v)) <= 1e-5 * max(1.0, abs(np.mean(v))), (epoch, k)
+            assert abs(hist[epoch][1][k] - np.mean(v)) <= 1e-5 * max(1.0, abs(np.mean(v))), (epoch, k)

@@ -167,18 +167,23 @@ def test_update_from_device_gather_and_philox_noise_runs():
     ds = MDPDataset(rs.randn(S, O).astype(np.float32), rs.uniform(-1, 1, (S, A)).astype(np.float32),
                     rs.randn(S).astype(np.float32), (np.arange(S) % 1000 == 999).astype(np.float32))
     algo = CQL(actor_encoder_factory=[64, 64], critic_encoder_factory=[64, 64], batch_size=64, n_action_samples=4)
-    hist = algo.fit(ds, n_steps=20, n_steps_per_epoch=10, seed=0)
-    assert len(hist) == 2 and algo.grad_step == 20
-    for h in hist:
+    seen = []
+    hist = algo.fit(ds, n_steps=20, n_steps_per_epoch=10, seed=0,
+                    callback=lambda a, epoch, total_step: seen.append((epoch, total_step, a.grad_step)))
+    assert [e for e, _ in hist] == [1, 2] and algo.grad_step == 20      # (epoch, metrics) pairs, base.py:349-434
+    assert seen == [(1 + (i - 1) // 10, i, i) for i in range(1, 21)]    # callback after every step, base.py:655-657
+    for _, h in hist:
         assert set(h) == {"temp_loss", "temp", "alpha_loss", "alpha", "critic_loss", "actor_loss"}
         assert all(np.isfinite(v) for v in h.values())
-    assert hist[1]["temp"] < 1.0 and hist[1]["alpha"] != 1.0
+    assert hist[1][1]["temp"] < 1.0 and hist[1][1]["alpha"] != 1.0
     # RoundIterator mode (n_epochs): every epoch visits len // batch_size shuffled batches
     small = MDPDataset(rs.randn(2_000, O).astype(np.float32), rs.uniform(-1, 1, (2_000, A)).astype(np.float32),
                        rs.randn(2_000).astype(np.float32), (np.arange(2_000) % 500 == 499).astype(np.float32))
     algo2 = CQL(actor_encoder_factory=[64, 64], critic_encoder_factory=[64, 64], batch_size=64, n_action_samples=4)
-    hist2 = algo2.fit(small, n_epochs=2, seed=0)
-    assert len(hist2) == 2 and algo2.grad_step == 2 * (len(small.device_replay(algo2.impl._device)) // 64)
+    hist2 = list(algo2.fitter(small, n_epochs=2, seed=0, eval_episodes=small.episodes[:1],
+                              scorers={"n_eval": lambda a, eps: float(len(eps))}))
+    assert [e for e, _ in hist2] == [1, 2] and hist2[0][1]["n_eval"] == 1.0
+    assert algo2.grad_step == 2 * (len(small.device_replay(algo2.impl._device)) // 64)
     with pytest.raises(ValueError):
         algo2.fit(small)
 
