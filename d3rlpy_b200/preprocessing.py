@@ -92,6 +92,7 @@ class StandardScaler(_Scaler):
 
     def affine_f32(self):
         """(subtrahend, divisor, eps) of `(x - s) / (d + eps)` as the kernels take them."""
+        assert self._mean is not None and self._std is not None, "standard scaler is not fitted"   # scalers.py:351
         return (np.asarray(self._mean, np.float32).reshape(-1), np.asarray(self._std, np.float32).reshape(-1),
                 float(self._eps))
 
@@ -128,6 +129,7 @@ class MinMaxScaler(_Scaler):
         self._maximum = np.asarray(env.observation_space.high).reshape((1,) + shape)
 
     def affine_f32(self):
+        assert self._minimum is not None and self._maximum is not None, "min_max scaler is not fitted"   # scalers.py:210
         mn = np.asarray(self._minimum, np.float32).reshape(-1)
         mx = np.asarray(self._maximum, np.float32).reshape(-1)
         return mn, mx - mn, 0.0
@@ -171,6 +173,7 @@ class MinMaxActionScaler(_Scaler):
         self._maximum = np.asarray(env.action_space.high).reshape((1,) + shape)
 
     def bounds_f32(self):
+        assert self._minimum is not None and self._maximum is not None, "action scaler is not fitted"   # action_scalers.py:186
         return (np.asarray(self._minimum, np.float32).reshape(-1), np.asarray(self._maximum, np.float32).reshape(-1))
 
     def get_params(self, deep: bool = False) -> Dict[str, Any]:
@@ -240,6 +243,7 @@ class MinMaxRewardScaler(_RewardScaler):
         self._minimum, self._maximum = float(np.min(rewards)), float(np.max(rewards))
 
     def constants(self):
+        assert self._minimum is not None and self._maximum is not None, "reward scaler is not fitted"   # reward_scalers.py:262
         return (-np.inf, np.inf, float(self._minimum), float(self._multiplier), float(self._maximum - self._minimum))
 
     def get_params(self, deep: bool = False) -> Dict[str, Any]:
@@ -267,6 +271,7 @@ class StandardRewardScaler(_RewardScaler):
         self._mean, self._std = float(np.mean(rewards)), float(np.std(rewards))
 
     def constants(self):
+        assert self._mean is not None and self._std is not None, "reward scaler is not fitted"   # reward_scalers.py:357
         return (-np.inf, np.inf, float(self._mean), float(self._multiplier), float(self._std + self._eps))
 
     def get_params(self, deep: bool = False) -> Dict[str, Any]:
@@ -301,6 +306,7 @@ class ReturnBasedRewardScaler(_RewardScaler):
         self._return_max, self._return_min = float(np.max(returns)), float(np.min(returns))
 
     def constants(self):
+        assert self._return_max is not None and self._return_min is not None, "reward scaler is not fitted"   # :471
         return (-np.inf, np.inf, 0.0, float(self._multiplier), float(self._return_max - self._return_min))
 
     def get_params(self, deep: bool = False) -> Dict[str, Any]:
