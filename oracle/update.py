@@ -881,6 +881,83 @@ class AWAC(_Algo):
         return m
 
 
+class CRR(_Algo):
+    """CRR._update (algos/crr.py:226-244) over CRRImpl (algos/torch/crr_impl.py:17-191): DDPG-style critic step against
+    a target action sampled from the TARGET policy, advantage-weighted Gaussian log-likelihood actor step (binary or
+    clipped-exponential weights; state value = mean or max of Q over n sampled actions), hard or soft target updates.
+    The policy is NonSquashedNormalPolicy with a logstd HEAD clamped to [-20, 2] (builders default), i.e. the same
+    parameter layout as the squashed policy.  Oracle only: the CUDA path for CRR is not built yet."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=1, actor_lr=3e-4, critic_lr=3e-4, gamma=0.99, beta=1.0,
+                 n_action_samples=4, advantage_type="mean", weight_type="exp", max_weight=20.0,
+                 target_update_type="hard", tau=5e-3, target_update_interval=100, seed=0, policy=None, critics=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_squashed_normal_policy(obs, act, hidden, gen))
+        self.targ_q, self.targ_pi = clone_params(self.q, False), clone_params(self.pi, False)
+        self.critic_optim, self.actor_optim = make_adam(self.q, critic_lr), make_adam(self.pi, actor_lr)
+        self.gamma, self.beta, self.n, self.act = gamma, beta, n_action_samples, act
+        self.advantage_type, self.weight_type, self.max_weight = advantage_type, weight_type, max_weight
+        self.target_update_type, self.tau, self.target_update_interval = target_update_type, tau, target_update_interval
+        self.grad_step = 0
+
+    @staticmethod
+    def _dist(p: Params, x):
+        """NormalPolicy.dist with squash_distribution=False and a logstd head (policies.py:160-181)."""
+        h = mlp_forward(p, "_encoder.", x)
+        mu = F.linear(h, p["_mu.weight"], p["_mu.bias"])
+        logstd = F.linear(h, p["_logstd.weight"], p["_logstd.bias"]).clamp(-20.0, 2.0)
+        return torch.distributions.Normal(torch.tanh(mu), logstd.exp())
+
+    def compute_target(self, b: Batch, noise: Noise):
+        """crr_impl.py:143-153: a' = targ_policy.sample(s') = clamp(tanh(mu) + std * eps, -1, 1) (distributions.py:52-53)."""
+        with torch.no_grad():
+            dist = self._dist(self.targ_pi, b.next_observations)
+            action = (dist.loc + noise.normal(*b.actions.shape) * dist.scale).clamp(-1.0, 1.0)
+            return q_target_continuous(self.targ_q, b.next_observations, action.clamp(-1.0, 1.0))
+
+    def compute_advantage(self, b: Batch, noise: Noise):
+        """crr_impl.py:104-141; `self._q_func(x, a)` reduces over members with the default "mean"."""
+        with torch.no_grad():
+            B = b.observations.shape[0]
+            dist = self._dist(self.pi, b.observations)
+            acts_T = (dist.loc + noise.normal(self.n, B, self.act) * dist.scale).clamp(-1.0, 1.0)
+            flat_actions = acts_T.transpose(0, 1).reshape(-1, self.act)
+            flat_obs = b.observations.view(B, 1, -1).expand(B, self.n, b.observations.shape[1]).reshape(B * self.n, -1)
+            reshaped = q_continuous(self.q, flat_obs, flat_actions, "mean").view(B, -1, 1)
+            values = reshaped.mean(dim=1) if self.advantage_type == "mean" else reshaped.max(dim=1).values
+            return q_continuous(self.q, b.observations, b.actions, "mean") - values
+
+    def compute_weight(self, b: Batch, noise: Noise):
+        adv = self.compute_advantage(b, noise)
+        if self.weight_type == "binary":
+            return (adv > 0.0).float()
+        return (adv / self.beta).exp().clamp(0.0, self.max_weight)
+
+    def compute_actor_loss(self, b: Batch, noise: Noise):
+        log_probs = self._dist(self.pi, b.observations).log_prob(b.actions).sum(dim=-1, keepdim=True)
+        return -(log_probs * self.compute_weight(b, noise)).mean()
+
+    def _update(self, b, noise):
+        self.critic_optim.zero_grad()
+        c_loss = td_error_continuous(self.q, b.observations, b.actions, b.rewards, self.compute_target(b, noise),
+                                     b.terminals, self.gamma ** b.n_steps)
+        c_loss.backward()
+        self.critic_optim.step()
+        self.actor_optim.zero_grad()
+        a_loss = self.compute_actor_loss(b, noise)
+        a_loss.backward()
+        self.actor_optim.step()
+        if self.target_update_type == "hard":
+            if self.grad_step % self.target_update_interval == 0:
+                hard_sync(self.targ_q, self.q)
+                hard_sync(self.targ_pi, self.pi)
+        else:
+            soft_sync(self.targ_q, self.q, self.tau)
+            soft_sync(self.targ_pi, self.pi, self.tau)
+        return {"critic_loss": float(c_loss.detach()), "actor_loss": float(a_loss.detach())}
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

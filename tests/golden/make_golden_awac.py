@@ -1,4 +1,4 @@
-"""Golden fixture for AWAC, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC and CRR, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -47,6 +47,38 @@ def main():
                                      update_actor_interval=interval, lam=lam), init,
                      [mg.batch_arrays(b) for b in batches], noises, metrics, final)
         cases.append(name)
+    # ---- CRR: hard target copies every 2 steps with exp weights / mean advantage; soft targets with binary / max
+    from d3rlpy.algos import CRR
+
+    for name, kw, seed in (("crr", dict(target_update_type="hard", target_update_interval=2, beta=0.5, max_weight=4.0,
+                                        n_action_samples=3), 63),
+                           ("crr_binary_max_soft", dict(target_update_type="soft", weight_type="binary",
+                                                        advantage_type="max", n_critics=2), 64)):
+        O, A, B, steps = 6, 3, 16, 4
+        o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+        trs = mg.ref_transitions(o, a, r, t)
+        torch.manual_seed(seed)
+        enc = VectorEncoderFactory([32, 32])
+        algo = CRR(actor_encoder_factory=enc, critic_encoder_factory=enc, batch_size=B, n_steps=2, **kw)
+        algo.create_impl((O,), A)
+        impl = algo._impl
+        init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy)}
+        okw = {k: v for k, v in kw.items() if k != "n_critics"}
+        orc = oupdate.CRR(O, A, critics=init["q"], policy=init["pi"], **okw)
+        batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+        metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+        final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "targ_q": mg.sd(impl._targ_q_func),
+                 "targ_pi": mg.sd(impl._targ_policy)}
+        for g, p in (("q", orc.q), ("pi", orc.pi), ("targ_q", orc.targ_q), ("targ_pi", orc.targ_pi)):
+            mg.assert_params_close(final[g], p, f"{name} {g}")
+        cfg = dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, hard=float(kw["target_update_type"] == "hard"),
+                   target_update_interval=kw.get("target_update_interval", 100), beta=kw.get("beta", 1.0),
+                   max_weight=kw.get("max_weight", 20.0), n_action_samples=kw.get("n_action_samples", 4),
+                   binary=float(kw.get("weight_type", "exp") == "binary"),
+                   adv_max=float(kw.get("advantage_type", "mean") == "max"))
+        mg.pack_case(name, out, cfg, init, [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+        cases.append(name)
+
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)
     print("update_awac.npz:", cases)

@@ -140,3 +140,24 @@ def test_awac_oracle_matches_reference_golden(name):
     for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
+
+
+@pytest.mark.parametrize("name", ["crr", "crr_binary_max_soft"])
+def test_crr_oracle_matches_reference_golden(name):
+    """CRR, pinned ahead of its CUDA path like AWAC: both weight types, both advantage types, hard and soft targets."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), name)
+    c = case.cfg
+    algo = oupdate.CRR(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"), policy=case.group("init", "pi"),
+                       beta=float(c["beta"]), n_action_samples=int(c["n_action_samples"]),
+                       advantage_type="max" if c["adv_max"] else "mean", weight_type="binary" if c["binary"] else "exp",
+                       max_weight=float(c["max_weight"]), target_update_type="hard" if c["hard"] else "soft",
+                       target_update_interval=int(c["target_update_interval"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), oupdate.Noise(injected=case.noise(s)))
+        for k, v in case.step_metrics(s).items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (name, s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
