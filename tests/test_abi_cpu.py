@@ -26,6 +26,16 @@ def test_error_convention_no_exceptions_across_boundary():
         L.adam_step(None, None, None, None, None, -1, None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, None)
     with pytest.raises(D3BError, match="out_features"):
         L.head_forward(None, 0, 0, None, 0, 0, None, 0, None, 0, 0, 4, 64, 8, 1, 0, None)
+    with pytest.raises(D3BError, match="empty clip interval or zero divisor"):
+        L.scale_rewards(1, 4, 1.0, -1.0, 0.0, 1.0, 1.0, None)          # lo > hi
+    with pytest.raises(D3BError, match="empty clip interval or zero divisor"):
+        L.scale_rewards(1, 4, -1.0, 1.0, 0.0, 1.0, 0.0, None)          # a degenerate (max == min) reward scaler
+    with pytest.raises(D3BError, match="null pointer"):
+        L.scale_actions(None, None, None, 4, 3, None)
+    with pytest.raises(D3BError, match="bad sizes"):
+        L.unscale_actions(None, None, None, 4, 0, None)
+    assert L.scale_rewards(None, 0, -1.0, 1.0, 0.0, 1.0, 1.0, None) == 0
+    assert L.scale_actions(None, None, None, 0, 3, None) == 0
     # zero-sized work is a no-op, not an error
     assert L.gather_vector(None, 4, None, 2, 0, None, None, None, 0, 1, 0.99, None, None, None, None, None, None, None,
                            None, 0.0, None) == 0
