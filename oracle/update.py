@@ -958,6 +958,63 @@ class CRR(_Algo):
         return {"critic_loss": float(c_loss.detach()), "actor_loss": float(a_loss.detach())}
 
 
+class PLAS(_Algo):
+    """PLAS._update (algos/plas.py:189-206) over PLASImpl (algos/torch/plas_impl.py:25-168): a conditional VAE trained
+    alone for `warmup_steps`, then TD3-style steps whose actions are decode(s, 2 * pi(s)) with a deterministic policy
+    over the 2A-dimensional latent; the target mixes min / max over members with `lam`.  Oracle only."""
+
+    def __init__(self, obs, act, hidden=(256, 256), vae_hidden=(256, 256), n_critics=2, actor_lr=1e-4, critic_lr=1e-3,
+                 imitator_lr=1e-4, gamma=0.99, tau=0.005, lam=0.75, beta=0.5, update_actor_interval=1,
+                 warmup_steps=500000, seed=0, policy=None, critics=None, imitator=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.imitator = clone_params(imitator if imitator is not None else make_cvae(obs, act, 2 * act, vae_hidden, gen))
+        self.q = clone_params(critics if critics is not None else make_critics(obs, act, hidden, n_critics, gen))
+        self.pi = clone_params(policy if policy is not None else make_deterministic_policy(obs, 2 * act, hidden, gen))
+        self.targ_q, self.targ_pi = clone_params(self.q, False), clone_params(self.pi, False)
+        self.critic_optim, self.actor_optim = make_adam(self.q, critic_lr), make_adam(self.pi, actor_lr)
+        self.imitator_optim = make_adam(self.imitator, imitator_lr)
+        self.gamma, self.tau, self.lam, self.beta, self.act = gamma, tau, lam, beta, act
+        self.update_actor_interval, self.warmup_steps = update_actor_interval, warmup_steps
+        self.grad_step = 0
+
+    def compute_target(self, b: Batch):
+        with torch.no_grad():
+            actions = vae_decode(self.imitator, b.next_observations, 2.0 * deterministic_policy(self.targ_pi, b.next_observations))
+            return q_continuous(self.targ_q, b.next_observations, actions, "mix", self.lam)
+
+    def compute_actor_loss(self, b: Batch):
+        actions = vae_decode(self.imitator, b.observations, 2.0 * deterministic_policy(self.pi, b.observations))
+        return -q_continuous(self.q, b.observations, actions, "none")[0].mean()
+
+    def _update(self, b, noise):
+        m = {}
+        if self.grad_step < self.warmup_steps:
+            self.imitator_optim.zero_grad()
+            loss = vae_error(self.imitator, b.observations, b.actions,
+                             noise.normal(b.observations.shape[0], 2 * self.act), self.beta)
+            loss.backward()
+            self.imitator_optim.step()
+            m["imitator_loss"] = float(loss.detach())
+            return m
+        self.critic_optim.zero_grad()
+        c_loss = td_error_continuous(self.q, b.observations, b.actions, b.rewards, self.compute_target(b), b.terminals,
+                                     self.gamma ** b.n_steps)
+        c_loss.backward()
+        self.critic_optim.step()
+        m["critic_loss"] = float(c_loss.detach())
+        if self.grad_step % self.update_actor_interval == 0:
+            self.actor_optim.zero_grad()
+            a_loss = self.compute_actor_loss(b)
+            a_loss.backward()
+            for v in list(self.q.values()) + list(self.imitator.values()):
+                v.grad = None
+            self.actor_optim.step()
+            m["actor_loss"] = float(a_loss.detach())
+            soft_sync(self.targ_pi, self.pi, self.tau)
+            soft_sync(self.targ_q, self.q, self.tau)
+        return m
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

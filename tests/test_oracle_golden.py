@@ -161,3 +161,24 @@ def test_crr_oracle_matches_reference_golden(name):
     for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
+
+
+def test_plas_oracle_matches_reference_golden():
+    """PLAS, pinned ahead of its CUDA path: VAE warm-up steps, then latent-policy TD3 steps with the min/max mix target."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), "plas")
+    c = case.cfg
+    algo = oupdate.PLAS(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"), policy=case.group("init", "pi"),
+                        imitator=case.group("init", "imitator"), warmup_steps=int(c["warmup_steps"]),
+                        update_actor_interval=int(c["update_actor_interval"]), lam=float(c["lam"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), oupdate.Noise(injected=case.noise(s)))
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref), (s, set(m), set(ref))
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("imitator", algo.imitator), ("targ_q", algo.targ_q),
+                        ("targ_pi", algo.targ_pi)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
