@@ -1015,6 +1015,128 @@ class PLAS(_Algo):
         return m
 
 
+def max_with_n_actions_and_indices(targ_q: Params, x, actions, lam):
+    """compute_max_with_n_actions_and_indices (q_functions/__init__.py:8-63): x (B, O), actions (B, N, A) -> per sample
+    the lam-mix of the members' min / max value at the action maximising that mix, and the action's index."""
+    B, N = actions.shape[0], actions.shape[1]
+    flat_x = x.expand(N, *x.shape).transpose(0, 1).reshape(-1, x.shape[1])
+    vals = q_continuous(targ_q, flat_x, actions.reshape(B * N, -1), "none")   # (E, B*N, 1)
+    E = vals.shape[0]
+    values = vals.view(E, B, N, -1).transpose(0, 1)                            # (B, E, N, 1)
+    mean_values = values.mean(dim=3)
+    max_values, max_idx = mean_values.max(dim=1)
+    min_values, min_idx = mean_values.min(dim=1)
+    action_idx = ((1.0 - lam) * max_values + lam * min_values).argmax(dim=1)
+    flat_values = values.transpose(1, 2).reshape(B * N, E, -1)
+    bn = torch.arange(B * N)
+    mx = flat_values[bn, max_idx.reshape(-1)].view(B, N, -1)
+    mn = flat_values[bn, min_idx.reshape(-1)].view(B, N, -1)
+    return ((1.0 - lam) * mx + lam * mn)[torch.arange(B), action_idx], action_idx
+
+
+class BEAR(CQL):
+    """BEAR._update (algos/bear.py:279-309) over BEARImpl (algos/torch/bear_impl.py:41-329), which extends SACImpl:
+    VAE step, temperature step, Lagrange step on the MMD constraint (log_alpha clamped to [-5, 10]), TD critic step
+    against the best of n target samples (lam-mix over members) minus the entropy term of that sample, then an actor
+    step on the MMD loss alone during warm-up and on SAC's loss + MMD loss afterwards.  MMD between n raw (pre-tanh)
+    policy samples and n raw decoder samples with a Laplacian or Gaussian kernel.  Oracle only.
+    Inherits the SAC pieces (update_temp, SAC actor loss) from the CQL oracle."""
+
+    def __init__(self, obs, act, hidden=(256, 256), vae_hidden=(256, 256), n_critics=2, actor_lr=1e-4, critic_lr=3e-4,
+                 imitator_lr=3e-4, temp_lr=1e-4, alpha_lr=1e-3, gamma=0.99, tau=0.005, initial_temperature=1.0,
+                 initial_alpha=1.0, alpha_threshold=0.05, lam=0.75, n_target_samples=10, n_mmd_action_samples=4,
+                 mmd_kernel="laplacian", mmd_sigma=20.0, vae_kl_weight=0.5, warmup_steps=40000, seed=0, policy=None,
+                 critics=None, imitator=None):
+        super().__init__(obs, act, hidden=hidden, n_critics=n_critics, actor_lr=actor_lr, critic_lr=critic_lr,
+                         temp_lr=temp_lr, alpha_lr=alpha_lr, gamma=gamma, tau=tau,
+                         initial_temperature=initial_temperature, initial_alpha=initial_alpha,
+                         alpha_threshold=alpha_threshold, n_action_samples=0, seed=seed, policy=policy, critics=critics)
+        gen = torch.Generator().manual_seed(seed + 1)
+        self.imitator = clone_params(imitator if imitator is not None else make_cvae(obs, act, 2 * act, vae_hidden, gen))
+        self.imitator_optim = make_adam(self.imitator, imitator_lr)
+        self.lam, self.n_target, self.n_mmd = lam, n_target_samples, n_mmd_action_samples
+        self.mmd_kernel, self.mmd_sigma, self.beta, self.warmup_steps = mmd_kernel, mmd_sigma, vae_kl_weight, warmup_steps
+
+    def compute_mmd(self, obs, noise: Noise):
+        """bear_impl.py:233-281; draw order: decoder latents (n*B, 2A), then policy eps (n, B, A)."""
+        B, n, A = obs.shape[0], self.n_mmd, self.act
+        with torch.no_grad():
+            latent = noise.normal(n * B, 2 * A).clamp(-0.5, 0.5)
+            flat_x = obs.expand(n, *obs.shape).reshape(-1, obs.shape[1])
+            h = mlp_forward(self.imitator, "_decoder_encoder.", torch.cat([flat_x, latent], dim=1))
+            behavior = F.linear(h, self.imitator["_fc.weight"], self.imitator["_fc.bias"]).view(n, B, -1).transpose(0, 1)
+        mu, std = policy_dist(self.pi, obs)
+        policy = (mu.unsqueeze(0) + noise.normal(n, B, A) * std.unsqueeze(0)).transpose(0, 1)
+        if self.mmd_kernel == "gaussian":
+            kernel = lambda x, y: (-((x - y) ** 2).sum(dim=3) / (2 * self.mmd_sigma)).exp()   # noqa: E731
+        else:
+            kernel = lambda x, y: (-(x - y).abs().sum(dim=3) / (2 * self.mmd_sigma)).exp()    # noqa: E731
+        b1, p1 = behavior.reshape(B, -1, 1, A), policy.reshape(B, -1, 1, A)
+        bT, pT = behavior.reshape(B, 1, -1, A), policy.reshape(B, 1, -1, A)
+        mmd = kernel(p1, pT).mean(dim=[1, 2])
+        mmd = mmd + kernel(b1, bT).mean(dim=[1, 2])
+        mmd = mmd - 2 * kernel(p1, bT).mean(dim=[1, 2])
+        return (mmd + 1e-6).sqrt().view(-1, 1)
+
+    def compute_mmd_loss(self, obs, noise: Noise):
+        alpha = self.log_alpha["_parameter"].exp()
+        return (alpha * (self.compute_mmd(obs, noise) - self.alpha_threshold)).mean()
+
+    def update_imitator(self, b, noise):
+        self.imitator_optim.zero_grad()
+        loss = vae_error(self.imitator, b.observations, b.actions, noise.normal(b.observations.shape[0], 2 * self.act),
+                         self.beta)
+        loss.backward()
+        self.imitator_optim.step()
+        return float(loss.detach())
+
+    def update_alpha(self, b, noise):
+        loss = -self.compute_mmd_loss(b.observations, noise)
+        self.alpha_optim.zero_grad()
+        loss.backward()
+        for v in self.pi.values():
+            v.grad = None
+        self.alpha_optim.step()
+        self.log_alpha["_parameter"].data.clamp_(-5.0, 10.0)
+        return float(loss.detach()), float(self.log_alpha["_parameter"].exp().detach()[0][0])
+
+    def compute_target(self, b, noise):
+        with torch.no_grad():
+            B = b.observations.shape[0]
+            actions, log_probs = policy_sample_n_with_log_prob(self.pi, b.next_observations,
+                                                               noise.normal(self.n_target, B, self.act))
+            values, idx = max_with_n_actions_and_indices(self.targ_q, b.next_observations, actions, self.lam)
+            return values - self.log_temp["_parameter"].exp() * log_probs[torch.arange(B), idx]
+
+    def compute_critic_loss(self, b, q_tpn, noise):
+        return td_error_continuous(self.q, b.observations, b.actions, b.rewards, q_tpn, b.terminals,
+                                   self.gamma ** b.n_steps)
+
+    def update_actor(self, b, noise):
+        self.actor_optim.zero_grad()
+        if self.grad_step < self.warmup_steps:
+            loss = self.compute_mmd_loss(b.observations, noise)
+        else:
+            loss = self.compute_actor_loss(b, noise) + self.compute_mmd_loss(b.observations, noise)
+        loss.backward()
+        for v in list(self.q.values()) + [self.log_temp["_parameter"], self.log_alpha["_parameter"]]:
+            v.grad = None
+        self.actor_optim.step()
+        return float(loss.detach())
+
+    def _update(self, b, noise):
+        m = {"imitator_loss": self.update_imitator(b, noise)}
+        if self.temp_lr > 0:
+            m["temp_loss"], m["temp"] = self.update_temp(b, noise)
+        if self.alpha_lr > 0:
+            m["alpha_loss"], m["alpha"] = self.update_alpha(b, noise)
+        m["critic_loss"] = self.update_critic(b, noise)
+        m["actor_loss"] = self.update_actor(b, noise)
+        soft_sync(self.targ_pi, self.pi, self.tau)
+        soft_sync(self.targ_q, self.q, self.tau)
+        return m
+
+
 class BCQ(_Algo):
     """BCQ._update (algos/bcq.py:261-279) over BCQImpl (algos/torch/bcq_impl.py:132-226)."""
 

@@ -1,4 +1,4 @@
-"""Golden fixtures for AWAC, CRR and PLAS, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC, CRR, PLAS and BEAR, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -105,6 +105,37 @@ def main():
                                    update_actor_interval=2, lam=0.6), init,
                  [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     cases.append("plas")
+
+    # ---- BEAR: two warm-up actor steps (MMD only), then SAC + MMD; Laplacian and Gaussian kernels
+    from d3rlpy.algos import BEAR
+
+    for name, kernel, seed in (("bear", "laplacian", 66), ("bear_gaussian", "gaussian", 67)):
+        O, A, B, steps = 6, 3, 16, 4
+        o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+        trs = mg.ref_transitions(o, a, r, t)
+        torch.manual_seed(seed)
+        enc, venc = VectorEncoderFactory([32, 32]), VectorEncoderFactory([48, 48])
+        algo = BEAR(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=venc, batch_size=B,
+                    n_steps=2, warmup_steps=2, n_target_samples=3, n_mmd_action_samples=4, mmd_kernel=kernel,
+                    mmd_sigma=5.0, lam=0.6)
+        algo.create_impl((O,), A)
+        impl = algo._impl
+        init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "imitator": mg.sd(impl._imitator)}
+        orc = oupdate.BEAR(O, A, critics=init["q"], policy=init["pi"], imitator=init["imitator"], warmup_steps=2,
+                           n_target_samples=3, n_mmd_action_samples=4, mmd_kernel=kernel, mmd_sigma=5.0, lam=0.6)
+        batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+        metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+        final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "imitator": mg.sd(impl._imitator),
+                 "targ_q": mg.sd(impl._targ_q_func), "targ_pi": mg.sd(impl._targ_policy),
+                 "log_temp": mg.sd(impl._log_temp), "log_alpha": mg.sd(impl._log_alpha)}
+        for g, p in (("q", orc.q), ("pi", orc.pi), ("imitator", orc.imitator), ("targ_q", orc.targ_q),
+                     ("targ_pi", orc.targ_pi), ("log_temp", orc.log_temp), ("log_alpha", orc.log_alpha)):
+            mg.assert_params_close(final[g], p, f"{name} {g}")
+        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, v0=48, v1=48, warmup_steps=2,
+                                     n_target_samples=3, n_mmd_action_samples=4, gaussian=float(kernel == "gaussian"),
+                                     mmd_sigma=5.0, lam=0.6), init,
+                     [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+        cases.append(name)
 
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)

@@ -182,3 +182,27 @@ def test_plas_oracle_matches_reference_golden():
                         ("targ_pi", algo.targ_pi)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
+
+
+@pytest.mark.parametrize("name", ["bear", "bear_gaussian"])
+def test_bear_oracle_matches_reference_golden(name):
+    """BEAR, pinned ahead of its CUDA path: VAE / temperature / MMD-Lagrange / critic / (warm-up or full) actor steps."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), name)
+    c = case.cfg
+    algo = oupdate.BEAR(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"), policy=case.group("init", "pi"),
+                        imitator=case.group("init", "imitator"), warmup_steps=int(c["warmup_steps"]),
+                        n_target_samples=int(c["n_target_samples"]), n_mmd_action_samples=int(c["n_mmd_action_samples"]),
+                        mmd_kernel="gaussian" if c["gaussian"] else "laplacian", mmd_sigma=float(c["mmd_sigma"]),
+                        lam=float(c["lam"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), oupdate.Noise(injected=case.noise(s)))
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref), (s, set(m), set(ref))
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (name, s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("imitator", algo.imitator), ("targ_q", algo.targ_q),
+                        ("targ_pi", algo.targ_pi), ("log_temp", algo.log_temp), ("log_alpha", algo.log_alpha)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
