@@ -1,8 +1,9 @@
 """CPU oracle for the offline-RL update step.
 
-TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and
-bench.py's cpu_baseline / ``--impl reference`` legs; the product path
-(d3rlpy_b200) never imports it and has no CPU fallback.
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke(),
+bench.py's cpu_baseline / ``--impl reference`` legs and the baseline legs of the
+measurement scripts under profiles/ (as the thing the product is compared WITH);
+the product path (d3rlpy_b200) never imports it and has no CPU fallback.
 
 A plain-PyTorch (fp32, autograd, ``torch.optim.Adam``) restatement of what one
 ``algo.update(batch)`` of the reference computes, written functionally over
@@ -12,7 +13,8 @@ function cites the reference lines it follows (relative to /root/reference/).
 
 Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
 the reference.  Pinned against the live reference by
-tests/golden/update_*.npz (tests/golden/make_golden.py) — see DESIGN.md §oracle.
+tests/golden/update*.npz and scalers.npz (tests/golden/make_golden*.py) — see DESIGN.md §2.
+AWAC, CRR, PLAS and BEAR are restated and pinned here ahead of their CUDA paths.
 """
 from __future__ import annotations
 
