@@ -14,7 +14,7 @@ function cites the reference lines it follows (relative to /root/reference/).
 Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
 the reference.  Pinned against the live reference by
 tests/golden/update*.npz and scalers.npz (tests/golden/make_golden*.py) — see DESIGN.md §2.
-AWAC, CRR, PLAS and BEAR are restated and pinned here ahead of their CUDA paths.
+AWAC, CRR, PLAS, BEAR and DiscreteBCQ are restated and pinned here ahead of their CUDA paths.
 """
 from __future__ import annotations
 
@@ -1281,3 +1281,49 @@ class DiscreteCQL(_Algo):
         if self.grad_step % self.interval == 0:
             hard_sync(self.targ_q, self.q)
         return {"loss": float(loss.detach())}
+
+
+class DiscreteBCQ(DiscreteCQL):
+    """DiscreteBCQ (algos/bcq.py:390-420 `_update` = DQN's) over DiscreteBCQImpl (algos/torch/bcq_impl.py:228-330): Double
+    DQN whose greedy action is restricted to actions the behaviour-cloning head finds plausible
+    (log pi(a|s) - max_a log pi > log action_flexibility), plus that head's loss (NLL + beta * mean(logits^2)) in the same
+    objective and the same Adam.  Vector observations: the imitator has its own encoder (bcq_impl.py:276-282).
+    Oracle only: the CUDA path is not built yet."""
+
+    def __init__(self, obs_shape, act, n_critics=1, lr=6.25e-5, gamma=0.99, target_update_interval=8000,
+                 action_flexibility=0.3, beta=0.5, seed=0, critics=None, imitator=None, hidden=None):
+        super().__init__(obs_shape, act, n_critics=n_critics, lr=lr, gamma=gamma,
+                         target_update_interval=target_update_interval, seed=seed, critics=critics, hidden=hidden,
+                         double=True, conservative=False)
+        gen = torch.Generator().manual_seed(seed + 1)
+        if imitator is None:
+            h = hidden or [256, 256]
+            imitator = make_mlp("_encoder.", obs_shape[0], h, gen)
+            imitator.update(make_head("_fc", act, h[-1], gen))
+        self.imitator = clone_params(imitator)
+        self.flex, self.beta = action_flexibility, beta
+        self.optim = make_adam(OrderedDict(list(self.q.items()) + [("im." + k, v) for k, v in self.imitator.items()]), lr)
+
+    def _logits(self, x):
+        return F.linear(mlp_forward(self.imitator, "_encoder.", x), self.imitator["_fc.weight"], self.imitator["_fc.bias"])
+
+    def best_action(self, x):
+        log_probs = F.log_softmax(self._logits(x), dim=1)
+        ratio = log_probs - log_probs.max(dim=1, keepdim=True).values
+        mask = (ratio > math.log(self.flex)).float()
+        value = q_discrete(self.q, x)
+        normalized = value - value.min(dim=1, keepdim=True).values
+        return (normalized * mask).argmax(dim=1)
+
+    def compute_target(self, b):
+        with torch.no_grad():
+            action = self.best_action(b.next_observations)
+            vals = q_discrete(self.targ_q, b.next_observations, "none")
+            one_hot = F.one_hot(action.view(-1), num_classes=self.act).float()
+            return reduce_ensemble((vals * one_hot.unsqueeze(0)).sum(dim=2, keepdim=True), "min")
+
+    def compute_loss(self, b, q_tpn):
+        loss = super().compute_loss(b, q_tpn)
+        logits = self._logits(b.observations)
+        imitator_loss = F.nll_loss(F.log_softmax(logits, dim=1), b.actions.long().view(-1)) + self.beta * (logits ** 2).mean()
+        return loss + imitator_loss

@@ -1,4 +1,4 @@
-"""Golden fixtures for AWAC, CRR, PLAS and BEAR, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC, CRR, PLAS, BEAR and DiscreteBCQ, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -136,6 +136,35 @@ def main():
                                      mmd_sigma=5.0, lam=0.6), init,
                      [mg.batch_arrays(b) for b in batches], noises, metrics, final)
         cases.append(name)
+
+    # ---- DiscreteBCQ (vector observations: the imitator owns its encoder), target copied every 2 steps
+    from d3rlpy.algos import DiscreteBCQ
+
+    O, A, B, steps = 6, 4, 16, 4
+    o, a, r, t = mg.vector_dataset(rs, obs=O, act=A, discrete=True)
+    trs = mg.ref_transitions(o, a, r, t)
+    torch.manual_seed(68)
+    algo = DiscreteBCQ(encoder_factory=VectorEncoderFactory([32, 32]), batch_size=B, n_steps=2, n_critics=2,
+                       target_update_interval=2, action_flexibility=0.6, beta=0.3)
+    algo.create_impl((O,), A)
+    impl = algo._impl
+    init = {"q": mg.sd(impl._q_func), "imitator": mg.sd(impl._imitator)}
+    orc = oupdate.DiscreteBCQ((O,), A, critics=init["q"], imitator=init["imitator"], target_update_interval=2,
+                              action_flexibility=0.6, beta=0.3)
+    batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+    metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+    assert all(len(n) == 0 for n in noises)
+    final = {"q": mg.sd(impl._q_func), "imitator": mg.sd(impl._imitator), "targ_q": mg.sd(impl._targ_q_func)}
+    for g, p in (("q", orc.q), ("imitator", orc.imitator), ("targ_q", orc.targ_q)):
+        mg.assert_params_close(final[g], p, f"discrete_bcq {g}")
+    xe = o[:20]
+    greedy = algo.predict(xe)
+    assert np.array_equal(greedy, orc.best_action(torch.tensor(xe)).numpy())
+    mg.pack_case("discrete_bcq", out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, n_critics=2,
+                                           target_update_interval=2, action_flexibility=0.6, beta=0.3), init,
+                 [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+    out["discrete_bcq/eval_x"], out["discrete_bcq/predict"] = xe, greedy
+    cases.append("discrete_bcq")
 
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)

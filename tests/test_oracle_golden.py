@@ -206,3 +206,25 @@ def test_bear_oracle_matches_reference_golden(name):
                         ("targ_pi", algo.targ_pi), ("log_temp", algo.log_temp), ("log_alpha", algo.log_alpha)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (name, grp, k)
+
+
+def test_discrete_bcq_oracle_matches_reference_golden():
+    """DiscreteBCQ, pinned ahead of its CUDA path: Double-DQN target over the imitator-masked greedy action, joint loss."""
+    from tests.golden_io import load_awac
+
+    z = load_awac()
+    case = Case(z, "discrete_bcq")
+    c = case.cfg
+    algo = oupdate.DiscreteBCQ((int(c["obs"]),), int(c["act"]), critics=case.group("init", "q"),
+                               imitator=case.group("init", "imitator"),
+                               target_update_interval=int(c["target_update_interval"]),
+                               action_flexibility=float(c["action_flexibility"]), beta=float(c["beta"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), None)
+        for k, v in case.step_metrics(s).items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("imitator", algo.imitator), ("targ_q", algo.targ_q)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
+    with torch.no_grad():
+        assert np.array_equal(algo.best_action(torch.tensor(z["discrete_bcq/eval_x"])).numpy(), z["discrete_bcq/predict"])
