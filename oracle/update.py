@@ -14,7 +14,7 @@ function cites the reference lines it follows (relative to /root/reference/).
 Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
 the reference.  Pinned against the live reference by
 tests/golden/update*.npz and scalers.npz (tests/golden/make_golden*.py) — see DESIGN.md §2.
-AWAC, CRR, PLAS, BEAR and DiscreteBCQ are restated and pinned here ahead of their CUDA paths.
+AWAC, CRR, PLAS, BEAR, DiscreteBCQ and DiscreteSAC are restated and pinned here ahead of their CUDA paths.
 """
 from __future__ import annotations
 
@@ -1327,3 +1327,76 @@ class DiscreteBCQ(DiscreteCQL):
         logits = self._logits(b.observations)
         imitator_loss = F.nll_loss(F.log_softmax(logits, dim=1), b.actions.long().view(-1)) + self.beta * (logits ** 2).mean()
         return loss + imitator_loss
+
+
+class DiscreteSAC(_Algo):
+    """DiscreteSAC._update (algos/sac.py:373-392) over DiscreteSACImpl (algos/torch/sac_impl.py:165-420): categorical
+    policy, expectation-form soft target sum_a pi(a|s') (min_e Q'_e(s', a) - temp * log pi(a|s')), Huber critics,
+    temperature towards 0.98 * log |A|, hard target copy every `target_update_interval` steps; every Adam with
+    eps = 1e-4 (algos/sac.py:305-307).  `log_probs` is `Categorical(softmax(h)).logits`, i.e. log of the re-normalised,
+    eps-clamped probabilities (policies.py:303-306,350-352).  Oracle only: the CUDA path is not built yet."""
+
+    def __init__(self, obs, act, hidden=(256, 256), n_critics=2, actor_lr=3e-4, critic_lr=3e-4, temp_lr=3e-4, gamma=0.99,
+                 initial_temperature=1.0, target_update_interval=8000, adam_eps=1e-4, seed=0, policy=None, critics=None):
+        gen = torch.Generator().manual_seed(seed)
+        self.q = clone_params(critics if critics is not None
+                              else make_discrete_critics((obs,), act, n_critics, gen, list(hidden)))
+        if policy is None:
+            policy = make_mlp("_encoder.", obs, hidden, gen)
+            policy.update(make_head("_fc", act, hidden[-1], gen))
+        self.pi = clone_params(policy)
+        self.targ_q = clone_params(self.q, False)
+        self.log_temp = {"_parameter": torch.full((1, 1), math.log(initial_temperature)).requires_grad_(True)}
+        self.critic_optim = make_adam(self.q, critic_lr, eps=adam_eps)
+        self.actor_optim = make_adam(self.pi, actor_lr, eps=adam_eps)
+        self.temp_optim = make_adam(self.log_temp, temp_lr, eps=adam_eps)
+        self.temp_lr, self.gamma, self.interval, self.act = temp_lr, gamma, target_update_interval, act
+        self.grad_step = 0
+
+    def log_probs(self, x):
+        h = F.linear(mlp_forward(self.pi, "_encoder.", x), self.pi["_fc.weight"], self.pi["_fc.bias"])
+        return torch.distributions.Categorical(torch.softmax(h, dim=1)).logits
+
+    def update_temp(self, b):
+        self.temp_optim.zero_grad()
+        with torch.no_grad():
+            log_probs = self.log_probs(b.observations)
+            expct = (log_probs.exp() * log_probs).sum(dim=1, keepdim=True)
+            targ_temp = expct + 0.98 * (-math.log(1 / self.act))
+        loss = -(self.log_temp["_parameter"].exp() * targ_temp).mean()
+        loss.backward()
+        self.temp_optim.step()
+        return float(loss.detach()), float(self.log_temp["_parameter"].exp().detach()[0][0])
+
+    def compute_target(self, b):
+        with torch.no_grad():
+            log_probs = self.log_probs(b.next_observations)
+            entropy = self.log_temp["_parameter"].exp() * log_probs
+            target = q_discrete(self.targ_q, b.next_observations, "min")
+            return (log_probs.exp() * (target - entropy)).sum(dim=1, keepdim=True)
+
+    def compute_actor_loss(self, b):
+        with torch.no_grad():
+            q_t = q_discrete(self.q, b.observations, "min")
+        log_probs = self.log_probs(b.observations)
+        entropy = self.log_temp["_parameter"].exp() * log_probs
+        return (log_probs.exp() * (entropy - q_t)).sum(dim=1).mean()
+
+    def _update(self, b, noise=None):
+        m = {}
+        if self.temp_lr > 0:
+            m["temp_loss"], m["temp"] = self.update_temp(b)
+        self.critic_optim.zero_grad()
+        c_loss = td_error_discrete(self.q, b.observations, b.actions.long(), b.rewards, self.compute_target(b),
+                                   b.terminals, self.gamma ** b.n_steps)
+        c_loss.backward()
+        self.critic_optim.step()
+        self.actor_optim.zero_grad()
+        a_loss = self.compute_actor_loss(b)
+        a_loss.backward()
+        self.log_temp["_parameter"].grad = None
+        self.actor_optim.step()
+        if self.grad_step % self.interval == 0:
+            hard_sync(self.targ_q, self.q)
+        m["critic_loss"], m["actor_loss"] = float(c_loss.detach()), float(a_loss.detach())
+        return m

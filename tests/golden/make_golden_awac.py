@@ -1,4 +1,4 @@
-"""Golden fixtures for AWAC, CRR, PLAS, BEAR and DiscreteBCQ, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC, CRR, PLAS, BEAR, DiscreteBCQ and DiscreteSAC, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -165,6 +165,31 @@ def main():
                  [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     out["discrete_bcq/eval_x"], out["discrete_bcq/predict"] = xe, greedy
     cases.append("discrete_bcq")
+
+    # ---- DiscreteSAC: categorical policy, expectation-form soft target, Adam eps 1e-4, target copied every 2 steps
+    from d3rlpy.algos import DiscreteSAC
+
+    O, A, B, steps = 6, 4, 16, 4
+    o, a, r, t = mg.vector_dataset(rs, obs=O, act=A, discrete=True)
+    trs = mg.ref_transitions(o, a, r, t)
+    torch.manual_seed(69)
+    enc = VectorEncoderFactory([32, 32])
+    algo = DiscreteSAC(actor_encoder_factory=enc, critic_encoder_factory=enc, batch_size=B, n_steps=2,
+                       target_update_interval=2)
+    algo.create_impl((O,), A)
+    impl = algo._impl
+    init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy)}
+    orc = oupdate.DiscreteSAC(O, A, critics=init["q"], policy=init["pi"], target_update_interval=2)
+    batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+    metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+    assert all(len(n) == 0 for n in noises)
+    final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "targ_q": mg.sd(impl._targ_q_func),
+             "log_temp": mg.sd(impl._log_temp)}
+    for g, p in (("q", orc.q), ("pi", orc.pi), ("targ_q", orc.targ_q), ("log_temp", orc.log_temp)):
+        mg.assert_params_close(final[g], p, f"discrete_sac {g}")
+    mg.pack_case("discrete_sac", out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, target_update_interval=2),
+                 init, [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+    cases.append("discrete_sac")
 
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)

@@ -228,3 +228,23 @@ def test_discrete_bcq_oracle_matches_reference_golden():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
     with torch.no_grad():
         assert np.array_equal(algo.best_action(torch.tensor(z["discrete_bcq/eval_x"])).numpy(), z["discrete_bcq/predict"])
+
+
+def test_discrete_sac_oracle_matches_reference_golden():
+    """DiscreteSAC, pinned ahead of its CUDA path: temperature, Huber critics on the expectation-form soft target,
+    categorical actor, Adam eps = 1e-4, hard target copies."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), "discrete_sac")
+    c = case.cfg
+    algo = oupdate.DiscreteSAC(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"),
+                               policy=case.group("init", "pi"), target_update_interval=int(c["target_update_interval"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), None)
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref)
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("log_temp", algo.log_temp)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
