@@ -14,7 +14,8 @@ function cites the reference lines it follows (relative to /root/reference/).
 Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
 the reference.  Pinned against the live reference by
 tests/golden/update*.npz and scalers.npz (tests/golden/make_golden*.py) — see DESIGN.md §2.
-AWAC, CRR, PLAS, BEAR, DiscreteBCQ and DiscreteSAC are restated and pinned here ahead of their CUDA paths.
+AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC and TD3PlusRelation are restated and pinned here ahead of
+their CUDA paths.
 """
 from __future__ import annotations
 
@@ -1399,4 +1400,36 @@ class DiscreteSAC(_Algo):
         if self.grad_step % self.interval == 0:
             hard_sync(self.targ_q, self.q)
         m["critic_loss"], m["actor_loss"] = float(c_loss.detach()), float(a_loss.detach())
+        return m
+
+
+class TD3PlusRelation(TD3PlusBC):
+    """TD3PlusRelation._update (algos/td3_relational.py:176-192) over TD3PlusRelationImpl
+    (algos/torch/td3_relational_impl.py:17-96) -- the algorithm this fork adds: TD3+BC's schedule and lambda-normalised
+    -Q term, with the cloning term replaced by a batch-relational distillation loss between the B x B similarity
+    matrices  a_data a_data^T / 0.04 (softmax, detached)  and  pi(s) a_data^T / 0.1 (log-softmax).  Extra metrics
+    absQmean / RelationLoss / TD3Loss / BCLoss are those of the most recent actor step.  Oracle only."""
+
+    T_K, T_Q = 0.04, 0.1
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.log_metrics: Dict[str, float] = {}
+
+    def compute_actor_loss(self, b: Batch):
+        action = deterministic_policy(self.pi, b.observations)
+        q_t = q_continuous(self.q, b.observations, action, "none")[0]
+        lam = self.alpha / (q_t.abs().mean()).detach()
+        logits_q = torch.einsum("nc,kc->nk", [action, b.actions])
+        logits_k = torch.einsum("nc,kc->nk", [b.actions, b.actions])
+        relation = -torch.sum(F.softmax(logits_k.detach() / self.T_K, dim=1) * F.log_softmax(logits_q / self.T_Q, dim=1),
+                              dim=1).mean()
+        self.log_metrics = {"absQmean": float(q_t.abs().mean().detach()), "RelationLoss": float(relation.detach()),
+                            "TD3Loss": float(-q_t.mean().detach()),
+                            "BCLoss": float(((b.actions - action.detach()) ** 2).mean())}
+        return lam * -q_t.mean() + relation + False * ((b.actions - action) ** 2).mean()
+
+    def _update(self, b, noise):
+        m = super()._update(b, noise)
+        m.update(self.log_metrics)
         return m

@@ -1,4 +1,4 @@
-"""Golden fixtures for AWAC, CRR, PLAS, BEAR, DiscreteBCQ and DiscreteSAC, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC and TD3PlusRelation, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -190,6 +190,30 @@ def main():
     mg.pack_case("discrete_sac", out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, target_update_interval=2),
                  init, [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     cases.append("discrete_sac")
+
+    # ---- TD3PlusRelation (the fork's own algorithm): TD3+BC schedule with the batch-relational actor term
+    from d3rlpy.algos import TD3PlusRelation
+
+    O, A, B, steps = 6, 3, 16, 4
+    o, a, r, t = mg.vector_dataset(rs, obs=O, act=A)
+    trs = mg.ref_transitions(o, a, r, t)
+    torch.manual_seed(70)
+    enc = VectorEncoderFactory([32, 32])
+    algo = TD3PlusRelation(actor_encoder_factory=enc, critic_encoder_factory=enc, batch_size=B, n_steps=2, scaler=None,
+                           use_gpu=False)
+    algo.create_impl((O,), A)
+    impl = algo._impl
+    init = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy)}
+    orc = oupdate.TD3PlusRelation(O, A, critics=init["q"], policy=init["pi"])
+    batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B), n_steps=2) for _ in range(steps)]
+    metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+    final = {"q": mg.sd(impl._q_func), "pi": mg.sd(impl._policy), "targ_q": mg.sd(impl._targ_q_func),
+             "targ_pi": mg.sd(impl._targ_policy)}
+    for g, p in (("q", orc.q), ("pi", orc.pi), ("targ_q", orc.targ_q), ("targ_pi", orc.targ_pi)):
+        mg.assert_params_close(final[g], p, f"td3_relation {g}")
+    mg.pack_case("td3_relation", out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32), init,
+                 [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+    cases.append("td3_relation")
 
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)

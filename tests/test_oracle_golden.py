@@ -248,3 +248,23 @@ def test_discrete_sac_oracle_matches_reference_golden():
     for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("log_temp", algo.log_temp)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
+
+
+def test_td3_plus_relation_oracle_matches_reference_golden():
+    """TD3PlusRelation -- the one algorithm this fork adds to d3rlpy -- pinned ahead of its CUDA path: delayed actor,
+    lambda-normalised Q term, B x B relational distillation term, its four extra metrics (stale on critic-only steps)."""
+    from tests.golden_io import load_awac
+
+    case = Case(load_awac(), "td3_relation")
+    c = case.cfg
+    algo = oupdate.TD3PlusRelation(int(c["obs"]), int(c["act"]), critics=case.group("init", "q"),
+                                   policy=case.group("init", "pi"))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), oupdate.Noise(injected=case.noise(s)))
+        ref = case.step_metrics(s)
+        assert set(m) == set(ref), (s, set(m), set(ref))
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (s, k, m[k], v)
+    for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
+        for k, v in case.group("final", grp).items():
+            assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
