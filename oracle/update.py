@@ -14,8 +14,8 @@ function cites the reference lines it follows (relative to /root/reference/).
 Third-party arithmetic (GEMM, Adam, Normal, logsumexp) is torch 2.11.0 as in
 the reference.  Pinned against the live reference by
 tests/golden/update*.npz and scalers.npz (tests/golden/make_golden*.py) — see DESIGN.md §2.
-AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC and TD3PlusRelation are restated and pinned here ahead of
-their CUDA paths.
+AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC, TD3PlusRelation and BC / DiscreteBC are restated and
+pinned here ahead of their CUDA paths.
 """
 from __future__ import annotations
 
@@ -1433,3 +1433,41 @@ class TD3PlusRelation(TD3PlusBC):
         m = super()._update(b, noise)
         m.update(self.log_metrics)
         return m
+
+
+class BC(_Algo):
+    """BC / DiscreteBC `_update` (algos/bc.py:58-61) over BCImpl / DiscreteBCImpl (algos/torch/bc_impl.py:24-242):
+    one Adam step (lr 1e-3) on DeterministicRegressor.compute_error = mse(tanh(fc(enc(s))), a) (imitators.py:158-175),
+    or for discrete actions on DiscreteImitator.compute_error = nll(log_softmax(logits), a) + beta * mean(logits^2)
+    (imitators.py:136-160).  Oracle only: the CUDA path is not built yet."""
+
+    def __init__(self, obs, act, hidden=(256, 256), lr=1e-3, discrete=False, beta=0.5, seed=0, imitator=None):
+        gen = torch.Generator().manual_seed(seed)
+        if imitator is None:
+            imitator = make_mlp("_encoder.", obs, hidden, gen)
+            imitator.update(make_head("_fc", act, hidden[-1], gen))
+        self.imitator = clone_params(imitator)
+        self.optim = make_adam(self.imitator, lr)
+        self.discrete, self.beta = discrete, beta
+        self.grad_step = 0
+
+    def _out(self, x):
+        return F.linear(mlp_forward(self.imitator, "_encoder.", x), self.imitator["_fc.weight"], self.imitator["_fc.bias"])
+
+    def compute_loss(self, b: Batch):
+        if self.discrete:
+            logits = self._out(b.observations)
+            return F.nll_loss(F.log_softmax(logits, dim=1), b.actions.long().view(-1)) + self.beta * (logits ** 2).mean()
+        return F.mse_loss(torch.tanh(self._out(b.observations)), b.actions)
+
+    def predict(self, x):
+        with torch.no_grad():
+            out = self._out(x)
+            return out.argmax(dim=1) if self.discrete else torch.tanh(out)
+
+    def _update(self, b, noise=None):
+        self.optim.zero_grad()
+        loss = self.compute_loss(b)
+        loss.backward()
+        self.optim.step()
+        return {"loss": float(loss.detach())}

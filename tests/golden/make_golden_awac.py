@@ -1,4 +1,4 @@
-"""Golden fixtures for AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC and TD3PlusRelation, recorded from the LIVE unmodified reference like
+"""Golden fixtures for AWAC, CRR, PLAS, BEAR, DiscreteBCQ, DiscreteSAC, TD3PlusRelation and BC / DiscreteBC, recorded from the LIVE unmodified reference like
 tests/golden/make_golden_siblings.py.  The CUDA path for AWAC is not built yet; this pins the oracle class
 (oracle/update.py:AWAC) that path will be held to: non-squashed Gaussian policy with a logstd parameter in [-6, 0],
 batch-softmax advantage weights with sampled state values, actor Adam with weight decay.
@@ -214,6 +214,33 @@ def main():
     mg.pack_case("td3_relation", out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32), init,
                  [mg.batch_arrays(b) for b in batches], noises, metrics, final)
     cases.append("td3_relation")
+
+    # ---- BC (deterministic regressor) and DiscreteBC
+    from d3rlpy.algos import BC, DiscreteBC
+
+    for name, cls, discrete, seed in (("bc", BC, False, 71), ("discrete_bc", DiscreteBC, True, 72)):
+        O, A, B, steps = 6, 3, 16, 3
+        o, a, r, t = mg.vector_dataset(rs, obs=O, act=A, discrete=discrete)
+        trs = mg.ref_transitions(o, a, r, t)
+        torch.manual_seed(seed)
+        kw = dict(beta=0.3) if discrete else {}
+        algo = cls(encoder_factory=VectorEncoderFactory([32, 32]), batch_size=B, **kw)
+        algo.create_impl((O,), A)
+        impl = algo._impl
+        init = {"imitator": mg.sd(impl._imitator)}
+        orc = oupdate.BC(O, A, imitator=init["imitator"], discrete=discrete, beta=0.3)
+        batches = [mg.ref_batch(trs, rs.randint(len(trs), size=B)) for _ in range(steps)]
+        metrics, noises = mg.run_steps(algo, orc, batches, [oupdate.Batch(mg.batch_arrays(b)) for b in batches])
+        final = {"imitator": mg.sd(impl._imitator)}
+        mg.assert_params_close(final["imitator"], orc.imitator, name)
+        xe = o[:20]
+        pred = algo.predict(xe)
+        got = orc.predict(torch.tensor(xe)).numpy()
+        assert np.array_equal(pred, got) if discrete else np.allclose(pred, got, atol=1e-6)
+        mg.pack_case(name, out, dict(obs=O, act=A, batch=B, steps=steps, h0=32, h1=32, discrete=float(discrete),
+                                     beta=0.3), init, [mg.batch_arrays(b) for b in batches], noises, metrics, final)
+        out[f"{name}/eval_x"], out[f"{name}/predict"] = xe, pred
+        cases.append(name)
 
     out["cases"] = np.array(cases)
     np.savez_compressed(os.path.join(HERE, "update_awac.npz"), **out)

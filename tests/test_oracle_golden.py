@@ -268,3 +268,23 @@ def test_td3_plus_relation_oracle_matches_reference_golden():
     for grp, params in (("q", algo.q), ("pi", algo.pi), ("targ_q", algo.targ_q), ("targ_pi", algo.targ_pi)):
         for k, v in case.group("final", grp).items():
             assert float((params[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), (grp, k)
+
+
+@pytest.mark.parametrize("name", ["bc", "discrete_bc"])
+def test_bc_oracle_matches_reference_golden(name):
+    """BC / DiscreteBC, pinned ahead of their CUDA path: losses, post-step parameters and `predict`."""
+    from tests.golden_io import load_awac
+
+    z = load_awac()
+    case = Case(z, name)
+    c = case.cfg
+    algo = oupdate.BC(int(c["obs"]), int(c["act"]), imitator=case.group("init", "imitator"), discrete=bool(c["discrete"]),
+                      beta=float(c["beta"]))
+    for s in range(case.steps):
+        m = algo.update(oupdate.Batch(case.batch(s)), None)
+        for k, v in case.step_metrics(s).items():
+            assert abs(m[k] - v) <= 1e-5 * max(1.0, abs(v)), (s, k, m[k], v)
+    for k, v in case.group("final", "imitator").items():
+        assert float((algo.imitator[k].detach() - v).abs().max()) <= 2e-6 * max(1.0, float(v.abs().max())), k
+    got = algo.predict(torch.tensor(z[f"{name}/eval_x"])).numpy()
+    assert np.array_equal(got, z[f"{name}/predict"]) if c["discrete"] else np.allclose(got, z[f"{name}/predict"], atol=1e-6)
