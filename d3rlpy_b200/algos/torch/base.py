@@ -108,8 +108,9 @@ class ImplBase:
         self._slots_host = torch.zeros(64, dtype=torch.float32).pin_memory()
         self._graphs: Dict[tuple, int] = {}
         self._graph_nodes: Dict[tuple, int] = {}
-        self._batch: Optional[DeviceBatch] = None
-        self._noise: Optional[torch.Tensor] = None
+        self._batch: Optional[DeviceBatch] = None          # the active minibatch buffer
+        self._batches: Dict[int, DeviceBatch] = {}         # impl-owned buffers, one per batch size (stable pointers)
+        self._noise_by_b: Dict[int, torch.Tensor] = {}
         self._noise_injected = False
         self._seed = 0
         self._ws: Dict[str, torch.Tensor] = {}
@@ -146,10 +147,15 @@ class ImplBase:
         return self._reward_scaler
 
     def ws(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
-        t = self._ws.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
+        """Named workspace.  Keyed by (name, shape, dtype): buffers of different minibatch sizes coexist, so a
+        captured graph of one size keeps valid pointers while another size (e.g. a 1-row evaluation) runs."""
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None:
             t = torch.zeros(*shape, dtype=dtype, device=self._device)
-            self._ws[name] = t
+            self._ws[key] = t
+            # the zero-fill ran on torch's current stream; our kernels run on the private stream
+            torch.cuda.current_stream(self._device).synchronize()
         return t
 
     def counter_ptr(self, i: int) -> int:
@@ -233,10 +239,14 @@ class ImplBase:
     DISCRETE = False
 
     def device_batch(self, B: int) -> DeviceBatch:
-        if self._batch is None or self._batch.B != B:
-            self._batch = self._make_batch(B)
-            self._graphs_invalidate()
-        return self._batch
+        """The impl-owned minibatch buffer of size B (created once: graphs captured over it stay valid when another
+        batch size is used in between, e.g. the 1-row evaluation batches of the online loop)."""
+        db = self._batches.get(B)
+        if db is None:
+            db = self._batches[B] = self._make_batch(B)
+            torch.cuda.current_stream(self._device).synchronize()
+        self._batch = db
+        return db
 
     def load_batch(self, batch, defer: bool = False) -> DeviceBatch:
         """Accepts a host minibatch (numpy properties, e.g. the reference's TransitionMiniBatch or ours)
@@ -246,10 +256,8 @@ class ImplBase:
         self._pending_upload = None
         dev = getattr(batch, "_device_batch", None)
         if dev is not None:
-            dev = self._scale_device_batch(batch, dev)
-            if self._batch is not dev:
-                self._batch = dev
-                self._graphs_invalidate()
+            dev = self._adopt_device_batch(batch, dev)
+            self._batch = dev
             return dev
         B = len(batch.rewards) if hasattr(batch, "rewards") else len(batch)
         db = self.device_batch(B)
@@ -260,26 +268,33 @@ class ImplBase:
             self._upload(db)
         return db
 
-    def _scale_device_batch(self, batch, dev: DeviceBatch) -> DeviceBatch:
+    def _adopt_device_batch(self, batch, dev: DeviceBatch) -> DeviceBatch:
         """A minibatch gathered in HBM carries in `batch.scaled` which of the TorchMiniBatch transforms
         (torch_utility.py:179-185) were already applied to it (fused into the gather, or by `fit`).  Whatever is
-        missing is applied here.  A buffer owned by the caller (e.g. `TransitionMiniBatch(transitions)`, whose numpy
-        properties must keep showing the raw data) is copied into an impl-owned buffer first."""
+        missing is applied here.  A buffer owned by the caller (a fresh `ReplayBuffer.sample()` /
+        `TransitionMiniBatch(transitions)`, whose numpy properties must keep showing the raw data) is copied device to
+        device into the impl-owned buffer of that size first: the update graph is captured once over the impl's
+        buffers and replayed for every such batch instead of being re-captured per sample."""
         have = getattr(batch, "scaled", True)   # a bare holder of device buffers: its owner manages the transforms
         have = {"obs", "act_rew"} if have is True else set(have or ())
         need_obs = self._vector_scaler() is not None and not dev.pixel_shape and "obs" not in have
         need_ar = self._scales_actions_rewards(dev) and "act_rew" not in have
-        if not (need_obs or need_ar):
-            return dev
-        if dev is not self._batch or getattr(batch, "_transitions", None) is not None:
-            own = getattr(self, "_own_batch", None)
-            if own is None or own.B != dev.B or own is dev:
-                own = self._own_batch = self._make_batch(dev.B)
+        mine = self._batches.get(dev.B)
+        foreign = dev is not mine
+        if foreign or ((need_obs or need_ar) and getattr(batch, "_transitions", None) is not None):
+            if foreign:
+                own = self.device_batch(dev.B)
+            else:   # the caller's view of our own buffer must keep showing raw data: scale a private copy
+                own = getattr(self, "_own_batch", None)
+                if own is None or own.B != dev.B:
+                    own = self._own_batch = self._make_batch(dev.B)
+                    torch.cuda.current_stream(self._device).synchronize()
+                    self._graphs_invalidate()
             self._lib.copy_d2d(own.dev.data_ptr(), dev.dev.data_ptr(), 4 * dev.nfloat, self._stream)
             if dev.pixel_shape:
                 self._lib.copy_d2d(own.pix_dev.data_ptr(), dev.pix_dev.data_ptr(), 2 * dev.npix, self._stream)
             dev = own
-        else:   # gathered straight into the impl's own buffer: scale in place, once
+        elif need_obs or need_ar:   # gathered straight into the impl's own buffer: scale in place, once
             batch.scaled = have | {"obs", "act_rew"}
         if need_obs:
             self._scale_observations(dev)
@@ -365,12 +380,20 @@ class ImplBase:
         n_normal = sum(int(np.prod(s)) for _, s in normals)
         return plan, n_normal, off - n_normal, list(layout.keys())
 
+    def _noise_arena(self, B: int) -> torch.Tensor:
+        """One noise arena per batch size (pointers captured in that size's graphs never move)."""
+        t = self._noise_by_b.get(B)
+        if t is None:
+            _, n_norm, n_uni, _ = self._noise_plan(B)
+            t = torch.zeros(max(4, _align4(n_norm + n_uni)), dtype=torch.float32, device=self._device)
+            self._noise_by_b[B] = t
+            torch.cuda.current_stream(self._device).synchronize()
+        return t
+
     def noise_view(self, name: str, B: int) -> torch.Tensor:
-        plan, n_norm, n_uni, _ = self._noise_plan(B)
-        if self._noise is None or self._noise.numel() < n_norm + n_uni:
-            self._noise = torch.zeros(max(4, _align4(n_norm + n_uni)), dtype=torch.float32, device=self._device)
+        plan = self._noise_plan(B)[0]
         off, shape = plan[name]
-        return self._noise[off:off + int(np.prod(shape))].view(shape)
+        return self._noise_arena(B)[off:off + int(np.prod(shape))].view(shape)
 
     def inject_noise(self, tensors: List[torch.Tensor], B: int, names: Optional[List[str]] = None):
         """Parity mode: replay recorded draws (in reference draw order) instead of Philox."""
@@ -394,10 +417,9 @@ class ImplBase:
         plan, n_norm, n_uni, _ = self._noise_plan(B)
         if n_norm + n_uni == 0 or self._noise_injected:
             return
-        self.noise_view(next(iter(plan)), B)  # ensure allocation
         # per-rank Philox key: ranks draw independent noise for their own rows
         seed = (self._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF
-        self._lib.noise_fill(self._noise.data_ptr(), n_norm, n_uni, seed, self.counter_ptr(0), self._stream)
+        self._lib.noise_fill(self._noise_arena(B).data_ptr(), n_norm, n_uni, seed, self.counter_ptr(0), self._stream)
 
     # ------------------------------------------------------------------ graphs
     def _graphs_invalidate(self):
@@ -420,7 +442,7 @@ class ImplBase:
             if pend is not None:  # host caller: it will read the metrics right away
                 self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
 
-        key = tuple(key) + (pend is not None,)
+        key = tuple(key) + (pend is not None, id(self._batch))
         self._metrics_on_host = pend is not None
         if not self.use_graph:
             program()

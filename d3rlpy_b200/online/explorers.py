@@ -45,7 +45,8 @@ class LinearDecayEpsilonGreedy(Explorer):
 
 class NormalNoise(Explorer):
     """explorers.py:128-171: ONE scalar draw added to every action component (the reference's documented quirk);
-    action scalers are outside the accelerated path, so the clip range is always [-1, 1]."""
+    the result is clipped to the MinMaxActionScaler's [minimum, maximum] when the algorithm carries one (`predict`
+    returns actions already mapped back to that range), else to [-1, 1]."""
 
     def __init__(self, mean: float = 0.0, std: float = 0.1):
         self._mean, self._std = mean, std
@@ -53,4 +54,12 @@ class NormalNoise(Explorer):
     def sample(self, algo, x: np.ndarray, step: int) -> np.ndarray:
         action = algo.predict(x)
         noise = np.random.normal(self._mean, self._std)
-        return np.clip(action + noise, -1.0, 1.0)
+        from ..preprocessing import MinMaxActionScaler
+
+        scaler = getattr(algo, "action_scaler", None)
+        if isinstance(scaler, MinMaxActionScaler):
+            params = scaler.get_params()
+            minimum, maximum = params["minimum"], params["maximum"]
+        else:
+            minimum, maximum = -1.0, 1.0
+        return np.clip(action + noise, minimum, maximum)

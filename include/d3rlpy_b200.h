@@ -86,6 +86,22 @@ int d3b_linear_backward_weight(const float* dy, int64_t lddy, int64_t stride_dy,
                                int64_t stride_db, int rows, int out_features, int in_features, int members,
                                void* stream);
 
+/* fp32-mode engine of the three calls above: 1 (default) = error-compensated TF32 ("3xTF32") on the tcgen05 tensor
+ * cores (csrc/gemm_tf32x3.cu: every fp32 operand is split x = hi + lo in registers, three kind::tf32 MMAs per step,
+ * fp32 accumulate; fp32-grade accuracy, so the 1e-5 parity of fp32 mode holds), 0 = SIMT FFMA GEMMs.  Layers with
+ * fewer than 64 rows always run on the SIMT kernels.  Environment override at first use: D3B_FP32_ENGINE=simt. */
+int d3b_set_fp32_engine(int engine);
+int d3b_get_fp32_engine(void);
+/* The 3xTF32 GEMM itself: c[e] (m x n) (+)= sum_r a(m, r) b(n, r), fp32 row-major operands of any leading dimension.
+ * a_rc: a stored [m][r] (else [r][m]); b_rc: b stored [n][r] (else [r][n]) — forward (1,1), data gradient (1,0),
+ * weight gradient (0,0).  Epilogue: + bias[n], ReLU, keep where mask[m][n] > 0, store or RED.ADD (`atomic`, needed
+ * for splits > 1 over r); colsum[e][m] += sum_r a(m, r) (bias gradient; weight-gradient form only). */
+int d3b_tc32_gemm(const float* a, int64_t lda, int64_t stride_a, int a_rc, const float* b, int64_t ldb,
+                  int64_t stride_b, int b_rc, float* c, int64_t ldc, int64_t stride_c, int m, int n, int r,
+                  int members, int splits, const float* bias, int64_t stride_bias, int relu, const float* mask,
+                  int64_t ld_mask, int64_t stride_mask, float* colsum, int64_t stride_colsum, int atomic,
+                  void* stream);
+
 /* Narrow heads (out_features <= 32): Q head, mu|logstd, VAE heads, discrete Q head.
  * Replace `_fc/_mu/_logstd` (q_functions/mean_q_function.py:21,69; policies.py:55,92,153-158;
  * imitators.py:45-54). act_tanh fuses DeterministicPolicy's tanh (policies.py:57-59). */
@@ -153,6 +169,8 @@ int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const in
                              const int64_t* stride_b_host, const int* m_host, const int* n_host, int k, int members,
                              float* const* out_host, const int64_t* ldf_host, int64_t stride_f, void* stream);
 int d3b_umma_set_debug(void* device_buffer);
+int d3b_tc32_set_variant(int variant);  /* profiling hook: knock out loads (1) / smem stores (2) / MMAs (4) */
+int d3b_tc32_set_debug(void* device_buffer);  /* profiling hook: 64 clock64 phase stamps per CTA of d3b_tc32_gemm */
 int d3b_mlp_set_debug(void* device_buffer);  /* profiling hook: 16 clock64 phase stamps per CTA of mlp_forward_bf16 */ /* profiling hook: 8 clock64 phase stamps per CTA */
 int d3b_shadow_weights(const float* src, int64_t src_member_stride, void* dst_bf16, int64_t dst_member_stride,
                        const int64_t* table_host, int n_entries, int members, void* stream);

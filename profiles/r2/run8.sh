@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_tc32_gpu.py -q 2>&1 | tail -3
+timeout 120 python profiles/r2/tc32_bench.py 2>&1 | tail -12 | cut -c1-140 | tee gpurun_out/r2_tc32_bench_e.log
+timeout 900 python -m pytest tests/test_update_gpu.py -q -k "c2_shape_vs_oracle_three or bcq_c3 or c4_shape_vs" --tb=line 2>&1 | grep -v Warning | tail -12
+timeout 300 python bench.py --precision fp32 --steps 200 --warmup 10 > gpurun_out/r2_fp32_tc.json 2> gpurun_out/r2_fp32_tc.err; tail -c 600 gpurun_out/r2_fp32_tc.err; python -c "
+import json;d=json.load(open('gpurun_out/r2_fp32_tc.json'));print(d['value'],d['ms_per_step'],d['e2e']['value'],d['graph_nodes_per_update']);
+[print(k,v) for k,v in d['roofline']['families'].items() if 'linear' in k or 'head' in k]"

@@ -72,3 +72,14 @@ def test_explorers_follow_reference_arithmetic_and_numpy_stream():
     got = NormalNoise(0.0, 0.3).sample(algo, x, 0)
     np.random.seed(5)
     assert np.allclose(got, np.clip(0.95 + np.random.normal(0.0, 0.3), -1.0, 1.0)) and got.shape == (6, 2)
+    # with a MinMaxActionScaler the clip range is the scaler's [minimum, maximum] (explorers.py:144-151): `predict`
+    # returns actions in environment units, which may exceed +-1
+    from d3rlpy_b200.preprocessing import MinMaxActionScaler
+
+    algo.action_scaler = MinMaxActionScaler(minimum=np.array([[-2.0, -3.0]]), maximum=np.array([[2.0, 1.0]]))
+    algo.predict = lambda x: np.tile(np.array([[1.9, 0.9]], np.float32), (x.shape[0], 1))
+    np.random.seed(6)
+    got = NormalNoise(0.5, 0.01).sample(algo, x, 0)
+    np.random.seed(6)
+    n = np.random.normal(0.5, 0.01)
+    assert np.allclose(got, np.tile([[min(1.9 + n, 2.0), min(0.9 + n, 1.0)]], (6, 1))) and got[0, 0] > 1.0
