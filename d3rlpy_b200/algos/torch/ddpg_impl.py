@@ -9,30 +9,11 @@ import numpy as np
 import torch
 
 from ...nets import DenseNet
+from ...q_functions import EnsembleContinuousQFunction, _ModuleView
 from .base import ImplBase
 
 # counter slots (device int32): 0 = noise epoch; the rest are Adam step counts
 C_DRAW, C_CRITIC, C_ACTOR, C_TEMP, C_ALPHA, C_IMITATOR = 0, 1, 2, 3, 4, 5
-
-
-class _ModuleView:
-    """Minimal stand-in for the nn.Module the reference exposes through `impl.q_function` /
-    `impl.policy`: `state_dict()`, `load_state_dict()`, `parameters()` over arena views."""
-
-    def __init__(self, net: DenseNet, which: str = "params"):
-        self._net, self._which = net, which
-
-    def state_dict(self):
-        return self._net.arena.state_dict(self._which)
-
-    def load_state_dict(self, sd):
-        self._net.arena.load_state_dict(sd, self._which)
-        st = torch.cuda.current_stream(self._net.device)
-        self._net.refresh_shadow(self._which, st.cuda_stream)
-        st.synchronize()
-
-    def parameters(self):
-        return list(self.state_dict().values())
 
 
 class _OptimView:
@@ -129,11 +110,13 @@ class DDPGBaseImpl(ImplBase):
 
     @property
     def q_function(self):
-        return _ModuleView(self._q_func)
+        """Callable like the reference's EnsembleContinuousQFunction (`(x, action, reduction)`, `compute_error`,
+        `compute_target`, `q_funcs`), see d3rlpy_b200/q_functions.py."""
+        return EnsembleContinuousQFunction(self)
 
     @property
     def targ_q_function(self):
-        return _ModuleView(self._q_func, "target")
+        return EnsembleContinuousQFunction(self, "target")
 
     @property
     def policy_optim(self):

@@ -71,11 +71,15 @@ class DQNImpl(ImplBase):
     # ------------------------------------------------------------------ reference-visible properties
     @property
     def q_function(self):
-        return _ModuleView(self._q_func)
+        from ...q_functions import EnsembleDiscreteQFunction
+
+        return EnsembleDiscreteQFunction(self)
 
     @property
     def targ_q_function(self):
-        return _ModuleView(self._q_func, "target")
+        from ...q_functions import EnsembleDiscreteQFunction
+
+        return EnsembleDiscreteQFunction(self, "target")
 
     @property
     def q_function_optim(self):

@@ -218,6 +218,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 // 3xTF32 tensor-core engine (gemm_tf32x3.cu): same operands, same results to fp32 rounding
 namespace tc32 {
 int engine();
+int ops();
 int gemm(const float* a, long long lda, long long stride_a, int a_rc, const float* b, long long ldb,
          long long stride_b, int b_rc, float* c, long long ldc, long long stride_c, int m, int n, int r, int members,
          int splits, const float* bias, long long stride_bias, int relu, const float* mask, long long ld_mask,
@@ -225,7 +226,7 @@ int gemm(const float* a, long long lda, long long stride_a, int a_rc, const floa
 }  // namespace tc32
 
 // the tensor-core tile is 128 rows: below half a tile the SIMT small-M kernel wastes less
-static bool use_tc(int m_rows) { return tc32::engine() == 1 && m_rows >= 64; }
+static bool use_tc(int m_rows, int op_bit) { return tc32::engine() == 1 && (tc32::ops() & op_bit) && m_rows >= 64; }
 
 }  // namespace d3b
 
@@ -239,7 +240,7 @@ extern "C" int d3b_linear_forward(const float* x, int64_t ldx, int64_t stride_x,
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && w && y, "linear_forward: null pointer");
   D3B_REQUIRE(ldx >= in_features && ldw >= in_features && ldy >= out_features, "linear_forward: bad leading dims");
-  if (use_tc(rows))
+  if (use_tc(rows, 1))
     return tc32::gemm(x, ldx, stride_x, 1, w, ldw, stride_w, 1, y, ldy, stride_y, rows, out_features, in_features,
                       members, 1, bias, stride_b, relu, nullptr, 0, 0, nullptr, 0, 0, (cudaStream_t)stream);
   GemmArgs g{};
@@ -262,7 +263,7 @@ extern "C" int d3b_linear_backward_data(const float* dy, int64_t lddy, int64_t s
   D3B_REQUIRE(rows >= 0 && out_features > 0 && in_features > 0 && members > 0, "linear_backward_data: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dy && w && dx, "linear_backward_data: null pointer");
-  if (use_tc(rows))
+  if (use_tc(rows, 2))
     return tc32::gemm(dy, lddy, stride_dy, 1, w, ldw, stride_w, 0, dx, lddx, stride_dx, rows, in_features,
                       out_features, members, 1, nullptr, 0, 0, relu_src, ld_src, stride_src, nullptr, 0, 0,
                       (cudaStream_t)stream);
@@ -286,7 +287,7 @@ extern "C" int d3b_linear_backward_weight(const float* dy, int64_t lddy, int64_t
   D3B_REQUIRE(rows >= 0 && out_features > 0 && in_features > 0 && members > 0, "linear_backward_weight: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dy && x && dw, "linear_backward_weight: null pointer");
-  if (use_tc(out_features) && rows >= 32) {
+  if (use_tc(out_features, 4) && rows >= 32) {
     // split the minibatch-row reduction so that ~one wave of CTAs exists
     int bn = in_features > 64 ? 128 : (in_features > 32 ? 64 : 32);
     long long tiles = (long long)ceil_div(out_features, 128) * ceil_div(in_features, bn) * members;

@@ -512,6 +512,8 @@ static bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 
 static long long* g_dbg = nullptr;
 static int g_variant = 0;
+static int g_ops = 7;  // which layer GEMMs run on the tensor cores: bit 0 forward, bit 1 data gradient, bit 2 weight gradient
+int ops() { return g_ops; }
 static int g_engine = -1;  // -1: read D3B_FP32_ENGINE on first use; 0 = SIMT FFMA, 1 = 3xTF32 tensor cores
 
 int engine() {
@@ -601,6 +603,10 @@ extern "C" int d3b_tc32_set_debug(void* device_buffer) {
 }
 // profiling hook: knock out one pipeline phase (bit 0 global loads, bit 1 shared-memory stores, bit 2 MMAs); results
 // are then meaningless — only the timing is of interest
+extern "C" int d3b_tc32_set_ops(int mask) {
+  tc32::g_ops = mask & 7;
+  return D3B_OK;
+}
 extern "C" int d3b_tc32_set_variant(int variant) {
   tc32::g_variant = variant;
   return D3B_OK;

@@ -163,3 +163,82 @@ extern "C" int d3b_head_backward_weight(const float* dy, int64_t lddy, int64_t s
                                                              in_features, rpb);
   return check_launch("head_backward_weight");
 }
+
+// ---- _reduce_ensemble (q_functions/ensemble_q_function.py:9-24) over the member axis of q[members][n], and the
+// ensemble TD error EnsembleQFunction.compute_error (ensemble_q_function.py:81-106) — the callable Q-function API.
+namespace d3b {
+
+__global__ void ensemble_reduce_kernel(const float* __restrict__ q, long long stride_member, int n, int members,
+                                       int mode, float lam, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v0 = q[i];
+  float mn = v0, mx = v0, sum = v0;
+  for (int e = 1; e < members; ++e) {
+    float v = q[(long long)e * stride_member + i];
+    mn = fminf(mn, v);
+    mx = fmaxf(mx, v);
+    sum = __fadd_rn(sum, v);
+  }
+  float r;
+  if (mode == 0) r = mn;
+  else if (mode == 1) r = mx;
+  else if (mode == 2) r = __fdiv_rn(sum, (float)members);
+  else r = __fadd_rn(__fmul_rn(lam, mn), __fmul_rn(1.0f - lam, mx));   // lam * min + (1 - lam) * max
+  out[i] = r;
+}
+
+// out[0] = sum_e mean_b loss(q_e[b] - y_b),  y = r + gamma * target * (1 - terminal); gamma per row when gamma_rows.
+// One block, fixed summation order (bit-reproducible).
+__global__ void td_error_kernel(const float* __restrict__ q, long long stride_member, const float* __restrict__ rew,
+                                const float* __restrict__ target, const float* __restrict__ term,
+                                const float* __restrict__ gamma_rows, float gamma, int n, int members, int huber,
+                                float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  float total = 0.f;
+  for (int e = 0; e < members; ++e) {
+    float part = 0.f;
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+      float g = gamma_rows ? gamma_rows[b] : gamma;
+      float y = __fadd_rn(rew[b], __fmul_rn(__fmul_rn(g, target[b]), __fsub_rn(1.0f, term[b])));
+      float d = __fsub_rn(q[(long long)e * stride_member + b], y);
+      float l;
+      if (huber) {  // compute_huber_loss (q_functions/utility.py:27-32), beta = 1
+        float a = fabsf(d);
+        l = a < 1.0f ? 0.5f * d * d : a - 0.5f;
+      } else {
+        l = d * d;
+      }
+      part += l;
+    }
+    part = block_sum(part);
+    if (threadIdx.x == 0) total += part / (float)n;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = total;
+}
+
+}  // namespace d3b
+
+extern "C" int d3b_ensemble_reduce(const float* q, int64_t stride_member, int n, int members, int mode, float lam,
+                                   float* out, void* stream) {
+  D3B_REQUIRE(n >= 0 && members >= 1 && mode >= 0 && mode <= 3, "ensemble_reduce: bad arguments (mode 0 min, 1 max, 2 mean, 3 mix)");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(q && out, "ensemble_reduce: null pointer");
+  launch_pdl(ensemble_reduce_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, q,
+             (long long)stride_member, n, members, mode, lam, out);
+  return check_launch("ensemble_reduce");
+}
+
+extern "C" int d3b_td_error(const float* q, int64_t stride_member, const float* rewards, const float* target,
+                            const float* terminals, const float* gamma_rows, float gamma, int n, int members,
+                            int huber, float* out, void* stream) {
+  D3B_REQUIRE(n >= 1 && members >= 1, "td_error: bad sizes");
+  D3B_REQUIRE(q && rewards && target && terminals && out, "td_error: null pointer");
+  launch_pdl(td_error_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, q, (long long)stride_member, rewards,
+             target, terminals, gamma_rows, gamma, n, members, huber, out);
+  return check_launch("td_error");
+}

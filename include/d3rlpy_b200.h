@@ -169,6 +169,7 @@ int d3b_umma_gemm_tn_batched(int n_problems, const void* const* a_host, const in
                              const int64_t* stride_b_host, const int* m_host, const int* n_host, int k, int members,
                              float* const* out_host, const int64_t* ldf_host, int64_t stride_f, void* stream);
 int d3b_umma_set_debug(void* device_buffer);
+int d3b_tc32_set_ops(int mask);  /* which layer GEMMs use the 3xTF32 engine: bit 0 forward, 1 data gradient, 2 weight gradient (default 7) */
 int d3b_tc32_set_variant(int variant);  /* profiling hook: knock out loads (1) / smem stores (2) / MMAs (4) */
 int d3b_tc32_set_debug(void* device_buffer);  /* profiling hook: 64 clock64 phase stamps per CTA of d3b_tc32_gemm */
 int d3b_mlp_set_debug(void* device_buffer);  /* profiling hook: 16 clock64 phase stamps per CTA of mlp_forward_bf16 */ /* profiling hook: 8 clock64 phase stamps per CTA */
@@ -190,6 +191,17 @@ int d3b_head_backward_weight_bf16(const float* dy, int64_t lddy, int64_t stride_
                                   void* stream);
 int d3b_colsum_bf16(const void* dz, int64_t ld, int64_t stride_z, float* dbias, int64_t stride_db, int rows,
                     int cols, int members, void* stream);
+
+/* The callable Q-function API.  ensemble_reduce: _reduce_ensemble (q_functions/ensemble_q_function.py:9-24) over the
+ * member axis of q[members][n] -> out[n]; mode 0 = min, 1 = max, 2 = mean, 3 = mix (lam * min + (1 - lam) * max).
+ * td_error: EnsembleQFunction.compute_error (ensemble_q_function.py:81-106) — out[0] = sum_members mean_b loss(q_e[b] -
+ * (r[b] + gamma * target[b] * (1 - terminal[b]))), squared error (mean_q_function.py:74-87) or Huber with beta 1
+ * (utility.py:27-32); gamma_rows (one gamma per row, e.g. gamma ** n_steps) overrides the scalar when non-NULL. */
+int d3b_ensemble_reduce(const float* q, int64_t stride_member, int n, int members, int mode, float lam, float* out,
+                        void* stream);
+int d3b_td_error(const float* q, int64_t stride_member, const float* rewards, const float* target,
+                 const float* terminals, const float* gamma_rows, float gamma, int n, int members, int huber,
+                 float* out, void* stream);
 
 /* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
  * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
