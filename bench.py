@@ -504,6 +504,11 @@ def dp_check(w, world, rank, local, precision):
                     "injected noise); only the summation order differs"}
 
 
+def trace(msg):
+    if os.environ.get("BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args, w):
     import torch
     import torch.distributed as dist
@@ -532,8 +537,10 @@ def run_ours(args, w):
     total_ms, step_ms, launches, graph_nodes = r.timed(K, W, flush_buf)
     clocks = sampler.stop()
     head = summarize(r, total_ms, step_ms, K)
+    trace(f"headline timed: {head['ms_per_step']:.4f} ms/step")
     e2e, hb, hbs = r.e2e(max(10, min(K, 200)))
     plane = r.plane()
+    trace("e2e done")
 
     extra = {}
     fp32_mode = None
@@ -570,8 +577,15 @@ def run_ours(args, w):
                                        "per_gpu_batch": r5.B, "steps": k5, "parallelism": r5.plane(),
                                        "unit": "batch-8192 updates/s (minibatch sharded over the ranks)"})
             del r5
+            trace("c5 done")
         if world > 1 and w["algo"] == "cql":
             check = dp_check(w, world, rank, local, args.precision)
+            trace("dp_check done")
+        if world > 1 and args.profile_dp:
+            # per-launch device times of the data-parallel update (every rank runs the instrumented pass: the update is
+            # collective); kernels that wait for a peer include the wait
+            prof_dp, _ = kernel_profile(r.algo, hbs[0], n_iter=10)
+            extra["dp_families"] = prof_dp
 
     if rank == 0 and world == 1 and not args.headline_only:
         # ---- roofline of the dominant kernel family (dense layers), measured live with CUDA events
@@ -628,6 +642,7 @@ def run_ours(args, w):
             variant = {"alpha_learning_rate": 0.0, "updates_per_s": k0 / (t0 * 1e-3), "ms_per_step": t0 / k0,
                        "note": "reproductions/offline/cql.py variant: no update_alpha step"}
 
+    trace("assembling the line")
     if rank == 0:
         line = {
             "metric": METRIC if not strong else "CQL gradient updates/sec at batch 8192 (c5, sharded)",
@@ -653,9 +668,11 @@ def run_ours(args, w):
             "roofline": roof, "hbm": hbm, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
+        trace("line printed")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    trace("exit")
 
 
 def main():
@@ -667,6 +684,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the extra workloads / roofline / baselines")
+    ap.add_argument("--profile-dp", action="store_true", help="N > 1: add per-launch device times of the sharded update")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core GEMMs (bf16 operands, fp32 accumulate; losses within 1e-2); "
                          "fp32: 3xTF32 tcgen05 GEMMs, fp32 everything else (parity 1e-5)")

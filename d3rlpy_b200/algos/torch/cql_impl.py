@@ -416,7 +416,7 @@ class CQLImpl(DDPGBaseImpl):
     def _peer_setup(self):
         from ... import parallel
 
-        px = parallel.peers(self._device)
+        px = parallel.new_peers(self._device)
         if px is not None and getattr(self._q_func, "_peer", None) is None:
             for net in (self._q_func, self._policy):   # collective: same order on every rank
                 net._peer = px.register_arena(net.arena.grads)

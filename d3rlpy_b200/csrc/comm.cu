@@ -105,6 +105,10 @@ extern "C" int d3b_comm_destroy(void* comm) {
 // Flags are monotonically increasing update epochs: ready[r] >= e  <=>  rank r's gradients of update e are
 // complete; done[r] >= e  <=>  rank r has finished reading everybody's gradients of update e (so they may
 // be zeroed for update e+1; that wait + the zeroing is the first kernel of the next update).
+// Flags are PUSHED: every rank's flag block holds one slot per (flag, writer rank); a writer stores its epoch into its
+// slot of EVERY rank's block (W posted NVLink stores issued by W threads) and a waiter polls only its OWN block (local
+// L2 hits, W threads in parallel) — a poll never crosses NVLink (round 1 polled the W-1 remote flags one after the
+// other, ~2-3 us per remote poll).
 // =====================================================================================================
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -147,16 +151,23 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
   }
 }
 
+// flag f of writer rank w lives at flags[any rank] + f * kMaxRanks + w
+__device__ __forceinline__ void signal_all(const PeerPtrs& ps, int f, int e) {   // threads 0..world-1 of one block
+  if ((int)threadIdx.x < ps.world) st_release_sys(ps.flags[threadIdx.x] + f * kMaxRanks + ps.rank, e);
+}
+__device__ __forceinline__ void wait_all(const PeerPtrs& ps, int f, int e) {     // threads 0..world-1, local polls
+  if ((int)threadIdx.x < ps.world) wait_flag_ge(ps.flags[ps.rank] + f * kMaxRanks + threadIdx.x, e);
+}
+
 // first kernel of an update: wait until every rank has finished reading this rank's gradients of the previous
 // update, then zero them (the backward kernels accumulate with RED)
 __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int done_index, const int* epoch,
                                                              float* __restrict__ grads, long long n, int done_index2,
                                                              float* __restrict__ grads2, long long n2) {
-  if (threadIdx.x == 0) {
+  {
     const int prev = *epoch - 1;
-    for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + done_index, prev);
-    if (grads2)
-      for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + done_index2, prev);
+    wait_all(ps, done_index, prev);
+    if (grads2) wait_all(ps, done_index2, prev);
   }
   __syncthreads();
   const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -173,8 +184,8 @@ __global__ void peer_allreduce_small_kernel(float* __restrict__ vec, int n, Peer
   if (t < n) mine[t] = vec[t];
   __threadfence_system();
   __syncwarp();
-  if (t == 0) st_release_sys(ps.flags[ps.rank] + 2 * channel, e);
-  if (t < ps.world) wait_flag_ge(ps.flags[t] + 2 * channel, e);
+  signal_all(ps, 2 * channel, e);
+  wait_all(ps, 2 * channel, e);
   __syncwarp();
   if (t < n) {
     float s = 0.f;
@@ -219,8 +230,8 @@ __global__ void dp_scalar_steps_kernel(float* __restrict__ vec, PeerPtrs ps, int
   if (t < n) mine[t] = vec[t];
   __threadfence_system();
   __syncwarp();
-  if (t == 0) st_release_sys(ps.flags[ps.rank] + 2 * channel, e);
-  if (t < ps.world) wait_flag_ge(ps.flags[t] + 2 * channel, e);
+  signal_all(ps, 2 * channel, e);
+  wait_all(ps, 2 * channel, e);
   __syncwarp();
   if (t < n) {
     float s = 0.f;
@@ -286,13 +297,11 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     __threadfence_system();
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      st_release_sys(ps.flags[ps.rank] + flag_index, e);  // my gradients of update e are complete
-    }
-    for (int r = 0; r < ps.world; ++r) wait_flag_ge(ps.flags[r] + flag_index, e);
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    signal_all(ps, flag_index, e);  // my gradients of update e are complete
   }
+  wait_all(ps, flag_index, e);
   __syncthreads();
   if (blockIdx.x == 0 && (int)threadIdx.x < sv.n) {
     float acc = 0.f;
@@ -369,9 +378,10 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     if (last_block) {
       *block_counter = 0u;
       __threadfence_system();
-      st_release_sys(ps.flags[ps.rank] + flag_index + 1, e);
     }
   }
+  __syncthreads();
+  if (last_block) signal_all(ps, flag_index + 1, e);
 }
 
 int fill_peers(PeerPtrs& ps, const void* const* grads_host, const void* const* flags_host, int world, int rank) {

@@ -109,7 +109,8 @@ class PeerExchange:
     other ranks' gradient arenas over NVLink directly (csrc/comm.cu: adam_allreduce / peer_allreduce_small).
     All methods are collective: every rank must call them in the same order."""
 
-    N_FLAGS = 32          # int32 per rank: {ready, done} pairs; channels 0-3 small vectors, 4.. gradient arenas
+    N_FLAGS = 32          # flags per rank: {ready, done} pairs; channels 0-3 small vectors, 4.. gradient arenas
+    MAX_RANKS = 8         # every flag has one int32 slot per WRITER rank (pushed flags, csrc/comm.cu)
     XCHG_FLOATS = 4 * 2 * 16
 
     def __init__(self, world_size: int, rank: int, device):
@@ -118,7 +119,7 @@ class PeerExchange:
         if not (dist.is_available() and dist.is_initialized()):
             raise D3BError("PeerExchange needs an initialised torch.distributed process group for the rendezvous")
         self.world, self.rank = world_size, rank
-        self.flags = torch.zeros(self.N_FLAGS, dtype=torch.int32, device=device)
+        self.flags = torch.zeros(self.N_FLAGS * self.MAX_RANKS, dtype=torch.int32, device=device)
         self.xchg = torch.zeros(self.XCHG_FLOATS, dtype=torch.float32, device=device)
         self.counters = torch.zeros(8, dtype=torch.int32, device=device)  # block counters of the fused Adam kernels
         torch.cuda.synchronize(device)
@@ -156,12 +157,11 @@ class PeerExchange:
         return self.register(grads), 8 + 2 * i, self.counters.data_ptr() + 4 * i
 
 
-_PEERS: Optional[PeerExchange] = None
-
-
-def peers(device=None) -> Optional[PeerExchange]:
-    """The process-wide peer exchange (created on first use when world_size > 1 and D3B_PEER != 0)."""
-    global _PEERS
-    if _PEERS is None and _WORLD > 1 and os.environ.get("D3B_PEER", "1") != "0":
-        _PEERS = PeerExchange(_WORLD, _RANK, device)
-    return _PEERS
+def new_peers(device=None) -> Optional[PeerExchange]:
+    """A peer exchange for ONE data-parallel impl (None when world_size == 1 or D3B_PEER=0).  Collective: every rank
+    must create its impls in the same order.  The flags are monotonically increasing update epochs of the owning impl,
+    so two impls must never share a flag block (a second impl starting at epoch 0 would see every flag as already
+    raised and read gradients that are not there yet)."""
+    if _WORLD > 1 and os.environ.get("D3B_PEER", "1") != "0":
+        return PeerExchange(_WORLD, _RANK, device)
+    return None
