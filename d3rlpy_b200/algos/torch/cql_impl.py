@@ -280,7 +280,7 @@ class CQLImpl(DDPGBaseImpl):
         px = getattr(self, "_px", None) if dp else None
         if px is not None:
             # peers have finished reading last update's gradients -> zero them for this update's RED accumulation
-            (_, fq, _), (_, fp, _) = self._q_func._peer, self._policy._peer
+            fq, fp = self._q_func._peer[1], self._policy._peer[1]
             L.peer_wait_zero(px.flags_ptrs, px.world, px.rank, fq + 1, self.counter_ptr(C_DRAW),
                              self._q_func.arena.grads.data_ptr(), self._q_func.arena.size, fp + 1,
                              self._policy.arena.grads.data_ptr(), self._policy.arena.size, st)
@@ -425,8 +425,8 @@ class CQLImpl(DDPGBaseImpl):
     def _peer_args(self, px, net, small=None):
         if px is None:
             return None
-        gptrs, fidx, cptr = net._peer
-        return (px, gptrs, fidx, cptr, self.counter_ptr(C_DRAW), small)
+        gptrs, fidx, cptr, gred, cptr2 = net._peer
+        return (px, gptrs, fidx, cptr, self.counter_ptr(C_DRAW), small, gred, cptr2)
 
     def _small_allreduce(self, px, t, channel: int):
         if px is None:

@@ -286,11 +286,23 @@ __device__ __forceinline__ float adam_one2(float p, float g, float& m, float& v,
   return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_ss, m), denom));
 }
 
-// all-reduce (over NVLink peer loads) + Adam + Polyak + bf16 shadow refresh in one pass
+// reduced-gradient buffers of every rank (two-shot exchange); gred[0] == nullptr selects the one-shot form
+struct GredPtrs { float* gred[kMaxRanks]; };
+
+// all-reduce (over NVLink peer memory) + Adam + Polyak + bf16 shadow refresh in one kernel.
+//   one-shot (gred absent): every rank reads all W gradient arenas in rank order — W-1 remote arena reads per rank.
+//   two-shot (gred present): reduce-scatter + all-gather of the reduced gradients inside the kernel.  Phase 1: rank r
+//     sums its 1/W slice of the arena over all ranks (fixed rank order, so the sum exists once and is bit-identical
+//     everywhere) and PUSHES it into every rank's `gred` buffer; the last block raises `done` (nobody's gradients are
+//     needed any more) and `reduced`.  Phase 2: after all W `reduced` flags arrived (local polls) every rank runs Adam
+//     over the whole arena from its local `gred`.  NVLink traffic per rank: 2 (W-1)/W arena sizes instead of W-1.
+//     All blocks must be co-resident (they wait for each other's phase 1 through the flag): the host bounds the grid.
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 segs, PeerPtrs ps, int flag_index,
-                                                             const int* epoch, unsigned* block_counter, SmallVec sv) {
+                                                             const int* epoch, unsigned* block_counter, SmallVec sv,
+                                                             GredPtrs gp, unsigned* block_counter2) {
   const int e = *epoch;
   __shared__ bool last_block;
+  const bool two_shot = gp.gred[0] != nullptr;
   const int sv_off = (sv.channel * 2 + (e & 1)) * 16;
   if (blockIdx.x == 0 && sv.n > 0) {  // publish my partial sums before announcing that my data is ready
     if ((int)threadIdx.x < sv.n) sv.xchg[ps.rank][sv_off + threadIdx.x] = sv.vec[threadIdx.x];
@@ -320,11 +332,47 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
   const float neg_ss = sc[0], bc2s = sc[1];
   const float one_m_tau = (float)(1.0 - (double)a.tau);
   const long long n4 = a.n >> 2;
+  if (two_shot) {
+    // ---- phase 1: my slice of the arena, summed over the ranks, pushed to everybody
+    const long long chunk = (n4 + ps.world - 1) / ps.world;
+    const long long lo = chunk * ps.rank, hi = min(n4, lo + chunk);
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < ps.world; ++r) {
+        float4 x = ((const float4*)ps.grads[r])[i];
+        G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+      }
+      for (int r = 0; r < ps.world; ++r) ((float4*)gp.gred[r])[i] = G;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned prev = atomicAdd(block_counter2, 1u);
+      last_block = (prev == gridDim.x - 1);
+      if (last_block) {
+        *block_counter2 = 0u;
+        __threadfence_system();
+      }
+    }
+    __syncthreads();
+    if (last_block) {
+      signal_all(ps, flag_index + 1, e);   // done: I no longer read anybody's gradients of update e
+      signal_all(ps, flag_index + 2, e);   // reduced: my slice has been pushed to every rank
+    }
+    // ---- phase 2 needs every rank's slice
+    wait_all(ps, flag_index + 2, e);
+    __syncthreads();
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r = 0; r < ps.world; ++r) {  // fixed rank order: every rank computes the same sum bit for bit
-      float4 x = ((const float4*)ps.grads[r])[i];
-      G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+    if (two_shot) {
+      G = __ldcg((const float4*)gp.gred[ps.rank] + i);   // written over NVLink by the slice owners: bypass L1
+    } else {
+      for (int r = 0; r < ps.world; ++r) {  // fixed rank order: every rank computes the same sum bit for bit
+        float4 x = ((const float4*)ps.grads[r])[i];
+        G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
+      }
     }
     float4 P = ((float4*)a.p)[i], M = ((float4*)a.m)[i], V = ((float4*)a.v)[i];
     P.x = adam_one2(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
@@ -381,7 +429,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     }
   }
   __syncthreads();
-  if (last_block) signal_all(ps, flag_index + 1, e);
+  if (last_block && !two_shot) signal_all(ps, flag_index + 1, e);
 }
 
 int fill_peers(PeerPtrs& ps, const void* const* grads_host, const void* const* flags_host, int world, int rank) {
@@ -492,9 +540,11 @@ extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_
                                   int64_t member_size, int64_t shadow_member, const void* const* grads_host,
                                   const void* const* flags_host, int world, int rank, int flag_index,
                                   const int* epoch, void* block_counter, float* small_vec, int small_n,
-                                  const void* const* xchg_host, int small_channel, void* stream) {
+                                  const void* const* xchg_host, int small_channel, const void* const* gred_host,
+                                  void* block_counter2, void* stream) {
   D3B_REQUIRE(n >= 0 && n % 4 == 0 && params && exp_avg && exp_avg_sq && step && epoch && block_counter,
               "adam_step_peer: bad arguments");
+  D3B_REQUIRE(!gred_host || block_counter2, "adam_step_peer: the two-shot exchange needs its own block counter");
   if (n == 0) return D3B_OK;
   PeerPtrs ps{};
   D3B_REQUIRE(fill_peers(ps, grads_host, flags_host, world, rank) == 0, "adam_step_peer: bad peer table");
@@ -521,9 +571,23 @@ extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_
       D3B_REQUIRE(sv.xchg[r], "adam_step_peer: null exchange block");
     }
   }
+  GredPtrs gp{};
+  if (gred_host)
+    for (int r = 0; r < world; ++r) {
+      gp.gred[r] = (float*)gred_host[r];
+      D3B_REQUIRE(gp.gred[r], "adam_step_peer: null reduced-gradient buffer");
+    }
+  // every block waits for the other blocks (and ranks) in the middle of the kernel: all must be co-resident
+  static int per_sm = 0;
+  if (!per_sm) {
+    D3B_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adam_allreduce_kernel, 256, 0));
+    if (per_sm > 2) per_sm = 2;
+    D3B_REQUIRE(per_sm >= 1, "adam_step_peer: kernel does not fit an SM");
+  }
   long long blocks = (n / 4 + 255) / 256;
-  if (blocks > 4 * d3b::kNumSM) blocks = 4 * d3b::kNumSM;  // every block spins on the flags: all must be resident
+  if (blocks > (long long)per_sm * d3b::kNumSM) blocks = (long long)per_sm * d3b::kNumSM;
   adam_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, segs, ps, flag_index, epoch,
-                                                                           (unsigned*)block_counter, sv);
+                                                                           (unsigned*)block_counter, sv, gp,
+                                                                           (unsigned*)block_counter2);
   return d3b::check_launch("adam_step_peer");
 }

@@ -446,6 +446,7 @@ class DenseNet:
 
             px, gptrs, fidx, cptr, eptr = peer[:5]
             small = peer[5] if len(peer) > 5 else None   # (tensor, channel): sums riding along with the exchange
+            gred, cptr2 = (peer[6], peer[7]) if len(peer) > 7 else (None, None)   # two-shot exchange buffers
             shadow = self.precision == "bf16" and self.fused_ok and self.head_out <= 16
             seg, nseg = None, 0
             if shadow:
@@ -459,7 +460,7 @@ class DenseNet:
                                  seg, nseg, a.member_size, self.shadow_member if shadow else 0, gptrs, px.flags_ptrs,
                                  px.world, px.rank, fidx, eptr, cptr, _p(small[0]) if small else None,
                                  small[0].numel() if small else 0, px.xchg_ptrs if small else None,
-                                 small[1] if small else 0, stream)
+                                 small[1] if small else 0, gred, cptr2, stream)
             if not shadow:
                 self.refresh_shadow("params", stream)
                 if sync:

@@ -121,7 +121,7 @@ class PeerExchange:
         self.world, self.rank = world_size, rank
         self.flags = torch.zeros(self.N_FLAGS * self.MAX_RANKS, dtype=torch.int32, device=device)
         self.xchg = torch.zeros(self.XCHG_FLOATS, dtype=torch.float32, device=device)
-        self.counters = torch.zeros(8, dtype=torch.int32, device=device)  # block counters of the fused Adam kernels
+        self.counters = torch.zeros(16, dtype=torch.int32, device=device)  # block counters of the fused Adam kernels
         torch.cuda.synchronize(device)
         self.flags_ptrs = self.register(self.flags)
         self.xchg_ptrs = self.register(self.xchg)
@@ -150,11 +150,23 @@ class PeerExchange:
         return ptrs
 
     def register_arena(self, grads: torch.Tensor):
-        """Gradient arena -> (peer pointer table, flag index of its {ready, done} pair, block counter pointer)."""
+        """Gradient arena -> (peer pointer table, flag index of its {ready, done, reduced} triple, block counter
+        pointer, peer pointer table of the reduced-gradient buffers, second block counter pointer).  The reduced-
+        gradient buffer (two-shot exchange, csrc/comm.cu) is allocated here, one per arena and rank."""
         i = self._next_arena
         self._next_arena += 1
-        assert 8 + 2 * i + 1 < self.N_FLAGS
-        return self.register(grads), 8 + 2 * i, self.counters.data_ptr() + 4 * i
+        assert 8 + 3 * i + 2 < self.N_FLAGS and i < 8
+        gred = torch.zeros_like(grads)
+        torch.cuda.synchronize(grads.device)
+        self._keep = getattr(self, "_keep", []) + [gred]
+        # two-shot costs one more rendezvous inside the kernel (~14 us measured at W = 2) and saves (W-1) - 2 (W-1)/W
+        # arena sizes of NVLink traffic: it pays for large arenas on many ranks (c5's 6.5 MB critic arena at W = 8: 45 MB
+        # -> 11 MB per rank and update), not for c2's 1.1 MB.  D3B_TWO_SHOT=0 forces one-shot, =2 forces two-shot.
+        mode = os.environ.get("D3B_TWO_SHOT", "1")
+        remote_read_bytes = (self.world - 1) * grads.numel() * 4
+        two_shot = mode == "2" or (mode != "0" and self.world > 2 and remote_read_bytes >= 16 * 1024 * 1024)
+        return (self.register(grads), 8 + 3 * i, self.counters.data_ptr() + 4 * i,
+                self.register(gred) if two_shot else None, self.counters.data_ptr() + 4 * (8 + i))
 
 
 def new_peers(device=None) -> Optional[PeerExchange]:

@@ -428,7 +428,12 @@ int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_sq, float* 
                        void* shadow_target, const int64_t* table_host, int n_segments, int64_t member_size,
                        int64_t shadow_member, const void* const* grads_host, const void* const* flags_host, int world,
                        int rank, int flag_index, const int* epoch, void* block_counter, float* small_vec, int small_n,
-                       const void* const* xchg_host, int small_channel, void* stream);
+                       const void* const* xchg_host, int small_channel, const void* const* gred_host,
+                       void* block_counter2, void* stream);
+/* gred_host (optional): every rank's reduced-gradient buffer (n floats each, peer-mapped) — selects the TWO-SHOT
+ * exchange: each rank sums its 1/W slice over all ranks and pushes it to everybody (reduce-scatter + all-gather inside
+ * the kernel, flag_index + 2 = "reduced" flag, block_counter2 = a second zero-initialised uint32), then every rank
+ * runs Adam from its local copy: 2 (W-1)/W arena sizes over NVLink per rank instead of W-1. */
 /* small_vec (<= 16 floats, optional): loss partial sums that ride along with the gradient exchange (in: this
  * rank's values, out: all-rank sums) through exchange channel small_channel. */
 
