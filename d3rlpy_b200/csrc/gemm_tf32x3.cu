@@ -171,11 +171,14 @@ __device__ __forceinline__ float4 load_chunk(const float* __restrict__ base, lon
   return v;
 }
 
-// x = hi + lo with hi and lo on the TF32 grid (x - hi is exact in fp32); written to the same offset of two buffers
+// x = hi + lo: hi = x rounded to the TF32 grid, lo = x - hi (exact in fp32, <= 13 significant bits), of which the
+// tensor core reads the leading 11 (kind::tf32 ignores the low 13 mantissa bits of its operands): the dropped part is
+// <= 2^-21 |x| with the sign of lo, i.e. unbiased with respect to x.  Three ALU ops per element — the producers are
+// instruction-issue bound (profiles/r2), rounding lo explicitly as well costs two more.
 __device__ __forceinline__ void split_store(uint8_t* hi_buf, uint8_t* lo_buf, uint32_t off, float4 v) {
   float4 h, l;
   h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-  l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
   *reinterpret_cast<float4*>(hi_buf + off) = h;
   *reinterpret_cast<float4*>(lo_buf + off) = l;
 }

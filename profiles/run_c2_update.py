@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d3rlpy_b200.algos import CQL  # noqa: E402
 
 O, A, B, N, H = 17, 6, 256, 10, [256, 256, 256]
-algo = CQL(actor_encoder_factory=H, critic_encoder_factory=H, n_action_samples=N, precision="bf16")
+PRECISION = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+algo = CQL(actor_encoder_factory=H, critic_encoder_factory=H, n_action_samples=N, precision=PRECISION)
 algo.create_impl((O,), A)
 algo.impl.use_graph = False
 rs = np.random.RandomState(0)
