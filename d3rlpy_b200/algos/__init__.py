@@ -7,3 +7,5 @@ from .sac import SAC  # noqa: F401
 from .td3 import TD3  # noqa: F401
 from .ddpg import DDPG  # noqa: F401
 from .iql import IQL  # noqa: F401
+from .awac import AWAC  # noqa: F401
+from .crr import CRR  # noqa: F401

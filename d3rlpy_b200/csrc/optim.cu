@@ -56,7 +56,8 @@ __device__ __forceinline__ float adam_one(float p, float g, float& m, float& v, 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    float* __restrict__ targ, long long n, const int* step, double lr,
-                                                   double b1, double b2, double eps, float tau, int zero_grad) {
+                                                   double b1, double b2, double eps, float tau, int zero_grad,
+                                                   float weight_decay) {
   float w1, fb2, w2, feps, neg_ss, bc2s;
   adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
   float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
@@ -65,6 +66,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += stride) {
     float4 P = ((float4*)p)[i], G = ((float4*)g)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+    if (weight_decay != 0.f) {   // torch.optim.Adam: grad = grad.add(param, alpha=weight_decay) (L2, not decoupled)
+      G.x = __fmaf_rn(weight_decay, P.x, G.x); G.y = __fmaf_rn(weight_decay, P.y, G.y);
+      G.z = __fmaf_rn(weight_decay, P.z, G.z); G.w = __fmaf_rn(weight_decay, P.w, G.w);
+    }
     P.x = adam_one(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
     P.y = adam_one(P.y, G.y, M.y, V.y, w1, fb2, w2, feps, neg_ss, bc2s);
     P.z = adam_one(P.z, G.z, M.z, V.z, w1, fb2, w2, feps, neg_ss, bc2s);
@@ -84,7 +89,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   }
   for (long long i = (n4 << 2) + tid; i < n; i += stride) {
     float M = m[i], V = v[i];
-    float P = adam_one(p[i], g[i], M, V, w1, fb2, w2, feps, neg_ss, bc2s);
+    float P = adam_one(p[i], weight_decay != 0.f ? __fmaf_rn(weight_decay, p[i], g[i]) : g[i], M, V, w1, fb2, w2, feps,
+                       neg_ss, bc2s);
     p[i] = P;
     m[i] = M;
     v[i] = V;
@@ -265,8 +271,24 @@ extern "C" int d3b_adam_step(float* params, float* grads, float* exp_avg, float*
                (uintptr_t)target) % 16 == 0,
               "adam_step: arenas must be 16-byte aligned");
   adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
-                                                                lr, beta1, beta2, eps, tau, zero_grad);
+                                                                lr, beta1, beta2, eps, tau, zero_grad, 0.f);
   return check_launch("adam_step");
+}
+
+// adam_step with torch.optim.Adam's weight_decay (L2 term added to the gradient): AWAC's actor optimizer
+// (d3rlpy/algos/awac.py:105, AdamFactory(weight_decay=1e-4))
+extern "C" int d3b_adam_step_wd(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target,
+                                int64_t n, const int* step, double lr, double beta1, double beta2, double eps,
+                                float weight_decay, float tau, int zero_grad, void* stream) {
+  D3B_REQUIRE(n >= 0 && weight_decay >= 0.f, "adam_step_wd: bad arguments");
+  if (n == 0) return D3B_OK;
+  D3B_REQUIRE(params && grads && exp_avg && exp_avg_sq && step, "adam_step_wd: null pointer");
+  D3B_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
+               (uintptr_t)target) % 16 == 0,
+              "adam_step_wd: arenas must be 16-byte aligned");
+  adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
+                                                                lr, beta1, beta2, eps, tau, zero_grad, weight_decay);
+  return check_launch("adam_step_wd");
 }
 
 // adam_step + bf16 shadow refresh in one pass.  table_host: n_segments x {param_off, rows, cols, shadow_off, ld}

@@ -203,6 +203,31 @@ int d3b_td_error(const float* q, int64_t stride_member, const float* rewards, co
                  const float* terminals, const float* gamma_rows, float gamma, int n, int members, int huber,
                  float* out, void* stream);
 
+/* ---- advantage-weighted actor steps over a non-squashed Gaussian policy (AWAC, CRR; csrc/awr.cu) -----------------
+ * dist = Normal(tanh(mu), exp(logstd)) (policies.py:160-181, distributions.py:33-88); logstd is the sigmoid-squashed
+ * parameter logstd_param[act_dim] when non-NULL (AWAC, policies.py:248-253), else the clamped head columns
+ * [act_dim, 2 act_dim) of `head` (CRR).
+ * gauss_policy_rows: x[b*n + k] = [obs_b | clamp(loc_b + scale * eps[k][b], -1, 1)], eps laid out (n, batch, act_dim).
+ * awr_weights: advantage = reduce_members(q_data)[b] - reduce_n(reduce_members(q_samples)[b*n + k]);
+ *   member_reduce 0 = min (AWAC, awac_impl.py:126-148), 1 = mean (CRR, crr_impl.py:104-141); value_reduce 0 = mean,
+ *   1 = max over the n samples; weight_mode 0 = softmax over the batch of adv / temperature, times batch
+ *   (awac_impl.py:150-154), 1 = clamp(exp(adv / temperature), 0, max_weight), 2 = [adv > 0] (crr_impl.py:94-102).
+ * gauss_wll_loss: loss = -scale * sum_b weights[b] * log pi(a_b | s_b) (awac_impl.py:103-116 with scale 1,
+ *   crr_impl.py:82-92 with scale 1 / batch), d loss / d head (mu columns; logstd columns for the head form) and the
+ *   accumulated gradient of the logstd parameter; metric_mean_std (optional) = mean exp(logstd parameter). */
+int d3b_gauss_mean_std(const float* logstd_param, float min_logstd, float max_logstd, int act_dim, float* out,
+                       void* stream);  /* mean_j exp(squashed logstd parameter): AWAC's `mean_std` metric (awac_impl.py:97-99) */
+int d3b_gauss_policy_rows(const float* head, int64_t ld_head, const float* logstd_param, float min_logstd,
+                          float max_logstd, const float* eps, const float* obs, int64_t ld_obs, float* x, int64_t ldx,
+                          int batch, int n, int obs_dim, int act_dim, void* stream);
+int d3b_awr_weights(const float* q_data, int64_t stride_q_data, const float* q_samples, int64_t stride_q_samples,
+                    int members, int batch, int n, int member_reduce, int value_reduce, int weight_mode,
+                    float temperature, float max_weight, float* weights, void* stream);
+int d3b_gauss_wll_loss(const float* head, int64_t ld_head, const float* logstd_param, const float* actions,
+                       int64_t ld_act, const float* weights, float min_logstd, float max_logstd, float scale,
+                       float* d_head, int64_t ld_dhead, float* dlogstd_param, float* metric_loss,
+                       float* metric_mean_std, int batch, int act_dim, void* stream);
+
 /* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
  * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
  *   VectorEncoderWithAction.forward (encoders.py:328-339) plus the repeat/transpose/reshape of
@@ -378,6 +403,11 @@ int d3b_col2im(const float* dpatch, int64_t ldp, int64_t stride_p, const void* y
 int d3b_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
                   const int* step, double lr, double beta1, double beta2, double eps, float tau, int zero_grad,
                   void* stream);
+/* adam_step with torch.optim.Adam's weight_decay: grad += weight_decay * param before the moments (AWAC's actor
+ * optimizer, d3rlpy/algos/awac.py:105). */
+int d3b_adam_step_wd(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,
+                     const int* step, double lr, double beta1, double beta2, double eps, float weight_decay, float tau,
+                     int zero_grad, void* stream);
 /* adam_step that also rewrites the bf16 K-major weight shadows (params and, when synced, target) in the same
  * pass; table_host: n_segments x {param_off, rows, cols, shadow_off, ld} int64 per trunk weight matrix. */
 int d3b_adam_step_shadow(float* params, float* grads, float* exp_avg, float* exp_avg_sq, float* target, int64_t n,

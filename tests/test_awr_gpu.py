@@ -1,0 +1,113 @@
+"""GPU: AWAC and CRR (`algo.update(batch)` through the public API) against the golden vectors recorded from the
+unmodified reference (tests/golden/update_awac.npz, make_golden_awac.py): identical weights, minibatches and injected
+noise; metrics per step and post-update parameters (incl. target networks and the logstd parameter).
+Tolerance: 1e-5 relative in fp32 mode (eager and graph), bf16 mode: metrics 1e-2, update relative L2 <= 0.3."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_io import Case, load_awac
+from tests.test_update_gpu import BF16_REL, BF16_UPDATE_REL, REL, _assert_metrics, _assert_params, _assert_update
+
+pytestmark = pytest.mark.gpu
+
+
+def _ns(arrays):
+    return SimpleNamespace(**arrays)
+
+
+def _load(impl, case):
+    impl.q_function.load_state_dict(case.group("init", "q"))
+    impl.targ_q_function.load_state_dict(case.group("init", "q"))
+    impl.policy.load_state_dict(case.group("init", "pi"))
+    impl.targ_policy.load_state_dict(case.group("init", "pi"))
+
+
+def _check_final(impl, case, precision):
+    for grp, view in (("q", impl.q_function), ("pi", impl.policy), ("targ_q", impl.targ_q_function),
+                      ("targ_pi", impl.targ_policy)):
+        if precision == "fp32":
+            _assert_params(view.state_dict(), case.group("final", grp), grp, rel=REL)
+        if grp in ("q", "pi"):
+            _assert_update(view.state_dict(), case.group("final", grp), case.group("init", grp), grp,
+                           1e-3 if precision == "fp32" else BF16_UPDATE_REL)
+
+
+@pytest.mark.parametrize("name,precision,use_graph", [("awac", "fp32", False), ("awac", "fp32", True),
+                                                      ("awac_n4", "fp32", True), ("awac_n4", "bf16", True)])
+def test_awac_matches_reference_golden(name, precision, use_graph):
+    from d3rlpy_b200.algos import AWAC
+
+    case = Case(load_awac(), name)
+    c = case.cfg
+    B = int(c["batch"])
+    algo = AWAC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=B,
+                n_action_samples=int(c["n_action_samples"]), update_actor_interval=int(c["update_actor_interval"]),
+                lam=float(c["lam"]), precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    _load(impl, case)
+    assert list(impl.policy.state_dict().keys())[0] == "_logstd"   # the parameter precedes the sub-modules
+    rel = REL if precision == "fp32" else BF16_REL
+    for s in range(case.steps):
+        noise = case.noise(s)   # the weights draw only exists on actor steps
+        impl.inject_noise(noise, B, names=["target", "weights"][:len(noise)])
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    _check_final(impl, case, precision)
+    assert algo.grad_step == case.steps
+
+
+@pytest.mark.parametrize("name,precision,use_graph", [("crr", "fp32", False), ("crr", "fp32", True),
+                                                      ("crr_binary_max_soft", "fp32", True), ("crr", "bf16", True)])
+def test_crr_matches_reference_golden(name, precision, use_graph):
+    from d3rlpy_b200.algos import CRR
+
+    case = Case(load_awac(), name)
+    c = case.cfg
+    B = int(c["batch"])
+    algo = CRR(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=B, beta=float(c["beta"]),
+               n_action_samples=int(c["n_action_samples"]), advantage_type="max" if c["adv_max"] else "mean",
+               weight_type="binary" if c["binary"] else "exp", max_weight=float(c["max_weight"]),
+               target_update_type="hard" if c["hard"] else "soft", target_update_interval=int(c["target_update_interval"]),
+               n_critics=len({k.split(".")[1] for k in case.group("init", "q")}), precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    _load(impl, case)
+    rel = REL if precision == "fp32" else BF16_REL
+    for s in range(case.steps):
+        impl.inject_noise(case.noise(s), B)
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    _check_final(impl, case, precision)
+
+
+def test_awac_hooks_and_predict():
+    """update_critic / update_actor / compute_actor_loss on their own, predict / sample_action shapes."""
+    from d3rlpy_b200.algos import AWAC
+
+    case = Case(load_awac(), "awac")
+    c = case.cfg
+    B = int(c["batch"])
+    algo = AWAC(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=B)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    _load(impl, case)
+    ref = case.step_metrics(0)
+    impl.inject_noise(case.noise(0), B)
+    b = _ns(case.batch(0))
+    loss0 = float(impl.compute_actor_loss(b))          # before the critic step: finite, nothing stepped
+    assert np.isfinite(loss0)
+    c_loss = float(impl.update_critic(b))
+    assert abs(c_loss - ref["critic_loss"]) <= REL * max(1.0, abs(ref["critic_loss"]))
+    a_loss, mean_std = impl.update_actor(b)
+    assert abs(float(a_loss) - ref["actor_loss"]) <= REL * max(1.0, abs(ref["actor_loss"]))
+    assert abs(float(mean_std) - ref["mean_std"]) <= REL
+    x = np.asarray(case.batch(0)["observations"])
+    assert algo.predict(x).shape == (B, int(c["act"])) and algo.sample_action(x).shape == (B, int(c["act"]))
+    v = algo.predict_value(x, np.asarray(case.batch(0)["actions"]))
+    assert v.shape == (B,)
