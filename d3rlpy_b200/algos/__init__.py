@@ -9,3 +9,4 @@ from .ddpg import DDPG  # noqa: F401
 from .iql import IQL  # noqa: F401
 from .awac import AWAC  # noqa: F401
 from .crr import CRR  # noqa: F401
+from .plas import PLAS  # noqa: F401

@@ -236,3 +236,57 @@ extern "C" int d3b_gauss_wll_loss(const float* head, int64_t ld_head, const floa
              dlogstd_param, metric_loss, metric_mean_std, batch, act_dim);
   return check_launch("gauss_wll_loss");
 }
+
+// ---- PLAS glue (d3rlpy/algos/torch/plas_impl.py:138-168): the deterministic policy acts in the VAE's latent space,
+// action = decode(s, 2 * tanh(fc(encoder(s)))).
+namespace d3b {
+
+// x[b] = [obs_b | scale * z_b]
+__global__ void scaled_concat_rows_kernel(const float* __restrict__ obs, long long ldo, const float* __restrict__ z,
+                                          long long ldz, float scale, float* __restrict__ x, long long ldx, int B, int O,
+                                          int Z) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = O + Z;
+  if (i >= (long long)B * W) return;
+  const int b = (int)(i / W), j = (int)(i % W);
+  x[(long long)b * ldx + j] = j < O ? __ldg(obs + (long long)b * ldo + j) : scale * __ldg(z + (long long)b * ldz + (j - O));
+}
+
+// out = scale * dy * (1 - y^2): gradient through y = tanh(pre) (and through the scale of the latent)
+__global__ void tanh_backward_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ y,
+                                     long long ldy, float scale, float* __restrict__ out, long long ldo, int rows,
+                                     int cols) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i % cols);
+  const float v = __ldg(y + (long long)r * ldy + c);
+  out[(long long)r * ldo + c] = scale * __ldg(dy + (long long)r * lddy + c) * (1.f - v * v);
+}
+
+}  // namespace d3b
+
+extern "C" int d3b_scaled_concat_rows(const float* obs, int64_t ldo, const float* z, int64_t ldz, float scale, float* x,
+                                      int64_t ldx, int batch, int obs_dim, int z_dim, void* stream) {
+  D3B_REQUIRE(batch >= 0 && obs_dim >= 0 && z_dim >= 1, "scaled_concat_rows: bad sizes");
+  if (batch == 0) return D3B_OK;
+  D3B_REQUIRE(z && x && (obs || obs_dim == 0), "scaled_concat_rows: null pointer");
+  const long long n = (long long)batch * (obs_dim + z_dim);
+  launch_pdl(scaled_concat_rows_kernel, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, (cudaStream_t)stream, obs,
+             (long long)ldo, z, (long long)ldz, scale, x, (long long)ldx, batch, obs_dim, z_dim);
+  return check_launch("scaled_concat_rows");
+}
+
+extern "C" int d3b_tanh_backward(const float* dy, int64_t lddy, const float* y, int64_t ldy, float scale, float* out,
+                                 int64_t ldo, int rows, int cols, void* stream) {
+  D3B_REQUIRE(rows >= 0 && cols >= 1, "tanh_backward: bad sizes");
+  if (rows == 0) return D3B_OK;
+  D3B_REQUIRE(dy && y && out, "tanh_backward: null pointer");
+  const long long n = (long long)rows * cols;
+  launch_pdl(tanh_backward_kernel, dim3((unsigned)ceil_div_ll(n, 256)), dim3(256), 0, (cudaStream_t)stream, dy,
+             (long long)lddy, y, (long long)ldy, scale, out, (long long)ldo, rows, cols);
+  return check_launch("tanh_backward");
+}

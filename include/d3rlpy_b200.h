@@ -228,6 +228,13 @@ int d3b_gauss_wll_loss(const float* head, int64_t ld_head, const float* logstd_p
                        float* d_head, int64_t ld_dhead, float* dlogstd_param, float* metric_loss,
                        float* metric_mean_std, int batch, int act_dim, void* stream);
 
+/* PLAS glue (plas_impl.py:138-168): scaled_concat_rows x[b] = [obs_b | scale * z_b] (the latent action 2 * pi(s) next
+ * to the observation, the decoder's input); tanh_backward out = scale * dy * (1 - y^2) for y = tanh(pre). */
+int d3b_scaled_concat_rows(const float* obs, int64_t ldo, const float* z, int64_t ldz, float scale, float* x, int64_t ldx,
+                           int batch, int obs_dim, int z_dim, void* stream);
+int d3b_tanh_backward(const float* dy, int64_t lddy, const float* y, int64_t ldy, float scale, float* out, int64_t ldo,
+                      int rows, int cols, void* stream);
+
 /* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
  * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
  *   VectorEncoderWithAction.forward (encoders.py:328-339) plus the repeat/transpose/reshape of

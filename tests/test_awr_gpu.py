@@ -111,3 +111,38 @@ def test_awac_hooks_and_predict():
     assert algo.predict(x).shape == (B, int(c["act"])) and algo.sample_action(x).shape == (B, int(c["act"]))
     v = algo.predict_value(x, np.asarray(case.batch(0)["actions"]))
     assert v.shape == (B,)
+
+
+@pytest.mark.parametrize("precision,use_graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_plas_matches_reference_golden(precision, use_graph):
+    """PLAS: two VAE warm-up steps, then critic every step and the latent-policy actor step every other step
+    (tests/golden/update_awac.npz "plas", recorded from the unmodified reference)."""
+    from d3rlpy_b200.algos import PLAS
+
+    case = Case(load_awac(), "plas")
+    c = case.cfg
+    B = int(c["batch"])
+    algo = PLAS(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], imitator_encoder_factory=[48, 48],
+                batch_size=B, warmup_steps=int(c["warmup_steps"]), update_actor_interval=int(c["update_actor_interval"]),
+                lam=float(c["lam"]), precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    impl = algo.impl
+    impl.use_graph = use_graph
+    _load(impl, case)
+    impl.imitator.load_state_dict(case.group("init", "imitator"))
+    rel = REL if precision == "fp32" else BF16_REL
+    for s in range(case.steps):
+        noise = case.noise(s)
+        if noise:
+            impl.inject_noise(noise, B)
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"plas {precision} step {s}", rel=rel)
+    for grp, view in (("q", impl.q_function), ("pi", impl.policy), ("imitator", impl.imitator),
+                      ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy)):
+        if precision == "fp32":
+            _assert_params(view.state_dict(), case.group("final", grp), grp, rel=REL)
+        if grp in ("q", "pi", "imitator"):
+            _assert_update(view.state_dict(), case.group("final", grp), case.group("init", grp), grp,
+                           1e-3 if precision == "fp32" else BF16_UPDATE_REL)
+    x = np.asarray(case.batch(0)["observations"])
+    assert algo.predict(x).shape == (B, int(c["act"]))
