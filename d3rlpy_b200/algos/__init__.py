@@ -10,3 +10,4 @@ from .iql import IQL  # noqa: F401
 from .awac import AWAC  # noqa: F401
 from .crr import CRR  # noqa: F401
 from .plas import PLAS  # noqa: F401
+from .bear import BEAR  # noqa: F401

@@ -235,6 +235,29 @@ int d3b_scaled_concat_rows(const float* obs, int64_t ldo, const float* z, int64_
 int d3b_tanh_backward(const float* dy, int64_t lddy, const float* y, int64_t ldy, float scale, float* out, int64_t ldo,
                       int rows, int cols, void* stream);
 
+/* ---- BEAR (csrc/bear.cu; d3rlpy/algos/torch/bear_impl.py) ----------------------------------------------------------
+ * bear_latent_rows: x[k*batch + b] = [obs_b | clamp(latent[k*batch + b], +-clip)], the decoder input of
+ *   ConditionalVAE.sample_n_without_squash (imitators.py:94-118; rows in sample-major order).
+ * bear_mmd: per observation the MMD (bear_impl.py:233-281) between the n raw policy samples mu + exp(clamp(logstd)) *
+ *   eps[k][b] (head = mu | logstd) and the n raw decoder outputs behavior_raw[k*batch + b]; Laplacian or Gaussian kernel
+ *   (bear_impl.py:27-38); sum_out[0] += sum_b (sqrt(mmd_b + 1e-6) - threshold); when d_head is non-NULL the gradient of
+ *   exp(log_alpha) * inv_batch * sum_b mmd_b w.r.t. the policy head is ADDED to d_head.
+ * bear_alpha_step: update_alpha (bear_impl.py:215-231) from that sum: loss, Adam on log_alpha ({p,g,m,v} at float
+ *   offsets 0,4,8,12), clamp to [-5, 10], metrics.  bear_actor_metric: [SAC actor loss] + exp(log_alpha) * mean(mmd - thr).
+ * bear_target: compute_target (bear_impl.py:283-303) from q[members][batch*n] and logp[batch*n]. */
+int d3b_bear_latent_rows(const float* obs, int64_t ldo, const float* latent, float clip, float* x, int64_t ldx, int batch,
+                         int n, int obs_dim, int latent_dim, void* stream);
+int d3b_bear_mmd(const float* head, int64_t ld_head, const float* eps, const float* behavior_raw, int64_t ld_behavior,
+                 int gaussian_kernel, float sigma, float min_logstd, float max_logstd, const float* log_alpha,
+                 float threshold, float inv_batch, float* d_head, int64_t ld_dhead, float* sum_out, int batch, int n,
+                 int act_dim, void* stream);
+int d3b_bear_alpha_step(const float* mmd_sum, float* alpha_scalar, const int* step, double lr, float inv_batch,
+                        float* metric_loss, float* metric_alpha, void* stream);
+int d3b_bear_actor_metric(const float* sac_loss, const float* mmd_sum, const float* log_alpha, float inv_batch,
+                          float* metric, void* stream);
+int d3b_bear_target(const float* q, int64_t stride_q, const float* logp, const float* log_temp, float lam, float* q_tpn,
+                    int batch, int n, int members, void* stream);
+
 /* ---- K4-K7: row assembly, sampling, losses ---------------------------------------
  * concat_rows: x[b*n+k] = [obs[b] | f(act[b*n+k])]  — torch.cat([x, action]) of
  *   VectorEncoderWithAction.forward (encoders.py:328-339) plus the repeat/transpose/reshape of

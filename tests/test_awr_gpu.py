@@ -1,4 +1,4 @@
-"""GPU: AWAC and CRR (`algo.update(batch)` through the public API) against the golden vectors recorded from the
+"""GPU: AWAC, CRR, PLAS and BEAR (`algo.update(batch)` through the public API) against the golden vectors recorded from the
 unmodified reference (tests/golden/update_awac.npz, make_golden_awac.py): identical weights, minibatches and injected
 noise; metrics per step and post-update parameters (incl. target networks and the logstd parameter).
 Tolerance: 1e-5 relative in fp32 mode (eager and graph), bf16 mode: metrics 1e-2, update relative L2 <= 0.3."""
@@ -146,3 +146,77 @@ def test_plas_matches_reference_golden(precision, use_graph):
                            1e-3 if precision == "fp32" else BF16_UPDATE_REL)
     x = np.asarray(case.batch(0)["observations"])
     assert algo.predict(x).shape == (B, int(c["act"]))
+
+
+_BEAR_NOISE = ["imitator", "temp", "mmd_lat_alpha", "mmd_eps_alpha", "target", "actor", "mmd_lat_actor", "mmd_eps_actor"]
+
+
+def _bear(case, precision):
+    from d3rlpy_b200.algos import BEAR
+
+    c = case.cfg
+    algo = BEAR(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], imitator_encoder_factory=[48, 48],
+                batch_size=int(c["batch"]), warmup_steps=int(c["warmup_steps"]),
+                n_target_samples=int(c["n_target_samples"]), n_mmd_action_samples=int(c["n_mmd_action_samples"]),
+                mmd_kernel="gaussian" if c["gaussian"] else "laplacian", mmd_sigma=float(c["mmd_sigma"]),
+                lam=float(c["lam"]), precision=precision)
+    algo.create_impl((int(c["obs"]),), int(c["act"]))
+    _load(algo.impl, case)
+    algo.impl.imitator.load_state_dict(case.group("init", "imitator"))
+    return algo
+
+
+def _bear_noise_names(noise):
+    # the SAC actor draw only exists after warm-up (7 draws during warm-up, 8 afterwards)
+    return _BEAR_NOISE if len(noise) == 8 else [n for n in _BEAR_NOISE if n != "actor"]
+
+
+@pytest.mark.parametrize("name,precision,use_graph", [("bear", "fp32", False), ("bear", "fp32", True),
+                                                      ("bear_gaussian", "fp32", True), ("bear", "bf16", True)])
+def test_bear_matches_reference_golden(name, precision, use_graph):
+    """BEAR: two warm-up steps (actor on the MMD loss alone), then SAC + MMD actor steps; Laplacian and Gaussian
+    kernels (tests/golden/update_awac.npz "bear" / "bear_gaussian", recorded from the unmodified reference)."""
+    case = Case(load_awac(), name)
+    B = int(case.cfg["batch"])
+    algo = _bear(case, precision)
+    impl = algo.impl
+    impl.use_graph = use_graph
+    rel = REL if precision == "fp32" else BF16_REL
+    for s in range(case.steps):
+        noise = case.noise(s)
+        impl.inject_noise(noise, B, names=_bear_noise_names(noise))
+        m = algo.update(_ns(case.batch(s)))
+        _assert_metrics(m, case.step_metrics(s), f"{name} {precision} step {s}", rel=rel)
+    for grp, view in (("q", impl.q_function), ("pi", impl.policy), ("imitator", impl.imitator),
+                      ("targ_q", impl.targ_q_function), ("targ_pi", impl.targ_policy), ("log_temp", impl._log_temp),
+                      ("log_alpha", impl._log_alpha)):
+        if precision == "fp32":
+            _assert_params(view.state_dict(), case.group("final", grp), grp, rel=REL)
+        if grp in ("q", "pi", "imitator"):
+            _assert_update(view.state_dict(), case.group("final", grp), case.group("init", grp), grp,
+                           1e-3 if precision == "fp32" else BF16_UPDATE_REL)
+    x = np.asarray(case.batch(0)["observations"])
+    assert algo.predict(x).shape == (B, int(case.cfg["act"]))
+
+
+def test_bear_hooks():
+    """The reference hooks one by one reproduce the first golden step's metrics."""
+    case = Case(load_awac(), "bear")
+    B = int(case.cfg["batch"])
+    algo = _bear(case, "fp32")
+    impl = algo.impl
+    ref, b, noise = case.step_metrics(0), _ns(case.batch(0)), case.noise(0)
+    close = lambda got, key: abs(float(got) - ref[key]) <= REL * max(1.0, abs(ref[key]))
+    impl.inject_noise(noise, B, names=_bear_noise_names(noise))
+    assert close(impl.update_imitator(b), "imitator_loss")
+    t_loss, temp = impl.update_temp(b)
+    assert close(t_loss, "temp_loss") and close(temp, "temp")
+    a_loss, alpha = impl.update_alpha(b)
+    assert close(a_loss, "alpha_loss") and close(alpha, "alpha")
+    assert impl.compute_target(b).shape == (B, 1)
+    assert close(impl.update_critic(b), "critic_loss")
+    assert close(impl.warmup_actor(b), "actor_loss")
+    with pytest.raises(ValueError):
+        from d3rlpy_b200.algos import BEAR
+
+        BEAR(mmd_kernel="cauchy").create_impl((6,), 3)
