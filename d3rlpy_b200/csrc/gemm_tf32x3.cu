@@ -54,6 +54,8 @@ struct Params {
   const float* mask; long long ldmask, sMask; int vecMask;
   float* colsum; long long sColsum;
   int atomic;
+  int csplit;      // > 1: the `splits` CTAs of one output tile form a thread-block cluster and reduce their partial
+                   // tiles through distributed shared memory in the epilogue (fixed order, full bias / ReLU / mask epilogue)
   int variant;     // profiling only: bit 0 skip global loads, bit 1 skip smem stores, bit 2 skip MMAs
   long long* dbg;  // optional: 64 clock64() phase stamps per CTA (profiles/r2/tc32_phase_probe.py)
 };
@@ -129,6 +131,31 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
+}
+// thread-block cluster helpers (cluster split-K epilogue)
+// Cluster-wide barrier for the shared-memory tile exchange.  `barrier.cluster.arrive.release` lowers to
+// MEMBAR.ALL.GPU + ERRBAR in SASS and measured ~4.4 k cycles here (profiles/r2/r2_tc32_phase_c.log) — more than the
+// whole main loop of a split tile.  What the exchange needs is only that this thread's st.shared are performed
+// before its arrival: a CTA-scope fence (MEMBAR.ALL.CTA, tens of cycles) and a relaxed arrive.
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile(
+      "fence.acq_rel.cta;\n\t"
+      "barrier.cluster.arrive.relaxed.aligned;\n\t"
+      "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra));   // volatile keeps it behind the cluster barrier; no memory clobber: loads may overlap
+  return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -261,7 +288,6 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();  // setup done
 
   if (warp == 8) {
@@ -270,28 +296,39 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
       // instruction descriptor: D = f32 (bit 4), A = B = tf32 (2 at bits 7 and 10), majors at bits 15 / 16
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (A_RC ? 0u : (1u << 15)) |
                              (B_RC ? 0u : (1u << 16)) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % STAGES;
-        mbar_wait(full + s, (i / STAGES) & 1);
-        if (dbg && i < 6) dbg[32 + 2 * i] = clock64();      // stage i landed
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint8_t* st = smem + s * stage_bytes;
-        const uint32_t a_hi = smem_u32(st), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
-        const uint64_t dah = A_RC ? desc_k(a_hi) : desc_mn(a_hi), dal = A_RC ? desc_k(a_lo) : desc_mn(a_lo);
-        const uint64_t dbh = B_RC ? desc_k(b_hi) : desc_mn(b_hi), dbl = B_RC ? desc_k(b_lo) : desc_mn(b_lo);
-        // one UMMA_K = 8 step: K-major +32 B inside the swizzle row, MN-major +8 reduction rows (1024 B)
-        constexpr uint64_t ka = A_RC ? 2 : 64, kbs = B_RC ? 2 : 64;
-        if (!(p.variant & 4))
+      // operand descriptors of every stage, built while the first tiles are still in flight
+      uint64_t dah[STAGES], dal[STAGES], dbh[STAGES], dbl[STAGES];
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
-          mma_tf32(tmem_base, dal + ka * k, dbh + kbs * k, idesc, first);      // correction accumulator
-          mma_tf32(tmem_base, dah + ka * k, dbl + kbs * k, idesc, 1u);
-          mma_tf32(tmem_base + (uint32_t)BN, dah + ka * k, dbh + kbs * k, idesc, first);
+      for (int s = 0; s < STAGES; ++s) {
+        const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+        dah[s] = A_RC ? desc_k(a_hi) : desc_mn(a_hi); dal[s] = A_RC ? desc_k(a_lo) : desc_mn(a_lo);
+        dbh[s] = B_RC ? desc_k(b_hi) : desc_mn(b_hi); dbl[s] = B_RC ? desc_k(b_lo) : desc_mn(b_lo);
+      }
+      // one UMMA_K = 8 step: K-major +32 B inside the swizzle row, MN-major +8 reduction rows (1024 B)
+      constexpr uint64_t ka = A_RC ? 2 : 64, kbs = B_RC ? 2 : 64;
+      const bool run = !(p.variant & 4);
+      for (int i0 = 0; i0 < nkb; i0 += STAGES) {
+        const uint32_t par = (uint32_t)(i0 / STAGES) & 1u;
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+          const int i = i0 + s;
+          if (i >= nkb) break;
+          mbar_wait(full + s, par);
+          if (dbg && i < 6) dbg[32 + 2 * i] = clock64();      // stage i landed
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (run) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
+              mma_tf32(tmem_base, dal[s] + ka * k, dbh[s] + kbs * k, idesc, first);      // correction accumulator
+              mma_tf32(tmem_base, dah[s] + ka * k, dbl[s] + kbs * k, idesc, 1u);
+              mma_tf32(tmem_base + (uint32_t)BN, dah[s] + ka * k, dbh[s] + kbs * k, idesc, first);
+            }
+          }
+          mma_commit(empty + s);   // the stage may be refilled once these MMAs have read it
+          if (dbg && i < 6) dbg[33 + 2 * i] = clock64();      // stage i issued
         }
-        mma_commit(empty + s);   // the stage may be refilled once these MMAs have read it
-        if (dbg && i < 6) dbg[33 + 2 * i] = clock64();      // stage i issued
       }
       mma_commit(tmem_full);
     }
@@ -300,10 +337,6 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
     const int t = threadIdx.x;
     const float* A = p.A + (long long)e * p.sA;
     const float* B = p.B + (long long)e * p.sB;
-    if (p.bias) {
-      const float* bias = p.bias + (long long)e * p.sBias;
-      for (int j = t; j < BN; j += PROD_THREADS) bias_s[j] = (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
-    }
     constexpr int GT = PROD_THREADS / G;   // threads per producer group
     constexpr int NCH = 2 * G;             // chunks per thread per operand and K block
     const int grp = t / GT, tg = t % GT;
@@ -338,6 +371,14 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
       pb[i] = B_RC ? B + (long long)xb * p.ldb + b_k[i] : B + (long long)b_k[i] * p.ldb + xb;
       pa[i] += a_step * (kb_begin + grp);
       pb[i] += b_step * (kb_begin + grp);
+    }
+    // everything above is index arithmetic: under programmatic dependent launch it overlaps the previous kernel's
+    // tail; the first global access follows (the MMA warp touches no global memory and does not wait)
+    pdl_wait();
+    if (dbg && t == 0) dbg[61] = clock64();           // load plan ready, dependencies resolved
+    if (p.bias) {
+      const float* bias = p.bias + (long long)e * p.sBias;
+      for (int j = t; j < BN; j += PROD_THREADS) bias_s[j] = (n0 + j < p.N) ? __ldg(bias + n0 + j) : 0.f;
     }
     for (int i = grp; i < nkb; i += G) {
       // ---- this group's K block i: loads, then (once the stage is free) split + stores, fence, arrive
@@ -401,8 +442,11 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
     }
     // ---- epilogue.  Phase 1: thread = accumulator row 32*(warp%4)+lane, column half warp/4: TMEM -> (+bias, ReLU)
     // -> fp32 tile in the (now idle) operand stages.  Phase 2: coalesced 16-byte stores / REDs with the ReLU mask.
+    // Cluster split-K (csplit > 1): phase 1 stages the raw partial tile; phase 2 of CTA rank q sums rows
+    // [q BM/S, (q+1) BM/S) of all S partial tiles through distributed shared memory in rank order, then bias / ReLU.
     const int ldfs = BN + 4;
     float* f_s = (float*)smem;
+    const bool ep1 = p.csplit <= 1;
     if (dbg && t == 0) dbg[2] = clock64();            // mainloop (producer side) done
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
@@ -433,46 +477,96 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
       for (int j = 0; j < 32; j += 4) {
         float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                __uint_as_float(v[j + 3]));
-        if (p.bias) {
+        if (ep1 && p.bias) {
           const float4 bv = *reinterpret_cast<const float4*>(bias_s + c + j);
           o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
         }
-        if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        if (ep1 && p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
         *reinterpret_cast<float4*>(f_s + row * ldfs + c + j) = o;
       }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    // thread t owns the fixed 16-byte column group (t % (BN/4)) and rows t / (BN/4) + k * (1024 / BN)
-    float* C = p.C + (long long)e * p.sC;
-    const float* mask = p.mask ? p.mask + (long long)e * p.sMask : nullptr;
-    const int lg4 = p.lg_bn - 2;
-    const int col = (t & ((1 << lg4) - 1)) << 2, row0 = t >> lg4, row_step = PROD_THREADS >> lg4;
-    const int n = n0 + col;
-    const int rows_here = min(BM, p.M - m0);
-    const bool col_full = n + 3 < p.N, col_any = n < p.N;
-    const bool fast = col_full && p.vecC && (!mask || p.vecMask);
-    float* dst = C + (long long)(m0 + row0) * p.ldc + n;
-    const float* mp = mask ? mask + (long long)(m0 + row0) * p.ldmask + n : nullptr;
-    const float* src = f_s + row0 * ldfs + col;
-    const long long dstep = (long long)row_step * p.ldc, mstep = (long long)row_step * p.ldmask;
+  }
+  const int S = p.csplit > 1 ? p.csplit : 1;
+  // phase-2 ownership: thread t owns the fixed 16-byte column group (t % (BN/4)) and rows t / (BN/4) + k * (1024 / BN)
+  const int ldfs = BN + 4;
+  const float* f_s = (const float*)smem;
+  float* C = p.C + (long long)e * p.sC;
+  const float* mask = p.mask ? p.mask + (long long)e * p.sMask : nullptr;
+  const int lg4 = p.lg_bn - 2;
+  const int t2 = threadIdx.x & (PROD_THREADS - 1);
+  const int col = (t2 & ((1 << lg4) - 1)) << 2, row0 = t2 >> lg4, row_step = PROD_THREADS >> lg4;
+  const int n = n0 + col;
+  const int rows_here = min(BM, p.M - m0);
+  const bool col_full = n + 3 < p.N, col_any = n < p.N;
+  const bool fast = col_full && p.vecC && (!mask || p.vecMask);
+  int r_lo = 0, r_hi = rows_here;
+  if (S > 1) {
+    const int slab = BM / S, q = (int)cluster_ctarank();
+    r_lo = q * slab;
+    r_hi = min(rows_here, r_lo + slab);
+  }
+  // ReLU mask of the first four owned rows: its L2 round trip overlaps the barrier below
+  float4 mk0[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    mk0[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+    const int rr = r_lo + row0 + u * row_step;
+    if (warp != 8 && mask && fast && rr < r_hi) mk0[u] = __ldg((const float4*)(mask + (long long)(m0 + rr) * p.ldmask + n));
+  }
+  __syncwarp();
+  const long long t_staged = dbg ? clock64() : 0;     // partial tile staged (stored after the barrier: no store in flight)
+  if (S > 1) cluster_sync();                          // every CTA of the cluster has staged its partial tile
+  else if (warp != 8) asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (dbg && (threadIdx.x == 0 || threadIdx.x == 256)) {
+    const long long t_all = clock64();                // partial tiles of the whole cluster staged
+    dbg[threadIdx.x == 0 ? 62 : 58] = t_staged;
+    dbg[threadIdx.x == 0 ? 63 : 59] = t_all;
+  }
+  if (warp != 8) {
+    // row rr of the finished tile, this thread's four columns.  Cluster mode: the S partial rows are fetched with S
+    // independent distributed-shared-memory loads in flight (215-cycle round trips), then summed in rank order.
+    auto fetch = [&](int rr) -> float4 {
+      const float* sp = f_s + rr * ldfs + col;
+      if (S == 1) return *reinterpret_cast<const float4*>(sp);
+      const uint32_t la = smem_u32(sp);
+      float4 part[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < S) part[j] = ld_dsmem_f4(la, (uint32_t)j);
+      float4 acc = part[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j)
+        if (j < S) { acc.x += part[j].x; acc.y += part[j].y; acc.z += part[j].z; acc.w += part[j].w; }
+      if (p.bias) {
+        const float4 bv = *reinterpret_cast<const float4*>(bias_s + col);
+        acc.x += bv.x; acc.y += bv.y; acc.z += bv.z; acc.w += bv.w;
+      }
+      if (p.relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      return acc;
+    };
     if (fast) {
-      for (int r = row0; r < rows_here; r += 4 * row_step) {
+      for (int r = r_lo + row0; r < r_hi; r += 4 * row_step) {
         float4 val[4], mk[4];
+        const bool first = r == r_lo + row0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          val[u] = *reinterpret_cast<const float4*>(src + (long long)u * row_step * ldfs);
-          mk[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (mask && r + u * row_step < rows_here) mk[u] = __ldg((const float4*)(mp + u * mstep));
+          const int rr = r + u * row_step;
+          mk[u] = mk0[u];
+          if (rr < r_hi) {
+            if (mask && !first) mk[u] = __ldg((const float4*)(mask + (long long)(m0 + rr) * p.ldmask + n));
+            val[u] = fetch(rr);
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (r + u * row_step >= rows_here) break;
+          const int rr = r + u * row_step;
+          if (rr >= r_hi) break;
           float4 o = val[u];
           if (mask) {
             o.x = mk[u].x > 0.f ? o.x : 0.f; o.y = mk[u].y > 0.f ? o.y : 0.f;
             o.z = mk[u].z > 0.f ? o.z : 0.f; o.w = mk[u].w > 0.f ? o.w : 0.f;
           }
-          float* d = dst + u * dstep;
+          float* d = C + (long long)(m0 + rr) * p.ldc + n;
           if (p.atomic)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(o.x), "f"(o.y), "f"(o.z),
                          "f"(o.w)
@@ -480,13 +574,13 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
           else
             *reinterpret_cast<float4*>(d) = o;
         }
-        src += 4 * row_step * ldfs; dst += 4 * dstep;
-        if (mask) mp += 4 * mstep;
       }
     } else if (col_any) {
-      for (int r = row0; r < rows_here; r += row_step) {
-        const float4 o4 = *reinterpret_cast<const float4*>(src);
+      for (int rr = r_lo + row0; rr < r_hi; rr += row_step) {
+        const float4 o4 = fetch(rr);
         const float tmp[4] = {o4.x, o4.y, o4.z, o4.w};
+        float* dst = C + (long long)(m0 + rr) * p.ldc + n;
+        const float* mp = mask ? mask + (long long)(m0 + rr) * p.ldmask + n : nullptr;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (n + j < p.N) {
@@ -496,12 +590,11 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
             else dst[j] = o;
           }
         }
-        src += row_step * ldfs; dst += dstep;
-        if (mask) mp += mstep;
       }
     }
   }
   if (dbg && threadIdx.x == 0) dbg[60] = clock64();   // epilogue (warp 0) done
+  if (S > 1) cluster_sync();                          // peers may still be reading this CTA's partial tile
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 8) {
@@ -544,12 +637,34 @@ int gemm(const float* a, long long lda, long long stride_a, int a_rc, const floa
   p.M = m; p.N = n; p.R = r;
   p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.sA = stride_a; p.sB = stride_b; p.sC = stride_c;
   int BN = n > 64 ? 128 : (n > 32 ? 64 : 32);
-  p.BN = BN; p.lg_bn = BN == 128 ? 7 : (BN == 64 ? 6 : 5);
   int num_kb = ceil_div(r, BK);
   if (num_kb < 1) num_kb = 1;
-  if (splits > num_kb) splits = num_kb;
-  p.kb_per_split = ceil_div(num_kb, splits);
-  p.splits = ceil_div(num_kb, p.kb_per_split);
+  // Latency configuration (forward / data gradient of the 256 ... 1024-row layers of a batch-256 update): a launch far
+  // below one wave is cut into 128 x 64 tiles and split over the reduction by a thread-block cluster of S CTAs per
+  // tile, >= 4 K blocks each (one per producer group: the whole reduction is ONE L2 round trip); the cluster reduces
+  // its partial tiles through distributed shared memory.
+  int csplit = 1;
+  if (a_rc && splits == 1 && !atomic) {
+    const int force_s = (g_variant >> 8) & 15, force_bn = (g_variant >> 12) & 3;
+    long long tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
+    if (tiles * 2 <= kNumSM && force_s != 1) {
+      if (BN == 128) BN = 64;
+      if (force_bn) BN = 16 << force_bn;
+      tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
+      while (csplit * 2 <= 8 && tiles * csplit * 2 <= kNumSM && num_kb >= csplit * 2 * 4) csplit *= 2;
+      if (force_s) csplit = force_s;
+    }
+  }
+  p.BN = BN; p.lg_bn = BN == 128 ? 7 : (BN == 64 ? 6 : 5);
+  if (csplit > 1) {
+    p.splits = csplit;
+    p.kb_per_split = ceil_div(num_kb, csplit);
+  } else {
+    if (splits > num_kb) splits = num_kb;
+    p.kb_per_split = ceil_div(num_kb, splits);
+    p.splits = ceil_div(num_kb, p.kb_per_split);
+  }
+  p.csplit = csplit;
   p.vecA = aligned16(a) && lda % 4 == 0 && stride_a % 4 == 0;
   p.vecB = aligned16(b) && ldb % 4 == 0 && stride_b % 4 == 0;
   p.vecC = aligned16(c) && ldc % 4 == 0 && stride_c % 4 == 0;
@@ -573,7 +688,7 @@ int gemm(const float* a, long long lda, long long stride_a, int a_rc, const floa
                                     227 * 1024));                                                                     \
       attr_set[IDX] = true;                                                                                           \
     }                                                                                                                 \
-    launch_pdl(tc32_gemm_kernel<ARC, BRC, PFV>, grid, dim3(NTHREADS), smem, stream, p);                               \
+    launch_pdl_cluster(tc32_gemm_kernel<ARC, BRC, PFV>, grid, dim3(NTHREADS), smem, stream, (unsigned)csplit, p);                             \
   } while (0)
   if (a_rc && b_rc) {
     if (small) D3B_TC32_LAUNCH(true, true, 4, 0); else D3B_TC32_LAUNCH(true, true, 2, 1);

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_tc32_gpu.py -q -x 2>&1 | tail -5
+timeout 200 python profiles/r2/tc32_phase_probe.py 2>&1 | tee gpurun_out/r2_tc32_phase_d.log | grep shape
+timeout 200 python profiles/r2/tc32_small.py 2>&1 | tee gpurun_out/r2_tc32_small_b.log | tail -20

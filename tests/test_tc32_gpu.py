@@ -43,6 +43,10 @@ def _rand(g, *shape, scale=1.0):
     (512, 300, 400, 1, False, 0),     # BCQ widths (N tiles 128+128+44)
     (64, 32, 256, 1, False, 0),       # half a row tile, the narrowest N tile
     (1000, 128, 512, 5, False, 4),
+    (256, 256, 256, 2, False, 0),     # latency configuration: 128 x 64 tiles, cluster split-K over 4 CTAs
+    (512, 256, 256, 1, False, 0),
+    (200, 100, 300, 2, False, 3),     # ragged tile + ragged K split (19 K blocks over 4 CTAs), padded rows
+    (100, 750, 750, 1, False, 0),     # BCQ widths at batch 100
 ])
 def test_tc32_forward(M, N, K, E, shared, ldpad):
     from d3rlpy_b200._lib import lib
@@ -70,7 +74,8 @@ def test_tc32_forward(M, N, K, E, shared, ldpad):
 
 
 @pytest.mark.parametrize("M,N,K,E,cols", [(15872, 256, 256, 2, None), (256, 256, 23, 2, None), (256, 256, 23, 2, (17, 6)),
-                                          (130, 70, 45, 3, None), (512, 300, 400, 1, None)])
+                                          (130, 70, 45, 3, None), (512, 300, 400, 1, None),
+                                          (256, 256, 256, 2, None), (200, 300, 100, 2, None)])   # cluster split-K
 def test_tc32_backward_data(M, N, K, E, cols):
     """dx = (dy W) * [src > 0]; `cols` = (first column, count) restricts to a column range of W (actor step)."""
     from d3rlpy_b200._lib import lib
@@ -146,3 +151,26 @@ def test_tc32_beats_single_tf32_and_matches_simt():
     trunc = lambda t: (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
     y1 = torch.einsum("emk,enk->emn", trunc(x).double(), trunc(w).double())
     assert float(((y1 - ref).abs() / (BOUND * bound)).max()) > 20.0
+
+
+@pytest.mark.parametrize("force_s", [1, 2, 8])
+def test_tc32_cluster_split_sizes(force_s):
+    """Every cluster size gives the same result within the bound (forced through the profiling variant word)."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), _dev()
+    g = torch.Generator().manual_seed(force_s)
+    M, N, K, E = 256, 192, 512, 2
+    x, w = _rand(g, E, M, K).to(dev), _rand(g, E, N, K, scale=1 / math.sqrt(K)).to(dev)
+    b = torch.randn(E, N, generator=g).to(dev)
+    y = torch.empty(E, M, N, device=dev)
+    L.tc32_set_variant(force_s << 8)
+    try:
+        L.tc32_gemm(x.data_ptr(), K, M * K, 1, w.data_ptr(), K, N * K, 1, y.data_ptr(), N, M * N, M, N, K, E, 1,
+                    b.data_ptr(), N, 1, None, 0, 0, None, 0, 0, 0, _st())
+        torch.cuda.synchronize()
+    finally:
+        L.tc32_set_variant(0)
+    pre = torch.einsum("emk,enk->emn", x.double(), w.double()) + b.double()[:, None, :]
+    bound = torch.einsum("emk,enk->emn", x.double().abs(), w.double().abs()) + b.double().abs()[:, None, :]
+    _check(y, torch.relu(pre), bound, f"forward, cluster of {force_s}")

@@ -229,37 +229,46 @@ def _run_cql_c2_steps(n_steps, flips, rel_q, update_l2):
         assert abs(float(sc.buf[8]) - float(opt.state[p]["exp_avg"])) <= 1e-5 * max(1.0, abs(float(opt.state[p]["exp_avg"]))), name
 
 
-def test_td3bc_c1_shape_vs_oracle_four_steps():
+@pytest.mark.parametrize("engine", ["tc32", "simt"])
+def test_td3bc_c1_shape_vs_oracle_four_steps(engine):
     """BASELINE config c1 (obs 11, act 3, B 256, 2 critics, 256x256); four steps so that the %2 actor
-    schedule and both Adam step counters advance."""
+    schedule and both Adam step counters advance.  Per element: SIMT engine within 2e-5 everywhere, tensor-core
+    engine within 5e-5 on all but <= 1 % of a tensor's elements (see `_assert_params`); metrics, update and moment
+    L2 bounds are the same for both."""
+    from d3rlpy_b200._lib import lib
     from d3rlpy_b200.algos import TD3PlusBC
 
-    O, A, B = 11, 3, 256
-    orc = ou.TD3PlusBC(O, A, seed=2)
-    q0, pi0 = _clone_sd(orc.q), _clone_sd(orc.pi)
-    algo = TD3PlusBC(scaler=None)
-    algo.create_impl((O,), A)
-    impl = algo.impl
-    impl.q_function.load_state_dict(orc.q)
-    impl.targ_q_function.load_state_dict(orc.q)
-    impl.policy.load_state_dict(orc.pi)
-    impl.targ_policy.load_state_dict(orc.pi)
-    rs = np.random.RandomState(1)
-    for s in range(4):
-        arrays = _synthetic_batch(rs, B, O, A)
-        noise = ou.Noise(seed=7 + s)
-        ref = orc.update(ou.Batch(arrays), noise)
-        impl.inject_noise(noise.log, B)
-        m = algo.update(_ns(arrays))
-        _assert_metrics(m, ref, f"c1 step {s}", rel=2e-5)
-    for grp, view, refp in (("q", impl.q_function, orc.q), ("pi", impl.policy, orc.pi),
-                            ("targ_q", impl.targ_q_function, orc.targ_q), ("targ_pi", impl.targ_policy, orc.targ_pi)):
-        _assert_params(view.state_dict(), refp, grp, rel=2e-5)
-    _assert_update(impl.q_function.state_dict(), orc.q, q0, "q", 1e-3)
-    _assert_update(impl.policy.state_dict(), orc.pi, pi0, "pi", 1e-3)
-    _assert_moments(impl._q_func, orc.q, orc.critic_optim, "q", 1e-3)
-    _assert_moments(impl._policy, orc.pi, orc.actor_optim, "pi", 1e-3)
-    assert int(impl._counters[1]) == 4 and int(impl._counters[2]) == 2  # critic / actor Adam steps
+    tc = engine == "tc32"
+    lib().set_fp32_engine(1 if tc else 0)
+    try:
+        O, A, B = 11, 3, 256
+        orc = ou.TD3PlusBC(O, A, seed=2)
+        q0, pi0 = _clone_sd(orc.q), _clone_sd(orc.pi)
+        algo = TD3PlusBC(scaler=None)
+        algo.create_impl((O,), A)
+        impl = algo.impl
+        impl.q_function.load_state_dict(orc.q)
+        impl.targ_q_function.load_state_dict(orc.q)
+        impl.policy.load_state_dict(orc.pi)
+        impl.targ_policy.load_state_dict(orc.pi)
+        rs = np.random.RandomState(1)
+        for s in range(4):
+            arrays = _synthetic_batch(rs, B, O, A)
+            noise = ou.Noise(seed=7 + s)
+            ref = orc.update(ou.Batch(arrays), noise)
+            impl.inject_noise(noise.log, B)
+            m = algo.update(_ns(arrays))
+            _assert_metrics(m, ref, f"c1 step {s}", rel=2e-5)
+        for grp, view, refp in (("q", impl.q_function, orc.q), ("pi", impl.policy, orc.pi),
+                                ("targ_q", impl.targ_q_function, orc.targ_q), ("targ_pi", impl.targ_policy, orc.targ_pi)):
+            _assert_params(view.state_dict(), refp, grp, rel=5e-5 if tc else 2e-5, flips=1e-2 if tc else 0.0)
+        _assert_update(impl.q_function.state_dict(), orc.q, q0, "q", 1e-3)
+        _assert_update(impl.policy.state_dict(), orc.pi, pi0, "pi", 1e-3)
+        _assert_moments(impl._q_func, orc.q, orc.critic_optim, "q", 1e-3)
+        _assert_moments(impl._policy, orc.pi, orc.actor_optim, "pi", 1e-3)
+        assert int(impl._counters[1]) == 4 and int(impl._counters[2]) == 2  # critic / actor Adam steps
+    finally:
+        lib().set_fp32_engine(1)
 
 
 def test_update_from_device_gather_and_philox_noise_runs():
