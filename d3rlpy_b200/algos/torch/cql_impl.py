@@ -263,14 +263,29 @@ class CQLImpl(DDPGBaseImpl):
 
         B, O, A, N, E = db.B, db.O, self._action_size, self._n_action_samples, self._n_critics
         L, st = self._lib, self._stream
-        bf = torch.bfloat16
+        f32 = self._precision == "fp32"   # fp32 mode: fp32 operand rows, one GEMM launch per layer (3xTF32 / SIMT)
         R = B * (1 + 3 * N)
         G = 2 if do_alpha else 1
-        ld = (O + A + 7) // 8 * 8
-        X = self.ws("xf_rows", G * R + 2 * B, ld, dtype=bf)
+        ld = (O + A + 3) // 4 * 4 if f32 else (O + A + 7) // 8 * 8
+        esz = 4 if f32 else 2
+        X = self.ws("xf_rows", G * R + 2 * B, ld, dtype=torch.float32 if f32 else torch.bfloat16)
+        xrows = lambda row0: X.data_ptr() + esz * row0 * ld
+
+        def q_forward(which, row0, rows, ctx, out, stream, save_rows=0):
+            if f32:
+                q_net.forward(which, xrows(row0), ld, rows, ctx, out, stream)
+            else:
+                q_net.forward(which, None, 0, rows, ctx, out, stream, x_bf16=(xrows(row0), ld), save_rows=save_rows)
+
+        def q_backward(row0, rows, ctx, dq_, stream, **kw):
+            if f32:
+                q_net.backward(xrows(row0), ld, rows, ctx, dq_, stream, **kw)
+            else:
+                q_net.backward(None, 0, rows, ctx, dq_, stream, **kw)
         lp = self.ws("xf_lp", 4, max(B * N, 1))
         lpm = self.ws("xf_lpm", 3, B)  # soft-backup, actor, temp log-probs
-        done = self.ws("xf_done", 4, dtype=torch.int32)
+        # per loss kernel: block counter + per-block partial sums (fixed-order final sums, csrc/cql_fused.cu)
+        done = self.ws("xf_done", 3, 4 + 3 * ((B * E + 7) // 8) + 4, dtype=torch.int32)
         dp = self.world_size > 1  # sharded minibatch: sums / gradients are all-reduced between the partial kernels
         inv_b = 1.0 / (B * self.world_size)
         mask = 0
@@ -295,9 +310,10 @@ class CQLImpl(DDPGBaseImpl):
         ptrs += [nv("soft") if soft else None, lpm[0].data_ptr() if soft else None, nv("actor"), lpm[1].data_ptr(),
                  nv("temp") if do_temp else None, lpm[2].data_ptr() if do_temp else None]
         t_row0, a_row0 = G * R, G * R + B
-        L.cql_rows(head.data_ptr(), db.ptr("obs"), db.ptr("next_obs"), db.ptr("act"), B, N, O, A, MIN_LOGSTD,
-                   MAX_LOGSTD, X.data_ptr(), ld, G, (ctypes.c_void_p * 16)(*ptrs),
-                   (ctypes.c_int64 * 4)(0, R, t_row0, a_row0), st)
+        (L.cql_rows_f32 if f32 else L.cql_rows)(head.data_ptr(), db.ptr("obs"), db.ptr("next_obs"), db.ptr("act"), B, N,
+                                                O, A, MIN_LOGSTD, MAX_LOGSTD, X.data_ptr(), ld, G,
+                                                (ctypes.c_void_p * 16)(*ptrs),
+                                                (ctypes.c_int64 * 4)(0, R, t_row0, a_row0), st)
         la, lt = self._log_alpha, self._log_temp
         q_net = self._q_func
         # ---- side branch (independent of the importance-sampling pass): temperature step, target critics
@@ -325,7 +341,7 @@ class CQLImpl(DDPGBaseImpl):
                             self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS), self.metric_ptr(M_TEMP), side)
         ctx_t = q_net.ctx("tq", B, E, False)
         q_t = self.ws("tq_q", E, B)
-        q_net.forward("target", None, 0, B, ctx_t, q_t, side, x_bf16=(X.data_ptr() + 2 * t_row0 * ld, ld))
+        q_forward("target", t_row0, B, ctx_t, q_t, side)
         q_tpn = None
         if soft:
             q_tpn = self.ws("soft_tpn", B)
@@ -333,11 +349,11 @@ class CQLImpl(DDPGBaseImpl):
         # ---- main branch: critic-step rows [0,R) (activations saved) and alpha-step rows [R,2R) (forward only)
         ctx = q_net.ctx("is2", G * R, E, True)
         q = self.ws("is2_q", E, G * R)
-        q_net.forward("params", None, 0, G * R, ctx, q, st, x_bf16=(X.data_ptr(), ld), save_rows=R)
+        q_forward("params", 0, G * R, ctx, q, st, save_rows=R)
         if do_alpha and not dp:
             L.cql_loss_step(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma,
                             lp[2].data_ptr(), lp[3].data_ptr(), N, A, la.buf.data_ptr(), self._conservative_weight,
-                            self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done.data_ptr(), B, E, inv_b, 1,
+                            self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done[0].data_ptr(), B, E, inv_b, 1,
                             self.counter_ptr(C_ALPHA), self._alpha_learning_rate, self.metric_ptr(M_ALPHA_LOSS),
                             self.metric_ptr(M_ALPHA), st)
         elif do_alpha:
@@ -367,14 +383,14 @@ class CQLImpl(DDPGBaseImpl):
                             q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
                             self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.buf.data_ptr(),
                             self._conservative_weight, self._alpha_threshold, dq.data_ptr(), R,
-                            self.sums_ptr(S_CRITIC), done.data_ptr() + 4, B, E, inv_b, 0, None, 0.0,
+                            self.sums_ptr(S_CRITIC), done[1].data_ptr(), B, E, inv_b, 0, None, 0.0,
                             self.metric_ptr(M_CRITIC), None, st)
         else:
             L.critic_loss(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
                           q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
                           self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.ptr("p"), self._conservative_weight,
                           dq.data_ptr(), R, self.sums_ptr(S_CRITIC), None, B, E, inv_b, 1, st)
-        q_net.backward(None, 0, R, ctx, dq, st)
+        q_backward(0, R, ctx, dq, st)
         # the loss partial sums only feed the reported metric: with the peer exchange they ride along with the
         # gradient all-reduce inside the Adam kernel (no rendezvous of their own)
         csum = self._slots[32 + S_CRITIC:32 + S_CRITIC + 3]
@@ -385,17 +401,17 @@ class CQLImpl(DDPGBaseImpl):
         # actor step on the updated critics
         ctx_a = q_net.ctx("aq", B, E, True)
         qa = self.ws("aq_q", E, B)
-        q_net.forward("params", None, 0, B, ctx_a, qa, st, x_bf16=(X.data_ptr() + 2 * a_row0 * ld, ld))
+        q_forward("params", a_row0, B, ctx_a, qa, st)
         dqa = self.ws("a_dq", E, B)
         if not dp:
             L.sac_actor_step(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B,
-                             self.sums_ptr(S_ACTOR), done.data_ptr() + 8, self.metric_ptr(M_ACTOR), B, E, inv_b, st)
+                             self.sums_ptr(S_ACTOR), done[2].data_ptr(), self.metric_ptr(M_ACTOR), B, E, inv_b, st)
         else:
             L.sac_actor_loss(qa.data_ptr(), B, lpm[1].data_ptr(), lt.ptr("p"), dqa.data_ptr(), B,
                              self.sums_ptr(S_ACTOR), B, E, inv_b, st)
         dxa = self.ws("a_dx", E, B, A)
-        q_net.backward(None, 0, B, ctx_a, dqa, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
-                       dx_cols=A)
+        q_backward(a_row0, B, ctx_a, dqa, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
+                   dx_cols=A)
         dhead = self.ws("pi_dhead", 1, B, 2 * A)
         L.sac_actor_backward(head.data_ptr(), 2 * A, nv("actor"), dxa.data_ptr(), A, B * A, E, lt.ptr("p"),
                              dhead.data_ptr(), 2 * A, B, A, MIN_LOGSTD, MAX_LOGSTD, inv_b, st)
@@ -459,8 +475,11 @@ class CQLImpl(DDPGBaseImpl):
             self._p_critic(db, head, q_t=q_t, q_tpn=q_tpn, conservative=self._n_action_samples > 0)
             self._p_actor(db, acts_p, head)
 
-        fused = (self._precision == "bf16" and self._q_func.fused_ok
-                 and self._policy.fused_ok and self.fused_glue)
+        # fused glue (csrc/cql_fused.cu): bf16 mode over the whole-network kernels (any world size), fp32 mode over the
+        # per-layer GEMMs on one GPU (the NCCL data-parallel fp32 path keeps the generic program)
+        fused = self.fused_glue and ((self._precision == "bf16" and self._q_func.fused_ok and self._policy.fused_ok)
+                                     or (self._precision == "fp32" and self.world_size == 1
+                                         and not self._q_func.wide_head))
         if fused and self.world_size > 1 and not hasattr(self, "_px"):
             self._px = self._peer_setup()  # collective IPC rendezvous: outside the dry pass / graph capture
         self.run_program((type(self).__name__, db.B, do_temp, do_alpha, self._noise_injected, fused),

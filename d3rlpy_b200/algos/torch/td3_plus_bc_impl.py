@@ -152,7 +152,7 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
         self.fill_noise(B)
         X = self.ws("xf_rows", 3 * B, ld, dtype=bf)        # [critic rows | target rows | actor rows]
-        done = self.ws("xf_done", 4, dtype=torch.int32)
+        done = self.ws("xf_done", 4 + 3 * ((B * E + 7) // 8) + 4, dtype=torch.int32)
         q_net, pi = self._q_func, self._policy
         # ---- branch: online critics on (s, a)
         side = self._side_stream()

@@ -35,7 +35,7 @@ struct RowsParams {
   const float* act;       // [B][A]
   int B, N, O, A;
   float min_logstd, max_logstd;
-  __nv_bfloat16* X;       // [rows_total][ldx]
+  void* X;                // [rows_total][ldx], bf16 (tensor-core mode) or fp32 (fp32 mode) GEMM operand rows
   long long ldx;
   // per IS group g (0 = critic step, 1 = alpha step): noise and log-prob outputs
   const float* eps_t[2];      // [N][B][A]
@@ -69,7 +69,11 @@ __device__ __forceinline__ float sample_action(const float* __restrict__ head_ro
   return nlp - jac;
 }
 
+__device__ __forceinline__ void put(__nv_bfloat16* x, int j, float v) { x[j] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void put(float* x, int j, float v) { x[j] = v; }
+
 // one warp per work item; items: per group R = B(1+3N) rows, then B target rows, B actor rows, B temp items
+template <typename T>
 __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
   pdl_trigger();
   pdl_wait();
@@ -81,7 +85,8 @@ __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
   const int R = B + 3 * BN;
   const int n_is = R * p.n_groups;
   const float* obs_row;
-  __nv_bfloat16* x = nullptr;
+  T* const X = (T*)p.X;
+  T* x = nullptr;
   // decode
   int kind;         // 0 data, 1 pi(s_t), 2 pi(s_tp1), 3 random, 4 target, 5 actor, 6 temp
   int b, k = 0, g = 0;
@@ -96,17 +101,17 @@ __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
       b = r / N;
       k = r - b * N;
     }
-    x = p.X + (p.group_row0[g] + (long long)(item - g * R)) * p.ldx;
+    x = X + (p.group_row0[g] + (long long)(item - g * R)) * p.ldx;
     obs_row = p.obs + (long long)b * O;
   } else {
     int r = item - n_is;
-    if (r < B) { kind = 4; b = r; x = p.X + (p.target_row0 + b) * p.ldx; obs_row = p.next_obs + (long long)b * O; }
-    else if (r < 2 * B) { kind = 5; b = r - B; x = p.X + (p.actor_row0 + b) * p.ldx; obs_row = p.obs + (long long)b * O; }
+    if (r < B) { kind = 4; b = r; x = X + (p.target_row0 + b) * p.ldx; obs_row = p.next_obs + (long long)b * O; }
+    else if (r < 2 * B) { kind = 5; b = r - B; x = X + (p.actor_row0 + b) * p.ldx; obs_row = p.obs + (long long)b * O; }
     else if (r < 3 * B && p.eps_temp) { kind = 6; b = r - 2 * B; obs_row = nullptr; }
     else return;
   }
   if (x) {
-    for (int j = lane; j < O; j += 32) x[j] = __float2bfloat16_rn(__ldg(obs_row + j));
+    for (int j = lane; j < O; j += 32) put(x, j, __ldg(obs_row + j));
   }
   float lp = 0.f;
   for (int j = lane; j < A; j += 32) {
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
       default: lp += sample_action(p.head + (long long)b * 2 * A, A, j, __ldg(p.eps_temp + (long long)b * A + j),
                                    p.min_logstd, p.max_logstd, a); break;
     }
-    if (x) x[O + j] = __float2bfloat16_rn(a);
+    if (x) put(x, O + j, a);
   }
   if (kind == 1 || kind == 2 || kind >= 4) {
     lp = warp_sum(lp);
@@ -187,8 +192,10 @@ struct LossParams {
   float* scalar_alpha;                     // log_alpha {p,g,m,v} at float stride 4
   float cw, threshold;
   float* dq; long long sDq;                // gradient seed [E][R] (critic mode) or null
-  float* sums;                             // 3 partial sums
-  unsigned* done;                          // block completion counter (self-resetting)
+  float* sums;                             // 3 sums (written once, by the last block)
+  unsigned* done;                          // workspace: word 0 = block completion counter (self-resetting), words
+                                           // [4, 4 + 3 gridDim.x) = per-block partial sums (fixed-order final sum:
+                                           // metrics and the alpha gradient are bit-reproducible run to run)
   int B, E; float inv_b, inv_eb;
   int mode;                                // 0 critic loss metric; 1 alpha loss + Adam on log_alpha
   const int* step_alpha; double lr_alpha;
@@ -301,18 +308,30 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) { a0 += red3[0][w]; a1 += red3[1][w]; a2 += red3[2][w]; }
-    if (td_enabled) atomicAdd(p.sums + 0, a0);
-    atomicAdd(p.sums + 1, a1);
-    atomicAdd(p.sums + 2, a2);
+    float* part = reinterpret_cast<float*>(p.done + 4);
+    part[blockIdx.x] = a0;
+    part[gridDim.x + blockIdx.x] = a1;
+    part[2 * gridDim.x + blockIdx.x] = a2;
     __threadfence();
     unsigned prev = atomicAdd(p.done, 1u);
     is_last = (prev == gridDim.x - 1);
   }
   __syncthreads();
-  if (!is_last || threadIdx.x != 0) return;
-  // ---- scalar tail, executed once by the last block to finish (cql_impl.py:217-223, 119-141)
+  if (!is_last) return;
+  // ---- the last block to finish adds the per-block partial sums in a fixed order ...
   __threadfence();
-  volatile float* sv = p.sums;
+  const volatile float* part = reinterpret_cast<const volatile float*>(p.done + 4);
+  float s3[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float acc = 0.f;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += part[k * gridDim.x + i];
+    s3[k] = block_sum(acc);
+  }
+  if (threadIdx.x != 0) return;
+  // ---- ... and runs the scalar tail (cql_impl.py:217-223, 119-141)
+  float sv[3] = {td_enabled ? s3[0] : 0.f, s3[1], s3[2]};
+  p.sums[0] = sv[0]; p.sums[1] = sv[1]; p.sums[2] = sv[2];
   float tdm = sv[0] * p.inv_b;
   if (N == 0) {  // plain TD loss (no conservative term): TD3+BC / BCQ critics
     *p.metric = tdm;
@@ -360,12 +379,18 @@ __global__ void __launch_bounds__(256) sac_actor_step_kernel(const float* __rest
   }
   l = block_sum(l);
   if (threadIdx.x == 0) {
-    atomicAdd(loss_sum, l);
+    // done: word 0 = block counter (self-resetting), words [4, 4 + gridDim.x) = per-block partial sums, added in
+    // block order by the last block to finish (bit-reproducible metric)
+    volatile float* part = reinterpret_cast<volatile float*>(done + 4);
+    part[blockIdx.x] = l;
     __threadfence();
     unsigned prev = atomicAdd(done, 1u);
     if (prev == gridDim.x - 1) {
       __threadfence();
-      *metric = *(volatile float*)loss_sum;
+      float acc = 0.f;
+      for (unsigned i = 0; i < gridDim.x; ++i) acc += part[i];
+      *loss_sum = acc;
+      *metric = acc;
       *done = 0u;
     }
   }
@@ -386,7 +411,7 @@ extern "C" int d3b_begin_step(int* counters, int n, unsigned mask, float* slots,
 //   {eps_t[0], eps_tp1[0], rand[0], logp_t[0], logp_tp1[0], eps_t[1], eps_tp1[1], rand[1], logp_t[1], logp_tp1[1],
 //    eps_soft, logp_soft, eps_actor, logp_actor, eps_temp, logp_temp}
 // rows_host: {group_row0[0], group_row0[1], target_row0, actor_row0}
-extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+static int cql_rows_any(bool f32, const float* head, const float* obs, const float* next_obs, const float* act, int batch,
                             int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd,
                             void* x_bf16, int64_t ldx, int n_groups, const void* const* ptrs_host,
                             const int64_t* rows_host, void* stream) {
@@ -398,7 +423,7 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
   p.head = head; p.obs = obs; p.next_obs = next_obs; p.act = act;
   p.B = batch; p.N = n_action_samples; p.O = obs_dim; p.A = act_dim;
   p.min_logstd = min_logstd; p.max_logstd = max_logstd;
-  p.X = (__nv_bfloat16*)x_bf16; p.ldx = ldx; p.n_groups = n_groups;
+  p.X = x_bf16; p.ldx = ldx; p.n_groups = n_groups;
   for (int g = 0; g < 2; ++g) {
     p.eps_t[g] = (const float*)ptrs_host[5 * g + 0];
     p.eps_tp1[g] = (const float*)ptrs_host[5 * g + 1];
@@ -418,8 +443,25 @@ extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* ne
   p.target_row0 = rows_host[2]; p.actor_row0 = rows_host[3];
   long long items = ((long long)batch + 3LL * batch * n_action_samples) * n_groups + 3LL * batch;
   D3B_REQUIRE(items < (1LL << 30), "cql_rows: too many rows for one launch");
-  launch_pdl(cql_rows_kernel, dim3((unsigned)ceil_div_ll(items, 8)), dim3(256), 0, ST, p);
+  if (f32) launch_pdl(cql_rows_kernel<float>, dim3((unsigned)ceil_div_ll(items, 8)), dim3(256), 0, ST, p);
+  else launch_pdl(cql_rows_kernel<__nv_bfloat16>, dim3((unsigned)ceil_div_ll(items, 8)), dim3(256), 0, ST, p);
   return check_launch("cql_rows");
+}
+
+extern "C" int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+                            int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd,
+                            void* x_bf16, int64_t ldx, int n_groups, const void* const* ptrs_host,
+                            const int64_t* rows_host, void* stream) {
+  return cql_rows_any(false, head, obs, next_obs, act, batch, n_action_samples, obs_dim, act_dim, min_logstd, max_logstd,
+                      x_bf16, ldx, n_groups, ptrs_host, rows_host, stream);
+}
+// the same rows as fp32 GEMM operands (fp32 mode: 3xTF32 / SIMT dense layers)
+extern "C" int d3b_cql_rows_f32(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+                                int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd,
+                                float* x, int64_t ldx, int n_groups, const void* const* ptrs_host,
+                                const int64_t* rows_host, void* stream) {
+  return cql_rows_any(true, head, obs, next_obs, act, batch, n_action_samples, obs_dim, act_dim, min_logstd, max_logstd,
+                      x, ldx, n_groups, ptrs_host, rows_host, stream);
 }
 
 extern "C" int d3b_sac_temp_step(const float* logp, float* scalar, const int* step, int batch, int act_dim,

@@ -239,9 +239,10 @@ class DenseNet:
             d = self.in_dim
             for i, h in enumerate(self.hidden):
                 y = ctx.acts[i]
+                # member stride = the workspace's row count: a later backward may cover a prefix of the rows only
                 L.linear_forward(cur, ld, sx, self._w(which, i, member0), d, ms, self._b(which, i, member0), ms,
-                                 _p(y), h, rows * h, rows, h, d, E, 1, stream)
-                cur, ld, sx, d = _p(y), h, rows * h, h
+                                 _p(y), h, ctx.rows * h, rows, h, d, E, 1, stream)
+                cur, ld, sx, d = _p(y), h, ctx.rows * h, h
             if head_out is not None and self.wide_head:
                 assert not head_tanh
                 _wide_head_forward(self, which, cur, ld, sx, rows, E, head_out, stream, member0)
@@ -309,22 +310,23 @@ class DenseNet:
         if self.precision == "fp32":
             last = ctx.acts[-1]
             dcur = ctx.scratch[0]
+            ar = ctx.rows   # member stride of the saved activations (rows <= ar: backward over a prefix of the rows)
             if self.wide_head:
-                _wide_head_backward(self, ctx, rows, E, d_head, _p(last), feat, rows * feat, _p(dcur), feat, rows * feat,
+                _wide_head_backward(self, ctx, rows, E, d_head, _p(last), feat, ar * feat, _p(dcur), feat, rows * feat,
                                     stream, weight_grads, member0)
             else:
                 if weight_grads:
-                    L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, rows * feat,
+                    L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, ar * feat,
                                            self._hw("grads", member0), feat, ms, self._hb("grads", member0), ms, rows,
                                            n, feat, E, stream)
                 L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat,
-                                     rows * feat, _p(last), feat, rows * feat, rows, n, feat, E, stream)
+                                     rows * feat, _p(last), feat, ar * feat, rows, n, feat, E, stream)
             which = 0
             for i in range(nl - 1, -1, -1):
                 h = self.hidden[i]
                 d_in = self.hidden[i - 1] if i > 0 else self.in_dim
                 if i > 0:
-                    inp, ldi, si = _p(ctx.acts[i - 1]), d_in, rows * d_in
+                    inp, ldi, si = _p(ctx.acts[i - 1]), d_in, ar * d_in
                 else:
                     inp, ldi, si = _p(x), ldx, 0
                 if weight_grads:

@@ -311,11 +311,18 @@ int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int members, cons
  * sac_temp_step: update_temp loss + gradient + Adam (sac_impl.py:123-146); scalar = {p,g,m,v} at float stride 4.
  * cql_loss_step: conservative + TD loss and gradient seed, then the scalar tail by the last block: mode 0 critic
  *   metric (cql_impl.py:110-117), mode 1 alpha loss + Adam on log_alpha (cql_impl.py:119-141).
- * sac_actor_step: SACImpl.compute_actor_loss (sac_impl.py:114-121) + gradient seed + metric. */
+ * sac_actor_step: SACImpl.compute_actor_loss (sac_impl.py:114-121) + gradient seed + metric.
+ * done_counter (cql_loss_step, sac_actor_step): zero-initialised workspace of 32-bit words: word 0 = self-resetting block
+ *   counter, words [4, 4 + 3 * ceil(batch * members / 8)) (cql_loss_step) or [4, 4 + ceil(batch / 256)) (sac_actor_step) =
+ *   per-block partial sums; the last block adds them in a fixed order, so `sums` and the metrics are bit-reproducible. */
 int d3b_begin_step(int* counters, int n, unsigned mask, float* slots, int n_slots, void* stream);
 int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
                  int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd, void* x_bf16,
                  int64_t ldx, int n_groups, const void* const* ptrs_host, const int64_t* rows_host, void* stream);
+/* cql_rows with fp32 output rows (fp32 mode) */
+int d3b_cql_rows_f32(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
+                     int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd, float* x,
+                     int64_t ldx, int n_groups, const void* const* ptrs_host, const int64_t* rows_host, void* stream);
 int d3b_sac_temp_step(const float* logp, float* scalar, const int* step, int batch, int act_dim, float inv_batch,
                       double lr, float* metric_loss, float* metric_exp, void* stream);
 int d3b_cql_loss_step(const float* q, int64_t stride_q, const float* q_targ, int64_t stride_qt, int targ_members,

@@ -300,6 +300,15 @@ def test_cql_fused_glue_kernels_match_unfused_kernels():
     assert torch.equal(X[:R, :W], xc.to(torch.bfloat16)) and torch.equal(X[R:2 * R, :W], xa.to(torch.bfloat16))
     assert torch.equal(X[2 * R:2 * R + B, :W], xt.to(torch.bfloat16))
     assert torch.equal(X[2 * R + B:, :W], xact.to(torch.bfloat16))
+    # the fp32-mode variant writes the same rows as fp32 operands (padded leading dimension)
+    ld4 = (W + 3) // 4 * 4
+    X32 = torch.zeros(2 * R + 2 * B, ld4, device=dev)
+    L.cql_rows_f32(p(head), p(obs), p(nobs), p(act), B, N, O, A, -20.0, 2.0, p(X32), ld4, 2, (ctypes.c_void_p * 16)(*ptrs),
+                   (ctypes.c_int64 * 4)(0, R, 2 * R, 2 * R + B), st)
+    torch.cuda.synchronize()
+    for got, want, what in ((X32[:R], xc, "critic rows"), (X32[R:2 * R], xa, "alpha rows"),
+                            (X32[2 * R:2 * R + B], xt, "target rows"), (X32[2 * R + B:], xact, "actor rows")):
+        _close(got[:, :W], want, rtol=1e-6, msg=what)
     _close(lp[:2], lc, rtol=1e-6, msg="critic logp")
     _close(lp[2:], la_, rtol=1e-6, msg="alpha logp")
     _close(lpm[0], lsoft, rtol=1e-6, msg="soft logp")
@@ -318,7 +327,7 @@ def test_cql_fused_glue_kernels_match_unfused_kernels():
         sums_a, sums_b = torch.zeros(4, device=dev), torch.zeros(4, device=dev)
         dq_a, dq_b = torch.zeros(E, R, device=dev), torch.zeros(E, R, device=dev)
         met_a, met_b = torch.zeros(2, device=dev), torch.zeros(2, device=dev)
-        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        done = torch.zeros(4 + 3 * ((B * E + 7) // 8), dtype=torch.int32, device=dev)   # counter + per-block partials
         td = mode == 0
         L.cql_loss_step(p(q), R, p(q_t) if td else None, B, E, None, p(rew) if td else None, p(term) if td else None,
                         p(nst) if td else None, 0.99, p(lc[0]), p(lc[1]), N, A, p(sc_a), 5.0, 10.0,
@@ -334,7 +343,7 @@ def test_cql_fused_glue_kernels_match_unfused_kernels():
         _close(sc_a, sc_b, rtol=1e-6, msg="log_alpha adam state")
         if td:
             _close(dq_a, dq_b, rtol=2e-6, msg="dq")
-        assert int(done.item()) == 0
+        assert int(done[0]) == 0
     # ---- temp / actor
     sc_a = torch.zeros(16, device=dev); sc_a[0] = -0.2
     sc_b = sc_a.clone()
@@ -346,7 +355,7 @@ def test_cql_fused_glue_kernels_match_unfused_kernels():
     qa = rnd(E, B)
     dqa, dqb = torch.zeros(E, B, device=dev), torch.zeros(E, B, device=dev)
     ls_a, ls_b = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
-    done = torch.zeros(1, dtype=torch.int32, device=dev)
+    done = torch.zeros(4 + (B + 255) // 256, dtype=torch.int32, device=dev)
     m_act = torch.zeros(1, device=dev)
     L.sac_actor_step(p(qa), B, p(lact), p(sc_a), p(dqa), B, p(ls_a), p(done), p(m_act), B, E, 1.0 / B, st)
     L.sac_actor_loss(p(qa), B, p(lact), p(sc_a), p(dqb), B, p(ls_b), B, E, 1.0 / B, st)
