@@ -39,7 +39,7 @@ constexpr int MAX_STAGES = 4;
 constexpr int PROD_THREADS = 256;
 constexpr int NTHREADS = PROD_THREADS + 32;  // + warp 8: TMEM allocation and MMA issue
 constexpr int A_BYTES = BM * BK * 4;         // 8 KB per (hi | lo) buffer
-constexpr int N_ACC = 2;                     // TMEM accumulators: correction terms [0, BN), hi*hi [BN, 2 BN)
+constexpr int N_ACC = 2;                     // TMEM accumulators: hi*hi [0, BN), correction terms [BN, 2 BN)
 
 struct Params {
   const float* A;
@@ -294,16 +294,18 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
     // ===================== MMA issuer
     if (lane == 0 && nkb > 0) {
       // instruction descriptor: D = f32 (bit 4), A = B = tf32 (2 at bits 7 and 10), majors at bits 15 / 16
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (A_RC ? 0u : (1u << 15)) |
-                             (B_RC ? 0u : (1u << 16)) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | (A_RC ? 0u : (1u << 15)) |
+                              (B_RC ? 0u : (1u << 16)) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = idesc0 | ((uint32_t)(BN >> 3) << 17);          // N = BN
+      const uint32_t idesc2 = idesc0 | ((uint32_t)((2 * BN) >> 3) << 17);   // N = 2 BN: [B_hi ; B_lo] as one operand
       // operand descriptors of every stage, built while the first tiles are still in flight
-      uint64_t dah[STAGES], dal[STAGES], dbh[STAGES], dbl[STAGES];
+      uint64_t dah[STAGES], dal[STAGES], dbh[STAGES];
 #pragma unroll
       for (int s = 0; s < STAGES; ++s) {
         const uint32_t a_hi = smem_u32(smem + s * stage_bytes), a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES;   // B_lo follows B_hi directly: rows [BN, 2 BN) of one operand
         dah[s] = A_RC ? desc_k(a_hi) : desc_mn(a_hi); dal[s] = A_RC ? desc_k(a_lo) : desc_mn(a_lo);
-        dbh[s] = B_RC ? desc_k(b_hi) : desc_mn(b_hi); dbl[s] = B_RC ? desc_k(b_lo) : desc_mn(b_lo);
+        dbh[s] = B_RC ? desc_k(b_hi) : desc_mn(b_hi);
       }
       // one UMMA_K = 8 step: K-major +32 B inside the swizzle row, MN-major +8 reduction rows (1024 B)
       constexpr uint64_t ka = A_RC ? 2 : 64, kbs = B_RC ? 2 : 64;
@@ -321,9 +323,12 @@ __global__ void __launch_bounds__(NTHREADS, G <= 2 ? 2 : 1) tc32_gemm_kernel(con
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint32_t first = (i > 0 || k > 0) ? 1u : 0u;
-              mma_tf32(tmem_base, dal[s] + ka * k, dbh[s] + kbs * k, idesc, first);      // correction accumulator
-              mma_tf32(tmem_base, dah[s] + ka * k, dbl[s] + kbs * k, idesc, 1u);
-              mma_tf32(tmem_base + (uint32_t)BN, dah[s] + ka * k, dbh[s] + kbs * k, idesc, first);
+              // B_hi and B_lo are adjacent in the stage, so ONE MMA of width 2 BN forms A_hi B_hi (columns [0, BN):
+              // main accumulator) and A_hi B_lo (columns [BN, 2 BN): correction accumulator) reading A_hi once; the
+              // second adds A_lo B_hi to the correction accumulator.  Two instructions and 40 KB of operand reads per
+              // step instead of three and 48 KB (the kernel is shared-memory-bandwidth bound).
+              mma_tf32(tmem_base, dah[s] + ka * k, dbh[s] + kbs * k, idesc2, first);
+              mma_tf32(tmem_base + (uint32_t)BN, dal[s] + ka * k, dbh[s] + kbs * k, idesc, 1u);
             }
           }
           mma_commit(empty + s);   // the stage may be refilled once these MMAs have read it

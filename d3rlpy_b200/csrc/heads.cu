@@ -10,12 +10,15 @@ namespace d3b {
 
 constexpr int HEAD_MAX_N = 32;
 
-// One warp per (member,row).  Y[e][m][n] = act(X[e][m][:] . W[e][n][:] + b[e][n])
+// One warp per (member,row).  Y[e][m][n] = act(X[e][m][:] . W[e][n][:] + b[e][n]).  The row stays in registers
+// (K <= 1024) and four outputs are reduced at a time, so the shuffle chains of different outputs overlap.
 __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restrict__ X, long long ldx, long long sX,
                                                            const float* __restrict__ W, long long ldw, long long sW,
                                                            const float* __restrict__ bias, long long sB,
                                                            float* __restrict__ Y, long long ldy, long long sY, int M,
                                                            int N, int K, int E, int act_tanh) {
+  pdl_trigger();
+  pdl_wait();
   int lane = threadIdx.x & 31;
   long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= (long long)M * E) return;
@@ -23,12 +26,38 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
   const float* x = X + (long long)e * sX + (long long)m * ldx;
   const float* w = W + (long long)e * sW;
   float mine = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* wr = w + (long long)n * ldw;
-    float s = 0.f;
-    for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + k), __ldg(wr + k), s);
-    s = warp_sum(s);
-    if (lane == n) mine = s;
+  if (K <= 1024) {
+    float xr[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xr[i] = (lane + 32 * i < K) ? __ldg(x + lane + 32 * i) : 0.f;
+    for (int n0 = 0; n0 < N; n0 += 4) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n0 + j < N) {
+          const float* wr = w + (long long)(n0 + j) * ldw;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * i < K) { const int k = lane + 32 * i; if (k < K) s[j] = fmaf(xr[i], __ldg(wr + k), s[j]); }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane == n0 + j) mine = s[j];
+    }
+  } else {
+    for (int n = 0; n < N; ++n) {
+      const float* wr = w + (long long)n * ldw;
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s = fmaf(__ldg(x + k), __ldg(wr + k), s);
+      s = warp_sum(s);
+      if (lane == n) mine = s;
+    }
   }
   if (lane < N) {
     float v = mine + (bias ? __ldg(bias + (long long)e * sB + lane) : 0.f);
@@ -37,23 +66,45 @@ __global__ void __launch_bounds__(256) head_forward_kernel(const float* __restri
   }
 }
 
-// dX[e][m][k] = (sum_n dY[e][m][n] W[e][n][k]) * [src[e][m][k] > 0]
+// dX[e][m][k] = (sum_n dY[e][m][n] W[e][n][k]) * [src[e][m][k] > 0]; VEC = 4: one thread per four consecutive k
+// (16-byte loads / stores; K, the leading dimensions and the member strides multiples of 4, pointers 16-byte aligned)
+template <int VEC>
 __global__ void __launch_bounds__(256) head_backward_data_kernel(
     const float* __restrict__ dY, long long lddy, long long sdY, const float* __restrict__ W, long long ldw,
     long long sW, float* __restrict__ dX, long long lddx, long long sdX, const float* __restrict__ src,
     long long ldsrc, long long sSrc, int M, int N, int K, int E) {
+  pdl_trigger();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)E * M * K;
+  const int KV = K / VEC;
+  long long total = (long long)E * M * KV;
   if (idx >= total) return;
-  int k = (int)(idx % K);
-  long long t = idx / K;
+  int k = (int)(idx % KV) * VEC;
+  long long t = idx / KV;
   int m = (int)(t % M), e = (int)(t / M);
   const float* dy = dY + (long long)e * sdY + (long long)m * lddy;
   const float* w = W + (long long)e * sW + k;
-  float s = 0.f;
-  for (int n = 0; n < N; ++n) s = fmaf(__ldg(dy + n), __ldg(w + (long long)n * ldw), s);
-  if (src && !(__ldg(src + (long long)e * sSrc + (long long)m * ldsrc + k) > 0.f)) s = 0.f;
-  dX[(long long)e * sdX + (long long)m * lddx + k] = s;
+  if (VEC == 4) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+      const float d = __ldg(dy + n);
+      const float4 wv = __ldg((const float4*)(w + (long long)n * ldw));
+      s.x = fmaf(d, wv.x, s.x); s.y = fmaf(d, wv.y, s.y); s.z = fmaf(d, wv.z, s.z); s.w = fmaf(d, wv.w, s.w);
+    }
+    if (src) {
+      const float4 h = __ldg((const float4*)(src + (long long)e * sSrc + (long long)m * ldsrc + k));
+      if (!(h.x > 0.f)) s.x = 0.f;
+      if (!(h.y > 0.f)) s.y = 0.f;
+      if (!(h.z > 0.f)) s.z = 0.f;
+      if (!(h.w > 0.f)) s.w = 0.f;
+    }
+    *reinterpret_cast<float4*>(dX + (long long)e * sdX + (long long)m * lddx + k) = s;
+  } else {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s = fmaf(__ldg(dy + n), __ldg(w + (long long)n * ldw), s);
+    if (src && !(__ldg(src + (long long)e * sSrc + (long long)m * ldsrc + k) > 0.f)) s = 0.f;
+    dX[(long long)e * sdX + (long long)m * lddx + k] = s;
+  }
 }
 
 // dW[e][n][k] += sum_m dY[e][m][n] X[e][m][k];  db[e][n] += sum_m dY[e][m][n]
@@ -64,6 +115,8 @@ __global__ void __launch_bounds__(256) head_backward_weight_kernel(
     long long sX, float* __restrict__ dW, long long lddw, long long sdW, float* __restrict__ db, long long sdb, int M,
     int N, int K, int rows_per_block) {
   extern __shared__ float sdy[];  // [rows_per_block][N]
+  pdl_trigger();
+  pdl_wait();
   int e = blockIdx.z;
   int m0 = blockIdx.y * rows_per_block;
   int rows = min(rows_per_block, M - m0);
@@ -111,9 +164,9 @@ extern "C" int d3b_head_forward(const float* x, int64_t ldx, int64_t stride_x, c
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && w && y, "head_forward: null pointer");
   long long warps = (long long)rows * members;
-  head_forward_kernel<<<(unsigned)ceil_div_ll(warps, 8), 256, 0, (cudaStream_t)stream>>>(
-      x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features, in_features, members,
-      act_tanh);
+  launch_pdl(head_forward_kernel, dim3((unsigned)ceil_div_ll(warps, 8)), dim3(256), 0, (cudaStream_t)stream, x,
+             (long long)ldx, (long long)stride_x, w, (long long)ldw, (long long)stride_w, bias, (long long)stride_b, y,
+             (long long)ldy, (long long)stride_y, rows, out_features, in_features, members, act_tanh);
   return check_launch("head_forward");
 }
 
@@ -124,10 +177,20 @@ extern "C" int d3b_head_backward_data(const float* dy, int64_t lddy, int64_t str
   D3B_REQUIRE(rows >= 0 && in_features > 0 && members > 0 && out_features >= 1, "head_backward_data: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dy && w && dx, "head_backward_data: null pointer");
-  long long total = (long long)rows * in_features * members;
-  head_backward_data_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      dy, lddy, stride_dy, w, ldw, stride_w, dx, lddx, stride_dx, relu_src, ld_src, stride_src, rows, out_features,
-      in_features, members);
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool vec = in_features % 4 == 0 && ldw % 4 == 0 && stride_w % 4 == 0 && lddx % 4 == 0 && stride_dx % 4 == 0 &&
+                   al16(w) && al16(dx) && (!relu_src || (al16(relu_src) && ld_src % 4 == 0 && stride_src % 4 == 0));
+  long long total = (long long)rows * (in_features / (vec ? 4 : 1)) * members;
+  if (vec)
+    launch_pdl(head_backward_data_kernel<4>, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+               dy, (long long)lddy, (long long)stride_dy, w, (long long)ldw, (long long)stride_w, dx, (long long)lddx,
+               (long long)stride_dx, relu_src, (long long)ld_src, (long long)stride_src, rows, out_features,
+               in_features, members);
+  else
+    launch_pdl(head_backward_data_kernel<1>, dim3((unsigned)ceil_div_ll(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+               dy, (long long)lddy, (long long)stride_dy, w, (long long)ldw, (long long)stride_w, dx, (long long)lddx,
+               (long long)stride_dx, relu_src, (long long)ld_src, (long long)stride_src, rows, out_features,
+               in_features, members);
   return check_launch("head_backward_data");
 }
 
@@ -148,19 +211,21 @@ extern "C" int d3b_head_backward_weight(const float* dy, int64_t lddy, int64_t s
   size_t smem = (size_t)rpb * out_features * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_features <= 1)
-    head_backward_weight_kernel<1><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw, stride_dw,
-                                                            dbias, stride_db, rows, out_features, in_features, rpb);
+    launch_pdl(head_backward_weight_kernel<1>, grid, dim3(256), smem, st, dy, (long long)lddy, (long long)stride_dy, x,
+               (long long)ldx, (long long)stride_x, dw, (long long)lddw, (long long)stride_dw, dbias, (long long)stride_db, rows,
+               out_features, in_features, rpb);
   else if (out_features <= 8)
-    head_backward_weight_kernel<8><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw, stride_dw,
-                                                            dbias, stride_db, rows, out_features, in_features, rpb);
+    launch_pdl(head_backward_weight_kernel<8>, grid, dim3(256), smem, st, dy, (long long)lddy, (long long)stride_dy, x,
+               (long long)ldx, (long long)stride_x, dw, (long long)lddw, (long long)stride_dw, dbias, (long long)stride_db, rows,
+               out_features, in_features, rpb);
   else if (out_features <= 16)
-    head_backward_weight_kernel<16><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw,
-                                                             stride_dw, dbias, stride_db, rows, out_features,
-                                                             in_features, rpb);
+    launch_pdl(head_backward_weight_kernel<16>, grid, dim3(256), smem, st, dy, (long long)lddy, (long long)stride_dy, x,
+               (long long)ldx, (long long)stride_x, dw, (long long)lddw, (long long)stride_dw, dbias, (long long)stride_db, rows,
+               out_features, in_features, rpb);
   else
-    head_backward_weight_kernel<32><<<grid, 256, smem, st>>>(dy, lddy, stride_dy, x, ldx, stride_x, dw, lddw,
-                                                             stride_dw, dbias, stride_db, rows, out_features,
-                                                             in_features, rpb);
+    launch_pdl(head_backward_weight_kernel<32>, grid, dim3(256), smem, st, dy, (long long)lddy, (long long)stride_dy, x,
+               (long long)ldx, (long long)stride_x, dw, (long long)lddw, (long long)stride_dw, dbias, (long long)stride_db, rows,
+               out_features, in_features, rpb);
   return check_launch("head_backward_weight");
 }
 

@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    float* __restrict__ targ, long long n, const int* step, double lr,
                                                    double b1, double b2, double eps, float tau, int zero_grad,
                                                    float weight_decay) {
+  pdl_trigger();
+  pdl_wait();
   float w1, fb2, w2, feps, neg_ss, bc2s;
   adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
   float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
@@ -270,8 +272,8 @@ extern "C" int d3b_adam_step(float* params, float* grads, float* exp_avg, float*
   D3B_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
                (uintptr_t)target) % 16 == 0,
               "adam_step: arenas must be 16-byte aligned");
-  adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
-                                                                lr, beta1, beta2, eps, tau, zero_grad, 0.f);
+  launch_pdl(adam_kernel, dim3(grid_for(n, 4)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq,
+             target, (long long)n, step, lr, beta1, beta2, eps, tau, zero_grad, 0.f);
   return check_launch("adam_step");
 }
 
@@ -286,8 +288,8 @@ extern "C" int d3b_adam_step_wd(float* params, float* grads, float* exp_avg, flo
   D3B_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq |
                (uintptr_t)target) % 16 == 0,
               "adam_step_wd: arenas must be 16-byte aligned");
-  adam_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, target, n, step,
-                                                                lr, beta1, beta2, eps, tau, zero_grad, weight_decay);
+  launch_pdl(adam_kernel, dim3(grid_for(n, 4)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq,
+             target, (long long)n, step, lr, beta1, beta2, eps, tau, zero_grad, weight_decay);
   return check_launch("adam_step_wd");
 }
 
