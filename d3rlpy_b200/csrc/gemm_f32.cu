@@ -219,6 +219,7 @@ static bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 namespace tc32 {
 int engine();
 int ops();
+int wgrad_split_mode();
 int gemm(const float* a, long long lda, long long stride_a, int a_rc, const float* b, long long ldb,
          long long stride_b, int b_rc, float* c, long long ldc, long long stride_c, int m, int n, int r, int members,
          int splits, const float* bias, long long stride_bias, int relu, const float* mask, long long ld_mask,
@@ -288,10 +289,16 @@ extern "C" int d3b_linear_backward_weight(const float* dy, int64_t lddy, int64_t
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dy && x && dw, "linear_backward_weight: null pointer");
   if (use_tc(out_features, 4) && rows >= 32) {
-    // split the minibatch-row reduction so that ~one wave of CTAs exists
+    // split the minibatch-row reduction so that two CTAs per SM exist (the throughput configuration of the kernel:
+    // measured 27.9 -> 19.2 us at the c2 shape and 1105 -> 683 us at the c5 shape against one CTA per SM; four per SM
+    // is slower again, profiles/r2/tc32_wgrad.py)
     int bn = in_features > 64 ? 128 : (in_features > 32 ? 64 : 32);
     long long tiles = (long long)ceil_div(out_features, 128) * ceil_div(in_features, bn) * members;
-    int want = (int)ceil_div_ll(kNumSM, tiles);
+    int want = (int)((2 * kNumSM) / tiles);
+    const int mode = tc32::wgrad_split_mode();               // profiling knob
+    if (mode == 1) want = (int)ceil_div_ll(kNumSM, tiles);
+    if (mode == 2) want = (int)(kNumSM / tiles);
+    if (mode == 3) want = (int)((4 * kNumSM) / tiles);
     int max_splits = ceil_div(rows, 64);
     int splits = want < 1 ? 1 : (want > max_splits ? max_splits : want);
     return tc32::gemm(dy, lddy, stride_dy, 0, x, ldx, stride_x, 0, dw, lddw, stride_dw, out_features, in_features,

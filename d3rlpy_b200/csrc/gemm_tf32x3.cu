@@ -615,6 +615,7 @@ static long long* g_dbg = nullptr;
 static int g_variant = 0;
 static int g_ops = 7;  // which layer GEMMs run on the tensor cores: bit 0 forward, bit 1 data gradient, bit 2 weight gradient
 int ops() { return g_ops; }
+int wgrad_split_mode() { return (g_variant >> 16) & 3; }
 static int g_engine = -1;  // -1: read D3B_FP32_ENGINE on first use; 0 = SIMT FFMA, 1 = 3xTF32 tensor cores
 
 int engine() {
