@@ -11,6 +11,7 @@ backward in update_alpha and the unused critic weight-gradients in update_actor 
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -97,13 +98,15 @@ class CQLImpl(DDPGBaseImpl):
         return lay
 
     # ------------------------------------------------------------------ program pieces
-    def _p_policy(self, db):
-        """Policy trunk + (mu|logstd) head on [obs; next_obs] (contiguous in the device batch)."""
+    def _p_policy(self, db, converted: bool = False):
+        """Policy trunk + (mu|logstd) head on [obs; next_obs] (contiguous in the device batch).  converted: the
+        update prologue already wrote the bf16 operand rows into the workspace."""
         B, O, A = db.B, db.O, self._action_size
         acts = self._policy.ctx("pi", 2 * B, 1, True)
         head = self.ws("pi_head", 1, 2 * B, 2 * A)
         assert db.off["next_obs"] == db.off["obs"] + B * O, "obs/next_obs must be contiguous"
-        self._policy.forward("params", db.ptr("obs"), O, 2 * B, acts, head, self._stream)
+        self._policy.forward("params", db.ptr("obs"), O, 2 * B, acts, head, self._stream,
+                             x_bf16=(acts.xb.data_ptr(), acts.ldk0) if converted else None)
         return acts, head
 
     def _p_temp(self, db, head):
@@ -285,22 +288,36 @@ class CQLImpl(DDPGBaseImpl):
         lp = self.ws("xf_lp", 4, max(B * N, 1))
         lpm = self.ws("xf_lpm", 3, B)  # soft-backup, actor, temp log-probs
         # per loss kernel: block counter + per-block partial sums (fixed-order final sums, csrc/cql_fused.cu)
-        done = self.ws("xf_done", 3, 4 + 3 * ((B * E + 7) // 8) + 4, dtype=torch.int32)
+        done = self.ws("xf_done", 4, 4 + 3 * ((B * E + 7) // 8) + 4, dtype=torch.int32)
         dp = self.world_size > 1  # sharded minibatch: sums / gradients are all-reduced between the partial kernels
         inv_b = 1.0 / (B * self.world_size)
         mask = 0
         for c in [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else []):
             mask |= 1 << c
-        L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
         px = getattr(self, "_px", None) if dp else None
+        one_prologue = not dp and os.environ.get("D3B_PROLOGUE", "1") != "0"   # 0: the three separate launches (A/B timing)
+        if one_prologue:
+            # ONE prologue launch: counters, slot zeroing, the update's noise, bf16 operand rows of the policy input
+            _, n_norm, n_uni, _ = self._noise_plan(B)
+            draw = not self._noise_injected and n_norm + n_uni > 0
+            pre = self._policy.ctx("pi", 2 * B, 1, True) if not f32 else None
+            L.update_prologue(self._counters.data_ptr(), self.N_COUNTERS, mask, C_DRAW, self._slots.data_ptr(), 64,
+                              self._noise_arena(B).data_ptr() if draw else None, n_norm if draw else 0,
+                              n_uni if draw else 0, self._seed & 0xFFFFFFFFFFFFFFFF,
+                              db.ptr("obs") if pre is not None else None, O, 2 * B, O,
+                              pre.xb.data_ptr() if pre is not None else None, pre.ldk0 if pre is not None else 0,
+                              done[3].data_ptr(), st)
+        else:
+            L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
         if px is not None:
             # peers have finished reading last update's gradients -> zero them for this update's RED accumulation
             fq, fp = self._q_func._peer[1], self._policy._peer[1]
             L.peer_wait_zero(px.flags_ptrs, px.world, px.rank, fq + 1, self.counter_ptr(C_DRAW),
                              self._q_func.arena.grads.data_ptr(), self._q_func.arena.size, fp + 1,
                              self._policy.arena.grads.data_ptr(), self._policy.arena.size, st)
-        self.fill_noise(B)
-        acts_p, head = self._p_policy(db)
+        if not one_prologue:
+            self.fill_noise(B)
+        acts_p, head = self._p_policy(db, converted=one_prologue and not f32)
         nv = lambda name: self.noise_view(name, B).data_ptr()
         soft = self._soft_q_backup
         ptrs = [nv("critic_t"), nv("critic_tp1"), nv("critic_rand"), lp[0].data_ptr(), lp[1].data_ptr()] if N > 0 \

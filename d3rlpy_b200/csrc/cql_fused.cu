@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace d3b {
 
@@ -26,6 +27,54 @@ __global__ void begin_step_kernel(int* counters, int n, unsigned mask, float* sl
   int i = threadIdx.x;
   if (i < n && ((mask >> i) & 1u)) counters[i] += 1;
   for (int j = i; j < n_slots; j += blockDim.x) slots[j] = 0.f;
+}
+
+// Update prologue in ONE launch (begin_step + noise_fill + to_bf16 of the policy input were three):
+//   * loss partial sums / metric slots zeroed (block 0);
+//   * the update's noise arena drawn with Philox at epoch = counters[draw] + 1 (read BEFORE any bump: the counters are
+//     bumped by the last block to finish, so every block sees the same epoch without a grid barrier);
+//   * rows x cols of fp32 `src` (policy input [obs; next_obs]) converted to a bf16 GEMM operand (optional).
+struct PrologueParams {
+  int* counters; int n_counters; unsigned mask; int draw;
+  float* slots; int n_slots;
+  float* noise; long long n_normal, n_uniform; unsigned long long seed; int noise_blocks;
+  const float* src; long long lds; int rows, cols; __nv_bfloat16* dst; long long ldd;
+  unsigned* done;
+};
+
+__global__ void __launch_bounds__(256) update_prologue_kernel(PrologueParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int t = threadIdx.x;
+  const uint32_t epoch = (uint32_t)(p.counters[p.draw] + (int)((p.mask >> p.draw) & 1u));
+  if (blockIdx.x == 0)
+    for (int j = t; j < p.n_slots; j += blockDim.x) p.slots[j] = 0.f;
+  if ((int)blockIdx.x < p.noise_blocks) {
+    const long long n = p.n_normal + p.n_uniform;
+    long long q = (long long)blockIdx.x * blockDim.x + t;
+    const long long stride = (long long)p.noise_blocks * blockDim.x;
+    for (; (q << 2) < n; q += stride) noise_quad(p.noise, q, p.n_normal, n, p.seed, epoch);
+  } else if (p.src) {
+    // element (r, c) of the padded bf16 operand; padding columns stay zero (written once at allocation)
+    const long long total = (long long)p.rows * p.cols;
+    long long i = (long long)(blockIdx.x - p.noise_blocks) * blockDim.x + t;
+    const long long stride = (long long)(gridDim.x - p.noise_blocks) * blockDim.x;
+    for (; i < total; i += stride) {
+      const int r = (int)(i / p.cols), c = (int)(i % p.cols);
+      p.dst[(long long)r * p.ldd + c] = __float2bfloat16_rn(__ldg(p.src + (long long)r * p.lds + c));
+    }
+  }
+  // every block has read the old counters by now; the last one to get here bumps them
+  __syncthreads();
+  if (t == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(p.done, 1u);
+    if (prev == gridDim.x - 1) {
+      for (int i = 0; i < p.n_counters; ++i)
+        if ((p.mask >> i) & 1u) p.counters[i] += 1;
+      *p.done = 0u;
+    }
+  }
 }
 
 struct RowsParams {
@@ -405,6 +454,34 @@ extern "C" int d3b_begin_step(int* counters, int n, unsigned mask, float* slots,
   D3B_REQUIRE(counters && n >= 0 && n <= 32 && slots && n_slots >= 0, "begin_step: bad arguments");
   launch_pdl(begin_step_kernel, dim3(1), dim3(64), 0, ST, counters, n, mask, slots, n_slots);
   return check_launch("begin_step");
+}
+
+extern "C" int d3b_update_prologue(int* counters, int n_counters, unsigned mask, int draw_index, float* slots,
+                                   int n_slots, float* noise, int64_t n_normal, int64_t n_uniform, uint64_t seed,
+                                   const float* src, int64_t lds, int rows, int cols, void* dst_bf16, int64_t ldd,
+                                   void* done_counter, void* stream) {
+  D3B_REQUIRE(counters && n_counters >= 0 && n_counters <= 32 && draw_index >= 0 && draw_index < 32 && slots &&
+                  n_slots >= 0 && done_counter,
+              "update_prologue: bad arguments");
+  D3B_REQUIRE(n_normal >= 0 && n_uniform >= 0 && (n_normal + n_uniform == 0 || noise), "update_prologue: noise arena");
+  D3B_REQUIRE(!src || (dst_bf16 && rows >= 0 && cols >= 1), "update_prologue: conversion arguments");
+  PrologueParams p{};
+  p.counters = counters; p.n_counters = n_counters; p.mask = mask; p.draw = draw_index;
+  p.slots = slots; p.n_slots = n_slots;
+  p.noise = noise; p.n_normal = n_normal; p.n_uniform = n_uniform; p.seed = seed;
+  const long long quads = (n_normal + n_uniform + 3) / 4;
+  p.noise_blocks = (int)(quads == 0 ? 0 : (quads + 255) / 256 > 2 * kNumSM ? 2 * kNumSM : (quads + 255) / 256);
+  p.src = src; p.lds = lds; p.rows = rows; p.cols = cols; p.dst = (__nv_bfloat16*)dst_bf16; p.ldd = ldd;
+  p.done = (unsigned*)done_counter;
+  int conv_blocks = 0;
+  if (src && rows > 0) {
+    const long long total = (long long)rows * cols;
+    conv_blocks = (int)((total + 255) / 256 > kNumSM ? kNumSM : (total + 255) / 256);
+  }
+  int blocks = p.noise_blocks + conv_blocks;
+  if (blocks < 1) blocks = 1;
+  launch_pdl(update_prologue_kernel, dim3((unsigned)blocks), dim3(256), 0, ST, p);
+  return check_launch("update_prologue");
 }
 
 // ptrs_host: 16 device pointers in the order

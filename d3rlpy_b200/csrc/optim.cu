@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace d3b {
 
@@ -200,24 +201,6 @@ __global__ void tick_kernel(int* counters, int n, unsigned mask) {
   if (i < n && ((mask >> i) & 1u)) counters[i] += 1;
 }
 
-// ---------------------------------------------------------------- Philox4x32-10 noise fill
-__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
-  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
-  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-}
-__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    philox_round(c, k0, k1);
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
-  }
-}
-__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
-
 // segment layout: first n_normal floats ~ N(0,1), next n_uniform floats ~ U(-1,1).
 // counter = (*draw_counter) so that graph replays advance the stream; bumped by tick_kernel.
 __global__ void __launch_bounds__(256) noise_fill_kernel(float* __restrict__ out, long long n_normal,
@@ -229,26 +212,7 @@ __global__ void __launch_bounds__(256) noise_fill_kernel(float* __restrict__ out
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one Philox call -> 4 floats
   long long stride = (long long)gridDim.x * blockDim.x;
   uint32_t epoch = (uint32_t)(*draw_counter);
-  for (; (q << 2) < n; q += stride) {
-    uint32_t c[4] = {(uint32_t)q, (uint32_t)(q >> 32), epoch, 0x5eedu};
-    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    float r[4];
-    long long base = q << 2;
-    // Box-Muller on pairs; uniform section gets 2u-1
-    float u0 = u01(c[0]), u1 = u01(c[1]), u2 = u01(c[2]), u3 = u01(c[3]);
-    float ra = sqrtf(-2.f * logf(u0)), rb = sqrtf(-2.f * logf(u2));
-    float s0, c0, s1, c1;
-    sincospif(2.f * u1, &s0, &c0);
-    sincospif(2.f * u3, &s1, &c1);
-    float nrm[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
-    float uni[4] = {2.f * u0 - 1.f, 2.f * u1 - 1.f, 2.f * u2 - 1.f, 2.f * u3 - 1.f};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      long long i = base + j;
-      r[j] = (i < n_normal) ? nrm[j] : uni[j];
-      if (i < n) out[i] = r[j];
-    }
-  }
+  for (; (q << 2) < n; q += stride) noise_quad(out, q, n_normal, n, seed, epoch);
 }
 
 }  // namespace d3b

@@ -316,6 +316,13 @@ int d3b_sac_soft_backup(const float* q_targ, int64_t stride_q, int members, cons
  *   counter, words [4, 4 + 3 * ceil(batch * members / 8)) (cql_loss_step) or [4, 4 + ceil(batch / 256)) (sac_actor_step) =
  *   per-block partial sums; the last block adds them in a fixed order, so `sums` and the metrics are bit-reproducible. */
 int d3b_begin_step(int* counters, int n, unsigned mask, float* slots, int n_slots, void* stream);
+/* begin_step + noise_fill (epoch = counters[draw_index] after its bump) + optional fp32 -> bf16 conversion of the
+ * policy input rows, in ONE launch; done_counter: one zero-initialised 32-bit word (self-resetting).  The counters are
+ * bumped by the last block to finish, so the launch needs no grid barrier. */
+int d3b_update_prologue(int* counters, int n_counters, unsigned mask, int draw_index, float* slots, int n_slots,
+                        float* noise, int64_t n_normal, int64_t n_uniform, uint64_t seed, const float* src,
+                        int64_t lds, int rows, int cols, void* dst_bf16, int64_t ldd, void* done_counter,
+                        void* stream);
 int d3b_cql_rows(const float* head, const float* obs, const float* next_obs, const float* act, int batch,
                  int n_action_samples, int obs_dim, int act_dim, float min_logstd, float max_logstd, void* x_bf16,
                  int64_t ldx, int n_groups, const void* const* ptrs_host, const int64_t* rows_host, void* stream);

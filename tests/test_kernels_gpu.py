@@ -468,3 +468,43 @@ def test_wide_head_dense_layer_forward_backward(precision, rows, feat, n, E):
             got = net.arena.view(k, e, "grads").cpu().double()
             scale = max(float(v.grad.abs().max()), 1e-6)
             assert float((got - v.grad).abs().max()) <= tol * scale + 1e-7, (precision, k, e)
+
+
+@pytest.mark.gpu
+def test_update_prologue_equals_begin_step_noise_fill_to_bf16():
+    """One launch == begin_step + noise_fill + to_bf16 (csrc/cql_fused.cu): same counters, zeroed slots, the same
+    Philox stream bit for bit (epoch read before the bump), the same bf16 rows; repeated launches advance the epoch."""
+    from d3rlpy_b200._lib import lib
+
+    L = lib()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(0)
+    rows, cols, ld = 70, 17, 24
+    src = torch.randn(rows, cols, generator=g).to(dev)
+    n_norm, n_uni, seed = 70001, 3333, 0x1234ABCD5678
+    mask = 0b100101
+    for rep in range(2):
+        ca = torch.tensor([5, 7, 9, 11, 13, 15], dtype=torch.int32, device=dev) + rep
+        cb = ca.clone()
+        slots_a, slots_b = torch.ones(64, device=dev), torch.ones(64, device=dev)
+        na, nb = torch.zeros(n_norm + n_uni + 3, device=dev), torch.zeros(n_norm + n_uni + 3, device=dev)
+        xa = torch.zeros(rows, ld, dtype=torch.bfloat16, device=dev)
+        xb = torch.zeros(rows, ld, dtype=torch.bfloat16, device=dev)
+        done = torch.zeros(4, dtype=torch.int32, device=dev)
+        L.update_prologue(ca.data_ptr(), 6, mask, 0, slots_a.data_ptr(), 64, na.data_ptr(), n_norm, n_uni, seed,
+                          src.data_ptr(), cols, rows, cols, xa.data_ptr(), ld, done.data_ptr(), st)
+        L.begin_step(cb.data_ptr(), 6, mask, slots_b.data_ptr(), 64, st)
+        L.noise_fill(nb.data_ptr(), n_norm, n_uni, seed, cb.data_ptr(), st)
+        L.to_bf16(src.data_ptr(), cols, rows, cols, xb.data_ptr(), ld, None, 0, st)
+        torch.cuda.synchronize()
+        assert torch.equal(ca, cb) and int(done[0]) == 0
+        assert torch.equal(slots_a, slots_b) and float(slots_a.abs().sum()) == 0.0
+        assert torch.equal(na, nb), "noise stream differs"
+        assert torch.equal(xa, xb)
+    # no noise, no conversion: counters and slots only
+    ca = torch.zeros(6, dtype=torch.int32, device=dev)
+    L.update_prologue(ca.data_ptr(), 6, 0b11, 0, slots_a.data_ptr(), 64, None, 0, 0, 0, None, 0, 0, 0, None, 0,
+                      done.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ca.tolist() == [1, 1, 0, 0, 0, 0]
