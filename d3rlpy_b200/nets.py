@@ -89,9 +89,9 @@ class Ctx:
         hid = net.hidden
         if net.precision == "fp32":
             self.acts = [torch.zeros(E, rows, h, dtype=torch.float32, device=dev) for h in hid]
-            hm = max(hid)
-            self.scratch = (torch.zeros(E, rows, hm, dtype=torch.float32, device=dev),
-                            torch.zeros(E, rows, hm, dtype=torch.float32, device=dev)) if train else None
+            # dZ_l of every layer: the weight-gradient GEMMs run on a side stream beside the data-gradient chain, so a
+            # layer's dZ must stay intact while the chain moves on (no ping-pong scratch)
+            self.dz = [torch.zeros(E, rows, h, dtype=torch.float32, device=dev) for h in hid] if train else None
         else:
             bf = torch.bfloat16
             self.ldk0 = _a8(net.in_dim)
@@ -217,6 +217,13 @@ class DenseNet:
     def _hb(self, which, member=0):
         return self.arena.addr(which, "__head.bias", member)
 
+    wgrad_side = True   # fp32 mode: weight-gradient GEMMs on a side stream beside the data-gradient chain
+
+    def _wgrad_stream(self) -> int:
+        if getattr(self, "_wg_side", None) is None:
+            self._wg_side = torch.cuda.Stream(device=self.device)
+        return self._wg_side.cuda_stream
+
     def ctx(self, tag: str, rows: int, members: Optional[int] = None, train: bool = True) -> Ctx:
         E = members or self.members
         c = self._ctx.get(tag)
@@ -309,19 +316,23 @@ class DenseNet:
         nl = len(self.hidden)
         if self.precision == "fp32":
             last = ctx.acts[-1]
-            dcur = ctx.scratch[0]
+            dcur = ctx.dz[nl - 1]
             ar = ctx.rows   # member stride of the saved activations (rows <= ar: backward over a prefix of the rows)
+            # weight gradients on a side stream: dW_l only needs dZ_l, the chain dZ_l -> dZ_{l-1} does not need dW_l
+            side = self._wgrad_stream() if weight_grads and self.wgrad_side else None
+            ws = side if side is not None else stream
             if self.wide_head:
                 _wide_head_backward(self, ctx, rows, E, d_head, _p(last), feat, ar * feat, _p(dcur), feat, rows * feat,
                                     stream, weight_grads, member0)
             else:
                 if weight_grads:
+                    if side is not None:
+                        L.stream_fork(stream, side)
                     L.head_backward_weight(_p(d_head), ldh, sdh, _p(last), feat, ar * feat,
                                            self._hw("grads", member0), feat, ms, self._hb("grads", member0), ms, rows,
-                                           n, feat, E, stream)
+                                           n, feat, E, ws)
                 L.head_backward_data(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), feat,
                                      rows * feat, _p(last), feat, ar * feat, rows, n, feat, E, stream)
-            which = 0
             for i in range(nl - 1, -1, -1):
                 h = self.hidden[i]
                 d_in = self.hidden[i - 1] if i > 0 else self.in_dim
@@ -330,16 +341,20 @@ class DenseNet:
                 else:
                     inp, ldi, si = _p(x), ldx, 0
                 if weight_grads:
+                    if side is not None:
+                        L.stream_fork(stream, side)   # dZ_i is complete on the main stream
                     L.linear_backward_weight(_p(dcur), h, rows * h, inp, ldi, si, self._w("grads", i, member0), d_in,
-                                             ms, self._b("grads", i, member0), ms, rows, h, d_in, E, stream)
+                                             ms, self._b("grads", i, member0), ms, rows, h, d_in, E, ws)
                 if i > 0:
-                    dnext = ctx.scratch[1 - which]
+                    dnext = ctx.dz[i - 1]
                     L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", i, member0), d_in, ms, _p(dnext),
                                            d_in, rows * d_in, inp, ldi, si, rows, h, d_in, E, stream)
-                    dcur, which = dnext, 1 - which
+                    dcur = dnext
                 elif dx is not None:
                     L.linear_backward_data(_p(dcur), h, rows * h, self._w("params", 0, member0) + 4 * dx_col0, d_in,
                                            ms, _p(dx), lddx, stride_dx, None, 0, 0, rows, h, dx_cols, E, stream)
+            if side is not None:
+                L.stream_join(stream, side)
             return
         # ---- bf16 mode.  dgrad: C = A B^T over K-major operands (dZ_l, W_l^T shadow); wgrad: C += A^T B with
         # both operands row-major (MN-major UMMA tiles): dW_l = dZ_l^T H_{l-1}, reduction over the minibatch rows
