@@ -599,7 +599,7 @@ def run_ours(args, w):
         achieved = dom["gflop_per_launch"] / (dom["us_per_launch"] * 1e-6) / 1e3 if dom else 0.0
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_dominant.json")))["dram_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_dominant.json")))["dram_bytes_per_launch"]
         except Exception:  # noqa: BLE001
             pass
         roof = {"bound": "tensor",
@@ -611,7 +611,7 @@ def run_ours(args, w):
                 else "fallback 1.59 PFLOP/s",
                 "traffic": traffic,
                 "traffic_source": "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of this launch from "
-                                  "the committed ncu capture profiles/r1_ncu_dominant.json",
+                                  "the committed ncu capture profiles/r2_ncu_dominant.json",
                 "how": "algorithmic FLOPs of the launch / mean CUDA-event duration around that launch on the update "
                        "stream, eager instrumented pass of the same update (a busy-wait kernel keeps the stream ahead "
                        "of the host); the graph replay itself cannot be split by events",
