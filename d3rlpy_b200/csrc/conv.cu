@@ -33,33 +33,39 @@ __device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
 // patches[e][(b,oh,ow)][ic*k*k + kh*k + kw] = x[...] / divisor ; x[e][b][ic][oh*s+kh][ow*s+kw]  (generic element strides)
+// One thread per (patch row, ic, kh): it writes the ksz consecutive kw entries (32-bit index arithmetic; the host
+// checks the sizes).  With unit stride along the width (first layer: NCHW uint8 frames) the run is contiguous in
+// the source as well.
 template <typename In, typename Out>
 __global__ void __launch_bounds__(256) im2col_kernel(const In* __restrict__ x, long long sx_member, long long sb,
                                                      long long sc, long long sh, long long sw,
                                                      Out* __restrict__ out, long long ldo, long long so_member,
                                                      int images, int C, int OH, int OW, int ksz, int stride,
                                                      float scale, int K_pad) {
+  pdl_trigger();
+  pdl_wait();
   const int K = C * ksz * ksz;
-  const long long rows = (long long)images * OH * OW;
-  const long long total = rows * K_pad;
+  const int runs = C * ksz;                         // (ic, kh) runs per patch row
+  const int pad_runs = (K_pad - K + ksz - 1) / ksz; // zero padding up to the leading dimension, in runs of ksz
+  const int per_row = runs + pad_runs;
+  const unsigned rows = (unsigned)images * OH * OW;
+  const unsigned total = rows * (unsigned)per_row;
   const In* xe = x + (long long)blockIdx.y * sx_member;
   Out* oe = out + (long long)blockIdx.y * so_member;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    long long row = idx / K_pad;
-    int k = (int)(idx - row * K_pad);
-    float v = 0.f;
-    if (k < K) {
-      int kw = k % ksz, t = k / ksz;
-      int kh = t % ksz, ic = t / ksz;
-      int ow = (int)(row % OW);
-      long long t2 = row / OW;
-      int oh = (int)(t2 % OH);
-      long long b = t2 / OH;
-      v = load_scaled<In>(xe + b * sb + ic * sc + (long long)(oh * stride + kh) * sh + (long long)(ow * stride + kw) * sw,
-                          scale);
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned row = idx / per_row;
+    const int run = (int)(idx - row * per_row);
+    Out* o = oe + (long long)row * ldo + run * ksz;
+    if (run >= runs) {
+      for (int j = 0; j < ksz && run * ksz + j < K_pad; ++j) store_out(o + j, 0.f);
+      continue;
     }
-    store_out(oe + row * ldo + k, v);
+    const int kh = run % ksz, ic = run / ksz;
+    const unsigned ow = row % OW, t2 = row / OW;
+    const unsigned oh = t2 % OH, b = t2 / OH;
+    const In* src = xe + (long long)b * sb + (long long)ic * sc + (long long)(oh * stride + kh) * sh +
+                    (long long)(ow * stride) * sw;
+    for (int j = 0; j < ksz; ++j) store_out(o + j, load_scaled<In>(src + (long long)j * sw, scale));
   }
 }
 
@@ -122,11 +128,14 @@ extern "C" int d3b_im2col(const void* x, int x_is_u8, int64_t stride_x, int64_t 
   int K = channels * ksize * ksize;
   D3B_REQUIRE(ldo >= K, "im2col: ldo < C*k*k");
   int K_pad = out_is_bf16 ? (int)ldo : K;  // bf16 rows are zero-padded to the 16-byte leading dimension
-  long long total = (long long)images * OH * OW * K_pad;
+  long long per_row = (long long)channels * ksize + (K_pad - K + ksize - 1) / ksize;
+  long long total = (long long)images * OH * OW * per_row;
+  D3B_REQUIRE(total < (1LL << 31), "im2col: too many patch runs for one launch");
   dim3 grid(grid_for(total), members);
-#define LAUNCH(IN, OUT)                                                                                          \
-  im2col_kernel<IN, OUT><<<grid, 256, 0, ST>>>((const IN*)x, stride_x, sb, sc, sh, sw, (OUT*)out, ldo, stride_o, \
-                                               images, channels, OH, OW, ksize, stride, divisor, K_pad)
+#define LAUNCH(IN, OUT)                                                                                               \
+  launch_pdl(im2col_kernel<IN, OUT>, grid, dim3(256), 0, ST, (const IN*)x, (long long)stride_x, (long long)sb,        \
+             (long long)sc, (long long)sh, (long long)sw, (OUT*)out, (long long)ldo, (long long)stride_o, images,     \
+             channels, OH, OW, ksize, stride, divisor, K_pad)
   // x_is_u8: 0 = fp32 input, 1 = uint8 input, 2 = bf16 input (NHWC activations of the tensor-core path)
   if (x_is_u8 == 1 && out_is_bf16) LAUNCH(uint8_t, __nv_bfloat16);
   else if (x_is_u8 == 1) LAUNCH(uint8_t, float);
