@@ -227,7 +227,13 @@ int gemm(const float* a, long long lda, long long stride_a, int a_rc, const floa
 }  // namespace tc32
 
 // the tensor-core tile is 128 rows: below half a tile the SIMT small-M kernel wastes less
-static bool use_tc(int m_rows, int op_bit) { return tc32::engine() == 1 && (tc32::ops() & op_bit) && m_rows >= 64; }
+static bool use_tc(int m_rows, int op_bit, long long weight_elems = 0) {
+  if (tc32::engine() != 1 || !(tc32::ops() & op_bit)) return false;
+  // below half a row tile the SIMT small-M kernel wastes less — unless the layer is big: the Nature-DQN fc layer
+  // (3136 -> 512) at batch 32 ran 272 us on 8 SIMT CTAs; the cluster split-K tensor-core configuration spreads the
+  // reduction over the machine
+  return m_rows >= 64 || (m_rows >= 16 && weight_elems >= (1LL << 20));
+}
 
 }  // namespace d3b
 
@@ -241,7 +247,7 @@ extern "C" int d3b_linear_forward(const float* x, int64_t ldx, int64_t stride_x,
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && w && y, "linear_forward: null pointer");
   D3B_REQUIRE(ldx >= in_features && ldw >= in_features && ldy >= out_features, "linear_forward: bad leading dims");
-  if (use_tc(rows, 1))
+  if (use_tc(rows, 1, (long long)out_features * in_features))
     return tc32::gemm(x, ldx, stride_x, 1, w, ldw, stride_w, 1, y, ldy, stride_y, rows, out_features, in_features,
                       members, 1, bias, stride_b, relu, nullptr, 0, 0, nullptr, 0, 0, (cudaStream_t)stream);
   GemmArgs g{};
@@ -264,7 +270,7 @@ extern "C" int d3b_linear_backward_data(const float* dy, int64_t lddy, int64_t s
   D3B_REQUIRE(rows >= 0 && out_features > 0 && in_features > 0 && members > 0, "linear_backward_data: bad sizes");
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(dy && w && dx, "linear_backward_data: null pointer");
-  if (use_tc(rows, 2))
+  if (use_tc(rows, 2, (long long)out_features * in_features))
     return tc32::gemm(dy, lddy, stride_dy, 1, w, ldw, stride_w, 0, dx, lddx, stride_dx, rows, in_features,
                       out_features, members, 1, nullptr, 0, 0, relu_src, ld_src, stride_src, nullptr, 0, 0,
                       (cudaStream_t)stream);

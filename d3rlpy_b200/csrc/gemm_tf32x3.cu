@@ -655,6 +655,8 @@ int gemm(const float* a, long long lda, long long stride_a, int a_rc, const floa
     long long tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
     if (tiles * 2 <= kNumSM && force_s != 1) {
       if (BN == 128) BN = 64;
+      // a long reduction over few tiles (Nature-DQN fc layer at batch 32): narrower tiles fill the machine
+      if (BN == 64 && (long long)ceil_div(m, BM) * ceil_div(n, BN) * members * 16 <= kNumSM && num_kb >= 64) BN = 32;
       if (force_bn) BN = 16 << force_bn;
       tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
       while (csplit * 2 <= 8 && tiles * csplit * 2 <= kNumSM && num_kb >= csplit * 2 * 4) csplit *= 2;
