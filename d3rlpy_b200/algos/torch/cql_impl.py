@@ -295,7 +295,7 @@ class CQLImpl(DDPGBaseImpl):
         for c in [C_DRAW, C_CRITIC, C_ACTOR] + ([C_TEMP] if do_temp else []) + ([C_ALPHA] if do_alpha else []):
             mask |= 1 << c
         px = getattr(self, "_px", None) if dp else None
-        one_prologue = not dp and os.environ.get("D3B_PROLOGUE", "1") != "0"   # 0: the three separate launches (A/B timing)
+        one_prologue = os.environ.get("D3B_PROLOGUE", "1") != "0"   # 0: the three separate launches (A/B timing)
         if one_prologue:
             # ONE prologue launch: counters, slot zeroing, the update's noise, bf16 operand rows of the policy input
             _, n_norm, n_uni, _ = self._noise_plan(B)
@@ -303,7 +303,8 @@ class CQLImpl(DDPGBaseImpl):
             pre = self._policy.ctx("pi", 2 * B, 1, True) if not f32 else None
             L.update_prologue(self._counters.data_ptr(), self.N_COUNTERS, mask, C_DRAW, self._slots.data_ptr(), 64,
                               self._noise_arena(B).data_ptr() if draw else None, n_norm if draw else 0,
-                              n_uni if draw else 0, self._seed & 0xFFFFFFFFFFFFFFFF,
+                              n_uni if draw else 0,
+                              (self._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF,   # per-rank Philox key
                               db.ptr("obs") if pre is not None else None, O, 2 * B, O,
                               pre.xb.data_ptr() if pre is not None else None, pre.ldk0 if pre is not None else 0,
                               done[3].data_ptr(), st)

@@ -159,6 +159,29 @@ __device__ __forceinline__ void wait_all(const PeerPtrs& ps, int f, int e) {    
   if ((int)threadIdx.x < ps.world) wait_flag_ge(ps.flags[ps.rank] + f * kMaxRanks + threadIdx.x, e);
 }
 
+// Short vectors (loss partial sums) are PUSHED like the flags: writer w stores its n values into slot
+// [channel][parity][w] of EVERY rank's exchange block (W independent remote stores), fences, raises its flag; after the
+// flags arrived each rank sums its own block in rank order.  (Pulling them — one dependent NVLink round trip per peer,
+// 2-3 us each, serialised by the volatile loads — cost ~20 us per rendezvous at 8 GPUs.)
+__device__ __forceinline__ int xchg_slot(int channel, int e, int writer) {
+  return ((channel * 2 + (e & 1)) * kMaxRanks + writer) * 16;
+}
+__device__ __forceinline__ void push_small(float* const* xchg, const PeerPtrs& ps, int channel, int e, const float* vec,
+                                           int n) {   // threads 0..n-1 of one warp
+  const int t = threadIdx.x;
+  if (t < n) {
+    const float v = vec[t];
+    for (int r = 0; r < ps.world; ++r) xchg[r][xchg_slot(channel, e, ps.rank) + t] = v;
+  }
+  __threadfence_system();
+}
+__device__ __forceinline__ float sum_small(float* const* xchg, const PeerPtrs& ps, int channel, int e, int t) {
+  const volatile float* mine = xchg[ps.rank];
+  float s = 0.f;
+  for (int r = 0; r < ps.world; ++r) s += mine[xchg_slot(channel, e, r) + t];
+  return s;
+}
+
 // first kernel of an update: wait until every rank has finished reading this rank's gradients of the previous
 // update, then zero them (the backward kernels accumulate with RED)
 __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int done_index, const int* epoch,
@@ -180,21 +203,13 @@ __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int do
 __global__ void peer_allreduce_small_kernel(float* __restrict__ vec, int n, PeerPtrs ps, int channel, const int* epoch) {
   const int e = *epoch;
   const int t = threadIdx.x;
-  float* mine = const_cast<float*>(ps.grads[ps.rank]) + ((channel * 2 + (e & 1)) * 16);
-  if (t < n) mine[t] = vec[t];
-  __threadfence_system();
+  float* const* xchg = (float* const*)ps.grads;   // the peer table carries the exchange blocks here
+  push_small(xchg, ps, channel, e, vec, n);
   __syncwarp();
   signal_all(ps, 2 * channel, e);
   wait_all(ps, 2 * channel, e);
   __syncwarp();
-  if (t < n) {
-    float s = 0.f;
-    for (int r = 0; r < ps.world; ++r) {
-      const volatile float* src = ps.grads[r] + ((channel * 2 + (e & 1)) * 16);
-      s += src[t];
-    }
-    vec[t] = s;
-  }
+  if (t < n) vec[t] = sum_small(xchg, ps, channel, e, t);
 }
 
 // Data-parallel CQL: the two scalar optimizer steps that need rank sums, in ONE launch (was: small all-reduce, metric
@@ -226,19 +241,14 @@ __global__ void dp_scalar_steps_kernel(float* __restrict__ vec, PeerPtrs ps, int
   const int t = threadIdx.x;
   const int n = temp ? 4 : 3;
   __shared__ float sum_s[4];
-  float* mine = const_cast<float*>(ps.grads[ps.rank]) + ((channel * 2 + (e & 1)) * 16);
-  if (t < n) mine[t] = vec[t];
-  __threadfence_system();
+  float* const* xchg = (float* const*)ps.grads;   // the peer table carries the exchange blocks here
+  push_small(xchg, ps, channel, e, vec, n);
   __syncwarp();
   signal_all(ps, 2 * channel, e);
   wait_all(ps, 2 * channel, e);
   __syncwarp();
   if (t < n) {
-    float s = 0.f;
-    for (int r = 0; r < ps.world; ++r) {
-      const volatile float* src = ps.grads[r] + ((channel * 2 + (e & 1)) * 16);
-      s += src[t];
-    }
+    const float s = sum_small(xchg, ps, channel, e, t);
     vec[t] = s;
     sum_s[t] = s;
   }
@@ -286,6 +296,21 @@ __device__ __forceinline__ float adam_one2(float p, float g, float& m, float& v,
   return __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_ss, m), denom));
 }
 
+// sum over the ranks of float4 i of the gradient arenas, in rank order (every rank computes the same sum bit for
+// bit).  All W loads are issued before the first add: W-1 of them are NVLink round trips of 2-3 us, which a
+// load-add-load-add loop would serialise.
+__device__ __forceinline__ float4 sum_ranks(const PeerPtrs& ps, long long i) {
+  float4 x[kMaxRanks];
+#pragma unroll
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (r < ps.world) x[r] = ((const float4*)ps.grads[r])[i];
+  float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < kMaxRanks; ++r)
+    if (r < ps.world) { G.x += x[r].x; G.y += x[r].y; G.z += x[r].z; G.w += x[r].w; }
+  return G;
+}
+
 // reduced-gradient buffers of every rank (two-shot exchange); gred[0] == nullptr selects the one-shot form
 struct GredPtrs { float* gred[kMaxRanks]; };
 
@@ -303,10 +328,8 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
   const int e = *epoch;
   __shared__ bool last_block;
   const bool two_shot = gp.gred[0] != nullptr;
-  const int sv_off = (sv.channel * 2 + (e & 1)) * 16;
-  if (blockIdx.x == 0 && sv.n > 0) {  // publish my partial sums before announcing that my data is ready
-    if ((int)threadIdx.x < sv.n) sv.xchg[ps.rank][sv_off + threadIdx.x] = sv.vec[threadIdx.x];
-    __threadfence_system();
+  if (blockIdx.x == 0 && sv.n > 0) {  // push my partial sums to every rank before announcing that my data is ready
+    push_small(sv.xchg, ps, sv.channel, e, sv.vec, sv.n);
     __syncthreads();
   }
   if (blockIdx.x == 0) {
@@ -315,11 +338,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
   }
   wait_all(ps, flag_index, e);
   __syncthreads();
-  if (blockIdx.x == 0 && (int)threadIdx.x < sv.n) {
-    float acc = 0.f;
-    for (int r = 0; r < ps.world; ++r) acc += ((const volatile float*)sv.xchg[r])[sv_off + threadIdx.x];
-    sv.vec[threadIdx.x] = acc;
-  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < sv.n) sv.vec[threadIdx.x] = sum_small(sv.xchg, ps, sv.channel, e, threadIdx.x);
   __shared__ float sc[2];
   if (threadIdx.x == 0) {  // double pow/sqrt once per block
     const int t = *a.step;
@@ -338,11 +357,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     const long long lo = chunk * ps.rank, hi = min(n4, lo + chunk);
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
          i += (long long)gridDim.x * blockDim.x) {
-      float4 G = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < ps.world; ++r) {
-        float4 x = ((const float4*)ps.grads[r])[i];
-        G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
-      }
+      const float4 G = sum_ranks(ps, i);
       for (int r = 0; r < ps.world; ++r) ((float4*)gp.gred[r])[i] = G;
     }
     __threadfence_system();
@@ -369,10 +384,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     if (two_shot) {
       G = __ldcg((const float4*)gp.gred[ps.rank] + i);   // written over NVLink by the slice owners: bypass L1
     } else {
-      for (int r = 0; r < ps.world; ++r) {  // fixed rank order: every rank computes the same sum bit for bit
-        float4 x = ((const float4*)ps.grads[r])[i];
-        G.x += x.x; G.y += x.y; G.z += x.z; G.w += x.w;
-      }
+      G = sum_ranks(ps, i);
     }
     float4 P = ((float4*)a.p)[i], M = ((float4*)a.m)[i], V = ((float4*)a.v)[i];
     P.x = adam_one2(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);

@@ -74,11 +74,20 @@ class DeviceReplay:
         return self.n_transitions
 
     def scaler_tensors(self, scaler):
-        key = id(scaler)
-        if key not in self._scaler_cache:
-            sub, div, eps = scaler.affine_f32()   # StandardScaler: (mean, std, eps); MinMaxScaler: (min, max - min, 0)
-            self._scaler_cache[key] = (torch.tensor(sub, device=self.device), torch.tensor(div, device=self.device), eps)
-        return self._scaler_cache[key]
+        return scaler_device_tensors(self._scaler_cache, scaler, self.device)
+
+
+def scaler_device_tensors(cache: dict, scaler, device):
+    """(subtrahend, divisor, eps) of `(x - s) / (d + eps)` as device tensors, cached per scaler OBJECT (the entry holds
+    a reference, so an id cannot be recycled while it is cached).  StandardScaler: (mean, std, eps); MinMaxScaler:
+    (min, max - min, 0).  Shared by the offline replay and the online ReplayBuffer."""
+    key = id(scaler)
+    hit = cache.get(key)
+    if hit is None or hit[0] is not scaler:
+        sub, div, eps = scaler.affine_f32()
+        hit = (scaler, torch.tensor(sub, device=device), torch.tensor(div, device=device), eps)
+        cache[key] = hit
+    return hit[1], hit[2], hit[3]
 
 
 class Transition:

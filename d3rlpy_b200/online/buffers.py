@@ -255,10 +255,6 @@ class ReplayBuffer:
         self.flush()
 
     def _scaler_tensors(self, scaler):
-        v = self._view
-        key = id(scaler)
-        if key not in v._scaler_cache:
-            mean = torch.tensor(np.asarray(scaler._mean, np.float32).reshape(-1), device=self._device)
-            std = torch.tensor(np.asarray(scaler._std, np.float32).reshape(-1), device=self._device)
-            v._scaler_cache[key] = (mean, std, float(scaler._eps))
-        return v._scaler_cache[key]
+        from ..dataset import scaler_device_tensors
+
+        return scaler_device_tensors(self._view._scaler_cache, scaler, self._device)

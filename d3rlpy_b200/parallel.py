@@ -111,7 +111,7 @@ class PeerExchange:
 
     N_FLAGS = 32          # flags per rank: {ready, done} pairs; channels 0-3 small vectors, 4.. gradient arenas
     MAX_RANKS = 8         # every flag has one int32 slot per WRITER rank (pushed flags, csrc/comm.cu)
-    XCHG_FLOATS = 4 * 2 * 16
+    XCHG_FLOATS = 4 * 2 * 8 * 16   # [channel][epoch parity][WRITER rank][16 floats]: partial sums are pushed too
 
     def __init__(self, world_size: int, rank: int, device):
         import torch.distributed as dist
