@@ -444,7 +444,7 @@ class CQLImpl(DDPGBaseImpl):
             # metrics from the all-reduced sums, after everything that is on the critical path
             L.cql_finalize(self.sums_ptr(S_CRITIC), la.ptr("p"), inv_b, E, self._conservative_weight,
                            self._alpha_threshold, 0, 1 if N > 0 else 0, self.metric_ptr(M_CRITIC), None, st)
-            L.copy_d2d(self.metric_ptr(M_ACTOR), self.sums_ptr(S_ACTOR), 4, st)
+            # the actor metric is the all-reduced sum itself: update_fused_async reads it from the sums slot
 
     # ---- NVLink peer-memory exchange (csrc/comm.cu): all-reduce fused into the Adam pass, no NCCL in the update
     def _peer_setup(self):
@@ -507,7 +507,7 @@ class CQLImpl(DDPGBaseImpl):
             names += [(M_TEMP_LOSS, "temp_loss"), (M_TEMP, "temp")]
         if do_alpha:
             names += [(M_ALPHA_LOSS, "alpha_loss"), (M_ALPHA, "alpha")]
-        names += [(M_CRITIC, "critic_loss"), (M_ACTOR, "actor_loss")]
+        names += [(M_CRITIC, "critic_loss"), ((32 + S_ACTOR) if fused and self.world_size > 1 else M_ACTOR, "actor_loss")]
         return names
 
     # ------------------------------------------------------------------ reference hooks (eager, one sync each)

@@ -151,6 +151,26 @@ __device__ __forceinline__ void wait_flag_ge(const int* p, int v) {
   }
 }
 
+// profiling hook (d3b_peer_set_trace): per traced kernel k and update e, slot (k * 64 + e % 64) * 4 of the buffer gets
+// {globaltimer at entry, clock64 cycles spent in the rendezvous wait, clock64 cycles entry -> end of block 0, epoch}
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct Trace {
+  long long* slot; long long c0, c1; unsigned long long t0;
+  __device__ __forceinline__ void begin(int kernel, int e) {
+    slot = (g_trace && blockIdx.x == 0 && threadIdx.x == 0) ? g_trace + ((kernel * 64 + (e & 63)) * 4) : nullptr;
+    if (slot) { t0 = gtime(); c0 = clock64(); c1 = c0; slot[3] = e; }
+  }
+  __device__ __forceinline__ void waited(long long since) { if (slot) c1 += clock64() - since; }
+  __device__ __forceinline__ void end() {
+    if (slot) { slot[0] = (long long)t0; slot[1] = c1 - c0; slot[2] = clock64() - c0; }
+  }
+};
+
 // flag f of writer rank w lives at flags[any rank] + f * kMaxRanks + w
 __device__ __forceinline__ void signal_all(const PeerPtrs& ps, int f, int e) {   // threads 0..world-1 of one block
   if ((int)threadIdx.x < ps.world) st_release_sys(ps.flags[threadIdx.x] + f * kMaxRanks + ps.rank, e);
@@ -187,12 +207,19 @@ __device__ __forceinline__ float sum_small(float* const* xchg, const PeerPtrs& p
 __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int done_index, const int* epoch,
                                                              float* __restrict__ grads, long long n, int done_index2,
                                                              float* __restrict__ grads2, long long n2) {
+  d3b::pdl_trigger();
+  d3b::pdl_wait();
+  Trace tr;
+  tr.begin(0, *epoch);
   {
     const int prev = *epoch - 1;
+    const long long w0 = clock64();
     wait_all(ps, done_index, prev);
     if (grads2) wait_all(ps, done_index2, prev);
+    tr.waited(w0);
   }
   __syncthreads();
+  tr.end();
   const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = i0; i < (n >> 2); i += stride) ((float4*)grads)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (grads2)
@@ -201,6 +228,8 @@ __global__ void __launch_bounds__(256) peer_wait_zero_kernel(PeerPtrs ps, int do
 
 // sum of a short vector over the ranks through the exchange block: slot = epoch & 1
 __global__ void peer_allreduce_small_kernel(float* __restrict__ vec, int n, PeerPtrs ps, int channel, const int* epoch) {
+  d3b::pdl_trigger();
+  d3b::pdl_wait();
   const int e = *epoch;
   const int t = threadIdx.x;
   float* const* xchg = (float* const*)ps.grads;   // the peer table carries the exchange blocks here
@@ -237,15 +266,22 @@ __global__ void dp_scalar_steps_kernel(float* __restrict__ vec, PeerPtrs ps, int
                                        float* metric_temp, float* alpha, const int* step_alpha, double lr_alpha,
                                        float inv_eb, float cw, float threshold, float* metric_alpha_loss,
                                        float* metric_alpha) {
+  d3b::pdl_trigger();
+  d3b::pdl_wait();
   const int e = *epoch;
   const int t = threadIdx.x;
   const int n = temp ? 4 : 3;
   __shared__ float sum_s[4];
   float* const* xchg = (float* const*)ps.grads;   // the peer table carries the exchange blocks here
+  Trace tr;
+  tr.begin(1, e);
   push_small(xchg, ps, channel, e, vec, n);
   __syncwarp();
   signal_all(ps, 2 * channel, e);
+  const long long w0 = clock64();
   wait_all(ps, 2 * channel, e);
+  tr.waited(w0);
+  tr.end();
   __syncwarp();
   if (t < n) {
     const float s = sum_small(xchg, ps, channel, e, t);
@@ -325,9 +361,13 @@ struct GredPtrs { float* gred[kMaxRanks]; };
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 segs, PeerPtrs ps, int flag_index,
                                                              const int* epoch, unsigned* block_counter, SmallVec sv,
                                                              GredPtrs gp, unsigned* block_counter2) {
+  d3b::pdl_trigger();
+  d3b::pdl_wait();
   const int e = *epoch;
   __shared__ bool last_block;
   const bool two_shot = gp.gred[0] != nullptr;
+  Trace tr;
+  tr.begin(flag_index <= 8 ? 2 : 3, e);
   if (blockIdx.x == 0 && sv.n > 0) {  // push my partial sums to every rank before announcing that my data is ready
     push_small(sv.xchg, ps, sv.channel, e, sv.vec, sv.n);
     __syncthreads();
@@ -336,7 +376,11 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
     __threadfence_system();
     signal_all(ps, flag_index, e);  // my gradients of update e are complete
   }
-  wait_all(ps, flag_index, e);
+  {
+    const long long w0 = clock64();
+    wait_all(ps, flag_index, e);
+    tr.waited(w0);
+  }
   __syncthreads();
   if (blockIdx.x == 0 && (int)threadIdx.x < sv.n) sv.vec[threadIdx.x] = sum_small(sv.xchg, ps, sv.channel, e, threadIdx.x);
   __shared__ float sc[2];
@@ -376,7 +420,9 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
       signal_all(ps, flag_index + 2, e);   // reduced: my slice has been pushed to every rank
     }
     // ---- phase 2 needs every rank's slice
+    const long long w0 = clock64();
     wait_all(ps, flag_index + 2, e);
+    tr.waited(w0);
     __syncthreads();
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -429,6 +475,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(AdamArgs a, Segs2 s
       }
     }
   }
+  tr.end();
   // completion: the last block of this rank announces that it no longer needs anybody's gradients of update e
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -456,6 +503,12 @@ int fill_peers(PeerPtrs& ps, const void* const* grads_host, const void* const* f
 }
 
 }  // namespace
+
+extern "C" int d3b_peer_set_trace(void* device_buffer) {
+  long long* p = (long long*)device_buffer;
+  D3B_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+  return D3B_OK;
+}
 
 extern "C" int d3b_peer_export(const void* ptr, void* handle_out_64, int64_t* offset_out) {
   D3B_REQUIRE(ptr && handle_out_64 && offset_out, "peer_export: null pointer");
@@ -512,7 +565,7 @@ extern "C" int d3b_peer_wait_zero(const void* const* flags_host, int world, int 
   long long blocks = ((n > n2 || !grads2 ? n : n2) / 4 + 255) / 256;
   if (blocks > 2 * d3b::kNumSM) blocks = 2 * d3b::kNumSM;
   if (blocks < 1) blocks = 1;
-  peer_wait_zero_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ps, done_index, epoch, grads, (long long)n,
+  d3b::launch_pdl(peer_wait_zero_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, ps, done_index, epoch, grads, (long long)n,
                                                                            done_index2, grads2, (long long)n2);
   return d3b::check_launch("peer_wait_zero");
 }
@@ -528,7 +581,7 @@ extern "C" int d3b_dp_scalar_steps(float* vec, const void* const* xchg_host, con
   D3B_REQUIRE(!temp_scalar || (step_temp && metric_temp_loss && metric_temp), "dp_scalar_steps: null temperature pointers");
   PeerPtrs ps{};
   D3B_REQUIRE(fill_peers(ps, xchg_host, flags_host, world, rank) == 0, "dp_scalar_steps: bad peer table");
-  dp_scalar_steps_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vec, ps, channel, epoch, temp_scalar, step_temp, lr_temp,
+  d3b::launch_pdl(dp_scalar_steps_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, vec, ps, channel, epoch, temp_scalar, step_temp, lr_temp,
                                                               metric_temp_loss, metric_temp, alpha_scalar, step_alpha,
                                                               lr_alpha, inv_members_batch, conservative_weight,
                                                               alpha_threshold, metric_alpha_loss, metric_alpha);
@@ -540,7 +593,7 @@ extern "C" int d3b_peer_allreduce_small(float* vec, int n, const void* const* xc
   D3B_REQUIRE(vec && n >= 1 && n <= 16 && channel >= 0 && channel < 4 && epoch, "peer_allreduce_small: bad arguments");
   PeerPtrs ps{};
   D3B_REQUIRE(fill_peers(ps, xchg_host, flags_host, world, rank) == 0, "peer_allreduce_small: bad peer table");
-  peer_allreduce_small_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(vec, n, ps, channel, epoch);
+  d3b::launch_pdl(peer_allreduce_small_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, vec, n, ps, channel, epoch);
   return d3b::check_launch("peer_allreduce_small");
 }
 
@@ -598,7 +651,7 @@ extern "C" int d3b_adam_step_peer(float* params, float* exp_avg, float* exp_avg_
   }
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > (long long)per_sm * d3b::kNumSM) blocks = (long long)per_sm * d3b::kNumSM;
-  adam_allreduce_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a, segs, ps, flag_index, epoch,
+  d3b::launch_pdl(adam_allreduce_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, a, segs, ps, flag_index, epoch,
                                                                            (unsigned*)block_counter, sv, gp,
                                                                            (unsigned*)block_counter2);
   return d3b::check_launch("adam_step_peer");

@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(256) critic_loss_kernel(
     const float* __restrict__ logp_tp1, int N, int A, const float* __restrict__ log_alpha, float cw,
     float* __restrict__ dq, long long sDq, float* __restrict__ sums, float* __restrict__ y_out, int B, int E,
     float inv_b, float inv_eb, int td_enabled) {
+  pdl_trigger();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   float td = 0.f, lse_v = 0.f, data_v = 0.f;
   if (idx < B * E) {
@@ -182,6 +184,8 @@ __global__ void __launch_bounds__(256) critic_loss_kernel(
 __global__ void cql_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ log_alpha, float inv_b,
                                     float inv_eb, float cw, float threshold, int mode, int conservative,
                                     float* __restrict__ metric, float* __restrict__ grad_log_alpha) {
+  pdl_trigger();
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   float td = sums[0] * inv_b;
   if (!conservative) {
@@ -227,6 +231,8 @@ __global__ void __launch_bounds__(256) sac_actor_loss_kernel(const float* __rest
                                                              const float* __restrict__ log_temp,
                                                              float* __restrict__ dq, long long sDq,
                                                              float* __restrict__ loss_sum, int B, int E, float inv_b) {
+  pdl_trigger();
+  pdl_wait();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   float l = 0.f;
   if (b < B) {
@@ -274,6 +280,8 @@ __global__ void __launch_bounds__(1024) sac_temp_loss_kernel(const float* __rest
                                                              const float* __restrict__ log_temp, int B, int A,
                                                              float inv_b, float* __restrict__ metric,
                                                              float* __restrict__ grad, int accumulate) {
+  pdl_trigger();
+  pdl_wait();
   float s = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += __ldg(logp + b) - (float)A;
   s = block_sum(s);
@@ -486,7 +494,7 @@ extern "C" int d3b_critic_loss(const float* q, int64_t stride_q, const float* q_
   D3B_REQUIRE(n_action_samples == 0 || (logp_t && logp_tp1 && log_alpha),
               "critic_loss: conservative term needs log-probs and log_alpha");
   int total = batch * members;
-  critic_loss_kernel<<<ceil_div(total, 256), 256, 0, ST>>>(
+  launch_pdl(critic_loss_kernel, dim3(ceil_div(total, 256)), dim3(256), 0, ST, 
       q, stride_q, q_targ, stride_qt, targ_members, q_tpn, rewards, terminals, n_steps, gamma, logp_t, logp_tp1,
       n_action_samples, act_dim, log_alpha, conservative_weight, dq, stride_dq, sums, y_out, batch, members, inv_batch,
       inv_batch / (float)members, td_enabled);
@@ -497,7 +505,7 @@ extern "C" int d3b_cql_finalize(const float* sums, const float* log_alpha, float
                                 float conservative_weight, float alpha_threshold, int mode, int conservative,
                                 float* metric, float* grad_log_alpha, void* stream) {
   D3B_REQUIRE(sums && metric && (!conservative || log_alpha), "cql_finalize: null pointer");
-  cql_finalize_kernel<<<1, 32, 0, ST>>>(sums, log_alpha, inv_batch, inv_batch / (float)members, conservative_weight,
+  launch_pdl(cql_finalize_kernel, dim3(1), dim3(32), 0, ST, sums, log_alpha, inv_batch, inv_batch / (float)members, conservative_weight,
                                         alpha_threshold, mode, conservative, metric, grad_log_alpha);
   return check_launch("cql_finalize");
 }
@@ -515,7 +523,7 @@ extern "C" int d3b_sac_actor_loss(const float* q, int64_t stride_q, const float*
   D3B_REQUIRE(batch >= 0 && members >= 1, "sac_actor_loss: bad sizes");
   if (batch == 0) return D3B_OK;
   D3B_REQUIRE(q && logp && log_temp && dq && loss_sum, "sac_actor_loss: null pointer");
-  sac_actor_loss_kernel<<<ceil_div(batch, 256), 256, 0, ST>>>(q, stride_q, logp, log_temp, dq, stride_dq, loss_sum,
+  launch_pdl(sac_actor_loss_kernel, dim3(ceil_div(batch, 256)), dim3(256), 0, ST, q, stride_q, logp, log_temp, dq, stride_dq, loss_sum,
                                                               batch, members, inv_batch);
   return check_launch("sac_actor_loss");
 }
@@ -535,7 +543,7 @@ extern "C" int d3b_sac_actor_backward(const float* head, int64_t ld_head, const 
 extern "C" int d3b_sac_temp_loss(const float* logp, const float* log_temp, int batch, int act_dim, float inv_batch,
                                  float* metric, float* grad, int accumulate, void* stream) {
   D3B_REQUIRE(logp && log_temp && metric && grad && batch >= 0, "sac_temp_loss: bad arguments");
-  sac_temp_loss_kernel<<<1, 1024, 0, ST>>>(logp, log_temp, batch, act_dim, inv_batch, metric, grad, accumulate);
+  launch_pdl(sac_temp_loss_kernel, dim3(1), dim3(1024), 0, ST, logp, log_temp, batch, act_dim, inv_batch, metric, grad, accumulate);
   return check_launch("sac_temp_loss");
 }
 

@@ -481,6 +481,10 @@ int d3b_comm_destroy(void* comm);
  * itself (fixed rank order => bit-identical sums on all ranks) and applies Adam + Polyak + shadow refresh — no
  * NCCL call on the update path.  flags: per-rank int32 block, {ready, done} epoch pairs; epoch: device counter of
  * the update.  peer_export/import map a device allocation into the other ranks of the box. */
+/* profiling hook: device buffer of 4 * 64 * 4 int64 receiving, per traced peer kernel (0 wait-and-zero, 1 scalar
+ * steps, 2 / 3 critic / actor Adam exchange) and update, {globaltimer at entry, cycles spent waiting for peers, cycles
+ * of block 0, epoch}; NULL switches it off */
+int d3b_peer_set_trace(void* device_buffer);
 int d3b_peer_export(const void* ptr, void* handle_out_64, int64_t* offset_out);
 int d3b_peer_import(const void* handle_64, int64_t offset, void** ptr_out);
 int d3b_peer_wait_zero(const void* const* flags_host, int world, int rank, int done_index, const int* epoch,
