@@ -32,6 +32,9 @@ struct Params {
   int lg_bn;              // log2(BN)
   int stages;             // operand ring depth (3 when a mask tile needs the space, else 4)
   int splits, kb_per_split;
+  int csplit;             // > 1: the `splits` CTAs of a tile are a thread-block cluster; partial tiles are reduced through
+                          // distributed shared memory and the full epilogue runs on the sum (latency configuration)
+  int part_off;           // byte offset of the fp32 partial tile inside the operand stages (csplit > 1)
   int a_shared, b_shared; // operand shared by all members -> member coordinate 0
   int mn_major;           // 1: both operands are MN-major in memory (A [K][M], B [K][N]) — the weight-gradient form
   // epilogue
@@ -126,6 +129,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// thread-block cluster helpers (cluster split-K, see gemm_tf32x3.cu for the measurements behind the relaxed arrive)
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile(
+      "fence.acq_rel.cta;\n\t"
+      "barrier.cluster.arrive.relaxed.aligned;\n\t"
+      "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  float4 v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(ra));
+  return v;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -206,6 +231,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
       }
       if (dbg) dbg[2] = clock64();  // all TMA issued
     }
+    if (p.csplit > 1) { __syncwarp(); cluster_sync(); }   // partial tiles staged (epilogue warps arrive below)
   } else if (warp == 9) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
@@ -239,6 +265,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
       mma_commit(tmem_full);    // accumulator complete
       if (dbg) dbg[4] = clock64();  // all MMAs issued
     }
+    if (p.csplit > 1) { __syncwarp(); cluster_sync(); }
   } else {
     // ---- epilogue (warps 0-7, 256 threads).  Phase 0 (overlaps the mainloop): stage bias and the ReLU
     // mask tile in shared memory with coalesced loads.  Phase 1: thread owns tile row 32*warp+lane, reads
@@ -246,6 +273,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
     // bf16 or fp32) into the now-free operand stages.  Phase 2: fully coalesced 16-byte global stores / REDs.
     const int t = threadIdx.x;  // 0..EPI_THREADS-1
     const int BN = p.BN;
+    const int S = p.csplit > 1 ? p.csplit : 1;
+    const int r_lo = S > 1 ? (int)cluster_ctarank() * (BM / S) : 0;   // tile rows this CTA finishes and stores
+    const int r_hi = S > 1 ? r_lo + BM / S : BM;
     const int ldc = BN + 8, ldts = BM + 8, ldfs = BN + 4;
     float* bias_s = (float*)(smem + p.stages * (A_STAGE_BYTES + b_stage_bytes) + 256);
     __nv_bfloat16* mask_s = (__nv_bfloat16*)((uint8_t*)bias_s + 1024);
@@ -291,18 +321,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    mbar_wait(tmem_full, 0);
+    if (kb_end > kb_begin) mbar_wait(tmem_full, 0);
     if (dbg && threadIdx.x == 0) dbg[5] = clock64();  // accumulator ready
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // thread owns tile row 32*(warp%4)+lane and the column half warp/4 (BN=32: a single half)
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
     const int half_cols = BN >= 64 ? (BN >> 1) : BN;
     const int c_begin = (warp >> 2) * half_cols;
     const int c_end = (BN >= 64 || warp < 4) ? c_begin + half_cols : c_begin;
-    for (int c = c_begin; c < c_end; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+    // 32 accumulator columns [c, c + 32) of tile row `row`: bias / ReLU / mask, then into the staging tiles
+    auto finish = [&](int row, int c, const uint32_t (&v)[32]) {
       float f[32];
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
@@ -343,6 +371,56 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
           for (int j = 0; j < 32; ++j) t_s[(c + j) * ldts + row] = __float2bfloat16_rn(f[j]);
         }
       }
+    };
+    if (S == 1) {
+      const int row = quarter * 32 + lane;
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+        finish(row, c, v);
+      }
+    } else {
+      // cluster split-K: stage the raw partial tile, meet the other CTAs of the tile, then CTA q finishes rows
+      // [q BM/S, (q+1) BM/S) on the sum of the S partial tiles (rank order: deterministic)
+      float* part_s = (float*)(smem + p.part_off);
+      {
+        const int row = quarter * 32 + lane;
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t v[32];
+          if (kb_end > kb_begin) {
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<uint4*>(part_s + row * ldfs + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      __syncwarp();
+      cluster_sync();
+      const int slab = BM / S, nchunk = BN >> 5;
+      if (t < slab * nchunk) {
+        const int row = r_lo + (t % slab), c = (t / slab) << 5;
+        const uint32_t la = smem_u32(part_s + row * ldfs + c);
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        for (int r = 0; r < S; ++r) {
+          float4 x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = ld_dsmem_f4(la + 16 * j, (uint32_t)r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[4 * j] += x[j].x; acc[4 * j + 1] += x[j].y; acc[4 * j + 2] += x[j].z; acc[4 * j + 3] += x[j].w;
+          }
+        }
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
+        finish(row, c, v);
+      }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     // ---- phase 2: coalesced global traffic (shift/mask indexing, 4 vectors in flight per thread)
@@ -362,7 +440,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
         for (int u = 0; u < 4; ++u) {
           int v = v0 + u * EPI_THREADS;
           int m = m0 + (v >> lg4), n = n0 + ((v & m4) << 2);
-          if (v >= total || m >= p.M || n >= p.N) continue;
+          if (v >= total || m >= p.M || n >= p.N || (v >> lg4) < r_lo || (v >> lg4) >= r_hi) continue;
           float* dst = o + (long long)m * p.ldf + n;
           if (vec_ok && n + 3 < p.N) {
             if (p.atomic)
@@ -399,7 +477,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
           for (int u = 0; u < 4; ++u) {
             int v = v0 + u * EPI_THREADS;
             int m = m0 + (v >> lg_nvec), n = n0 + ((v & nvec_mask) << 3);
-            if (v >= total || m >= p.M || n >= p.N) continue;
+            if (v >= total || m >= p.M || n >= p.N || (v >> lg_nvec) < r_lo || (v >> lg_nvec) >= r_hi) continue;
             __nv_bfloat16* dst = o + (long long)m * p.ldo + n;
             if (vec_ok && n + 7 < p.N) {
               *reinterpret_cast<uint4*>(dst) = val[u];
@@ -427,7 +505,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
           for (int u = 0; u < 4; ++u) {
             int v = v0 + u * EPI_THREADS;
             int n = n0 + (v >> 4), m = m0 + ((v & 15) << 3);
-            if (v >= total || n >= p.N || m >= p.M) continue;
+            if (v >= total || n >= p.N || m >= p.M || ((v & 15) << 3) < r_lo || ((v & 15) << 3) >= r_hi) continue;
             __nv_bfloat16* dst = o + (long long)n * p.ldt + m;
             if (vec_ok && m + 7 < p.M) {
               *reinterpret_cast<uint4*>(dst) = val[u];
@@ -443,6 +521,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap* tmA_p, const CUtens
     }
   }
   if (dbg && threadIdx.x == 0) dbg[6] = clock64();  // epilogue (warp 0) done
+  if (p.csplit > 1) { __syncwarp(); cluster_sync(); }   // peers may still be reading this CTA's partial tile
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (dbg && threadIdx.x == 0) dbg[7] = clock64();
@@ -539,6 +618,12 @@ using namespace d3b;
 using namespace d3b::umma;
 
 static long long* g_umma_dbg = nullptr;
+static bool g_umma_cluster = true;
+// profiling hook: 0 switches the cluster split-K latency configuration of d3b_umma_gemm off
+extern "C" int d3b_umma_set_cluster(int enabled) {
+  g_umma_cluster = enabled != 0;
+  return D3B_OK;
+}
 // test/profiling hook: device buffer receiving 8 clock64() phase stamps per CTA of the next launches
 extern "C" int d3b_umma_set_debug(void* device_buffer) {
   g_umma_dbg = (long long*)device_buffer;
@@ -565,13 +650,33 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
   // Few tiles: halve the tile so that twice as many CTAs exist and two of them fit on one SM
   // (~100 KB shared memory, 128 TMEM columns each) — one CTA's epilogue overlaps the other's mainloop.
   if (BN == 256 && (long long)ceil_div(m, BM) * ceil_div(n, 256) * members * splits < 2LL * kNumSM) BN = 128;
+  int num_kb = ceil_div(k, BK);
+  // Long reductions over few tiles (the fc layer of the pixel encoder: 32 x 512 x 3136): the launch is cut into
+  // 128 x 64 tiles and each tile's reduction is split over a thread-block cluster of up to 8 CTAs (>= 6 K blocks of
+  // 64 each); see gemm_body.  Measured (profiles/r2/umma_small.py): 21.3 -> 13.3 us for that layer; for K <= 752 the
+  // TMA pipeline already streams the reduction in 5-9 us and the cluster epilogue costs more than it saves, so
+  // shorter reductions keep the single-CTA tiles.
+  int csplit = 1;
+  if (splits == 1 && !atomic && g_umma_cluster) {
+    long long tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
+    if (tiles * 2 <= kNumSM && num_kb >= 16) {
+      if (BN > 64) BN = 64;
+      tiles = (long long)ceil_div(m, BM) * ceil_div(n, BN) * members;
+      while (csplit * 2 <= 8 && tiles * csplit * 2 <= kNumSM && num_kb >= csplit * 2 * 6) csplit *= 2;
+    }
+  }
   Params p{};
   p.M = m; p.N = n; p.K = k; p.BN = BN;
   p.lg_bn = BN == 256 ? 8 : (BN == 128 ? 7 : (BN == 64 ? 6 : 5));
-  int num_kb = ceil_div(k, BK);
-  if (splits > num_kb) splits = num_kb;
-  p.kb_per_split = ceil_div(num_kb, splits);
-  p.splits = ceil_div(num_kb, p.kb_per_split);
+  if (csplit > 1) {
+    p.splits = csplit;
+    p.kb_per_split = ceil_div(num_kb, csplit);
+  } else {
+    if (splits > num_kb) splits = num_kb;
+    p.kb_per_split = ceil_div(num_kb, splits);
+    p.splits = ceil_div(num_kb, p.kb_per_split);
+  }
+  p.csplit = csplit;
   p.a_shared = stride_a == 0; p.b_shared = stride_b == 0;
   p.bias = bias; p.sBias = stride_bias; p.relu = relu;
   p.mask = (const __nv_bfloat16*)mask; p.ldmask = ld_mask; p.sMask = stride_mask;
@@ -589,6 +694,10 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
   size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)BN * BK * 2;
   size_t need_epi = out_f32 ? (size_t)BM * (BN + 4) * 4
                             : (size_t)BM * (BN + 8) * 2 + (out_t_bf16 ? (size_t)BN * (BM + 8) * 2 : 0);
+  if (csplit > 1) {  // the fp32 partial tile sits behind the output staging tiles
+    p.part_off = (int)((need_epi + 127) / 128 * 128);
+    need_epi = (size_t)p.part_off + (size_t)BM * (BN + 4) * 4;
+  }
   size_t tail = 256 + 1024 + (mask ? (size_t)BM * (BN + 8) * 2 : 0);
   int stages = BN == 256 ? MAX_STAGES : 3;
   if (mask && !out_t_bf16 && BN <= 128) stages = 2;  // keeps two CTAs per SM with the mask tile resident
@@ -604,7 +713,7 @@ extern "C" int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const
     attr_set = true;
   }
   dim3 grid(ceil_div(m, BM), ceil_div(n, BN), members * p.splits);
-  launch_pdl(umma_gemm_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, tmA, tmB, p);
+  launch_pdl_cluster(umma_gemm_kernel, grid, dim3(NTHREADS), smem, (cudaStream_t)stream, (unsigned)csplit, tmA, tmB, p);
   return check_launch("umma_gemm");
 }
 

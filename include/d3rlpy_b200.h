@@ -131,6 +131,10 @@ int d3b_umma_gemm(const void* a, int64_t lda, int64_t stride_a, const void* b, i
                   const void* mask, int64_t ld_mask, int64_t stride_mask, void* out_bf16, int64_t ldo,
                   int64_t stride_o, void* out_t_bf16, int64_t ldt, int64_t stride_t, float* out_f32, int64_t ldf,
                   int64_t stride_f, int atomic, void* stream);
+/* profiling hook: 0 switches off the cluster split-K latency configuration umma_gemm picks for launches far below
+ * one wave (128 x 64 tiles, the reduction split over a thread-block cluster, partial tiles summed through distributed
+ * shared memory) */
+int d3b_umma_set_cluster(int enabled);
 /* weight-gradient form c[e] (m x n) (+)= a[e]^T b[e], a [k][m] and b [k][n] row-major bf16 (MN-major UMMA
  * operands loaded by TMA straight from the saved dZ_l / H_{l-1}; no transposed copies) */
 int d3b_umma_gemm_tn(const void* a, int64_t lda, int64_t stride_a, const void* b, int64_t ldb, int64_t stride_b, int m,

@@ -30,7 +30,9 @@ def _gemm(L, a, b, m, n, k, E, *, lda, sa, ldb, sb, splits=1, bias=None, relu=0,
     torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("M,N,K,E", [(300, 256, 256, 2), (128, 64, 64, 1), (7936, 256, 256, 2), (1000, 400, 320, 1)])
+@pytest.mark.parametrize("M,N,K,E", [(300, 256, 256, 2), (128, 64, 64, 1), (7936, 256, 256, 2), (1000, 400, 320, 1),
+                                     # long reductions over few tiles: 128 x 64 tiles, cluster split-K (pixel fc layer)
+                                     (256, 750, 752, 1), (32, 512, 3136, 1), (200, 300, 2048, 2), (130, 70, 1032, 3)])
 def test_umma_forward_bias_relu_bf16_and_transposed(M, N, K, E):
     from d3rlpy_b200._lib import lib
 
@@ -50,6 +52,41 @@ def test_umma_forward_bias_relu_bf16_and_transposed(M, N, K, E):
     assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
     assert torch.equal(out, _bf(out_f))
     assert torch.equal(out_t[:, :, :M], out.transpose(1, 2))
+
+
+@pytest.mark.parametrize("M,N,K,E", [(256, 400, 1200, 2), (200, 750, 3000, 1), (130, 70, 1030, 3)])
+def test_umma_cluster_split_k_with_mask_matches_single_cta(M, N, K, E):
+    """dgrad-style launch (ReLU mask, bf16 + fp32 outputs) in the cluster split-K configuration against the same launch
+    with the configuration switched off: same values up to the fp32 summation order."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M * 3 + K)
+    ldk, ldn = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    a = torch.full((E, M, ldk), 9.0, dtype=torch.bfloat16)
+    a[:, :, :K] = _bf(torch.randn(E, M, K, generator=g))
+    b = torch.full((E, N, ldk), -9.0, dtype=torch.bfloat16)
+    b[:, :, :K] = _bf(torch.randn(E, N, K, generator=g) / math.sqrt(K))
+    a, b = a.to(dev), b.to(dev)
+    mask = _bf(torch.randn(E, M, ldn, generator=g)).to(dev)
+    outs = {}
+    for cluster in (1, 0):
+        L.umma_set_cluster(cluster)
+        try:
+            out = torch.full((E, M, ldn), 3.0, dtype=torch.bfloat16, device=dev)
+            out_f = torch.zeros(E, M, N, device=dev)
+            _gemm(L, a, b, M, N, K, E, lda=ldk, sa=M * ldk, ldb=ldk, sb=N * ldk, mask=mask, out_bf16=out)
+            _gemm(L, a, b, M, N, K, E, lda=ldk, sa=M * ldk, ldb=ldk, sb=N * ldk, mask=mask, out_f32=out_f)
+        finally:
+            L.umma_set_cluster(1)
+        outs[cluster] = (out, out_f)
+        assert bool((out[:, :, N:] == 3.0).all()), "padding columns written"
+        assert torch.equal(out[:, :, :N], _bf(out_f))
+    ref = torch.einsum("emk,enk->emn", a[:, :, :K].float(), b[:, :, :K].float()) * (mask[:, :, :N].float() > 0)
+    scale = max(1.0, ref.abs().max().item())
+    for cluster in (1, 0):
+        assert (outs[cluster][1] - ref).abs().max().item() <= 1e-4 * scale
+    assert (outs[1][1] - outs[0][1]).abs().max().item() <= 2e-5 * scale
 
 
 def test_umma_small_k_zero_fill_shared_a_and_mask():
