@@ -20,6 +20,7 @@ def _adam_weight_decay(factory, default: float) -> float:
 
 class AWAC(AlgoBase):
     IMPL = AWACImpl
+    WEIGHT_DECAY_OPTIMS = ("actor_optim_factory",)   # params.json carries the actor's weight decay inside its AdamFactory
 
     def __init__(self, *, actor_learning_rate: float = 3e-4, critic_learning_rate: float = 3e-4,
                  actor_optim_factory=None, critic_optim_factory=None, actor_encoder_factory="default",

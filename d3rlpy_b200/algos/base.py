@@ -45,6 +45,16 @@ class VectorEncoderFactory:
 _ADAM_DEFAULTS = {"optim_cls": "Adam", "betas": [0.9, 0.999], "eps": 1e-08, "weight_decay": 0, "amsgrad": False}
 
 
+class _AdamWeightDecay:
+    """Stand-in for the reference's AdamFactory(weight_decay=...) when an algorithm is rebuilt from params.json."""
+
+    def __init__(self, weight_decay: float):
+        self.weight_decay = weight_decay
+
+    def get_params(self, deep: bool = False):
+        return dict(_ADAM_DEFAULTS, weight_decay=self.weight_decay)
+
+
 def _q_func_to_json(factory) -> Dict[str, Any]:
     """QFunctionFactory -> {"type", "params"} (models/q_functions.py:60-77,117-121,156-161)."""
     if factory is None or factory == "mean" or getattr(factory, "TYPE", None) == "mean":
@@ -259,7 +269,7 @@ class AlgoBase:
     def get_params(self, deep: bool = True) -> Dict[str, Any]:
         """Constructor arguments by name (LearnableBase.get_params, base.py:266-319): every `_x` attribute that is a
         hyper-parameter, the factories as objects."""
-        skip = {"_impl", "_grad_step", "_kwargs", "_factories", "_use_gpu", "_n_quantiles"}
+        skip = {"_impl", "_grad_step", "_kwargs", "_factories", "_use_gpu", "_n_quantiles", "_actor_weight_decay"}
         out: Dict[str, Any] = {}
         for key, value in vars(self).items():
             if key in skip or not key.startswith("_") or key.endswith("_hidden"):
@@ -290,7 +300,10 @@ class AlgoBase:
             else:
                 doc[key] = value
             if key.endswith("learning_rate"):
-                doc[key[:-len("learning_rate")] + "optim_factory"] = dict(_ADAM_DEFAULTS)
+                okey = key[:-len("learning_rate")] + "optim_factory"
+                doc[okey] = dict(_ADAM_DEFAULTS)
+                if okey in getattr(self, "WEIGHT_DECAY_OPTIMS", ()):
+                    doc[okey]["weight_decay"] = getattr(self, "_" + okey[:-len("optim_factory")] + "weight_decay")
         doc = dict(sorted(doc.items()))
         doc["algorithm"] = type(self).__name__
         doc["observation_shape"] = list(self._impl.observation_shape)
@@ -328,6 +341,12 @@ class AlgoBase:
             value = params[key]
             if key.endswith("encoder_factory"):
                 params[key] = _encoder_from_json(value)
+            elif key.endswith("optim_factory") and key in getattr(cls, "WEIGHT_DECAY_OPTIMS", ()):
+                # AdamFactory(weight_decay=...) is part of this algorithm's definition (AWAC's actor, awac.py:105)
+                wd = dict(_ADAM_DEFAULTS, weight_decay=(value or {}).get("weight_decay", 0))
+                if value is not None and any(value.get(k, v) != v for k, v in wd.items() if not isinstance(v, list)):
+                    raise ValueError(f"{key}: only Adam with weight decay is on the accelerated path, got {value}")
+                params[key] = None if value is None else _AdamWeightDecay(float(wd["weight_decay"]))
             elif key.endswith("optim_factory"):
                 if value is not None and any(value.get(k, v) != v and list(value.get(k, v)) != v
                                              for k, v in _ADAM_DEFAULTS.items() if not isinstance(v, list)) or \

@@ -256,6 +256,22 @@ class AWACImpl(_GaussActorImpl):
         self._lam = float(lam)
         self.ACTOR_WEIGHT_DECAY = float(actor_weight_decay)
 
+    def build(self) -> None:
+        super().build()
+        # AWACImpl is a SACImpl with a frozen temperature (awac_impl.py:46-48: initial_temperature 1e-20,
+        # temp_learning_rate 0): the scalar and its never-stepped Adam exist only so that checkpoints interchange
+        import math
+
+        from .cql_impl import _Scalar
+        from .ddpg_impl import C_TEMP
+
+        self._log_temp = _Scalar(math.log(1e-20), self._device, self._counters[C_TEMP:C_TEMP + 1])
+
+    def _checkpoint_views(self):
+        v = super()._checkpoint_views()
+        v.update({"_log_temp": self._log_temp, "_temp_optim": self._log_temp.optim_view(0.0)})
+        return v
+
     def _weights_args(self):
         return 0, 0, self._lam, 0.0        # value = mean over samples, softmax over the batch of adv / lam, times B
 

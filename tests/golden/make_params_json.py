@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import ref_import  # noqa: E402
 
 ref_import.load()
-from d3rlpy.algos import DDPG, DQN, IQL, NFQ, BCQ, CQL, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
+from d3rlpy.algos import AWAC, BEAR, CRR, DDPG, DQN, IQL, NFQ, BCQ, CQL, PLAS, SAC, TD3, DiscreteCQL, TD3PlusBC  # noqa: E402
 from d3rlpy.models.encoders import VectorEncoderFactory  # noqa: E402
 from d3rlpy.models.q_functions import QRQFunctionFactory  # noqa: E402
 
@@ -35,6 +35,11 @@ cases = {
     "iql": (IQL(actor_encoder_factory=enc, critic_encoder_factory=enc, value_encoder_factory=enc), (6,), 3),
     "dqn_qr": (DQN(encoder_factory=enc, q_func_factory="qr"), (6,), 4),
     "nfq": (NFQ(encoder_factory=enc), (6,), 4),
+    "awac": (AWAC(actor_encoder_factory=enc, critic_encoder_factory=enc, n_action_samples=2), (6,), 3),
+    "crr": (CRR(actor_encoder_factory=enc, critic_encoder_factory=enc, advantage_type="max", weight_type="binary"), (6,), 3),
+    "plas": (PLAS(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc, lam=0.6), (6,), 3),
+    "bear": (BEAR(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc,
+                  mmd_kernel="gaussian", n_mmd_action_samples=3), (6,), 3),
 }
 out = {}
 for name, (algo, obs, act) in cases.items():

@@ -127,7 +127,8 @@ def test_params_json_matches_reference_format():
     import os
     from types import SimpleNamespace
 
-    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, IQL, NFQ, SAC, TD3, DiscreteCQL, QRQFunctionFactory, TD3PlusBC
+    from d3rlpy_b200.algos import (AWAC, BCQ, BEAR, CQL, CRR, DDPG, DQN, IQL, NFQ, PLAS, SAC, TD3, DiscreteCQL,
+                                   QRQFunctionFactory, TD3PlusBC)
 
     ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "params_json.json")))
     enc = [32, 32]
@@ -147,6 +148,13 @@ def test_params_json_matches_reference_format():
         "dcql_pixel": (DiscreteCQL(n_frames=4, scaler="pixel", use_gpu=None), (4, 84, 84), 4),
         "sac": (SAC(actor_encoder_factory=enc, critic_encoder_factory=enc, use_gpu=None), (6,), 3),
         "td3": (TD3(actor_encoder_factory=enc, critic_encoder_factory=enc, use_gpu=None), (6,), 3),
+        "awac": (AWAC(actor_encoder_factory=enc, critic_encoder_factory=enc, n_action_samples=2, use_gpu=None), (6,), 3),
+        "crr": (CRR(actor_encoder_factory=enc, critic_encoder_factory=enc, advantage_type="max", weight_type="binary",
+                    use_gpu=None), (6,), 3),
+        "plas": (PLAS(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc, lam=0.6,
+                      use_gpu=None), (6,), 3),
+        "bear": (BEAR(actor_encoder_factory=enc, critic_encoder_factory=enc, imitator_encoder_factory=enc,
+                      mmd_kernel="gaussian", n_mmd_action_samples=3, use_gpu=None), (6,), 3),
     }
     for name, (algo, obs, act) in cases.items():
         algo._impl = SimpleNamespace(observation_shape=obs, action_size=act)  # the document needs the shapes only

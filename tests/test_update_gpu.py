@@ -650,7 +650,8 @@ def test_predict_api_matches_oracle():
         algo.sample_action(x)
 
 
-@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3", "ddpg", "dqn_qr", "iql"])
+@pytest.mark.parametrize("name", ["cql", "td3bc", "bcq", "dcql", "sac", "td3", "ddpg", "dqn_qr", "iql", "awac", "crr", "plas",
+                                  "bear"])
 def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     """impl.save_model writes the reference's checkpoint layout (tests/golden/checkpoint_keys.json, recorded from the
     unmodified reference's save_model); load_model restores parameters, targets and optimizer state exactly
@@ -658,7 +659,7 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
     import json
     import os
 
-    from d3rlpy_b200.algos import BCQ, CQL, DDPG, DQN, IQL, SAC, TD3, DiscreteCQL, TD3PlusBC
+    from d3rlpy_b200.algos import AWAC, BCQ, BEAR, CQL, CRR, DDPG, DQN, IQL, PLAS, SAC, TD3, DiscreteCQL, TD3PlusBC
 
     golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "checkpoint_keys.json")))[name]
     H = [32, 32]
@@ -680,6 +681,14 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
             a = TD3PlusBC(actor_encoder_factory=H, critic_encoder_factory=H, scaler=None)
         elif name == "bcq":
             a = BCQ(actor_encoder_factory=H, critic_encoder_factory=H, imitator_encoder_factory=H)
+        elif name == "awac":
+            a = AWAC(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "crr":
+            a = CRR(actor_encoder_factory=H, critic_encoder_factory=H)
+        elif name == "plas":
+            a = PLAS(actor_encoder_factory=H, critic_encoder_factory=H, imitator_encoder_factory=H, warmup_steps=1)
+        elif name == "bear":
+            a = BEAR(actor_encoder_factory=H, critic_encoder_factory=H, imitator_encoder_factory=H, warmup_steps=1)
         else:
             a = DiscreteCQL(encoder_factory=H, n_critics=2)
         a.create_impl((6,), 4 if name in ("dcql", "dqn_qr") else 3)
@@ -710,6 +719,9 @@ def test_checkpoint_layout_matches_reference_and_round_trips(name, tmp_path):
             assert sorted(ck[k]["param_groups"][0].keys()) == sorted(g["param_groups"][0].keys()), k
             assert ck[k]["param_groups"][0]["params"] == g["param_groups"][0]["params"], k
             n_params = len(g["param_groups"][0]["params"])
+            if name == "awac" and k == "_temp_optim":   # the frozen temperature is never stepped: no Adam state
+                assert ck[k]["state"] == {}
+                continue
             assert sorted(ck[k]["state"].keys()) == list(range(n_params)), k
             assert sorted(ck[k]["state"][0].keys()) == ["exp_avg", "exp_avg_sq", "step"]
         else:                     # module
