@@ -289,3 +289,34 @@ def test_f4_from_json_reads_reference_params(name, tmp_path):
     for key, value in ref.items():
         if key != "use_gpu":
             assert json.loads(json.dumps(doc[key])) == value, (key, doc[key], value)
+
+
+@pytest.mark.parametrize("name", ["awac", "crr", "plas", "bear"])
+def test_f4_fit_loop_and_evaluation_api(name):
+    """`fit()` over an HBM-resident dataset (device gather + update graph per step), then the evaluation calls the
+    reference's scorers use: shapes, finiteness, action range."""
+    import d3rlpy_b200.algos as algos
+    from d3rlpy_b200.dataset import MDPDataset
+
+    cls = {"awac": algos.AWAC, "crr": algos.CRR, "plas": algos.PLAS, "bear": algos.BEAR}[name]
+    rs = np.random.RandomState(0)
+    S, O, A = 4000, 6, 3
+    ds = MDPDataset(rs.randn(S, O).astype(np.float32), rs.uniform(-1, 1, (S, A)).astype(np.float32),
+                    rs.randn(S).astype(np.float32), (np.arange(S) % 200 == 199).astype(np.float32))
+    kw = dict(actor_encoder_factory=[32, 32], critic_encoder_factory=[32, 32], batch_size=64)
+    if name in ("plas", "bear"):
+        kw.update(imitator_encoder_factory=[48, 48], warmup_steps=5)
+    algo = cls(**kw)
+    hist = algo.fit(ds, n_steps=20, n_steps_per_epoch=10, seed=0)
+    assert len(hist) == 2 and algo.grad_step == 20
+    for _, metrics in hist:
+        assert "critic_loss" in metrics or name in ("plas",) and "imitator_loss" in metrics
+        assert all(np.isfinite(float(v)) for v in metrics.values()), metrics
+    x = rs.randn(9, O).astype(np.float32)
+    act = algo.predict(x)
+    assert act.shape == (9, A) and np.all(np.isfinite(act)) and np.all(np.abs(act) <= 1.0 + 1e-6)
+    v = algo.predict_value(x, act)
+    assert v.shape == (9,) and np.all(np.isfinite(v))
+    if name != "bear":
+        s = algo.sample_action(x)
+        assert s.shape == (9, A) and np.all(np.isfinite(s))
