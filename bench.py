@@ -257,6 +257,51 @@ def kernel_profile(algo, batch_np, n_iter=5):
     return fams, dominant
 
 
+def other_configs_e2e(precision, n=60, warm=10):
+    """BASELINE configs[2] (BCQ, 750x750 VAE + 400x300 nets, n_action_samples 100, batch 256) and configs[3]
+    (DiscreteCQL, NatureDQN encoder on 4x84x84 uint8 frames, batch 32): `algo.update(numpy batch)` wall clock per update
+    (pinned H2D + one CUDA-graph replay + metric D2H), both modes."""
+    import torch
+
+    from d3rlpy_b200.algos import BCQ, DiscreteCQL
+
+    rs = np.random.RandomState(0)
+    out = {"how": "wall clock over algo.update(host numpy batch) calls, 4 rotating batches; us per update"}
+    vec = [SimpleNamespace(observations=rs.randn(256, 17).astype(np.float32),
+                           actions=rs.uniform(-1, 1, (256, 6)).astype(np.float32),
+                           rewards=rs.randn(256, 1).astype(np.float32),
+                           next_observations=rs.randn(256, 17).astype(np.float32),
+                           terminals=(rs.rand(256, 1) < 0.01).astype(np.float32),
+                           n_steps=np.ones((256, 1), np.float32)) for _ in range(4)]
+    pix = [SimpleNamespace(observations=rs.randint(0, 256, (32, 4, 84, 84)).astype(np.uint8),
+                           actions=rs.randint(0, 4, 32).astype(np.int32),
+                           rewards=(rs.rand(32, 1) < 0.1).astype(np.float32),
+                           next_observations=rs.randint(0, 256, (32, 4, 84, 84)).astype(np.uint8),
+                           terminals=(rs.rand(32, 1) < 0.01).astype(np.float32),
+                           n_steps=np.ones((32, 1), np.float32)) for _ in range(4)]
+    for prec in dict.fromkeys([precision, "fp32"]):
+        for name, make, batches, shape, act in (
+                ("c3_bcq_b256", lambda: BCQ(actor_encoder_factory=[400, 300], critic_encoder_factory=[400, 300],
+                                            imitator_encoder_factory=[750, 750], batch_size=256, n_action_samples=100,
+                                            precision=prec), vec, (17,), 6),
+                ("c4_discrete_cql_pixels_b32", lambda: DiscreteCQL(batch_size=32, n_frames=4, scaler="pixel",
+                                                                   precision=prec), pix, (4, 84, 84), 4)):
+            algo = make()
+            algo.create_impl(shape, act)
+            for i in range(warm):
+                algo.update(batches[i % 4])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n):
+                algo.update(batches[i % 4])
+            torch.cuda.synchronize()
+            us = (time.perf_counter() - t0) / n * 1e6
+            out[f"{name}_{prec}"] = {"us_per_update": us, "updates_per_s": 1e6 / us}
+            del algo
+            torch.cuda.empty_cache()
+    return out
+
+
 class Runner:
     """One workload on this rank: replay + indices in HBM, device-timed steps, end-to-end steps."""
 
@@ -567,6 +612,9 @@ def run_ours(args, w):
                 c1[prec].update({"steps": kc, "graph_nodes_per_update": nc, "e2e": rc.e2e(max(10, min(kc, 100)))[0]})
                 del rc
             extra["c1"] = {"workload": WORKLOADS["c1"]["desc"], "metric": "TD3+BC gradient updates/sec at batch 256", **c1}
+        # ---- c3 (BCQ) and c4 (DiscreteCQL on pixels): end to end through the public API (host batch in, metrics out)
+        if world == 1 and args.workload == "c2":
+            extra["c3_c4_e2e"] = other_configs_e2e(args.precision)
         # ---- c5 strong scaling (the north-star scaling configuration) at every N
         if args.workload == "c2" and WORKLOADS["c5"]["batch"] % world == 0:
             r5 = Runner(WORKLOADS["c5"], world, rank, local, args.precision, True)
