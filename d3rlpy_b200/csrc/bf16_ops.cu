@@ -218,6 +218,84 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   atomicAdd(db + (long long)blockIdx.z * sdb + n, s);
 }
 
+// Wide inputs (BCQ's 750 / 300-feature heads over 25 600 rows): each lane reads 16-byte chunks of 8 bf16 activations
+// and the matching weights as four 8-byte loads (the fp32 head rows are only 8-byte aligned when K is even), two
+// outputs at a time.  The element-wise kernel above issues one 2-byte activation load and one 4-byte weight load per
+// FMA.  Used where it measures faster (see d3b_head_forward_bf16).
+template <int NCH>
+__global__ void __launch_bounds__(256) head_forward_bf16_vec_kernel(const __nv_bfloat16* __restrict__ X, long long ldx,
+                                                                    long long sX, const float* __restrict__ W,
+                                                                    long long ldw, long long sW,
+                                                                    const float* __restrict__ bias, long long sB,
+                                                                    float* __restrict__ Y, long long ldy, long long sY,
+                                                                    int M, int N, int K, int E, int act_tanh) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (long long)M * E) return;
+  const int e = (int)(wid / M), m = (int)(wid % M);
+  const __nv_bfloat16* x = X + (long long)e * sX + (long long)m * ldx;
+  const float* w = W + (long long)e * sW;
+  const int nfull = K >> 3, tail = K & 7;
+  float xr[NCH][8];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nfull) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + 8 * c));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(h[j]);
+        xr[i][2 * j] = f.x;
+        xr[i][2 * j + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xr[i][j] = 0.f;
+    }
+  }
+  const int kt = 8 * nfull + lane;
+  const float xt = lane < tail ? __bfloat162float(x[kt]) : 0.f;
+  float mine = 0.f;
+  for (int n0 = 0; n0 < N; n0 += 2) {
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + j;
+      if (n < N) {
+        const float* wr = w + (long long)n * ldw;
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nfull) {
+            const float2* wp = reinterpret_cast<const float2*>(wr + 8 * c);
+            const float2 a0 = __ldg(wp), a1 = __ldg(wp + 1), a2 = __ldg(wp + 2), a3 = __ldg(wp + 3);
+            s[j] = fmaf(xr[i][0], a0.x, s[j]); s[j] = fmaf(xr[i][1], a0.y, s[j]);
+            s[j] = fmaf(xr[i][2], a1.x, s[j]); s[j] = fmaf(xr[i][3], a1.y, s[j]);
+            s[j] = fmaf(xr[i][4], a2.x, s[j]); s[j] = fmaf(xr[i][5], a2.y, s[j]);
+            s[j] = fmaf(xr[i][6], a3.x, s[j]); s[j] = fmaf(xr[i][7], a3.y, s[j]);
+          }
+        }
+        if (lane < tail) s[j] = fmaf(xt, __ldg(wr + kt), s[j]);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+      s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+    }
+    if (lane == n0) mine = s[0];
+    if (lane == n0 + 1) mine = s[1];
+  }
+  if (lane < N) {
+    float v = mine + (bias ? __ldg(bias + (long long)e * sB + lane) : 0.f);
+    if (act_tanh) v = tanhf(v);
+    Y[(long long)e * sY + (long long)m * ldy + lane] = v;
+  }
+}
+
 }  // namespace d3b
 
 using namespace d3b;
@@ -265,6 +343,24 @@ extern "C" int d3b_head_forward_bf16(const void* x, int64_t ldx, int64_t stride_
   if (rows == 0) return D3B_OK;
   D3B_REQUIRE(x && w && y, "head_forward_bf16: null pointer");
   long long warps = (long long)rows * members;
+  // measured (profiles/r2/head_bf16_bench.py): the chunked kernel wins for one or two outputs (25 600 x 300 -> 1, two
+  // members: 32.3 -> 19.4 us) and for few rows (256 x 750 -> 6: 8.0 -> 6.1 us); with six outputs over 25 600 rows the
+  // element-wise kernel's four-outputs-at-a-time loop is faster (32 us against 60), so it keeps those
+  const bool vec_ok = in_features > 256 && in_features <= 1024 && ldx % 8 == 0 && stride_x % 8 == 0 &&
+                      ((uintptr_t)x & 15) == 0 && ldw % 2 == 0 && stride_w % 2 == 0 && ((uintptr_t)w & 7) == 0 &&
+                      (out_features <= 2 || warps <= 2048);
+  if (vec_ok) {
+    dim3 grid((unsigned)ceil_div_ll(warps, 8));
+    if (in_features <= 768)
+      launch_pdl(head_forward_bf16_vec_kernel<3>, grid, dim3(256), 0, ST, (const __nv_bfloat16*)x, (long long)ldx,
+                 (long long)stride_x, w, (long long)ldw, (long long)stride_w, bias, (long long)stride_b, y,
+                 (long long)ldy, (long long)stride_y, rows, out_features, in_features, members, act_tanh);
+    else
+      launch_pdl(head_forward_bf16_vec_kernel<4>, grid, dim3(256), 0, ST, (const __nv_bfloat16*)x, (long long)ldx,
+                 (long long)stride_x, w, (long long)ldw, (long long)stride_w, bias, (long long)stride_b, y,
+                 (long long)ldy, (long long)stride_y, rows, out_features, in_features, members, act_tanh);
+    return check_launch("head_forward_bf16");
+  }
   if (in_features <= 256)
     head_forward_bf16_kernel<8><<<(unsigned)ceil_div_ll(warps, 8), 256, 0, ST>>>(
         (const __nv_bfloat16*)x, ldx, stride_x, w, ldw, stride_w, bias, stride_b, y, ldy, stride_y, rows, out_features,

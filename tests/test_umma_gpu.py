@@ -442,3 +442,28 @@ def test_fused_mlp_backward_matches_torch(rows, E, in_dim, hidden, n_head, wg, d
         close(grads[:, hw_off:hw_off + n_head * feat].view(E, n_head, feat),
               torch.einsum("erj,erc->ejc", d_head, acts[-1][:, :, :feat].float()), 2e-3, "d_head_w")
         close(grads[:, hb_off:hb_off + n_head], d_head.sum(1), 2e-3, "d_head_b")
+
+
+@pytest.mark.parametrize("M,K,N,E,tanh", [(300, 750, 6, 1, True), (1000, 300, 1, 2, False), (130, 1000, 32, 1, False),
+                                          (64, 516, 7, 3, False)])
+def test_head_forward_bf16_wide_inputs(M, K, N, E, tanh):
+    """Heads over wide bf16 activations (BCQ's 750 / 300 features): the 16-byte-chunk kernel, incl. K not a multiple of
+    8 (tail elements), padded leading dimension with garbage, tanh."""
+    from d3rlpy_b200._lib import lib
+
+    L, dev = lib(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + K)
+    ld = (K + 7) // 8 * 8
+    x = torch.full((E, M, ld), 77.0, dtype=torch.bfloat16)
+    x[:, :, :K] = _bf(torch.relu(torch.randn(E, M, K, generator=g)))
+    x = x.to(dev)
+    w = (torch.randn(E, N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(E, N, generator=g).to(dev)
+    y = torch.zeros(E, M, N, device=dev)
+    L.head_forward_bf16(x.data_ptr(), ld, M * ld, w.data_ptr(), K, N * K, b.data_ptr(), N, y.data_ptr(), N, M * N, M, N,
+                        K, E, 1 if tanh else 0, _st())
+    torch.cuda.synchronize()
+    ref = torch.einsum("emk,enk->emn", x[:, :, :K].float(), w) + b[:, None, :]
+    if tanh:
+        ref = torch.tanh(ref)
+    assert (y - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
