@@ -140,6 +140,11 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             self._side_obj = torch.cuda.Stream(device=self._device)
         return self._side_obj.cuda_stream
 
+    def _side_stream2(self) -> int:
+        if getattr(self, "_side2_obj", None) is None:
+            self._side2_obj = torch.cuda.Stream(device=self._device)
+        return self._side2_obj.cuda_stream
+
     def _program_fused(self, db, actor_step: bool):
         """Same update as `program` with the rows written straight as bf16 GEMM operands, the loss tail fused, and
         the online-critic forward running on a graph branch beside the target path (policy' -> smoothing -> Q')."""
@@ -161,6 +166,15 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         ctx_c = q_net.ctx("cq", B, E, True)
         q = self.ws("cq_q", E, B)
         q_net.forward("params", None, 0, B, ctx_c, q, side, x_bf16=(X.data_ptr(), ld))
+        if actor_step:
+            # ---- second branch: pi(s) and the actor rows do not depend on the critic step -> beside it, not after it
+            side2 = self._side_stream2()
+            L.stream_fork(st, side2)
+            acts_p = pi.ctx("pi", B, 1, True)
+            a = self.ws("pi_a", 1, B, A)
+            pi.forward("params", db.ptr("obs"), O, B, acts_p, a, side2, head_tanh=True)
+            xa = X.data_ptr() + 2 * 2 * B * ld
+            L.concat_rows_bf16(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, side2)
         # ---- main: target policy -> smoothed action -> target critics
         a_next = self.ws("tp_a", 1, B, A)
         pi.forward("target", db.ptr("next_obs"), O, B, pi.ctx("tp", B, 1, False), a_next, st, head_tanh=True)
@@ -178,12 +192,8 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         q_net.adam(self._critic_learning_rate, st, tau=self._tau if actor_step else None)
         if not actor_step:
             return
-        # ---- actor step (td3_plus_bc_impl.py:64-70): member 0 only
-        acts_p = pi.ctx("pi", B, 1, True)
-        a = self.ws("pi_a", 1, B, A)
-        pi.forward("params", db.ptr("obs"), O, B, acts_p, a, st, head_tanh=True)
-        xa = X.data_ptr() + 2 * 2 * B * ld
-        L.concat_rows_bf16(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, st)
+        # ---- actor step (td3_plus_bc_impl.py:64-70): member 0 only, on the updated critics
+        L.stream_join(st, side2)
         ctx_a = q_net.ctx("aq", B, 1, True)
         q0 = self.ws("aq_q", 1, B)
         q_net.forward("params", None, 0, B, ctx_a, q0, st, x_bf16=(xa, ld))
