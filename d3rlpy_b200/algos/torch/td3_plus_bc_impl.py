@@ -150,22 +150,34 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         the online-critic forward running on a graph branch beside the target path (policy' -> smoothing -> Q')."""
         B, O, A, E = db.B, db.O, self._action_size, self._n_critics
         L, st = self._lib, self._stream
-        bf = torch.bfloat16
-        ld = (O + A + 7) // 8 * 8
+        f32 = self._precision == "fp32"   # fp32 mode: fp32 operand rows, one GEMM launch per layer (3xTF32 / SIMT)
+        ld = (O + A + 3) // 4 * 4 if f32 else (O + A + 7) // 8 * 8
+        esz = 4 if f32 else 2
         inv_b = 1.0 / B
         mask = (1 << C_DRAW) | (1 << C_CRITIC) | ((1 << C_ACTOR) if actor_step else 0)
         L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
         self.fill_noise(B)
-        X = self.ws("xf_rows", 3 * B, ld, dtype=bf)        # [critic rows | target rows | actor rows]
+        X = self.ws("xf_rows", 3 * B, ld, dtype=torch.float32 if f32 else torch.bfloat16)   # [critic | target | actor] rows
+        concat = L.concat_rows if f32 else L.concat_rows_bf16
+
+        def q_forward(which, xptr, ctx, out, stream):
+            if f32:
+                q_net.forward(which, xptr, ld, B, ctx, out, stream)
+            else:
+                q_net.forward(which, None, 0, B, ctx, out, stream, x_bf16=(xptr, ld))
+
+        def q_backward(xptr, ctx, dq_, stream, **kw):
+            q_net.backward(xptr if f32 else None, ld if f32 else 0, B, ctx, dq_, stream, **kw)
+
         done = self.ws("xf_done", 4 + 3 * ((B * E + 7) // 8) + 4, dtype=torch.int32)
         q_net, pi = self._q_func, self._policy
         # ---- branch: online critics on (s, a)
         side = self._side_stream()
         L.stream_fork(st, side)
-        L.concat_rows_bf16(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, X.data_ptr(), ld, B, 1, O, A, side)
+        concat(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, X.data_ptr(), ld, B, 1, O, A, side)
         ctx_c = q_net.ctx("cq", B, E, True)
         q = self.ws("cq_q", E, B)
-        q_net.forward("params", None, 0, B, ctx_c, q, side, x_bf16=(X.data_ptr(), ld))
+        q_forward("params", X.data_ptr(), ctx_c, q, side)
         if actor_step:
             # ---- second branch: pi(s) and the actor rows do not depend on the critic step -> beside it, not after it
             side2 = self._side_stream2()
@@ -173,22 +185,22 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             acts_p = pi.ctx("pi", B, 1, True)
             a = self.ws("pi_a", 1, B, A)
             pi.forward("params", db.ptr("obs"), O, B, acts_p, a, side2, head_tanh=True)
-            xa = X.data_ptr() + 2 * 2 * B * ld
-            L.concat_rows_bf16(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, side2)
+            xa = X.data_ptr() + esz * 2 * B * ld
+            concat(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, side2)
         # ---- main: target policy -> smoothed action -> target critics
         a_next = self.ws("tp_a", 1, B, A)
         pi.forward("target", db.ptr("next_obs"), O, B, pi.ctx("tp", B, 1, False), a_next, st, head_tanh=True)
-        xt = X.data_ptr() + 2 * B * ld
-        L.concat_rows_bf16(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
-                           self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt, ld, B, 1, O, A, st)
+        xt = X.data_ptr() + esz * B * ld
+        concat(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
+               self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt, ld, B, 1, O, A, st)
         q_t = self.ws("tq_q", E, B)
-        q_net.forward("target", None, 0, B, q_net.ctx("tq", B, E, False), q_t, st, x_bf16=(xt, ld))
+        q_forward("target", xt, q_net.ctx("tq", B, E, False), q_t, st)
         L.stream_join(st, side)
         dq = self.ws("dq", E, B)
         L.cql_loss_step(q.data_ptr(), B, q_t.data_ptr(), B, E, None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
                         self._gamma, None, None, 0, A, None, 0.0, 0.0, dq.data_ptr(), B, self.sums_ptr(S_TD),
                         done.data_ptr(), B, E, inv_b, 0, None, 0.0, self.metric_ptr(M_CRITIC), None, st)
-        q_net.backward(None, 0, B, ctx_c, dq, st)
+        q_backward(X.data_ptr(), ctx_c, dq, st)
         q_net.adam(self._critic_learning_rate, st, tau=self._tau if actor_step else None)
         if not actor_step:
             return
@@ -196,12 +208,11 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         L.stream_join(st, side2)
         ctx_a = q_net.ctx("aq", B, 1, True)
         q0 = self.ws("aq_q", 1, B)
-        q_net.forward("params", None, 0, B, ctx_a, q0, st, x_bf16=(xa, ld))
+        q_forward("params", xa, ctx_a, q0, st)
         dq0 = self.ws("a_dq", 1, B)
         bc_w = self._actor_seed(q0, a, db, dq0, B, A, inv_b)
         dxa = self.ws("a_dx", B, A)
-        q_net.backward(None, 0, B, ctx_a, dq0, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O,
-                       dx_cols=A)
+        q_backward(xa, ctx_a, dq0, st, weight_grads=False, dx=dxa, lddx=A, stride_dx=B * A, dx_col0=O, dx_cols=A)
         dz = self.ws("pi_dz", 1, B, A)
         L.td3bc_actor_backward(a.data_ptr(), A, db.ptr("act"), A, dxa.data_ptr(), A, dz.data_ptr(), A, B, A, bc_w, st)
         pi.backward(db.ptr("obs"), O, B, acts_p, dz, st)
@@ -225,8 +236,9 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             if actor_step:
                 self._p_actor(db)
 
-        fused = (self._precision == "bf16" and self.world_size == 1 and self._q_func.fused_ok
-                 and self._policy.fused_ok and self.fused_glue and not self._n_quantiles)
+        fused = (self.world_size == 1 and self.fused_glue and not self._n_quantiles
+                 and ((self._precision == "bf16" and self._q_func.fused_ok and self._policy.fused_ok)
+                      or (self._precision == "fp32" and not self._q_func.wide_head)))
         self.run_program(("td3bc", db.B, actor_step, self._noise_injected, fused),
                          (lambda: self._program_fused(db, actor_step)) if fused else program)
         return [(M_CRITIC, "critic_loss")] + ([(M_ACTOR, "actor_loss")] if actor_step else [])
