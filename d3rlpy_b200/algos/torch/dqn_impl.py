@@ -89,9 +89,10 @@ class DQNImpl(ImplBase):
         return {"_q_func": self.q_function, "_targ_q_func": self.targ_q_function, "_optim": self.q_function_optim}
 
     # ------------------------------------------------------------------ program pieces
-    def _forward(self, which, db, field, tag, train):
+    def _forward(self, which, db, field, tag, train, stream=None):
         """Q values [E, B, A] (quantiles [E, B, A * n_quantiles]) of the chosen parameter set on obs / next_obs."""
-        B, A, E, st = db.B, self._action_size * max(1, self._n_quantiles), self._n_critics, self._stream
+        B, A, E = db.B, self._action_size * max(1, self._n_quantiles), self._n_critics
+        st = self._stream if stream is None else stream
         q = self.ws(f"{tag}_q", E, B, A)
         if self._pixel:
             ctx = self._q_func.ctx(tag, B, E, train)
@@ -101,11 +102,34 @@ class DQNImpl(ImplBase):
             self._q_func.forward(which, db.ptr(field), db.O, B, ctx, q, st)
         return ctx, q
 
-    def _p_target(self, db):
-        """DQNImpl.compute_target (dqn_impl.py:133-141) / DoubleDQNImpl.compute_target (:162-171)."""
+    def _side_streams(self):
+        if getattr(self, "_side_objs", None) is None:
+            self._side_objs = (torch.cuda.Stream(device=self._device), torch.cuda.Stream(device=self._device))
+        return self._side_objs[0].cuda_stream, self._side_objs[1].cuda_stream
+
+    def _p_next_values(self, db):
+        """The target network on s' and (Double DQN) the online network on s', each on its own graph branch; the caller
+        joins them with `_join_branches` before `_p_target_kernel`.  Together with the online network on s (main
+        stream, `_p_loss`) these are three independent chains of small launches."""
+        L, st = self._lib, self._stream
+        s1, s2 = self._side_streams()
+        L.stream_fork(st, s1)
+        _, q_t = self._forward("target", db, "next_obs", "tq", False, stream=s1)
+        self._pending_joins = [s1]
+        q_sel = q_t
+        if self.DOUBLE:
+            L.stream_fork(st, s2)
+            q_sel = self._forward("params", db, "next_obs", "oq", False, stream=s2)[1]
+            self._pending_joins.append(s2)
+        return q_sel, q_t
+
+    def _join_branches(self):
+        for s in getattr(self, "_pending_joins", []):
+            self._lib.stream_join(self._stream, s)
+        self._pending_joins = []
+
+    def _p_target_kernel(self, db, q_sel, q_t):
         B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
-        _, q_t = self._forward("target", db, "next_obs", "tq", False)
-        q_sel = self._forward("params", db, "next_obs", "oq", False)[1] if self.DOUBLE else q_t
         nq = self._n_quantiles
         if nq:
             q_tpn = self.ws("q_tpn", B, nq)
@@ -115,10 +139,23 @@ class DQNImpl(ImplBase):
         L.dqn_target(q_sel.data_ptr(), B * A, q_t.data_ptr(), B * A, q_tpn.data_ptr(), B, A, E, st)
         return q_tpn
 
-    def _p_loss(self, db, q_tpn, step=True):
+    def _p_target(self, db):
+        """DQNImpl.compute_target (dqn_impl.py:133-141) / DoubleDQNImpl.compute_target (:162-171)."""
+        q_sel, q_t = self._p_next_values(db)
+        self._join_branches()
+        return self._p_target_kernel(db, q_sel, q_t)
+
+    def _p_update(self, db):
+        """One whole update: the three forward passes side by side, then target, loss, backward, Adam."""
+        q_sel, q_t = self._p_next_values(db)
+        fwd = self._forward("params", db, "obs", "lq", True)
+        self._join_branches()
+        self._p_loss(db, self._p_target_kernel(db, q_sel, q_t), fwd=fwd)
+
+    def _p_loss(self, db, q_tpn, step=True, fwd=None):
         """compute_loss (dqn_impl.py:113-131; cql_impl.py:279-302) [+ backward + Adam (dqn_impl.py:97-111)]."""
         B, A, E, L, st = db.B, self._action_size, self._n_critics, self._lib, self._stream
-        ctx, q = self._forward("params", db, "obs", "lq", True)
+        ctx, q = fwd if fwd is not None else self._forward("params", db, "obs", "lq", True)
         nq = self._n_quantiles
         dq = self.ws("dq", E, B, A * max(1, nq))
         inv_b = 1.0 / (B * self.world_size)
@@ -169,7 +206,7 @@ class DQNImpl(ImplBase):
         def program():
             self._tick(C_CRITIC)
             self.zero_slots()
-            self._p_loss(db, self._p_target(db))
+            self._p_update(db)
             if sync_target:
                 self._p_hard_sync()
 
@@ -181,7 +218,7 @@ class DQNImpl(ImplBase):
         db = self.load_batch(batch)
         self._tick(C_CRITIC)
         self.zero_slots()
-        self._p_loss(db, self._p_target(db))
+        self._p_update(db)
         return self.read_slots()[M_LOSS].copy()
 
     def compute_target(self, batch) -> torch.Tensor:
