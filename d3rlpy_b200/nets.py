@@ -416,13 +416,18 @@ class DenseNet:
         last = ctx.hb[-1]
         lf = _a8(feat)
         dcur = ctx.dz[nl - 1]
+        # per-layer launches (layers wider than the fused kernels' 256 columns): weight / bias gradients on a side stream
+        side = self._wgrad_stream() if weight_grads and self.wgrad_side and not self.wide_head else None
+        ws = side if side is not None else stream
+        if side is not None:
+            L.stream_fork(stream, side)
         if self.wide_head:
             _wide_head_backward(self, ctx, rows, E, d_head, _p(last), lf, rows * lf, _p(dcur), lf, rows * lf, stream,
                                 weight_grads, member0)
         else:
             if weight_grads:
                 L.head_backward_weight_bf16(_p(d_head), ldh, sdh, _p(last), lf, rows * lf, self._hw("grads", member0),
-                                            feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, stream)
+                                            feat, ms, self._hb("grads", member0), ms, rows, n, feat, E, ws)
             L.head_backward_data_bf16(_p(d_head), ldh, sdh, self._hw("params", member0), feat, ms, _p(dcur), lf,
                                       rows * lf, None, 0, 0, _p(last), lf, rows * lf, rows, n, feat, E, stream)
         for i in range(nl - 1, -1, -1):
@@ -431,7 +436,9 @@ class DenseNet:
             d_in = self.hidden[i - 1] if i > 0 else self.in_dim
             ldi = _a8(d_in)
             if weight_grads:
-                L.colsum_bf16(_p(dcur), lh, rows * lh, self._b("grads", i, member0), ms, rows, h, E, stream)
+                if side is not None:
+                    L.stream_fork(stream, side)   # dZ_i is complete on the main stream
+                L.colsum_bf16(_p(dcur), lh, rows * lh, self._b("grads", i, member0), ms, rows, h, E, ws)
                 if i > 0:
                     bsrc, ldb, sb = _p(ctx.hb[i - 1]), ldi, rows * ldi
                 else:
@@ -439,7 +446,7 @@ class DenseNet:
                 tiles = -(-h // 128) * -(-d_in // 256) * E
                 splits = max(1, min(-(-rows // 64), -(-148 // tiles)))
                 L.umma_gemm_tn(_p(dcur), lh, rows * lh, bsrc, ldb, sb, h, d_in, rows, E, splits,
-                               self._w("grads", i, member0), d_in, ms, 1, stream)
+                               self._w("grads", i, member0), d_in, ms, 1, ws)
             if i > 0:
                 dnext = ctx.dz[i - 1]
                 wt, ldwt = self._swt(i, member0)
@@ -451,6 +458,8 @@ class DenseNet:
                 wt, ldwt = self._swt(0, member0)
                 L.umma_gemm(_p(dcur), lh, rows * lh, wt + 2 * dx_col0 * ldwt, ldwt, sms, rows, dx_cols, h, E, 1, None, 0,
                             0, None, 0, 0, None, 0, 0, None, 0, 0, _p(dx), lddx, stride_dx, 0, stream)
+        if side is not None:
+            L.stream_join(stream, side)
 
     # ------------------------------------------------------------------ optimizer
     def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None, peer=None):
@@ -688,18 +697,26 @@ class ConvNet:
         dcur = ctx.dacts[-1]
         ldd = dcur.shape[2]
         hw_g, hb_g = self.arena.addr("grads", "__head.weight"), self.arena.addr("grads", "__head.bias")
+        # weight / bias gradients on a side stream beside the data-gradient chain (dW_l needs dY_l only; every layer
+        # has its own dY buffer)
+        # (bf16 mode only: measured on c4, the fp32-mode weight gradients — 3xTF32 launches split to fill the machine —
+        # slow the data-gradient chain down more than the overlap gains: 507 -> 655 us)
+        side = self._wgrad_stream() if self.wgrad_side and bf and not self.wide_head else None
+        ws = side if side is not None else stream
+        if side is not None:
+            L.stream_fork(stream, side)
         if self.wide_head:
             _wide_head_backward(self, ctx, images, E, d_head, _p(last), ldl, last.shape[1] * ldl, _p(dcur), ldd,
                                 dcur.shape[1] * ldd, stream)
         elif bf:
             L.head_backward_weight_bf16(_p(d_head), n, images * n, _p(last), ldl, last.shape[1] * ldl, hw_g, d, ms, hb_g,
-                                        ms, images, n, d, E, stream)
+                                        ms, images, n, d, E, ws)
             L.head_backward_data_bf16(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms,
                                       _p(dcur), ldd, dcur.shape[1] * ldd, None, 0, 0, _p(last), ldl, last.shape[1] * ldl,
                                       images, n, d, E, stream)
         else:
             L.head_backward_weight(_p(d_head), n, images * n, _p(last), d, last.shape[1] * d, hw_g, d, ms, hb_g, ms,
-                                   images, n, d, E, stream)
+                                   images, n, d, E, ws)
             L.head_backward_data(_p(d_head), n, images * n, self.arena.addr("params", "__head.weight"), d, ms, _p(dcur),
                                  d, dcur.shape[1] * d, _p(last), d, last.shape[1] * d, images, n, d, E, stream)
         for i in range(len(self.layers) - 1, -1, -1):
@@ -708,16 +725,18 @@ class ConvNet:
             p = ctx.patches[i]
             ldp, ldd = p.shape[2], dcur.shape[2]
             sx = 0 if i == 0 else p.shape[1] * ldp
+            if side is not None:
+                L.stream_fork(stream, side)   # dY_i is complete on the main stream
             if bf:
-                L.colsum_bf16(_p(dcur), ldd, dcur.shape[1] * ldd, self._b("grads", i), ms, rows, oc, E, stream)
+                L.colsum_bf16(_p(dcur), ldd, dcur.shape[1] * ldd, self._b("grads", i), ms, rows, oc, E, ws)
                 tiles = -(-oc // 128) * -(-K // 128) * E
                 splits = max(1, min(-(-rows // 64), -(-296 // tiles)))
                 # dW[oc][K] += dY^T patches: both operands row-major => MN-major tensor-core tiles
                 L.umma_gemm_tn(_p(dcur), ldd, dcur.shape[1] * ldd, _p(p), ldp, sx, oc, K, rows, E, splits,
-                               self._w("grads", i), K, ms, 1, stream)
+                               self._w("grads", i), K, ms, 1, ws)
             else:
                 L.linear_backward_weight(_p(dcur), oc, dcur.shape[1] * oc, _p(p), K, sx, self._w("grads", i), K, ms,
-                                         self._b("grads", i), ms, rows, oc, K, E, stream)
+                                         self._b("grads", i), ms, rows, oc, K, E, ws)
             if i == 0:
                 break
             sdp = p.shape[1] * K
@@ -733,6 +752,15 @@ class ConvNet:
             L.col2im(_p(ctx.dpatch), K, sdp, _p(prev), 1 if bf else 0, prev.shape[2], prev.shape[1] * prev.shape[2],
                      _p(dprev), dprev.shape[2], dprev.shape[1] * dprev.shape[2], images, C, H, W, k, s, E, stream)
             dcur = dprev
+        if side is not None:
+            L.stream_join(stream, side)
+
+    wgrad_side = True
+
+    def _wgrad_stream(self) -> int:
+        if getattr(self, "_wg_side", None) is None:
+            self._wg_side = torch.cuda.Stream(device=self.device)
+        return self._wg_side.cuda_stream
 
     def adam(self, lr: float, stream: int, betas=(0.9, 0.999), eps=1e-8, tau: Optional[float] = None):
         a = self.arena
