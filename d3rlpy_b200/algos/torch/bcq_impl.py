@@ -199,11 +199,18 @@ class BCQImpl(DDPGBaseImpl):
     def sample_action(self, x):
         raise NotImplementedError("BCQ does not support sampling action")  # bcq_impl.py:213-214
 
-    def _p_critic(self, db, q_tpn, step=True, sync_target=False):
-        B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics
+    def _p_critic_forward(self, db, stream=None):
+        """Online critics on (s, a): independent of the imitator step and of the target computation."""
+        B, O, A, L = db.B, db.O, self._action_size, self._lib
+        st = self._stream if stream is None else stream
         xc = self.ws("xc", B, O + A)
         L.concat_rows(db.ptr("obs"), O, db.ptr("act"), A, None, 0.0, 0.0, 0.0, xc.data_ptr(), O + A, B, 1, O, A, st)
-        acts, q = self._critic_rows_forward("params", xc, B, "cq")
+        acts, q = self._critic_rows_forward("params", xc, B, "cq", stream=st)
+        return xc, acts, q
+
+    def _p_critic(self, db, q_tpn, step=True, sync_target=False, fwd=None):
+        B, O, A, L, st, E = db.B, db.O, self._action_size, self._lib, self._stream, self._n_critics
+        xc, acts, q = fwd if fwd is not None else self._p_critic_forward(db)
         dq = self.ws("dq", E, B)
         inv_b = 1.0 / (B * self.world_size)
         L.critic_loss(q.data_ptr(), B, None, B, E, q_tpn.data_ptr(), db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
@@ -216,10 +223,17 @@ class BCQImpl(DDPGBaseImpl):
             self._allreduce(self._q_func.arena.grads)
             self._q_func.adam(self._critic_learning_rate, st, tau=self._tau if sync_target else None)
 
-    def _p_actor(self, db, sync_target=True, step=True):
+    def _p_actor(self, db, sync_target=True, step=True, front=None):
         """compute_actor_loss (bcq_impl.py:132-146): -Q_0(s, pi(s, decode(s, clamp(randn)))).mean(); step=False stops
         after the loss value."""
-        B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
+        front = front if front is not None else self._p_actor_front(db)
+        self._p_actor_back(db, front, sync_target, step)
+
+    def _p_actor_front(self, db, stream=None):
+        """decode(s, clamp(randn)) -> residual policy -> critic input rows: needs the updated imitator and the current
+        policy, not the critic step."""
+        B, O, A, L = db.B, db.O, self._action_size, self._lib
+        st = self._stream if stream is None else stream
         Lz = 2 * A
         xd = self.ws("a_xd", B, O + Lz)
         L.concat_rows(db.ptr("obs"), O, self.noise_view("actor", B).data_ptr(), Lz, None, 0.0, 0.0, 0.5,
@@ -236,6 +250,11 @@ class BCQImpl(DDPGBaseImpl):
         xq = self.ws("a_xq", B, O + A)
         L.residual_rows(z.data_ptr(), A, sampled.data_ptr(), A, db.ptr("obs"), O, xq.data_ptr(), O + A,
                         self._action_flexibility, B, 1, O, A, st)
+        return xp, cp, z, sampled, xq
+
+    def _p_actor_back(self, db, front, sync_target=True, step=True):
+        B, O, A, L, st = db.B, db.O, self._action_size, self._lib, self._stream
+        xp, cp, z, sampled, xq = front
         cc, q0 = self._critic_rows_forward("params", xq, B, "aq", members=1)
         dq = self.ws("a_dq", 1, B)
         inv_b = 1.0 / (B * self.world_size)
@@ -253,6 +272,11 @@ class BCQImpl(DDPGBaseImpl):
         self._policy.backward(xp, O + A, B, cp, dz, st)
         self._allreduce(self._policy.arena.grads)
         self._policy.adam(self._actor_learning_rate, st, tau=self._tau if sync_target else None)
+
+    def _side_streams(self):
+        if getattr(self, "_side_objs", None) is None:
+            self._side_objs = (torch.cuda.Stream(device=self._device), torch.cuda.Stream(device=self._device))
+        return self._side_objs[0].cuda_stream, self._side_objs[1].cuda_stream
 
     def _allreduce(self, t):
         if self.world_size > 1:
@@ -273,15 +297,28 @@ class BCQImpl(DDPGBaseImpl):
             self._tick(*ticks)
             self.zero_slots()
             self.fill_noise(db.B)
+            L, st = self._lib, self._stream
+            fwd = front = None
+            if rl_step:
+                # graph branch 1: the online critics on (s, a) depend on nothing else in the update
+                s1, s2 = self._side_streams()
+                L.stream_fork(st, s1)
+                fwd = self._p_critic_forward(db, stream=s1)
             self._p_imitator(db)
             if rl_step:
+                if actor_step:
+                    # graph branch 2: the front of the actor step needs the updated imitator only
+                    L.stream_fork(st, s2)
+                    front = self._p_actor_front(db, stream=s2)
                 q_tpn = self._p_target(db)
                 # reference order: critic step, actor step, actor-target sync, critic-target sync
                 # (bcq.py:270-277); the critic target depends only on the critic params, so its soft
                 # sync is fused into the critic Adam pass.
-                self._p_critic(db, q_tpn, sync_target=actor_step)
+                L.stream_join(st, s1)
+                self._p_critic(db, q_tpn, sync_target=actor_step, fwd=fwd)
                 if actor_step:
-                    self._p_actor(db)
+                    L.stream_join(st, s2)
+                    self._p_actor(db, front=front)
 
         self.run_program(("bcq", db.B, rl_step, actor_step, self._noise_injected), program)
         names = [(M_IMITATOR, "imitator_loss")]

@@ -135,13 +135,14 @@ class DDPGBaseImpl(ImplBase):
                 "_actor_optim": self.policy_optim}
 
     # ------------------------------------------------------------------ shared program pieces
-    def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0, train=True):
+    def _critic_rows_forward(self, which: str, x, rows: int, tag: str, members=None, member0=0, train=True, stream=None):
         """Runs the critic trunk+head on `rows` shared input rows; returns (ctx, q[E,rows]) — (ctx, theta[E,rows,n])
         for quantile-regression critics."""
         E = members or self._n_critics
         ctx = self._q_func.ctx(tag, rows, E, train)
         q = self.ws(f"{tag}_q", E, rows, self._n_quantiles) if self._n_quantiles else self.ws(f"{tag}_q", E, rows)
-        self._q_func.forward(which, x, self._q_func.in_dim, rows, ctx, q, self._stream, member0=member0)
+        self._q_func.forward(which, x, self._q_func.in_dim, rows, ctx, q, self._stream if stream is None else stream,
+                             member0=member0)
         return ctx, q
 
     def update_critic_target(self) -> None:
