@@ -259,6 +259,11 @@ class CQLImpl(DDPGBaseImpl):
             self._side_obj = torch.cuda.Stream(device=self._device)
         return self._side_obj.cuda_stream
 
+    def _alpha_stream(self) -> int:
+        if getattr(self, "_alpha_obj", None) is None:
+            self._alpha_obj = torch.cuda.Stream(device=self._device, priority=-1)   # high priority: its blocks go first
+        return self._alpha_obj.cuda_stream
+
     def _program_fused(self, db, do_temp, do_alpha):
         """The same update as `program` in update_fused_async with ~half the launches: one row-assembly
         kernel, the alpha-step and critic-step critic forwards in ONE launch, loss + scalar tails fused."""
@@ -365,10 +370,42 @@ class CQLImpl(DDPGBaseImpl):
             q_tpn = self.ws("soft_tpn", B)
             L.sac_soft_backup(q_t.data_ptr(), B, E, lpm[0].data_ptr(), lt.ptr("p"), q_tpn.data_ptr(), B, side)
         # ---- main branch: critic-step rows [0,R) (activations saved) and alpha-step rows [R,2R) (forward only)
-        ctx = q_net.ctx("is2", G * R, E, True)
-        q = self.ws("is2_q", E, G * R)
-        q_forward("params", 0, G * R, ctx, q, st, save_rows=R)
-        if do_alpha and not dp:
+        alpha_branch = do_alpha and (not dp or px is not None) and os.environ.get("D3B_ALPHA_BRANCH", "1") != "0"
+        if alpha_branch:
+            # The alpha-step rows get their own forward launch on a high-priority branch, followed by the alpha loss
+            # step: its blocks are placed first, so log_alpha is already updated when the critic-step rows (main
+            # stream, second wave of the same 2 x 124 units) finish — the alpha loss leaves the critical path.
+            side_a = self._alpha_stream()
+            L.stream_fork(st, side_a)
+            q_al = self.ws("is_al_q", E, R)
+            q_forward("params", R, R, q_net.ctx("is_al", R, E, False), q_al, side_a)
+            if not dp:
+                L.cql_loss_step(q_al.data_ptr(), R, None, 0, 0, None, None, None, None, self._gamma,
+                                lp[2].data_ptr(), lp[3].data_ptr(), N, A, la.buf.data_ptr(), self._conservative_weight,
+                                self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done[0].data_ptr(), B, E, inv_b,
+                                1, self.counter_ptr(C_ALPHA), self._alpha_learning_rate,
+                                self.metric_ptr(M_ALPHA_LOSS), self.metric_ptr(M_ALPHA), side_a)
+            else:
+                # sharded: partial sums, then exchange + temperature step + alpha step in one launch — the rendezvous
+                # of the scalar steps runs on this branch too (its flags / exchange slots are its own channel)
+                L.critic_loss(q_al.data_ptr(), R, None, 0, 0, None, None, None, None, self._gamma, lp[2].data_ptr(),
+                              lp[3].data_ptr(), N, A, la.ptr("p"), self._conservative_weight, None, 0,
+                              self.sums_ptr(S_ALPHA), None, B, E, inv_b, 0, side_a)
+                L.dp_scalar_steps(self.sums_ptr(S_ALPHA), px.xchg_ptrs, px.flags_ptrs, px.world, px.rank, 1,
+                                  self.counter_ptr(C_DRAW), lt.buf.data_ptr() if temp_merged else None,
+                                  self.counter_ptr(C_TEMP), self._temp_learning_rate, self.metric_ptr(M_TEMP_LOSS),
+                                  self.metric_ptr(M_TEMP), la.buf.data_ptr(), self.counter_ptr(C_ALPHA),
+                                  self._alpha_learning_rate, inv_b / E, self._conservative_weight,
+                                  self._alpha_threshold, self.metric_ptr(M_ALPHA_LOSS), self.metric_ptr(M_ALPHA), side_a)
+            GR = R
+        else:
+            GR = G * R
+        ctx = q_net.ctx("is2", GR, E, True)
+        q = self.ws("is2_q", E, GR)
+        q_forward("params", 0, GR, ctx, q, st, save_rows=R)
+        if alpha_branch:
+            L.stream_join(st, side_a)
+        elif do_alpha and not dp:
             L.cql_loss_step(q.data_ptr() + 4 * R, G * R, None, 0, 0, None, None, None, None, self._gamma,
                             lp[2].data_ptr(), lp[3].data_ptr(), N, A, la.buf.data_ptr(), self._conservative_weight,
                             self._alpha_threshold, None, 0, self.sums_ptr(S_ALPHA), done[0].data_ptr(), B, E, inv_b, 1,
@@ -397,14 +434,14 @@ class CQLImpl(DDPGBaseImpl):
         L.stream_join(st, side)
         dq = self.ws("is2_dq", E, R)
         if not dp:
-            L.cql_loss_step(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
+            L.cql_loss_step(q.data_ptr(), GR, None if soft else q_t.data_ptr(), B, E,
                             q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
                             self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.buf.data_ptr(),
                             self._conservative_weight, self._alpha_threshold, dq.data_ptr(), R,
                             self.sums_ptr(S_CRITIC), done[1].data_ptr(), B, E, inv_b, 0, None, 0.0,
                             self.metric_ptr(M_CRITIC), None, st)
         else:
-            L.critic_loss(q.data_ptr(), G * R, None if soft else q_t.data_ptr(), B, E,
+            L.critic_loss(q.data_ptr(), GR, None if soft else q_t.data_ptr(), B, E,
                           q_tpn.data_ptr() if soft else None, db.ptr("rew"), db.ptr("term"), db.ptr("nsteps"),
                           self._gamma, lp[0].data_ptr(), lp[1].data_ptr(), N, A, la.ptr("p"), self._conservative_weight,
                           dq.data_ptr(), R, self.sums_ptr(S_CRITIC), None, B, E, inv_b, 1, st)
