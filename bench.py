@@ -652,7 +652,8 @@ def run_ours(args, w):
             pass
         roof = {"bound": "tensor",
                 "kernel": (f"{dom['name']} (largest launch: fused critic trunk+head, tcgen05.mma + TMA + TMEM, "
-                           "all members and all importance-sampling rows of the alpha and critic steps)")
+                           "all members, the 7 936 importance-sampling rows of the critic step; the alpha step's rows are an identical "
+                           "launch on a concurrent graph branch)")
                 if args.precision == "bf16" and dom else "tc32_gemm_kernel (3xTF32 tcgen05)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst: kernel timed alone)" if peaks
