@@ -1,14 +1,16 @@
 // CQL/SAC update, fused "glue" kernels: at batch 256 the update is launch-latency bound, so everything that
 // sits between the tensor-core launches is collapsed into a handful of kernels:
 //   begin_step      : Adam/noise counters += mask, loss partial sums zeroed            (was tick + memset)
+//   update_prologue : begin_step + the update's Philox noise + bf16 policy-input rows in one launch
 //   cql_rows        : every row the critics see in one update — [data | pi(s_t) | pi(s_t+1) | random] for the
 //                     critic step and for the alpha step, the target row tanh(mu(s')) (or a sampled one for
-//                     soft_q_backup) and the actor row — written as bf16 straight into the GEMM operand, with
+//                     soft_q_backup) and the actor row — written as bf16 (fp32 in fp32 mode) straight into the GEMM operand, with
 //                     all tanh-Gaussian log-probs (cql_impl.py:143-204, policies.py:167-249,
 //                     distributions.py:91-143).                                       (was 15 launches)
 //   sac_temp_step   : update_temp loss + d/dlog_temp + Adam (sac_impl.py:123-146)      (was 2)
 //   cql_loss_step   : IS-logsumexp conservative term + TD term + softmax gradient seed, then — by the last block
-//                     to finish — the scalar tail: critic metric, or alpha loss + d/dlog_alpha + Adam
+//                     to finish, which first adds the per-block partial sums in a fixed order (bit-reproducible) —
+//                     the scalar tail: critic metric, or alpha loss + d/dlog_alpha + Adam
 //                     (cql_impl.py:110-141,196-223)                                    (was 2-3)
 //   sac_actor_step  : actor loss + arg-min routing of dQ + metric                      (was 2)
 #include <cuda_bf16.h>

@@ -1,7 +1,7 @@
 // K2/K3 (fp32 mode, tensor-core engine): batched-ensemble dense layers at fp32-grade accuracy on the
 // 5th-gen tensor cores by error-compensated TF32 ("3xTF32"):
 //
-//   x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi)        (22 significant bits between them)
+//   x = hi + lo,  hi = rna_tf32(x),  lo = x - hi (exact; the tensor core reads its leading 11 bits)   (22 significant bits)
 //   C[e][m][n] (+)= sum_r A(m,r) B(n,r)  ~=  sum_r  A_lo B_hi + A_hi B_lo + A_hi B_hi       (fp32 accumulate in TMEM)
 //
 // The dropped lo*lo term and the rounding of lo are ~2^-22 relative per product — the same order as the rounding
@@ -15,11 +15,13 @@
 // shared memory, overlap one tile's epilogue and load latency with the other's MMAs.)
 //
 // Operands stay plain row-major fp32 in HBM (the same buffers the SIMT kernels of gemm_f32.cu read, any leading
-// dimension / alignment): 256 producer threads load the tile with coalesced 16-byte (or guarded scalar) loads one
-// K block ahead, split every value in registers and write hi and lo into two SWIZZLE_64B
+// dimension / alignment): 256 producer threads in G groups (group g owns every G-th K block) load the tile with
+// coalesced 16-byte (or guarded scalar) loads, split every value in registers and write hi and lo into two SWIZZLE_64B
 // (K-major) / SWIZZLE_128B_BASE32B (MN-major, the only form 32-bit MN-major operands have) UMMA operand buffers;
-// one elected thread issues three tcgen05.mma.kind::tf32 (M128 x BN x K8) per 8-column step; the producers then
-// turn into the epilogue (tcgen05.ld -> bias / ReLU -> smem -> coalesced store or RED.ADD with the ReLU mask).
+// one elected thread issues two tcgen05.mma.kind::tf32 per 8-column step (A_hi x [B_hi ; B_lo] at width 2 BN, then
+// A_lo x B_hi); the producers then turn into the epilogue (tcgen05.ld -> bias / ReLU -> smem -> coalesced store or
+// RED.ADD with the ReLU mask).  Launches far below one wave split each tile's reduction over a thread-block cluster
+// and reduce the partial tiles through distributed shared memory (see `gemm`).
 // All three layer GEMMs are this one kernel:
 //   forward : A = X   [rows][in]  (K-major)   B = W  [out][in]   (K-major)
 //   dgrad   : A = dY  [rows][out] (K-major)   B = W  [out][in]   (MN-major: the reduction index is the row)
