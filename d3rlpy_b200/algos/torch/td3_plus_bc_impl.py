@@ -155,8 +155,21 @@ class TD3PlusBCImpl(DDPGBaseImpl):
         esz = 4 if f32 else 2
         inv_b = 1.0 / B
         mask = (1 << C_DRAW) | (1 << C_CRITIC) | ((1 << C_ACTOR) if actor_step else 0)
-        L.begin_step(self._counters.data_ptr(), self.N_COUNTERS, mask, self._slots.data_ptr(), 64, st)
-        self.fill_noise(B)
+        # ONE prologue launch: counters, slot zeroing, the update's noise, bf16 operand rows of [obs; next_obs] (the
+        # inputs of pi(s) and pi'(s'))
+        _, n_norm, n_uni, _ = self._noise_plan(B)
+        draw = not self._noise_injected and n_norm + n_uni > 0
+        assert db.off["next_obs"] == db.off["obs"] + B * O, "obs/next_obs must be contiguous"
+        ldo = (O + 7) // 8 * 8
+        xb = None if f32 else self.ws("pi_xb", 2 * B, ldo, dtype=torch.bfloat16)
+        L.update_prologue(self._counters.data_ptr(), self.N_COUNTERS, mask, C_DRAW, self._slots.data_ptr(), 64,
+                          self._noise_arena(B).data_ptr() if draw else None, n_norm if draw else 0, n_uni if draw else 0,
+                          (self._seed + 0x9E3779B97F4A7C15 * self.rank) & 0xFFFFFFFFFFFFFFFF,
+                          db.ptr("obs") if xb is not None else None, O, 2 * B, O,
+                          xb.data_ptr() if xb is not None else None, ldo, self.ws("pro_done", 4, dtype=torch.int32).data_ptr(),
+                          st)
+        xb_obs = None if xb is None else (xb.data_ptr(), ldo)
+        xb_next = None if xb is None else (xb.data_ptr() + 2 * B * ldo, ldo)
         X = self.ws("xf_rows", 3 * B, ld, dtype=torch.float32 if f32 else torch.bfloat16)   # [critic | target | actor] rows
         concat = L.concat_rows if f32 else L.concat_rows_bf16
 
@@ -184,12 +197,13 @@ class TD3PlusBCImpl(DDPGBaseImpl):
             L.stream_fork(st, side2)
             acts_p = pi.ctx("pi", B, 1, True)
             a = self.ws("pi_a", 1, B, A)
-            pi.forward("params", db.ptr("obs"), O, B, acts_p, a, side2, head_tanh=True)
+            pi.forward("params", db.ptr("obs"), O, B, acts_p, a, side2, head_tanh=True, x_bf16=xb_obs)
             xa = X.data_ptr() + esz * 2 * B * ld
             concat(db.ptr("obs"), O, a.data_ptr(), A, None, 0.0, 0.0, 0.0, xa, ld, B, 1, O, A, side2)
         # ---- main: target policy -> smoothed action -> target critics
         a_next = self.ws("tp_a", 1, B, A)
-        pi.forward("target", db.ptr("next_obs"), O, B, pi.ctx("tp", B, 1, False), a_next, st, head_tanh=True)
+        pi.forward("target", db.ptr("next_obs"), O, B, pi.ctx("tp", B, 1, False), a_next, st, head_tanh=True,
+                   x_bf16=xb_next)
         xt = X.data_ptr() + esz * B * ld
         concat(db.ptr("next_obs"), O, a_next.data_ptr(), A, self.noise_view("target", B).data_ptr(),
                self._target_smoothing_sigma, self._target_smoothing_clip, 0.0, xt, ld, B, 1, O, A, st)
