@@ -232,3 +232,27 @@ def test_exported_greedy_policies_match_oracle(tmp_path):
     assert out.shape == (n, A) and float(out.abs().max()) <= 1.0
     with pytest.raises(ValueError):
         save_policy(GreedyPolicy("normal", policy=ou.CQL(O, A, hidden=[32, 32], seed=1).pi), (O,), str(tmp_path / "p.bin"))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU reference arm: the oracle port timed on the host cores, no GPU needed):
+    ONE JSON line with the arm's keys — same metric / unit / config as our arm, `impl`, `cpu_baseline` describing the
+    run and an `e2e` object without copies."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "CQL gradient updates/sec at batch 256" and d["unit"] == "updates/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["config"]["workload"].startswith("CQL halfcheetah-shaped")
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
