@@ -48,6 +48,8 @@ WORKLOADS = {
                desc="CQL ant-shaped (obs 111, act 8), batch 8192, n_action_samples 10, 10 critics, 3x256 MLP"),
 }
 METRIC = "CQL gradient updates/sec at batch 256"
+# keys of `config`, identical on both arms (the driver compares the two lines' configs)
+CONFIG_KEYS = ("workload", "per_gpu_batch", "precision", "global_batch", "units", "parallelism", "l2", "timing")
 CQL_NOISE_KINDS = {"temp": "B*", "alpha_t": "NB*", "alpha_tp1": "NB*", "alpha_rand": "BN*", "soft": "B*",
                    "critic_t": "NB*", "critic_tp1": "NB*", "critic_rand": "BN*", "actor": "B*", "target": "B*"}
 
@@ -136,7 +138,8 @@ def build_oracle(w, seed=0):
     return ou.TD3PlusBC(w["obs"], w["act"], hidden=w["hidden"], n_critics=w["critics"], seed=seed)
 
 
-def time_oracle(w, batches, threads, steps, warmup, budget_s=None):
+def time_oracle(w, batches, threads, steps, warmup, budget_s=None, warm_budget_s=30.0):
+    """(updates/s, timed updates done, seconds, warm-up updates done); both loops stop early at their time budget."""
     import torch
 
     from oracle import update as ou
@@ -144,8 +147,13 @@ def time_oracle(w, batches, threads, steps, warmup, budget_s=None):
     torch.set_num_threads(threads)
     orc = build_oracle(w)
     noise = ou.Noise(seed=0)
+    t0 = time.perf_counter()
+    warmed = 0
     for i in range(warmup):
         orc.update(ou.Batch(batches[i % len(batches)]), noise)
+        warmed += 1
+        if time.perf_counter() - t0 > warm_budget_s:
+            break
     t0 = time.perf_counter()
     done = 0
     for i in range(steps):
@@ -154,7 +162,7 @@ def time_oracle(w, batches, threads, steps, warmup, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return done / dt, done, dt
+    return done / dt, done, dt, warmed
 
 
 def host_batches(w, n_batches, obs, act, rew, term):
@@ -183,12 +191,17 @@ def run_reference(args, w):
     # the reference arm gets its best thread count: short probes at {1, cores/2, cores}, full run with the fastest
     probes = {th: time_oracle(w, batches, th, 4, 1, budget_s=15.0)[0] for th in thread_sweep(cores)}
     threads = max(probes, key=probes.get)
-    rate, done, dt = time_oracle(w, batches, threads, args.steps, min(args.warmup, 3), budget_s=150.0)
+    rate, done, dt, warmed = time_oracle(w, batches, threads, args.steps, args.warmup, budget_s=150.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "updates/s", "n_gpus": args.gpus,
-        "steps": done, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 / rate, "higher_is_better": True,
+        "steps": done, "warmup": warmed, "ms_per_step": 1e3 / rate, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "batch": w["batch"]},
+        # the same keys as the GPU arm's `config` (same workload, this arm's own values)
+        "config": {"workload": w["desc"], "per_gpu_batch": w["batch"],
+                   "precision": "fp32 (plain PyTorch CPU kernels of the oracle port)", "global_batch": w["batch"],
+                   "units": "updates of 256-transition minibatches per second",
+                   "parallelism": f"host CPU, {threads} torch threads (rank 0 only)", "l2": "n/a (CPU)",
+                   "timing": "time.perf_counter around the timed updates"},
         "cpu_baseline": {"value": rate, "unit": "updates/s", "cores": threads, "host_cores": cores, "kind": "port",
                          "sample": f"{done} full updates of the oracle port (plain PyTorch fp32 CPU) in {dt:.1f}s; torch "
                                    f"threads swept over {thread_sweep(cores)} of {cores} host cores "
@@ -196,6 +209,7 @@ def run_reference(args, w):
         "e2e": {"value": rate, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "torch_threads": torch.get_num_threads(),
     }
+    assert tuple(line["config"]) == CONFIG_KEYS
     print(json.dumps(line), flush=True)
 
 
@@ -674,7 +688,7 @@ def run_ours(args, w):
         cores = os.cpu_count() or 1
         best, swept = None, {}
         for th in ([] if strong else thread_sweep(cores)):
-            rate, done, dts = time_oracle(w, hb, th, 100000, 1, budget_s=6.0)
+            rate, done, dts, _ = time_oracle(w, hb, th, 100000, 1, budget_s=6.0)
             swept[th] = round(rate, 2)
             if best is None or rate > best[0]:
                 best = (rate, th, done, dts)
@@ -709,13 +723,13 @@ def run_ours(args, w):
                        "parallelism": plane,
                        "l2": ("flushed (256 MiB write) between timed steps" + (", barrier after the flush" if world > 1 else ""))
                        if not args.no_flush else "not flushed",
-                       "timing": "CUDA events per step on the launching stream, max over ranks",
-                       "step_ms_p10_p50_p90": head["step_ms_p10_p50_p90"],
-                       "variant_alpha_lr0": variant},
+                       "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "step_ms_p10_p50_p90": head["step_ms_p10_p50_p90"], "variant_alpha_lr0": variant,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "graph_nodes_per_update": graph_nodes,
             "fp32_parity_mode": fp32_mode, "extra": extra, "dp_check": check,
             "roofline": roof, "hbm": hbm, "cpu_baseline": cpu_baseline,
         }
+        assert tuple(line["config"]) == CONFIG_KEYS
         print(json.dumps(line), flush=True)
         trace("line printed")
     if world > 1:

@@ -43,9 +43,27 @@ class DeviceBatch:
         if pixel_shape:
             n = batch * int(np.prod(pixel_shape))
             self.pix_dev = torch.zeros(2 * n, dtype=torch.uint8, device=device)
-            self.pix_host = torch.zeros(2 * n, dtype=torch.uint8).pin_memory()
+            self.pix_host = torch.zeros(2 * n, dtype=torch.uint8)
+            if device.type == "cuda":
+                self.pix_host = self.pix_host.pin_memory()
             self.pix_host_np = self.pix_host.numpy()
             self.npix = n
+        # shaped views of the staging buffer, one per minibatch property: `stage_host` is six np.copyto calls
+        h, B = self.host_np, batch
+        shapes = {"act": (B,) if discrete else (B, act_dim), "rew": (B, 1), "term": (B, 1), "nsteps": (B, 1)}
+        if pixel_shape:
+            self._stage = [("observations", self.pix_host_np[:n].reshape(B, *self.pixel_shape)),
+                           ("next_observations", self.pix_host_np[n:].reshape(B, *self.pixel_shape))]
+        else:
+            shapes.update(obs=(B, obs_dim), next_obs=(B, obs_dim))
+            self._stage = [("observations", self._host_view(h, "obs", shapes)),
+                           ("next_observations", self._host_view(h, "next_obs", shapes))]
+        self._stage += [("actions", self._host_view(h, "act", shapes)), ("rewards", self._host_view(h, "rew", shapes)),
+                        ("terminals", self._host_view(h, "term", shapes)), ("n_steps", self._host_view(h, "nsteps", shapes))]
+
+    def _host_view(self, h, name, shapes):
+        shape = shapes[name]
+        return h[self.off[name]:self.off[name] + int(np.prod(shape))].reshape(shape)
 
     def ptr(self, name: str) -> int:
         if self.pixel_shape and name in ("obs", "next_obs"):
@@ -69,19 +87,11 @@ class DeviceBatch:
     def stage_host(self, batch) -> None:
         """numpy TransitionMiniBatch-like -> pinned staging (float32 casts as _convert_to_torch,
         d3rlpy/torch_utility.py:146-149; uint8 frames stay uint8 on the wire)."""
-        h, off, B = self.host_np, self.off, self.B
-        if self.pixel_shape:
-            self.pix_host_np[:self.npix] = np.asarray(batch.observations).reshape(-1)
-            self.pix_host_np[self.npix:] = np.asarray(batch.next_observations).reshape(-1)
-        else:
-            h[off["obs"]:off["obs"] + B * self.O] = np.asarray(batch.observations, dtype=np.float32).reshape(-1)
-            h[off["next_obs"]:off["next_obs"] + B * self.O] = np.asarray(batch.next_observations,
-                                                                         dtype=np.float32).reshape(-1)
-        na = B * (1 if self.discrete else self.A)
-        h[off["act"]:off["act"] + na] = np.asarray(batch.actions, dtype=np.float32).reshape(-1)
-        h[off["rew"]:off["rew"] + B] = np.asarray(batch.rewards, dtype=np.float32).reshape(-1)
-        h[off["term"]:off["term"] + B] = np.asarray(batch.terminals, dtype=np.float32).reshape(-1)
-        h[off["nsteps"]:off["nsteps"] + B] = np.asarray(batch.n_steps, dtype=np.float32).reshape(-1)
+        for name, view in self._stage:
+            src = getattr(batch, name)
+            if getattr(src, "shape", None) != view.shape:   # (B,) scalars, lists, flattened frames
+                src = np.asarray(src).reshape(view.shape)
+            np.copyto(view, src, casting="unsafe")
 
 
 class ImplBase:
@@ -106,6 +116,7 @@ class ImplBase:
         self._counters = torch.zeros(self.N_COUNTERS, dtype=torch.int32, device=self._device)
         self._slots = torch.zeros(64, dtype=torch.float32, device=self._device)  # [0:32) metrics, [32:64) sums
         self._slots_host = torch.zeros(64, dtype=torch.float32).pin_memory()
+        self._slots_host_np = self._slots_host.numpy()   # the same pinned words, as numpy
         self._graphs: Dict[tuple, int] = {}
         self._graph_nodes: Dict[tuple, int] = {}
         self._batch: Optional[DeviceBatch] = None          # the active minibatch buffer
@@ -178,12 +189,12 @@ class ImplBase:
         if not getattr(self, "_metrics_on_host", False):
             return self.read_slots()  # device-resident batch: the graph has no read-back node
         self.sync()
-        return self._slots_host.numpy()
+        return self._slots_host_np
 
     def read_slots(self) -> np.ndarray:
         self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
         self.sync()
-        return self._slots_host.numpy()
+        return self._slots_host_np
 
     # ------------------------------------------------------------------ checkpoints
     def _checkpoint_views(self):

@@ -199,17 +199,25 @@ __global__ void __launch_bounds__(256) cql_rows_kernel(RowsParams p) {
   }
 }
 
-// exact restatement of torch.optim.Adam's single-tensor step for a scalar
-__device__ __forceinline__ float scalar_adam_update(float* p, float G, float* m, float* v, int t, double lr, double b1,
-                                                    double b2, double eps) {
-  double bc1 = 1.0 - pow(b1, (double)t), bc2 = 1.0 - pow(b2, (double)t);
+// exact restatement of torch.optim.Adam's single-tensor step for a scalar.  The two bias
+// corrections (double pow: a few hundred dependent FP64 instructions each) depend only on the step counter, so the
+// callers evaluate them on two otherwise idle warps (`scalar_adam_bias`, threads 32 and 64) while the block reduction
+// that produces the gradient is still running, instead of in front of the parameter write.
+__device__ __forceinline__ void scalar_adam_bias(float* sc /*shared [2]*/, const int* step, double lr, double b1,
+                                                 double b2) {
+  if (threadIdx.x == 32) sc[0] = (float)(-(lr / (1.0 - pow(b1, (double)*step))));
+  else if (threadIdx.x == 64) sc[1] = (float)sqrt(1.0 - pow(b2, (double)*step));
+}
+
+__device__ __forceinline__ float scalar_adam_update(float* p, float G, float* m, float* v, float neg_step_size,
+                                                    float bc2_sqrt, double b1, double b2, double eps) {
   float w1 = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2);
   float M = *m, V = *v;
   M = __fmaf_rn(w1, __fsub_rn(G, M), M);
   V = __fmul_rn(V, fb2);
   V = __fadd_rn(V, __fmul_rn(__fmul_rn(w2, G), G));
-  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V), (float)sqrt(bc2)), (float)eps);
-  float P = __fadd_rn(*p, __fdiv_rn(__fmul_rn((float)(-(lr / bc1)), M), denom));
+  float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(V), bc2_sqrt), (float)eps);
+  float P = __fadd_rn(*p, __fdiv_rn(__fmul_rn(neg_step_size, M), denom));
   *p = P;
   *m = M;
   *v = V;
@@ -222,13 +230,15 @@ __global__ void __launch_bounds__(1024) sac_temp_step_kernel(const float* __rest
                                                              float* metric_loss, float* metric_exp) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float adam_sc[2];
   float s = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += __ldg(logp + b) - (float)A;
-  s = block_sum(s);
+  scalar_adam_bias(adam_sc, step, lr, 0.9, 0.999);
+  s = block_sum(s);   // its barriers order adam_sc before thread 0's read
   if (threadIdx.x == 0) {
     float l = -expf(scalar[0]) * s * inv_b;
     *metric_loss = l;
-    float P = scalar_adam_update(scalar + 0, l, scalar + 8, scalar + 12, *step, lr, 0.9, 0.999, 1e-8);
+    float P = scalar_adam_update(scalar + 0, l, scalar + 8, scalar + 12, adam_sc[0], adam_sc[1], 0.9, 0.999, 1e-8);
     scalar[4] = 0.f;
     *metric_exp = expf(P);
   }
@@ -371,10 +381,12 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
   if (!is_last) return;
   // ---- the last block to finish adds the per-block partial sums in a fixed order ...
   __threadfence();
+  __shared__ float adam_sc[2];
+  if (p.mode == 1 && N > 0) scalar_adam_bias(adam_sc, p.step_alpha, p.lr_alpha, 0.9, 0.999);
   const volatile float* part = reinterpret_cast<const volatile float*>(p.done + 4);
   float s3[3];
 #pragma unroll
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 3; ++k) {   // block_sum's barriers order adam_sc before thread 0's read below
     float acc = 0.f;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += part[k * gridDim.x + i];
     s3[k] = block_sum(acc);
@@ -399,8 +411,8 @@ __global__ void __launch_bounds__(256) cql_loss_step_kernel(LossParams p) {
     *p.metric = -cons;
     float inside = (ea >= 0.f && ea <= 1e6f) ? 1.f : 0.f;
     float G = -inside * ea * (scaled - p.threshold);
-    float P = scalar_adam_update(p.scalar_alpha + 0, G, p.scalar_alpha + 8, p.scalar_alpha + 12, *p.step_alpha,
-                                 p.lr_alpha, 0.9, 0.999, 1e-8);
+    float P = scalar_adam_update(p.scalar_alpha + 0, G, p.scalar_alpha + 8, p.scalar_alpha + 12, adam_sc[0],
+                                 adam_sc[1], 0.9, 0.999, 1e-8);
     p.scalar_alpha[4] = 0.f;
     *p.metric_exp = expf(P);
   }

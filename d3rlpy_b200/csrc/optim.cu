@@ -14,30 +14,24 @@
 
 namespace d3b {
 
-struct AdamScalars {
-  float one_minus_b1, b2, one_minus_b2, eps, neg_step_size, inv_bc2_sqrt_den;  // den: divide by bc2_sqrt
-};
-
-__device__ __forceinline__ void adam_scalars(const int* step, double lr, double b1, double b2, double eps,
-                                             float& w1, float& fb2, float& w2, float& feps, float& neg_ss,
-                                             float& bc2_sqrt) {
-  int t = *step;
-  double bc1 = 1.0 - pow(b1, (double)t);
-  double bc2 = 1.0 - pow(b2, (double)t);
-  w1 = (float)(1.0 - b1);
-  fb2 = (float)b2;
-  w2 = (float)(1.0 - b2);
-  feps = (float)eps;
-  neg_ss = (float)(-(lr / bc1));
-  bc2_sqrt = (float)sqrt(bc2);
-}
-
-// the bias corrections need double pow/sqrt: evaluate them once per block, not once per thread
+// the bias corrections need double pow/sqrt: evaluate them once per block, not once per thread -- the two pow() chains
+// (a few hundred dependent FP64 instructions each) on two warps side by side; the callers issue their first operand
+// loads BEFORE this call, so the chains run under the memory latency instead of in front of it.  blockDim.x >= 64.
 __device__ __forceinline__ void adam_scalars_block(const int* step, double lr, double b1, double b2, double eps,
                                                    float& w1, float& fb2, float& w2, float& feps, float& neg_ss,
                                                    float& bc2_sqrt) {
   __shared__ float sc[6];
-  if (threadIdx.x == 0) adam_scalars(step, lr, b1, b2, eps, sc[0], sc[1], sc[2], sc[3], sc[4], sc[5]);
+  if (threadIdx.x == 0) {
+    double bc1 = 1.0 - pow(b1, (double)*step);
+    sc[0] = (float)(1.0 - b1);
+    sc[3] = (float)eps;
+    sc[4] = (float)(-(lr / bc1));
+  } else if (threadIdx.x == 32) {
+    double bc2 = 1.0 - pow(b2, (double)*step);
+    sc[1] = (float)b2;
+    sc[2] = (float)(1.0 - b2);
+    sc[5] = (float)sqrt(bc2);
+  }
   __syncthreads();
   w1 = sc[0]; fb2 = sc[1]; w2 = sc[2]; feps = sc[3]; neg_ss = sc[4]; bc2_sqrt = sc[5];
 }
@@ -61,14 +55,21 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    float weight_decay) {
   pdl_trigger();
   pdl_wait();
-  float w1, fb2, w2, feps, neg_ss, bc2s;
-  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
-  float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
   long long n4 = n >> 2;
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = tid; i < n4; i += stride) {
-    float4 P = ((float4*)p)[i], G = ((float4*)g)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+  // operands of the first pass in flight while the bias corrections are evaluated
+  long long i = tid;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 P = zero4, G = zero4, M = zero4, V = zero4, T = zero4;
+  if (i < n4) {
+    P = ((float4*)p)[i]; G = ((float4*)g)[i]; M = ((float4*)m)[i]; V = ((float4*)v)[i];
+    if (targ) T = ((float4*)targ)[i];
+  }
+  float w1, fb2, w2, feps, neg_ss, bc2s;
+  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  float one_m_tau = (float)(1.0 - (double)tau);  // python: (1 - tau) in double, then cast by mul_
+  while (i < n4) {
     if (weight_decay != 0.f) {   // torch.optim.Adam: grad = grad.add(param, alpha=weight_decay) (L2, not decoupled)
       G.x = __fmaf_rn(weight_decay, P.x, G.x); G.y = __fmaf_rn(weight_decay, P.y, G.y);
       G.z = __fmaf_rn(weight_decay, P.z, G.z); G.w = __fmaf_rn(weight_decay, P.w, G.w);
@@ -80,14 +81,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     ((float4*)p)[i] = P;
     ((float4*)m)[i] = M;
     ((float4*)v)[i] = V;
-    if (zero_grad) ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zero_grad) ((float4*)g)[i] = zero4;
     if (targ) {
-      float4 T = ((float4*)targ)[i];
       T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(tau, P.x));
       T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(tau, P.y));
       T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(tau, P.z));
       T.w = __fadd_rn(__fmul_rn(T.w, one_m_tau), __fmul_rn(tau, P.w));
       ((float4*)targ)[i] = T;
+    }
+    i += stride;
+    if (i < n4) {
+      P = ((float4*)p)[i]; G = ((float4*)g)[i]; M = ((float4*)m)[i]; V = ((float4*)v)[i];
+      if (targ) T = ((float4*)targ)[i];
     }
   }
   for (long long i = (n4 << 2) + tid; i < n; i += stride) {
@@ -125,14 +130,25 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ p,
                                                           __nv_bfloat16* __restrict__ sh_t, ShadowSegs segs) {
   pdl_trigger();
   pdl_wait();
-  float w1, fb2, w2, feps, neg_ss, bc2s;
-  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
-  float one_m_tau = (float)(1.0 - (double)tau);
   long long n4 = n >> 2;  // arenas are padded to multiples of 4 floats per member
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = tid; i < n4; i += stride) {
-    float4 P = ((float4*)p)[i], G = ((float4*)g)[i], M = ((float4*)m)[i], V = ((float4*)v)[i];
+  // operands of the first pass in flight while the bias corrections are evaluated
+  long long i = tid;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 P = zero4, G = zero4, M = zero4, V = zero4, T0 = zero4;
+  if (i < n4) {
+    P = ((float4*)p)[i]; G = ((float4*)g)[i]; M = ((float4*)m)[i]; V = ((float4*)v)[i];
+    if (targ) T0 = ((float4*)targ)[i];
+  }
+  float w1, fb2, w2, feps, neg_ss, bc2s;
+  adam_scalars_block(step, lr, b1, b2, eps, w1, fb2, w2, feps, neg_ss, bc2s);
+  float one_m_tau = (float)(1.0 - (double)tau);
+  for (; i < n4; i += stride) {
+    if (i != tid) {   // later passes (arenas beyond one grid of float4s)
+      P = ((float4*)p)[i]; G = ((float4*)g)[i]; M = ((float4*)m)[i]; V = ((float4*)v)[i];
+      if (targ) T0 = ((float4*)targ)[i];
+    }
     P.x = adam_one(P.x, G.x, M.x, V.x, w1, fb2, w2, feps, neg_ss, bc2s);
     P.y = adam_one(P.y, G.y, M.y, V.y, w1, fb2, w2, feps, neg_ss, bc2s);
     P.z = adam_one(P.z, G.z, M.z, V.z, w1, fb2, w2, feps, neg_ss, bc2s);
@@ -140,10 +156,10 @@ __global__ void __launch_bounds__(256) adam_shadow_kernel(float* __restrict__ p,
     ((float4*)p)[i] = P;
     ((float4*)m)[i] = M;
     ((float4*)v)[i] = V;
-    ((float4*)g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ((float4*)g)[i] = zero4;
     float4 T = P;
     if (targ) {
-      T = ((float4*)targ)[i];
+      T = T0;
       T.x = __fadd_rn(__fmul_rn(T.x, one_m_tau), __fmul_rn(tau, P.x));
       T.y = __fadd_rn(__fmul_rn(T.y, one_m_tau), __fmul_rn(tau, P.y));
       T.z = __fadd_rn(__fmul_rn(T.z, one_m_tau), __fmul_rn(tau, P.z));

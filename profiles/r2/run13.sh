@@ -12,5 +12,5 @@ print('roof',d['roofline']['achieved'],d['roofline']['frac'],d['roofline']['domi
 for k,v in d['hbm'].items():
     if isinstance(v,dict): print('  hbm',k,round(v['us'],2),'us',round(v['gbs'],1),'GB/s',round(v['frac'],3))
 print('cpu',d['cpu_baseline'])
-print('variant',d['config']['variant_alpha_lr0'])
+print('variant',d['variant_alpha_lr0'])
 PY

@@ -14,5 +14,5 @@ print('c5', d['extra']['c5_strong']['value'], d['extra']['c5_strong']['ms_per_st
 print({k:v for k,v in d['dp_check'].items() if k!='what'})
 lines=[l for l in open(f'gpurun_out/r2_bench_c5_n{N}.json') if l.startswith('{')]
 d=json.loads(lines[-1])
-print('c5 strong value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'], d['config']['step_ms_p10_p50_p90'])
+print('c5 strong value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'], d['step_ms_p10_p50_p90'])
 PY

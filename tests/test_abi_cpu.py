@@ -253,6 +253,13 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "CQL gradient updates/sec at batch 256" and d["unit"] == "updates/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
     assert d["config"]["workload"].startswith("CQL halfcheetah-shaped")
+    sys.path.insert(0, root)
+    try:
+        import bench
+    finally:
+        sys.path.pop(0)
+    assert tuple(d["config"]) == bench.CONFIG_KEYS   # the GPU arm asserts the same key set on its own line
+    assert d["warmup"] == 3 and d["steps"] == 1
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
