@@ -8,6 +8,7 @@ batch ONCE per update, and reads every metric back with ONE pinned D2H copy.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -191,8 +192,25 @@ class ImplBase:
         self.sync()
         return self._slots_host_np
 
+    # Staged copies up to this many bytes run as a kernel over the pinned (device-addressable) host buffer instead of
+    # a copy-engine transfer: in front of / behind a 160 us update the node's start latency is what counts
+    # (csrc/util.cu: copy_mapped).  D3B_ZEROCOPY_MAX=0 restores cudaMemcpyAsync everywhere.
+    zero_copy_max = int(os.environ.get("D3B_ZEROCOPY_MAX", str(256 << 10)))
+
+    def _copy_h2d(self, dst: int, src_pinned: int, nbytes: int) -> None:
+        if nbytes <= self.zero_copy_max:
+            self._lib.copy_mapped(dst, src_pinned, nbytes, self._stream)
+        else:
+            self._lib.copy_h2d(dst, src_pinned, nbytes, self._stream)
+
+    def _copy_d2h(self, dst_pinned: int, src: int, nbytes: int) -> None:
+        if nbytes <= self.zero_copy_max:
+            self._lib.copy_mapped(dst_pinned, src, nbytes, self._stream)
+        else:
+            self._lib.copy_d2h(dst_pinned, src, nbytes, self._stream)
+
     def read_slots(self) -> np.ndarray:
-        self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
+        self._copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64)
         self.sync()
         return self._slots_host_np
 
@@ -314,9 +332,9 @@ class ImplBase:
         return dev
 
     def _upload(self, db: DeviceBatch) -> None:
-        self._lib.copy_h2d(db.dev.data_ptr(), db.host.data_ptr(), 4 * db.nfloat, self._stream)
+        self._copy_h2d(db.dev.data_ptr(), db.host.data_ptr(), 4 * db.nfloat)
         if db.pixel_shape:
-            self._lib.copy_h2d(db.pix_dev.data_ptr(), db.pix_host.data_ptr(), 2 * db.npix, self._stream)
+            self._copy_h2d(db.pix_dev.data_ptr(), db.pix_host.data_ptr(), 2 * db.npix)
         self._apply_scalers(db)
 
     def _apply_scalers(self, db: DeviceBatch):
@@ -451,7 +469,7 @@ class ImplBase:
                 self._upload(pend)
             inner()
             if pend is not None:  # host caller: it will read the metrics right away
-                self._lib.copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64, self._stream)
+                self._copy_d2h(self._slots_host.data_ptr(), self._slots.data_ptr(), 4 * 64)
 
         key = tuple(key) + (pend is not None, id(self._batch))
         self._metrics_on_host = pend is not None

@@ -73,6 +73,57 @@ extern "C" int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, vo
   return D3B_OK;
 }
 
+// Small staged copies as a KERNEL between device memory and pinned host memory (either direction): pinned
+// allocations are device-addressable under unified addressing, and inside the update graph a kernel node chained by
+// programmatic dependent launch starts sooner than a copy-engine node (the minibatch upload in front of the update
+// and the 256-byte metric read-back behind it are latency, not bandwidth).  Large transfers keep cudaMemcpyAsync.
+namespace {
+__global__ void __launch_bounds__(256) copy_mapped_kernel(unsigned char* __restrict__ dst,
+                                                          const unsigned char* __restrict__ src, long long bytes,
+                                                          int vec16) {
+  pdl_trigger();
+  pdl_wait();
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long done = 0;
+  if (vec16) {
+    const long long n16 = bytes >> 4;
+    for (long long i = tid; i < n16; i += stride) ((uint4*)dst)[i] = ((const uint4*)src)[i];
+    done = n16 << 4;
+  }
+  for (long long i = done + tid; i < bytes; i += stride) dst[i] = src[i];
+}
+}  // namespace
+
+extern "C" int d3b_copy_mapped(void* dst, const void* src, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0 && ((dst && src) || bytes == 0), "copy_mapped: bad arguments");
+  if (bytes == 0) return D3B_OK;
+  // a pinned host buffer is addressed through its device alias (the same pointer under unified addressing); pageable
+  // memory is refused here instead of faulting in the kernel
+  void* ends[2] = {dst, const_cast<void*>(src)};
+  for (int k = 0; k < 2; ++k) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, ends[k]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    D3B_REQUIRE(at.type != cudaMemoryTypeUnregistered, "copy_mapped: %s is pageable host memory (pin it)",
+                k == 0 ? "dst" : "src");
+    if (at.type == cudaMemoryTypeHost) {
+      D3B_REQUIRE(at.devicePointer != nullptr, "copy_mapped: pinned %s has no device alias", k == 0 ? "dst" : "src");
+      ends[k] = at.devicePointer;
+    }
+  }
+  dst = ends[0];
+  src = ends[1];
+  const int vec16 = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
+  long long blocks = ceil_div_ll(vec16 ? ceil_div_ll(bytes, 16) : bytes, 256);
+  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+  launch_pdl(copy_mapped_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (unsigned char*)dst,
+             (const unsigned char*)src, (long long)bytes, vec16);
+  return check_launch("copy_mapped");
+}
+
 extern "C" int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
   D3B_REQUIRE(bytes >= 0, "copy_d2d: bytes < 0");
   if (bytes == 0) return D3B_OK;

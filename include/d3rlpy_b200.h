@@ -524,6 +524,11 @@ int d3b_memset_zero(void* ptr, int64_t bytes, void* stream);
 int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream);
 int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream);
 int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+/* The same small copies as a KERNEL (either direction; the host side must be pinned, i.e. device-addressable under
+ * unified addressing): inside the update graph a kernel node starts sooner than a copy-engine node.  Replaces the
+ * `torch.tensor(array, device=...)` upload of _convert_to_torch (d3rlpy/torch_utility.py:146-149) and the
+ * `loss.cpu().detach().numpy()` read-back (e.g. d3rlpy/algos/torch/ddpg_impl.py:152) for small minibatches. */
+int d3b_copy_mapped(void* dst, const void* src, int64_t bytes, void* stream);
 int d3b_stream_sync(void* stream);
 int d3b_spin(int64_t ns, void* stream); /* measurement helper: busy-wait kernel (keeps the stream ahead of the host) */
 /* fork/join a side stream (graph branches under capture): independent steps of one update run concurrently */

@@ -508,3 +508,31 @@ def test_update_prologue_equals_begin_step_noise_fill_to_bf16():
                       done.data_ptr(), st)
     torch.cuda.synchronize()
     assert ca.tolist() == [1, 1, 0, 0, 0, 0]
+
+
+@pytest.mark.parametrize("nbytes", [1, 15, 16, 256, 4 * 11008, 44032 + 3, 1 << 20])
+def test_copy_mapped_round_trip_is_bit_exact(nbytes):
+    """csrc/util.cu copy_mapped: pinned host -> device -> pinned host through the kernel (both directions, aligned and
+    unaligned ends), bit-exact; a pageable host pointer is refused with an error instead of faulting."""
+    from d3rlpy_b200._lib import D3BError, lib
+
+    L, dev, st = lib(), _dev(), _st()
+    rs = np.random.RandomState(nbytes % 1000)
+    src = torch.from_numpy(rs.randint(0, 256, nbytes + 32).astype(np.uint8)).pin_memory()
+    back = torch.zeros(nbytes + 32, dtype=torch.uint8).pin_memory()
+    d = torch.zeros(nbytes + 32, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    for off in (0, 1):   # 16-byte aligned and misaligned
+        d.zero_()
+        back.zero_()
+        torch.cuda.synchronize()
+        L.copy_mapped(d.data_ptr() + off, src.data_ptr() + off, nbytes, st)
+        L.copy_mapped(back.data_ptr() + off, d.data_ptr() + off, nbytes, st)
+        torch.cuda.synchronize()
+        assert torch.equal(d.cpu()[off:off + nbytes], src[off:off + nbytes])
+        assert torch.equal(back[off:off + nbytes], src[off:off + nbytes])
+        assert int(back[off + nbytes:].sum()) == 0 and int(back[:off].sum()) == 0   # nothing written past the ends
+    pageable = torch.zeros(64, dtype=torch.uint8)
+    with pytest.raises(D3BError):
+        L.copy_mapped(d.data_ptr(), pageable.data_ptr(), 64, st)
+    torch.cuda.synchronize()
