@@ -51,28 +51,6 @@ extern "C" int d3b_device_info(int device, int* sm_count, int* cc_major, int* cc
   return D3B_OK;
 }
 
-extern "C" int d3b_memset_zero(void* ptr, int64_t bytes, void* stream) {
-  D3B_REQUIRE(bytes >= 0 && (ptr || bytes == 0), "memset_zero: bad arguments");
-  if (bytes == 0) return D3B_OK;
-  D3B_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
-  count_launch();
-  return D3B_OK;
-}
-
-extern "C" int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream) {
-  D3B_REQUIRE(bytes >= 0, "copy_h2d: bytes < 0");
-  if (bytes == 0) return D3B_OK;
-  D3B_CUDA(cudaMemcpyAsync(dst, src_pinned, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  return D3B_OK;
-}
-
-extern "C" int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream) {
-  D3B_REQUIRE(bytes >= 0, "copy_d2h: bytes < 0");
-  if (bytes == 0) return D3B_OK;
-  D3B_CUDA(cudaMemcpyAsync(dst_pinned, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-  return D3B_OK;
-}
-
 // Small staged copies as a KERNEL between device memory and pinned host memory (either direction): pinned
 // allocations are device-addressable under unified addressing, and inside the update graph a kernel node chained by
 // programmatic dependent launch starts sooner than a copy-engine node (the minibatch upload in front of the update
@@ -93,7 +71,53 @@ __global__ void __launch_bounds__(256) copy_mapped_kernel(unsigned char* __restr
   }
   for (long long i = done + tid; i < bytes; i += stride) dst[i] = src[i];
 }
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ dst, long long n_words) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = 0u;
+}
+constexpr long long kSmallCopy = 256 << 10;  // below this a copy / fill is latency: run it as a PDL-chained kernel node
+int copy_by_kernel(void* dst, const void* src, long long bytes, cudaStream_t st, const char* what) {
+  const int vec16 = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
+  long long blocks = ceil_div_ll(vec16 ? ceil_div_ll(bytes, 16) : bytes, 256);
+  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+  launch_pdl(copy_mapped_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (unsigned char*)dst,
+             (const unsigned char*)src, bytes, vec16);
+  return check_launch(what);
+}
 }  // namespace
+
+
+extern "C" int d3b_memset_zero(void* ptr, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0 && (ptr || bytes == 0), "memset_zero: bad arguments");
+  if (bytes == 0) return D3B_OK;
+  if (bytes <= kSmallCopy && (((uintptr_t)ptr | (uintptr_t)bytes) & 3) == 0) {
+    const long long words = bytes >> 2;
+    long long blocks = ceil_div_ll(words, 256);
+    if (blocks > kNumSM * 4) blocks = kNumSM * 4;
+    launch_pdl(zero_words_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (uint32_t*)ptr, words);
+    return check_launch("memset_zero");
+  }
+  D3B_CUDA(cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream));
+  count_launch();
+  return D3B_OK;
+}
+
+extern "C" int d3b_copy_h2d(void* dst, const void* src_pinned, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0, "copy_h2d: bytes < 0");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemcpyAsync(dst, src_pinned, (size_t)bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return D3B_OK;
+}
+
+extern "C" int d3b_copy_d2h(void* dst_pinned, const void* src, int64_t bytes, void* stream) {
+  D3B_REQUIRE(bytes >= 0, "copy_d2h: bytes < 0");
+  if (bytes == 0) return D3B_OK;
+  D3B_CUDA(cudaMemcpyAsync(dst_pinned, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return D3B_OK;
+}
 
 extern "C" int d3b_copy_mapped(void* dst, const void* src, int64_t bytes, void* stream) {
   D3B_REQUIRE(bytes >= 0 && ((dst && src) || bytes == 0), "copy_mapped: bad arguments");
@@ -116,17 +140,13 @@ extern "C" int d3b_copy_mapped(void* dst, const void* src, int64_t bytes, void* 
   }
   dst = ends[0];
   src = ends[1];
-  const int vec16 = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
-  long long blocks = ceil_div_ll(vec16 ? ceil_div_ll(bytes, 16) : bytes, 256);
-  if (blocks > kNumSM * 4) blocks = kNumSM * 4;
-  launch_pdl(copy_mapped_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (unsigned char*)dst,
-             (const unsigned char*)src, (long long)bytes, vec16);
-  return check_launch("copy_mapped");
+  return copy_by_kernel(dst, src, (long long)bytes, (cudaStream_t)stream, "copy_mapped");
 }
 
 extern "C" int d3b_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
   D3B_REQUIRE(bytes >= 0, "copy_d2d: bytes < 0");
   if (bytes == 0) return D3B_OK;
+  if (bytes <= kSmallCopy) return copy_by_kernel(dst, src, (long long)bytes, (cudaStream_t)stream, "copy_d2d");
   D3B_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   count_launch();
   return D3B_OK;
