@@ -55,7 +55,7 @@ extern "C" int d3b_device_info(int device, int* sm_count, int* cc_major, int* cc
 // allocations are device-addressable under unified addressing, and inside the update graph a kernel node chained by
 // programmatic dependent launch starts sooner than a copy-engine node (the minibatch upload in front of the update
 // and the 256-byte metric read-back behind it are latency, not bandwidth).  Large transfers keep cudaMemcpyAsync.
-namespace {
+namespace d3b {
 __global__ void __launch_bounds__(256) copy_mapped_kernel(unsigned char* __restrict__ dst,
                                                           const unsigned char* __restrict__ src, long long bytes,
                                                           int vec16) {
@@ -78,6 +78,9 @@ __global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ 
        i += (long long)gridDim.x * blockDim.x)
     dst[i] = 0u;
 }
+}  // namespace d3b
+
+namespace {
 constexpr long long kSmallCopy = 256 << 10;  // below this a copy / fill is latency: run it as a PDL-chained kernel node
 int copy_by_kernel(void* dst, const void* src, long long bytes, cudaStream_t st, const char* what) {
   const int vec16 = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
