@@ -35,6 +35,14 @@ def test_dp_sharded_oracle_matches_full_batch_gloo_world2():
     assert r.returncode == 0 and "DP_EQUIVALENCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world,port", [(4, 29623), (8, 29633)])
+def test_dp_sharded_oracle_matches_full_batch_gloo_wider_worlds(world, port):
+    """The same sharding (row ranges, per-kind noise slices, 1/W loss scaling) at the world sizes the scaling bench
+    runs: 4 and 8 ranks over gloo."""
+    r = _torchrun("cpu", world, port)
+    assert r.returncode == 0 and "DP_EQUIVALENCE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.gpu
 def test_dp_cuda_update_matches_full_batch_nccl():
     n = torch.cuda.device_count()
